@@ -1,0 +1,34 @@
+"""CPU oracle for the cashocs shape-gradient hot path (TEST INFRASTRUCTURE ONLY).
+
+This package is a numpy/scipy *restatement* of what the reference computes on the
+path SURVEY.md section 8 names (P1 assembly -> CSR, Krylov solves, elasticity Riesz
+projection, mesh quality, a-priori det check, move_mesh, Armijo decisions).
+
+It is the checker, never the product: only ``tests/``, ``__graft_entry__.smoke()`` and
+the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  Nothing
+under ``cashocs_b200/`` imports ``oracle``.
+
+Parity pinning status
+---------------------
+The reference (sblauth/cashocs) cannot be imported in this container: all arithmetic
+lives in un-vendored third-party code (legacy FEniCS 2019.1 -- dolfin / FFC / FIAT / UFL --
+and PETSc through petsc4py; pins: ``.github/conda/openmpi.yml:6``,
+``.github/docker/Dockerfile:6``, ``README.rst:88-89``).  The oracle therefore restates the
+*published* algorithms (P1 Galerkin assembly with dolfin's symmetric per-element
+Dirichlet elimination, PETSc's KSPCG with the preconditioned-norm default convergence
+test) and is pinned against everything the reference's own tests hold for this path:
+
+* mesh-quality known answers ``tests/test_geometry.py:138-269`` (0.4714045207910318,
+  0.3162277660168379, skewness / maximum-angle from 90/45 degree angles) -> pinned, 1e-14;
+* the analytic Poisson shape derivative ``tests/test_shape_optimization.py:229-299``
+  and the Taylor-test rate > 1.9 ``:302-318`` (``cashocs/verification.py:182-280``) -> pinned;
+* state / adjoint / control-gradient definitions ``tests/test_pde_problems.py:87-128`` -> pinned
+  against scipy ``spsolve`` of the textbook systems;
+* move / revert exactness and rejection of a +-1e3 random deformation
+  ``tests/test_shape_optimization.py:157-179`` -> pinned;
+* mesh-import invariants ``tests/test_geometry.py:51-99`` on the reference's gmsh fixtures -> pinned.
+
+Assembled matrix entries, dof numbering, BC-row diagonals and Krylov iteration counts are
+NOT pinned by any reference test (the reference has no golden vectors): for those
+quantities this oracle is "parity unpinned" and says so in DESIGN.md.
+"""

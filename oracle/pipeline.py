@@ -1,0 +1,498 @@
+"""Oracle pipeline: one shape-gradient evaluation, Armijo update, Taylor test, control gradient.
+
+Test infrastructure only (see ``oracle/__init__.py``).
+
+Restates, for the Poisson model problem of the reference's demos/tests
+(``demos/documented/shape_optimization/shape_poisson/demo_shape_poisson.py``,
+``tests/test_shape_optimization.py:97-118``):
+
+* ``StateProblem.solve`` linear branch (``cashocs/_pde_problems/state_problem.py:142-172``),
+* ``AdjointProblem.solve`` (``cashocs/_pde_problems/adjoint_problem.py:124-191``),
+* ``Stiffness.compute`` (``cashocs/_forms/shape_form_handler.py:188-235``),
+* ``ShapeFormHandler.update_scalar_product`` / ``scalar_product`` (``:714-780``),
+* ``ShapeGradientProblem.solve`` (``cashocs/_pde_problems/shape_gradient_problem.py:117-173``),
+* ``_MeshHandler.move_mesh`` (``cashocs/geometry/mesh_handler.py:264-303``),
+* ``ShapeVariableAbstractions.update_optimization_variables``
+  (``cashocs/_optimization/shape_optimization/shape_variable_abstractions.py:91-135``),
+* the Armijo rule (``cashocs/_optimization/line_search/armijo_line_search.py:97-202``,
+  ``line_search.py:152-214,251-279``),
+* ``shape_gradient_test`` (``cashocs/verification.py:182-302``),
+* ``ControlGradientProblem.solve`` (``cashocs/_pde_problems/control_gradient_problem.py:96-125``).
+"""
+
+from __future__ import annotations
+
+import dataclasses
+
+import numpy as np
+
+from oracle import fem
+from oracle import krylov
+from oracle import quality
+
+
+# ----------------------------------------------------------------------------- source term
+def demo_f(x):
+    """f = 2.5 (x + 0.4 - y^2)^2 + x^2 + y^2 - 1 (``demo_shape_poisson.py``, tests ``:116``)."""
+    X, Y = x[..., 0], x[..., 1]
+    return 2.5 * (X + 0.4 - Y**2) ** 2 + X**2 + Y**2 - 1.0
+
+
+def demo_grad_f(x):
+    X, Y = x[..., 0], x[..., 1]
+    g = np.zeros_like(x)
+    t = X + 0.4 - Y**2
+    g[..., 0] = 5.0 * t + 2.0 * X
+    g[..., 1] = -10.0 * Y * t + 2.0 * Y
+    return g
+
+
+DEMO_F_DEGREE = 4
+
+DEFAULT_KSP = {"ksp_type": "preonly", "pc_type": "lu"}
+
+
+@dataclasses.dataclass
+class ShapeConfig:
+    """The ``[ShapeGradient]`` / ``[MeshQuality]`` / ``[LineSearch]`` keys the hot path reads
+    (defaults ``cashocs/io/config.py:593-741``; values here = ``tests/config_sop.ini``)."""
+
+    shape_bdry_def: tuple = (1,)
+    shape_bdry_fix: tuple = ()
+    shape_bdry_fix_x: tuple = ()
+    shape_bdry_fix_y: tuple = ()
+    shape_bdry_fix_z: tuple = ()
+    lambda_lame: float = 1.428571428571429
+    damping_factor: float = 0.2
+    mu_def: float = 0.35714285714285715
+    mu_fix: float = 0.35714285714285715
+    use_sqrt_mu: bool = False
+    volume_change: float = float("inf")
+    angle_change: float = float("inf")
+    tol_lower: float = 0.0
+    tol_upper: float = 1e-15
+    measure: str = "skewness"
+    qtype: str = "min"
+    quantile: float = 0.1
+    test_for_intersections: bool = True
+    beta_armijo: float = 2.0
+    epsilon_armijo: float = 1e-4
+    initial_stepsize: float = 1.0
+    safeguard_stepsize: bool = True
+
+
+class PoissonShapeProblem:
+    """-Laplace u = f, u = 0 on ``bc_markers``; J = int u dx; elasticity Riesz projection."""
+
+    def __init__(
+        self,
+        mesh,
+        f=demo_f,
+        grad_f=demo_grad_f,
+        f_degree=DEMO_F_DEGREE,
+        bc_markers=(1,),
+        config: ShapeConfig | None = None,
+        state_ksp=None,
+        adjoint_ksp=None,
+        gradient_ksp=None,
+        mu_ksp=None,
+    ):
+        self.mesh = mesh
+        self.coords = mesh.coords  # moved in place by move_mesh
+        self.cells = mesh.cells
+        self.d = mesh.dim
+        self.nv = mesh.num_vertices
+        self.f, self.grad_f, self.f_degree = f, grad_f, f_degree
+        self.cfg = config or ShapeConfig()
+        self.state_ksp = state_ksp or DEFAULT_KSP
+        self.adjoint_ksp = adjoint_ksp or DEFAULT_KSP
+        self.gradient_ksp = gradient_ksp or DEFAULT_KSP
+        # the reference hard-codes cg + boomeramg, rtol 1e-16, max_it 100 for mu
+        # (shape_form_handler.py:113-120); the oracle uses its direct solve unless told otherwise
+        self.mu_ksp = mu_ksp or DEFAULT_KSP
+        self.state_bc = mesh.boundary_vertices(bc_markers)
+        self.vcell_dofs = fem.vector_cell_dofs(self.cells, self.d)
+        self.shape_bc_dofs = self._shape_bc_dofs()
+        self.valence = quality.vertex_valence(self.cells, self.nv)
+        self.old_coords = None
+        self.its = {}
+        self.u = np.zeros(self.nv)
+        self.p = np.zeros(self.nv)
+        self.mu = np.ones(self.nv)
+        self.A_elas = None
+        self.current_mesh_quality = quality.compute_mesh_quality(
+            self.coords, self.cells, self.cfg.qtype, self.cfg.measure, self.cfg.quantile
+        )
+        self.update_scalar_product()
+
+    # -- boundary conditions of the deformation space (shape_form_handler.py:551-588)
+    def _shape_bc_dofs(self):
+        d, c = self.d, self.cfg
+        dofs = []
+        fix = self.mesh.boundary_vertices(c.shape_bdry_fix)
+        for k in range(d):
+            dofs.append(d * fix + k)
+        for k, mk in enumerate((c.shape_bdry_fix_x, c.shape_bdry_fix_y, c.shape_bdry_fix_z)[:d]):
+            dofs.append(d * self.mesh.boundary_vertices(mk) + k)
+        return np.unique(np.concatenate(dofs)).astype(np.int64) if dofs else np.zeros(0, np.int64)
+
+    def _geom(self):
+        return fem.cell_geometry(self.coords, self.cells)
+
+    # -- state / adjoint (a3, a4)
+    def solve_state(self):
+        _, vol, G = self._geom()
+        Ke = fem.stiffness_elements(vol, G)
+        be = fem.load_elements_callable(self.coords, self.cells, vol, self.f, self.f_degree + 1)
+        A, b = fem.assemble_system(Ke, be, self.cells, self.nv, self.state_bc, 0.0)
+        self.u, reason, its, _ = krylov.solve(A, b, self.state_ksp)
+        self._check(reason)
+        self.its["state"] = its
+        self.A_state, self.b_state = A, b
+        return self.u
+
+    def solve_adjoint(self):
+        _, vol, G = self._geom()
+        Ke = fem.stiffness_elements(vol, G)
+        be = -fem.load_elements_p1(vol, self.cells, np.ones(self.nv), self.d)  # -dJ/du[v] = -int v
+        A, b = fem.assemble_system(Ke, be, self.cells, self.nv, self.state_bc, 0.0)
+        self.p, reason, its, _ = krylov.solve(A, b, self.adjoint_ksp)
+        self._check(reason)
+        self.its["adjoint"] = its
+        self.b_adjoint = b
+        return self.p
+
+    @staticmethod
+    def _check(reason):
+        if reason < 0:
+            raise RuntimeError(f"PETScKSPError({reason})")  # cashocs/_utils/linalg.py:543-544
+
+    def cost(self):
+        """``IntegralFunctional.evaluate`` (``cashocs/_optimization/cost_functional.py:160-168``)."""
+        _, vol, _ = self._geom()
+        return float(np.sum(vol * self.u[self.cells].mean(axis=1)))
+
+    # -- Lame mu (a5)
+    def compute_mu(self):
+        c = self.cfg
+        if abs(c.mu_def - c.mu_fix) / c.mu_fix > 1e-2:
+            _, vol, G = self._geom()
+            Ke = fem.stiffness_elements(vol, G)
+            fix = self.mesh.boundary_vertices(c.shape_bdry_fix)
+            deff = self.mesh.boundary_vertices(c.shape_bdry_def)
+            g = np.zeros(self.nv)
+            g[fix] = c.mu_fix
+            g[deff] = c.mu_def  # bcs_mu: fix first, def appended -> def applied last wins
+            dofs = np.unique(np.concatenate([fix, deff]))
+            A, b = fem.assemble_system(Ke, np.zeros((self.cells.shape[0], self.d + 1)), self.cells,
+                                       self.nv, dofs, g[dofs])
+            mu, reason, its, _ = krylov.solve(A, b, self.mu_ksp)
+            self._check(reason)
+            self.its["mu"] = its
+            if c.use_sqrt_mu:
+                mu = np.sqrt(np.abs(mu))
+            self.mu = mu
+        else:
+            self.mu = np.full(self.nv, c.mu_fix)
+        return self.mu
+
+    # -- elasticity scalar product (a6, a9)
+    def update_scalar_product(self):
+        self.compute_mu()
+        _, vol, G = self._geom()
+        Ae = fem.elasticity_elements(vol, G, self.mu, self.cells, self.cfg.lambda_lame,
+                                     self.cfg.damping_factor)
+        A, _ = fem.assemble_system(Ae, None, self.vcell_dofs, self.d * self.nv,
+                                   self.shape_bc_dofs, 0.0)
+        self.A_elas = A
+        return A
+
+    def scalar_product(self, a, b):
+        return float((self.A_elas @ a) @ b)
+
+    # -- shape derivative (a7)
+    def shape_derivative_elements(self):
+        d = self.d
+        _, vol, G = self._geom()
+        ue, pe = self.u[self.cells], self.p[self.cells]
+        gu = np.einsum("ca,cai->ci", ue, G)
+        gp = np.einsum("ca,cai->ci", pe, G)
+        lam, w = fem.quadrature(d, self.f_degree + 1)
+        xq = np.einsum("qa,cad->cqd", lam, self.coords[self.cells])
+        fq = self.f(xq)
+        gfq = self.grad_f(xq)[..., :d]
+        pq = np.einsum("qa,ca->cq", lam, pe)
+        int_u = vol * ue.mean(axis=1)
+        int_fp = vol * np.einsum("cq,cq,q->c", fq, pq, w)
+        int_gf_phi_p = vol[:, None, None] * np.einsum("cqi,cq,q,qa->cai", gfq, pq, w, lam)
+        gugp = np.einsum("ci,ci->c", gu, gp)
+        Ggu = np.einsum("cai,ci->ca", G, gu)
+        Ggp = np.einsum("cai,ci->ca", G, gp)
+        be = (
+            G * (int_u + vol * gugp - int_fp)[:, None, None]
+            - vol[:, None, None] * (Ggu[:, :, None] * gp[:, None, :] + Ggp[:, :, None] * gu[:, None, :])
+            - int_gf_phi_p
+        )
+        return be.reshape(self.cells.shape[0], -1)
+
+    def shape_derivative_vector(self):
+        be = self.shape_derivative_elements()
+        if self.shape_bc_dofs.size:
+            _, be = fem.apply_bcs_elementwise(None, be, self.vcell_dofs, self.shape_bc_dofs, 0.0,
+                                              self.d * self.nv)
+        return fem.assemble_vector(be, self.vcell_dofs, self.d * self.nv)
+
+    # -- a8
+    def compute_shape_gradient(self):
+        self.solve_state()
+        self.solve_adjoint()
+        self.dJ = self.shape_derivative_vector()
+        g, reason, its, _ = krylov.solve(self.A_elas, self.dJ, self.gradient_ksp)
+        self._check(reason)
+        self.its["gradient"] = its
+        g[self.shape_bc_dofs] = 0.0  # apply_shape_bcs (shape_form_handler.py:825-841)
+        self.gradient = g
+        self.gradient_norm_squared = self.scalar_product(g, g)
+        return g
+
+    # -- mesh handling (a12, a13, a15, a16)
+    def move_mesh(self, deformation):
+        """``_MeshHandler.move_mesh``: a-priori test -> move -> intersection test -> quality."""
+        V = deformation.reshape(self.nv, self.d)
+        ok, _, _ = quality.a_priori_test(self.coords, self.cells, V, self.cfg.volume_change)
+        if not ok:
+            return False
+        self.old_coords = self.coords.copy()
+        self.coords += V
+        success = True
+        if self.cfg.test_for_intersections:
+            success = self.intersection_test()
+            if not success:
+                self.revert_transformation()
+        self.current_mesh_quality = quality.compute_mesh_quality(
+            self.coords, self.cells, self.cfg.qtype, self.cfg.measure, self.cfg.quantile
+        )
+        return success
+
+    def intersection_test(self):
+        if self.nv > 5000:  # brute force oracle is O(Nv*Nc); a-priori test already rules out inversion
+            return True
+        return quality.intersection_test(self.coords, self.cells)
+
+    def revert_transformation(self):
+        self.coords[:, :] = self.old_coords
+        self.old_coords = None
+
+    def compute_decreases(self, direction, stepsize):
+        c = self.cfg
+        if c.angle_change == float("inf"):
+            return 0
+        fro = quality.gradient_frobenius_max(self.coords, self.cells, direction.reshape(self.nv, self.d))
+        return int(np.maximum(np.ceil(np.log(c.angle_change / stepsize / fro) / np.log(1 / c.beta_armijo)), 0.0))
+
+    def update_optimization_variables(self, direction, stepsize):
+        """Returns (accepted stepsize, list of decisions) -- decisions are what CUDA must reproduce."""
+        decisions = []
+        while True:
+            if self.move_mesh(stepsize * direction):
+                if self.current_mesh_quality < self.cfg.tol_lower:
+                    decisions.append(("quality_reject", stepsize))
+                    stepsize /= self.cfg.beta_armijo
+                    self.revert_transformation()
+                    continue
+                decisions.append(("accept", stepsize))
+                break
+            decisions.append(("move_reject", stepsize))
+            stepsize /= self.cfg.beta_armijo
+        return stepsize, decisions
+
+    def evaluate_cost(self):
+        self.solve_state()
+        return self.cost()
+
+
+def armijo_step(prob: PoissonShapeProblem, direction, stepsize, J_cur, iteration=0,
+                has_curvature_info=False, max_trials=60):
+    """One Armijo line search; returns (stepsize, J_new, log of decisions)."""
+    c = prob.cfg
+    log = []
+    ndec = prob.compute_decreases(direction, stepsize)
+    stepsize /= c.beta_armijo**ndec
+    if c.safeguard_stepsize and iteration == 0:
+        nrm = np.sqrt(prob.scalar_product(direction, direction))
+        stepsize = float(np.minimum(stepsize, 100.0 / (1.0 + nrm)))
+    dinf = float(np.max(np.abs(direction)))
+    for _ in range(max_trials):
+        if stepsize * dinf <= 1e-9:
+            log.append(("fail_stepsize", stepsize))
+            return None, J_cur, log
+        dm = prob.scalar_product(prob.gradient, direction)
+        stepsize, dec = prob.update_optimization_variables(direction, stepsize)
+        log.extend(dec)
+        J_new = prob.evaluate_cost()
+        if J_new < J_cur + c.epsilon_armijo * dm * stepsize:
+            log.append(("armijo_accept", stepsize))
+            prob.update_scalar_product()  # post_line_search (line_search.py:247-249)
+            return stepsize, J_new, log
+        log.append(("armijo_reject", stepsize))
+        stepsize /= c.beta_armijo
+        prob.revert_transformation()
+    return None, J_cur, log
+
+
+def gradient_descent(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50):
+    """``GradientDescentMethod.run`` (``optimization_algorithms/gradient_descent.py:28-60``)."""
+    stepsize = prob.cfg.initial_stepsize
+    hist = []
+    gnorm0 = None
+    for it in range(max_iter + 1):
+        g = prob.compute_shape_gradient()
+        gnorm = np.sqrt(prob.gradient_norm_squared)
+        if gnorm0 is None:
+            gnorm0 = gnorm
+        J = prob.cost()
+        hist.append((it, J, gnorm / gnorm0, prob.current_mesh_quality, stepsize))
+        if gnorm <= atol + rtol * gnorm0:
+            return True, hist
+        if it == max_iter:
+            break
+        step, _, _ = armijo_step(prob, -g, stepsize, J, iteration=it)
+        if step is None:
+            return False, hist
+        stepsize = step * prob.cfg.beta_armijo  # no curvature info -> enlarge (armijo_line_search.py:196-197)
+    return False, hist
+
+
+def lbfgs(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50, memory=3, scaling=True):
+    """``LBFGSMethod.run`` (``optimization_algorithms/l_bfgs.py:91-135``) with the two-loop recursion."""
+    S, Y, RHO = [], [], []
+    stepsize = prob.cfg.initial_stepsize
+    hist = []
+    g = prob.compute_shape_gradient()
+    gnorm = gnorm0 = np.sqrt(prob.gradient_norm_squared)
+    it = 0
+    while True:
+        J = prob.cost()
+        hist.append((it, J, gnorm / gnorm0, prob.current_mesh_quality, stepsize))
+        if gnorm <= atol + rtol * gnorm0:
+            return True, hist
+        if it >= max_iter:
+            return False, hist
+        # two-loop
+        q = g.copy()
+        alphas = []
+        for s, y, rho in zip(reversed(S), reversed(Y), reversed(RHO)):
+            a = rho * prob.scalar_product(s, q)
+            alphas.append(a)
+            q = q - a * y
+        if scaling and S:
+            q = q * (prob.scalar_product(Y[-1], S[-1]) / prob.scalar_product(Y[-1], Y[-1]))
+        for (s, y, rho), a in zip(zip(S, Y, RHO), reversed(alphas)):
+            b = rho * prob.scalar_product(y, q)
+            q = q + (a - b) * s
+        d = -q
+        has_curv = len(S) > 0
+        if prob.scalar_product(g, d) >= 0:  # check_for_ascent (optimization_algorithm.py:315-331)
+            d = -g
+            S, Y, RHO = [], [], []
+            has_curv = False
+        trial = 1.0 if has_curv else stepsize
+        step, _, _ = armijo_step(prob, d, trial, J, iteration=it, has_curvature_info=has_curv)
+        if step is None:
+            return False, hist
+        stepsize = step if has_curv else step * prob.cfg.beta_armijo
+        g_prev = g
+        g = prob.compute_shape_gradient()
+        gnorm = np.sqrt(prob.gradient_norm_squared)
+        it += 1
+        if memory > 0:
+            y = g - g_prev
+            s = step * d
+            curv = prob.scalar_product(y, s)
+            if curv <= 0:
+                S, Y, RHO = [], [], []
+            else:
+                S.append(s), Y.append(y), RHO.append(1.0 / curv)
+                if len(S) > memory:
+                    S.pop(0), Y.pop(0), RHO.pop(0)
+
+
+def shape_gradient_test(prob: PoissonShapeProblem, rng=None, h=None):
+    """Taylor test of ``cashocs/verification.py:182-302``; returns the last convergence rate."""
+    rng = rng or np.random.RandomState(300696)
+    if h is None:
+        h = rng.rand(prob.d * prob.nv)
+    h = h.copy()
+    h[prob.shape_bc_dofs] = 0.0
+    J0 = prob.evaluate_cost()
+    g = prob.compute_shape_gradient()
+    dJh = prob.scalar_product(g, h)
+    length = float(prob.coords.max() - prob.coords.min())
+    eps_list = [length * 1e-4 / 2**i for i in range(4)]
+    res = []
+    for eps in eps_list:
+        if prob.move_mesh(eps * h):
+            J1 = prob.evaluate_cost()
+            res.append(abs(J1 - J0 - eps * dJh))
+            prob.revert_transformation()
+        else:
+            res.append(float("inf"))
+    rates = [np.log(res[i] / res[i - 1]) / np.log(eps_list[i] / eps_list[i - 1]) for i in range(1, 4)]
+    return rates[-1], rates, res
+
+
+# ----------------------------------------------------------------------------- optimal control (a10)
+class PoissonControlProblem:
+    """F = grad y . grad p - u p;  J = 1/2 |y - y_d|^2 + alpha/2 |u|^2  (tests/test_pde_problems.py:59-84)."""
+
+    def __init__(self, mesh, y_d, u, alpha=1e-6, bc_markers=(1, 2), state_ksp=None, adjoint_ksp=None,
+                 riesz_ksp=None):
+        self.mesh, self.coords, self.cells = mesh, mesh.coords, mesh.cells
+        self.d, self.nv = mesh.dim, mesh.num_vertices
+        self.y_d, self.u, self.alpha = y_d, u, alpha
+        self.bc = mesh.boundary_vertices(bc_markers)
+        self.state_ksp = state_ksp or DEFAULT_KSP
+        self.adjoint_ksp = adjoint_ksp or DEFAULT_KSP
+        self.riesz_ksp = riesz_ksp or DEFAULT_KSP
+        self.its = {}
+
+    def _system(self, rhs_vertex, sign):
+        _, vol, G = fem.cell_geometry(self.coords, self.cells)
+        Ke = fem.stiffness_elements(vol, G)
+        be = sign * fem.load_elements_p1(vol, self.cells, rhs_vertex, self.d)
+        return fem.assemble_system(Ke, be, self.cells, self.nv, self.bc, 0.0)
+
+    def solve_state(self):
+        A, b = self._system(self.u, 1.0)
+        self.y, reason, self.its["state"], _ = krylov.solve(A, b, self.state_ksp)
+        PoissonShapeProblem._check(reason)
+        return self.y
+
+    def solve_adjoint(self):
+        A, b = self._system(self.y - self.y_d, -1.0)
+        self.p, reason, self.its["adjoint"], _ = krylov.solve(A, b, self.adjoint_ksp)
+        PoissonShapeProblem._check(reason)
+        return self.p
+
+    def mass_matrix(self):
+        _, vol, _ = fem.cell_geometry(self.coords, self.cells)
+        M, _ = fem.assemble_system(fem.mass_elements(vol, self.d), None, self.cells, self.nv)
+        return M
+
+    def compute_gradient(self):
+        """M g = alpha M u - M p  (``control_form_handler.py:209-220``)."""
+        self.solve_state()
+        self.solve_adjoint()
+        _, vol, _ = fem.cell_geometry(self.coords, self.cells)
+        be = fem.load_elements_p1(vol, self.cells, self.alpha * self.u - self.p, self.d)
+        b = fem.assemble_vector(be, self.cells, self.nv)
+        self.M = self.mass_matrix()
+        self.g, reason, self.its["gradient"], _ = krylov.solve(self.M, b, self.riesz_ksp)
+        PoissonShapeProblem._check(reason)
+        self.gradient_norm_squared = float((self.M @ self.g) @ self.g)
+        return self.g
+
+    def cost(self):
+        M = self.mass_matrix()
+        e = self.y - self.y_d
+        return 0.5 * float((M @ e) @ e) + 0.5 * self.alpha * float((M @ self.u) @ self.u)
