@@ -1,0 +1,135 @@
+"""Form descriptors: the restricted UFL form family of the hot path as plain Python objects.
+
+The reference derives its systems symbolically with UFL (``cashocs/_forms/general_form_handler.py``):
+state ``derivative(F, p, test)`` split by ``ufl.system`` (``:101-140``), adjoint
+``derivative(Lagrangian, y, test)`` with homogenised BCs (``:170-244``).  UFL is not available
+here and symbolic differentiation is outside the hot path, so users state *which* member of the
+supported family they mean; the descriptors carry exactly the data the element kernels need.
+``fenics_adapter`` recognises these forms in UFL input when FEniCS is importable.
+
+Supported family:
+    F(u, p) = kappa * grad(u).grad(p) dx + c * u p dx - f p dx ,   u = g on Dirichlet markers
+    J(u)    = int alpha_u * u dx  +  1/2 int (u - u_d)^2 dx  +  alpha/2 int control^2 dx
+"""
+
+from __future__ import annotations
+
+import dataclasses
+
+import torch
+
+from cashocs_b200 import _exceptions
+from cashocs_b200._forms import expressions
+
+
+class Function:
+    """A P1 finite-element function: a device vector plus its value size (1 = scalar, d = vector)."""
+
+    def __init__(self, mesh, value_size: int = 1, name: str = "f") -> None:
+        self.mesh = mesh
+        self.value_size = int(value_size)
+        self.name = name
+        # ghost entries (distributed meshes) live at the tail
+        self.vector = torch.zeros(mesh.num_vertices * self.value_size, dtype=torch.float64, device=mesh.device)
+
+    def owned(self) -> torch.Tensor:
+        return self.vector[: self.mesh.n_owned_vertices * self.value_size]
+
+    def assign(self, other) -> None:
+        src = other.vector if isinstance(other, Function) else other
+        self.vector.copy_(src)
+
+    def copy(self) -> "Function":
+        f = Function(self.mesh, self.value_size, self.name)
+        f.vector.copy_(self.vector)
+        return f
+
+    def interpolate(self, expr) -> None:
+        """Nodal interpolation of a polynomial / callable of the vertex coordinates."""
+        x = self.mesh.coords
+        if isinstance(expr, expressions.Polynomial):
+            out = torch.zeros(x.shape[0], dtype=torch.float64, device=x.device)
+            for (a, b, c), v in expr.terms.items():
+                m = v * x[:, 0] ** a * x[:, 1] ** b
+                if x.shape[1] == 3:
+                    m = m * x[:, 2] ** c
+                out += m
+            self.vector.copy_(out)
+        else:
+            self.vector.copy_(expr(x).reshape(-1))
+
+
+@dataclasses.dataclass
+class DirichletBC:
+    """``DirichletBC(V, value, boundaries, marker)`` for a (sub)space of a P1 space.
+
+    ``component`` = None constrains all components (``V``), an int only ``V.sub(component)``.
+    """
+
+    value: float
+    markers: tuple
+    component: int | None = None
+
+    def __post_init__(self):
+        if isinstance(self.markers, int):
+            self.markers = (self.markers,)
+        self.markers = tuple(int(m) for m in self.markers)
+
+
+def create_dirichlet_bcs(value: float, markers, component: int | None = None) -> list[DirichletBC]:
+    """``cashocs.create_dirichlet_bcs`` (``cashocs/_utils/forms.py:214-271``): one BC per marker."""
+    if isinstance(markers, int):
+        markers = [markers]
+    return [DirichletBC(value, (int(m),), component) for m in markers]
+
+
+def bc_flag_arrays(mesh, bcs: list[DirichletBC], value_size: int):
+    """Flag / value arrays over all dofs of a P1 space; later BCs overwrite earlier ones."""
+    n = mesh.num_vertices * value_size
+    flag = torch.zeros(n, dtype=torch.uint8, device=mesh.device)
+    val = torch.zeros(n, dtype=torch.float64, device=mesh.device)
+    any_bc = False
+    for bc in bcs:
+        verts = mesh.boundary_vertices(bc.markers)
+        if verts.numel() == 0:
+            continue
+        any_bc = True
+        comps = range(value_size) if bc.component is None else [bc.component]
+        for c in comps:
+            dofs = verts * value_size + c
+            flag[dofs] = 1
+            val[dofs] = float(bc.value)
+    return (flag, val) if any_bc else (None, None)
+
+
+@dataclasses.dataclass
+class PoissonForm:
+    """``F = kappa*inner(grad(u), grad(p))*dx + reaction*u*p*dx - source*p*dx``.
+
+    ``source`` is a :class:`Polynomial` in the spatial coordinates (shape problems: it moves
+    with the domain), a :class:`Function` (a P1 field, e.g. the control) or ``None``.
+    """
+
+    source: object = None
+    kappa: float = 1.0
+    reaction: float = 0.0
+    source_scale: float = 1.0
+
+    @property
+    def is_self_adjoint(self) -> bool:
+        return True
+
+
+@dataclasses.dataclass
+class IntegralFunctional:
+    """``J = int (c_state*u + c_track/2 (u-u_d)^2) dx + c_control/2 int control^2 dx``
+    (``cashocs.IntegralFunctional``, ``cashocs/_optimization/cost_functional.py:146-206``)."""
+
+    c_state: float = 0.0
+    c_track: float = 0.0
+    desired_state: Function | None = None
+    c_control: float = 0.0
+
+    def __post_init__(self):
+        if self.c_track != 0.0 and self.desired_state is None:
+            raise _exceptions.InputError("IntegralFunctional", "desired_state", "tracking term needs u_d")

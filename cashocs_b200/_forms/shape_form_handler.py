@@ -1,0 +1,168 @@
+"""Shape form handling (``cashocs/_forms/shape_form_handler.py``): Lame parameters, the
+linear-elasticity Riesz scalar product, its boundary conditions and the shape derivative."""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from cashocs_b200 import _exceptions
+from cashocs_b200._forms import forms
+from cashocs_b200._utils import linalg
+
+
+class Stiffness:
+    """Lame mu from an auxiliary Laplace problem (``shape_form_handler.py:56-235``).
+
+    ``-Laplace(mu) = 0`` with ``mu = mu_fix`` on ``shape_bdry_fix`` and ``mu_def`` on
+    ``shape_bdry_def`` whenever ``|mu_def - mu_fix| / mu_fix > 1e-2`` (``:110``), otherwise the
+    constant ``mu_fix`` (``:210-214``).  The reference solves with CG + BoomerAMG at rtol 1e-16
+    / max_it 100 (``:113-120``); the device maps that option set explicitly
+    (``linalg.parse_ksp_options``).
+    """
+
+    def __init__(self, mu_lame: forms.Function, config, mesh, shape_bdry_def, shape_bdry_fix,
+                 linear_solver: linalg.LinearSolver | None = None, ksp_options=None) -> None:
+        self.mu_lame = mu_lame
+        self.config = config
+        self.mesh = mesh
+        self.shape_bdry_def = list(shape_bdry_def)
+        self.shape_bdry_fix = list(shape_bdry_fix)
+        self.linear_solver = linear_solver or linalg.LinearSolver()
+        self.inhomogeneous_mu = False
+        if config.getboolean("ShapeGradient", "use_distance_mu"):
+            raise _exceptions.InputError("cashocs_b200.Stiffness", "use_distance_mu", "outside the hot path (SURVEY.md 8a)")
+        mu_def = config.getfloat("ShapeGradient", "mu_def")
+        mu_fix = config.getfloat("ShapeGradient", "mu_fix")
+        self.options_mu = ksp_options or {
+            "ksp_type": "cg", "pc_type": "hypre", "pc_hypre_type": "boomeramg",
+            "ksp_rtol": 1e-16, "ksp_atol": 1e-50, "ksp_max_it": 100,
+        }
+        if np.abs(mu_def - mu_fix) / mu_fix > 1e-2:
+            self.inhomogeneous_mu = True
+            self.bcs_mu = forms.create_dirichlet_bcs(mu_fix, self.shape_bdry_fix)
+            self.bcs_mu += forms.create_dirichlet_bcs(mu_def, self.shape_bdry_def)
+            self.bc_flag, self.bc_val = forms.bc_flag_arrays(mesh, self.bcs_mu, 1)
+            self.A_mu_matrix = linalg.Matrix(mesh, 1)
+            self.b_mu = torch.zeros(mesh.n_owned_vertices, dtype=torch.float64, device=mesh.device)
+        self.last_its = 0
+
+    def compute(self) -> None:
+        """Computes the elasticity parameter mu (``shape_form_handler.py:188-235``)."""
+        if self.inhomogeneous_mu:
+            linalg.assemble_scalar_system(self.mesh, 1.0, 0.0, bc_flag=self.bc_flag, bc_val=self.bc_val,
+                                          A=self.A_mu_matrix, b=self.b_mu)
+            res = self.linear_solver.solve(self.mu_lame.vector, A=self.A_mu_matrix, b=self.b_mu,
+                                           ksp_options=self.options_mu)
+            self.last_its = res.its
+            if self.mesh.dist is not None:
+                self.mesh.dist.halo_exchange(self.mu_lame.vector, 1)
+            if self.config.getboolean("ShapeGradient", "use_sqrt_mu"):
+                self.mu_lame.vector.abs_().sqrt_()
+        else:
+            self.mu_lame.vector.fill_(self.config.getfloat("ShapeGradient", "mu_fix"))
+
+
+class ShapeFormHandler:
+    """Riesz scalar product + shape derivative for a shape problem (``shape_form_handler.py:238-860``)."""
+
+    def __init__(self, mesh, config, state_form: forms.PoissonForm, cost: forms.IntegralFunctional,
+                 state: forms.Function, adjoint: forms.Function, mu_linear_solver=None) -> None:
+        self.mesh = mesh
+        self.config = config
+        self.state_form, self.cost = state_form, cost
+        self.state, self.adjoint = state, adjoint
+        d = mesh.dim
+        g = lambda k: [int(m) for m in config.getlist("ShapeGradient", k)]  # noqa: E731
+        self.shape_bdry_def = g("shape_bdry_def")
+        self.shape_bdry_fix = g("shape_bdry_fix")
+        self.shape_bdry_fix_x = g("shape_bdry_fix_x")
+        self.shape_bdry_fix_y = g("shape_bdry_fix_y")
+        self.shape_bdry_fix_z = g("shape_bdry_fix_z")
+        self.fixed_dimensions = [int(i) for i in config.getlist("ShapeGradient", "fixed_dimensions")]
+        self.use_fixed_dimensions = len(self.fixed_dimensions) > 0
+        for key in ("use_p_laplacian", "reextend_from_boundary", "inhomogeneous", "update_inhomogeneous"):
+            if config.getboolean("ShapeGradient", key) and key in ("use_p_laplacian", "reextend_from_boundary"):
+                raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", key, "outside the hot path (SURVEY.md 8a)")
+        self.inhomogeneous = config.getboolean("ShapeGradient", "inhomogeneous")
+        self.update_inhomogeneous = config.getboolean("ShapeGradient", "update_inhomogeneous")
+        self.lambda_lame = config.getfloat("ShapeGradient", "lambda_lame")
+        self.damping_factor = config.getfloat("ShapeGradient", "damping_factor")
+        self.mu_lame = forms.Function(mesh, 1, "mu_lame")
+        self.stiffness = Stiffness(self.mu_lame, config, mesh, self.shape_bdry_def, self.shape_bdry_fix,
+                                   linear_solver=mu_linear_solver)
+        self.bcs_shape = self._setup_bcs_shape()
+        self.bc_flag, _ = forms.bc_flag_arrays(mesh, self.bcs_shape, d)
+        if self.use_fixed_dimensions:
+            if self.bc_flag is None:
+                self.bc_flag = torch.zeros(mesh.num_vertices * d, dtype=torch.uint8, device=mesh.device)
+            for c in self.fixed_dimensions:
+                self.bc_flag.view(-1, d)[:, c] = 1  # _project_scalar_product (shape_form_handler.py:693-712)
+        self.volumes = None
+        if self.inhomogeneous:
+            self._update_volumes()
+        self.fe_scalar_product_matrix = linalg.Matrix(mesh, d)
+        self.scalar_product_matrix = self.fe_scalar_product_matrix
+        self.fe_shape_derivative_vector = torch.zeros(mesh.n_owned_vertices * d, dtype=torch.float64,
+                                                      device=mesh.device)
+        self.update_scalar_product()
+
+    def _setup_bcs_shape(self) -> list[forms.DirichletBC]:
+        """``shape_form_handler.py:551-588``."""
+        bcs = forms.create_dirichlet_bcs(0.0, self.shape_bdry_fix)
+        bcs += forms.create_dirichlet_bcs(0.0, self.shape_bdry_fix_x, 0)
+        bcs += forms.create_dirichlet_bcs(0.0, self.shape_bdry_fix_y, 1)
+        if self.mesh.dim == 3:
+            bcs += forms.create_dirichlet_bcs(0.0, self.shape_bdry_fix_z, 2)
+        return bcs
+
+    def _update_volumes(self) -> None:
+        """Cell volumes normalised by their maximum (l2_projection of CellVolume, ``:629-644``)."""
+        from cashocs_b200.geometry import measures
+
+        vol = measures.cell_volumes(self.mesh)
+        vmax = vol.max()
+        if self.mesh.dist is not None:
+            vmax = vmax.reshape(1).clone()
+            self.mesh.dist.allreduce(vmax, "max")
+        expo = self.config.getfloat("ShapeGradient", "inhomogeneous_exponent")
+        self.volumes = vol / vmax
+        self.cell_scale = torch.pow(self.volumes, -expo).contiguous()
+
+    def update_scalar_product(self) -> None:
+        """mu solve + elasticity re-assembly + ident_zeros (``shape_form_handler.py:714-746``)."""
+        self.stiffness.compute()
+        if self.inhomogeneous and self.update_inhomogeneous:
+            self._update_volumes()
+        linalg.assemble_elasticity_matrix(
+            self.mesh, self.mu_lame.vector, self.lambda_lame, self.damping_factor, bc_flag=self.bc_flag,
+            cell_scale=self.cell_scale if self.inhomogeneous else None, A=self.fe_scalar_product_matrix,
+        )
+
+    def scalar_product(self, a: torch.Tensor, b: torch.Tensor) -> float:
+        """``b^T A a`` (``shape_form_handler.py:748-780``)."""
+        return self.scalar_product_matrix.scalar_product(a, b)
+
+    def assemble_shape_derivative(self) -> torch.Tensor:
+        """``assembler.assemble(fe_shape_derivative_vector)`` (``shape_gradient_problem.py:142-144``)."""
+        src = self.state_form.source
+        if not isinstance(src, (type(None),)) and not hasattr(src, "terms"):
+            raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "source",
+                                         "shape problems need a polynomial (coordinate) source term")
+        if self.cost.c_track != 0.0 or self.state_form.reaction != 0.0 or self.state_form.kappa != 1.0:
+            raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "forms",
+                                         "shape derivative implemented for kappa=1, no reaction, J = c*int(u)")
+        from cashocs_b200._forms import expressions
+
+        f = src if src is not None else expressions.Polynomial()
+        f = f * self.state_form.source_scale
+        return linalg.assemble_shape_derivative(
+            self.mesh, self.state.vector, self.adjoint.vector, f, self.cost.c_state, bc_flag=self.bc_flag,
+            b=self.fe_shape_derivative_vector,
+        )
+
+    def apply_shape_bcs(self, function: torch.Tensor) -> None:
+        """Impose the geometric constraints on a deformation (``shape_form_handler.py:825-841``)."""
+        if self.bc_flag is not None:
+            n = function.numel()
+            function.masked_fill_(self.bc_flag[:n].bool(), 0.0)

@@ -1,0 +1,192 @@
+"""ctypes binding of the C-ABI declared in ``include/cashocs_b200.h``.
+
+The CUDA library is the product: if ``libcashocs_b200.so`` is missing this module raises
+loudly -- there is no CPU or PyTorch fallback for any hot-path operation.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from cashocs_b200 import _exceptions
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcashocs_b200.so")
+
+POLY_MAXT = 24
+QUAD_MAXQ = 64
+
+
+class cb_poly(C.Structure):
+    _fields_ = [
+        ("nterms", C.c_int32),
+        ("pad", C.c_int32),
+        ("coef", C.c_double * POLY_MAXT),
+        ("ex", C.c_int8 * POLY_MAXT),
+        ("ey", C.c_int8 * POLY_MAXT),
+        ("ez", C.c_int8 * POLY_MAXT),
+    ]
+
+
+class cb_quad(C.Structure):
+    _fields_ = [
+        ("nq", C.c_int32),
+        ("pad", C.c_int32),
+        ("lam", (C.c_double * 4) * QUAD_MAXQ),
+        ("w", C.c_double * QUAD_MAXQ),
+    ]
+
+
+class cb_mesh_view(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32),
+        ("ncolours", C.c_int32),
+        ("colour_off", C.c_void_p),
+        ("cells", C.c_void_p),
+        ("cell2nnz", C.c_void_p),
+        ("coords", C.c_void_p),
+        ("nv", C.c_int64),
+        ("nrows_owned", C.c_int64),
+        ("nnz", C.c_int64),
+    ]
+
+
+class cb_mat(C.Structure):
+    _fields_ = [
+        ("nrows", C.c_int64),
+        ("ncols", C.c_int64),
+        ("bs", C.c_int32),
+        ("pad", C.c_int32),
+        ("rowptr", C.c_void_p),
+        ("col", C.c_void_p),
+        ("val", C.c_void_p),
+    ]
+
+
+class cb_ksp_opts(C.Structure):
+    _fields_ = [
+        ("ksp_type", C.c_int32),
+        ("pc_type", C.c_int32),
+        ("rtol", C.c_double),
+        ("atol", C.c_double),
+        ("dtol", C.c_double),
+        ("max_it", C.c_int32),
+        ("cheb_degree", C.c_int32),
+        ("cheb_ratio", C.c_double),
+        ("check_every", C.c_int32),
+        ("monitor", C.c_int32),
+    ]
+
+
+class cb_ksp_result(C.Structure):
+    _fields_ = [
+        ("reason", C.c_int32),
+        ("its", C.c_int32),
+        ("rnorm", C.c_double),
+        ("rnorm0", C.c_double),
+    ]
+
+
+P = C.c_void_p
+I64 = C.c_int64
+I32 = C.c_int
+DBL = C.c_double
+
+# name -> (restype, argtypes); every symbol declared in include/cashocs_b200.h
+SIGNATURES = {
+    "cb_last_error": (C.c_char_p, []),
+    "cb_version": (I32, []),
+    "cb_num_sms": (I32, []),
+    "cb_v2c_build": (I32, [P, I64, I64, I32, P, P, P]),
+    "cb_pattern_rowptr": (I32, [P, I64, I32, P, P, P, P]),
+    "cb_pattern_fill": (I32, [P, I64, I64, I32, P, P, P, P, P, P]),
+    "cb_colour_cells_host": (I32, [I64, I64, I32, P, P]),
+    "cb_assemble_scalar": (I32, [P, C.POINTER(cb_mesh_view), DBL, DBL, DBL, C.POINTER(cb_poly),
+                                 C.POINTER(cb_quad), DBL, P, P, P, P, P]),
+    "cb_assemble_elasticity": (I32, [P, C.POINTER(cb_mesh_view), P, DBL, DBL, P, P, P]),
+    "cb_assemble_shape_derivative_poisson": (I32, [P, C.POINTER(cb_mesh_view), P, P, C.POINTER(cb_poly),
+                                                   C.POINTER(cb_poly), C.POINTER(cb_quad), DBL, P, P]),
+    "cb_ident_zeros": (I32, [P, I64, I32, P, P, P, P]),
+    "cb_spmv": (I32, [P, C.POINTER(cb_mat), P, P]),
+    "cb_scalar_product": (I32, [P, C.POINTER(cb_mat), P, P, P, P, I64]),
+    "cb_dot": (I32, [P, I64, P, P, P, P, I64]),
+    "cb_reduce_scratch_len": (I64, []),
+    "cb_extract_diag_inv": (I32, [P, C.POINTER(cb_mat), P, P, P, I64]),
+    "cb_ksp_workspace_len": (I64, [I64, I64, C.POINTER(cb_ksp_opts)]),
+    "cb_ksp_solve": (I32, [P, C.POINTER(cb_mat), P, P, C.POINTER(cb_ksp_opts), P, P, I64,
+                           C.POINTER(cb_ksp_result), P, I64]),
+    "cb_mesh_quality": (I32, [P, I32, I64, P, P, I32, P, P, P, I64]),
+    "cb_det_check": (I32, [P, I32, I64, P, P, P, DBL, P, P, P, I64]),
+    "cb_gradient_frobenius_max": (I32, [P, I32, I64, P, P, P, P, P, I64]),
+    "cb_move_mesh": (I32, [P, I64, P, P, P, DBL]),
+    "cb_functional": (I32, [P, I32, I64, P, P, DBL, P, DBL, P, P, P, I64]),
+    "cb_intersection_test": (I32, [P, I32, I64, I64, P, P, P, P, P]),
+    "cb_dist_unique_id": (I32, [P]),
+    "cb_dist_create": (I32, [C.POINTER(P), P, I32, I32, I32, P, P, P, P, I64, I64]),
+    "cb_dist_destroy": (I32, [P]),
+    "cb_dist_halo_exchange": (I32, [P, P, P, I32, P]),
+    "cb_dist_allreduce": (I32, [P, P, P, I32, I32]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m cashocs_b200.build` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "cashocs_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> int:
+    """Raise on a negative library return code."""
+    if rc < 0:
+        msg = load().cb_last_error().decode("utf-8", "replace")
+        raise _exceptions.CashocsException(f"cashocs_b200 C-ABI error {rc} in {what}: {msg}")
+    return rc
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+def stream_ptr():
+    """The current torch CUDA stream as a void*."""
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    """Hot-path entry points accept CUDA fp64/int32/int64 contiguous tensors only."""
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _exceptions.CashocsException(
+                "cashocs_b200: this operation runs on the GPU only (got a CPU tensor); "
+                "there is no CPU fallback."
+            )
+        if not t.is_contiguous():
+            raise _exceptions.CashocsException("cashocs_b200: tensors must be contiguous")

@@ -1,0 +1,42 @@
+"""Reduced cost functional (``cashocs/_optimization/cost_functional.py:44-88,146-206``)."""
+
+from __future__ import annotations
+
+import torch
+
+from cashocs_b200 import _lib
+
+
+class ReducedCostFunctional:
+    """J(u) evaluated through a state solve + one fused cell-loop reduction kernel."""
+
+    def __init__(self, mesh, cost, states, state_problem, control=None, mass_scalar_product=None) -> None:
+        self.mesh, self.cost, self.states = mesh, cost, states
+        self.state_problem = state_problem
+        self.control = control
+        self.mass_scalar_product = mass_scalar_product
+        self._out = torch.zeros(1, dtype=torch.float64, device=mesh.device)
+
+    def _integral(self, u, c_u, c_track, ud) -> float:
+        mesh = self.mesh
+        scratch = mesh.reduce_scratch()
+        _lib.check(
+            _lib.load().cb_functional(_lib.stream_ptr(), mesh.dim, mesh.n_owned_cells, _lib.ptr(mesh.coords),
+                                      _lib.ptr(mesh.cells), float(c_u), _lib.ptr(u), float(c_track), _lib.ptr(ud),
+                                      _lib.ptr(self._out), _lib.ptr(scratch), scratch.numel()),
+            "cb_functional",
+        )
+        if mesh.dist is not None:
+            mesh.dist.allreduce(self._out, "sum")
+        return float(self._out.item())
+
+    def evaluate(self) -> float:
+        """``ReducedCostFunctional.evaluate`` (``cost_functional.py:65-88``)."""
+        self.state_problem.solve()
+        c = self.cost
+        ud = c.desired_state.vector if c.c_track != 0.0 else None
+        val = self._integral(self.states[0].vector, c.c_state, c.c_track, ud)
+        if c.c_control != 0.0 and self.control is not None:
+            # alpha/2 int u^2 = alpha/2 u^T M u
+            val += 0.5 * c.c_control * self.mass_scalar_product(self.control.vector, self.control.vector)
+        return val

@@ -1,0 +1,149 @@
+"""Armijo line search (``cashocs/_optimization/line_search/armijo_line_search.py:97-245``,
+``line_search.py:152-214,251-279``) and the shape variable update loop
+(``shape_optimization/shape_variable_abstractions.py:91-135``).  Host Python: only scalars
+cross the PCIe bus, every vector operation is a device op."""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from cashocs_b200 import _exceptions
+
+
+class ShapeVariableAbstractions:
+    """Abstractions of the optimisation variables in the case of shape optimisation."""
+
+    def __init__(self, problem) -> None:
+        self.problem = problem
+        self.mesh_handler = problem.mesh_handler
+        self.form_handler = problem.form_handler
+        self.deformation = torch.zeros_like(problem.gradient.vector)
+        self.decisions: list[tuple[str, float]] = []
+
+    def compute_decrease_measure(self, search_direction: torch.Tensor) -> float:
+        return self.form_handler.scalar_product(self.problem.gradient.vector, search_direction)
+
+    def compute_gradient_norm(self) -> float:
+        g = self.problem.gradient.vector
+        return float(np.sqrt(self.form_handler.scalar_product(g, g)))
+
+    def revert_variable_update(self) -> None:
+        self.mesh_handler.revert_transformation()
+
+    def update_optimization_variables(self, search_direction: torch.Tensor, stepsize: float, beta: float) -> float:
+        """Halve the step until the mesh move succeeds and the quality is >= tol_lower (``:91-135``)."""
+        while True:
+            torch.mul(search_direction, stepsize, out=self.deformation)
+            if self.mesh_handler.move_mesh(self.deformation):
+                if self.mesh_handler.current_mesh_quality < self.mesh_handler.mesh_quality_tol_lower:
+                    self.decisions.append(("quality_reject", stepsize))
+                    stepsize /= beta
+                    self.mesh_handler.revert_transformation()
+                    continue
+                self.decisions.append(("accept", stepsize))
+                break
+            self.decisions.append(("move_reject", stepsize))
+            stepsize /= beta
+            if stepsize < 1e-300:
+                raise _exceptions.NotConvergedError("mesh update", "no admissible step size")
+        return stepsize
+
+    def compute_a_priori_decreases(self, search_direction: torch.Tensor, stepsize: float) -> int:
+        return self.mesh_handler.compute_decreases(search_direction, stepsize)
+
+    def requires_remeshing(self) -> bool:
+        return bool(self.mesh_handler.current_mesh_quality < self.mesh_handler.mesh_quality_tol_upper)
+
+
+class ArmijoLineSearch:
+    """Armijo backtracking (``armijo_line_search.py:36-245``)."""
+
+    def __init__(self, problem) -> None:
+        self.problem = problem
+        cfg = problem.config
+        self.config = cfg
+        self.form_handler = problem.form_handler
+        self.ova = problem.optimization_variable_abstractions
+        self.cost_functional = problem.reduced_cost_functional
+        self.state_problem = problem.state_problem
+        self.epsilon_armijo = cfg.getfloat("LineSearch", "epsilon_armijo")
+        self.beta_armijo = cfg.getfloat("LineSearch", "beta_armijo")
+        self.stepsize = cfg.getfloat("LineSearch", "initial_stepsize")
+        self.safeguard_stepsize = cfg.getboolean("LineSearch", "safeguard_stepsize")
+        self.armijo_stepsize_initial = self.stepsize
+        self.search_direction_inf = 1.0
+        self.decrease_measure_w_o_step = 1.0
+        self.log: list[tuple[str, float]] = []
+
+    def initialize_stepsize(self, solver, search_direction: torch.Tensor, has_curvature_info: bool) -> None:
+        """``line_search.py:152-214``."""
+        self.search_direction_inf = float(search_direction.abs().max().item())
+        if self.problem.mesh.dist is not None:
+            t = torch.tensor([self.search_direction_inf], dtype=torch.float64, device=search_direction.device)
+            self.problem.mesh.dist.allreduce(t, "max")
+            self.search_direction_inf = float(t.item())
+        if has_curvature_info:
+            self.stepsize = 1.0
+        num_decreases = self.ova.compute_a_priori_decreases(search_direction, self.stepsize)
+        self.stepsize /= pow(self.beta_armijo, num_decreases)
+        if self.safeguard_stepsize and solver.iteration == 0:
+            nrm = np.sqrt(self.form_handler.scalar_product(search_direction, search_direction))
+            self.stepsize = float(np.minimum(self.stepsize, 100.0 / (1.0 + nrm)))
+
+    def _check_for_nonconvergence(self, solver) -> bool:
+        """``armijo_line_search.py:59-94``."""
+        if solver.iteration >= solver.max_iter:
+            return True
+        if self.stepsize * self.search_direction_inf <= 1e-9:
+            solver.line_search_broken = True
+            return True
+        if self.stepsize / self.armijo_stepsize_initial <= 1e-9:
+            solver.line_search_broken = True
+            return True
+        return False
+
+    def search(self, solver, search_direction: torch.Tensor, has_curvature_info: bool):
+        """``armijo_line_search.py:97-202``; returns the accepted deformation or None."""
+        self.initialize_stepsize(solver, search_direction, has_curvature_info)
+        while True:
+            if self._check_for_nonconvergence(solver):
+                self.log.append(("fail_stepsize", self.stepsize))
+                return None
+            self.decrease_measure_w_o_step = self.ova.compute_decrease_measure(search_direction)
+            n0 = len(self.ova.decisions)
+            self.stepsize = self.ova.update_optimization_variables(search_direction, self.stepsize, self.beta_armijo)
+            self.log.extend(self.ova.decisions[n0:])
+            current_function_value = solver.objective_value
+            objective_step = self._compute_objective_at_new_iterate(current_function_value)
+            decrease_measure = self.decrease_measure_w_o_step * self.stepsize
+            if objective_step < current_function_value + self.epsilon_armijo * decrease_measure:
+                self.log.append(("armijo_accept", self.stepsize))
+                if solver.iteration == 0:
+                    self.armijo_stepsize_initial = self.stepsize
+                break
+            self.log.append(("armijo_reject", self.stepsize))
+            self.stepsize /= self.beta_armijo
+            self.ova.revert_variable_update()
+        solver.stepsize = self.stepsize
+        if not has_curvature_info:
+            self.stepsize *= self.beta_armijo
+        return self.ova.deformation
+
+    def _compute_objective_at_new_iterate(self, current_function_value: float) -> float:
+        """``armijo_line_search.py:225-245``: failed state solve -> J = 2|J| and state revert."""
+        self.state_problem.has_solution = False
+        try:
+            return self.cost_functional.evaluate()
+        except (_exceptions.PETScError, _exceptions.NotConvergedError):
+            if self.config.getboolean("LineSearch", "fail_if_not_converged"):
+                raise
+            self.state_problem.revert_to_checkpoint()
+            return 2.0 * abs(current_function_value)
+
+    def perform(self, solver, search_direction, has_curvature_info):
+        """``line_search.py:95-150``: search, then ``post_line_search`` (scalar product update)."""
+        deformation = self.search(solver, search_direction, has_curvature_info)
+        if deformation is not None:
+            self.form_handler.update_scalar_product()  # line_search.py:247-249
+        return deformation

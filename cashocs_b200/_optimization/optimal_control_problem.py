@@ -1,0 +1,75 @@
+"""``OptimalControlProblem`` (``cashocs/_optimization/optimal_control/optimal_control_problem.py:64-90``).
+
+Distributed-control Poisson problems: ``F = kappa grad y.grad p + c y p - s u p``,
+``J = 1/2|y - y_d|^2 + alpha/2 |u|^2``; ``compute_gradient`` (``:427-439``) returns the L2 Riesz
+representative ``M g = alpha M u - s M p``.
+"""
+
+from __future__ import annotations
+
+import copy
+
+from cashocs_b200 import _exceptions
+from cashocs_b200._forms import forms
+from cashocs_b200._optimization import cost_functional
+from cashocs_b200._pde_problems import adjoint_problem
+from cashocs_b200._pde_problems import control_gradient_problem
+from cashocs_b200._pde_problems import state_problem
+from cashocs_b200._utils import linalg
+from cashocs_b200.io import config as config_module
+
+
+def _enlist(x):
+    return list(x) if isinstance(x, (list, tuple)) else [x]
+
+
+class OptimalControlProblem:
+    def __init__(self, state_forms, bcs_list, cost_functional_form, states, controls, adjoints, config=None,
+                 ksp_options=None, adjoint_ksp_options=None, gradient_ksp_options=None, linear_solver=None,
+                 adjoint_linear_solver=None) -> None:
+        self.state_forms = _enlist(state_forms)
+        self.states, self.controls, self.adjoints = _enlist(states), _enlist(controls), _enlist(adjoints)
+        if not (len(self.states) == len(self.adjoints) == len(self.state_forms) == 1 and len(self.controls) == 1):
+            raise _exceptions.InputError("cashocs_b200.OptimalControlProblem", "states",
+                                         "one state / control / adjoint is on the hot path")
+        bcs_list = _enlist(bcs_list) if bcs_list is not None else []
+        self.bcs_list = [bcs_list] if (not bcs_list or isinstance(bcs_list[0], forms.DirichletBC)) else bcs_list
+        self.cost = cost_functional_form
+        self.mesh = self.states[0].mesh
+        self.config = config if config is not None else config_module.Config()
+        self.config.validate_config()
+        if self.state_forms[0].source is not self.controls[0]:
+            raise _exceptions.InputError("cashocs_b200.OptimalControlProblem", "state_forms",
+                                         "the control must be the source term of the state equation")
+        norm = lambda o: [copy.deepcopy(linalg.direct_ksp_options)] if o is None else _enlist(o)  # noqa: E731
+        self.ksp_options = norm(ksp_options)
+        self.adjoint_ksp_options = norm(adjoint_ksp_options)
+        self.mesh.build_pattern()
+        self.gradient = forms.Function(self.mesh, 1, "gradient")
+        self.state_problem = state_problem.StateProblem(
+            self.mesh, self.state_forms, self.bcs_list, self.states, self.ksp_options, self.config, linear_solver)
+        self.adjoint_problem = adjoint_problem.AdjointProblem(
+            self.mesh, self.state_forms, self.bcs_list, self.cost, self.states, self.adjoints, self.state_problem,
+            self.adjoint_ksp_options, adjoint_linear_solver)
+        self.gradient_problem = control_gradient_problem.ControlGradientProblem(
+            self.mesh, self.cost, self.state_forms[0], self.controls[0], self.adjoints[0], self.gradient,
+            self.state_problem, self.adjoint_problem, self.config,
+            None if gradient_ksp_options is None else _enlist(gradient_ksp_options)[0])
+        self.reduced_cost_functional = cost_functional.ReducedCostFunctional(
+            self.mesh, self.cost, self.states, self.state_problem, self.controls[0],
+            self.gradient_problem.scalar_product)
+
+    def compute_state_variables(self) -> None:
+        self.state_problem.solve()
+
+    def compute_adjoint_variables(self) -> None:
+        self.state_problem.solve()
+        self.adjoint_problem.solve()
+
+    def compute_gradient(self):
+        return self.gradient_problem.solve()
+
+    def _erase_pde_memory(self) -> None:
+        self.state_problem.has_solution = False
+        self.adjoint_problem.has_solution = False
+        self.gradient_problem.has_solution = False

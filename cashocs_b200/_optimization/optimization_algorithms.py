@@ -1,0 +1,163 @@
+"""Optimisation algorithms driving the hot path (``cashocs/_optimization/optimization_algorithms/``).
+
+Gradient descent (``gradient_descent.py:28-60``) and L-BFGS with the two-loop recursion
+(``l_bfgs.py:91-300``); every inner product is ``form_handler.scalar_product`` (= fused SpMV + dot
+on the device), vectors never leave HBM.  Convergence test and ascent check follow
+``optimization_algorithm.py:281-331``.
+"""
+
+from __future__ import annotations
+
+import collections
+
+import numpy as np
+import torch
+
+
+class OptimizationAlgorithm:
+    def __init__(self, problem, line_search) -> None:
+        self.problem = problem
+        self.line_search = line_search
+        cfg = problem.config
+        self.config = cfg
+        self.form_handler = problem.form_handler
+        self.gradient_problem = problem.gradient_problem
+        self.adjoint_problem = problem.adjoint_problem
+        self.state_problem = problem.state_problem
+        self.cost_functional = problem.reduced_cost_functional
+        self.ova = problem.optimization_variable_abstractions
+        self.gradient = problem.gradient.vector
+        self.search_direction = torch.zeros_like(self.gradient)
+        self.rtol = cfg.getfloat("OptimizationRoutine", "rtol")
+        self.atol = cfg.getfloat("OptimizationRoutine", "atol")
+        self.max_iter = cfg.getint("OptimizationRoutine", "max_iter")
+        self.iteration = 0
+        self.objective_value = 1.0
+        self.gradient_norm = 1.0
+        self.gradient_norm_initial = 1.0
+        self.relative_norm = 1.0
+        self.stepsize = 1.0
+        self.converged = False
+        self.line_search_broken = False
+        self.has_curvature_info = False
+        self.history: list[dict] = []
+
+    def compute_gradient(self) -> None:
+        self.adjoint_problem.has_solution = False
+        self.gradient_problem.has_solution = False
+        self.gradient_problem.solve()
+
+    def evaluate_cost_functional(self) -> None:
+        self.objective_value = self.cost_functional.evaluate()
+
+    def convergence_test(self) -> bool:
+        if self.iteration == 0:
+            self.gradient_norm_initial = self.gradient_norm
+        self.relative_norm = self.gradient_norm / self.gradient_norm_initial if self.gradient_norm > 0.0 else 0.0
+        if self.gradient_norm <= self.atol + self.rtol * self.gradient_norm_initial:
+            self.objective_value = self.cost_functional.evaluate()
+            self.converged = True
+            return True
+        return False
+
+    def check_for_ascent(self) -> None:
+        if self.form_handler.scalar_product(self.gradient, self.search_direction) >= 0:
+            torch.neg(self.gradient, out=self.search_direction)
+            self.has_curvature_info = False
+
+    def nonconvergence(self) -> bool:
+        return self.iteration >= self.max_iter or self.line_search_broken
+
+    def _record(self) -> None:
+        self.history.append(
+            dict(iteration=self.iteration, objective_value=self.objective_value, relative_norm=self.relative_norm,
+                 gradient_norm=self.gradient_norm, mesh_quality=getattr(self.problem.mesh_handler, "current_mesh_quality", None),
+                 stepsize=self.stepsize)
+        )
+
+
+class GradientDescentMethod(OptimizationAlgorithm):
+    def run(self) -> None:
+        while True:
+            self.compute_gradient()
+            self.gradient_norm = self.ova.compute_gradient_norm()
+            if self.convergence_test():
+                self._record()
+                break
+            self.evaluate_cost_functional()
+            self._record()
+            torch.neg(self.gradient, out=self.search_direction)
+            self.line_search.perform(self, self.search_direction, self.has_curvature_info)
+            self.iteration += 1
+            if self.nonconvergence():
+                break
+
+
+class LBFGSMethod(OptimizationAlgorithm):
+    def __init__(self, problem, line_search) -> None:
+        super().__init__(problem, line_search)
+        self.bfgs_memory_size = self.config.getint("AlgoLBFGS", "bfgs_memory_size")
+        self.use_bfgs_scaling = self.config.getboolean("AlgoLBFGS", "use_bfgs_scaling")
+        self.history_s: collections.deque = collections.deque()
+        self.history_y: collections.deque = collections.deque()
+        self.history_rho: collections.deque = collections.deque()
+        self.gradient_prev = torch.zeros_like(self.gradient)
+
+    def compute_search_direction(self) -> None:
+        sp = self.form_handler.scalar_product
+        d = self.search_direction
+        if self.bfgs_memory_size > 0 and len(self.history_s) > 0:
+            d.copy_(self.gradient)
+            alphas = []
+            for s, y, rho in zip(self.history_s, self.history_y, self.history_rho):
+                a = rho * sp(s, d)
+                alphas.append(a)
+                d.add_(y, alpha=-a)
+            if self.use_bfgs_scaling and self.iteration > 0:
+                d.mul_(sp(self.history_y[0], self.history_s[0]) / sp(self.history_y[0], self.history_y[0]))
+            m = len(self.history_s)
+            for i in range(m):
+                b = self.history_rho[-1 - i] * sp(self.history_y[-1 - i], d)
+                d.add_(self.history_s[-1 - i], alpha=alphas[-1 - i] - b)
+            d.neg_()
+        else:
+            torch.neg(self.gradient, out=d)
+
+    def update_hessian_approximation(self) -> None:
+        if self.bfgs_memory_size <= 0:
+            return
+        y_k = self.gradient - self.gradient_prev
+        s_k = self.stepsize * self.search_direction
+        curvature = self.form_handler.scalar_product(y_k, s_k)
+        self.history_y.appendleft(y_k)
+        self.history_s.appendleft(s_k)
+        if curvature <= 0.0:
+            self.has_curvature_info = False
+            self.history_s.clear(), self.history_y.clear(), self.history_rho.clear()
+        else:
+            self.has_curvature_info = True
+            self.history_rho.appendleft(1.0 / curvature)
+        if len(self.history_s) > self.bfgs_memory_size:
+            self.history_s.pop(), self.history_y.pop(), self.history_rho.pop()
+
+    def run(self) -> None:
+        self.compute_gradient()
+        self.gradient_norm = self.ova.compute_gradient_norm()
+        self.converged = self.convergence_test()
+        while not self.converged:
+            self.compute_search_direction()
+            self.check_for_ascent()
+            self.evaluate_cost_functional()
+            self._record()
+            self.line_search.perform(self, self.search_direction, self.has_curvature_info)
+            self.iteration += 1
+            if self.nonconvergence():
+                break
+            self.gradient_prev.copy_(self.gradient)
+            self.compute_gradient()
+            self.gradient_norm = self.ova.compute_gradient_norm()
+            self.relative_norm = self.gradient_norm / self.gradient_norm_initial
+            if self.convergence_test():
+                break
+            self.update_hessian_approximation()
+        self._record()

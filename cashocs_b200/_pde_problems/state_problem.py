@@ -1,0 +1,74 @@
+"""State system (``cashocs/_pde_problems/state_problem.py``), linear branch ``:142-172``."""
+
+from __future__ import annotations
+
+import torch
+
+from cashocs_b200 import _exceptions
+from cashocs_b200._forms import expressions
+from cashocs_b200._forms import forms
+from cashocs_b200._pde_problems import pde_problem
+from cashocs_b200._utils import linalg
+
+
+class StateProblem(pde_problem.PDEProblem):
+    """Assemble + solve the (linear) state equation for every state variable."""
+
+    def __init__(self, mesh, state_forms, bcs_list, states, ksp_options, config, linear_solver=None) -> None:
+        super().__init__(linear_solver)
+        self.mesh = mesh
+        self.state_forms = state_forms
+        self.bcs_list = bcs_list
+        self.states = states
+        self.ksp_options = ksp_options
+        self.config = config
+        if not config.getboolean("StateSystem", "is_linear"):
+            raise _exceptions.InputError(
+                "cashocs_b200.StateProblem", "config",
+                "only linear state systems are on the B200 hot path: set [StateSystem] is_linear = True "
+                "(nonlinear solvers are SURVEY.md 8f row 1).",
+            )
+        self.number_of_solves = 0
+        self.iterations = [0] * len(states)
+        # tensors preallocated once, like A_tensors / b_tensors (state_problem.py:101-108)
+        self.A_tensors = [linalg.Matrix(mesh, 1) for _ in states]
+        self.b_tensors = [torch.zeros(mesh.n_owned_vertices, dtype=torch.float64, device=mesh.device) for _ in states]
+        self.bc_arrays = [forms.bc_flag_arrays(mesh, bcs, 1) for bcs in bcs_list]
+        self._checkpoint = None
+
+    def _generate_checkpoint(self) -> None:
+        """``state_problem.py:252-258``."""
+        self._checkpoint = [y.vector.clone() for y in self.states]
+
+    def revert_to_checkpoint(self) -> None:
+        """``state_problem.py:260-274``."""
+        if self._checkpoint is not None:
+            for y, c in zip(self.states, self._checkpoint):
+                y.vector.copy_(c)
+
+    def assemble(self, i: int):
+        form = self.state_forms[i]
+        flag, val = self.bc_arrays[i]
+        src = form.source
+        kw = {}
+        if isinstance(src, expressions.Polynomial):
+            kw = dict(f_poly=src, f_poly_scale=form.source_scale)
+        elif isinstance(src, forms.Function):
+            kw = dict(f_nodal=src.vector, f_nodal_scale=form.source_scale)
+        return linalg.assemble_scalar_system(
+            self.mesh, form.kappa, form.reaction, bc_flag=flag, bc_val=val,
+            A=self.A_tensors[i], b=self.b_tensors[i], **kw,
+        )
+
+    def solve(self):
+        if not self.has_solution:
+            self._generate_checkpoint()
+            for i in range(len(self.states)):
+                A, b = self.assemble(i)
+                res = self.linear_solver.solve(self.states[i].vector, A=A, b=b, ksp_options=self.ksp_options[i])
+                self.iterations[i] = res.its
+                if self.mesh.dist is not None:
+                    self.mesh.dist.halo_exchange(self.states[i].vector, 1)
+            self.has_solution = True
+            self.number_of_solves += 1
+        return self.states

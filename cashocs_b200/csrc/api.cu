@@ -1,0 +1,36 @@
+// Error reporting and device queries of the C-ABI.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace cb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  cached = n;
+  return n;
+}
+
+}  // namespace cb
+
+extern "C" const char* cb_last_error(void) { return cb::g_err; }
+extern "C" int cb_version(void) { return 100; }
+extern "C" int cb_num_sms(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cb::set_error("no CUDA device"); return CB_ERR_CUDA; }
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cb::set_error("cudaDeviceGetAttribute failed"); return CB_ERR_CUDA; }
+  return n;
+}

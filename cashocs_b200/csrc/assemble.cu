@@ -1,0 +1,385 @@
+// Cell-batched P1 element kernels with precomputed cell->nnz scatter maps.
+//
+// Replaces the dolfin cell loop behind assemble_petsc_system
+// (cashocs/_utils/linalg.py:107-188 -> fenics.assemble_system), SystemAssembler.assemble
+// (cashocs/_forms/shape_form_handler.py:737, cashocs/_pde_problems/shape_gradient_problem.py:142)
+// and the FFC-generated tabulate_tensor kernels.  One thread = one cell.  Cells arrive
+// colour-sorted; cells of one colour share no dof, so the read-modify-write scatter into the
+// CSR values needs no atomics and the summation order (colour 0, 1, 2, ...) is fixed: results
+// are bit-reproducible run to run.
+#include "common.cuh"
+
+namespace cb {
+
+template <int D>
+struct CellData {
+  int v[D + 1];
+  double x[D + 1][D];
+  Geo<D> g;
+};
+
+template <int D>
+__device__ __forceinline__ void load_cell_data(const int32_t* __restrict__ cells,
+                                               const double* __restrict__ coords, int64_t c,
+                                               CellData<D>& cd) {
+  load_cell<D>(cells, c, cd.v);
+  load_coords<D>(coords, cd.v, cd.x);
+  simplex_geometry(cd.x, cd.g);
+}
+
+// ------------------------------------------------------------------ scalar P1
+template <int D>
+__global__ void __launch_bounds__(128)
+k_assemble_scalar(int64_t c_begin, int64_t c_end, const int32_t* __restrict__ cells,
+                  const int32_t* __restrict__ cell2nnz, const double* __restrict__ coords,
+                  int64_t nrows_owned, double c_stiff, double c_mass, double s_poly, cb_poly f,
+                  cb_quad q, double s_nodal, const double* __restrict__ fnodal,
+                  const uint8_t* __restrict__ bc_flag, const double* __restrict__ bc_val,
+                  double* __restrict__ val, double* __restrict__ rhs) {
+  constexpr int K = D + 1;
+  constexpr double MREF = 1.0 / ((D + 1) * (D + 2));
+  for (int64_t c = c_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < c_end;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    CellData<D> cd;
+    load_cell_data<D>(cells, coords, c, cd);
+    const double vol = cd.g.vol;
+    double Ae[K][K];
+    double be[K];
+    bool isbc[K];
+    double gbc[K];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+      be[a] = 0.0;
+      isbc[a] = bc_flag ? (bc_flag[cd.v[a]] != 0) : false;
+      gbc[a] = isbc[a] ? bc_val[cd.v[a]] : 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+#pragma unroll
+      for (int b = 0; b < K; ++b) {
+        double gg = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) gg += cd.g.G[a][i] * cd.g.G[b][i];
+        Ae[a][b] = vol * (c_stiff * gg + c_mass * (a == b ? 2.0 * MREF : MREF));
+      }
+    }
+    if (rhs) {
+      if (s_poly != 0.0) {
+        double acc[K];
+#pragma unroll
+        for (int a = 0; a < K; ++a) acc[a] = 0.0;
+        for (int iq = 0; iq < q.nq; ++iq) {
+          double xq[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+          for (int a = 0; a < K; ++a) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) xq[i] += q.lam[iq][a] * cd.x[a][i];
+          }
+          const double fw = poly_eval(f, xq[0], xq[1], xq[2]) * q.w[iq];
+#pragma unroll
+          for (int a = 0; a < K; ++a) acc[a] += fw * q.lam[iq][a];
+        }
+#pragma unroll
+        for (int a = 0; a < K; ++a) be[a] += s_poly * vol * acc[a];
+      }
+      if (s_nodal != 0.0) {
+        double fe[K], fsum = 0.0;
+#pragma unroll
+        for (int a = 0; a < K; ++a) { fe[a] = fnodal[cd.v[a]]; fsum += fe[a]; }
+#pragma unroll
+        for (int a = 0; a < K; ++a) be[a] += s_nodal * vol * MREF * (fsum + fe[a]);
+      }
+    }
+    // symmetric Dirichlet elimination on the element tensor (dolfin SystemAssembler)
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+      double lift = 0.0;
+#pragma unroll
+      for (int b = 0; b < K; ++b) lift += Ae[a][b] * gbc[b];
+      be[a] = isbc[a] ? gbc[a] : be[a] - lift;
+    }
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+#pragma unroll
+      for (int b = 0; b < K; ++b) {
+        if (isbc[a] || isbc[b]) Ae[a][b] = (a == b) ? 1.0 : 0.0;
+      }
+    }
+    if (val) {
+      const int32_t* c2n = cell2nnz + c * (K * K);
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+          const int32_t pos = __ldg(c2n + a * K + b);
+          if (pos >= 0) val[pos] += Ae[a][b];
+        }
+      }
+    }
+    if (rhs) {
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        if (cd.v[a] < nrows_owned) rhs[cd.v[a]] += be[a];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ vector P1 elasticity
+template <int D>
+__global__ void __launch_bounds__(128)
+k_assemble_elasticity(int64_t c_begin, int64_t c_end, const int32_t* __restrict__ cells,
+                      const int32_t* __restrict__ cell2nnz, const double* __restrict__ coords,
+                      const double* __restrict__ mu, double lambda_lame, double damping,
+                      const double* __restrict__ cell_scale, const uint8_t* __restrict__ bc_flag,
+                      double* __restrict__ val) {
+  constexpr int K = D + 1;
+  constexpr double MREF = 1.0 / ((D + 1) * (D + 2));
+  for (int64_t c = c_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < c_end;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    CellData<D> cd;
+    load_cell_data<D>(cells, coords, c, cd);
+    double mubar = 0.0;
+#pragma unroll
+    for (int a = 0; a < K; ++a) mubar += mu[cd.v[a]];
+    mubar *= (1.0 / K);
+    const double scale = cell_scale ? cell_scale[c] : 1.0;
+    const double vol = cd.g.vol;
+    const double vm = scale * vol * mubar, vl = scale * vol * lambda_lame, dm = scale * damping * vol * MREF;
+    unsigned bcmask = 0;  // bit a*D+i
+    if (bc_flag) {
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          if (bc_flag[(int64_t)cd.v[a] * D + i]) bcmask |= 1u << (a * D + i);
+        }
+      }
+    }
+    const int32_t* c2n = cell2nnz + c * (K * K);
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+#pragma unroll
+      for (int b = 0; b < K; ++b) {
+        const int32_t pos = __ldg(c2n + a * K + b);
+        if (pos < 0) continue;
+        double gg = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) gg += cd.g.G[a][i] * cd.g.G[b][i];
+        const double mass = (a == b) ? 2.0 * dm : dm;
+        double* blk = val + (int64_t)pos * (D * D);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            double e = vm * cd.g.G[a][j] * cd.g.G[b][i] + vl * cd.g.G[a][i] * cd.g.G[b][j];
+            if (i == j) e += vm * gg + mass;
+            if ((bcmask >> (a * D + i)) & 1u || (bcmask >> (b * D + j)) & 1u)
+              e = (a == b && i == j) ? 1.0 : 0.0;
+            blk[i * D + j] += e;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ shape derivative (Poisson, J = c * int u)
+template <int D>
+__global__ void __launch_bounds__(128)
+k_shape_derivative_poisson(int64_t c_begin, int64_t c_end, const int32_t* __restrict__ cells,
+                           const double* __restrict__ coords, int64_t nrows_owned,
+                           const double* __restrict__ u, const double* __restrict__ p, cb_poly f,
+                           cb_poly gf0, cb_poly gf1, cb_poly gf2, cb_quad q, double c_int_u,
+                           const uint8_t* __restrict__ bc_flag, double* __restrict__ rhs) {
+  constexpr int K = D + 1;
+  for (int64_t c = c_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < c_end;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    CellData<D> cd;
+    load_cell_data<D>(cells, coords, c, cd);
+    const double vol = cd.g.vol;
+    double ue[K], pe[K], usum = 0.0;
+#pragma unroll
+    for (int a = 0; a < K; ++a) { ue[a] = u[cd.v[a]]; pe[a] = p[cd.v[a]]; usum += ue[a]; }
+    double gu[D], gp[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      gu[i] = 0.0; gp[i] = 0.0;
+#pragma unroll
+      for (int a = 0; a < K; ++a) { gu[i] += ue[a] * cd.g.G[a][i]; gp[i] += pe[a] * cd.g.G[a][i]; }
+    }
+    double gugp = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) gugp += gu[i] * gp[i];
+    // quadrature: int f p  and  int (d_i f) phi_a p
+    double int_fp = 0.0;
+    double igf[K][D];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) igf[a][i] = 0.0;
+    }
+    for (int iq = 0; iq < q.nq; ++iq) {
+      double xq[3] = {0.0, 0.0, 0.0};
+      double pq = 0.0;
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        pq += q.lam[iq][a] * pe[a];
+#pragma unroll
+        for (int i = 0; i < D; ++i) xq[i] += q.lam[iq][a] * cd.x[a][i];
+      }
+      const double wp = q.w[iq] * pq;
+      int_fp += wp * poly_eval(f, xq[0], xq[1], xq[2]);
+      double gfq[3];
+      gfq[0] = poly_eval(gf0, xq[0], xq[1], xq[2]);
+      gfq[1] = poly_eval(gf1, xq[0], xq[1], xq[2]);
+      gfq[2] = (D == 3) ? poly_eval(gf2, xq[0], xq[1], xq[2]) : 0.0;
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) igf[a][i] += wp * q.lam[iq][a] * gfq[i];
+      }
+    }
+    const double s0 = c_int_u * vol * usum * (1.0 / K) + vol * gugp - vol * int_fp;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+      if (cd.v[a] >= nrows_owned) continue;
+      double Ggu = 0.0, Ggp = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) { Ggu += cd.g.G[a][i] * gu[i]; Ggp += cd.g.G[a][i] * gp[i]; }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double e = cd.g.G[a][i] * s0 - vol * (Ggu * gp[i] + Ggp * gu[i]) - vol * igf[a][i];
+        const int64_t dof = (int64_t)cd.v[a] * D + i;
+        if (bc_flag && bc_flag[dof]) e = 0.0;
+        rhs[dof] += e;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ ident_zeros
+__global__ void k_ident_zeros(int64_t nrows, int bs, const int64_t* __restrict__ rowptr,
+                              const int32_t* __restrict__ col, double* __restrict__ val,
+                              unsigned long long* __restrict__ n_fixed) {
+  const int64_t total = nrows * bs;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < total;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t br = r / bs;
+    const int i = (int)(r - br * bs);
+    double s = 0.0;
+    int64_t dpos = -1;
+    for (int64_t k = rowptr[br]; k < rowptr[br + 1]; ++k) {
+      for (int j = 0; j < bs; ++j) s += fabs(val[(k * bs + i) * bs + j]);
+      if (col[k] == br) dpos = k;
+    }
+    if (s < 3.0e-16 && dpos >= 0) {
+      val[(dpos * bs + i) * bs + i] = 1.0;
+      if (n_fixed) atomicAdd(n_fixed, 1ULL);
+    }
+  }
+}
+
+template <typename F>
+int for_each_colour(const cb_mesh_view* m, F&& launch) {
+  for (int c = 0; c < m->ncolours; ++c) {
+    const int64_t b = m->colour_off[c], e = m->colour_off[c + 1];
+    if (e <= b) continue;
+    const int grid = grid_for(e - b, 128, 12);
+    launch(b, e, grid);
+    CB_LAUNCH_CHECK();
+  }
+  return CB_OK;
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+static int check_view(const cb_mesh_view* m) {
+  CB_REQUIRE(m != nullptr, "mesh view is NULL");
+  CB_REQUIRE(m->dim == 2 || m->dim == 3, "dim must be 2 or 3");
+  CB_REQUIRE(m->ncolours > 0 && m->colour_off != nullptr, "colour offsets missing");
+  CB_REQUIRE(m->cells && m->coords, "cells / coords missing");
+  return CB_OK;
+}
+
+extern "C" int cb_assemble_scalar(void* stream, const cb_mesh_view* m, double c_stiff,
+                                  double c_mass, double s_poly, const cb_poly* f, const cb_quad* q,
+                                  double s_nodal, const double* fnodal, const uint8_t* bc_flag,
+                                  const double* bc_val, double* val, double* rhs) {
+  if (int e = check_view(m)) return e;
+  CB_REQUIRE(val == nullptr || m->cell2nnz != nullptr, "cell2nnz missing");
+  CB_REQUIRE(s_poly == 0.0 || (f && q), "polynomial source needs f and a quadrature rule");
+  CB_REQUIRE(s_nodal == 0.0 || fnodal, "nodal source missing");
+  CB_REQUIRE(bc_flag == nullptr || bc_val != nullptr, "bc_val missing");
+  cudaStream_t s = as_stream(stream);
+  if (val) CB_CUDA_CHECK(cudaMemsetAsync(val, 0, sizeof(double) * m->nnz, s));
+  if (rhs) CB_CUDA_CHECK(cudaMemsetAsync(rhs, 0, sizeof(double) * m->nrows_owned, s));
+  cb_poly fz;
+  memset(&fz, 0, sizeof(fz));
+  cb_quad qz;
+  memset(&qz, 0, sizeof(qz));
+  const cb_poly& ff = f ? *f : fz;
+  const cb_quad& qq = q ? *q : qz;
+  return for_each_colour(m, [&](int64_t b, int64_t e, int grid) {
+    if (m->dim == 2)
+      k_assemble_scalar<2><<<grid, 128, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, m->nrows_owned,
+                                               c_stiff, c_mass, s_poly, ff, qq, s_nodal, fnodal,
+                                               bc_flag, bc_val, val, rhs);
+    else
+      k_assemble_scalar<3><<<grid, 128, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, m->nrows_owned,
+                                               c_stiff, c_mass, s_poly, ff, qq, s_nodal, fnodal,
+                                               bc_flag, bc_val, val, rhs);
+  });
+}
+
+extern "C" int cb_assemble_elasticity(void* stream, const cb_mesh_view* m, const double* mu,
+                                      double lambda_lame, double damping, const double* cell_scale,
+                                      const uint8_t* bc_flag, double* val) {
+  if (int e = check_view(m)) return e;
+  CB_REQUIRE(m->cell2nnz && mu && val, "cell2nnz / mu / val missing");
+  cudaStream_t s = as_stream(stream);
+  CB_CUDA_CHECK(cudaMemsetAsync(val, 0, sizeof(double) * m->nnz * m->dim * m->dim, s));
+  return for_each_colour(m, [&](int64_t b, int64_t e, int grid) {
+    if (m->dim == 2)
+      k_assemble_elasticity<2><<<grid, 128, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, mu,
+                                                   lambda_lame, damping, cell_scale, bc_flag, val);
+    else
+      k_assemble_elasticity<3><<<grid, 128, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, mu,
+                                                   lambda_lame, damping, cell_scale, bc_flag, val);
+  });
+}
+
+extern "C" int cb_assemble_shape_derivative_poisson(void* stream, const cb_mesh_view* m,
+                                                    const double* u, const double* p,
+                                                    const cb_poly* f, const cb_poly* gradf,
+                                                    const cb_quad* q, double c_int_u,
+                                                    const uint8_t* bc_flag, double* rhs) {
+  if (int e = check_view(m)) return e;
+  CB_REQUIRE(u && p && f && gradf && q && rhs, "missing argument");
+  cudaStream_t s = as_stream(stream);
+  CB_CUDA_CHECK(cudaMemsetAsync(rhs, 0, sizeof(double) * m->nrows_owned * m->dim, s));
+  cb_poly gz;
+  memset(&gz, 0, sizeof(gz));
+  return for_each_colour(m, [&](int64_t b, int64_t e, int grid) {
+    if (m->dim == 2)
+      k_shape_derivative_poisson<2><<<grid, 128, 0, s>>>(b, e, m->cells, m->coords, m->nrows_owned, u, p,
+                                                        *f, gradf[0], gradf[1], gz, *q, c_int_u,
+                                                        bc_flag, rhs);
+    else
+      k_shape_derivative_poisson<3><<<grid, 128, 0, s>>>(b, e, m->cells, m->coords, m->nrows_owned, u, p,
+                                                        *f, gradf[0], gradf[1], gradf[2], *q, c_int_u,
+                                                        bc_flag, rhs);
+  });
+}
+
+extern "C" int cb_ident_zeros(void* stream, int64_t nrows, int bs, const int64_t* rowptr,
+                              const int32_t* col, double* val, int64_t* n_fixed) {
+  cudaStream_t s = as_stream(stream);
+  if (n_fixed) CB_CUDA_CHECK(cudaMemsetAsync(n_fixed, 0, sizeof(int64_t), s));
+  k_ident_zeros<<<grid_for(nrows * bs, 128, 16), 128, 0, s>>>(nrows, bs, rowptr, col, val,
+                                                              (unsigned long long*)n_fixed);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}

@@ -1,0 +1,699 @@
+// Preconditioned Krylov solvers with PETSc KSP semantics, device-resident control flow.
+//
+// Replaces LinearSolver.solve (cashocs/_utils/linalg.py:480-546) -> PETSc KSPSolve for
+// ksp_type in {cg, minres, preonly} and pc_type in {none, jacobi, chebyshev(jacobi)}.
+// Semantics restated from PETSc [third party]: zero initial guess, left preconditioning,
+// preconditioned residual norm, KSPConvergedDefault.
+//
+// All scalars (alpha, beta, norms, iteration count, converged reason) live in a small state
+// block in device memory.  Dot products are fused into the vector / SpMV kernels, reduced
+// deterministically (fixed-order block partials, last-arriving block finalises) and the
+// finalising block also runs the scalar recurrences and the convergence test, so the host
+// only enqueues kernels and polls the state every `check_every` iterations; once `done` is
+// set the remaining enqueued kernels return immediately, so the iterate is exactly the one
+// of the converged iteration.  With a cb_dist the per-rank sums go through one
+// ncclAllReduce per reduction point and a one-thread kernel runs the recurrences.
+#include <math.h>
+
+#include <utility>
+
+#include "spmv.cuh"
+
+namespace cb {
+
+int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
+                  double* result, double* scratch);
+int dist_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs, double* sendbuf);
+int dist_allreduce_sum(cudaStream_t s, cb_dist* d, double* buf, int n);
+int64_t dist_send_len(const cb_dist* d);
+
+struct KspState {
+  // sums[] is the landing zone of the fused reductions (allreduced in place when distributed)
+  double sums[4];
+  double beta, betaold, dpi, bcoef;
+  double rnorm, rnorm0, ttol;
+  double rtol, atol, dtol;
+  // MINRES recurrences
+  double oldb, mbeta, dbar, epsln, phibar, cs, sn, alfa, oldeps, delta, gamma, phi;
+  int its, reason, done, max_it;
+  int hist_len, pad;
+};
+constexpr int STATE_DOUBLES = 64;
+static_assert(sizeof(KspState) <= STATE_DOUBLES * sizeof(double), "state block too small");
+
+__device__ __forceinline__ void converged_default(KspState* st, double rnorm, int it) {
+  if (it == 0) {
+    st->ttol = fmax(st->rtol * rnorm, st->atol);
+    st->rnorm0 = rnorm;
+  }
+  st->rnorm = rnorm;
+  int reason = 0;
+  if (rnorm != rnorm || isinf(rnorm)) reason = CB_KSP_DIVERGED_NANORINF;
+  else if (rnorm <= st->ttol) reason = (rnorm < st->atol) ? CB_KSP_CONVERGED_ATOL : CB_KSP_CONVERGED_RTOL;
+  else if (rnorm >= st->dtol * st->rnorm0) reason = CB_KSP_DIVERGED_DTOL;
+  else if (it >= st->max_it) reason = CB_KSP_DIVERGED_ITS;
+  if (reason) { st->reason = reason; st->done = 1; }
+}
+
+// ---- CG scalar recurrences -------------------------------------------------------------
+// after (z.r, z.z) are known: called at it = 0 (init) and after every x/r update
+__device__ void cg_after_zr(KspState* st, double* hist, int is_init) {
+  const double zr = st->sums[0], zz = st->sums[1];
+  if (!is_init) st->its += 1;
+  st->betaold = st->beta;
+  st->beta = zr;
+  const double rnorm = sqrt(zz);
+  if (hist && st->its < st->hist_len) hist[st->its] = rnorm;
+  converged_default(st, rnorm, st->its);
+  if (st->done) return;
+  // PETSc KSPCG: beta == 0 -> converged (happy breakdown), beta < 0 -> indefinite PC
+  if (zr == 0.0) { st->reason = CB_KSP_CONVERGED_ATOL; st->done = 1; return; }
+  if (zr < 0.0) { st->reason = CB_KSP_DIVERGED_INDEFINITE_PC; st->done = 1; return; }
+  st->bcoef = is_init ? 0.0 : st->beta / st->betaold;
+}
+
+// after p.Ap is known
+__device__ void cg_after_pw(KspState* st) {
+  const double dpi = st->sums[0];
+  st->dpi = dpi;
+  if (dpi != dpi) { st->reason = CB_KSP_DIVERGED_NANORINF; st->done = 1; st->its += 1; }
+  else if (dpi <= 0.0) { st->reason = CB_KSP_DIVERGED_INDEFINITE_MAT; st->done = 1; st->its += 1; }
+}
+
+__global__ void k_state_step(KspState* st, double* hist, int which) {
+  if (st->done) return;
+  if (which == 0) cg_after_zr(st, hist, 1);
+  else if (which == 1) cg_after_zr(st, hist, 0);
+  else if (which == 2) cg_after_pw(st);
+}
+
+// ---- CG vector kernels -----------------------------------------------------------------
+// r = b, x = 0, z = dinv .* r (or r), sums = (z.r, z.z)
+template <bool FINALIZE>
+__global__ void __launch_bounds__(256)
+k_cg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ dinv,
+          double* __restrict__ r, double* __restrict__ z, double* __restrict__ x, bool apply_pc,
+          KspState* st, double* hist, double* scratch) {
+  __shared__ double s_red[66];
+  double zr = 0.0, zz = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = b[i];
+    r[i] = ri;
+    x[i] = 0.0;
+    if (apply_pc) {
+      const double zi = dinv ? dinv[i] * ri : ri;
+      z[i] = zi;
+      zr += zi * ri;
+      zz += zi * zi;
+    }
+  }
+  if (!apply_pc) return;
+  double v[2] = {zr, zz};
+  const int ops[2] = {RED_SUM, RED_SUM};
+  if (grid_reduce<2>(v, ops, scratch, s_red)) {
+    if (threadIdx.x == 0) {
+      st->sums[0] = v[0];
+      st->sums[1] = v[1];
+      if (FINALIZE) cg_after_zr(st, hist, 1);
+    }
+  }
+}
+
+// sums = (z.r, z.z) for an already applied preconditioner
+__global__ void __launch_bounds__(256)
+k_dots_zr(int64_t n, const double* __restrict__ z, const double* __restrict__ r, KspState* st,
+          double* hist, double* scratch, int finalize_mode /* -1 none, 0 init, 1 iter */) {
+  if (st->done) return;
+  __shared__ double s_red[66];
+  double zr = 0.0, zz = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double zi = z[i];
+    zr += zi * r[i];
+    zz += zi * zi;
+  }
+  double v[2] = {zr, zz};
+  const int ops[2] = {RED_SUM, RED_SUM};
+  if (grid_reduce<2>(v, ops, scratch, s_red)) {
+    if (threadIdx.x == 0) {
+      st->sums[0] = v[0];
+      st->sums[1] = v[1];
+      if (finalize_mode >= 0) cg_after_zr(st, hist, finalize_mode == 0);
+    }
+  }
+}
+
+// p = z + bcoef * p
+__global__ void __launch_bounds__(256)
+k_cg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const KspState* st) {
+  if (st->done) return;
+  const double bc = st->bcoef;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = z[i] + bc * p[i];
+}
+
+// w = A p ; sums[0] = p.w
+template <int BS, bool FINALIZE>
+__global__ void __launch_bounds__(SpmvCfg<BS>::THREADS)
+k_cg_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+          const double* __restrict__ val, const double* __restrict__ p, double* __restrict__ w,
+          KspState* st, double* scratch) {
+  if (st->done) return;
+  using C = SpmvCfg<BS>;
+  __shared__ double s_tile[C::TILE_DOUBLES];
+  __shared__ int64_t s_rp[C::R + 1];
+  __shared__ double s_red[33];
+  const int64_t nrb = (nrows + C::R - 1) / C::R;
+  double local = 0.0;
+  for (int64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+    const int64_t row0 = rb * C::R;
+    const int nr = (int)((nrows - row0 < C::R) ? (nrows - row0) : C::R);
+    const double acc = spmv_row_block<BS>(rowptr, col, val, p, row0, nr, s_tile, s_rp);
+    if ((int)threadIdx.x < nr * BS) {
+      const int64_t i = row0 * BS + threadIdx.x;
+      w[i] = acc;
+      local += acc * p[i];
+    }
+  }
+  double v[1] = {local};
+  const int ops[1] = {RED_SUM};
+  if (grid_reduce<1>(v, ops, scratch, s_red)) {
+    if (threadIdx.x == 0) {
+      st->sums[0] = v[0];
+      if (FINALIZE) cg_after_pw(st);
+    }
+  }
+}
+
+// x += a p ; r -= a w ; [z = dinv .* r ; sums = (z.r, z.z)]
+template <bool FINALIZE>
+__global__ void __launch_bounds__(256)
+k_cg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ w,
+        const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
+        double* __restrict__ z, bool fused_jacobi, KspState* st, double* hist, double* scratch) {
+  if (st->done) return;
+  __shared__ double s_red[66];
+  const double a = st->beta / st->dpi;
+  double zr = 0.0, zz = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += a * p[i];
+    const double ri = r[i] - a * w[i];
+    r[i] = ri;
+    if (fused_jacobi) {
+      const double zi = dinv ? dinv[i] * ri : ri;
+      z[i] = zi;
+      zr += zi * ri;
+      zz += zi * zi;
+    }
+  }
+  if (!fused_jacobi) return;
+  double v[2] = {zr, zz};
+  const int ops[2] = {RED_SUM, RED_SUM};
+  if (grid_reduce<2>(v, ops, scratch, s_red)) {
+    if (threadIdx.x == 0) {
+      st->sums[0] = v[0];
+      st->sums[1] = v[1];
+      if (FINALIZE) cg_after_zr(st, hist, 0);
+    }
+  }
+}
+
+// ---- Chebyshev(Jacobi) polynomial preconditioner ------------------------------------------
+// d = dinv .* r / theta ; z = d
+__global__ void __launch_bounds__(256)
+k_cheb_first(int64_t n, const double* __restrict__ r, const double* __restrict__ dinv,
+             double inv_theta, double* __restrict__ d, double* __restrict__ z, const KspState* st) {
+  if (st->done) return;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double di = dinv[i] * r[i] * inv_theta;
+    d[i] = di;
+    z[i] = di;
+  }
+}
+// d = c1 d + c2 dinv .* (r - t) ; z += d
+__global__ void __launch_bounds__(256)
+k_cheb_step(int64_t n, const double* __restrict__ r, const double* __restrict__ t,
+            const double* __restrict__ dinv, double c1, double c2, double* __restrict__ d,
+            double* __restrict__ z, const KspState* st) {
+  if (st->done) return;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double di = c1 * d[i] + c2 * dinv[i] * (r[i] - t[i]);
+    d[i] = di;
+    z[i] += di;
+  }
+}
+
+// ---- MINRES (Paige & Saunders) ------------------------------------------------------------
+__device__ void minres_after_beta(KspState* st, double* hist, int is_init) {
+  const double b2 = st->sums[0];
+  if (b2 < 0.0) { st->reason = CB_KSP_DIVERGED_INDEFINITE_PC; st->done = 1; return; }
+  if (b2 != b2) { st->reason = CB_KSP_DIVERGED_NANORINF; st->done = 1; return; }
+  const double beta = sqrt(b2);
+  if (is_init) {
+    st->oldb = 0.0; st->mbeta = beta; st->dbar = 0.0; st->epsln = 0.0; st->phibar = beta;
+    st->cs = -1.0; st->sn = 0.0; st->its = 0;
+    if (hist && st->hist_len > 0) hist[0] = beta;
+    converged_default(st, beta, 0);
+    return;
+  }
+  st->oldb = st->mbeta;
+  st->mbeta = beta;
+  const double alfa = st->alfa;
+  st->oldeps = st->epsln;
+  st->delta = st->cs * st->dbar + st->sn * alfa;
+  const double gbar = st->sn * st->dbar - st->cs * alfa;
+  st->epsln = st->sn * beta;
+  st->dbar = -st->cs * beta;
+  double gamma = sqrt(gbar * gbar + beta * beta);
+  if (gamma < 2.2250738585072014e-308) gamma = 2.2250738585072014e-308;
+  st->gamma = gamma;
+  st->cs = gbar / gamma;
+  st->sn = beta / gamma;
+  st->phi = st->cs * st->phibar;
+  st->phibar = st->sn * st->phibar;
+  st->its += 1;
+  const double rn = fabs(st->phibar);
+  if (hist && st->its < st->hist_len) hist[st->its] = rn;
+  // the x update of this iteration must still be applied: `done` is raised by k_minres_wx
+  st->rnorm = rn;
+}
+
+__global__ void k_minres_state(KspState* st, double* hist, int which) {
+  if (st->done) return;
+  if (which == 0) minres_after_beta(st, hist, 1);
+  else if (which == 1) minres_after_beta(st, hist, 0);
+  else if (which == 2) st->alfa = st->sums[0];
+}
+
+// r1 = b ; y = dinv .* r1 ; sums[0] = r1.y ; x = 0
+template <bool FINALIZE>
+__global__ void __launch_bounds__(256)
+k_minres_init(int64_t n, const double* __restrict__ b, const double* __restrict__ dinv,
+              double* __restrict__ r2, double* __restrict__ y, double* __restrict__ x,
+              KspState* st, double* hist, double* scratch) {
+  __shared__ double s_red[33];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = b[i];
+    r2[i] = ri;
+    x[i] = 0.0;
+    const double yi = dinv ? dinv[i] * ri : ri;
+    y[i] = yi;
+    s += ri * yi;
+  }
+  double v[1] = {s};
+  const int ops[1] = {RED_SUM};
+  if (grid_reduce<1>(v, ops, scratch, s_red)) {
+    if (threadIdx.x == 0) {
+      st->sums[0] = v[0];
+      if (FINALIZE) minres_after_beta(st, hist, 1);
+    }
+  }
+}
+
+// v = y / beta
+__global__ void __launch_bounds__(256)
+k_minres_v(int64_t n, const double* __restrict__ y, double* __restrict__ v, const KspState* st) {
+  if (st->done) return;
+  const double s = 1.0 / st->mbeta;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    v[i] = s * y[i];
+}
+
+// t = A v - (beta/oldb) r1 ; sums[0] = v.t
+template <int BS, bool FINALIZE>
+__global__ void __launch_bounds__(SpmvCfg<BS>::THREADS)
+k_minres_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+              const double* __restrict__ val, const double* __restrict__ v,
+              const double* __restrict__ r1, double* __restrict__ t, KspState* st,
+              double* scratch) {
+  if (st->done) return;
+  using C = SpmvCfg<BS>;
+  __shared__ double s_tile[C::TILE_DOUBLES];
+  __shared__ int64_t s_rp[C::R + 1];
+  __shared__ double s_red[33];
+  const double c = (st->its >= 1) ? st->mbeta / st->oldb : 0.0;
+  const int64_t nrb = (nrows + C::R - 1) / C::R;
+  double local = 0.0;
+  for (int64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+    const int64_t row0 = rb * C::R;
+    const int nr = (int)((nrows - row0 < C::R) ? (nrows - row0) : C::R);
+    double acc = spmv_row_block<BS>(rowptr, col, val, v, row0, nr, s_tile, s_rp);
+    if ((int)threadIdx.x < nr * BS) {
+      const int64_t i = row0 * BS + threadIdx.x;
+      if (c != 0.0) acc -= c * r1[i];
+      t[i] = acc;
+      local += acc * v[i];
+    }
+  }
+  double vv[1] = {local};
+  const int ops[1] = {RED_SUM};
+  if (grid_reduce<1>(vv, ops, scratch, s_red)) {
+    if (threadIdx.x == 0) {
+      st->sums[0] = vv[0];
+      if (FINALIZE) st->alfa = vv[0];
+    }
+  }
+}
+
+// r2new = t - (alfa/beta) r2 ; ynew = dinv .* r2new ; sums[0] = r2new.ynew
+template <bool FINALIZE>
+__global__ void __launch_bounds__(256)
+k_minres_r(int64_t n, double* __restrict__ t /* becomes r2new */, const double* __restrict__ r2,
+           const double* __restrict__ dinv, double* __restrict__ ynew, KspState* st, double* hist,
+           double* scratch) {
+  if (st->done) return;
+  __shared__ double s_red[33];
+  const double c = st->alfa / st->mbeta;
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = t[i] - c * r2[i];
+    t[i] = ri;
+    const double yi = dinv ? dinv[i] * ri : ri;
+    ynew[i] = yi;
+    s += ri * yi;
+  }
+  double v[1] = {s};
+  const int ops[1] = {RED_SUM};
+  if (grid_reduce<1>(v, ops, scratch, s_red)) {
+    if (threadIdx.x == 0) {
+      st->sums[0] = v[0];
+      if (FINALIZE) minres_after_beta(st, hist, 0);
+    }
+  }
+}
+
+// wnew = (v - oldeps w1 - delta w2) / gamma ; x += phi wnew ; then the convergence test
+__global__ void __launch_bounds__(256)
+k_minres_wx(int64_t n, const double* __restrict__ v, const double* __restrict__ w1 /* also wnew out */,
+            const double* __restrict__ w2, double* __restrict__ wnew, double* __restrict__ x,
+            KspState* st, unsigned int* ticket) {
+  if (st->done) return;
+  const double oldeps = st->oldeps, delta = st->delta, inv_gamma = 1.0 / st->gamma, phi = st->phi;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double wi = (v[i] - oldeps * w1[i] - delta * w2[i]) * inv_gamma;
+    wnew[i] = wi;
+    x[i] += phi * wi;
+  }
+  // last block to finish raises `done` if the recurrence says so (all blocks have read st by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1) converged_default(st, st->rnorm, st->its);
+  }
+}
+
+// x = dinv .* b (preonly + jacobi: DG0 projections, cashocs/geometry/mesh_testing.py:74-81)
+__global__ void __launch_bounds__(256)
+k_diag_solve(int64_t n, const double* __restrict__ b, const double* __restrict__ dinv,
+             double* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = dinv[i] * b[i];
+}
+
+int diag_inv_launch(cudaStream_t s, const cb_mat* A, double* dinv, double* lmax, double* scratch);
+
+struct Solver {
+  cudaStream_t s;
+  const cb_mat* A;
+  cb_dist* dist;
+  int64_t n, nc;
+  int bs;
+  KspState* st;
+  double* hist_dev;
+  double* scratch;
+  double* sendbuf;
+  int vgrid, sgrid;
+
+  template <int BS>
+  int cg_spmv_bs(const double* p, double* w) {
+    if (dist) k_cg_spmv<BS, false><<<sgrid, SpmvCfg<BS>::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, p, w, st, scratch);
+    else k_cg_spmv<BS, true><<<sgrid, SpmvCfg<BS>::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, p, w, st, scratch);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
+  int cg_spmv(double* p, double* w) {
+    if (dist) { if (int e = dist_halo_exchange(s, dist, p, bs, sendbuf)) return e; }
+    int e = bs == 1 ? cg_spmv_bs<1>(p, w) : bs == 2 ? cg_spmv_bs<2>(p, w) : cg_spmv_bs<3>(p, w);
+    if (e) return e;
+    if (dist) {
+      if (int e2 = dist_allreduce_sum(s, dist, st->sums, 1)) return e2;
+      k_state_step<<<1, 1, 0, s>>>(st, hist_dev, 2);
+      CB_LAUNCH_CHECK();
+    }
+    return CB_OK;
+  }
+  template <int BS>
+  int minres_spmv_bs(const double* v, const double* r1, double* t) {
+    if (dist) k_minres_spmv<BS, false><<<sgrid, SpmvCfg<BS>::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, v, r1, t, st, scratch);
+    else k_minres_spmv<BS, true><<<sgrid, SpmvCfg<BS>::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, v, r1, t, st, scratch);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
+  int plain_spmv(double* x, double* y) {
+    if (dist) { if (int e = dist_halo_exchange(s, dist, x, bs, sendbuf)) return e; }
+    return spmv_dispatch(s, A, x, y, nullptr, nullptr, nullptr);
+  }
+  int reduce_and_step(int nsums, int which, bool minres) {
+    if (!dist) return CB_OK;
+    if (int e = dist_allreduce_sum(s, dist, st->sums, nsums)) return e;
+    if (minres) k_minres_state<<<1, 1, 0, s>>>(st, hist_dev, which);
+    else k_state_step<<<1, 1, 0, s>>>(st, hist_dev, which);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
+};
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int64_t cb_ksp_workspace_len(int64_t n, int64_t nc, const cb_ksp_opts* opts) {
+  (void)opts;
+  // r, w, dinv, d, t : n ; z, p, (minres: 3 more with ghosts) : nc ; + state, scratch, send buffer
+  return 6 * n + 6 * nc + STATE_DOUBLES + RED_SCRATCH_LEN + nc + 64;
+}
+
+extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, double* x,
+                            const cb_ksp_opts* o, cb_dist* dist, double* work, int64_t work_len,
+                            cb_ksp_result* result, double* hist, int64_t hist_len) {
+  CB_REQUIRE(A && b && x && o && work && result, "cb_ksp_solve: missing argument");
+  CB_REQUIRE(A->bs >= 1 && A->bs <= 3, "cb_ksp_solve: block size must be 1..3");
+  const int64_t n = A->nrows * A->bs, nc = A->ncols * A->bs;
+  CB_REQUIRE(work_len >= cb_ksp_workspace_len(n, nc, o), "cb_ksp_solve: workspace too small");
+  CB_REQUIRE(o->pc_type != CB_PC_CHEBYSHEV || o->cheb_degree >= 1, "chebyshev degree must be >= 1");
+  cudaStream_t s = as_stream(stream);
+
+  // carve the workspace
+  double* wp = work;
+  auto take = [&](int64_t len) { double* p = wp; wp += (len + 1) & ~int64_t(1); return p; };
+  KspState* st = reinterpret_cast<KspState*>(take(STATE_DOUBLES));
+  double* scratch = take(RED_SCRATCH_LEN);
+  double* dinv = take(n);
+  double* r = take(n);
+  double* w = take(n);
+  double* cd = take(n);
+  double* ct = take(n);
+  double* z = take(nc);
+  double* p = take(nc);
+  double* m1 = take(nc);
+  double* m2 = take(nc);
+  double* m3 = take(nc);
+  double* sendbuf = take(nc);
+  double* hist_dev = nullptr;
+  const int64_t hlen = (o->monitor && hist && hist_len > 0) ? hist_len : 0;
+  if (hlen) CB_CUDA_CHECK(cudaMallocAsync(&hist_dev, sizeof(double) * hlen, s));
+
+  KspState h0;
+  memset(&h0, 0, sizeof(h0));
+  h0.rtol = o->rtol; h0.atol = o->atol; h0.dtol = o->dtol; h0.max_it = o->max_it;
+  h0.hist_len = (int)hlen;
+  CB_CUDA_CHECK(cudaMemcpyAsync(st, &h0, sizeof(h0), cudaMemcpyHostToDevice, s));
+  CB_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * RED_SCRATCH_LEN, s));
+
+  Solver S;
+  S.s = s; S.A = A; S.dist = dist; S.n = n; S.nc = nc; S.bs = A->bs; S.st = st;
+  S.hist_dev = hist_dev; S.scratch = scratch; S.sendbuf = sendbuf;
+  S.vgrid = grid_for(n, 256, 4);
+  if (S.vgrid > RED_MAXP) S.vgrid = RED_MAXP;
+  {
+    const int R = A->bs == 1 ? SpmvCfg<1>::R : A->bs == 2 ? SpmvCfg<2>::R : SpmvCfg<3>::R;
+    const int64_t nrb = (A->nrows + R - 1) / R;
+    int64_t cap = (int64_t)num_sms() * 6;
+    if (cap > RED_MAXP) cap = RED_MAXP;
+    S.sgrid = (int)(nrb < cap ? nrb : cap);
+  }
+  const int vg = S.vgrid;
+  const bool use_pc = o->pc_type != CB_PC_NONE;
+  double lmax_h = 0.0;
+  if (use_pc) {
+    double* lmax_dev = (o->pc_type == CB_PC_CHEBYSHEV) ? &st->sums[3] : nullptr;
+    if (int e = diag_inv_launch(s, A, dinv, lmax_dev, scratch)) return e;
+    if (lmax_dev) {
+      if (dist) { if (int e = cb_dist_allreduce(stream, dist, lmax_dev, 1, 2)) return e; }
+      CB_CUDA_CHECK(cudaMemcpyAsync(&lmax_h, lmax_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
+      CB_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+  }
+  const double* dinv_or_null = use_pc ? dinv : nullptr;
+
+  KspState hs;
+  auto poll = [&]() -> int {
+    CB_CUDA_CHECK(cudaMemcpyAsync(&hs, st, sizeof(hs), cudaMemcpyDeviceToHost, s));
+    CB_CUDA_CHECK(cudaStreamSynchronize(s));
+    return CB_OK;
+  };
+  int rc = CB_OK;
+  const int check_every = o->check_every > 0 ? o->check_every : 25;
+
+  if (o->ksp_type == CB_KSP_PREONLY) {
+    CB_REQUIRE(o->pc_type == CB_PC_JACOBI, "preonly supports pc_type jacobi only (no direct solver on the device)");
+    k_diag_solve<<<vg, 256, 0, s>>>(n, b, dinv, x);
+    CB_LAUNCH_CHECK();
+    CB_CUDA_CHECK(cudaStreamSynchronize(s));
+    result->reason = CB_KSP_CONVERGED_ITS; result->its = 1; result->rnorm = 0.0; result->rnorm0 = 0.0;
+    if (hist_dev) CB_CUDA_CHECK(cudaFreeAsync(hist_dev, s));
+    return CB_OK;
+  }
+
+  if (o->ksp_type == CB_KSP_CG) {
+    const bool cheb = o->pc_type == CB_PC_CHEBYSHEV;
+    // Chebyshev coefficients (fixed polynomial -> a linear SPD preconditioner)
+    std::pair<double, double> coef[64];
+    double inv_theta = 0.0;
+    if (cheb) {
+      CB_REQUIRE(o->cheb_degree <= 64, "chebyshev degree > 64");
+      const double ratio = o->cheb_ratio > 1.0 ? o->cheb_ratio : 30.0;
+      const double lmax = lmax_h, lmin = lmax / ratio;
+      const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
+      const double sigma = theta / delta;
+      double rho = 1.0 / sigma;
+      inv_theta = 1.0 / theta;
+      for (int j = 1; j < o->cheb_degree; ++j) {
+        const double rho_new = 1.0 / (2.0 * sigma - rho);
+        coef[j] = {rho_new * rho, 2.0 * rho_new / delta};
+        rho = rho_new;
+      }
+    }
+    auto apply_cheb = [&]() -> int {  // z = P(r)
+      k_cheb_first<<<vg, 256, 0, s>>>(n, r, dinv, inv_theta, cd, z, st);
+      CB_LAUNCH_CHECK();
+      for (int j = 1; j < o->cheb_degree; ++j) {
+        if (int e = S.plain_spmv(z, ct)) return e;
+        k_cheb_step<<<vg, 256, 0, s>>>(n, r, ct, dinv, coef[j].first, coef[j].second, cd, z, st);
+        CB_LAUNCH_CHECK();
+      }
+      return CB_OK;
+    };
+    CB_CUDA_CHECK(cudaMemsetAsync(p, 0, sizeof(double) * nc, s));
+    if (cheb) CB_CUDA_CHECK(cudaMemsetAsync(z, 0, sizeof(double) * nc, s));
+    if (!cheb) {
+      if (dist) k_cg_init<false><<<vg, 256, 0, s>>>(n, b, dinv_or_null, r, z, x, true, st, hist_dev, scratch);
+      else k_cg_init<true><<<vg, 256, 0, s>>>(n, b, dinv_or_null, r, z, x, true, st, hist_dev, scratch);
+      CB_LAUNCH_CHECK();
+      if ((rc = S.reduce_and_step(2, 0, false))) return rc;
+    } else {
+      k_cg_init<true><<<vg, 256, 0, s>>>(n, b, dinv_or_null, r, z, x, false, st, hist_dev, scratch);
+      CB_LAUNCH_CHECK();
+      if ((rc = apply_cheb())) return rc;
+      k_dots_zr<<<vg, 256, 0, s>>>(n, z, r, st, hist_dev, scratch, dist ? -1 : 0);
+      CB_LAUNCH_CHECK();
+      if ((rc = S.reduce_and_step(2, 0, false))) return rc;
+    }
+    int enq = 0;
+    while (true) {
+      for (int c = 0; c < check_every && enq < o->max_it; ++c, ++enq) {
+        k_cg_p<<<vg, 256, 0, s>>>(n, z, p, st);
+        CB_LAUNCH_CHECK();
+        if ((rc = S.cg_spmv(p, w))) return rc;
+        if (!cheb) {
+          if (dist) k_cg_xr<false><<<vg, 256, 0, s>>>(n, p, w, dinv_or_null, x, r, z, true, st, hist_dev, scratch);
+          else k_cg_xr<true><<<vg, 256, 0, s>>>(n, p, w, dinv_or_null, x, r, z, true, st, hist_dev, scratch);
+          CB_LAUNCH_CHECK();
+          if ((rc = S.reduce_and_step(2, 1, false))) return rc;
+        } else {
+          k_cg_xr<false><<<vg, 256, 0, s>>>(n, p, w, dinv_or_null, x, r, z, false, st, hist_dev, scratch);
+          CB_LAUNCH_CHECK();
+          if ((rc = apply_cheb())) return rc;
+          k_dots_zr<<<vg, 256, 0, s>>>(n, z, r, st, hist_dev, scratch, dist ? -1 : 1);
+          CB_LAUNCH_CHECK();
+          if ((rc = S.reduce_and_step(2, 1, false))) return rc;
+        }
+      }
+      if ((rc = poll())) return rc;
+      if (hs.done || enq >= o->max_it) break;
+    }
+  } else if (o->ksp_type == CB_KSP_MINRES) {
+    CB_REQUIRE(o->pc_type != CB_PC_CHEBYSHEV, "minres supports pc_type none / jacobi");
+    // rotating roles: (r1, r2, y) and (w1, w2, w)
+    double* R3[3] = {r, w, ct};       // n each
+    double* W3[3] = {m1, m2, m3};     // n each (allocated nc)
+    double* v = p;                    // SpMV input (ghost tail)
+    double* y = z;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(cd);
+    CB_CUDA_CHECK(cudaMemsetAsync(cd, 0, 16, s));
+    CB_CUDA_CHECK(cudaMemsetAsync(m1, 0, sizeof(double) * n, s));
+    CB_CUDA_CHECK(cudaMemsetAsync(m2, 0, sizeof(double) * n, s));
+    CB_CUDA_CHECK(cudaMemsetAsync(m3, 0, sizeof(double) * n, s));
+    CB_CUDA_CHECK(cudaMemsetAsync(R3[0], 0, sizeof(double) * n, s));
+    CB_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * nc, s));
+    // r2 = R3[1]
+    if (dist) k_minres_init<false><<<vg, 256, 0, s>>>(n, b, dinv_or_null, R3[1], y, x, st, hist_dev, scratch);
+    else k_minres_init<true><<<vg, 256, 0, s>>>(n, b, dinv_or_null, R3[1], y, x, st, hist_dev, scratch);
+    CB_LAUNCH_CHECK();
+    if ((rc = S.reduce_and_step(1, 0, true))) return rc;
+    int enq = 0;
+    while (true) {
+      for (int c = 0; c < check_every && enq < o->max_it; ++c, ++enq) {
+        double* r1 = R3[enq % 3];
+        double* r2 = R3[(enq + 1) % 3];
+        double* t = R3[(enq + 2) % 3];
+        double* w1 = W3[enq % 3];
+        double* w2 = W3[(enq + 1) % 3];
+        double* wn = W3[(enq + 2) % 3];  // slot of the w from three iterations ago (free)
+        k_minres_v<<<vg, 256, 0, s>>>(n, y, v, st);
+        CB_LAUNCH_CHECK();
+        if (dist) { if ((rc = dist_halo_exchange(s, dist, v, S.bs, sendbuf))) return rc; }
+        rc = S.bs == 1 ? S.minres_spmv_bs<1>(v, r1, t) : S.bs == 2 ? S.minres_spmv_bs<2>(v, r1, t) : S.minres_spmv_bs<3>(v, r1, t);
+        if (rc) return rc;
+        if ((rc = S.reduce_and_step(1, 2, true))) return rc;
+        if (dist) k_minres_r<false><<<vg, 256, 0, s>>>(n, t, r2, dinv_or_null, y, st, hist_dev, scratch);
+        else k_minres_r<true><<<vg, 256, 0, s>>>(n, t, r2, dinv_or_null, y, st, hist_dev, scratch);
+        CB_LAUNCH_CHECK();
+        if ((rc = S.reduce_and_step(1, 1, true))) return rc;
+        k_minres_wx<<<vg, 256, 0, s>>>(n, v, w1, w2, wn, x, st, ticket);
+        CB_LAUNCH_CHECK();
+      }
+      if ((rc = poll())) return rc;
+      if (hs.done || enq >= o->max_it) break;
+    }
+  } else {
+    set_error("cb_ksp_solve: unsupported ksp_type %d", o->ksp_type);
+    return CB_ERR_UNSUPPORTED;
+  }
+
+  if (!hs.done) {  // max_it exhausted without the device raising done (cannot happen, but be safe)
+    hs.reason = CB_KSP_DIVERGED_ITS;
+  }
+  result->reason = hs.reason;
+  result->its = hs.its;
+  result->rnorm = hs.rnorm;
+  result->rnorm0 = hs.rnorm0;
+  if (hist_dev) {
+    const int64_t ncopy = (hs.its + 1 < hlen) ? hs.its + 1 : hlen;
+    CB_CUDA_CHECK(cudaMemcpyAsync(hist, hist_dev, sizeof(double) * ncopy, cudaMemcpyDeviceToHost, s));
+    CB_CUDA_CHECK(cudaStreamSynchronize(s));
+    CB_CUDA_CHECK(cudaFreeAsync(hist_dev, s));
+  }
+  return CB_OK;
+}

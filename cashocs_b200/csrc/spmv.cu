@@ -1,0 +1,157 @@
+// SpMV, scalar products and BLAS-1 reductions (PETSc Mat.mult / Vec.dot call sites:
+// cashocs/_forms/shape_form_handler.py:776-778, cashocs/_forms/control_form_handler.py:184-207).
+#include "spmv.cuh"
+
+namespace cb {
+
+template <int BS, bool WRITE_Y, bool DOT>
+__global__ void __launch_bounds__(SpmvCfg<BS>::THREADS)
+k_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+       const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+       const double* __restrict__ w, double* __restrict__ result, double* __restrict__ scratch) {
+  using C = SpmvCfg<BS>;
+  __shared__ double s_tile[C::TILE_DOUBLES];
+  __shared__ int64_t s_rp[C::R + 1];
+  __shared__ double s_red[33];
+  const int64_t nrb = (nrows + C::R - 1) / C::R;
+  double local = 0.0;
+  for (int64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+    const int64_t row0 = rb * C::R;
+    const int nr = (int)((nrows - row0 < C::R) ? (nrows - row0) : C::R);
+    const double acc = spmv_row_block<BS>(rowptr, col, val, x, row0, nr, s_tile, s_rp);
+    if ((int)threadIdx.x < nr * BS) {
+      const int64_t i = row0 * BS + threadIdx.x;
+      if (WRITE_Y) y[i] = acc;
+      if (DOT) local += acc * w[i];
+    }
+  }
+  if (DOT) {
+    double v[1] = {local};
+    const int ops[1] = {RED_SUM};
+    if (grid_reduce<1>(v, ops, scratch, s_red)) {
+      if (threadIdx.x == 0) *result = v[0];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_dot(int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+      double* __restrict__ result, double* __restrict__ scratch) {
+  __shared__ double s_red[33];
+  double local = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    local += x[i] * y[i];
+  double v[1] = {local};
+  const int ops[1] = {RED_SUM};
+  if (grid_reduce<1>(v, ops, scratch, s_red)) {
+    if (threadIdx.x == 0) *result = v[0];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_diag_inv(int64_t nrows, int bs, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+           const double* __restrict__ val, double* __restrict__ dinv, double* __restrict__ lmax,
+           double* __restrict__ scratch) {
+  __shared__ double s_red[33];
+  const int64_t total = nrows * bs;
+  double local = 0.0;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < total;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t br = r / bs;
+    const int i = (int)(r - br * bs);
+    double d = 0.0, s = 0.0;
+    for (int64_t k = rowptr[br]; k < rowptr[br + 1]; ++k) {
+      for (int j = 0; j < bs; ++j) s += fabs(val[(k * bs + i) * bs + j]);
+      if (col[k] == br) d = val[(k * bs + i) * bs + i];
+    }
+    dinv[r] = 1.0 / d;
+    const double ratio = s / fabs(d);
+    local = ratio > local ? ratio : local;
+  }
+  if (lmax) {
+    double v[1] = {local};
+    const int ops[1] = {RED_MAX};
+    if (grid_reduce<1>(v, ops, scratch, s_red)) {
+      if (threadIdx.x == 0) *lmax = v[0];
+    }
+  }
+}
+
+template <int BS>
+int launch_spmv(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
+                double* result, double* scratch) {
+  using C = SpmvCfg<BS>;
+  const int64_t nrb = (A->nrows + C::R - 1) / C::R;
+  int64_t cap = (int64_t)num_sms() * 6;
+  if (cap > RED_MAXP) cap = RED_MAXP;
+  const int grid = (int)(nrb < cap ? nrb : cap);
+  if (y && !w)
+    k_spmv<BS, true, false><<<grid, C::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, x, y, nullptr, nullptr, nullptr);
+  else if (y && w)
+    k_spmv<BS, true, true><<<grid, C::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, x, y, w, result, scratch);
+  else
+    k_spmv<BS, false, true><<<grid, C::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, x, nullptr, w, result, scratch);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+int diag_inv_launch(cudaStream_t s, const cb_mat* A, double* dinv, double* lmax, double* scratch) {
+  int grid = grid_for(A->nrows * A->bs, 256, 4);
+  if (grid > RED_MAXP) grid = RED_MAXP;
+  k_diag_inv<<<grid, 256, 0, s>>>(A->nrows, A->bs, A->rowptr, A->col, A->val, dinv, lmax, scratch);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
+                  double* result, double* scratch) {
+  CB_REQUIRE(A && A->rowptr && A->col && A->val && x, "cb_spmv: missing argument");
+  switch (A->bs) {
+    case 1: return launch_spmv<1>(s, A, x, y, w, result, scratch);
+    case 2: return launch_spmv<2>(s, A, x, y, w, result, scratch);
+    case 3: return launch_spmv<3>(s, A, x, y, w, result, scratch);
+  }
+  set_error("cb_spmv: unsupported block size %d", A->bs);
+  return CB_ERR_UNSUPPORTED;
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int64_t cb_reduce_scratch_len(void) { return RED_SCRATCH_LEN; }
+
+extern "C" int cb_spmv(void* stream, const cb_mat* A, const double* x, double* y) {
+  CB_REQUIRE(y != nullptr, "cb_spmv: y is NULL");
+  return spmv_dispatch(as_stream(stream), A, x, y, nullptr, nullptr, nullptr);
+}
+
+extern "C" int cb_scalar_product(void* stream, const cb_mat* A, const double* x, const double* y,
+                                 double* result_dev, double* scratch, int64_t scratch_len) {
+  CB_REQUIRE(scratch && scratch_len >= RED_SCRATCH_LEN, "cb_scalar_product: scratch too small");
+  CB_REQUIRE(y && result_dev, "cb_scalar_product: missing argument");
+  return spmv_dispatch(as_stream(stream), A, x, nullptr, y, result_dev, scratch);
+}
+
+extern "C" int cb_dot(void* stream, int64_t n, const double* x, const double* y, double* result_dev,
+                      double* scratch, int64_t scratch_len) {
+  CB_REQUIRE(scratch && scratch_len >= RED_SCRATCH_LEN, "cb_dot: scratch too small");
+  int grid = grid_for(n, 256, 4);
+  if (grid > RED_MAXP) grid = RED_MAXP;
+  k_dot<<<grid, 256, 0, as_stream(stream)>>>(n, x, y, result_dev, scratch);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int cb_extract_diag_inv(void* stream, const cb_mat* A, double* dinv, double* lmax_dev,
+                                   double* scratch, int64_t scratch_len) {
+  CB_REQUIRE(A && dinv, "cb_extract_diag_inv: missing argument");
+  CB_REQUIRE(!lmax_dev || (scratch && scratch_len >= RED_SCRATCH_LEN), "scratch too small");
+  int grid = grid_for(A->nrows * A->bs, 256, 4);
+  if (grid > RED_MAXP) grid = RED_MAXP;
+  k_diag_inv<<<grid, 256, 0, as_stream(stream)>>>(A->nrows, A->bs, A->rowptr, A->col, A->val, dinv,
+                                                  lmax_dev, scratch);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}

@@ -1,0 +1,266 @@
+/* cashocs_b200 -- C-ABI of the B200-native shape-gradient hot path.
+ *
+ * Drop-in boundary for the per-iteration shape-gradient pipeline of sblauth/cashocs
+ * (SURVEY.md section 8b).  Plain pointers and sizes only; no torch / dolfin / PETSc types.
+ * Every function returns 0 on success and a negative CB_ERR_* code on failure
+ * (cb_last_error() gives the message).  Krylov outcomes are reported separately as
+ * PETSc-compatible `reason` values so the Python shim can raise PETScKSPError(reason)
+ * exactly like cashocs/_utils/linalg.py:543-544.
+ *
+ * Ownership: the CALLER allocates and frees every device buffer (torch CUDA tensors in
+ * the Python host layer); the library allocates only stream-ordered scratch that it
+ * frees before returning, plus the opaque cb_dist communicator object.
+ * Threading: not re-entrant per stream; all work is stream-ordered on the cudaStream_t
+ * passed as `stream` (void*), with a host synchronisation only where a scalar result is
+ * returned to the host (documented per function).
+ *
+ * Index types: "ptr" arrays (rowptr, v2c_ptr, colour offsets) are int64; column / dof /
+ * cell-to-nnz indices are int32.  All floating point data is IEEE fp64.
+ * Matrices are block-CSR with square blocks of size bs in {1,2,3}, row-major inside a
+ * block (bs == 1 is plain CSR; layout == PETSc AIJ / BAIJ), columns sorted ascending.
+ */
+#ifndef CASHOCS_B200_H
+#define CASHOCS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_OK 0
+#define CB_ERR_CUDA -1
+#define CB_ERR_ARG -2
+#define CB_ERR_CAPACITY -3
+#define CB_ERR_NCCL -4
+#define CB_ERR_UNSUPPORTED -5
+
+/* PETSc KSPConvergedReason values (cashocs/_exceptions.py:93-129). */
+#define CB_KSP_CONVERGED_RTOL 2
+#define CB_KSP_CONVERGED_ATOL 3
+#define CB_KSP_CONVERGED_ITS 4
+#define CB_KSP_DIVERGED_ITS -3
+#define CB_KSP_DIVERGED_DTOL -4
+#define CB_KSP_DIVERGED_BREAKDOWN -5
+#define CB_KSP_DIVERGED_INDEFINITE_PC -8
+#define CB_KSP_DIVERGED_NANORINF -9
+#define CB_KSP_DIVERGED_INDEFINITE_MAT -10
+
+const char* cb_last_error(void);
+int cb_version(void);
+/* Number of SMs of the current device (grid sizing); <0 on error. */
+int cb_num_sms(void);
+
+/* ------------------------------------------------------------------ polynomial data
+ * A source term f(x) is passed as a polynomial in the spatial coordinates (the reference
+ * JIT-compiles the UFL expression through FFC; cashocs/_forms/general_form_handler.py:101-140).
+ */
+#define CB_POLY_MAXT 24
+typedef struct {
+  int32_t nterms;
+  int32_t pad;
+  double coef[CB_POLY_MAXT];
+  int8_t ex[CB_POLY_MAXT];
+  int8_t ey[CB_POLY_MAXT];
+  int8_t ez[CB_POLY_MAXT];
+} cb_poly;
+
+/* Quadrature rule on the reference simplex in barycentric coordinates; weights sum to 1. */
+#define CB_QUAD_MAXQ 64
+typedef struct {
+  int32_t nq;
+  int32_t pad;
+  double lam[CB_QUAD_MAXQ][4];
+  double w[CB_QUAD_MAXQ];
+} cb_quad;
+
+/* ------------------------------------------------------------------ sparsity pattern
+ * Replaces dolfin's dofmap-graph sparsity (fenics.assemble_system with
+ * bilinear_boundary_form_modification, cashocs/_utils/forms.py:274-288,
+ * cashocs/_utils/linalg.py:149-156): pattern = all (test dof, trial dof) pairs per cell.
+ */
+/* vertex(dof)-to-cell adjacency; v2c_ptr [nd+1], v2c_idx [nc*k] (cells ascending per dof). */
+int cb_v2c_build(void* stream, int64_t nd, int64_t nc, int k, const int32_t* cell_dofs,
+                 int64_t* v2c_ptr, int32_t* v2c_idx);
+/* rowptr [nrows+1] of the dofmap graph restricted to rows < nrows (owned rows). */
+int cb_pattern_rowptr(void* stream, int64_t nrows, int k, const int32_t* cell_dofs,
+                      const int64_t* v2c_ptr, const int32_t* v2c_idx, int64_t* rowptr);
+/* col [nnz] sorted ascending per row, cell2nnz [nc*k*k] (-1 where the row is not owned). */
+int cb_pattern_fill(void* stream, int64_t nrows, int64_t nc, int k, const int32_t* cell_dofs,
+                    const int64_t* v2c_ptr, const int32_t* v2c_idx, const int64_t* rowptr,
+                    int32_t* col, int32_t* cell2nnz);
+/* Deterministic greedy colouring on the HOST (cells sharing a dof get different colours).
+ * cell_dofs_host [nc*k], colour_host [nc] out; returns the number of colours (<0 on error). */
+int cb_colour_cells_host(int64_t nd, int64_t nc, int k, const int32_t* cell_dofs_host,
+                         int32_t* colour_host);
+
+/* ------------------------------------------------------------------ assembly
+ * Cells are passed colour-sorted: colour c owns cells [colour_off[c], colour_off[c+1]) of
+ * `cells` / `cell2nnz` (colour_off is a HOST array of ncolours+1 int64).  bc_flag [ndof]
+ * (uint8, nullable) marks Dirichlet dofs, bc_val [ndof] their values; elimination is
+ * symmetric per element tensor like dolfin's SystemAssembler (assemble_system,
+ * cashocs/_utils/linalg.py:149-156).  val / rhs may be NULL to skip that tensor; they
+ * are zeroed by the call.  nrows_owned: rows >= nrows_owned (ghost dofs) are skipped.
+ */
+typedef struct {
+  int32_t dim;            /* 2 or 3 */
+  int32_t ncolours;
+  const int64_t* colour_off; /* host */
+  const int32_t* cells;      /* [nc, dim+1] colour-sorted, vertex ids (== scalar P1 dofs) */
+  const int32_t* cell2nnz;   /* [nc, (dim+1)^2] colour-sorted */
+  const double* coords;      /* [nv, dim] */
+  int64_t nv;                /* vertices incl. ghosts */
+  int64_t nrows_owned;       /* owned vertices (rows assembled) */
+  int64_t nnz;               /* block nnz */
+} cb_mesh_view;
+
+/* Scalar P1:  A = c_stiff*K + c_mass*M ;  rhs = s_poly*int(f phi) + s_nodal*M fnodal.
+ * Replaces assemble_petsc_system (cashocs/_utils/linalg.py:107-188) for the state,
+ * adjoint, Lame-mu and mass-matrix systems. */
+int cb_assemble_scalar(void* stream, const cb_mesh_view* m, double c_stiff, double c_mass,
+                       double s_poly, const cb_poly* f, const cb_quad* q, double s_nodal,
+                       const double* fnodal, const uint8_t* bc_flag, const double* bc_val,
+                       double* val, double* rhs);
+
+/* Vector P1 elasticity Riesz scalar product (cashocs/_forms/shape_form_handler.py:655-685):
+ * 2 mu eps(U):eps(W) + lambda div U div W + delta U.W, mu a P1 nodal field, optional per-cell
+ * scaling 1/vol^gamma (cell_scale [nc] colour-sorted, nullable).  Block-CSR bs = dim.
+ * bc_flag / bc_val are per vector dof [dim*nv] (vertex-blocked dof = dim*v + c). */
+int cb_assemble_elasticity(void* stream, const cb_mesh_view* m, const double* mu,
+                           double lambda_lame, double damping, const double* cell_scale,
+                           const uint8_t* bc_flag, double* val);
+
+/* Shape derivative vector of the Poisson Lagrangian with J = int u dx
+ * (cashocs/_forms/shape_form_handler.py:533-549; analytic form
+ * tests/test_shape_optimization.py:252-259):
+ * dJ[V] = int u divV + divV gu.gp - (gradV + gradV^T) gu.gp - divV f p - (gradf.V) p.
+ * gradf: dim polynomials.  BC rows are zeroed (SystemAssembler lifting with g = 0). */
+int cb_assemble_shape_derivative_poisson(void* stream, const cb_mesh_view* m, const double* u,
+                                         const double* p, const cb_poly* f, const cb_poly* gradf,
+                                         const cb_quad* q, double c_int_u,
+                                         const uint8_t* bc_flag, double* rhs);
+
+/* PETScMatrix.ident_zeros (cashocs/_utils/linalg.py:167): rows with |row|_1 < 3e-16 get a
+ * unit diagonal.  n_fixed (device int64, nullable) receives the number of rows fixed. */
+int cb_ident_zeros(void* stream, int64_t nrows, int bs, const int64_t* rowptr,
+                   const int32_t* col, double* val, int64_t* n_fixed);
+
+/* ------------------------------------------------------------------ SpMV / BLAS-1 */
+typedef struct {
+  int64_t nrows;          /* owned block rows */
+  int64_t ncols;          /* block columns incl. ghosts */
+  int32_t bs;             /* 1, 2 or 3 */
+  int32_t pad;
+  const int64_t* rowptr;  /* [nrows+1] */
+  const int32_t* col;     /* [nnzb] */
+  const double* val;      /* [nnzb*bs*bs] */
+} cb_mat;
+
+/* y = A x  (PETSc Mat.mult; cashocs/_forms/shape_form_handler.py:776-777). */
+int cb_spmv(void* stream, const cb_mat* A, const double* x, double* y);
+/* result (device double) = y^T A x without materialising A x
+ * (ShapeFormHandler.scalar_product, cashocs/_forms/shape_form_handler.py:748-780). */
+int cb_scalar_product(void* stream, const cb_mat* A, const double* x, const double* y,
+                      double* result_dev, double* scratch, int64_t scratch_len);
+/* Deterministic dot product, result on device. scratch >= cb_reduce_scratch_len() doubles. */
+int cb_dot(void* stream, int64_t n, const double* x, const double* y, double* result_dev,
+           double* scratch, int64_t scratch_len);
+int64_t cb_reduce_scratch_len(void);
+/* dinv = 1 / diag(A) per scalar row [nrows*bs]; also row-wise Gershgorin sum_j|a_ij|/a_ii max
+ * into lmax_dev (device double, nullable). */
+int cb_extract_diag_inv(void* stream, const cb_mat* A, double* dinv, double* lmax_dev,
+                        double* scratch, int64_t scratch_len);
+
+/* ------------------------------------------------------------------ Krylov solvers
+ * Replaces LinearSolver.solve (cashocs/_utils/linalg.py:480-546): zero initial guess,
+ * left preconditioning, preconditioned residual norm, KSPConvergedDefault. */
+#define CB_KSP_CG 0
+#define CB_KSP_MINRES 1
+#define CB_KSP_PREONLY 2
+#define CB_PC_NONE 0
+#define CB_PC_JACOBI 1
+#define CB_PC_CHEBYSHEV 2
+typedef struct {
+  int32_t ksp_type;
+  int32_t pc_type;
+  double rtol, atol, dtol;
+  int32_t max_it;
+  int32_t cheb_degree;
+  double cheb_ratio;      /* lmax / lmin of the Chebyshev interval (default 30) */
+  int32_t check_every;    /* host polls the device status every this many iterations */
+  int32_t monitor;        /* 1: record the residual history (hist, up to hist_len) */
+} cb_ksp_opts;
+typedef struct {
+  int32_t reason;
+  int32_t its;
+  double rnorm;
+  double rnorm0;
+} cb_ksp_result;
+
+typedef struct cb_dist cb_dist; /* opaque multi-GPU context, NULL for one GPU */
+
+/* Work-space size in doubles for cb_ksp_solve on a matrix with n = nrows*bs scalar rows
+ * and nc = ncols*bs scalar columns. */
+int64_t cb_ksp_workspace_len(int64_t n, int64_t nc, const cb_ksp_opts* opts);
+/* Solve A x = b. x [>= ncols*bs] is overwritten (zero initial guess). Host-synchronises on
+ * `stream` (the result is returned to the host).  hist (host, nullable) gets rnorm per
+ * iteration when opts->monitor. */
+int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, double* x,
+                 const cb_ksp_opts* opts, cb_dist* dist, double* work, int64_t work_len,
+                 cb_ksp_result* result, double* hist, int64_t hist_len);
+
+/* ------------------------------------------------------------------ mesh kernels */
+#define CB_Q_SKEWNESS 0
+#define CB_Q_MAXIMUM_ANGLE 1
+#define CB_Q_RADIUS_RATIOS 2
+#define CB_Q_CONDITION_NUMBER 3
+/* Per-cell quality (cashocs/geometry/quality.py:101-271, :371-461) over cells [0, nc_owned);
+ * q (nullable) gets the per-cell values; red_dev[0] = min, red_dev[1] = sum (device). */
+int cb_mesh_quality(void* stream, int dim, int64_t nc, const double* coords,
+                    const int32_t* cells, int measure, double* q, double* red_dev,
+                    double* scratch, int64_t scratch_len);
+/* det(I + grad V) per cell (APrioriMeshTester.test, cashocs/geometry/mesh_testing.py:84-132):
+ * red_dev[0] = min, red_dev[1] = max;  V [nv, dim] vertex field scaled by `step`. */
+int cb_det_check(void* stream, int dim, int64_t nc, const double* coords, const int32_t* cells,
+                 const double* V, double step, double* det, double* red_dev, double* scratch,
+                 int64_t scratch_len);
+/* max_K sqrt(grad d : grad d) (compute_decreases, cashocs/geometry/mesh_handler.py:329-377). */
+int cb_gradient_frobenius_max(void* stream, int dim, int64_t nc, const double* coords,
+                              const int32_t* cells, const double* D, double* red_dev,
+                              double* scratch, int64_t scratch_len);
+/* coords_old = coords; coords += step * V  (DeformationHandler.move_mesh,
+ * cashocs/geometry/deformations.py:132-133); n = nv*dim. */
+int cb_move_mesh(void* stream, int64_t n, double* coords, double* coords_old, const double* V,
+                 double step);
+/* int_Omega (c_u * u + c_track/2 (u-ud)^2) dx  (IntegralFunctional.evaluate,
+ * cashocs/_optimization/cost_functional.py:160-168); ud nullable; result_dev device double. */
+int cb_functional(void* stream, int dim, int64_t nc, const double* coords, const int32_t* cells,
+                  double c_u, const double* u, double c_track, const double* ud,
+                  double* result_dev, double* scratch, int64_t scratch_len);
+/* Per-vertex collision counts (compute_collisions, cashocs/geometry/mesh_testing.py:201-241)
+ * with a uniform-grid broad phase built on the device; mismatch_dev (device int64) receives the
+ * number of vertices whose count differs from `valence`. */
+int cb_intersection_test(void* stream, int dim, int64_t nv, int64_t nc, const double* coords,
+                         const int32_t* cells, const int32_t* valence, int32_t* counts,
+                         int64_t* mismatch_dev);
+
+/* ------------------------------------------------------------------ multi-GPU (NCCL) */
+/* 128-byte NCCL unique id (rank 0 creates it, the host layer broadcasts it). */
+int cb_dist_unique_id(char* id128);
+/* Create the communicator + halo plan.  nneigh neighbours; for neighbour j: rank
+ * neigh_rank[j], send_idx (device int32, scalar-vertex indices into the owned range,
+ * send_off[j]..send_off[j+1]) and a contiguous ghost range recv_off[j]..recv_off[j+1]
+ * relative to the first ghost vertex. */
+int cb_dist_create(cb_dist** out, const char* id128, int rank, int nranks, int nneigh,
+                   const int32_t* neigh_rank, const int64_t* send_off, const int32_t* send_idx_dev,
+                   const int64_t* recv_off, int64_t n_owned, int64_t n_ghost);
+int cb_dist_destroy(cb_dist* d);
+/* Ghost update of a vertex-blocked vector x [(n_owned+n_ghost)*bs] (Vec.ghostUpdate). */
+int cb_dist_halo_exchange(void* stream, cb_dist* d, double* x, int bs, double* sendbuf);
+/* In-place allreduce of n doubles (op: 0 sum, 1 min, 2 max). */
+int cb_dist_allreduce(void* stream, cb_dist* d, double* buf_dev, int n, int op);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CASHOCS_B200_H */

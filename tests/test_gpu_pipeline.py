@@ -1,0 +1,155 @@
+"""GPU parity of the whole shape-gradient pipeline against the oracle, plus the reference's own
+acceptance criteria (Taylor rate > 1.9, iteration budgets, control gradient definition)."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cashocs_b200 as cb
+from oracle import meshes, pipeline
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+KSP = {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-12, "ksp_atol": 1e-30, "ksp_max_it": 20000}
+
+
+def demo_poly(dim):
+    x = cb.spatial_coordinate(dim)
+    return 2.5 * (x[0] + 0.4 - x[1] ** 2) ** 2 + x[0] ** 2 + x[1] ** 2 - 1
+
+
+def sop_config(**shape):
+    cfg = cb.Config()
+    cfg.set("StateSystem", "is_linear", "True")
+    cfg.set("ShapeGradient", "shape_bdry_def", "[1]")
+    cfg.set("ShapeGradient", "lambda_lame", "1.428571428571429")
+    cfg.set("ShapeGradient", "damping_factor", "0.2")
+    cfg.set("ShapeGradient", "mu_fix", "0.35714285714285715")
+    cfg.set("ShapeGradient", "mu_def", "0.35714285714285715")
+    cfg.set("MeshQuality", "tol_lower", "0.01")
+    cfg.set("MeshQuality", "tol_upper", "0.02")
+    cfg.set("AlgoLBFGS", "bfgs_memory_size", "3")
+    for k, v in shape.items():
+        sec = "MeshQuality" if k in ("volume_change", "angle_change") else "ShapeGradient"
+        cfg.set(sec, k, str(v))
+    return cfg
+
+
+def make_sop(mesh, cfg, bc_markers=(1,), ksp=KSP):
+    u, p = cb.Function(mesh), cb.Function(mesh)
+    form = cb.PoissonForm(source=demo_poly(mesh.dim))
+    bcs = cb.create_dirichlet_bcs(0.0, list(bc_markers))
+    J = cb.IntegralFunctional(c_state=1.0)
+    return cb.ShapeOptimizationProblem(form, bcs, J, u, p, config=cfg, ksp_options=ksp, adjoint_ksp_options=ksp,
+                                       gradient_ksp_options=ksp)
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+def circle():
+    return cb.import_mesh(os.path.join(GOLDEN, "unit_circle.npz")), meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))
+
+
+def test_shape_gradient_matches_oracle_unit_circle():
+    dm, om = circle()
+    sop = make_sop(dm, sop_config())
+    prob = pipeline.PoissonShapeProblem(om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02))
+    g0 = prob.compute_shape_gradient()
+    g1 = sop.compute_shape_gradient()[0].vector.cpu().numpy()
+    assert rel(sop.states[0].vector.cpu().numpy(), prob.u) < 1e-8
+    assert rel(sop.adjoints[0].vector.cpu().numpy(), prob.p) < 1e-8
+    assert rel(g1, g0) < 1e-8
+    assert abs(sop.gradient_problem.gradient_norm_squared - prob.gradient_norm_squared) < 1e-8 * prob.gradient_norm_squared
+    assert abs(sop.reduced_cost_functional.evaluate() - prob.cost()) < 1e-10 * abs(prob.cost())
+
+
+@pytest.mark.parametrize("n", [6])
+def test_shape_gradient_matches_oracle_cube_with_mu_problem(n):
+    """3D, inhomogeneous mu from the auxiliary Laplace solve (mu_def=5e2, mu_fix=1), fixed sides."""
+    dm = cb.regular_mesh(n, 1.0, 1.0, 1.0)
+    om = meshes.regular_mesh(n, 1.0, 1.0, 1.0)
+    cfg = sop_config(shape_bdry_def="[2]", shape_bdry_fix="[1, 3, 4, 5, 6]", mu_def=5e2, mu_fix=1.0)
+    sop = make_sop(dm, cfg, bc_markers=(1, 2, 3, 4, 5, 6))
+    ocfg = pipeline.ShapeConfig(shape_bdry_def=(2,), shape_bdry_fix=(1, 3, 4, 5, 6), mu_def=5e2, mu_fix=1.0)
+    prob = pipeline.PoissonShapeProblem(om, bc_markers=(1, 2, 3, 4, 5, 6), config=ocfg)
+    g0 = prob.compute_shape_gradient()
+    g1 = sop.compute_shape_gradient()[0].vector.cpu().numpy()
+    assert rel(sop.form_handler.mu_lame.vector.cpu().numpy(), prob.mu) < 1e-8
+    assert rel(g1, g0) < 1e-8
+    fix = np.unique(np.concatenate([3 * om.boundary_vertices([1, 3, 4, 5, 6]) + k for k in range(3)]))
+    assert np.all(g1[fix] == 0.0)
+
+
+def test_taylor_test_rate():
+    """tests/test_shape_optimization.py:302-318: rate > 1.9."""
+    dm, _ = circle()
+    sop = make_sop(dm, sop_config())
+    assert sop.gradient_test(rng=np.random.RandomState(300696)) > 1.9
+
+
+def test_armijo_decisions_match_oracle():
+    """Identical accept/reject sequence for one line search started from a too-large step."""
+    dm, om = circle()
+    sop = make_sop(dm, sop_config())
+    prob = pipeline.PoissonShapeProblem(om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, safeguard_stepsize=False))
+    g0 = prob.compute_shape_gradient()
+    J0 = prob.cost()
+    step0, J1, log0 = pipeline.armijo_step(prob, -g0, 64.0, J0, iteration=1)
+
+    sop.config.set("LineSearch", "safeguard_stepsize", "False")
+    sop.config.set("LineSearch", "initial_stepsize", "64.0")
+    from cashocs_b200._optimization import line_search as ls
+    from cashocs_b200._optimization import optimization_algorithms as algs
+
+    search = ls.ArmijoLineSearch(sop)
+    solver = algs.GradientDescentMethod(sop, search)
+    solver.iteration = 1
+    solver.compute_gradient()
+    solver.evaluate_cost_functional()
+    d = -sop.gradient.vector
+    search.perform(solver, d, False)
+    assert [k for k, _ in search.log] == [k for k, _ in log0]
+    assert np.allclose([s for _, s in search.log], [s for _, s in log0], rtol=0, atol=0)
+    assert abs(solver.stepsize - step0) == 0.0
+    assert np.max(np.abs(dm.coords.cpu().numpy() - prob.coords)) < 1e-9
+
+
+@pytest.mark.parametrize("algorithm,budget", [("bfgs", 7), ("gradient_descent", 32)])
+def test_iteration_budgets_unit_circle(algorithm, budget):
+    """tests/test_shape_optimization.py:321-353: gd <= 32, L-BFGS <= 7 iterations to rtol 1e-2."""
+    dm, om = circle()
+    sop = make_sop(dm, sop_config())
+    sop.solve(algorithm=algorithm, rtol=1e-2, atol=0.0, max_iter=budget)
+    assert sop.solver.converged and sop.solver.relative_norm <= 1e-2
+    prob = pipeline.PoissonShapeProblem(om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02))
+    ok, hist = (pipeline.lbfgs if algorithm == "bfgs" else pipeline.gradient_descent)(prob, rtol=1e-2, max_iter=budget)
+    assert ok and len(hist) - 1 == sop.solver.iteration
+    assert abs(sop.solver.objective_value - hist[-1][1]) < 1e-8 * abs(hist[-1][1])
+
+
+def test_control_problem_matches_reference_definitions(rng):
+    """tests/test_pde_problems.py:87-128: state, adjoint, gradient = textbook systems."""
+    dm = cb.regular_mesh(10)
+    om = meshes.regular_mesh(10)
+    y, p, u, y_d = (cb.Function(dm) for _ in range(4))
+    yd_h, u_h = rng.rand(om.num_vertices), rng.rand(om.num_vertices)
+    y_d.vector.copy_(torch.from_numpy(yd_h))
+    u.vector.copy_(torch.from_numpy(u_h))
+    form = cb.PoissonForm(source=u)
+    J = cb.IntegralFunctional(c_track=1.0, desired_state=y_d, c_control=1e-6)
+    cfg = cb.Config()
+    cfg.set("StateSystem", "is_linear", "True")
+    ocp = cb.OptimalControlProblem(form, cb.create_dirichlet_bcs(0.0, [1, 2]), J, y, u, p, config=cfg,
+                                   ksp_options=KSP, adjoint_ksp_options=KSP, gradient_ksp_options=KSP)
+    g = ocp.compute_gradient()[0].vector.cpu().numpy()
+    ref = pipeline.PoissonControlProblem(om, yd_h, u_h, alpha=1e-6, bc_markers=(1, 2))
+    g0 = ref.compute_gradient()
+    assert np.allclose(y.vector.cpu().numpy(), ref.y, rtol=1e-8, atol=1e-12)
+    assert np.allclose(p.vector.cpu().numpy(), ref.p, rtol=1e-8, atol=1e-12)
+    assert np.allclose(g, g0, rtol=1e-8, atol=1e-12)
+    assert abs(ocp.reduced_cost_functional.evaluate() - ref.cost()) < 1e-10 * abs(ref.cost())
