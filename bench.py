@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark: shape-gradient evaluations per second on the synthetic unit-cube workload.
+
+One *step* = one full shape-gradient evaluation: [Lame-mu solve] +
+elasticity matrix assembly + state assemble+solve + adjoint assemble+solve + shape-derivative
+vector assembly + elasticity Riesz solve + shape BCs + g^T A g + one trial mesh move
+(a-priori det(I+grad V) test, coordinate update, intersection test, mesh quality) + revert.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n CELLS_PER_EDGE] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU); the mesh is partitioned into vertex slabs,
+halo exchange + all-reduces go over NCCL; `value` is whole-mesh evaluations per second.
+Prints ONE JSON line (rank 0).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "shape_gradient_evals_per_s"
+UNIT = "evals/s"
+KSP = {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_atol": 1e-30, "ksp_max_it": 20000}
+SHAPE = dict(lambda_lame=1.428571428571429, damping_factor=0.2, mu=0.35714285714285715)
+ALL_MARKERS = [1, 2, 3, 4, 5, 6]
+
+
+def workload_name(n: int, n_gpus: int) -> str:
+    tets = 6 * n**3
+    return (f"unit-cube regular_mesh({n},1,1,1): {tets} tets / {(n + 1) ** 3} vertices, P1 Poisson state+adjoint, "
+            f"vector-P1 elasticity Riesz shape gradient, cg+jacobi rtol 1e-10, trial move + quality; {n_gpus} GPU(s)")
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0) -> None:
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), smax.append(float(f[2])), power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, f[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "power_w_max": float(np.max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- oracle arm / cpu baseline
+def oracle_eval_seconds(n_sample: int, repeats: int = 1):
+    """Time one shape-gradient evaluation of the CPU oracle on an n_sample cube; returns (s, its)."""
+    from oracle import meshes, pipeline
+
+    om = meshes.regular_mesh(n_sample, 1.0, 1.0, 1.0)
+    cfg = pipeline.ShapeConfig(shape_bdry_def=tuple(ALL_MARKERS), lambda_lame=SHAPE["lambda_lame"],
+                               damping_factor=SHAPE["damping_factor"], mu_def=SHAPE["mu"], mu_fix=SHAPE["mu"],
+                               test_for_intersections=False)
+    ksp = dict(KSP)
+    prob = pipeline.PoissonShapeProblem(om, bc_markers=tuple(ALL_MARKERS), config=cfg, state_ksp=ksp, adjoint_ksp=ksp,
+                                        gradient_ksp=ksp)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        prob.update_scalar_product()
+        g = prob.compute_shape_gradient()
+        h = 1.0 / n_sample
+        scale = 0.1 * h / max(float(np.max(np.abs(g))), 1e-300)
+        if prob.move_mesh(-scale * g):
+            prob.revert_transformation()
+        best = min(best, time.perf_counter() - t0)
+    return best, dict(prob.its), om.num_cells
+
+
+def cpu_baseline(n_full: int, n_sample: int = 24) -> dict:
+    secs, its, nc = oracle_eval_seconds(n_sample)
+    # work per evaluation ~ cells * Krylov iterations ~ Nc^(4/3) (its ~ n for Jacobi-CG)
+    scale = (6.0 * n_full**3 / nc) ** (4.0 / 3.0)
+    return {
+        "value": 1.0 / (secs * scale), "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": (f"numpy/scipy oracle (CPU restatement, not FEniCS/PETSc), one evaluation on regular_mesh({n_sample},1,1,1) "
+                   f"= {nc} tets took {secs:.3f} s (its {its}); extrapolated to n={n_full} by (Nc ratio)^(4/3)"),
+        "sample_seconds": secs,
+    }
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = 24
+    times = []
+    its = {}
+    for i in range(args.warmup + args.steps):
+        secs, its, nc = oracle_eval_seconds(n_sample)
+        if i >= args.warmup:
+            times.append(secs)
+    scale = (6.0 * args.n**3 / nc) ** (4.0 / 3.0)
+    per_eval = float(np.mean(times)) * scale
+    value = 1.0 / per_eval
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_eval * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.n, args.gpus), "n": args.n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": (f"oracle (numpy/scipy restatement; FEniCS/PETSc not installable) on regular_mesh({n_sample},1,1,1) "
+                                    f"= {nc} tets: {np.mean(times):.3f} s/eval (its {its}), extrapolated by (Nc ratio)^(4/3)")},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def build_problem(n: int, dist=None):
+    import cashocs_b200 as cb
+
+    if dist is None:
+        mesh = cb.regular_mesh(n, 1.0, 1.0, 1.0)
+    else:
+        from cashocs_b200 import distributed
+
+        mesh = distributed.distributed_regular_mesh(n, dist)
+    x = cb.spatial_coordinate(3)
+    f = 2.5 * (x[0] + 0.4 - x[1] ** 2) ** 2 + x[0] ** 2 + x[1] ** 2 - 1
+    cfg = cb.Config()
+    cfg.set("StateSystem", "is_linear", "True")
+    cfg.set("ShapeGradient", "shape_bdry_def", json.dumps(ALL_MARKERS))
+    cfg.set("ShapeGradient", "lambda_lame", repr(SHAPE["lambda_lame"]))
+    cfg.set("ShapeGradient", "damping_factor", repr(SHAPE["damping_factor"]))
+    cfg.set("ShapeGradient", "mu_fix", repr(SHAPE["mu"]))
+    cfg.set("ShapeGradient", "mu_def", repr(SHAPE["mu"]))
+    u, p = cb.Function(mesh), cb.Function(mesh)
+    gksp = dict(KSP)
+    gksp["ksp_profile_every"] = 8
+    sop = cb.ShapeOptimizationProblem(cb.PoissonForm(source=f), cb.create_dirichlet_bcs(0.0, ALL_MARKERS),
+                                      cb.IntegralFunctional(c_state=1.0), u, p, config=cfg, ksp_options=dict(KSP),
+                                      adjoint_ksp_options=dict(KSP), gradient_ksp_options=gksp)
+    return sop
+
+
+def evaluation_step(sop, h: float):
+    """One shape-gradient evaluation + one trial move (then revert, so every step sees the same mesh)."""
+    sop.state_problem.has_solution = False
+    sop.adjoint_problem.has_solution = False
+    sop.gradient_problem.has_solution = False
+    sop.form_handler.update_scalar_product()
+    g = sop.compute_shape_gradient()[0].vector
+    gnorm2 = sop.gradient_problem.gradient_norm_squared
+    ginf = float(g.abs().max().item())
+    if sop.mesh.dist is not None:
+        ginf = sop.mesh.dist.allreduce_scalar(ginf, "max")
+    step = -0.1 * h / max(ginf, 1e-300)
+    moved = sop.mesh_handler.move_mesh(g, step=step)
+    quality = sop.mesh_handler.current_mesh_quality
+    if moved:
+        sop.mesh_handler.revert_transformation()
+    return gnorm2, moved, quality
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=119, help="cells per cube edge (119 -> 10.1M tets, BASELINE configs[1])")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+
+    import cashocs_b200 as cb
+    from cashocs_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as td
+
+        from cashocs_b200 import distributed
+
+        td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = distributed.DistContext(rank, world)
+
+    lib = _lib.load()
+    sop = build_problem(args.n, dist)
+    mesh = sop.mesh
+    h = 1.0 / args.n
+    n_tets, n_verts = 6 * args.n**3, (args.n + 1) ** 3
+
+    # pinned host mirrors: the reference keeps mesh.coordinates() on the host (deformations.py:73)
+    coords_host = mesh.coords.cpu().pin_memory()
+    grad_host = torch.empty_like(sop.gradient.vector, device="cpu").pin_memory()
+
+    def barrier():
+        if dist is not None:
+            import torch.distributed as td
+
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps: int, e2e: bool):
+        its_acc = []
+        spmv_ms = spmv_prof = 0
+        barrier()
+        l0 = lib.cb_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(nsteps):
+            if e2e:
+                mesh.coords.copy_(coords_host, non_blocking=True)
+            out = evaluation_step(sop, h)
+            if e2e:
+                grad_host.copy_(sop.gradient.vector, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            r = sop.gradient_problem.linear_solver.last_result
+            spmv_ms += r.spmv_ms
+            spmv_prof += r.spmv_profiled
+            its_acc.append((sop.state_problem.iterations[0], sop.adjoint_problem.iterations[0], sop.gradient_problem.iterations))
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            ms = dist.allreduce_scalar(ms, "max")
+        return ms, lib.cb_launch_count() - l0, its_acc, spmv_ms, spmv_prof, out
+
+    timed(max(args.warmup, 3), False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches, its, spmv_ms, spmv_prof, out = timed(args.steps, False)
+    ms_e2e, _, _, _, _, _ = timed(args.steps, True)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    value = args.steps / (ms * 1e-3)
+    e2e_value = args.steps / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel: the block-CSR (3x3) SpMV of the elasticity PCG
+    nnzb_total = mesh.nnz if dist is None else int(dist.allreduce_scalar(float(mesh.nnz), "sum"))
+    nnzb_rank = mesh.nnz
+    nv_rank = mesh.n_owned_vertices
+    alg_bytes = 76.0 * nnzb_rank + 16.0 * 3 * nv_rank + 4.0 * nv_rank  # SURVEY.md 8d, 3x3 BSR
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    roofline = None
+    if spmv_prof > 0:
+        avg_ms = spmv_ms / spmv_prof
+        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_cg_spmv<3> (elasticity PCG: w = A p, fused p.w)", "achieved": achieved,
+                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "avg_launch_ms": avg_ms, "launches_profiled": spmv_prof, "algorithmic_bytes_per_launch": alg_bytes,
+                    "spmv_share_of_step": (avg_ms * sum(i[2] for i in its)) / ms}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.n, args.gpus), "n": args.n, "tets": n_tets, "vertices": n_verts,
+                       "block_nnz": nnzb_total, "krylov_its_state_adjoint_elasticity": list(its[-1]),
+                       "l2_policy": "inputs larger than L2 (elasticity matrix %.2f GB, L2 126 MB)" % (76e-9 * nnzb_rank),
+                       "parallelism": "1 GPU" if dist is None else f"mesh partitioned into {world} vertex slabs, NCCL halo + allreduce"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(coords_host.numel() * 8),
+                    "d2h_bytes_per_step": int(grad_host.numel() * 8), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "check": {"gradient_norm_squared": out[0], "move_accepted": bool(out[1]), "mesh_quality": out[2]},
+        }
+        if not args.no_cpu_baseline and args.gpus == 1:
+            line["cpu_baseline"] = cpu_baseline(args.n)
+        print(json.dumps(line))
+    if dist is not None:
+        import torch.distributed as td
+
+        barrier()
+        dist.destroy()
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

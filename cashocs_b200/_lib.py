@@ -78,6 +78,8 @@ class cb_ksp_opts(C.Structure):
         ("cheb_ratio", C.c_double),
         ("check_every", C.c_int32),
         ("monitor", C.c_int32),
+        ("profile_every", C.c_int32),
+        ("pad", C.c_int32),
     ]
 
 
@@ -87,6 +89,9 @@ class cb_ksp_result(C.Structure):
         ("its", C.c_int32),
         ("rnorm", C.c_double),
         ("rnorm0", C.c_double),
+        ("spmv_ms", C.c_double),
+        ("spmv_profiled", C.c_int32),
+        ("spmv_launches", C.c_int32),
     ]
 
 
@@ -100,6 +105,7 @@ SIGNATURES = {
     "cb_last_error": (C.c_char_p, []),
     "cb_version": (I32, []),
     "cb_num_sms": (I32, []),
+    "cb_launch_count": (C.c_longlong, []),
     "cb_v2c_build": (I32, [P, I64, I64, I32, P, P, P]),
     "cb_pattern_rowptr": (I32, [P, I64, I32, P, P, P, P]),
     "cb_pattern_fill": (I32, [P, I64, I64, I32, P, P, P, P, P, P]),

@@ -105,7 +105,7 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None) -> _l
         )
     known = {"ksp_type", "pc_type", "ksp_rtol", "ksp_atol", "ksp_divtol", "ksp_max_it",
              "pc_chebyshev_degree", "pc_chebyshev_ratio", "ksp_check_every", "ksp_ksp_type",
-             "ksp_ksp_max_it", "ksp_pc_type"} | _IGNORED_KEYS
+             "ksp_ksp_max_it", "ksp_pc_type", "ksp_profile_every"} | _IGNORED_KEYS
     unknown = set(opts) - known
     if unknown:
         raise _exceptions.InputError(
@@ -122,6 +122,7 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None) -> _l
     o.cheb_ratio = float(opts.get("pc_chebyshev_ratio", 30.0))
     o.check_every = int(opts.get("ksp_check_every", 0))
     o.monitor = 1 if ("ksp_monitor" in opts) else 0
+    o.profile_every = int(opts.get("ksp_profile_every", 0))
     return o
 
 
@@ -310,8 +311,10 @@ def assemble_shape_derivative(mesh, u: torch.Tensor, p: torch.Tensor, f_poly: ex
 
 
 class KSPResult:
-    def __init__(self, reason: int, its: int, rnorm: float, rnorm0: float, history=None) -> None:
+    def __init__(self, reason: int, its: int, rnorm: float, rnorm0: float, history=None, spmv_ms: float = 0.0,
+                 spmv_profiled: int = 0, spmv_launches: int = 0) -> None:
         self.reason, self.its, self.rnorm, self.rnorm0, self.history = reason, its, rnorm, rnorm0, history
+        self.spmv_ms, self.spmv_profiled, self.spmv_launches = spmv_ms, spmv_profiled, spmv_launches
 
     def __repr__(self) -> str:
         return f"KSPResult(reason={self.reason}, its={self.its}, rnorm={self.rnorm:.3e}, rnorm0={self.rnorm0:.3e})"
@@ -373,7 +376,8 @@ class LinearSolver:
             "cb_ksp_solve",
         )
         history = hist[: res.its + 1].copy() if hist is not None else None
-        self.last_result = KSPResult(int(res.reason), int(res.its), float(res.rnorm), float(res.rnorm0), history)
+        self.last_result = KSPResult(int(res.reason), int(res.its), float(res.rnorm), float(res.rnorm0), history,
+                                     float(res.spmv_ms), int(res.spmv_profiled), int(res.spmv_launches))
         self.total_iterations += int(res.its)
         if res.reason < 0:
             raise _exceptions.PETScKSPError(int(res.reason))

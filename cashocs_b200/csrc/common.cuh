@@ -20,7 +20,12 @@ void set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
-#define CB_LAUNCH_CHECK() CB_CUDA_CHECK(cudaGetLastError())
+extern long long g_launch_count;  // kernels launched by this library (bench.py's gpu_launches)
+#define CB_LAUNCH_CHECK()                 \
+  do {                                    \
+    ++cb::g_launch_count;                 \
+    CB_CUDA_CHECK(cudaGetLastError());    \
+  } while (0)
 
 #define CB_REQUIRE(cond, msg)                                \
   do {                                                       \

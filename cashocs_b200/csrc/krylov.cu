@@ -16,6 +16,7 @@
 #include <math.h>
 
 #include <utility>
+#include <vector>
 
 #include "spmv.cuh"
 
@@ -434,6 +435,34 @@ struct Solver {
   double* scratch;
   double* sendbuf;
   int vgrid, sgrid;
+  // optional live profiling of the SpMV launches (bench.py roofline): CUDA events around every
+  // profile_every-th launch on the launching stream
+  int profile_every = 0, spmv_launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
+
+  bool prof_begin() {
+    const bool on = profile_every > 0 && (spmv_launches % profile_every) == 0 && prof.size() < 1024;
+    ++spmv_launches;
+    if (!on) return false;
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return false;
+    prof.push_back({a, b});
+    cudaEventRecord(a, s);
+    return true;
+  }
+  void prof_end(bool on) {
+    if (on) cudaEventRecord(prof.back().second, s);
+  }
+  double prof_collect() {  // after a stream synchronisation
+    double total = 0.0;
+    for (auto& e : prof) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) total += ms;
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
+    return total;
+  }
 
   template <int BS>
   int cg_spmv_bs(const double* p, double* w) {
@@ -444,7 +473,9 @@ struct Solver {
   }
   int cg_spmv(double* p, double* w) {
     if (dist) { if (int e = dist_halo_exchange(s, dist, p, bs, sendbuf)) return e; }
+    const bool pr = prof_begin();
     int e = bs == 1 ? cg_spmv_bs<1>(p, w) : bs == 2 ? cg_spmv_bs<2>(p, w) : cg_spmv_bs<3>(p, w);
+    prof_end(pr);
     if (e) return e;
     if (dist) {
       if (int e2 = dist_allreduce_sum(s, dist, st->sums, 1)) return e2;
@@ -524,6 +555,7 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
   Solver S;
   S.s = s; S.A = A; S.dist = dist; S.n = n; S.nc = nc; S.bs = A->bs; S.st = st;
   S.hist_dev = hist_dev; S.scratch = scratch; S.sendbuf = sendbuf;
+  S.profile_every = o->profile_every;
   S.vgrid = grid_for(n, 256, 4);
   if (S.vgrid > RED_MAXP) S.vgrid = RED_MAXP;
   {
@@ -562,6 +594,7 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
     CB_LAUNCH_CHECK();
     CB_CUDA_CHECK(cudaStreamSynchronize(s));
     result->reason = CB_KSP_CONVERGED_ITS; result->its = 1; result->rnorm = 0.0; result->rnorm0 = 0.0;
+    result->spmv_ms = 0.0; result->spmv_profiled = 0; result->spmv_launches = 0;
     if (hist_dev) CB_CUDA_CHECK(cudaFreeAsync(hist_dev, s));
     return CB_OK;
   }
@@ -689,6 +722,9 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
   result->its = hs.its;
   result->rnorm = hs.rnorm;
   result->rnorm0 = hs.rnorm0;
+  result->spmv_launches = S.spmv_launches;
+  result->spmv_profiled = (int)S.prof.size();
+  result->spmv_ms = S.prof_collect();
   if (hist_dev) {
     const int64_t ncopy = (hs.its + 1 < hlen) ? hs.its + 1 : hlen;
     CB_CUDA_CHECK(cudaMemcpyAsync(hist, hist_dev, sizeof(double) * ncopy, cudaMemcpyDeviceToHost, s));

@@ -50,6 +50,8 @@ const char* cb_last_error(void);
 int cb_version(void);
 /* Number of SMs of the current device (grid sizing); <0 on error. */
 int cb_num_sms(void);
+/* Total number of CUDA kernels this library has launched in this process (monotonic). */
+long long cb_launch_count(void);
 
 /* ------------------------------------------------------------------ polynomial data
  * A source term f(x) is passed as a polynomial in the spatial coordinates (the reference
@@ -189,12 +191,17 @@ typedef struct {
   double cheb_ratio;      /* lmax / lmin of the Chebyshev interval (default 30) */
   int32_t check_every;    /* host polls the device status every this many iterations */
   int32_t monitor;        /* 1: record the residual history (hist, up to hist_len) */
+  int32_t profile_every;  /* >0: bracket every profile_every-th SpMV launch with CUDA events */
+  int32_t pad;
 } cb_ksp_opts;
 typedef struct {
   int32_t reason;
   int32_t its;
   double rnorm;
   double rnorm0;
+  double spmv_ms;         /* summed duration of the profiled SpMV launches (profile_every > 0) */
+  int32_t spmv_profiled;  /* number of SpMV launches profiled */
+  int32_t spmv_launches;  /* number of SpMV launches enqueued by this solve */
 } cb_ksp_result;
 
 typedef struct cb_dist cb_dist; /* opaque multi-GPU context, NULL for one GPU */

@@ -1,0 +1,154 @@
+"""CPU: host-side logic of the product (no compute calls): C-ABI exports, option parsing,
+config handling, polynomial expressions, mesh generators, exceptions."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import cashocs_b200 as cb
+from cashocs_b200 import _lib
+from cashocs_b200._forms import expressions
+from cashocs_b200._utils import linalg
+from oracle import fem, meshes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "cashocs_b200.h")).read()
+    declared = set(re.findall(r"\b(cb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().cb_version() >= 100
+    assert _lib.load().cb_reduce_scratch_len() > 0
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.cb_poly) == 8 + 8 * 24 + 3 * 24
+    assert ctypes.sizeof(_lib.cb_quad) == 8 + 8 * 4 * 64 + 8 * 64
+    assert ctypes.sizeof(_lib.cb_mat) == 48
+    assert ctypes.sizeof(_lib.cb_mesh_view) == 64
+    assert ctypes.sizeof(_lib.cb_ksp_opts) == 64
+    assert ctypes.sizeof(_lib.cb_ksp_result) == 40
+
+
+def test_host_colouring_through_c_abi():
+    m = meshes.regular_mesh(4, 1.0, 1.0, 1.0)
+    colour = np.empty(m.num_cells, dtype=np.int32)
+    ncol = _lib.load().cb_colour_cells_host(m.num_vertices, m.num_cells, 4, m.cells.ctypes.data, colour.ctypes.data)
+    assert 24 <= ncol <= 128
+    for c in range(ncol):
+        v = m.cells[colour == c].reshape(-1)
+        assert np.unique(v).size == v.size
+
+
+def test_no_cpu_fallback():
+    m = cb.regular_mesh(3, device="cpu")
+    with pytest.raises(cb.CashocsException, match="GPU only"):
+        m.build_pattern()
+    with pytest.raises(cb.CashocsException, match="GPU only"):
+        cb.compute_mesh_quality(m)
+
+
+def test_ksp_option_parsing():
+    o = linalg.parse_ksp_options({"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-9, "ksp_max_it": 77})
+    assert (o.ksp_type, o.pc_type, o.rtol, o.max_it, o.atol, o.dtol) == (0, 1, 1e-9, 77, 1e-50, 1e5)
+    o = linalg.parse_ksp_options({"ksp_type": "cg", "pc_type": "jacobi"}, rtol=1e-3, atol=1e-7)
+    assert (o.rtol, o.atol) == (1e-3, 1e-7)  # setTolerances overrides (linalg.py:533)
+    o = linalg.parse_ksp_options(None)  # direct solver of the reference -> documented CG mapping
+    assert (o.ksp_type, o.pc_type, o.rtol) == (0, 1, 1e-13)
+    o = linalg.parse_ksp_options(linalg.iterative_ksp_options)
+    assert (o.ksp_type, o.pc_type) == (0, 1) and o.rtol == 1e-14 and o.max_it >= 200000
+    o = linalg.parse_ksp_options({"ksp_type": "minres", "pc_type": "none", "ksp_monitor": None})
+    assert (o.ksp_type, o.pc_type, o.monitor) == (1, 0, 1)
+    o = linalg.parse_ksp_options({"ksp_type": "cg", "pc_type": "ksp", "ksp_ksp_type": "chebyshev", "ksp_ksp_max_it": 4, "ksp_pc_type": "jacobi"})
+    assert (o.pc_type, o.cheb_degree) == (2, 4)
+    o = linalg.parse_ksp_options({"ksp_type": "preonly", "pc_type": "jacobi", "pc_jacobi_type": "diagonal", "ksp_rtol": 1e-16,
+                                  "ksp_atol": 1e-20, "ksp_max_it": 1000})  # mesh_testing.py:74-81
+    assert (o.ksp_type, o.pc_type) == (2, 1)
+    for bad in ({"ksp_type": "gmres"}, {"ksp_type": "cg", "pc_type": "ilu"}, {"ksp_type": "cg", "pc_type": "jacobi", "foo": 1}):
+        with pytest.raises(cb.InputError):
+            linalg.parse_ksp_options(bad)
+
+
+def test_config_defaults_and_validation(tmp_path):
+    cfg = cb.Config()
+    assert cfg.getfloat("MeshQuality", "tol_upper") == 1e-15 and cfg.get("MeshQuality", "measure") == "skewness"
+    assert cfg.getfloat("LineSearch", "beta_armijo") == 2.0 and cfg.getfloat("LineSearch", "epsilon_armijo") == 1e-4
+    assert cfg.getfloat("MeshQuality", "volume_change") == float("inf")
+    assert cfg.getboolean("ShapeGradient", "test_for_intersections")
+    cfg.validate_config()
+    path = tmp_path / "config.ini"
+    path.write_text("[ShapeGradient]\nshape_bdry_def = [1, 2]\nlambda_lame = 1.5\n[MeshQuality]\ntol_lower = 0.01\ntol_upper = 0.02\n")
+    cfg = cb.load_config(str(path))
+    assert cfg.getlist("ShapeGradient", "shape_bdry_def") == [1, 2] and cfg.getfloat("ShapeGradient", "lambda_lame") == 1.5
+    cfg.validate_config()
+    cfg.set("MeshQuality", "tol_lower", "0.5")
+    cfg.set("LineSearch", "beta_armijo", "0.5")
+    cfg.set("MeshQuality", "measure", "bogus")
+    cfg.set("StateSystem", "is_linear", "maybe")
+    with pytest.raises(cb.ConfigError) as e:
+        cfg.validate_config()
+    assert len(e.value.config_errors) >= 4
+    with pytest.raises(cb.InputError):
+        cb.load_config(str(tmp_path / "missing.ini"))
+
+
+def test_polynomial_algebra_and_quadrature():
+    x = cb.spatial_coordinate(3)
+    f = 2.5 * (x[0] + 0.4 - x[1] ** 2) ** 2 + x[0] ** 2 + x[1] ** 2 - 1
+    assert f.degree == 4
+    pts = np.random.RandomState(0).rand(50, 3)
+    X, Y = pts[:, 0], pts[:, 1]
+    assert np.allclose(f(pts), 2.5 * (X + 0.4 - Y**2) ** 2 + X**2 + Y**2 - 1, rtol=1e-14)
+    assert np.allclose(f.derivative(0)(pts), 5 * (X + 0.4 - Y**2) + 2 * X, rtol=1e-13)
+    assert np.allclose(f.derivative(1)(pts), -10 * Y * (X + 0.4 - Y**2) + 2 * Y, rtol=1e-13)
+    assert f.derivative(2).terms == {}
+    s = f.struct()
+    assert s.nterms == len(f.terms) <= _lib.POLY_MAXT
+    for d in (2, 3):
+        lam, w = expressions.simplex_quadrature(d, 5)
+        lam0, w0 = fem.quadrature(d, 5)
+        assert abs(w.sum() - 1) < 1e-15 and len(w) == len(w0)
+        # same integrals as the oracle's independent rule
+        g = lambda l: (l[:, 1] ** 2 * l[:, 2] ** 3 + l[:, 0])  # noqa: E731
+        assert abs(np.sum(w * g(lam)) - np.sum(w0 * g(lam0))) < 1e-15
+
+
+def test_host_mesh_generators_match_oracle():
+    for args in ((5,), (3, 1.0, 2.0), (3, 1.0, 1.0, 1.0), (2, 1.0, 2.0, 3.0)):
+        dm, om = cb.regular_mesh(*args, device="cpu"), meshes.regular_mesh(*args)
+        assert np.array_equal(dm.cells.numpy(), om.cells) and np.array_equal(dm.coords.numpy(), om.coords)
+        for marker in np.unique(om.facet_tags):
+            assert np.array_equal(dm.boundary_vertices([int(marker)]).numpy(), om.boundary_vertices([marker]))
+    with pytest.raises(cb.InputError):
+        cb.regular_mesh(0, device="cpu")
+    with pytest.raises(cb.InputError):
+        cb.regular_box_mesh(3, start_z=0.0, device="cpu")
+
+
+def test_exceptions_mirror_reference():
+    e = cb.PETScKSPError(-3)
+    assert e.error_code == -3 and "maximum iterations" in str(e)
+    assert issubclass(cb.PETScKSPError, cb.CashocsException)
+    assert "faulty input" in str(cb.InputError("obj", "param", "msg"))
+    assert str(cb.NotConvergedError("solver")).startswith("The solver failed")
+
+
+def test_bench_reference_arm_runs(tmp_path):
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, check=True, timeout=600)
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0

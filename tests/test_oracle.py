@@ -1,0 +1,207 @@
+"""CPU: pin the oracle against every known answer / invariant the reference's tests hold for the
+hot path and against the committed mesh fixtures."""
+
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from oracle import fem, krylov, meshes, pipeline, quality
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_quality_known_answers_2d():
+    """tests/test_geometry.py:138-195 (reference)."""
+    m = meshes.regular_mesh(4)
+    opt, a1, a2 = np.pi / 3, np.pi / 2, np.pi / 4
+    q = min(1 - max((a1 - opt) / (np.pi - opt), (opt - a1) / opt), 1 - max((a2 - opt) / (np.pi - opt), (opt - a2) / opt))
+    for meas in ("skewness", "maximum_angle"):
+        for typ in ("min", "avg"):
+            assert abs(quality.compute_mesh_quality(m.coords, m.cells, typ, meas) - q) < 1e-14
+    assert abs(quality.compute_mesh_quality(m.coords, m.cells, "quantile", "skewness", 0.167) - q) < 1e-14
+    for typ, qt in (("min", 0.0), ("avg", 0.0), ("quantile", 0.75189)):
+        assert abs(quality.compute_mesh_quality(m.coords, m.cells, typ, "condition_number", qt) - 0.4714045207910318) < 1e-14
+    rr = quality.radius_ratios(m.coords, m.cells)
+    assert abs(rr.min() - rr.mean()) < 1e-14
+
+
+def test_quality_known_answers_3d():
+    """tests/test_geometry.py:198-269 (reference)."""
+    m = meshes.regular_mesh(4, 1.0, 1.0, 1.0)
+    ang = quality.cell_angles(m.coords, m.cells)
+    opt = np.arccos(1 / 3)
+    amin, amax = ang.min(), ang.max()
+    q = min(1 - max((amax - opt) / (np.pi - opt), (opt - amax) / opt), 1 - max((amin - opt) / (np.pi - opt), (opt - amin) / opt))
+    r = min(1 - max((amax - opt) / (np.pi - opt), 0.0), 1 - max((amin - opt) / (np.pi - opt), 0.0))
+    assert abs(quality.compute_mesh_quality(m.coords, m.cells, "min", "skewness") - q) < 1e-14
+    assert abs(quality.compute_mesh_quality(m.coords, m.cells, "avg", "skewness") - q) < 1e-14
+    assert abs(quality.compute_mesh_quality(m.coords, m.cells, "min", "maximum_angle") - r) < 1e-14
+    assert abs(quality.compute_mesh_quality(m.coords, m.cells, "quantile", "maximum_angle", 0.715) - r) < 1e-14
+    for typ, qt in (("min", 0.0), ("avg", 0.0), ("quantile", 0.91576)):
+        assert abs(quality.compute_mesh_quality(m.coords, m.cells, typ, "condition_number", qt) - 0.3162277660168379) < 1e-14
+    rr = quality.radius_ratios(m.coords, m.cells)
+    assert abs(rr.min() - rr.mean()) < 1e-14
+
+
+def test_regular_mesh_invariants():
+    """tests/test_geometry.py:51-99 style invariants: volume 1, each side 1, Euler counts."""
+    m = meshes.regular_mesh(5)
+    _, vol, _ = fem.cell_geometry(m.coords, m.cells)
+    assert abs(vol.sum() - 1.0) < 1e-14 and m.num_cells == 50 and m.num_vertices == 36
+    seg = np.linalg.norm(m.coords[m.facets[:, 1]] - m.coords[m.facets[:, 0]], axis=1)
+    for tag in (1, 2, 3, 4):
+        assert abs(seg[m.facet_tags == tag].sum() - 1.0) < 1e-14
+    m3 = meshes.regular_mesh(3, 1.0, 2.0, 1.0)
+    _, vol, _ = fem.cell_geometry(m3.coords, m3.cells)
+    assert abs(vol.sum() - 2.0) < 1e-13 and m3.num_cells == 6 * 3 * 6 * 3
+    assert sorted(np.unique(m3.facet_tags)) == [1, 2, 3, 4, 5, 6]
+    # interior vertex of the Kuhn mesh: 15 nnz per row, 24 incident tets
+    m4 = meshes.regular_mesh(4, 1.0, 1.0, 1.0)
+    rowptr, _ = fem.csr_pattern(m4.cells, m4.num_vertices)
+    centre = 2 + 5 * 2 + 25 * 2
+    assert rowptr[centre + 1] - rowptr[centre] == 15
+    assert quality.vertex_valence(m4.cells, m4.num_vertices)[centre] == 24
+
+
+def test_golden_mesh_fixtures():
+    """The reference's gmsh fixtures (tests/mesh/*.msh) converted by tests/golden/make_fixtures.py."""
+    mc = meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))
+    assert (mc.num_vertices, mc.num_cells) == (713, 1340) and set(mc.facet_tags) == {1}
+    _, vol, _ = fem.cell_geometry(mc.coords, mc.cells)
+    assert abs(vol.sum() - np.pi) < 5e-3
+    assert np.allclose(np.linalg.norm(mc.coords[mc.boundary_vertices([1])], axis=1), 1.0, atol=1e-12)
+    m2 = meshes.load_npz(os.path.join(GOLDEN, "mesh2d.npz"))
+    _, vol, _ = fem.cell_geometry(m2.coords, m2.cells)
+    assert abs(vol.sum() - 1.0) < 1e-14 and m2.num_vertices == 12  # int 1 dx = 1 (tests/test_geometry.py:51-99)
+    seg = np.linalg.norm(m2.coords[m2.facets[:, 1]] - m2.coords[m2.facets[:, 0]], axis=1)
+    assert abs(seg.sum() - 4.0) < 1e-14
+    for tag in (1, 2, 3, 4):
+        assert abs(seg[m2.facet_tags == tag].sum() - 1.0) < 1e-14
+    m3 = meshes.load_npz(os.path.join(GOLDEN, "mesh3d.npz"))
+    _, vol, _ = fem.cell_geometry(m3.coords, m3.cells)
+    assert abs(vol.sum() - 1.0) < 1e-13 and sorted(set(m3.facet_tags)) == [1, 2, 3, 4, 5, 6]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/tests/mesh/mesh.msh"), reason="reference tree not present")
+def test_fixtures_match_reference_files():
+    for name, rel in (("unit_circle", "unit_circle/mesh.msh"), ("mesh2d", "mesh.msh"), ("mesh3d", "mesh3.msh")):
+        a = meshes.read_gmsh41(os.path.join("/root/reference/tests/mesh", rel))
+        b = meshes.load_npz(os.path.join(GOLDEN, name + ".npz"))
+        assert np.array_equal(a.coords, b.coords) and np.array_equal(a.cells, b.cells)
+        assert np.array_equal(a.facets, b.facets) and np.array_equal(a.facet_tags, b.facet_tags)
+
+
+def test_quadrature_exactness():
+    from math import factorial
+
+    for d in (2, 3):
+        lam, w = fem.quadrature(d, 6)
+        rng = np.random.RandomState(0)
+        for _ in range(10):
+            e = rng.randint(0, 3, size=d + 1)
+            if e.sum() > 6:
+                continue
+            exact = factorial(d) * np.prod([factorial(int(k)) for k in e]) / factorial(int(e.sum()) + d)
+            assert abs(np.sum(w * np.prod(lam ** e, axis=1)) - exact) < 1e-14
+
+
+def test_state_adjoint_gradient_definitions(rng):
+    """tests/test_pde_problems.py:87-128: oracle pipeline == textbook systems solved directly."""
+    m = meshes.regular_mesh(10)
+    y_d, u = rng.rand(m.num_vertices), rng.rand(m.num_vertices)
+    ocp = pipeline.PoissonControlProblem(m, y_d, u, alpha=1e-6, bc_markers=(1, 2))
+    g = ocp.compute_gradient()
+    _, vol, G = fem.cell_geometry(m.coords, m.cells)
+    K = fem.assemble_matrix(fem.stiffness_elements(vol, G), m.cells, m.num_vertices).tolil()
+    M = fem.assemble_matrix(fem.mass_elements(vol, 2), m.cells, m.num_vertices)
+    bc = m.boundary_vertices([1, 2])
+    free = np.setdiff1d(np.arange(m.num_vertices), bc)
+    Kff = K.tocsr()[free][:, free].tocsc()
+    y = np.zeros(m.num_vertices)
+    y[free] = spla.spsolve(Kff, (M @ u)[free])
+    p = np.zeros(m.num_vertices)
+    p[free] = spla.spsolve(Kff, -(M @ (y - y_d))[free])
+    gref = spla.spsolve(M.tocsc(), 1e-6 * (M @ u) - M @ p)
+    assert np.allclose(ocp.y, y) and np.allclose(ocp.p, p) and np.allclose(g, gref)
+
+
+def test_bc_elimination_is_symmetric_and_counts_cells():
+    """BC diagonal = number of cells sharing the dof, matrix symmetric, solution = g on BC."""
+    m = meshes.regular_mesh(6)
+    _, vol, G = fem.cell_geometry(m.coords, m.cells)
+    bc = m.boundary_vertices([1, 2, 3, 4])
+    be = fem.load_elements_callable(m.coords, m.cells, vol, pipeline.demo_f, 5)
+    A, b = fem.assemble_system(fem.stiffness_elements(vol, G), be, m.cells, m.num_vertices, bc, 0.25)
+    assert abs(A - A.T).max() < 1e-15
+    assert np.array_equal(A.diagonal()[bc], quality.vertex_valence(m.cells, m.num_vertices)[bc].astype(float))
+    x = spla.spsolve(A.tocsc(), b)
+    assert np.allclose(x[bc], 0.25)
+
+
+def test_krylov_petsc_semantics():
+    m = meshes.regular_mesh(12)
+    _, vol, G = fem.cell_geometry(m.coords, m.cells)
+    bc = m.boundary_vertices([1, 2, 3, 4])
+    be = fem.load_elements_callable(m.coords, m.cells, vol, pipeline.demo_f, 5)
+    A, b = fem.assemble_system(fem.stiffness_elements(vol, G), be, m.cells, m.num_vertices, bc, 0.0)
+    xd = spla.spsolve(A.tocsc(), b)
+    for ksp in ("cg", "minres"):
+        for pc in ("jacobi", "none"):
+            hist = []
+            x, reason, its, rn = krylov.solve(A, b, {"ksp_type": ksp, "pc_type": pc, "ksp_rtol": 1e-10}, history=hist)
+            assert reason == krylov.CONVERGED_RTOL and len(hist) == its + 1
+            assert hist[-1] <= 1e-10 * hist[0] < hist[-2]
+            assert np.max(np.abs(x - xd)) < 1e-8 * np.max(np.abs(xd))
+    x, reason, its, _ = krylov.solve(A, b, {"ksp_type": "cg", "pc_type": "chebyshev", "pc_chebyshev_degree": 3, "ksp_rtol": 1e-10})
+    assert reason == 2 and np.max(np.abs(x - xd)) < 1e-8 * np.max(np.abs(xd))
+    _, reason, its, _ = krylov.solve(A, b, {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-12, "ksp_max_it": 3})
+    assert reason == krylov.DIVERGED_ITS and its == 3
+    _, reason, _, _ = krylov.solve(-A, b, {"ksp_type": "cg", "pc_type": "none"})
+    assert reason == krylov.DIVERGED_INDEFINITE_MAT
+    x, reason, its, _ = krylov.solve(A, None)
+    assert np.all(x == 0.0)
+
+
+def test_taylor_test_and_iteration_budgets_unit_circle():
+    """tests/test_shape_optimization.py:302-353 (reference): rate > 1.9; L-BFGS <= 7, GD <= 32 iterations."""
+    load = lambda: meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))  # noqa: E731
+    cfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02)
+    rate, _, _ = pipeline.shape_gradient_test(pipeline.PoissonShapeProblem(load(), config=cfg))
+    assert rate > 1.9
+    ok, hist = pipeline.lbfgs(pipeline.PoissonShapeProblem(load(), config=cfg), rtol=1e-2, max_iter=7)
+    assert ok and hist[-1][2] <= 1e-2
+    ok, hist = pipeline.gradient_descent(pipeline.PoissonShapeProblem(load(), config=cfg), rtol=1e-2, max_iter=32)
+    assert ok and hist[-1][2] <= 1e-2
+
+
+def test_taylor_test_inhomogeneous_mu():
+    """tests/test_shape_optimization.py:645-670 style: mu_fix=1, mu_def=10 on regular_mesh(20)."""
+    m = meshes.regular_mesh(20)
+    cfg = pipeline.ShapeConfig(shape_bdry_def=(1, 2), shape_bdry_fix=(3, 4), mu_def=10.0, mu_fix=1.0)
+    prob = pipeline.PoissonShapeProblem(m, bc_markers=(1, 2, 3, 4), config=cfg)
+    assert prob.mu.min() >= 1.0 - 1e-12 and prob.mu.max() <= 10.0 + 1e-12
+    rate, _, _ = pipeline.shape_gradient_test(prob)
+    assert rate > 1.9
+
+
+def test_move_revert_and_rejection(rng):
+    """tests/test_shape_optimization.py:157-179 (reference)."""
+    m = meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))
+    prob = pipeline.PoissonShapeProblem(m)
+    before = m.coords.copy()
+    V = np.zeros_like(m.coords)
+    V[:, 0] = 0.5
+    assert prob.move_mesh(V.reshape(-1))
+    assert np.max(np.abs(m.coords - before - V)) < 1e-10
+    prob.revert_transformation()
+    assert np.array_equal(m.coords, before)
+    assert not prob.move_mesh(rng.uniform(-1e3, 1e3, size=m.coords.size))
+    assert np.array_equal(m.coords, before)
+
+
+def test_collisions_equal_valence_on_valid_meshes():
+    for m in (meshes.regular_mesh(5), meshes.regular_mesh(3, 1.0, 1.0, 1.0), meshes.load_npz(os.path.join(GOLDEN, "mesh2d.npz"))):
+        assert np.array_equal(quality.compute_collisions(m.coords, m.cells), quality.vertex_valence(m.cells, m.num_vertices))
+        assert quality.intersection_test(m.coords, m.cells)
