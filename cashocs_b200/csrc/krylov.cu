@@ -163,17 +163,18 @@ k_cg_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __re
           KspState* st, double* scratch) {
   if (st->done) return;
   using C = SpmvCfg<BS>;
-  __shared__ double s_tile[C::TILE_DOUBLES];
-  __shared__ int64_t s_rp[C::R + 1];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[33];
+  const SpmvSmem<BS> sm = spmv_smem_init<BS>(smem_raw);
+  uint32_t phase = 0;
   const int64_t nrb = (nrows + C::R - 1) / C::R;
   double local = 0.0;
   for (int64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
     const int64_t row0 = rb * C::R;
     const int nr = (int)((nrows - row0 < C::R) ? (nrows - row0) : C::R);
-    const double acc = spmv_row_block<BS>(rowptr, col, val, p, row0, nr, s_tile, s_rp);
-    if ((int)threadIdx.x < nr * BS) {
-      const int64_t i = row0 * BS + threadIdx.x;
+    double acc;
+    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, p, row0, nr, phase, acc);
+    if (i >= 0) {
       w[i] = acc;
       local += acc * p[i];
     }
@@ -337,18 +338,19 @@ k_minres_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* 
               double* scratch) {
   if (st->done) return;
   using C = SpmvCfg<BS>;
-  __shared__ double s_tile[C::TILE_DOUBLES];
-  __shared__ int64_t s_rp[C::R + 1];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[33];
+  const SpmvSmem<BS> sm = spmv_smem_init<BS>(smem_raw);
+  uint32_t phase = 0;
   const double c = (st->its >= 1) ? st->mbeta / st->oldb : 0.0;
   const int64_t nrb = (nrows + C::R - 1) / C::R;
   double local = 0.0;
   for (int64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
     const int64_t row0 = rb * C::R;
     const int nr = (int)((nrows - row0 < C::R) ? (nrows - row0) : C::R);
-    double acc = spmv_row_block<BS>(rowptr, col, val, v, row0, nr, s_tile, s_rp);
-    if ((int)threadIdx.x < nr * BS) {
-      const int64_t i = row0 * BS + threadIdx.x;
+    double acc;
+    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, v, row0, nr, phase, acc);
+    if (i >= 0) {
       if (c != 0.0) acc -= c * r1[i];
       t[i] = acc;
       local += acc * v[i];
@@ -466,8 +468,8 @@ struct Solver {
 
   template <int BS>
   int cg_spmv_bs(const double* p, double* w) {
-    if (dist) k_cg_spmv<BS, false><<<sgrid, SpmvCfg<BS>::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, p, w, st, scratch);
-    else k_cg_spmv<BS, true><<<sgrid, SpmvCfg<BS>::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, p, w, st, scratch);
+    if (dist) k_cg_spmv<BS, false><<<sgrid, SpmvCfg<BS>::THREADS, SpmvCfg<BS>::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, p, w, st, scratch);
+    else k_cg_spmv<BS, true><<<sgrid, SpmvCfg<BS>::THREADS, SpmvCfg<BS>::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, p, w, st, scratch);
     CB_LAUNCH_CHECK();
     return CB_OK;
   }
@@ -486,8 +488,8 @@ struct Solver {
   }
   template <int BS>
   int minres_spmv_bs(const double* v, const double* r1, double* t) {
-    if (dist) k_minres_spmv<BS, false><<<sgrid, SpmvCfg<BS>::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, v, r1, t, st, scratch);
-    else k_minres_spmv<BS, true><<<sgrid, SpmvCfg<BS>::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, v, r1, t, st, scratch);
+    if (dist) k_minres_spmv<BS, false><<<sgrid, SpmvCfg<BS>::THREADS, SpmvCfg<BS>::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, v, r1, t, st, scratch);
+    else k_minres_spmv<BS, true><<<sgrid, SpmvCfg<BS>::THREADS, SpmvCfg<BS>::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, v, r1, t, st, scratch);
     CB_LAUNCH_CHECK();
     return CB_OK;
   }
@@ -560,10 +562,29 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
   if (S.vgrid > RED_MAXP) S.vgrid = RED_MAXP;
   {
     const int R = A->bs == 1 ? SpmvCfg<1>::R : A->bs == 2 ? SpmvCfg<2>::R : SpmvCfg<3>::R;
+    const int per_sm = A->bs == 1 ? SpmvCfg<1>::CTAS_PER_SM : A->bs == 2 ? SpmvCfg<2>::CTAS_PER_SM : SpmvCfg<3>::CTAS_PER_SM;
     const int64_t nrb = (A->nrows + R - 1) / R;
-    int64_t cap = (int64_t)num_sms() * 6;
+    int64_t cap = (int64_t)num_sms() * per_sm;
     if (cap > RED_MAXP) cap = RED_MAXP;
     S.sgrid = (int)(nrb < cap ? nrb : cap);
+    static bool configured = false;
+    if (!configured) {
+      const int co = (int)cudaSharedmemCarveoutMaxShared;
+      const auto attr = cudaFuncAttributePreferredSharedMemoryCarveout;
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_cg_spmv<1, true>, attr, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_cg_spmv<2, true>, attr, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_cg_spmv<3, true>, attr, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_cg_spmv<1, false>, attr, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_cg_spmv<2, false>, attr, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_cg_spmv<3, false>, attr, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_minres_spmv<1, true>, attr, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_minres_spmv<2, true>, attr, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_minres_spmv<3, true>, attr, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_minres_spmv<1, false>, attr, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_minres_spmv<2, false>, attr, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_minres_spmv<3, false>, attr, co));
+      configured = true;
+    }
   }
   const int vg = S.vgrid;
   const bool use_pc = o->pc_type != CB_PC_NONE;

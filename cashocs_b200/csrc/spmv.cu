@@ -10,17 +10,18 @@ k_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restr
        const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
        const double* __restrict__ w, double* __restrict__ result, double* __restrict__ scratch) {
   using C = SpmvCfg<BS>;
-  __shared__ double s_tile[C::TILE_DOUBLES];
-  __shared__ int64_t s_rp[C::R + 1];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[33];
+  const SpmvSmem<BS> sm = spmv_smem_init<BS>(smem_raw);
+  uint32_t phase = 0;
   const int64_t nrb = (nrows + C::R - 1) / C::R;
   double local = 0.0;
   for (int64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
     const int64_t row0 = rb * C::R;
     const int nr = (int)((nrows - row0 < C::R) ? (nrows - row0) : C::R);
-    const double acc = spmv_row_block<BS>(rowptr, col, val, x, row0, nr, s_tile, s_rp);
-    if ((int)threadIdx.x < nr * BS) {
-      const int64_t i = row0 * BS + threadIdx.x;
+    double acc;
+    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, x, row0, nr, phase, acc);
+    if (i >= 0) {
       if (WRITE_Y) y[i] = acc;
       if (DOT) local += acc * w[i];
     }
@@ -79,19 +80,39 @@ k_diag_inv(int64_t nrows, int bs, const int64_t* __restrict__ rowptr, const int3
 }
 
 template <int BS>
+int spmv_grid(int64_t nrows) {
+  using C = SpmvCfg<BS>;
+  const int64_t nrb = (nrows + C::R - 1) / C::R;
+  int64_t cap = (int64_t)num_sms() * C::CTAS_PER_SM;
+  if (cap > RED_MAXP) cap = RED_MAXP;
+  return (int)(nrb < cap ? nrb : cap);
+}
+
+template <typename K>
+int prefer_smem(K kernel) {
+  CB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
+  return CB_OK;
+}
+
+template <int BS>
 int launch_spmv(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
                 double* result, double* scratch) {
   using C = SpmvCfg<BS>;
-  const int64_t nrb = (A->nrows + C::R - 1) / C::R;
-  int64_t cap = (int64_t)num_sms() * 6;
-  if (cap > RED_MAXP) cap = RED_MAXP;
-  const int grid = (int)(nrb < cap ? nrb : cap);
+  const int grid = spmv_grid<BS>(A->nrows);
+  static bool configured = false;
+  if (!configured) {
+    if (int e = prefer_smem(k_spmv<BS, true, false>)) return e;
+    if (int e = prefer_smem(k_spmv<BS, true, true>)) return e;
+    if (int e = prefer_smem(k_spmv<BS, false, true>)) return e;
+    configured = true;
+  }
   if (y && !w)
-    k_spmv<BS, true, false><<<grid, C::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, x, y, nullptr, nullptr, nullptr);
+    k_spmv<BS, true, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, x, y, nullptr, nullptr, nullptr);
   else if (y && w)
-    k_spmv<BS, true, true><<<grid, C::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, x, y, w, result, scratch);
+    k_spmv<BS, true, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, x, y, w, result, scratch);
   else
-    k_spmv<BS, false, true><<<grid, C::THREADS, 0, s>>>(A->nrows, A->rowptr, A->col, A->val, x, nullptr, w, result, scratch);
+    k_spmv<BS, false, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, x, nullptr, w, result, scratch);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }

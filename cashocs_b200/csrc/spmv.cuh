@@ -1,11 +1,17 @@
-// Block-CSR SpMV building blocks shared by spmv.cu and krylov.cu.
+// Block-CSR SpMV building block shared by spmv.cu and krylov.cu (sm_100a).
 //
-// Streaming design ("CSR-stream"): a CTA owns R consecutive block rows.  The nonzeros of those
-// rows are one contiguous span of `val` / `col`, which the CTA streams through shared memory
-// tile by tile with perfectly coalesced loads (every DRAM sector of the matrix is used once);
-// the products val * x[col] are written to shared memory and then reduced row by row in a
-// fixed order.  x is gathered through L1/L2 (for mesh matrices consecutive rows share almost
-// all of their columns, so the gathers hit in cache and DRAM traffic for x stays ~8 B/row).
+// Design ("TMA-staged row blocks"): a CTA owns R consecutive block rows.  Their nonzeros are
+// one contiguous span of `val` / `col`; one elected thread streams that span into shared
+// memory with two 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP, completion on an
+// mbarrier), so the matrix -- 85-95 % of all bytes -- never passes through the LSU or the
+// register file and every DRAM sector of it is fetched exactly once.  BS threads then own one
+// block row: thread (r, j) multiplies column j of every block of row r with x[BS*col + j] (one
+// gather per block and thread; for mesh matrices neighbouring rows hit neighbouring columns, so
+// a warp's gather touches 2-3 lines and is served by L1/L2) and the BS partial vectors are
+// transposed-reduced with two warp shuffles per row.  No shared-memory partial products, no
+// atomics, fixed summation order per row: bit-reproducible.
+// Several CTAs are resident per SM (single-buffered): while one waits on its mbarrier the
+// others compute, which keeps ~150-200 KB of matrix data in flight per SM.
 #pragma once
 #include "common.cuh"
 
@@ -13,56 +19,180 @@ namespace cb {
 
 template <int BS>
 struct SpmvCfg {
-  static constexpr int THREADS = 256;
-  static constexpr int R = (BS == 1) ? 128 : (BS == 2 ? 64 : 32);  // block rows per CTA
-  static constexpr int T = 16 * R;                                  // blocks per smem tile
-  static constexpr int TILE_DOUBLES = T * BS * BS;
+  static constexpr int ROWS_PER_WARP = 32 / BS;           // 32, 16, 10 (2 idle lanes for BS = 3)
+  static constexpr int WARPS = 4;
+  static constexpr int THREADS = 32 * WARPS;
+  static constexpr int R = ROWS_PER_WARP * WARPS;          // block rows per CTA: 128, 64, 40
+  static constexpr int T = 16 * R;                         // tile capacity in blocks
+  static constexpr int BB = BS * BS;
+  static constexpr int VAL_DOUBLES = T * BB + 2;           // +2: 16-byte alignment slack (head)
+  static constexpr int COL_INTS = T + 8;                   // +8: alignment slack (head up to 3)
+  static constexpr size_t SMEM_BYTES = sizeof(double) * VAL_DOUBLES + sizeof(int32_t) * COL_INTS + 16;
+  static constexpr int CTAS_PER_SM = (BS == 3) ? 4 : (BS == 2 ? 5 : 8);
 };
 
-// Computes rows [row0, row0+nr) of y = A x.  Result for scalar row (lr, i) is returned in
-// `acc` of thread t = lr*BS + i (t < nr*BS).  smem_tile: TILE_DOUBLES doubles, smem_rp: R+1.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Per-CTA state for the streaming SpMV (dynamic shared memory carve-up).
 template <int BS>
-__device__ __forceinline__ double spmv_row_block(const int64_t* __restrict__ rowptr,
-                                                 const int32_t* __restrict__ col,
-                                                 const double* __restrict__ val,
-                                                 const double* __restrict__ x, int64_t row0, int nr,
-                                                 double* smem_tile, int64_t* smem_rp) {
+struct SpmvSmem {
+  double* val;
+  int32_t* col;
+  uint64_t* bar;
+  __device__ __forceinline__ explicit SpmvSmem(unsigned char* base) {
+    using C = SpmvCfg<BS>;
+    val = reinterpret_cast<double*>(base);
+    col = reinterpret_cast<int32_t*>(base + sizeof(double) * C::VAL_DOUBLES);
+    bar = reinterpret_cast<uint64_t*>(base + sizeof(double) * C::VAL_DOUBLES + sizeof(int32_t) * C::COL_INTS);
+  }
+};
+
+// One-time per-CTA setup: carve dynamic shared memory, initialise the mbarrier.
+template <int BS>
+__device__ __forceinline__ SpmvSmem<BS> spmv_smem_init(unsigned char* base) {
+  SpmvSmem<BS> sm(base);
+  if (threadIdx.x == 0) {
+    mbar_init(sm.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncthreads();
+  return sm;
+}
+
+// Stream tile [s, s+nblk) of (val, col) into shared memory.  Called by ONE thread.  The bulk
+// copies cover the 16-byte aligned interior; the unaligned head / tail elements (at most one
+// double, three ints each side) are moved with plain loads by the same thread before it
+// arrives on the barrier (arrive = release, so waiters see them).  Returns nothing; the
+// element offsets (val_head, col_head) are recomputed by every thread with tile_heads().
+template <int BS>
+__device__ __forceinline__ void issue_tile(const SpmvSmem<BS>& sm, const double* __restrict__ val,
+                                           const int32_t* __restrict__ col, int64_t s, int nblk) {
+  constexpr int BB = BS * BS;
+  const double* vsrc = val + s * BB;
+  const int32_t* csrc = col + s;
+  const int vhead = (int)((reinterpret_cast<uintptr_t>(vsrc) & 15) >> 3);  // 0 or 1 doubles
+  const int chead = (int)((reinterpret_cast<uintptr_t>(csrc) & 15) >> 2);  // 0..3 ints
+  const int nv = nblk * BB, ncol = nblk;
+  // aligned interior in elements relative to the tile start
+  const int vb = vhead ? 1 : 0;                    // first element at a 16-byte boundary
+  const int ve = vb + ((nv - vb) & ~1);            // multiple of 2 doubles
+  const int cb = chead ? (4 - chead) : 0;
+  const int cbeg = cb < ncol ? cb : ncol;
+  const int cend = cbeg + ((ncol - cbeg) & ~3);
+  uint32_t bytes = 0;
+  fence_proxy_async();
+  if (ve > vb) {
+    bulk_g2s(sm.val + vhead + vb, vsrc + vb, (uint32_t)(ve - vb) * 8u, sm.bar);
+    bytes += (uint32_t)(ve - vb) * 8u;
+  }
+  if (cend > cbeg) {
+    bulk_g2s(sm.col + chead + cbeg, csrc + cbeg, (uint32_t)(cend - cbeg) * 4u, sm.bar);
+    bytes += (uint32_t)(cend - cbeg) * 4u;
+  }
+  for (int e = 0; e < vb; ++e) sm.val[vhead + e] = vsrc[e];
+  for (int e = ve; e < nv; ++e) sm.val[vhead + e] = vsrc[e];
+  for (int e = 0; e < cbeg; ++e) sm.col[chead + e] = csrc[e];
+  for (int e = cend; e < ncol; ++e) sm.col[chead + e] = csrc[e];
+  mbar_arrive_expect_tx(sm.bar, bytes);
+}
+
+// Computes block rows [row0, row0+nr) of y = A x.  On return thread (warp w, lane l) with
+// l < ROWS_PER_WARP*BS holds in `acc` the result for scalar row
+//   out = (row0 + w*ROWS_PER_WARP + l/BS)*BS + l%BS      (valid iff that block row < row0+nr);
+// `out` is returned (-1 when the thread owns no row).  `phase` is the CTA's mbarrier parity
+// (in/out).  All threads of the CTA must call this together.
+template <int BS>
+__device__ __forceinline__ int64_t spmv_row_block(const SpmvSmem<BS>& sm, const int64_t* __restrict__ rowptr,
+                                                  const int32_t* __restrict__ col,
+                                                  const double* __restrict__ val,
+                                                  const double* __restrict__ x, int64_t row0, int nr,
+                                                  uint32_t& phase, double& acc_out) {
   using C = SpmvCfg<BS>;
   constexpr int BB = BS * BS;
-  const int tid = threadIdx.x;
-  if (tid <= nr) smem_rp[tid] = rowptr[row0 + tid];
-  __syncthreads();
-  const int64_t k0 = smem_rp[0], k1 = smem_rp[nr];
-  const int lr = tid / BS, li = tid - lr * BS;
-  const bool rowthread = tid < nr * BS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = warp * C::ROWS_PER_WARP + lane / BS;
+  const int j = lane % BS;
+  const bool active = (lane < C::ROWS_PER_WARP * BS) && (lr < nr);
+  const int64_t k0 = __ldg(rowptr + row0), k1 = __ldg(rowptr + row0 + nr);
   int64_t rb = 0, re = 0;
-  if (rowthread) { rb = smem_rp[lr]; re = smem_rp[lr + 1]; }
-  double acc = 0.0;
-  if (k0 == k1) __syncthreads();  // keep smem_rp stable until every thread has read it
-  for (int64_t s = k0; s < k1; s += C::T) {
-    const int64_t tile_blocks = (k1 - s < C::T) ? (k1 - s) : C::T;
-    const int tile_elems = (int)tile_blocks * BB;
-    const double* vsrc = val + s * BB;
-#pragma unroll 4
-    for (int e = tid; e < tile_elems; e += C::THREADS) {
-      const int blk = e / BB;
-      const int j = (e - blk * BB) % BS;
-      const int32_t cidx = __ldg(col + s + blk);
-      const double a = __ldcs(vsrc + e);  // streamed once: evict-first
-      smem_tile[e] = a * __ldg(x + (int64_t)cidx * BS + j);
-    }
-    __syncthreads();
-    if (rowthread) {
-      const int64_t b = (rb > s ? rb : s) - s;
-      const int64_t e2 = (re < s + tile_blocks ? re : s + tile_blocks) - s;
-      for (int64_t k = b; k < e2; ++k) {
+  if (active) { rb = __ldg(rowptr + row0 + lr); re = __ldg(rowptr + row0 + lr + 1); }
+  double acc[BS];
 #pragma unroll
-        for (int j = 0; j < BS; ++j) acc += smem_tile[k * BB + li * BS + j];
+  for (int i = 0; i < BS; ++i) acc[i] = 0.0;
+  for (int64_t s = k0; s < k1; s += C::T) {
+    const int nblk = (int)((k1 - s < C::T) ? (k1 - s) : C::T);
+    if (tid == 0) issue_tile<BS>(sm, val, col, s, nblk);
+    const int vhead = (int)((reinterpret_cast<uintptr_t>(val + s * BB) & 15) >> 3);
+    const int chead = (int)((reinterpret_cast<uintptr_t>(col + s) & 15) >> 2);
+    mbar_wait(sm.bar, phase);
+    phase ^= 1u;
+    if (active) {
+      const int b = (int)((rb > s ? rb : s) - s);
+      const int e = (int)((re < s + nblk ? re : s + nblk) - s);
+      const double* sv = sm.val + vhead;
+      const int32_t* sc = sm.col + chead;
+#pragma unroll 4
+      for (int k = b; k < e; ++k) {
+        const int32_t c = sc[k];
+        const double xv = __ldg(x + (int64_t)c * BS + j);
+#pragma unroll
+        for (int i = 0; i < BS; ++i) acc[i] = fma(sv[k * BB + i * BS + j], xv, acc[i]);
       }
     }
-    __syncthreads();
+    __syncthreads();  // the tile is consumed: the next bulk copy may overwrite it
   }
-  return acc;
+  // transpose-reduce the BS partial vectors of a row: thread j ends with y_j
+  double y = acc[0];
+  if constexpr (BS > 1) {
+    const int base = lane - j;
+    double mine = 0.0;
+#pragma unroll
+    for (int i = 0; i < BS; ++i) mine = (i == j) ? acc[i] : mine;
+    y = mine;
+#pragma unroll
+    for (int d = 1; d < BS; ++d) {
+      const int want = (j - d + BS) % BS;  // element the lane d positions "below" needs from us
+      double send = 0.0;
+#pragma unroll
+      for (int i = 0; i < BS; ++i) send = (i == want) ? acc[i] : send;
+      int src = base + (j + d) % BS;
+      src = src < 32 ? src : lane;
+      const double recv = __shfl_sync(0xffffffffu, send, src);
+      y += recv;
+    }
+  }
+  acc_out = y;
+  return active ? (row0 + lr) * BS + j : -1;
 }
 
 }  // namespace cb
