@@ -6,7 +6,7 @@ elasticity matrix assembly + state assemble+solve + adjoint assemble+solve + sha
 vector assembly + elasticity Riesz solve + shape BCs + g^T A g + one trial mesh move
 (a-priori det(I+grad V) test, coordinate update, intersection test, mesh quality) + revert.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--n CELLS_PER_EDGE] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mesh-n CELLS_PER_EDGE] [--impl reference]
 
 N > 1 is launched by torchrun (one rank per GPU); the mesh is partitioned into vertex slabs,
 halo exchange + all-reduces go over NCCL; `value` is whole-mesh evaluations per second.
@@ -214,7 +214,7 @@ def main() -> None:
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=119, help="cells per cube edge (119 -> 10.1M tets, BASELINE configs[1])")
+    ap.add_argument("--mesh-n", dest="n", type=int, default=119, help="cells per cube edge (119 -> 10.1M tets, BASELINE configs[1])")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
