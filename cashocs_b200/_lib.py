@@ -66,6 +66,37 @@ class cb_mat(C.Structure):
     ]
 
 
+class cb_amg_level(C.Structure):
+    _fields_ = [
+        ("A", cb_mat),
+        ("dinv", C.c_void_p),
+        ("lmax", C.c_double),
+        ("nc", C.c_int64),
+        ("p_rowptr", C.c_void_p),
+        ("p_col", C.c_void_p),
+        ("p_val", C.c_void_p),
+        ("pt_rowptr", C.c_void_p),
+        ("pt_col", C.c_void_p),
+        ("pt_val", C.c_void_p),
+        ("x", C.c_void_p),
+        ("b", C.c_void_p),
+        ("t", C.c_void_p),
+        ("d", C.c_void_p),
+    ]
+
+
+class cb_amg(C.Structure):
+    _fields_ = [
+        ("nlevels", C.c_int32),
+        ("smooth_degree", C.c_int32),
+        ("coarse_degree", C.c_int32),
+        ("pad", C.c_int32),
+        ("smooth_ratio", C.c_double),
+        ("coarse_ratio", C.c_double),
+        ("levels", C.c_void_p),
+    ]
+
+
 class cb_ksp_opts(C.Structure):
     _fields_ = [
         ("ksp_type", C.c_int32),
@@ -80,6 +111,7 @@ class cb_ksp_opts(C.Structure):
         ("monitor", C.c_int32),
         ("profile_every", C.c_int32),
         ("pad", C.c_int32),
+        ("amg", C.c_void_p),
     ]
 
 
@@ -124,6 +156,9 @@ SIGNATURES = {
     "cb_ksp_workspace_len": (I64, [I64, I64, C.POINTER(cb_ksp_opts)]),
     "cb_ksp_solve": (I32, [P, C.POINTER(cb_mat), P, P, C.POINTER(cb_ksp_opts), P, P, I64,
                            C.POINTER(cb_ksp_result), P, I64]),
+    "cb_amg_block_trace": (I32, [P, C.POINTER(cb_mat), P]),
+    "cb_amg_smooth_prolongator": (I32, [P, C.POINTER(cb_mat), DBL, P, P, P, P]),
+    "cb_amg_galerkin": (I32, [P, C.POINTER(cb_mat), P, P, P, P, P, P, P, P, P, C.POINTER(cb_mat)]),
     "cb_mesh_quality": (I32, [P, I32, I64, P, P, I32, P, P, P, I64]),
     "cb_det_check": (I32, [P, I32, I64, P, P, P, DBL, P, P, P, I64]),
     "cb_gradient_frobenius_max": (I32, [P, I32, I64, P, P, P, P, P, I64]),

@@ -23,7 +23,10 @@
 namespace cb {
 
 int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
-                  double* result, double* scratch);
+                  double* result, double* scratch, const int* done = nullptr);
+int amg_restrict(cudaStream_t s, int bs, const cb_amg_level* L, const double* b, const double* t, double* bc,
+                 const int* done);
+int amg_prolong(cudaStream_t s, int bs, const cb_amg_level* L, const double* xc, double* x, const int* done);
 int dist_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs, double* sendbuf);
 int dist_allreduce_sum(cudaStream_t s, cb_dist* d, double* buf, int n);
 int64_t dist_send_len(const cb_dist* d);
@@ -244,7 +247,8 @@ k_cheb_step(int64_t n, const double* __restrict__ r, const double* __restrict__ 
   if (st->done) return;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const double di = c1 * d[i] + c2 * dinv[i] * (r[i] - t[i]);
+    const double dprev = (c1 != 0.0) ? d[i] : 0.0;  // c1 == 0: first step from a non-zero guess
+    const double di = c1 * dprev + c2 * dinv[i] * (r[i] - t[i]);
     d[i] = di;
     z[i] += di;
   }
@@ -495,7 +499,69 @@ struct Solver {
   }
   int plain_spmv(double* x, double* y) {
     if (dist) { if (int e = dist_halo_exchange(s, dist, x, bs, sendbuf)) return e; }
-    return spmv_dispatch(s, A, x, y, nullptr, nullptr, nullptr);
+    return spmv_dispatch(s, A, x, y, nullptr, nullptr, nullptr, &st->done);
+  }
+
+  static void cheb_coefficients(double lmax, double ratio, int degree, double& inv_theta,
+                                std::pair<double, double>* coef) {
+    const double lmin = lmax / ratio;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
+    const double sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    inv_theta = 1.0 / theta;
+    for (int j = 1; j < degree; ++j) {
+      const double rho_new = 1.0 / (2.0 * sigma - rho);
+      coef[j] = {rho_new * rho, 2.0 * rho_new / delta};
+      rho = rho_new;
+    }
+  }
+
+  // `degree` Chebyshev-Jacobi steps on A_l x = b (zero or current initial guess); local operator
+  int amg_smooth(const cb_amg_level& L, const double* bl, double* xl, int degree, double ratio, bool zero_guess) {
+    const int64_t nl = L.A.nrows * bs;
+    int g = grid_for(nl, 256, 4);
+    std::pair<double, double> coef[64];
+    double inv_theta = 0.0;
+    cheb_coefficients(L.lmax, ratio, degree, inv_theta, coef);
+    int j0 = 0;
+    if (zero_guess) {
+      k_cheb_first<<<g, 256, 0, s>>>(nl, bl, L.dinv, inv_theta, L.d, xl, st);
+      CB_LAUNCH_CHECK();
+      j0 = 1;
+    }
+    for (int j = j0; j < degree; ++j) {
+      if (int e = spmv_dispatch(s, &L.A, xl, L.t, nullptr, nullptr, nullptr, &st->done)) return e;
+      const double c1 = (j == 0) ? 0.0 : coef[j].first;
+      const double c2 = (j == 0) ? inv_theta : coef[j].second;
+      k_cheb_step<<<g, 256, 0, s>>>(nl, bl, L.t, L.dinv, c1, c2, L.d, xl, st);
+      CB_LAUNCH_CHECK();
+    }
+    return CB_OK;
+  }
+
+  // z = M^-1 r : one symmetric V-cycle (pre/post Chebyshev smoothing, Chebyshev coarsest solve)
+  int amg_vcycle(const cb_amg* h, const double* r, double* z) {
+    const int L = h->nlevels;
+    for (int l = 0; l < L; ++l) {
+      const cb_amg_level& lev = h->levels[l];
+      const double* bl = (l == 0) ? r : lev.b;
+      double* xl = (l == 0) ? z : lev.x;
+      if (l == L - 1) {
+        if (int e = amg_smooth(lev, bl, xl, h->coarse_degree, h->coarse_ratio, true)) return e;
+        break;
+      }
+      if (int e = amg_smooth(lev, bl, xl, h->smooth_degree, h->smooth_ratio, true)) return e;
+      if (int e = spmv_dispatch(s, &lev.A, xl, lev.t, nullptr, nullptr, nullptr, &st->done)) return e;
+      if (int e = amg_restrict(s, bs, &lev, bl, lev.t, h->levels[l + 1].b, &st->done)) return e;
+    }
+    for (int l = L - 2; l >= 0; --l) {
+      const cb_amg_level& lev = h->levels[l];
+      const double* bl = (l == 0) ? r : lev.b;
+      double* xl = (l == 0) ? z : lev.x;
+      if (int e = amg_prolong(s, bs, &lev, h->levels[l + 1].x, xl, &st->done)) return e;
+      if (int e = amg_smooth(lev, bl, xl, h->smooth_degree, h->smooth_ratio, false)) return e;
+    }
+    return CB_OK;
   }
   int reduce_and_step(int nsums, int which, bool minres) {
     if (!dist) return CB_OK;
@@ -591,7 +657,9 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
   double lmax_h = 0.0;
   if (use_pc) {
     double* lmax_dev = (o->pc_type == CB_PC_CHEBYSHEV) ? &st->sums[3] : nullptr;
-    if (int e = diag_inv_launch(s, A, dinv, lmax_dev, scratch)) return e;
+    if (o->pc_type != CB_PC_AMG) {
+      if (int e = diag_inv_launch(s, A, dinv, lmax_dev, scratch)) return e;
+    }
     if (lmax_dev) {
       if (dist) { if (int e = cb_dist_allreduce(stream, dist, lmax_dev, 1, 2)) return e; }
       CB_CUDA_CHECK(cudaMemcpyAsync(&lmax_h, lmax_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -607,7 +675,7 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
     return CB_OK;
   };
   int rc = CB_OK;
-  const int check_every = o->check_every > 0 ? o->check_every : 25;
+  const int check_every = o->check_every > 0 ? o->check_every : (o->pc_type == CB_PC_AMG ? 4 : 25);
 
   if (o->ksp_type == CB_KSP_PREONLY) {
     CB_REQUIRE(o->pc_type == CB_PC_JACOBI, "preonly supports pc_type jacobi only (no direct solver on the device)");
@@ -621,11 +689,17 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
   }
 
   if (o->ksp_type == CB_KSP_CG) {
-    const bool cheb = o->pc_type == CB_PC_CHEBYSHEV;
+    const bool amg = o->pc_type == CB_PC_AMG;
+    const bool cheb = o->pc_type == CB_PC_CHEBYSHEV || amg;  // "general" (non-fused) preconditioner path
+    if (amg) {
+      CB_REQUIRE(o->amg && o->amg->nlevels >= 1 && o->amg->levels, "pc_type amg needs a hierarchy (cb_ksp_opts.amg)");
+      CB_REQUIRE(o->amg->smooth_degree >= 1 && o->amg->smooth_degree <= 64 && o->amg->coarse_degree >= 1 &&
+                 o->amg->coarse_degree <= 64, "amg smoother degrees must be in 1..64");
+    }
     // Chebyshev coefficients (fixed polynomial -> a linear SPD preconditioner)
     std::pair<double, double> coef[64];
     double inv_theta = 0.0;
-    if (cheb) {
+    if (cheb && !amg) {
       CB_REQUIRE(o->cheb_degree <= 64, "chebyshev degree > 64");
       const double ratio = o->cheb_ratio > 1.0 ? o->cheb_ratio : 30.0;
       const double lmax = lmax_h, lmin = lmax / ratio;
@@ -640,6 +714,7 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
       }
     }
     auto apply_cheb = [&]() -> int {  // z = P(r)
+      if (amg) return S.amg_vcycle(o->amg, r, z);
       k_cheb_first<<<vg, 256, 0, s>>>(n, r, dinv, inv_theta, cd, z, st);
       CB_LAUNCH_CHECK();
       for (int j = 1; j < o->cheb_degree; ++j) {

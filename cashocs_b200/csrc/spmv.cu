@@ -4,11 +4,16 @@
 
 namespace cb {
 
+int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
+                  double* result, double* scratch, const int* done);
+
 template <int BS, bool WRITE_Y, bool DOT>
 __global__ void __launch_bounds__(SpmvCfg<BS>::THREADS)
 k_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
        const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
-       const double* __restrict__ w, double* __restrict__ result, double* __restrict__ scratch) {
+       const double* __restrict__ w, double* __restrict__ result, double* __restrict__ scratch,
+       const int* __restrict__ done) {
+  if (done && *done) return;
   using C = SpmvCfg<BS>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[33];
@@ -97,7 +102,7 @@ int prefer_smem(K kernel) {
 
 template <int BS>
 int launch_spmv(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
-                double* result, double* scratch) {
+                double* result, double* scratch, const int* done) {
   using C = SpmvCfg<BS>;
   const int grid = spmv_grid<BS>(A->nrows);
   static bool configured = false;
@@ -108,11 +113,11 @@ int launch_spmv(cudaStream_t s, const cb_mat* A, const double* x, double* y, con
     configured = true;
   }
   if (y && !w)
-    k_spmv<BS, true, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, x, y, nullptr, nullptr, nullptr);
+    k_spmv<BS, true, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, x, y, nullptr, nullptr, nullptr, done);
   else if (y && w)
-    k_spmv<BS, true, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, x, y, w, result, scratch);
+    k_spmv<BS, true, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, x, y, w, result, scratch, done);
   else
-    k_spmv<BS, false, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, x, nullptr, w, result, scratch);
+    k_spmv<BS, false, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, x, nullptr, w, result, scratch, done);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
@@ -126,12 +131,12 @@ int diag_inv_launch(cudaStream_t s, const cb_mat* A, double* dinv, double* lmax,
 }
 
 int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
-                  double* result, double* scratch) {
+                  double* result, double* scratch, const int* done) {
   CB_REQUIRE(A && A->rowptr && A->col && A->val && x, "cb_spmv: missing argument");
   switch (A->bs) {
-    case 1: return launch_spmv<1>(s, A, x, y, w, result, scratch);
-    case 2: return launch_spmv<2>(s, A, x, y, w, result, scratch);
-    case 3: return launch_spmv<3>(s, A, x, y, w, result, scratch);
+    case 1: return launch_spmv<1>(s, A, x, y, w, result, scratch, done);
+    case 2: return launch_spmv<2>(s, A, x, y, w, result, scratch, done);
+    case 3: return launch_spmv<3>(s, A, x, y, w, result, scratch, done);
   }
   set_error("cb_spmv: unsupported block size %d", A->bs);
   return CB_ERR_UNSUPPORTED;
@@ -145,14 +150,14 @@ extern "C" int64_t cb_reduce_scratch_len(void) { return RED_SCRATCH_LEN; }
 
 extern "C" int cb_spmv(void* stream, const cb_mat* A, const double* x, double* y) {
   CB_REQUIRE(y != nullptr, "cb_spmv: y is NULL");
-  return spmv_dispatch(as_stream(stream), A, x, y, nullptr, nullptr, nullptr);
+  return spmv_dispatch(as_stream(stream), A, x, y, nullptr, nullptr, nullptr, nullptr);
 }
 
 extern "C" int cb_scalar_product(void* stream, const cb_mat* A, const double* x, const double* y,
                                  double* result_dev, double* scratch, int64_t scratch_len) {
   CB_REQUIRE(scratch && scratch_len >= RED_SCRATCH_LEN, "cb_scalar_product: scratch too small");
   CB_REQUIRE(y && result_dev, "cb_scalar_product: missing argument");
-  return spmv_dispatch(as_stream(stream), A, x, nullptr, y, result_dev, scratch);
+  return spmv_dispatch(as_stream(stream), A, x, nullptr, y, result_dev, scratch, nullptr);
 }
 
 extern "C" int cb_dot(void* stream, int64_t n, const double* x, const double* y, double* result_dev,

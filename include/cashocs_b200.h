@@ -182,6 +182,40 @@ int cb_extract_diag_inv(void* stream, const cb_mat* A, double* dinv, double* lma
 #define CB_PC_NONE 0
 #define CB_PC_JACOBI 1
 #define CB_PC_CHEBYSHEV 2
+#define CB_PC_AMG 3
+
+/* Smoothed-aggregation AMG hierarchy (device counterpart of `pc_type hypre|gamg`, the reference's
+ * iterative default cashocs/_utils/linalg.py:44-52).  All arrays are caller-owned device memory;
+ * the symbolic data (patterns) is built once per sparsity pattern by the host layer, the values by
+ * cb_amg_smooth_prolongator / cb_amg_galerkin for every new matrix.  P = P_s (x) I_bs: a scalar
+ * CSR prolongator applied to every component, so each level keeps the block size of the fine
+ * matrix.  Level l < nlevels-1 owns the prolongator from level l+1. */
+typedef struct {
+  cb_mat A;                 /* level operator */
+  const double* dinv;       /* [A.nrows*bs] inverse diagonal (Jacobi / Chebyshev smoother) */
+  double lmax;              /* upper bound of the spectrum of D^-1 A (Gershgorin) */
+  int64_t nc;               /* number of coarse nodes (0 on the last level) */
+  const int64_t* p_rowptr;  /* P  : [A.nrows] rows, nc columns */
+  const int32_t* p_col;
+  const double* p_val;
+  const int64_t* pt_rowptr; /* P^T: [nc] rows */
+  const int32_t* pt_col;
+  const double* pt_val;
+  double* x;                /* [A.ncols*bs] level iterate   (unused on level 0: caller's z) */
+  double* b;                /* [A.nrows*bs] level rhs       (unused on level 0: caller's r) */
+  double* t;                /* [A.nrows*bs] A*x scratch */
+  double* d;                /* [A.nrows*bs] Chebyshev direction */
+} cb_amg_level;
+typedef struct {
+  int32_t nlevels;
+  int32_t smooth_degree;    /* Chebyshev degree of the pre / post smoother */
+  int32_t coarse_degree;    /* Chebyshev degree of the coarsest-level solve */
+  int32_t pad;
+  double smooth_ratio;      /* smoother interval [lmax/ratio, lmax] */
+  double coarse_ratio;
+  const cb_amg_level* levels; /* host array */
+} cb_amg;
+
 typedef struct {
   int32_t ksp_type;
   int32_t pc_type;
@@ -193,6 +227,7 @@ typedef struct {
   int32_t monitor;        /* 1: record the residual history (hist, up to hist_len) */
   int32_t profile_every;  /* >0: bracket every profile_every-th SpMV launch with CUDA events */
   int32_t pad;
+  const cb_amg* amg;      /* hierarchy for pc_type CB_PC_AMG (NULL otherwise) */
 } cb_ksp_opts;
 typedef struct {
   int32_t reason;
@@ -215,6 +250,17 @@ int64_t cb_ksp_workspace_len(int64_t n, int64_t nc, const cb_ksp_opts* opts);
 int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, double* x,
                  const cb_ksp_opts* opts, cb_dist* dist, double* work, int64_t work_len,
                  cb_ksp_result* result, double* hist, int64_t hist_len);
+
+/* AMG numeric phase.  s_val [nnzb] = trace(A_blk)/bs (the scalar strength matrix S). */
+int cb_amg_block_trace(void* stream, const cb_mat* A, double* s_val);
+/* P = T - omega D_S^-1 S T for the piecewise-constant tentative prolongator T of `agg` [nrows]. */
+int cb_amg_smooth_prolongator(void* stream, const cb_mat* S, double omega, const int32_t* agg,
+                              const int64_t* p_rowptr, const int32_t* p_col, double* p_val);
+/* Ac = P^T A P through AP = A*P (pattern ap_rowptr/ap_col, scratch values ap_val [nnz(AP)*bs*bs]). */
+int cb_amg_galerkin(void* stream, const cb_mat* A, const int64_t* p_rowptr, const int32_t* p_col,
+                    const double* p_val, const int64_t* pt_rowptr, const int32_t* pt_col,
+                    const double* pt_val, const int64_t* ap_rowptr, const int32_t* ap_col,
+                    double* ap_val, const cb_mat* Ac);
 
 /* ------------------------------------------------------------------ mesh kernels */
 #define CB_Q_SKEWNESS 0

@@ -1,0 +1,110 @@
+"""GPU: smoothed-aggregation AMG (device counterpart of pc_type hypre / gamg): Galerkin
+operators against scipy, PCG solutions against a direct solve, determinism."""
+
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+import torch
+
+import cashocs_b200 as cb
+from cashocs_b200._forms import forms
+from cashocs_b200._utils import amg, linalg
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def demo_poly(dim):
+    x = cb.spatial_coordinate(dim)
+    return 2.5 * (x[0] + 0.4 - x[1] ** 2) ** 2 + x[0] ** 2 + x[1] ** 2 - 1
+
+
+def systems(kind):
+    if kind == "cube":
+        dm = cb.regular_mesh(14, 1.0, 1.0, 1.0)
+        markers = [1, 2, 3, 4, 5, 6]
+    elif kind == "square":
+        dm = cb.regular_mesh(48)
+        markers = [1, 2, 3, 4]
+    else:
+        dm = cb.import_mesh(os.path.join(GOLDEN, "mesh3d.npz"))
+        markers = [1, 2]
+    flag, val = forms.bc_flag_arrays(dm, forms.create_dirichlet_bcs(0.0, markers), 1)
+    A, b = linalg.assemble_scalar_system(dm, 1.0, 0.0, f_poly=demo_poly(dm.dim), bc_flag=flag, bc_val=val)
+    mu = torch.full((dm.num_vertices,), 0.35714285714285715, dtype=torch.float64, device="cuda")
+    E = linalg.assemble_elasticity_matrix(dm, mu, 1.428571428571429, 0.2)
+    rhs = torch.from_numpy(np.random.RandomState(1).rand(dm.dim * dm.num_vertices) - 0.5).cuda()
+    return dm, A, b, E, rhs
+
+
+def csr(rowptr, col, val, shape):
+    return sp.csr_matrix((val.cpu().numpy(), col.cpu().numpy(), rowptr.cpu().numpy()), shape=shape)
+
+
+@pytest.mark.parametrize("kind", ["cube", "square", "mesh3d"])
+def test_hierarchy_is_galerkin(kind):
+    dm, A, b, E, rhs = systems(kind)
+    for M in (A, E):
+        h = amg.AMGHierarchy(M, min_coarse=50)
+        h.numeric(M)
+        assert len(h.levels) >= 2 and h.operator_complexity < 2.5
+        bs = M.bs
+        cur = M.to_scipy()
+        for li, L in enumerate(h.levels[:-1]):
+            nxt = h.levels[li + 1]
+            P = csr(L.p_rowptr, L.p_col, L.p_val, (L.n, L.nc))
+            Pt = csr(L.pt_rowptr, L.pt_col, L.pt_val, (L.nc, L.n))
+            assert abs(Pt - P.T).max() == 0.0
+            # partition of unity of the smoothed prolongator on interior rows: row sums of P == 1 - w*rowsum(S)/S_ii
+            assert np.all(np.diff(L.p_rowptr.cpu().numpy()) >= 1)
+            Pb = sp.kron(P, sp.identity(bs)).tocsr() if bs > 1 else P
+            ref = (Pb.T @ cur @ Pb).tocsr()
+            if bs == 1:
+                got = csr(nxt.rowptr, nxt.col, nxt.val, (nxt.n, nxt.n))
+            else:
+                got = sp.bsr_matrix((nxt.val.cpu().numpy().reshape(-1, bs, bs), nxt.col.cpu().numpy(), nxt.rowptr.cpu().numpy()),
+                                    shape=(nxt.n * bs, nxt.n * bs)).tocsr()
+            assert abs(got - ref).max() <= 1e-12 * abs(ref).max()
+            cur = got
+        # aggregates cover every node exactly once
+        agg = h.levels[0].agg.cpu().numpy()
+        assert agg.min() == 0 and agg.max() == h.levels[0].nc - 1 and np.unique(agg).size == h.levels[0].nc
+
+
+@pytest.mark.parametrize("kind", ["cube", "square", "mesh3d"])
+@pytest.mark.parametrize("pc", ["hypre", "gamg"])
+def test_amg_pcg_matches_direct_solve(kind, pc):
+    dm, A, b, E, rhs = systems(kind)
+    for M, f in ((A, b), (E, rhs)):
+        n = M.nrows * M.bs
+        x = torch.zeros(n, dtype=torch.float64, device="cuda")
+        opts = {"ksp_type": "cg", "pc_type": pc, "ksp_rtol": 1e-11, "ksp_atol": 1e-30, "ksp_max_it": 500, "ksp_monitor": None}
+        if pc == "hypre":
+            opts["pc_hypre_type"] = "boomeramg"
+        res = cb.LinearSolver().solve(x, A=M, b=f, ksp_options=opts)
+        xj = torch.zeros_like(x)
+        resj = cb.LinearSolver().solve(xj, A=M, b=f, ksp_options={"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-11,
+                                                               "ksp_atol": 1e-30, "ksp_max_it": 20000})
+        assert res.reason == 2 and res.its < resj.its
+        assert np.all(np.diff(res.history) < 0) or res.history[-1] <= 1e-11 * res.history[0]
+        xd = spla.spsolve(M.to_scipy().tocsc(), f.cpu().numpy())
+        assert np.max(np.abs(x.cpu().numpy() - xd)) < 1e-8 * np.max(np.abs(xd))
+        # bitwise reproducible
+        x2 = torch.zeros_like(x)
+        res2 = cb.LinearSolver().solve(x2, A=M, b=f, ksp_options=opts)
+        assert res2.its == res.its and torch.equal(x, x2)
+
+
+def test_reference_iterative_defaults_use_amg():
+    """cashocs/_utils/linalg.py:44-52 (cg + boomeramg, rtol 1e-20 clamped) runs on the device AMG."""
+    dm, A, b, E, rhs = systems("cube")
+    o = linalg.parse_ksp_options(linalg.iterative_ksp_options)
+    assert o.pc_type == 3 and o.rtol == 1e-14
+    x = torch.zeros(A.nrows, dtype=torch.float64, device="cuda")
+    opts = dict(linalg.iterative_ksp_options)
+    opts["ksp_rtol"] = 1e-9  # gradient_tol (shape_gradient_problem.py:87-91)
+    res = cb.LinearSolver().solve(x, A=A, b=b, ksp_options=opts)
+    assert res.reason == 2 and res.its <= 40
