@@ -31,7 +31,10 @@ if ROOT not in sys.path:
 
 METRIC = "shape_gradient_evals_per_s"
 UNIT = "evals/s"
-KSP = {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_atol": 1e-30, "ksp_max_it": 20000}
+# the reference's iterative default (cashocs/_utils/linalg.py:44-52: cg + hypre/boomeramg) at rtol 1e-10;
+# `--pc jacobi` selects the one-level variant of SURVEY.md 8d
+KSP = {"ksp_type": "cg", "pc_type": "hypre", "pc_hypre_type": "boomeramg", "ksp_rtol": 1e-10, "ksp_atol": 1e-30,
+       "ksp_max_it": 20000}
 SHAPE = dict(lambda_lame=1.428571428571429, damping_factor=0.2, mu=0.35714285714285715)
 ALL_MARKERS = [1, 2, 3, 4, 5, 6]
 
@@ -39,7 +42,7 @@ ALL_MARKERS = [1, 2, 3, 4, 5, 6]
 def workload_name(n: int, n_gpus: int) -> str:
     tets = 6 * n**3
     return (f"unit-cube regular_mesh({n},1,1,1): {tets} tets / {(n + 1) ** 3} vertices, P1 Poisson state+adjoint, "
-            f"vector-P1 elasticity Riesz shape gradient, cg+jacobi rtol 1e-10, trial move + quality; {n_gpus} GPU(s)")
+            f"vector-P1 elasticity Riesz shape gradient, cg+{KSP['pc_type']} rtol 1e-10, trial move + quality; {n_gpus} GPU(s)")
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -106,7 +109,8 @@ def oracle_eval_seconds(n_sample: int, repeats: int = 1):
     cfg = pipeline.ShapeConfig(shape_bdry_def=tuple(ALL_MARKERS), lambda_lame=SHAPE["lambda_lame"],
                                damping_factor=SHAPE["damping_factor"], mu_def=SHAPE["mu"], mu_fix=SHAPE["mu"],
                                test_for_intersections=False)
-    ksp = dict(KSP)
+    # the oracle's Krylov restatement is one-level (cg + jacobi); hypre/MUMPS are not installable here
+    ksp = {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_atol": 1e-30, "ksp_max_it": 20000}
     prob = pipeline.PoissonShapeProblem(om, bc_markers=tuple(ALL_MARKERS), config=cfg, state_ksp=ksp, adjoint_ksp=ksp,
                                         gradient_ksp=ksp)
     best = float("inf")
@@ -216,8 +220,11 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--mesh-n", dest="n", type=int, default=119, help="cells per cube edge (119 -> 10.1M tets, BASELINE configs[1])")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pc", default="hypre", choices=["hypre", "jacobi"],
+                    help="pc_type of the three Krylov solves (hypre -> device smoothed-aggregation AMG on 1 GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    KSP["pc_type"] = args.pc
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -312,7 +319,9 @@ def main() -> None:
         roofline = {"bound": "hbm", "kernel": "k_cg_spmv<3> (elasticity PCG: w = A p, fused p.w)", "achieved": achieved,
                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "avg_launch_ms": avg_ms, "launches_profiled": spmv_prof, "algorithmic_bytes_per_launch": alg_bytes,
-                    "spmv_share_of_step": (avg_ms * sum(i[2] for i in its)) / ms}
+                    # fine-level launches per PCG iteration: 1 (w = A p) + 2*degree inside the AMG V-cycle
+                    "spmv_share_of_step": (avg_ms * sum(i[2] for i in its) *
+                                           (5 if (args.pc == "hypre" and dist is None) else 1)) / ms}
 
     if rank == 0:
         line = {
@@ -321,6 +330,8 @@ def main() -> None:
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.n, args.gpus), "n": args.n, "tets": n_tets, "vertices": n_verts,
                        "block_nnz": nnzb_total, "krylov_its_state_adjoint_elasticity": list(its[-1]),
+                       "ksp_options": {k: v for k, v in KSP.items()},
+                       "pc_on_device": ("smoothed-aggregation AMG" if (args.pc == "hypre" and dist is None) else "jacobi"),
                        "l2_policy": "inputs larger than L2 (elasticity matrix %.2f GB, L2 126 MB)" % (76e-9 * nnzb_rank),
                        "parallelism": "1 GPU" if dist is None else f"mesh partitioned into {world} vertex slabs, NCCL halo + allreduce"},
             "clocks": clocks,

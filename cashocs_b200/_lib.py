@@ -59,7 +59,7 @@ class cb_mat(C.Structure):
         ("nrows", C.c_int64),
         ("ncols", C.c_int64),
         ("bs", C.c_int32),
-        ("pad", C.c_int32),
+        ("row_split", C.c_int32),
         ("rowptr", C.c_void_p),
         ("col", C.c_void_p),
         ("val", C.c_void_p),
@@ -94,6 +94,7 @@ class cb_amg(C.Structure):
         ("smooth_ratio", C.c_double),
         ("coarse_ratio", C.c_double),
         ("levels", C.c_void_p),
+        ("coarse_inv", C.c_void_p),
     ]
 
 
@@ -158,7 +159,8 @@ SIGNATURES = {
                            C.POINTER(cb_ksp_result), P, I64]),
     "cb_amg_block_trace": (I32, [P, C.POINTER(cb_mat), P]),
     "cb_amg_smooth_prolongator": (I32, [P, C.POINTER(cb_mat), DBL, P, P, P, P]),
-    "cb_amg_galerkin": (I32, [P, C.POINTER(cb_mat), P, P, P, P, P, P, P, P, P, C.POINTER(cb_mat)]),
+    "cb_amg_spgemm_terms": (I32, [P, I32, I32, I64, P, P, P, P, P, P]),
+    "cb_amg_dense_inverse": (I32, [P, C.POINTER(cb_mat), P, P]),
     "cb_mesh_quality": (I32, [P, I32, I64, P, P, I32, P, P, P, I64]),
     "cb_det_check": (I32, [P, I32, I64, P, P, P, DBL, P, P, P, I64]),
     "cb_gradient_frobenius_max": (I32, [P, I32, I64, P, P, P, P, P, I64]),

@@ -67,14 +67,17 @@ def mis_aggregate(rows: torch.Tensor, cols: torch.Tensor, n: int):
     return agg.to(torch.int32), nc
 
 
-def _expand_unique(lhs_rows, lhs_cols, rhs_rowptr, rhs_col, nrows_out, ncols_out, chunk_rows=400_000):
-    """Pattern of (L * R): unique (row(L), col(R)) pairs, returned as CSR (rowptr, col int32)."""
+def _expand_terms(lhs_rows, lhs_cols, lhs_index, rhs_rowptr, rhs_col, nrows_out, ncols_out, chunk_rows=300_000):
+    """Symbolic sparse product L * R.
+
+    Returns the CSR pattern of the product (rowptr, col) and, for every output entry, the list of
+    contributing (lhs entry, rhs entry) pairs in a fixed order (seg_ptr, src_l, src_r) -- the
+    numeric phase is then a pure gather (``cb_amg_spgemm_terms``).  ``lhs_rows`` must be ascending.
+    """
     dev = lhs_rows.device
     lens_all = rhs_rowptr[1:] - rhs_rowptr[:-1]
-    keys = []
-    # rows of L are sorted ascending: process row ranges so the expansion stays bounded
-    bounds = torch.searchsorted(lhs_rows, torch.arange(0, nrows_out + chunk_rows, chunk_rows, device=dev))
-    bounds = bounds.tolist()
+    keys, counts, sl, sr = [], [], [], []
+    bounds = torch.searchsorted(lhs_rows, torch.arange(0, nrows_out + chunk_rows, chunk_rows, device=dev)).tolist()
     for a, b in zip(bounds[:-1], bounds[1:]):
         if b <= a:
             continue
@@ -85,48 +88,45 @@ def _expand_unique(lhs_rows, lhs_cols, rhs_rowptr, rhs_col, nrows_out, ncols_out
             continue
         rep = torch.repeat_interleave(torch.arange(b - a, device=dev), lens)
         start = torch.cumsum(lens, 0) - lens
-        offs = torch.arange(total, device=dev) - start[rep]
-        j = rhs_col[rhs_rowptr[k][rep] + offs].long()
-        keys.append(torch.unique(i[rep] * ncols_out + j))
-    key = torch.cat(keys) if keys else torch.zeros(0, dtype=torch.int64, device=dev)
+        rpos = rhs_rowptr[k][rep] + (torch.arange(total, device=dev) - start[rep])
+        key = i[rep] * ncols_out + rhs_col[rpos].long()
+        uniq, inv = torch.unique(key, return_inverse=True)
+        order = torch.argsort(inv, stable=True)  # expansion order inside a segment -> fixed summation order
+        keys.append(uniq)
+        counts.append(torch.bincount(inv, minlength=uniq.numel()))
+        sl.append(lhs_index[a:b][rep][order].to(torch.int32))
+        sr.append(rpos[order].to(torch.int32))
+        del rep, start, rpos, key, inv, order
+    key = torch.cat(keys)
+    seg_ptr = torch.zeros(key.numel() + 1, dtype=torch.int64, device=dev)
+    seg_ptr[1:] = torch.cumsum(torch.cat(counts), 0)
     out_rows = key // ncols_out
-    return _rowptr_from_rows(out_rows, nrows_out), (key % ncols_out).to(torch.int32).contiguous()
+    return (_rowptr_from_rows(out_rows, nrows_out), (key % ncols_out).to(torch.int32).contiguous(), seg_ptr,
+            torch.cat(sl).contiguous(), torch.cat(sr).contiguous())
 
 
 class _Level:
     pass
 
 
-class AMGHierarchy:
-    """Hierarchy for one block-CSR sparsity pattern; ``numeric(A)`` refreshes the values."""
+class AMGSymbolic:
+    """Everything that depends only on the sparsity pattern (shared by all block sizes)."""
 
-    def __init__(self, A, max_levels: int = 10, min_coarse: int = 300, smooth_degree: int = 2,
-                 coarse_degree: int = 16, smooth_ratio: float = 4.0, coarse_ratio: float = 40.0) -> None:
-        self.bs = A.bs
-        self.device = A.val.device
-        self.smooth_degree, self.coarse_degree = int(smooth_degree), int(coarse_degree)
-        self.smooth_ratio, self.coarse_ratio = float(smooth_ratio), float(coarse_ratio)
+    MAX_DENSE = 256  # scalar rows of a coarsest level that is inverted densely (bs <= 3 -> <= 85 nodes)
+
+    def __init__(self, rowptr, col, n, ncols, max_levels: int = 12) -> None:
         self.levels: list[_Level] = []
-        self.version = None
-        self._symbolic(A, max_levels, min_coarse)
-        self._struct = None
-        self._level_array = None
-
-    # ------------------------------------------------------------------ symbolic
-    def _symbolic(self, A, max_levels, min_coarse) -> None:
-        dev, bs = self.device, self.bs
-        rowptr, col, n = A.rowptr, A.col, A.nrows
-        ncols = A.ncols
         while True:
             L = _Level()
             L.n, L.ncols, L.rowptr, L.col = n, ncols, rowptr, col
             L.nnzb = int(rowptr[-1].item())
             L.last = True
             self.levels.append(L)
-            if n <= min_coarse or len(self.levels) >= max_levels:
+            if n * 3 <= self.MAX_DENSE or len(self.levels) >= max_levels:
                 break
             rows = _rows_of(rowptr)
             keep = col < n  # local columns only (ghost couplings are not part of the preconditioner)
+            a_index = torch.nonzero(keep).reshape(-1)
             r, c = rows[keep], col[keep].long()
             agg, nc = mis_aggregate(r, c, n)
             if nc >= 0.8 * n or nc < 1:
@@ -140,29 +140,14 @@ class AMGHierarchy:
             L.pt_col = p_rows[order].to(torch.int32).contiguous()
             L.pt_rowptr = _rowptr_from_rows(L.p_col.long()[order], nc)
             L.agg, L.nc = agg.contiguous(), nc
-            L.ap_rowptr, L.ap_col = _expand_unique(r, c, L.p_rowptr, L.p_col, n, nc)
-            c_rowptr, c_col = _expand_unique(_rows_of(L.pt_rowptr), L.pt_col.long(), L.ap_rowptr, L.ap_col, nc, nc)
+            L.ap_rowptr, L.ap_col, L.ap_seg, L.ap_sl, L.ap_sr = _expand_terms(
+                r, c, a_index, L.p_rowptr, L.p_col, n, nc)
+            nnzp = L.p_col.numel()
+            c_rowptr, c_col, L.ac_seg, L.ac_sl, L.ac_sr = _expand_terms(
+                _rows_of(L.pt_rowptr), L.pt_col.long(), torch.arange(nnzp, device=col.device), L.ap_rowptr, L.ap_col,
+                nc, nc)
             L.last = False
             rowptr, col, n, ncols = c_rowptr, c_col, nc, nc
-        f64 = dict(dtype=torch.float64, device=dev)
-        for li, L in enumerate(self.levels):
-            nb = L.n * bs
-            L.val = None if li == 0 else torch.zeros(L.nnzb * bs * bs, **f64)
-            L.dinv = torch.zeros(nb, **f64)
-            L.t = torch.zeros(nb, **f64)
-            L.d = torch.zeros(nb, **f64)
-            L.x = None if li == 0 else torch.zeros(L.ncols * bs, **f64)
-            L.b = None if li == 0 else torch.zeros(nb, **f64)
-            L.lmax = 2.0
-            if not L.last:
-                nnzp = L.p_col.numel()
-                L.p_val = torch.zeros(nnzp, **f64)
-                L.pt_val = torch.zeros(nnzp, **f64)
-                L.ap_val = torch.zeros(L.ap_col.numel() * bs * bs, **f64)
-                L.s_val = torch.zeros(L.nnzb, **f64) if bs > 1 else None
-                L.s_dinv = torch.zeros(L.n, **f64)
-        self.scratch = torch.zeros(int(_lib.load().cb_reduce_scratch_len()), **f64)
-        self.lmax_dev = torch.zeros(1, **f64)
 
     @property
     def sizes(self):
@@ -172,18 +157,101 @@ class AMGHierarchy:
     def operator_complexity(self) -> float:
         return sum(L.nnzb for L in self.levels) / self.levels[0].nnzb
 
+
+class AMGHierarchy:
+    """Values of the hierarchy for one block size; ``numeric(A)`` refreshes them for new matrix values."""
+
+    def __init__(self, A, symbolic: AMGSymbolic | None = None, smooth_degree: int = 2, coarse_degree: int = 16,
+                 smooth_ratio: float = 4.0, coarse_ratio: float = 40.0) -> None:
+        self.bs = bs = A.bs
+        self.device = dev = A.val.device
+        self.smooth_degree, self.coarse_degree = int(smooth_degree), int(coarse_degree)
+        self.smooth_ratio, self.coarse_ratio = float(smooth_ratio), float(coarse_ratio)
+        self.symbolic = symbolic if symbolic is not None else AMGSymbolic(A.rowptr, A.col, A.nrows, A.ncols)
+        self.levels = self.symbolic.levels
+        self.version = None
+        self.power_its = 12
+        self._power_x: dict = {}
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.data = []
+        for li, L in enumerate(self.levels):
+            D = _Level()
+            nb = L.n * bs
+            D.val = None if li == 0 else torch.zeros(L.nnzb * bs * bs, **f64)
+            D.dinv = torch.zeros(nb, **f64)
+            D.t = torch.zeros(nb, **f64)
+            D.d = torch.zeros(nb, **f64)
+            D.x = None if li == 0 else torch.zeros(L.ncols * bs, **f64)
+            D.b = None if li == 0 else torch.zeros(nb, **f64)
+            D.lmax = 2.0
+            if not L.last:
+                nnzp = L.p_col.numel()
+                D.p_val = torch.zeros(nnzp, **f64)
+                D.pt_val = torch.zeros(nnzp, **f64)
+                D.ap_val = torch.zeros(L.ap_col.numel() * bs * bs, **f64)
+                D.s_val = torch.zeros(L.nnzb, **f64) if bs > 1 else None
+                D.s_dinv = torch.zeros(L.n, **f64)
+            self.data.append(D)
+        last = self.levels[-1]
+        self.coarse_inv = self.coarse_work = None
+        if last.n * bs <= AMGSymbolic.MAX_DENSE and len(self.levels) > 1:
+            nn = last.n * bs
+            self.coarse_inv = torch.zeros(nn * nn, **f64)
+            self.coarse_work = torch.zeros(2 * nn * nn, **f64)
+        self.scratch = torch.zeros(int(_lib.load().cb_reduce_scratch_len()), **f64)
+        self.lmax_dev = torch.zeros(1, **f64)
+        self._struct = None
+        self._level_array = None
+
+    @property
+    def sizes(self):
+        return self.symbolic.sizes
+
+    @property
+    def operator_complexity(self) -> float:
+        return self.symbolic.operator_complexity
+
     # ------------------------------------------------------------------ numeric
     def _mat(self, L, val, bs) -> _lib.cb_mat:
+        from cashocs_b200._utils import linalg
+
         m = _lib.cb_mat()
         m.nrows, m.ncols, m.bs = L.n, L.ncols, bs
+        m.row_split = linalg.row_split_hint(L.nnzb, L.n)
         m.rowptr, m.col, m.val = L.rowptr.data_ptr(), L.col.data_ptr(), val.data_ptr()
         return m
 
-    def _diag_inv(self, m, dinv) -> float:
+    def _diag_inv(self, m, dinv, L, nscalar: int) -> float:
+        """Inverse diagonal and an upper estimate of lambda_max(D^-1 A).
+
+        Gershgorin is a safe bound but 2-6x too large for elasticity rows and for smoothed-aggregation
+        coarse operators, which would push the Chebyshev interval off the spectrum; so the bound is
+        tightened with `power_its` steps of the power method on D^-1 A (fixed start vector ->
+        deterministic) times a 1.15 safety factor, never exceeding Gershgorin.
+        """
         lib = _lib.load()
-        _lib.check(lib.cb_extract_diag_inv(_lib.stream_ptr(), C.byref(m), _lib.ptr(dinv), _lib.ptr(self.lmax_dev),
+        s = _lib.stream_ptr()
+        _lib.check(lib.cb_extract_diag_inv(s, C.byref(m), _lib.ptr(dinv), _lib.ptr(self.lmax_dev),
                                            _lib.ptr(self.scratch), self.scratch.numel()), "cb_extract_diag_inv")
-        return float(self.lmax_dev.item())
+        ncol = L.ncols * (nscalar // L.n)
+        x = self._power_x.get((id(L), nscalar))
+        if x is None:
+            gen = torch.Generator(device="cpu").manual_seed(1234 + nscalar)
+            x0 = torch.rand(nscalar, generator=gen, dtype=torch.float64) + 0.5
+            x0 = (x0 / torch.linalg.vector_norm(x0)).to(self.device)
+            x = (torch.zeros(ncol, dtype=torch.float64, device=self.device), x0,
+                 torch.zeros(nscalar, dtype=torch.float64, device=self.device))
+            self._power_x[(id(L), nscalar)] = x
+        xin, x0, y = x
+        xin[:nscalar] = x0
+        nrm = None
+        for _ in range(self.power_its):
+            _lib.check(lib.cb_spmv(s, C.byref(m), _lib.ptr(xin), _lib.ptr(y)), "cb_spmv")
+            y.mul_(dinv[:nscalar])
+            nrm = torch.linalg.vector_norm(y)
+            torch.div(y, nrm, out=xin[:nscalar])
+        both = torch.stack([self.lmax_dev[0], nrm]).cpu()  # one host sync per estimate
+        return min(float(both[0]), 1.15 * float(both[1]))
 
     def numeric(self, A) -> None:
         """Recompute prolongator values, Galerkin operators and smoother data for the values of ``A``."""
@@ -191,29 +259,34 @@ class AMGHierarchy:
         s = _lib.stream_ptr()
         bs = self.bs
         val = A.val
-        for li, L in enumerate(self.levels):
-            L.cur_val = val
+        for li, (L, D) in enumerate(zip(self.levels, self.data)):
+            D.cur_val = val
             m = self._mat(L, val, bs)
-            L.lmax = self._diag_inv(m, L.dinv)
+            if L.last and self.coarse_inv is not None:
+                _lib.check(lib.cb_amg_dense_inverse(s, C.byref(m), _lib.ptr(self.coarse_work), _lib.ptr(self.coarse_inv)),
+                           "cb_amg_dense_inverse")
+                break
+            D.lmax = self._diag_inv(m, D.dinv, L, L.n * bs)
             if L.last:
                 break
             if bs > 1:
-                _lib.check(lib.cb_amg_block_trace(s, C.byref(m), _lib.ptr(L.s_val)), "cb_amg_block_trace")
-                sval = L.s_val
+                _lib.check(lib.cb_amg_block_trace(s, C.byref(m), _lib.ptr(D.s_val)), "cb_amg_block_trace")
+                sval = D.s_val
             else:
                 sval = val
             ms = self._mat(L, sval, 1)
-            lmax_s = self._diag_inv(ms, L.s_dinv)
+            lmax_s = self._diag_inv(ms, D.s_dinv, L, L.n)
             omega = (4.0 / 3.0) / lmax_s
             _lib.check(lib.cb_amg_smooth_prolongator(s, C.byref(ms), omega, _lib.ptr(L.agg), _lib.ptr(L.p_rowptr),
-                                                     _lib.ptr(L.p_col), _lib.ptr(L.p_val)), "cb_amg_smooth_prolongator")
-            torch.index_select(L.p_val, 0, L.pt_perm, out=L.pt_val)
-            nxt = self.levels[li + 1]
-            mc = self._mat(nxt, nxt.val, bs)
-            _lib.check(lib.cb_amg_galerkin(s, C.byref(m), _lib.ptr(L.p_rowptr), _lib.ptr(L.p_col), _lib.ptr(L.p_val),
-                                           _lib.ptr(L.pt_rowptr), _lib.ptr(L.pt_col), _lib.ptr(L.pt_val),
-                                           _lib.ptr(L.ap_rowptr), _lib.ptr(L.ap_col), _lib.ptr(L.ap_val), C.byref(mc)),
-                       "cb_amg_galerkin")
+                                                     _lib.ptr(L.p_col), _lib.ptr(D.p_val)), "cb_amg_smooth_prolongator")
+            torch.index_select(D.p_val, 0, L.pt_perm, out=D.pt_val)
+            nxt = self.data[li + 1]
+            _lib.check(lib.cb_amg_spgemm_terms(s, bs, 1, L.ap_col.numel(), _lib.ptr(L.ap_seg), _lib.ptr(L.ap_sl),
+                                               _lib.ptr(L.ap_sr), _lib.ptr(val), _lib.ptr(D.p_val), _lib.ptr(D.ap_val)),
+                       "cb_amg_spgemm_terms(AP)")
+            _lib.check(lib.cb_amg_spgemm_terms(s, bs, 0, self.levels[li + 1].nnzb, _lib.ptr(L.ac_seg), _lib.ptr(L.ac_sl),
+                                               _lib.ptr(L.ac_sr), _lib.ptr(D.pt_val), _lib.ptr(D.ap_val), _lib.ptr(nxt.val)),
+                       "cb_amg_spgemm_terms(PtAP)")
             val = nxt.val
         self._struct = None
 
@@ -222,23 +295,24 @@ class AMGHierarchy:
         if self._struct is not None:
             return self._struct
         arr = (_lib.cb_amg_level * len(self.levels))()
-        for li, L in enumerate(self.levels):
+        for li, (L, D) in enumerate(zip(self.levels, self.data)):
             e = arr[li]
-            e.A = self._mat(L, L.cur_val, self.bs)
-            e.dinv = L.dinv.data_ptr()
-            e.lmax = L.lmax
+            e.A = self._mat(L, D.cur_val, self.bs)
+            e.dinv = D.dinv.data_ptr()
+            e.lmax = D.lmax
             e.nc = 0 if L.last else L.nc
             if not L.last:
-                e.p_rowptr, e.p_col, e.p_val = L.p_rowptr.data_ptr(), L.p_col.data_ptr(), L.p_val.data_ptr()
-                e.pt_rowptr, e.pt_col, e.pt_val = L.pt_rowptr.data_ptr(), L.pt_col.data_ptr(), L.pt_val.data_ptr()
-            e.x = L.x.data_ptr() if L.x is not None else None
-            e.b = L.b.data_ptr() if L.b is not None else None
-            e.t, e.d = L.t.data_ptr(), L.d.data_ptr()
+                e.p_rowptr, e.p_col, e.p_val = L.p_rowptr.data_ptr(), L.p_col.data_ptr(), D.p_val.data_ptr()
+                e.pt_rowptr, e.pt_col, e.pt_val = L.pt_rowptr.data_ptr(), L.pt_col.data_ptr(), D.pt_val.data_ptr()
+            e.x = D.x.data_ptr() if D.x is not None else None
+            e.b = D.b.data_ptr() if D.b is not None else None
+            e.t, e.d = D.t.data_ptr(), D.d.data_ptr()
         h = _lib.cb_amg()
         h.nlevels = len(self.levels)
         h.smooth_degree, h.coarse_degree = self.smooth_degree, self.coarse_degree
         h.smooth_ratio, h.coarse_ratio = self.smooth_ratio, self.coarse_ratio
         h.levels = C.cast(arr, C.c_void_p)
+        h.coarse_inv = self.coarse_inv.data_ptr() if self.coarse_inv is not None else None
         self._level_array = arr
         self._struct = h
         return h

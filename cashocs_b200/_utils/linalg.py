@@ -130,6 +130,13 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None, distr
     return o
 
 
+def row_split_hint(nnzb: int, nrows: int) -> int:
+    """Lane groups per row for the SpMV kernel: 1 for mesh stencils (~15 blocks / row), more for the
+    denser coarse AMG operators so that every lane still owns ~16 blocks."""
+    avg = nnzb / max(nrows, 1)
+    return 1 if avg <= 24 else (2 if avg <= 48 else (4 if avg <= 96 else 8))
+
+
 class Matrix:
     """Block-CSR matrix in HBM sharing the mesh's P1 pattern (``bs`` = 1 scalar, ``dim`` vector)."""
 
@@ -159,6 +166,7 @@ class Matrix:
     def struct(self) -> _lib.cb_mat:
         m = _lib.cb_mat()
         m.nrows, m.ncols, m.bs = self.nrows, self.ncols, self.bs
+        m.row_split = row_split_hint(self.nnzb, self.nrows)
         m.rowptr, m.col, m.val = self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr()
         return m
 
@@ -350,9 +358,13 @@ class LinearSolver:
         key = (id(A.mesh), A.bs)
         h = cls._amg_cache.get(key)
         if h is None or h.levels[0].rowptr is not A.rowptr:
+            skey = (id(A.mesh), "symbolic")
+            sym = cls._amg_cache.get(skey)
+            if sym is None or sym.levels[0].rowptr is not A.rowptr:
+                sym = amg.AMGSymbolic(A.rowptr, A.col, A.nrows, A.ncols)
+                cls._amg_cache[skey] = sym
             h = amg.AMGHierarchy(
-                A, min_coarse=int(options.get("pc_amg_min_coarse", 300)),
-                smooth_degree=int(options.get("pc_amg_smooth_degree", 2)),
+                A, sym, smooth_degree=int(options.get("pc_amg_smooth_degree", 2)),
                 coarse_degree=int(options.get("pc_amg_coarse_degree", 16)),
                 smooth_ratio=float(options.get("pc_amg_smooth_ratio", 4.0)),
                 coarse_ratio=float(options.get("pc_amg_coarse_ratio", 40.0)))

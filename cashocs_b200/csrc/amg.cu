@@ -55,59 +55,90 @@ k_smooth_prolongator(int64_t n, int64_t nlocal, const int64_t* __restrict__ s_ro
   }
 }
 
-// AP[i, J] = sum_k A[i, k] * P[k, J]   (A block bs x bs, P scalar); thread = (row, block entry)
-template <int BS>
-__global__ void __launch_bounds__(128)
-k_spgemm_ap(int64_t n, int64_t nlocal, const int64_t* __restrict__ a_rowptr, const int32_t* __restrict__ a_col,
-            const double* __restrict__ a_val, const int64_t* __restrict__ p_rowptr,
-            const int32_t* __restrict__ p_col, const double* __restrict__ p_val,
-            const int64_t* __restrict__ c_rowptr, const int32_t* __restrict__ c_col,
-            double* __restrict__ c_val) {
+// Numeric sparse product with a precomputed term list: for output entry q the terms
+// t in [seg_ptr[q], seg_ptr[q+1]) name one lhs entry and one rhs entry; exactly one of the two
+// operands carries bs x bs blocks (A or A*P), the other is scalar (P or P^T).  One thread owns one
+// (entry, block element): pure gather, no search, no atomics, fixed summation order.
+template <int BS, bool LHS_BLOCK>
+__global__ void __launch_bounds__(256)
+k_spgemm_terms(int64_t nnz_out, const int64_t* __restrict__ seg_ptr, const int32_t* __restrict__ src_l,
+               const int32_t* __restrict__ src_r, const double* __restrict__ lhs,
+               const double* __restrict__ rhs, double* __restrict__ out) {
   constexpr int BB = BS * BS;
-  const int64_t total = n * BB;
+  const int64_t total = nnz_out * BB;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = t / BB;
-    const int e = (int)(t - i * BB);
-    const int64_t cb = c_rowptr[i], ce = c_rowptr[i + 1];
-    for (int64_t k = cb; k < ce; ++k) c_val[k * BB + e] = 0.0;
-    for (int64_t ka = a_rowptr[i]; ka < a_rowptr[i + 1]; ++ka) {
-      const int32_t k = a_col[ka];
-      if (k >= nlocal) continue;
-      const double a = a_val[ka * BB + e];
-      for (int64_t kp = p_rowptr[k]; kp < p_rowptr[k + 1]; ++kp) {
-        const int64_t pos = find_col(c_col, cb, ce, p_col[kp]);
-        c_val[pos * BB + e] += a * p_val[kp];
-      }
+    const int64_t q = t / BB;
+    const int e = (int)(t - q * BB);
+    double acc = 0.0;
+    for (int64_t k = seg_ptr[q]; k < seg_ptr[q + 1]; ++k) {
+      const int64_t l = src_l[k], r = src_r[k];
+      if (LHS_BLOCK) acc += lhs[l * BB + e] * rhs[r];
+      else acc += lhs[l] * rhs[r * BB + e];
     }
+    out[t] = acc;
   }
 }
 
-// Ac[I, J] = sum_i Pt[I, i] * AP[i, J]
-template <int BS>
-__global__ void __launch_bounds__(128)
-k_spgemm_ptap(int64_t nc, const int64_t* __restrict__ pt_rowptr, const int32_t* __restrict__ pt_col,
-              const double* __restrict__ pt_val, const int64_t* __restrict__ ap_rowptr,
-              const int32_t* __restrict__ ap_col, const double* __restrict__ ap_val,
-              const int64_t* __restrict__ c_rowptr, const int32_t* __restrict__ c_col,
-              double* __restrict__ c_val) {
-  constexpr int BB = BS * BS;
-  const int64_t total = nc * BB;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t I = t / BB;
-    const int e = (int)(t - I * BB);
-    const int64_t cb = c_rowptr[I], ce = c_rowptr[I + 1];
-    for (int64_t k = cb; k < ce; ++k) c_val[k * BB + e] = 0.0;
-    for (int64_t kt = pt_rowptr[I]; kt < pt_rowptr[I + 1]; ++kt) {
-      const int32_t i = pt_col[kt];
-      const double w = pt_val[kt];
-      for (int64_t ka = ap_rowptr[i]; ka < ap_rowptr[i + 1]; ++ka) {
-        const int64_t pos = find_col(c_col, cb, ce, ap_col[ka]);
-        c_val[pos * BB + e] += w * ap_val[ka * BB + e];
-      }
+// Dense inverse of the coarsest operator (n <= 256 scalar rows): Gauss-Jordan without pivoting
+// (the matrix is SPD) by ONE CTA in global memory; `work` holds the n x 2n augmented matrix.
+__global__ void __launch_bounds__(256)
+k_dense_inverse(int n, int bs, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                const double* __restrict__ val, double* __restrict__ work, double* __restrict__ inv) {
+  const int w = 2 * n;
+  for (int i = threadIdx.x; i < n * w; i += blockDim.x) work[i] = 0.0;
+  __syncthreads();
+  const int nb = n / bs;
+  for (int br = threadIdx.x; br < nb; br += blockDim.x) {
+    for (int64_t k = rowptr[br]; k < rowptr[br + 1]; ++k) {
+      const int bc = col[k];
+      if (bc >= nb) continue;
+      for (int i = 0; i < bs; ++i)
+        for (int j = 0; j < bs; ++j) work[(br * bs + i) * w + bc * bs + j] = val[(k * bs + i) * bs + j];
     }
+    for (int i = 0; i < bs; ++i) work[(br * bs + i) * w + n + br * bs + i] = 1.0;
   }
+  __syncthreads();
+  for (int p = 0; p < n; ++p) {
+    const double piv = 1.0 / work[p * w + p];
+    __syncthreads();
+    for (int j = threadIdx.x; j < w; j += blockDim.x) work[p * w + j] *= piv;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n * w; idx += blockDim.x) {
+      const int r = idx / w, j = idx - r * w;
+      if (r == p || j == p) continue;
+      work[idx] -= work[r * w + p] * work[p * w + j];
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < n; r += blockDim.x)
+      if (r != p) work[r * w + p] = 0.0;
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int r = idx / n, j = idx - r * n;
+    inv[idx] = work[r * w + n + j];
+  }
+}
+
+// x = Ainv * b (dense, row-major), one warp per row
+__global__ void __launch_bounds__(256)
+k_dense_apply(int n, const double* __restrict__ inv, const double* __restrict__ b, double* __restrict__ x,
+              const int* __restrict__ done) {
+  if (done && *done) return;
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  double s = 0.0;
+  for (int j = lane; j < n; j += 32) s += inv[(int64_t)row * n + j] * b[j];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+  if (lane == 0) x[row] = s;
+}
+
+int amg_dense_apply(cudaStream_t s, int n, const double* inv, const double* b, double* x, const int* done) {
+  k_dense_apply<<<(n * 32 + 255) / 256, 256, 0, s>>>(n, inv, b, x, done);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
 }
 
 // bc[I, c] = sum_i Pt[I, i] * (b[i, c] - t[i, c])      (restriction of the residual)
@@ -193,25 +224,27 @@ extern "C" int cb_amg_smooth_prolongator(void* stream, const cb_mat* S, double o
   return CB_OK;
 }
 
-extern "C" int cb_amg_galerkin(void* stream, const cb_mat* A, const int64_t* p_rowptr, const int32_t* p_col,
-                               const double* p_val, const int64_t* pt_rowptr, const int32_t* pt_col,
-                               const double* pt_val, const int64_t* ap_rowptr, const int32_t* ap_col,
-                               double* ap_val, const cb_mat* Ac) {
-  CB_REQUIRE(A && Ac && p_rowptr && pt_rowptr && ap_rowptr && ap_val, "cb_amg_galerkin: missing argument");
-  CB_REQUIRE(A->bs == Ac->bs && A->bs >= 1 && A->bs <= 3, "cb_amg_galerkin: block sizes");
+extern "C" int cb_amg_spgemm_terms(void* stream, int bs, int lhs_block, int64_t nnz_out,
+                                   const int64_t* seg_ptr, const int32_t* src_l, const int32_t* src_r,
+                                   const double* lhs, const double* rhs, double* out) {
+  CB_REQUIRE(seg_ptr && src_l && src_r && lhs && rhs && out, "cb_amg_spgemm_terms: missing argument");
+  CB_REQUIRE(bs >= 1 && bs <= 3, "cb_amg_spgemm_terms: bs must be 1..3");
   cudaStream_t s = as_stream(stream);
-  const int bs = A->bs;
-  const int64_t n = A->nrows, nc = Ac->nrows;
-  const int g1 = grid_for(n * bs * bs, 128, 16), g2 = grid_for(nc * bs * bs, 128, 16);
-  double* acv = const_cast<double*>(Ac->val);
-#define CB_GALERKIN(BS)                                                                                   \
-  k_spgemm_ap<BS><<<g1, 128, 0, s>>>(n, n, A->rowptr, A->col, A->val, p_rowptr, p_col, p_val, ap_rowptr, \
-                                     ap_col, ap_val);                                                     \
-  CB_LAUNCH_CHECK();                                                                                      \
-  k_spgemm_ptap<BS><<<g2, 128, 0, s>>>(nc, pt_rowptr, pt_col, pt_val, ap_rowptr, ap_col, ap_val,         \
-                                       Ac->rowptr, Ac->col, acv);                                         \
+  const int grid = grid_for(nnz_out * bs * bs, 256, 16);
+#define CB_TERMS(BS)                                                                                            \
+  if (lhs_block) k_spgemm_terms<BS, true><<<grid, 256, 0, s>>>(nnz_out, seg_ptr, src_l, src_r, lhs, rhs, out); \
+  else k_spgemm_terms<BS, false><<<grid, 256, 0, s>>>(nnz_out, seg_ptr, src_l, src_r, lhs, rhs, out);
+  if (bs == 1) { CB_TERMS(1) } else if (bs == 2) { CB_TERMS(2) } else { CB_TERMS(3) }
+#undef CB_TERMS
   CB_LAUNCH_CHECK();
-  if (bs == 1) { CB_GALERKIN(1) } else if (bs == 2) { CB_GALERKIN(2) } else { CB_GALERKIN(3) }
-#undef CB_GALERKIN
+  return CB_OK;
+}
+
+extern "C" int cb_amg_dense_inverse(void* stream, const cb_mat* A, double* work, double* inv) {
+  CB_REQUIRE(A && work && inv, "cb_amg_dense_inverse: missing argument");
+  const int n = (int)(A->nrows * A->bs);
+  CB_REQUIRE(n >= 1 && n <= 256, "cb_amg_dense_inverse: coarsest level must have <= 256 scalar rows");
+  k_dense_inverse<<<1, 256, 0, as_stream(stream)>>>(n, A->bs, A->rowptr, A->col, A->val, work, inv);
+  CB_LAUNCH_CHECK();
   return CB_OK;
 }

@@ -15,6 +15,21 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// cudaMallocAsync scratch is returned to the driver at every synchronisation unless the pool's
+// release threshold is raised; keep it so repeated calls reuse the same blocks.
+int configure_scratch_pool() {
+  static int done_for_device = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return CB_ERR_CUDA;
+  if (done_for_device == dev) return CB_OK;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return CB_ERR_CUDA;
+  unsigned long long threshold = ~0ULL;
+  if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold) != cudaSuccess) return CB_ERR_CUDA;
+  done_for_device = dev;
+  return CB_OK;
+}
+
 int num_sms() {
   static int cached = 0;
   if (cached > 0) return cached;

@@ -38,6 +38,7 @@ extern long long g_launch_count;  // kernels launched by this library (bench.py'
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int num_sms();
+int configure_scratch_pool();
 
 // Grid size for grid-stride kernels: a multiple of the SM count, capped by the work.
 inline int grid_for(int64_t work_items, int threads, int ctas_per_sm) {

@@ -27,6 +27,7 @@ int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, c
 int amg_restrict(cudaStream_t s, int bs, const cb_amg_level* L, const double* b, const double* t, double* bc,
                  const int* done);
 int amg_prolong(cudaStream_t s, int bs, const cb_amg_level* L, const double* xc, double* x, const int* done);
+int amg_dense_apply(cudaStream_t s, int n, const double* inv, const double* b, double* x, const int* done);
 int dist_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs, double* sendbuf);
 int dist_allreduce_sum(cudaStream_t s, cb_dist* d, double* buf, int n);
 int64_t dist_send_len(const cb_dist* d);
@@ -161,7 +162,7 @@ k_cg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const Ks
 // w = A p ; sums[0] = p.w
 template <int BS, bool FINALIZE>
 __global__ void __launch_bounds__(SpmvCfg<BS>::THREADS)
-k_cg_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+k_cg_spmv(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
           const double* __restrict__ val, const double* __restrict__ p, double* __restrict__ w,
           KspState* st, double* scratch) {
   if (st->done) return;
@@ -170,13 +171,14 @@ k_cg_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __re
   __shared__ double s_red[33];
   const SpmvSmem<BS> sm = spmv_smem_init<BS>(smem_raw);
   uint32_t phase = 0;
-  const int64_t nrb = (nrows + C::R - 1) / C::R;
+  const int R = spmv_rows_per_cta<BS>(G);
+  const int64_t nrb = (nrows + R - 1) / R;
   double local = 0.0;
   for (int64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
-    const int64_t row0 = rb * C::R;
-    const int nr = (int)((nrows - row0 < C::R) ? (nrows - row0) : C::R);
+    const int64_t row0 = rb * R;
+    const int nr = (int)((nrows - row0 < R) ? (nrows - row0) : R);
     double acc;
-    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, p, row0, nr, phase, acc);
+    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, p, row0, nr, G, phase, acc);
     if (i >= 0) {
       w[i] = acc;
       local += acc * p[i];
@@ -336,7 +338,7 @@ k_minres_v(int64_t n, const double* __restrict__ y, double* __restrict__ v, cons
 // t = A v - (beta/oldb) r1 ; sums[0] = v.t
 template <int BS, bool FINALIZE>
 __global__ void __launch_bounds__(SpmvCfg<BS>::THREADS)
-k_minres_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+k_minres_spmv(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
               const double* __restrict__ val, const double* __restrict__ v,
               const double* __restrict__ r1, double* __restrict__ t, KspState* st,
               double* scratch) {
@@ -347,13 +349,14 @@ k_minres_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* 
   const SpmvSmem<BS> sm = spmv_smem_init<BS>(smem_raw);
   uint32_t phase = 0;
   const double c = (st->its >= 1) ? st->mbeta / st->oldb : 0.0;
-  const int64_t nrb = (nrows + C::R - 1) / C::R;
+  const int R = spmv_rows_per_cta<BS>(G);
+  const int64_t nrb = (nrows + R - 1) / R;
   double local = 0.0;
   for (int64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
-    const int64_t row0 = rb * C::R;
-    const int nr = (int)((nrows - row0 < C::R) ? (nrows - row0) : C::R);
+    const int64_t row0 = rb * R;
+    const int nr = (int)((nrows - row0 < R) ? (nrows - row0) : R);
     double acc;
-    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, v, row0, nr, phase, acc);
+    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, v, row0, nr, G, phase, acc);
     if (i >= 0) {
       if (c != 0.0) acc -= c * r1[i];
       t[i] = acc;
@@ -440,7 +443,7 @@ struct Solver {
   double* hist_dev;
   double* scratch;
   double* sendbuf;
-  int vgrid, sgrid;
+  int vgrid, sgrid, gsplit = 1;
   // optional live profiling of the SpMV launches (bench.py roofline): CUDA events around every
   // profile_every-th launch on the launching stream
   int profile_every = 0, spmv_launches = 0;
@@ -472,8 +475,8 @@ struct Solver {
 
   template <int BS>
   int cg_spmv_bs(const double* p, double* w) {
-    if (dist) k_cg_spmv<BS, false><<<sgrid, SpmvCfg<BS>::THREADS, SpmvCfg<BS>::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, p, w, st, scratch);
-    else k_cg_spmv<BS, true><<<sgrid, SpmvCfg<BS>::THREADS, SpmvCfg<BS>::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, p, w, st, scratch);
+    if (dist) k_cg_spmv<BS, false><<<sgrid, SpmvCfg<BS>::THREADS, SpmvCfg<BS>::SMEM_BYTES, s>>>(A->nrows, gsplit, A->rowptr, A->col, A->val, p, w, st, scratch);
+    else k_cg_spmv<BS, true><<<sgrid, SpmvCfg<BS>::THREADS, SpmvCfg<BS>::SMEM_BYTES, s>>>(A->nrows, gsplit, A->rowptr, A->col, A->val, p, w, st, scratch);
     CB_LAUNCH_CHECK();
     return CB_OK;
   }
@@ -492,8 +495,8 @@ struct Solver {
   }
   template <int BS>
   int minres_spmv_bs(const double* v, const double* r1, double* t) {
-    if (dist) k_minres_spmv<BS, false><<<sgrid, SpmvCfg<BS>::THREADS, SpmvCfg<BS>::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, v, r1, t, st, scratch);
-    else k_minres_spmv<BS, true><<<sgrid, SpmvCfg<BS>::THREADS, SpmvCfg<BS>::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, v, r1, t, st, scratch);
+    if (dist) k_minres_spmv<BS, false><<<sgrid, SpmvCfg<BS>::THREADS, SpmvCfg<BS>::SMEM_BYTES, s>>>(A->nrows, gsplit, A->rowptr, A->col, A->val, v, r1, t, st, scratch);
+    else k_minres_spmv<BS, true><<<sgrid, SpmvCfg<BS>::THREADS, SpmvCfg<BS>::SMEM_BYTES, s>>>(A->nrows, gsplit, A->rowptr, A->col, A->val, v, r1, t, st, scratch);
     CB_LAUNCH_CHECK();
     return CB_OK;
   }
@@ -547,7 +550,11 @@ struct Solver {
       const double* bl = (l == 0) ? r : lev.b;
       double* xl = (l == 0) ? z : lev.x;
       if (l == L - 1) {
-        if (int e = amg_smooth(lev, bl, xl, h->coarse_degree, h->coarse_ratio, true)) return e;
+        if (h->coarse_inv) {
+          if (int e = amg_dense_apply(s, (int)(lev.A.nrows * bs), h->coarse_inv, bl, xl, &st->done)) return e;
+        } else {
+          if (int e = amg_smooth(lev, bl, xl, h->coarse_degree, h->coarse_ratio, true)) return e;
+        }
         break;
       }
       if (int e = amg_smooth(lev, bl, xl, h->smooth_degree, h->smooth_ratio, true)) return e;
@@ -592,6 +599,7 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
   CB_REQUIRE(work_len >= cb_ksp_workspace_len(n, nc, o), "cb_ksp_solve: workspace too small");
   CB_REQUIRE(o->pc_type != CB_PC_CHEBYSHEV || o->cheb_degree >= 1, "chebyshev degree must be >= 1");
   cudaStream_t s = as_stream(stream);
+  configure_scratch_pool();
 
   // carve the workspace
   double* wp = work;
@@ -627,7 +635,8 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
   S.vgrid = grid_for(n, 256, 4);
   if (S.vgrid > RED_MAXP) S.vgrid = RED_MAXP;
   {
-    const int R = A->bs == 1 ? SpmvCfg<1>::R : A->bs == 2 ? SpmvCfg<2>::R : SpmvCfg<3>::R;
+    S.gsplit = spmv_sanitize_split(A->row_split);
+    const int R = A->bs == 1 ? spmv_rows_per_cta<1>(S.gsplit) : A->bs == 2 ? spmv_rows_per_cta<2>(S.gsplit) : spmv_rows_per_cta<3>(S.gsplit);
     const int per_sm = A->bs == 1 ? SpmvCfg<1>::CTAS_PER_SM : A->bs == 2 ? SpmvCfg<2>::CTAS_PER_SM : SpmvCfg<3>::CTAS_PER_SM;
     const int64_t nrb = (A->nrows + R - 1) / R;
     int64_t cap = (int64_t)num_sms() * per_sm;

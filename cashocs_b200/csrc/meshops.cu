@@ -505,6 +505,7 @@ extern "C" int cb_intersection_test(void* stream, int dim, int64_t nv, int64_t n
                                     const int32_t* valence, int32_t* counts, int64_t* mismatch_dev) {
   CB_REQUIRE(dim == 2 || dim == 3, "cb_intersection_test: dim must be 2 or 3");
   CB_REQUIRE(coords && cells && valence && counts && mismatch_dev, "cb_intersection_test: missing argument");
+  configure_scratch_pool();
   cudaStream_t s = as_stream(stream);
   double* bb = nullptr;
   double* scratch = nullptr;

@@ -131,6 +131,7 @@ using namespace cb;
 extern "C" int cb_v2c_build(void* stream, int64_t nd, int64_t nc, int k, const int32_t* cell_dofs,
                             int64_t* v2c_ptr, int32_t* v2c_idx) {
   CB_REQUIRE(nd > 0 && nc > 0 && k > 0, "cb_v2c_build: empty mesh");
+  configure_scratch_pool();
   cudaStream_t s = as_stream(stream);
   unsigned long long* cnt = nullptr;
   unsigned int* cursor = nullptr;
@@ -160,6 +161,7 @@ extern "C" int cb_v2c_build(void* stream, int64_t nd, int64_t nc, int k, const i
 extern "C" int cb_pattern_rowptr(void* stream, int64_t nrows, int k, const int32_t* cell_dofs,
                                  const int64_t* v2c_ptr, const int32_t* v2c_idx, int64_t* rowptr) {
   CB_REQUIRE(nrows > 0, "cb_pattern_rowptr: no rows");
+  configure_scratch_pool();
   cudaStream_t s = as_stream(stream);
   int64_t* rowlen = nullptr;
   int* err = nullptr;

@@ -9,7 +9,7 @@ int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, c
 
 template <int BS, bool WRITE_Y, bool DOT>
 __global__ void __launch_bounds__(SpmvCfg<BS>::THREADS)
-k_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+k_spmv(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
        const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
        const double* __restrict__ w, double* __restrict__ result, double* __restrict__ scratch,
        const int* __restrict__ done) {
@@ -19,13 +19,14 @@ k_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restr
   __shared__ double s_red[33];
   const SpmvSmem<BS> sm = spmv_smem_init<BS>(smem_raw);
   uint32_t phase = 0;
-  const int64_t nrb = (nrows + C::R - 1) / C::R;
+  const int R = spmv_rows_per_cta<BS>(G);
+  const int64_t nrb = (nrows + R - 1) / R;
   double local = 0.0;
   for (int64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
-    const int64_t row0 = rb * C::R;
-    const int nr = (int)((nrows - row0 < C::R) ? (nrows - row0) : C::R);
+    const int64_t row0 = rb * R;
+    const int nr = (int)((nrows - row0 < R) ? (nrows - row0) : R);
     double acc;
-    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, x, row0, nr, phase, acc);
+    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, x, row0, nr, G, phase, acc);
     if (i >= 0) {
       if (WRITE_Y) y[i] = acc;
       if (DOT) local += acc * w[i];
@@ -85,9 +86,10 @@ k_diag_inv(int64_t nrows, int bs, const int64_t* __restrict__ rowptr, const int3
 }
 
 template <int BS>
-int spmv_grid(int64_t nrows) {
+int spmv_grid(int64_t nrows, int G) {
   using C = SpmvCfg<BS>;
-  const int64_t nrb = (nrows + C::R - 1) / C::R;
+  const int R = spmv_rows_per_cta<BS>(G);
+  const int64_t nrb = (nrows + R - 1) / R;
   int64_t cap = (int64_t)num_sms() * C::CTAS_PER_SM;
   if (cap > RED_MAXP) cap = RED_MAXP;
   return (int)(nrb < cap ? nrb : cap);
@@ -104,7 +106,8 @@ template <int BS>
 int launch_spmv(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
                 double* result, double* scratch, const int* done) {
   using C = SpmvCfg<BS>;
-  const int grid = spmv_grid<BS>(A->nrows);
+  const int G = spmv_sanitize_split(A->row_split);
+  const int grid = spmv_grid<BS>(A->nrows, G);
   static bool configured = false;
   if (!configured) {
     if (int e = prefer_smem(k_spmv<BS, true, false>)) return e;
@@ -113,11 +116,11 @@ int launch_spmv(cudaStream_t s, const cb_mat* A, const double* x, double* y, con
     configured = true;
   }
   if (y && !w)
-    k_spmv<BS, true, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, x, y, nullptr, nullptr, nullptr, done);
+    k_spmv<BS, true, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, A->val, x, y, nullptr, nullptr, nullptr, done);
   else if (y && w)
-    k_spmv<BS, true, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, x, y, w, result, scratch, done);
+    k_spmv<BS, true, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, A->val, x, y, w, result, scratch, done);
   else
-    k_spmv<BS, false, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, A->rowptr, A->col, A->val, x, nullptr, w, result, scratch, done);
+    k_spmv<BS, false, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, A->val, x, nullptr, w, result, scratch, done);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }

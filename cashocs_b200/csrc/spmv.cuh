@@ -126,23 +126,33 @@ __device__ __forceinline__ void issue_tile(const SpmvSmem<BS>& sm, const double*
   mbar_arrive_expect_tx(sm.bar, bytes);
 }
 
-// Computes block rows [row0, row0+nr) of y = A x.  On return thread (warp w, lane l) with
-// l < ROWS_PER_WARP*BS holds in `acc` the result for scalar row
-//   out = (row0 + w*ROWS_PER_WARP + l/BS)*BS + l%BS      (valid iff that block row < row0+nr);
-// `out` is returned (-1 when the thread owns no row).  `phase` is the CTA's mbarrier parity
-// (in/out).  All threads of the CTA must call this together.
+// Rows per CTA for a row split of G thread groups per row (G in {1,2,4,8}; long rows of coarse
+// AMG operators are shared by G*BS lanes).
+template <int BS>
+__host__ __device__ __forceinline__ int spmv_rows_per_cta(int G) {
+  return (32 / (BS * G)) * SpmvCfg<BS>::WARPS;
+}
+__host__ __device__ __forceinline__ int spmv_sanitize_split(int g) { return g >= 8 ? 8 : (g >= 4 ? 4 : (g >= 2 ? 2 : 1)); }
+
+// Computes block rows [row0, row0+nr) of y = A x, nr <= spmv_rows_per_cta<BS>(G).  Lane layout
+// inside a warp: lane = (r*G + g)*BS + j  (row r, split group g, block column j).  On return the
+// g == 0 lanes hold in `acc_out` the result for scalar row (row0 + warp*rpw + r)*BS + j, which
+// is returned (-1 for all other lanes).  `phase` is the CTA's mbarrier parity (in/out).  All
+// threads of the CTA must call this together.
 template <int BS>
 __device__ __forceinline__ int64_t spmv_row_block(const SpmvSmem<BS>& sm, const int64_t* __restrict__ rowptr,
                                                   const int32_t* __restrict__ col,
                                                   const double* __restrict__ val,
-                                                  const double* __restrict__ x, int64_t row0, int nr,
+                                                  const double* __restrict__ x, int64_t row0, int nr, int G,
                                                   uint32_t& phase, double& acc_out) {
   using C = SpmvCfg<BS>;
   constexpr int BB = BS * BS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int lr = warp * C::ROWS_PER_WARP + lane / BS;
-  const int j = lane % BS;
-  const bool active = (lane < C::ROWS_PER_WARP * BS) && (lr < nr);
+  const int rpw = 32 / (BS * G);
+  const int q = lane / BS, j = lane - q * BS;
+  const int r = q / G, g = q - r * G;
+  const int lr = warp * rpw + r;
+  const bool active = (q < rpw * G) && (lr < nr);
   const int64_t k0 = __ldg(rowptr + row0), k1 = __ldg(rowptr + row0 + nr);
   int64_t rb = 0, re = 0;
   if (active) { rb = __ldg(rowptr + row0 + lr); re = __ldg(rowptr + row0 + lr + 1); }
@@ -162,7 +172,7 @@ __device__ __forceinline__ int64_t spmv_row_block(const SpmvSmem<BS>& sm, const 
       const double* sv = sm.val + vhead;
       const int32_t* sc = sm.col + chead;
 #pragma unroll 4
-      for (int k = b; k < e; ++k) {
+      for (int k = b + g; k < e; k += G) {
         const int32_t c = sc[k];
         const double xv = __ldg(x + (int64_t)c * BS + j);
 #pragma unroll
@@ -171,7 +181,15 @@ __device__ __forceinline__ int64_t spmv_row_block(const SpmvSmem<BS>& sm, const 
     }
     __syncthreads();  // the tile is consumed: the next bulk copy may overwrite it
   }
-  // transpose-reduce the BS partial vectors of a row: thread j ends with y_j
+  // sum the G split groups of a row (fixed tree order), result in the g == 0 lanes
+  for (int stride = G >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+    for (int i = 0; i < BS; ++i) {
+      const double o = __shfl_down_sync(0xffffffffu, acc[i], stride * BS);
+      acc[i] += o;
+    }
+  }
+  // transpose-reduce the BS partial vectors of a row: lane j ends with y_j
   double y = acc[0];
   if constexpr (BS > 1) {
     const int base = lane - j;
@@ -192,7 +210,7 @@ __device__ __forceinline__ int64_t spmv_row_block(const SpmvSmem<BS>& sm, const 
     }
   }
   acc_out = y;
-  return active ? (row0 + lr) * BS + j : -1;
+  return (active && g == 0) ? (row0 + lr) * BS + j : -1;
 }
 
 }  // namespace cb

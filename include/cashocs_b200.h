@@ -152,7 +152,7 @@ typedef struct {
   int64_t nrows;          /* owned block rows */
   int64_t ncols;          /* block columns incl. ghosts */
   int32_t bs;             /* 1, 2 or 3 */
-  int32_t pad;
+  int32_t row_split;      /* SpMV hint: lanes groups per row, 0/1, 2, 4 or 8 (set ~ avg row length / 16) */
   const int64_t* rowptr;  /* [nrows+1] */
   const int32_t* col;     /* [nnzb] */
   const double* val;      /* [nnzb*bs*bs] */
@@ -209,11 +209,12 @@ typedef struct {
 typedef struct {
   int32_t nlevels;
   int32_t smooth_degree;    /* Chebyshev degree of the pre / post smoother */
-  int32_t coarse_degree;    /* Chebyshev degree of the coarsest-level solve */
+  int32_t coarse_degree;    /* Chebyshev degree of the coarsest-level solve (coarse_inv == NULL) */
   int32_t pad;
   double smooth_ratio;      /* smoother interval [lmax/ratio, lmax] */
   double coarse_ratio;
   const cb_amg_level* levels; /* host array */
+  const double* coarse_inv;   /* dense inverse of the last level's operator (nullable) */
 } cb_amg;
 
 typedef struct {
@@ -256,11 +257,15 @@ int cb_amg_block_trace(void* stream, const cb_mat* A, double* s_val);
 /* P = T - omega D_S^-1 S T for the piecewise-constant tentative prolongator T of `agg` [nrows]. */
 int cb_amg_smooth_prolongator(void* stream, const cb_mat* S, double omega, const int32_t* agg,
                               const int64_t* p_rowptr, const int32_t* p_col, double* p_val);
-/* Ac = P^T A P through AP = A*P (pattern ap_rowptr/ap_col, scratch values ap_val [nnz(AP)*bs*bs]). */
-int cb_amg_galerkin(void* stream, const cb_mat* A, const int64_t* p_rowptr, const int32_t* p_col,
-                    const double* p_val, const int64_t* pt_rowptr, const int32_t* pt_col,
-                    const double* pt_val, const int64_t* ap_rowptr, const int32_t* ap_col,
-                    double* ap_val, const cb_mat* Ac);
+/* Numeric sparse product with a precomputed term list (symbolic phase of the host layer):
+ * out[q] = sum_{t in [seg_ptr[q], seg_ptr[q+1])} lhs[src_l[t]] * rhs[src_r[t]], where exactly one
+ * operand holds bs x bs blocks (lhs_block != 0: lhs, else rhs) and the other is scalar.  Used for
+ * A*P and P^T*(A*P) of the Galerkin coarse operators. */
+int cb_amg_spgemm_terms(void* stream, int bs, int lhs_block, int64_t nnz_out, const int64_t* seg_ptr,
+                        const int32_t* src_l, const int32_t* src_r, const double* lhs,
+                        const double* rhs, double* out);
+/* Dense inverse of the coarsest operator (<= 256 scalar rows); work [2 n^2], inv [n^2] row-major. */
+int cb_amg_dense_inverse(void* stream, const cb_mat* A, double* work, double* inv);
 
 /* ------------------------------------------------------------------ mesh kernels */
 #define CB_Q_SKEWNESS 0

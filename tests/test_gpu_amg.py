@@ -48,15 +48,16 @@ def csr(rowptr, col, val, shape):
 def test_hierarchy_is_galerkin(kind):
     dm, A, b, E, rhs = systems(kind)
     for M in (A, E):
-        h = amg.AMGHierarchy(M, min_coarse=50)
+        h = amg.AMGHierarchy(M)
         h.numeric(M)
         assert len(h.levels) >= 2 and h.operator_complexity < 2.5
         bs = M.bs
         cur = M.to_scipy()
         for li, L in enumerate(h.levels[:-1]):
-            nxt = h.levels[li + 1]
-            P = csr(L.p_rowptr, L.p_col, L.p_val, (L.n, L.nc))
-            Pt = csr(L.pt_rowptr, L.pt_col, L.pt_val, (L.nc, L.n))
+            nxt, D = h.levels[li + 1], h.data[li]
+            nxt.val = h.data[li + 1].val
+            P = csr(L.p_rowptr, L.p_col, D.p_val, (L.n, L.nc))
+            Pt = csr(L.pt_rowptr, L.pt_col, D.pt_val, (L.nc, L.n))
             assert abs(Pt - P.T).max() == 0.0
             # partition of unity of the smoothed prolongator on interior rows: row sums of P == 1 - w*rowsum(S)/S_ii
             assert np.all(np.diff(L.p_rowptr.cpu().numpy()) >= 1)
@@ -69,6 +70,11 @@ def test_hierarchy_is_galerkin(kind):
                                     shape=(nxt.n * bs, nxt.n * bs)).tocsr()
             assert abs(got - ref).max() <= 1e-12 * abs(ref).max()
             cur = got
+        # dense inverse of the coarsest operator
+        if h.coarse_inv is not None:
+            nn = h.levels[-1].n * bs
+            inv = h.coarse_inv.cpu().numpy().reshape(nn, nn)
+            assert np.abs(inv @ cur.toarray() - np.eye(nn)).max() < 1e-9
         # aggregates cover every node exactly once
         agg = h.levels[0].agg.cpu().numpy()
         assert agg.min() == 0 and agg.max() == h.levels[0].nc - 1 and np.unique(agg).size == h.levels[0].nc

@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Phase timing of one bench step (CUDA events + sync around each phase; diagnostic only)."""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import cashocs_b200 as cb  # noqa: E402
+from cashocs_b200._utils import linalg  # noqa: E402
+
+
+class T:
+    def __init__(self):
+        self.acc = {}
+
+    def __call__(self, name):
+        t = self
+
+        class Ctx:
+            def __enter__(self):
+                torch.cuda.synchronize()
+                self.t0 = time.perf_counter()
+
+            def __exit__(self, *a):
+                torch.cuda.synchronize()
+                t.acc[name] = t.acc.get(name, 0.0) + (time.perf_counter() - self.t0) * 1e3
+
+        return Ctx()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mesh-n", dest="n", type=int, default=119)
+    ap.add_argument("--pc", default="hypre")
+    ap.add_argument("--reps", type=int, default=2)
+    args = ap.parse_args()
+    bench.KSP["pc_type"] = args.pc
+    sop = bench.build_problem(args.n)
+    h = 1.0 / args.n
+    bench.evaluation_step(sop, h)
+    timer = T()
+    fh = sop.form_handler
+    for _ in range(args.reps):
+        sop.state_problem.has_solution = sop.adjoint_problem.has_solution = sop.gradient_problem.has_solution = False
+        with timer("mu + elasticity assembly"):
+            fh.update_scalar_product()
+        with timer("state assembly"):
+            A, b = sop.state_problem.assemble(0)
+        if args.pc == "hypre":
+            with timer("amg numeric scalar"):
+                linalg.LinearSolver.amg_hierarchy(A, {})
+            with timer("amg numeric elasticity"):
+                hE = linalg.LinearSolver.amg_hierarchy(fh.scalar_product_matrix, {})
+        with timer("state solve"):
+            sop.state_problem.linear_solver.solve(sop.states[0].vector, A=A, b=b, ksp_options=sop.ksp_options[0])
+        sop.state_problem.has_solution = True
+        with timer("adjoint assemble+solve"):
+            sop.adjoint_problem.solve()
+        with timer("shape derivative"):
+            rhs = fh.assemble_shape_derivative()
+        with timer("elasticity solve"):
+            g = sop.gradient.vector
+            g.zero_()
+            res = sop.gradient_problem.linear_solver.solve(g, A=fh.scalar_product_matrix, b=rhs, ksp_options=sop.gradient_problem.ksp_options)
+        with timer("gAg"):
+            fh.scalar_product(g, g)
+        with timer("move (det+move+intersection+quality) + revert"):
+            if sop.mesh_handler.move_mesh(g, step=-0.1 * h / float(g.abs().max())):
+                sop.mesh_handler.revert_transformation()
+    for k, v in timer.acc.items():
+        print(f"{k:50s} {v / args.reps:10.2f} ms")
+    print("its", sop.state_problem.linear_solver.last_result.its, sop.adjoint_problem.iterations, res.its)
+    if args.pc == "hypre":
+        print("levels", hE.sizes, "opc %.3f" % hE.operator_complexity, [L.nnzb for L in hE.levels], [round(D.lmax, 3) for D in hE.data])
+
+
+if __name__ == "__main__":
+    main()
