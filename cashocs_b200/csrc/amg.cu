@@ -148,17 +148,31 @@ k_restrict(int64_t nc, const int64_t* __restrict__ pt_rowptr, const int32_t* __r
            const double* __restrict__ pt_val, const double* __restrict__ b, const double* __restrict__ t,
            double* __restrict__ bc, const int* __restrict__ done) {
   if (done && *done) return;
-  const int64_t total = nc * BS;
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total;
-       q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t I = q / BS;
-    const int c = (int)(q - I * BS);
-    double s = 0.0;
-    for (int64_t k = pt_rowptr[I]; k < pt_rowptr[I + 1]; ++k) {
-      const int64_t i = (int64_t)pt_col[k] * BS + c;
-      s += pt_val[k] * (b[i] - t[i]);
+  // one warp per coarse node: lanes stride over the ~50 entries of the P^T row (coalesced index /
+  // weight loads), every lane accumulates all BS components, fixed-order shuffle tree at the end
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t I = warp0; I < nc; I += nwarps) {
+    double s[BS];
+#pragma unroll
+    for (int c = 0; c < BS; ++c) s[c] = 0.0;
+    const int64_t kb = pt_rowptr[I], ke = pt_rowptr[I + 1];
+    for (int64_t k = kb + lane; k < ke; k += 32) {
+      const int64_t i = (int64_t)pt_col[k] * BS;
+      const double w = pt_val[k];
+#pragma unroll
+      for (int c = 0; c < BS; ++c) s[c] += w * (b[i + c] - t[i + c]);
     }
-    bc[q] = s;
+#pragma unroll
+    for (int c = 0; c < BS; ++c) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s[c] += __shfl_down_sync(0xffffffffu, s[c], off);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < BS; ++c) bc[I * BS + c] = s[c];
+    }
   }
 }
 
@@ -182,7 +196,7 @@ k_prolong(int64_t n, const int64_t* __restrict__ p_rowptr, const int32_t* __rest
 
 int amg_restrict(cudaStream_t s, int bs, const cb_amg_level* L, const double* b, const double* t, double* bc,
                  const int* done) {
-  const int grid = grid_for(L->nc * bs, 256, 8);
+  const int grid = grid_for(L->nc * 32, 256, 8);
   if (bs == 1) k_restrict<1><<<grid, 256, 0, s>>>(L->nc, L->pt_rowptr, L->pt_col, L->pt_val, b, t, bc, done);
   else if (bs == 2) k_restrict<2><<<grid, 256, 0, s>>>(L->nc, L->pt_rowptr, L->pt_col, L->pt_val, b, t, bc, done);
   else k_restrict<3><<<grid, 256, 0, s>>>(L->nc, L->pt_rowptr, L->pt_col, L->pt_val, b, t, bc, done);

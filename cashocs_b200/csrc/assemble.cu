@@ -126,59 +126,73 @@ k_assemble_scalar(int64_t c_begin, int64_t c_end, const int32_t* __restrict__ ce
 }
 
 // ------------------------------------------------------------------ vector P1 elasticity
+// One thread per (cell, block (a, b)): the 16 (9 in 2-D) threads of a cell recompute the cheap cell
+// geometry (loads are warp-broadcasts) and each owns one d x d block, i.e. one contiguous
+// read-modify-write of d*d doubles through a coalesced read of the cell->nnz map.  Compared with
+// one thread per cell this needs 4x fewer registers and 16x more parallelism.
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_assemble_elasticity(int64_t c_begin, int64_t c_end, const int32_t* __restrict__ cells,
                       const int32_t* __restrict__ cell2nnz, const double* __restrict__ coords,
                       const double* __restrict__ mu, double lambda_lame, double damping,
                       const double* __restrict__ cell_scale, const uint8_t* __restrict__ bc_flag,
                       double* __restrict__ val) {
   constexpr int K = D + 1;
+  constexpr int KK = K * K;
   constexpr double MREF = 1.0 / ((D + 1) * (D + 2));
-  for (int64_t c = c_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < c_end;
-       c += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t t_end = c_end * KK;
+  for (int64_t t = c_begin * KK + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < t_end;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = t / KK;
+    const int ab = (int)(t - c * KK);
+    const int32_t pos = __ldg(cell2nnz + t);
+    if (pos < 0) continue;
+    const int a = ab / K, b = ab - a * K;
     CellData<D> cd;
     load_cell_data<D>(cells, coords, c, cd);
     double mubar = 0.0;
 #pragma unroll
-    for (int a = 0; a < K; ++a) mubar += mu[cd.v[a]];
+    for (int v = 0; v < K; ++v) mubar += mu[cd.v[v]];
     mubar *= (1.0 / K);
     const double scale = cell_scale ? cell_scale[c] : 1.0;
     const double vol = cd.g.vol;
     const double vm = scale * vol * mubar, vl = scale * vol * lambda_lame, dm = scale * damping * vol * MREF;
-    unsigned bcmask = 0;  // bit a*D+i
-    if (bc_flag) {
+    double Ga[D], Gb[D];
+    int va = 0, vb = 0;
 #pragma unroll
-      for (int a = 0; a < K; ++a) {
+    for (int v = 0; v < K; ++v) {
+      if (v == a) {
+        va = cd.v[v];
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-          if (bc_flag[(int64_t)cd.v[a] * D + i]) bcmask |= 1u << (a * D + i);
-        }
+        for (int i = 0; i < D; ++i) Ga[i] = cd.g.G[v][i];
+      }
+      if (v == b) {
+        vb = cd.v[v];
+#pragma unroll
+        for (int i = 0; i < D; ++i) Gb[i] = cd.g.G[v][i];
       }
     }
-    const int32_t* c2n = cell2nnz + c * (K * K);
+    unsigned bca = 0, bcb = 0;  // Dirichlet flags of the row dofs (a, i) and the column dofs (b, j)
+    if (bc_flag) {
 #pragma unroll
-    for (int a = 0; a < K; ++a) {
+      for (int i = 0; i < D; ++i) {
+        if (bc_flag[(int64_t)va * D + i]) bca |= 1u << i;
+        if (bc_flag[(int64_t)vb * D + i]) bcb |= 1u << i;
+      }
+    }
+    double gg = 0.0;
 #pragma unroll
-      for (int b = 0; b < K; ++b) {
-        const int32_t pos = __ldg(c2n + a * K + b);
-        if (pos < 0) continue;
-        double gg = 0.0;
+    for (int i = 0; i < D; ++i) gg += Ga[i] * Gb[i];
+    const double mass = (a == b) ? 2.0 * dm : dm;
+    double* blk = val + (int64_t)pos * (D * D);
 #pragma unroll
-        for (int i = 0; i < D; ++i) gg += cd.g.G[a][i] * cd.g.G[b][i];
-        const double mass = (a == b) ? 2.0 * dm : dm;
-        double* blk = val + (int64_t)pos * (D * D);
+    for (int i = 0; i < D; ++i) {
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-#pragma unroll
-          for (int j = 0; j < D; ++j) {
-            double e = vm * cd.g.G[a][j] * cd.g.G[b][i] + vl * cd.g.G[a][i] * cd.g.G[b][j];
-            if (i == j) e += vm * gg + mass;
-            if ((bcmask >> (a * D + i)) & 1u || (bcmask >> (b * D + j)) & 1u)
-              e = (a == b && i == j) ? 1.0 : 0.0;
-            blk[i * D + j] += e;
-          }
-        }
+      for (int j = 0; j < D; ++j) {
+        double e = vm * Ga[j] * Gb[i] + vl * Ga[i] * Gb[j];
+        if (i == j) e += vm * gg + mass;
+        if (((bca >> i) & 1u) || ((bcb >> j) & 1u)) e = (a == b && i == j) ? 1.0 : 0.0;
+        blk[i * D + j] += e;
       }
     }
   }
@@ -343,11 +357,11 @@ extern "C" int cb_assemble_elasticity(void* stream, const cb_mesh_view* m, const
   CB_CUDA_CHECK(cudaMemsetAsync(val, 0, sizeof(double) * m->nnz * m->dim * m->dim, s));
   return for_each_colour(m, [&](int64_t b, int64_t e, int grid) {
     if (m->dim == 2)
-      k_assemble_elasticity<2><<<grid, 128, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, mu,
-                                                   lambda_lame, damping, cell_scale, bc_flag, val);
+      k_assemble_elasticity<2><<<grid_for((e - b) * 9, 256, 8), 256, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, mu,
+                                                                            lambda_lame, damping, cell_scale, bc_flag, val);
     else
-      k_assemble_elasticity<3><<<grid, 128, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, mu,
-                                                   lambda_lame, damping, cell_scale, bc_flag, val);
+      k_assemble_elasticity<3><<<grid_for((e - b) * 16, 256, 8), 256, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, mu,
+                                                                             lambda_lame, damping, cell_scale, bc_flag, val);
   });
 }
 

@@ -29,12 +29,12 @@ def main():
         prob = getattr(sop, name)
         orig = prob.linear_solver.solve
 
-        def tolerant(*a, _orig=orig, **k):
+        def tolerant(*a, _orig=orig, _prob=prob, **k):
             try:
                 return _orig(*a, **k)
             except cb.PETScKSPError as e:  # -3 after `its` iterations is expected here
                 assert e.error_code == -3
-                return prob.linear_solver.last_result
+                return _prob.linear_solver.last_result
 
         prob.linear_solver.solve = tolerant
     for _ in range(2):
