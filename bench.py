@@ -321,7 +321,7 @@ def main() -> None:
                     "avg_launch_ms": avg_ms, "launches_profiled": spmv_prof, "algorithmic_bytes_per_launch": alg_bytes,
                     # fine-level launches per PCG iteration: 1 (w = A p) + 2*degree inside the AMG V-cycle
                     "spmv_share_of_step": (avg_ms * sum(i[2] for i in its) *
-                                           (5 if (args.pc == "hypre" and dist is None) else 1)) / ms}
+                                           (5 if args.pc == "hypre" else 1)) / ms}
 
     if rank == 0:
         line = {
@@ -331,7 +331,7 @@ def main() -> None:
             "config": {"workload": workload_name(args.n, args.gpus), "n": args.n, "tets": n_tets, "vertices": n_verts,
                        "block_nnz": nnzb_total, "krylov_its_state_adjoint_elasticity": list(its[-1]),
                        "ksp_options": {k: v for k, v in KSP.items()},
-                       "pc_on_device": ("smoothed-aggregation AMG" if (args.pc == "hypre" and dist is None) else "jacobi"),
+                       "pc_on_device": ("smoothed-aggregation AMG" if args.pc == "hypre" else "jacobi"),
                        "l2_policy": "inputs larger than L2 (elasticity matrix %.2f GB, L2 126 MB)" % (76e-9 * nnzb_rank),
                        "parallelism": "1 GPU" if dist is None else f"mesh partitioned into {world} vertex slabs, NCCL halo + allreduce"},
             "clocks": clocks,

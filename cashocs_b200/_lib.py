@@ -82,6 +82,8 @@ class cb_amg_level(C.Structure):
         ("b", C.c_void_p),
         ("t", C.c_void_p),
         ("d", C.c_void_p),
+        ("dist", C.c_void_p),
+        ("sendbuf", C.c_void_p),
     ]
 
 
@@ -158,7 +160,7 @@ SIGNATURES = {
     "cb_ksp_solve": (I32, [P, C.POINTER(cb_mat), P, P, C.POINTER(cb_ksp_opts), P, P, I64,
                            C.POINTER(cb_ksp_result), P, I64]),
     "cb_amg_block_trace": (I32, [P, C.POINTER(cb_mat), P]),
-    "cb_amg_smooth_prolongator": (I32, [P, C.POINTER(cb_mat), DBL, P, P, P, P]),
+    "cb_amg_smooth_prolongator": (I32, [P, C.POINTER(cb_mat), DBL, P, P, P, P, P]),
     "cb_amg_spgemm_terms": (I32, [P, I32, I32, I64, P, P, P, P, P, P]),
     "cb_amg_dense_inverse": (I32, [P, C.POINTER(cb_mat), P, P]),
     "cb_mesh_quality": (I32, [P, I32, I64, P, P, I32, P, P, P, I64]),
@@ -169,6 +171,7 @@ SIGNATURES = {
     "cb_intersection_test": (I32, [P, I32, I64, I64, P, P, P, P, P]),
     "cb_dist_unique_id": (I32, [P]),
     "cb_dist_create": (I32, [C.POINTER(P), P, I32, I32, I32, P, P, P, P, I64, I64]),
+    "cb_dist_clone_plan": (I32, [P, C.POINTER(P), I32, P, P, P, P, I64, I64]),
     "cb_dist_destroy": (I32, [P]),
     "cb_dist_halo_exchange": (I32, [P, P, P, I32, P]),
     "cb_dist_allreduce": (I32, [P, P, P, I32, I32]),

@@ -110,44 +110,86 @@ class _Level:
 
 
 class AMGSymbolic:
-    """Everything that depends only on the sparsity pattern (shared by all block sizes)."""
+    """Everything that depends only on the sparsity pattern (shared by all block sizes).
+
+    On a partitioned mesh (``dist`` given) aggregates never cross rank boundaries and the rows of
+    the partition interface (rows with ghost columns or in a send list) keep the *tentative*
+    prolongator row.  Then ``P`` maps owned fine nodes to owned coarse nodes only, the prolongator
+    row of every ghost node is known locally (``e_agg``), the Galerkin product of the owned coarse
+    rows needs no communication and the coarse operator stays globally symmetric.  Coarse ghost
+    nodes are the aggregates of the fine ghost nodes; every level gets its own halo plan.
+    """
 
     MAX_DENSE = 256  # scalar rows of a coarsest level that is inverted densely (bs <= 3 -> <= 85 nodes)
+    MIN_DIST_COARSE = 300  # global size at which a distributed hierarchy stops (Chebyshev coarse solve)
 
-    def __init__(self, rowptr, col, n, ncols, max_levels: int = 12) -> None:
+    def __init__(self, rowptr, col, n, ncols, dist=None, max_levels: int = 12) -> None:
         self.levels: list[_Level] = []
+        dev = col.device
         while True:
             L = _Level()
-            L.n, L.ncols, L.rowptr, L.col = n, ncols, rowptr, col
+            L.n, L.ncols, L.rowptr, L.col, L.dist = n, ncols, rowptr, col, dist
             L.nnzb = int(rowptr[-1].item())
             L.last = True
+            L.iface = None
             self.levels.append(L)
-            if n * 3 <= self.MAX_DENSE or len(self.levels) >= max_levels:
+            n_glob = n if dist is None else int(round(dist.allreduce_scalar(float(n), "sum")))
+            small = (n_glob * 3 <= self.MAX_DENSE) if dist is None else (n_glob <= self.MIN_DIST_COARSE)
+            if small or len(self.levels) >= max_levels:
                 break
             rows = _rows_of(rowptr)
-            keep = col < n  # local columns only (ghost couplings are not part of the preconditioner)
-            a_index = torch.nonzero(keep).reshape(-1)
-            r, c = rows[keep], col[keep].long()
-            agg, nc = mis_aggregate(r, c, n)
-            if nc >= 0.8 * n or nc < 1:
+            local = col < n
+            agg, nc = mis_aggregate(rows[local], col[local].long(), n)
+            nc_glob = nc if dist is None else int(round(dist.allreduce_scalar(float(nc), "sum")))
+            if nc_glob >= 0.8 * n_glob or nc_glob < 1:
                 break
-            key = torch.unique(r * nc + agg.long()[c])
-            p_rows = key // nc
-            L.p_rowptr = _rowptr_from_rows(p_rows, n)
-            L.p_col = (key % nc).to(torch.int32).contiguous()
-            order = torch.argsort(L.p_col.long() * n + p_rows)
+            agg = agg.long()
+            new_dist = None
+            if dist is None:
+                agg_ext, gc = agg, 0
+                pr, pc = rows, agg[col.long()]
+            else:
+                iface = torch.zeros(n, dtype=torch.bool, device=dev)
+                iface[rows[~local]] = True
+                if dist.send_idx is not None and dist.send_idx.numel():
+                    iface[dist.send_idx.long()] = True
+                L.iface = iface.to(torch.uint8).contiguous()
+                # aggregate ids of the ghost nodes (owner-local numbering) through one halo exchange
+                v = torch.zeros(ncols, dtype=torch.float64, device=dev)
+                v[:n] = agg.to(torch.float64)
+                dist.halo_exchange(v, 1)
+                gid = v[n:].round().long()
+                owner = dist.owner_of_ghost().to(dev)
+                big = int(gid.max().item()) + 1 if gid.numel() else 1
+                ukey, inv = torch.unique(owner * big + gid, return_inverse=True)  # sorted by (owner, id)
+                gc = int(ukey.numel())
+                agg_ext = torch.cat([agg, nc + inv])
+                new_dist = dist.derive_plan(ukey // big, ukey % big, nc, dev)
+                # P rows: interior rows are smoothed (pattern = aggregates of all neighbours, all owned),
+                # interface rows stay tentative, ghost rows are the owners' tentative rows
+                interior_entry = ~iface[rows]
+                pr = torch.cat([rows[interior_entry], torch.nonzero(iface).reshape(-1), torch.arange(n, ncols, device=dev)])
+                pc = torch.cat([agg_ext[col.long()[interior_entry]], agg[iface], agg_ext[n:]])
+            nct = nc + gc
+            key = torch.unique(pr * nct + pc)
+            p_rows = key // nct
+            L.p_rowptr = _rowptr_from_rows(p_rows, ncols)
+            L.p_col = (key % nct).to(torch.int32).contiguous()
+            L.nnzp_owned = int(L.p_rowptr[n].item())
+            po_rows, po_col = p_rows[: L.nnzp_owned], L.p_col[: L.nnzp_owned].long()
+            order = torch.argsort(po_col * n + po_rows)
             L.pt_perm = order
-            L.pt_col = p_rows[order].to(torch.int32).contiguous()
-            L.pt_rowptr = _rowptr_from_rows(L.p_col.long()[order], nc)
-            L.agg, L.nc = agg.contiguous(), nc
+            L.pt_col = po_rows[order].to(torch.int32).contiguous()
+            L.pt_rowptr = _rowptr_from_rows(po_col[order], nc)
+            L.agg, L.nc, L.gc = agg_ext.to(torch.int32).contiguous(), nc, gc
+            nnza = col.numel()
             L.ap_rowptr, L.ap_col, L.ap_seg, L.ap_sl, L.ap_sr = _expand_terms(
-                r, c, a_index, L.p_rowptr, L.p_col, n, nc)
-            nnzp = L.p_col.numel()
+                rows, col.long(), torch.arange(nnza, device=dev), L.p_rowptr, L.p_col, n, nct)
             c_rowptr, c_col, L.ac_seg, L.ac_sl, L.ac_sr = _expand_terms(
-                _rows_of(L.pt_rowptr), L.pt_col.long(), torch.arange(nnzp, device=col.device), L.ap_rowptr, L.ap_col,
-                nc, nc)
+                _rows_of(L.pt_rowptr), L.pt_col.long(), torch.arange(L.nnzp_owned, device=dev), L.ap_rowptr, L.ap_col,
+                nc, nct)
             L.last = False
-            rowptr, col, n, ncols = c_rowptr, c_col, nc, nc
+            rowptr, col, n, ncols, dist = c_rowptr, c_col, nc, nct, new_dist
 
     @property
     def sizes(self):
@@ -167,8 +209,10 @@ class AMGHierarchy:
         self.device = dev = A.val.device
         self.smooth_degree, self.coarse_degree = int(smooth_degree), int(coarse_degree)
         self.smooth_ratio, self.coarse_ratio = float(smooth_ratio), float(coarse_ratio)
-        self.symbolic = symbolic if symbolic is not None else AMGSymbolic(A.rowptr, A.col, A.nrows, A.ncols)
+        self.symbolic = symbolic if symbolic is not None else AMGSymbolic(A.rowptr, A.col, A.nrows, A.ncols,
+                                                                         dist=A.mesh.dist)
         self.levels = self.symbolic.levels
+        self.distributed = self.levels[0].dist is not None
         self.version = None
         self.power_its = 12
         self._power_x: dict = {}
@@ -183,18 +227,20 @@ class AMGHierarchy:
             D.d = torch.zeros(nb, **f64)
             D.x = None if li == 0 else torch.zeros(L.ncols * bs, **f64)
             D.b = None if li == 0 else torch.zeros(nb, **f64)
+            D.sendbuf = None
+            if L.dist is not None:
+                D.sendbuf = torch.zeros(max(int(L.dist.send_off[-1]) * bs, 1), **f64)
             D.lmax = 2.0
             if not L.last:
-                nnzp = L.p_col.numel()
-                D.p_val = torch.zeros(nnzp, **f64)
-                D.pt_val = torch.zeros(nnzp, **f64)
+                D.p_val = torch.ones(L.p_col.numel(), **f64)  # ghost rows stay 1.0 (tentative)
+                D.pt_val = torch.zeros(L.nnzp_owned, **f64)
                 D.ap_val = torch.zeros(L.ap_col.numel() * bs * bs, **f64)
                 D.s_val = torch.zeros(L.nnzb, **f64) if bs > 1 else None
                 D.s_dinv = torch.zeros(L.n, **f64)
             self.data.append(D)
         last = self.levels[-1]
         self.coarse_inv = self.coarse_work = None
-        if last.n * bs <= AMGSymbolic.MAX_DENSE and len(self.levels) > 1:
+        if not self.distributed and last.n * bs <= AMGSymbolic.MAX_DENSE and len(self.levels) > 1:
             nn = last.n * bs
             self.coarse_inv = torch.zeros(nn * nn, **f64)
             self.coarse_work = torch.zeros(2 * nn * nn, **f64)
@@ -227,18 +273,20 @@ class AMGHierarchy:
         Gershgorin is a safe bound but 2-6x too large for elasticity rows and for smoothed-aggregation
         coarse operators, which would push the Chebyshev interval off the spectrum; so the bound is
         tightened with `power_its` steps of the power method on D^-1 A (fixed start vector ->
-        deterministic) times a 1.15 safety factor, never exceeding Gershgorin.
+        deterministic) times a 1.15 safety factor, never exceeding Gershgorin.  On a partitioned
+        mesh both numbers are global (halo exchange per step, all-reduced norms), so every rank
+        builds the same Chebyshev polynomials.
         """
         lib = _lib.load()
         s = _lib.stream_ptr()
         _lib.check(lib.cb_extract_diag_inv(s, C.byref(m), _lib.ptr(dinv), _lib.ptr(self.lmax_dev),
                                            _lib.ptr(self.scratch), self.scratch.numel()), "cb_extract_diag_inv")
-        ncol = L.ncols * (nscalar // L.n)
+        comp = nscalar // L.n
+        ncol = L.ncols * comp
         x = self._power_x.get((id(L), nscalar))
         if x is None:
             gen = torch.Generator(device="cpu").manual_seed(1234 + nscalar)
-            x0 = torch.rand(nscalar, generator=gen, dtype=torch.float64) + 0.5
-            x0 = (x0 / torch.linalg.vector_norm(x0)).to(self.device)
+            x0 = (torch.rand(nscalar, generator=gen, dtype=torch.float64) + 0.5).to(self.device)
             x = (torch.zeros(ncol, dtype=torch.float64, device=self.device), x0,
                  torch.zeros(nscalar, dtype=torch.float64, device=self.device))
             self._power_x[(id(L), nscalar)] = x
@@ -246,11 +294,19 @@ class AMGHierarchy:
         xin[:nscalar] = x0
         nrm = None
         for _ in range(self.power_its):
+            if L.dist is not None:
+                L.dist.halo_exchange(xin, comp)
             _lib.check(lib.cb_spmv(s, C.byref(m), _lib.ptr(xin), _lib.ptr(y)), "cb_spmv")
             y.mul_(dinv[:nscalar])
-            nrm = torch.linalg.vector_norm(y)
+            nrm2 = torch.sum(y * y).reshape(1)
+            if L.dist is not None:
+                L.dist.allreduce(nrm2, "sum")
+            nrm = torch.sqrt(nrm2[0])
             torch.div(y, nrm, out=xin[:nscalar])
+        if L.dist is not None:
+            L.dist.allreduce(self.lmax_dev, "max")
         both = torch.stack([self.lmax_dev[0], nrm]).cpu()  # one host sync per estimate
+        # the first power step starts from an un-normalised vector; later steps are normalised
         return min(float(both[0]), 1.15 * float(both[1]))
 
     def numeric(self, A) -> None:
@@ -277,9 +333,10 @@ class AMGHierarchy:
             ms = self._mat(L, sval, 1)
             lmax_s = self._diag_inv(ms, D.s_dinv, L, L.n)
             omega = (4.0 / 3.0) / lmax_s
-            _lib.check(lib.cb_amg_smooth_prolongator(s, C.byref(ms), omega, _lib.ptr(L.agg), _lib.ptr(L.p_rowptr),
-                                                     _lib.ptr(L.p_col), _lib.ptr(D.p_val)), "cb_amg_smooth_prolongator")
-            torch.index_select(D.p_val, 0, L.pt_perm, out=D.pt_val)
+            _lib.check(lib.cb_amg_smooth_prolongator(s, C.byref(ms), omega, _lib.ptr(L.agg), _lib.ptr(L.iface),
+                                                     _lib.ptr(L.p_rowptr), _lib.ptr(L.p_col), _lib.ptr(D.p_val)),
+                       "cb_amg_smooth_prolongator")
+            torch.index_select(D.p_val[: L.nnzp_owned], 0, L.pt_perm, out=D.pt_val)
             nxt = self.data[li + 1]
             _lib.check(lib.cb_amg_spgemm_terms(s, bs, 1, L.ap_col.numel(), _lib.ptr(L.ap_seg), _lib.ptr(L.ap_sl),
                                                _lib.ptr(L.ap_sr), _lib.ptr(val), _lib.ptr(D.p_val), _lib.ptr(D.ap_val)),
@@ -307,6 +364,9 @@ class AMGHierarchy:
             e.x = D.x.data_ptr() if D.x is not None else None
             e.b = D.b.data_ptr() if D.b is not None else None
             e.t, e.d = D.t.data_ptr(), D.d.data_ptr()
+            if L.dist is not None:
+                e.dist = L.dist.handle
+                e.sendbuf = D.sendbuf.data_ptr()
         h = _lib.cb_amg()
         h.nlevels = len(self.levels)
         h.smooth_degree, h.coarse_degree = self.smooth_degree, self.coarse_degree

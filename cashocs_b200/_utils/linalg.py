@@ -82,12 +82,9 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None, distr
         ksp, pc = base["ksp_type"], base["pc_type"]
         opts = {**base}
     elif pc in ("hypre", "gamg", "ml", "amg"):
-        # algebraic multigrid -> the device smoothed-aggregation AMG (one GPU); on a partitioned
-        # mesh the hierarchy is not distributed yet, so the solve falls back to Jacobi with the
-        # AMG iteration budget (100 / 1000) lifted -- an explicit, documented substitution
-        pc = "jacobi" if distributed else "amg"
-        if distributed:
-            opts["ksp_max_it"] = max(int(opts.get("ksp_max_it", 10000)), 200000)
+        # algebraic multigrid -> the device smoothed-aggregation AMG (also on a partitioned mesh:
+        # rank-local aggregates, tentative interface rows, per-level halo plans)
+        pc = "amg"
         if float(opts.get("ksp_rtol", 1e-5)) < 1e-14:
             opts["ksp_rtol"] = 1e-14  # rtol 1e-16 / 1e-20 is below what fp64 round-off lets PCG reach
     if pc == "ksp":  # PETSc spelling of a polynomial preconditioner
@@ -361,7 +358,7 @@ class LinearSolver:
             skey = (id(A.mesh), "symbolic")
             sym = cls._amg_cache.get(skey)
             if sym is None or sym.levels[0].rowptr is not A.rowptr:
-                sym = amg.AMGSymbolic(A.rowptr, A.col, A.nrows, A.ncols)
+                sym = amg.AMGSymbolic(A.rowptr, A.col, A.nrows, A.ncols, dist=A.mesh.dist)
                 cls._amg_cache[skey] = sym
             h = amg.AMGHierarchy(
                 A, sym, smooth_degree=int(options.get("pc_amg_smooth_degree", 2)),

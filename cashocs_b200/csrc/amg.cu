@@ -35,11 +35,16 @@ __device__ __forceinline__ int64_t find_col(const int32_t* __restrict__ col, int
 __global__ void __launch_bounds__(128)
 k_smooth_prolongator(int64_t n, int64_t nlocal, const int64_t* __restrict__ s_rowptr,
                      const int32_t* __restrict__ s_col, const double* __restrict__ s_val, double omega,
-                     const int32_t* __restrict__ agg, const int64_t* __restrict__ p_rowptr,
-                     const int32_t* __restrict__ p_col, double* __restrict__ p_val) {
+                     const int32_t* __restrict__ agg, const uint8_t* __restrict__ tentative,
+                     const int64_t* __restrict__ p_rowptr, const int32_t* __restrict__ p_col,
+                     double* __restrict__ p_val) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pb = p_rowptr[i], pe = p_rowptr[i + 1];
+    if (tentative && tentative[i]) {  // interface row of a partitioned mesh: P[i, agg(i)] = 1
+      p_val[pb] = 1.0;
+      continue;
+    }
     for (int64_t k = pb; k < pe; ++k) p_val[k] = 0.0;
     double sii = 0.0;
     for (int64_t k = s_rowptr[i]; k < s_rowptr[i + 1]; ++k)
@@ -230,10 +235,11 @@ extern "C" int cb_amg_block_trace(void* stream, const cb_mat* A, double* s_val) 
 }
 
 extern "C" int cb_amg_smooth_prolongator(void* stream, const cb_mat* S, double omega, const int32_t* agg,
-                                         const int64_t* p_rowptr, const int32_t* p_col, double* p_val) {
+                                         const uint8_t* tentative, const int64_t* p_rowptr,
+                                         const int32_t* p_col, double* p_val) {
   CB_REQUIRE(S && S->bs == 1 && agg && p_rowptr && p_col && p_val, "cb_amg_smooth_prolongator: bad argument");
   k_smooth_prolongator<<<grid_for(S->nrows, 128, 16), 128, 0, as_stream(stream)>>>(
-      S->nrows, S->nrows, S->rowptr, S->col, S->val, omega, agg, p_rowptr, p_col, p_val);
+      S->nrows, S->ncols, S->rowptr, S->col, S->val, omega, agg, tentative, p_rowptr, p_col, p_val);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }

@@ -77,6 +77,7 @@ struct cb_dist {
   std::vector<int64_t> send_off, recv_off;
   const int32_t* send_idx = nullptr;  // device
   int64_t n_owned = 0, n_ghost = 0;
+  bool owns_comm = true;               // false for plans cloned from a parent (AMG coarse levels)
 };
 
 namespace cb {
@@ -162,9 +163,28 @@ extern "C" int cb_dist_create(cb_dist** out, const char* id128, int rank, int nr
   return CB_OK;
 }
 
+extern "C" int cb_dist_clone_plan(cb_dist* parent, cb_dist** out, int nneigh, const int32_t* neigh_rank,
+                                  const int64_t* send_off, const int32_t* send_idx_dev,
+                                  const int64_t* recv_off, int64_t n_owned, int64_t n_ghost) {
+  CB_REQUIRE(parent && out, "cb_dist_clone_plan: missing argument");
+  cb_dist* d = new cb_dist();
+  d->comm = parent->comm;
+  d->owns_comm = false;
+  d->rank = parent->rank;
+  d->nranks = parent->nranks;
+  d->neigh.assign(neigh_rank, neigh_rank + nneigh);
+  d->send_off.assign(send_off, send_off + nneigh + 1);
+  d->recv_off.assign(recv_off, recv_off + nneigh + 1);
+  d->send_idx = send_idx_dev;
+  d->n_owned = n_owned;
+  d->n_ghost = n_ghost;
+  *out = d;
+  return CB_OK;
+}
+
 extern "C" int cb_dist_destroy(cb_dist* d) {
   if (!d) return CB_OK;
-  if (d->comm) g_nccl.CommDestroy(d->comm);
+  if (d->comm && d->owns_comm) g_nccl.CommDestroy(d->comm);
   delete d;
   return CB_OK;
 }

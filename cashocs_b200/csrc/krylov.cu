@@ -519,6 +519,12 @@ struct Solver {
     }
   }
 
+  // t_l = A_l x_l (ghost update of x_l first on a partitioned mesh)
+  int level_spmv(const cb_amg_level& L, double* xl) {
+    if (L.dist) { if (int e = dist_halo_exchange(s, L.dist, xl, bs, L.sendbuf)) return e; }
+    return spmv_dispatch(s, &L.A, xl, L.t, nullptr, nullptr, nullptr, &st->done);
+  }
+
   // `degree` Chebyshev-Jacobi steps on A_l x = b (zero or current initial guess); local operator
   int amg_smooth(const cb_amg_level& L, const double* bl, double* xl, int degree, double ratio, bool zero_guess) {
     const int64_t nl = L.A.nrows * bs;
@@ -533,7 +539,7 @@ struct Solver {
       j0 = 1;
     }
     for (int j = j0; j < degree; ++j) {
-      if (int e = spmv_dispatch(s, &L.A, xl, L.t, nullptr, nullptr, nullptr, &st->done)) return e;
+      if (int e = level_spmv(L, xl)) return e;
       const double c1 = (j == 0) ? 0.0 : coef[j].first;
       const double c2 = (j == 0) ? inv_theta : coef[j].second;
       k_cheb_step<<<g, 256, 0, s>>>(nl, bl, L.t, L.dinv, c1, c2, L.d, xl, st);
@@ -558,7 +564,7 @@ struct Solver {
         break;
       }
       if (int e = amg_smooth(lev, bl, xl, h->smooth_degree, h->smooth_ratio, true)) return e;
-      if (int e = spmv_dispatch(s, &lev.A, xl, lev.t, nullptr, nullptr, nullptr, &st->done)) return e;
+      if (int e = level_spmv(lev, xl)) return e;
       if (int e = amg_restrict(s, bs, &lev, bl, lev.t, h->levels[l + 1].b, &st->done)) return e;
     }
     for (int l = L - 2; l >= 0; --l) {

@@ -42,6 +42,7 @@ class DistContext:
         self.n_owned = self.n_ghost = 0
         self._sendbuf: torch.Tensor | None = None
         self.cell_counts: list[int] | None = None
+        self.parent: DistContext | None = None  # plans derived for AMG coarse levels share the communicator
 
     # ------------------------------------------------------------------ setup
     def set_plan(self, neigh, send_lists, recv_counts, n_owned: int, n_ghost: int, device) -> None:
@@ -62,6 +63,17 @@ class DistContext:
 
     def _create_native(self, device) -> None:
         lib = _lib.load()
+        neigh = np.asarray(self.neigh, dtype=np.int32)
+        if self.parent is not None:
+            handle = C.c_void_p()
+            _lib.check(
+                lib.cb_dist_clone_plan(self.parent.handle, C.byref(handle), len(self.neigh), neigh.ctypes.data,
+                                       self.send_off.ctypes.data, _lib.ptr(self.send_idx), self.recv_off.ctypes.data,
+                                       self.n_owned, self.n_ghost),
+                "cb_dist_clone_plan",
+            )
+            self.handle = handle
+            return
         ident = [None]
         if self.rank == 0:
             buf = C.create_string_buffer(128)
@@ -77,6 +89,26 @@ class DistContext:
             "cb_dist_create",
         )
         self.handle = handle
+
+    def owner_of_ghost(self) -> torch.Tensor:
+        """Owner rank of every ghost vertex (ghosts are ordered by owner)."""
+        counts = torch.from_numpy(np.diff(self.recv_off))
+        return torch.repeat_interleave(torch.tensor(self.neigh, dtype=torch.int64), counts)
+
+    def derive_plan(self, owners: torch.Tensor, ids: torch.Tensor, n_owned: int, device) -> "DistContext":
+        """Halo plan of a derived (coarser) numbering: this rank needs the entities ``ids`` (numbered
+        locally by their owner) of ranks ``owners``; both sorted by (owner, id).  Collective."""
+        need = {int(r): ids[owners == r].cpu() for r in torch.unique(owners).tolist()}
+        all_need = [None] * self.world
+        td.all_gather_object(all_need, need)
+        neigh = sorted(set(need) | {r for r in range(self.world) if r != self.rank and self.rank in all_need[r]})
+        empty = torch.zeros(0, dtype=torch.int64)
+        send_lists = [all_need[r].get(self.rank, empty).to(torch.int64) for r in neigh]
+        recv_counts = [int(need[r].numel()) if r in need else 0 for r in neigh]
+        new = DistContext(self.rank, self.world, self.transport)
+        new.parent = self if self.parent is None else self.parent
+        new.set_plan(neigh, send_lists, recv_counts, n_owned, int(ids.numel()), device)
+        return new
 
     def destroy(self) -> None:
         if self.handle is not None:

@@ -184,6 +184,8 @@ int cb_extract_diag_inv(void* stream, const cb_mat* A, double* dinv, double* lma
 #define CB_PC_CHEBYSHEV 2
 #define CB_PC_AMG 3
 
+typedef struct cb_dist cb_dist; /* opaque multi-GPU context (communicator + halo plan), NULL for one GPU */
+
 /* Smoothed-aggregation AMG hierarchy (device counterpart of `pc_type hypre|gamg`, the reference's
  * iterative default cashocs/_utils/linalg.py:44-52).  All arrays are caller-owned device memory;
  * the symbolic data (patterns) is built once per sparsity pattern by the host layer, the values by
@@ -205,6 +207,8 @@ typedef struct {
   double* b;                /* [A.nrows*bs] level rhs       (unused on level 0: caller's r) */
   double* t;                /* [A.nrows*bs] A*x scratch */
   double* d;                /* [A.nrows*bs] Chebyshev direction */
+  cb_dist* dist;            /* halo plan of this level (NULL on one GPU) */
+  double* sendbuf;          /* [send count * bs] pack buffer of this level's halo exchange */
 } cb_amg_level;
 typedef struct {
   int32_t nlevels;
@@ -254,9 +258,12 @@ int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, double* x,
 
 /* AMG numeric phase.  s_val [nnzb] = trace(A_blk)/bs (the scalar strength matrix S). */
 int cb_amg_block_trace(void* stream, const cb_mat* A, double* s_val);
-/* P = T - omega D_S^-1 S T for the piecewise-constant tentative prolongator T of `agg` [nrows]. */
+/* P = T - omega D_S^-1 S T for the piecewise-constant tentative prolongator T of `agg` [ncols]
+ * (ghost columns carry their coarse ghost index).  Rows flagged in `tentative` (uint8 [nrows],
+ * nullable: the partition-interface rows of a distributed mesh) keep the unsmoothed row e_agg. */
 int cb_amg_smooth_prolongator(void* stream, const cb_mat* S, double omega, const int32_t* agg,
-                              const int64_t* p_rowptr, const int32_t* p_col, double* p_val);
+                              const uint8_t* tentative, const int64_t* p_rowptr, const int32_t* p_col,
+                              double* p_val);
 /* Numeric sparse product with a precomputed term list (symbolic phase of the host layer):
  * out[q] = sum_{t in [seg_ptr[q], seg_ptr[q+1])} lhs[src_l[t]] * rhs[src_r[t]], where exactly one
  * operand holds bs x bs blocks (lhs_block != 0: lhs, else rhs) and the other is scalar.  Used for
@@ -312,6 +319,10 @@ int cb_dist_unique_id(char* id128);
 int cb_dist_create(cb_dist** out, const char* id128, int rank, int nranks, int nneigh,
                    const int32_t* neigh_rank, const int64_t* send_off, const int32_t* send_idx_dev,
                    const int64_t* recv_off, int64_t n_owned, int64_t n_ghost);
+/* A second halo plan (e.g. an AMG coarse level) on the communicator of `parent`. */
+int cb_dist_clone_plan(cb_dist* parent, cb_dist** out, int nneigh, const int32_t* neigh_rank,
+                       const int64_t* send_off, const int32_t* send_idx_dev, const int64_t* recv_off,
+                       int64_t n_owned, int64_t n_ghost);
 int cb_dist_destroy(cb_dist* d);
 /* Ghost update of a vertex-blocked vector x [(n_owned+n_ghost)*bs] (Vec.ghostUpdate). */
 int cb_dist_halo_exchange(void* stream, cb_dist* d, double* x, int bs, double* sendbuf);

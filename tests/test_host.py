@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.cb_mat) == 48
     assert ctypes.sizeof(_lib.cb_mesh_view) == 64
     assert ctypes.sizeof(_lib.cb_ksp_opts) == 72
-    assert ctypes.sizeof(_lib.cb_amg_level) == 152
+    assert ctypes.sizeof(_lib.cb_amg_level) == 168
     assert ctypes.sizeof(_lib.cb_amg) == 48
     assert ctypes.sizeof(_lib.cb_ksp_result) == 40
 
@@ -68,8 +68,8 @@ def test_ksp_option_parsing():
     assert (o.ksp_type, o.pc_type, o.rtol) == (0, 1, 1e-13)
     o = linalg.parse_ksp_options(linalg.iterative_ksp_options)  # cg + boomeramg -> device AMG (one GPU)
     assert (o.ksp_type, o.pc_type) == (0, 3) and o.rtol == 1e-14
-    o = linalg.parse_ksp_options(linalg.iterative_ksp_options, distributed=True)  # partitioned mesh: Jacobi, budget lifted
-    assert (o.ksp_type, o.pc_type) == (0, 1) and o.rtol == 1e-14 and o.max_it >= 200000
+    o = linalg.parse_ksp_options(linalg.iterative_ksp_options, distributed=True)  # partitioned mesh: distributed AMG
+    assert (o.ksp_type, o.pc_type) == (0, 3) and o.rtol == 1e-14
     o = linalg.parse_ksp_options({"ksp_type": "minres", "pc_type": "none", "ksp_monitor": None})
     assert (o.ksp_type, o.pc_type, o.monitor) == (1, 0, 1)
     o = linalg.parse_ksp_options({"ksp_type": "cg", "pc_type": "ksp", "ksp_ksp_type": "chebyshev", "ksp_ksp_max_it": 4, "ksp_pc_type": "jacobi"})
