@@ -84,6 +84,8 @@ class cb_amg_level(C.Structure):
         ("d", C.c_void_p),
         ("dist", C.c_void_p),
         ("sendbuf", C.c_void_p),
+        ("rep_dist", C.c_void_p),
+        ("rep_off", C.c_int64),
     ]
 
 

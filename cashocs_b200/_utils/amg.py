@@ -121,20 +121,28 @@ class AMGSymbolic:
     """
 
     MAX_DENSE = 256  # scalar rows of a coarsest level that is inverted densely (bs <= 3 -> <= 85 nodes)
-    MIN_DIST_COARSE = 300  # global size at which a distributed hierarchy stops (Chebyshev coarse solve)
+    AGGLOMERATE = 20000  # global node count below which a distributed level is replicated on every rank
 
     def __init__(self, rowptr, col, n, ncols, dist=None, max_levels: int = 12) -> None:
         self.levels: list[_Level] = []
         dev = col.device
         while True:
             L = _Level()
+            L.rep_dist, L.rep_off, L.rep_pos, L.rep_nnzb_local = None, 0, None, 0
+            n_glob = n if dist is None else int(round(dist.allreduce_scalar(float(n), "sum")))
+            if dist is not None and self.levels and n_glob <= self.AGGLOMERATE:
+                # agglomeration: below this size halo latency dominates, so the level (and everything
+                # coarser) is replicated on every rank; the restriction all-reduces the rhs instead
+                L.rep_dist, L.rep_nnzb_local = dist, int(col.numel())
+                rowptr, col, L.rep_off, L.rep_pos = self._replicate(rowptr, col, n, ncols, n_glob, dist)
+                n = ncols = n_glob
+                dist = None
             L.n, L.ncols, L.rowptr, L.col, L.dist = n, ncols, rowptr, col, dist
             L.nnzb = int(rowptr[-1].item())
             L.last = True
             L.iface = None
             self.levels.append(L)
-            n_glob = n if dist is None else int(round(dist.allreduce_scalar(float(n), "sum")))
-            small = (n_glob * 3 <= self.MAX_DENSE) if dist is None else (n_glob <= self.MIN_DIST_COARSE)
+            small = n_glob * 3 <= self.MAX_DENSE
             if small or len(self.levels) >= max_levels:
                 break
             rows = _rows_of(rowptr)
@@ -191,6 +199,38 @@ class AMGSymbolic:
             L.last = False
             rowptr, col, n, ncols, dist = c_rowptr, c_col, nc, nct, new_dist
 
+    @staticmethod
+    def _replicate(rowptr, col, n, ncols, n_glob, dist):
+        """Global pattern of a distributed level, identical on every rank (collective).
+
+        Global node ids are rank offset + local id.  Returns (rowptr, col) of the global CSR, this
+        rank's node offset and, for every local entry, its position in the global value array.
+        """
+        import torch.distributed as td
+
+        dev = col.device
+        counts = [None] * dist.world
+        td.all_gather_object(counts, int(n))
+        off = int(sum(counts[: dist.rank]))
+        v = torch.zeros(ncols, dtype=torch.float64, device=dev)
+        v[:n] = torch.arange(off, off + n, dtype=torch.float64, device=dev)
+        dist.halo_exchange(v, 1)
+        gid = v.round().long()
+        key = gid[_rows_of(rowptr)] * n_glob + gid[col.long()]
+        allk = [None] * dist.world
+        td.all_gather_object(allk, key.cpu())
+        start = int(sum(k.numel() for k in allk[: dist.rank]))
+        allkeys = torch.cat(allk).to(dev)
+        skeys, order = torch.sort(allkeys)
+        if skeys.numel() > 1 and bool((skeys[1:] == skeys[:-1]).any()):
+            raise RuntimeError("replicated AMG level: a matrix row is owned by two ranks")
+        inv = torch.empty_like(order)
+        inv[order] = torch.arange(order.numel(), device=dev)
+        pos = inv[start: start + key.numel()].contiguous()
+        g_rowptr = _rowptr_from_rows(skeys // n_glob, n_glob)
+        g_col = (skeys % n_glob).to(torch.int32).contiguous()
+        return g_rowptr, g_col, off, pos
+
     @property
     def sizes(self):
         return [L.n for L in self.levels]
@@ -222,6 +262,8 @@ class AMGHierarchy:
             D = _Level()
             nb = L.n * bs
             D.val = None if li == 0 else torch.zeros(L.nnzb * bs * bs, **f64)
+            # rows of a replicated level computed by this rank (scattered + all-reduced into D.val)
+            D.val_local = torch.zeros(L.rep_nnzb_local * bs * bs, **f64) if L.rep_dist is not None else None
             D.dinv = torch.zeros(nb, **f64)
             D.t = torch.zeros(nb, **f64)
             D.d = torch.zeros(nb, **f64)
@@ -240,7 +282,7 @@ class AMGHierarchy:
             self.data.append(D)
         last = self.levels[-1]
         self.coarse_inv = self.coarse_work = None
-        if not self.distributed and last.n * bs <= AMGSymbolic.MAX_DENSE and len(self.levels) > 1:
+        if last.dist is None and last.n * bs <= AMGSymbolic.MAX_DENSE and len(self.levels) > 1:
             nn = last.n * bs
             self.coarse_inv = torch.zeros(nn * nn, **f64)
             self.coarse_work = torch.zeros(2 * nn * nn, **f64)
@@ -267,7 +309,7 @@ class AMGHierarchy:
         m.rowptr, m.col, m.val = L.rowptr.data_ptr(), L.col.data_ptr(), val.data_ptr()
         return m
 
-    def _diag_inv(self, m, dinv, L, nscalar: int) -> float:
+    def _diag_inv(self, m, dinv, L, nscalar: int, safe: bool = False) -> float:
         """Inverse diagonal and an upper estimate of lambda_max(D^-1 A).
 
         Gershgorin is a safe bound but 2-6x too large for elasticity rows and for smoothed-aggregation
@@ -281,6 +323,12 @@ class AMGHierarchy:
         s = _lib.stream_ptr()
         _lib.check(lib.cb_extract_diag_inv(s, C.byref(m), _lib.ptr(dinv), _lib.ptr(self.lmax_dev),
                                            _lib.ptr(self.scratch), self.scratch.numel()), "cb_extract_diag_inv")
+        if safe:
+            # coarsest level without a dense inverse: a degree-16 Chebyshev "solve" turns indefinite
+            # if lambda_max is underestimated at all, so take the rigorous Gershgorin bound
+            if L.dist is not None:
+                L.dist.allreduce(self.lmax_dev, "max")
+            return float(self.lmax_dev.item())
         comp = nscalar // L.n
         ncol = L.ncols * comp
         x = self._power_x.get((id(L), nscalar))
@@ -322,7 +370,7 @@ class AMGHierarchy:
                 _lib.check(lib.cb_amg_dense_inverse(s, C.byref(m), _lib.ptr(self.coarse_work), _lib.ptr(self.coarse_inv)),
                            "cb_amg_dense_inverse")
                 break
-            D.lmax = self._diag_inv(m, D.dinv, L, L.n * bs)
+            D.lmax = self._diag_inv(m, D.dinv, L, L.n * bs, safe=L.last)
             if L.last:
                 break
             if bs > 1:
@@ -337,13 +385,19 @@ class AMGHierarchy:
                                                      _lib.ptr(L.p_rowptr), _lib.ptr(L.p_col), _lib.ptr(D.p_val)),
                        "cb_amg_smooth_prolongator")
             torch.index_select(D.p_val[: L.nnzp_owned], 0, L.pt_perm, out=D.pt_val)
-            nxt = self.data[li + 1]
+            nxt, nxtL = self.data[li + 1], self.levels[li + 1]
+            rep = nxtL.rep_dist is not None
+            out = nxt.val_local if rep else nxt.val
             _lib.check(lib.cb_amg_spgemm_terms(s, bs, 1, L.ap_col.numel(), _lib.ptr(L.ap_seg), _lib.ptr(L.ap_sl),
                                                _lib.ptr(L.ap_sr), _lib.ptr(val), _lib.ptr(D.p_val), _lib.ptr(D.ap_val)),
                        "cb_amg_spgemm_terms(AP)")
-            _lib.check(lib.cb_amg_spgemm_terms(s, bs, 0, self.levels[li + 1].nnzb, _lib.ptr(L.ac_seg), _lib.ptr(L.ac_sl),
-                                               _lib.ptr(L.ac_sr), _lib.ptr(D.pt_val), _lib.ptr(D.ap_val), _lib.ptr(nxt.val)),
+            _lib.check(lib.cb_amg_spgemm_terms(s, bs, 0, out.numel() // (bs * bs), _lib.ptr(L.ac_seg), _lib.ptr(L.ac_sl),
+                                               _lib.ptr(L.ac_sr), _lib.ptr(D.pt_val), _lib.ptr(D.ap_val), _lib.ptr(out)),
                        "cb_amg_spgemm_terms(PtAP)")
+            if rep:  # every rank contributes its rows of the replicated operator
+                nxt.val.zero_()
+                nxt.val.view(-1, bs * bs)[nxtL.rep_pos] = out.view(-1, bs * bs)
+                nxtL.rep_dist.allreduce(nxt.val, "sum")
             val = nxt.val
         self._struct = None
 
@@ -367,6 +421,9 @@ class AMGHierarchy:
             if L.dist is not None:
                 e.dist = L.dist.handle
                 e.sendbuf = D.sendbuf.data_ptr()
+            if L.rep_dist is not None:
+                e.rep_dist = L.rep_dist.handle
+                e.rep_off = L.rep_off
         h = _lib.cb_amg()
         h.nlevels = len(self.levels)
         h.smooth_degree, h.coarse_degree = self.smooth_degree, self.coarse_degree

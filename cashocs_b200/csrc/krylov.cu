@@ -565,13 +565,25 @@ struct Solver {
       }
       if (int e = amg_smooth(lev, bl, xl, h->smooth_degree, h->smooth_ratio, true)) return e;
       if (int e = level_spmv(lev, xl)) return e;
-      if (int e = amg_restrict(s, bs, &lev, bl, lev.t, h->levels[l + 1].b, &st->done)) return e;
+      const cb_amg_level& nxt = h->levels[l + 1];
+      if (nxt.rep_dist) {
+        // agglomeration: the next level is replicated on every rank; this rank contributes its
+        // rows of the restricted residual, one all-reduce assembles the global vector everywhere
+        const size_t len = sizeof(double) * (size_t)(nxt.A.nrows * bs);
+        CB_CUDA_CHECK(cudaMemsetAsync(nxt.b, 0, len, s));
+        if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.b + nxt.rep_off * bs, &st->done)) return e;
+        if (int e = dist_allreduce_sum(s, nxt.rep_dist, nxt.b, (int)(nxt.A.nrows * bs))) return e;
+      } else {
+        if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.b, &st->done)) return e;
+      }
     }
     for (int l = L - 2; l >= 0; --l) {
       const cb_amg_level& lev = h->levels[l];
+      const cb_amg_level& nxt = h->levels[l + 1];
       const double* bl = (l == 0) ? r : lev.b;
       double* xl = (l == 0) ? z : lev.x;
-      if (int e = amg_prolong(s, bs, &lev, h->levels[l + 1].x, xl, &st->done)) return e;
+      const double* xc = nxt.rep_dist ? nxt.x + nxt.rep_off * bs : nxt.x;
+      if (int e = amg_prolong(s, bs, &lev, xc, xl, &st->done)) return e;
       if (int e = amg_smooth(lev, bl, xl, h->smooth_degree, h->smooth_ratio, false)) return e;
     }
     return CB_OK;

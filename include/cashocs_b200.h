@@ -209,6 +209,10 @@ typedef struct {
   double* d;                /* [A.nrows*bs] Chebyshev direction */
   cb_dist* dist;            /* halo plan of this level (NULL on one GPU) */
   double* sendbuf;          /* [send count * bs] pack buffer of this level's halo exchange */
+  cb_dist* rep_dist;        /* non-NULL: first *replicated* level of a distributed hierarchy -- A is the
+                             * global operator on every rank, b is all-reduced (sum) over this
+                             * communicator after the restriction wrote this rank's rows */
+  int64_t rep_off;          /* first node of this rank's rows inside the replicated level */
 } cb_amg_level;
 typedef struct {
   int32_t nlevels;

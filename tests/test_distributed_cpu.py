@@ -86,3 +86,125 @@ def test_partition_and_halo_world2(kind):
     results = mgr.dict()
     mp.spawn(_worker, args=(world, port, kind, results), nprocs=world, join=True)
     assert dict(results) == {0: "ok", 1: "ok"}, dict(results)
+
+
+# ----------------------------------------------------------------------------- distributed AMG (symbolic phase)
+def _terms(seg, sl, sr, lhs, rhs):
+    """numpy twin of cb_amg_spgemm_terms for bs = 1."""
+    seg, sl, sr = seg.numpy(), sl.numpy().astype(np.int64), sr.numpy().astype(np.int64)
+    prod = lhs[sl] * rhs[sr]
+    ids = np.repeat(np.arange(seg.size - 1), np.diff(seg))
+    return np.bincount(ids, weights=prod, minlength=seg.size - 1)
+
+
+def _amg_worker(rank, world, port, agglomerate, results):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scipy.sparse as sp
+
+        from cashocs_b200 import distributed
+        from cashocs_b200._utils import amg
+        from oracle import fem
+
+        dist = distributed.DistContext(rank, world, transport="torch")
+        lm = distributed.distributed_regular_mesh(10, dist, device="cpu")
+        n, ncols = lm.n_owned_vertices, lm.num_vertices
+        _, lvol, lG = fem.cell_geometry(lm.coords.numpy(), lm.cells.numpy())
+        Aloc = fem.assemble_matrix(fem.stiffness_elements(lvol, lG) + fem.mass_elements(lvol, 3), lm.cells.numpy(), ncols).tocsr()[:n]
+        Aloc.sort_indices()
+        amg.AMGSymbolic.AGGLOMERATE = agglomerate
+        sym = amg.AMGSymbolic(torch.from_numpy(Aloc.indptr.astype(np.int64)), torch.from_numpy(Aloc.indices.astype(np.int32)),
+                              n, ncols, dist=dist)
+        levels = sym.levels
+        assert len(levels) >= 3
+        kinds = ["rep" if L.rep_dist is not None else ("dist" if L.dist is not None else "local") for L in levels]
+        assert kinds[0] == "dist" and "rep" in kinds and kinds.index("rep") == (1 if agglomerate >= 1331 else 2)
+        assert all(k == "local" for k in kinds[kinds.index("rep") + 1:])
+        rng = np.random.RandomState(5)
+        val = Aloc.data.copy()
+        gid = lm.global_vertex_ids.numpy()
+        nglob = 11**3
+        for li, L in enumerate(levels[:-1]):
+            nxt = levels[li + 1]
+            # prolongator values: tentative on interface + ghost rows, arbitrary on interior rows
+            prp = L.p_rowptr.numpy()
+            pval = np.ones(L.p_col.numel())
+            if L.dist is not None:
+                interior = np.repeat(L.iface.numpy() == 0, np.diff(prp[: L.n + 1]))
+                pval[: L.nnzp_owned][interior] = rng.rand(int(interior.sum())) + 0.1
+            else:
+                pval[:] = rng.rand(pval.size) + 0.1
+            ap = _terms(L.ap_seg, L.ap_sl, L.ap_sr, val, pval)
+            ptval = pval[: L.nnzp_owned][L.pt_perm.numpy()]
+            ac = _terms(L.ac_seg, L.ac_sl, L.ac_sr, ptval, ap)
+            # global ids of the coarse nodes
+            if L.dist is not None:
+                counts = [None] * world
+                td.all_gather_object(counts, L.nc)
+                off = int(np.sum(counts[:rank]))
+                ncg = int(np.sum(counts))
+                if nxt.rep_dist is not None:
+                    assert off == nxt.rep_off and nxt.n == ncg
+                    cg = np.arange(off, off + L.nc)  # P of owned rows only references owned coarse nodes
+                    glob = torch.zeros(nxt.nnzb, dtype=torch.float64)
+                    glob[nxt.rep_pos] = torch.from_numpy(ac)
+                    dist.allreduce(glob, "sum")
+                    ac_next = glob.numpy()
+                else:
+                    v = torch.zeros(nxt.ncols, dtype=torch.float64)
+                    v[: nxt.n] = torch.arange(off, off + nxt.n, dtype=torch.float64)
+                    nxt.dist.halo_exchange(v, 1)
+                    cg = v.numpy().round().astype(np.int64)
+                    ac_next = ac
+                rows = np.repeat(np.arange(L.n), np.diff(L.rowptr.numpy()))
+                trip_a = (gid[rows], gid[L.col.numpy()], val)
+                prow = np.repeat(np.arange(L.n), np.diff(prp[: L.n + 1]))
+                assert L.p_col.numpy()[: L.nnzp_owned].max() < L.nc
+                trip_p = (gid[prow], cg[L.p_col.numpy()[: L.nnzp_owned]], pval[: L.nnzp_owned])
+                alla, allp = [None] * world, [None] * world
+                td.all_gather_object(alla, trip_a)
+                td.all_gather_object(allp, trip_p)
+                cat = lambda ts, k: np.concatenate([t[k] for t in ts])
+                Ag = sp.coo_matrix((cat(alla, 2), (cat(alla, 0), cat(alla, 1))), shape=(nglob, nglob)).tocsr()
+                Pg = sp.coo_matrix((cat(allp, 2), (cat(allp, 0), cat(allp, 1))), shape=(nglob, ncg)).tocsr()
+                ref = (Pg.T @ Ag @ Pg).tocsr()
+                if nxt.rep_dist is not None:
+                    got = sp.csr_matrix((ac_next, nxt.col.numpy(), nxt.rowptr.numpy()), shape=(ncg, ncg))
+                else:
+                    r2 = np.repeat(np.arange(nxt.n), np.diff(nxt.rowptr.numpy()))
+                    allc = [None] * world
+                    td.all_gather_object(allc, (cg[r2], cg[nxt.col.numpy()], ac_next))
+                    got = sp.coo_matrix((cat(allc, 2), (cat(allc, 0), cat(allc, 1))), shape=(ncg, ncg)).tocsr()
+                assert abs(got - ref).max() < 1e-13 * abs(ref).max()
+                assert abs(got - got.T).max() < 1e-13 * abs(ref).max()
+                gid, nglob = cg, ncg
+            else:
+                Al = sp.csr_matrix((val, L.col.numpy(), L.rowptr.numpy()), shape=(L.n, L.n))
+                Pl = sp.csr_matrix((pval, L.p_col.numpy(), prp), shape=(L.n, L.nc))
+                ref = (Pl.T @ Al @ Pl).tocsr()
+                got = sp.csr_matrix((ac, nxt.col.numpy(), nxt.rowptr.numpy()), shape=(L.nc, L.nc))
+                assert abs(got - ref).max() < 1e-13 * abs(ref).max()
+                ac_next = ac
+            val = ac_next
+        results[rank] = "ok"
+    except Exception as exc:  # pragma: no cover
+        import traceback
+
+        results[rank] = traceback.format_exc() + str(exc)
+    finally:
+        td.destroy_process_group()
+
+
+@pytest.mark.parametrize("agglomerate", [100, 20000])
+def test_distributed_amg_hierarchy_world2(agglomerate):
+    """Rank-local aggregates + tentative interface rows + replicated coarse tail give the exact
+    global Galerkin operators P^T A P (symmetric) on every level."""
+    world = 2
+    port = 31500 + (os.getpid() % 2000) + (0 if agglomerate == 100 else 1)
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_amg_worker, args=(world, port, agglomerate, results), nprocs=world, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}, dict(results)
