@@ -319,9 +319,9 @@ def main() -> None:
         roofline = {"bound": "hbm", "kernel": "k_cg_spmv<3> (elasticity PCG: w = A p, fused p.w)", "achieved": achieved,
                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "avg_launch_ms": avg_ms, "launches_profiled": spmv_prof, "algorithmic_bytes_per_launch": alg_bytes,
-                    # fine-level launches per PCG iteration: 1 (w = A p) + 2*degree inside the AMG V-cycle
+                    # fine-level launches per PCG iteration: 1 (w = A p) + 2 inside the AMG V(1,1)-cycle
                     "spmv_share_of_step": (avg_ms * sum(i[2] for i in its) *
-                                           (5 if args.pc == "hypre" else 1)) / ms}
+                                           (3 if args.pc == "hypre" else 1)) / ms}
 
     if rank == 0:
         line = {

@@ -51,6 +51,12 @@ class cb_mesh_view(C.Structure):
         ("nv", C.c_int64),
         ("nrows_owned", C.c_int64),
         ("nnz", C.c_int64),
+        ("cells_orig", C.c_void_p),
+        ("n2c_ptr", C.c_void_p),
+        ("n2c_idx", C.c_void_p),
+        ("v2c_ptr", C.c_void_p),
+        ("v2c_idx", C.c_void_p),
+        ("cell_scratch", C.c_void_p),
     ]
 
 

@@ -35,9 +35,15 @@ def _rowptr_from_rows(rows: torch.Tensor, n: int) -> torch.Tensor:
     return rp
 
 
-def mis_aggregate(rows: torch.Tensor, cols: torch.Tensor, n: int):
-    """MIS(1) aggregation: roots form a maximal independent set, every other node joins its
-    highest-priority adjacent root.  Returns (agg [n] int32, number of aggregates)."""
+def mis_aggregate(rows: torch.Tensor, cols: torch.Tensor, n: int, distance: int = 2):
+    """MIS(k) aggregation on the matrix graph (k = ``distance``).
+
+    Roots form a maximal independent set of the k-th power of the graph (hashed integer priorities
+    -> deterministic).  k = 2 is the classical smoothed-aggregation choice: roots are >= 3 edges
+    apart, so the root neighbourhoods are disjoint aggregates of diameter 2; nodes at distance 2
+    from every root join the aggregate of their highest-priority already-aggregated neighbour.
+    k = 1 gives small aggregates (root + part of its neighbourhood).
+    Returns (agg [n] int32, number of aggregates)."""
     dev = rows.device
     off = rows != cols
     r, c = rows[off], cols[off]
@@ -47,23 +53,36 @@ def mis_aggregate(rows: torch.Tensor, cols: torch.Tensor, n: int):
     prio = h * n + idx  # unique, < 2^31 * n
     state = torch.zeros(n, dtype=torch.int8, device=dev)  # 0 undecided, 1 root, 2 covered
     neg = torch.full((n,), -1, dtype=torch.int64, device=dev)
-    for _ in range(200):
+
+    def nbmax(v):  # max over the closed neighbourhood
+        return v.clone().scatter_reduce_(0, r, v[c], "amax", include_self=True)
+
+    for _ in range(400):
         und = state == 0
         if not bool(und.any()):
             break
         p = torch.where(und, prio, neg)
-        nbmax = neg.clone().scatter_reduce_(0, r, p[c], "amax", include_self=True)
-        newroot = und & (p > nbmax)
+        m = p
+        for _k in range(distance):
+            m = nbmax(m)
+        newroot = und & (p == m)
         state[newroot] = 1
-        cov = torch.zeros(n, dtype=torch.int8, device=dev).scatter_reduce_(0, r, newroot[c].to(torch.int8), "amax")
+        cov = newroot.to(torch.int64)
+        for _k in range(distance):
+            cov = nbmax(cov)
         state[(state == 0) & (cov > 0)] = 2
     is_root = state == 1
     nc = int(is_root.sum().item())
     agg = torch.full((n,), -1, dtype=torch.int64, device=dev)
     agg[is_root] = torch.arange(nc, device=dev)
-    best = neg.clone().scatter_reduce_(0, r, torch.where(is_root[c], prio[c], neg[c]), "amax", include_self=True)
-    nonroot = ~is_root
-    agg[nonroot] = agg[(best % n)[nonroot]]
+    for _k in range(distance):
+        # unassigned nodes join the aggregate of their highest-priority assigned neighbour
+        assigned = agg >= 0
+        best = neg.clone().scatter_reduce_(0, r, torch.where(assigned[c], prio[c], neg[c]), "amax", include_self=True)
+        join = (~assigned) & (best >= 0)
+        agg[join] = agg[(best % n)[join]]
+    if bool((agg < 0).any()):
+        raise RuntimeError("aggregation left unassigned nodes")
     return agg.to(torch.int32), nc
 
 
@@ -122,6 +141,7 @@ class AMGSymbolic:
 
     MAX_DENSE = 256  # scalar rows of a coarsest level that is inverted densely (bs <= 3 -> <= 85 nodes)
     AGGLOMERATE = 20000  # global node count below which a distributed level is replicated on every rank
+    DISTANCE = 2  # MIS(k) aggregation (see mis_aggregate)
 
     def __init__(self, rowptr, col, n, ncols, dist=None, max_levels: int = 12) -> None:
         self.levels: list[_Level] = []
@@ -147,7 +167,7 @@ class AMGSymbolic:
                 break
             rows = _rows_of(rowptr)
             local = col < n
-            agg, nc = mis_aggregate(rows[local], col[local].long(), n)
+            agg, nc = mis_aggregate(rows[local], col[local].long(), n, self.DISTANCE)
             nc_glob = nc if dist is None else int(round(dist.allreduce_scalar(float(nc), "sum")))
             if nc_glob >= 0.8 * n_glob or nc_glob < 1:
                 break
@@ -243,8 +263,8 @@ class AMGSymbolic:
 class AMGHierarchy:
     """Values of the hierarchy for one block size; ``numeric(A)`` refreshes them for new matrix values."""
 
-    def __init__(self, A, symbolic: AMGSymbolic | None = None, smooth_degree: int = 2, coarse_degree: int = 16,
-                 smooth_ratio: float = 4.0, coarse_ratio: float = 40.0) -> None:
+    def __init__(self, A, symbolic: AMGSymbolic | None = None, smooth_degree: int = 1, coarse_degree: int = 16,
+                 smooth_ratio: float = 10.0, coarse_ratio: float = 40.0) -> None:
         self.bs = bs = A.bs
         self.device = dev = A.val.device
         self.smooth_degree, self.coarse_degree = int(smooth_degree), int(coarse_degree)

@@ -134,6 +134,11 @@ def row_split_hint(nnzb: int, nrows: int) -> int:
     return 1 if avg <= 24 else (2 if avg <= 48 else (4 if avg <= 96 else 8))
 
 
+# matrices are assembled by the nnz-centric gather kernels; False selects the coloured cell-scatter
+# kernels (kept for meshes whose scatter map exceeds int32 and as a cross-check in the tests)
+USE_GATHER_ASSEMBLY = True
+
+
 class Matrix:
     """Block-CSR matrix in HBM sharing the mesh's P1 pattern (``bs`` = 1 scalar, ``dim`` vector)."""
 
@@ -251,7 +256,7 @@ def assemble_scalar_system(
     ``ident_zeros``.
     """
     lib = _lib.load()
-    view = mesh.view()
+    view = mesh.view(gather=USE_GATHER_ASSEMBLY)
     if matrix and A is None:
         A = Matrix(mesh, 1)
     if rhs and b is None:
@@ -285,12 +290,12 @@ def assemble_elasticity_matrix(mesh, mu: torch.Tensor, lambda_lame: float, dampi
                                A: Matrix | None = None) -> Matrix:
     """Elasticity Riesz scalar product (``cashocs/_forms/shape_form_handler.py:655-685,737-738``)."""
     lib = _lib.load()
-    view = mesh.view()
+    view = mesh.view(gather=USE_GATHER_ASSEMBLY)
     if A is None:
         A = Matrix(mesh, mesh.dim)
     _lib.require_cuda(mu, bc_flag, cell_scale)
-    if cell_scale is not None:
-        cell_scale = cell_scale[mesh.colour_perm].contiguous()
+    if cell_scale is not None and not view.n2c_ptr:
+        cell_scale = cell_scale[mesh.colour_perm].contiguous()  # the scatter kernels walk colour-sorted cells
     _lib.check(
         lib.cb_assemble_elasticity(_lib.stream_ptr(), C.byref(view), _lib.ptr(mu), float(lambda_lame),
                                    float(damping), _lib.ptr(cell_scale), _lib.ptr(bc_flag), _lib.ptr(A.val)),
@@ -307,7 +312,7 @@ def assemble_shape_derivative(mesh, u: torch.Tensor, p: torch.Tensor, f_poly: ex
                               b: torch.Tensor | None = None) -> torch.Tensor:
     """Shape-derivative vector of the Poisson Lagrangian (``shape_gradient_problem.py:142-144``)."""
     lib = _lib.load()
-    view = mesh.view()
+    view = mesh.view(gather=USE_GATHER_ASSEMBLY)
     d = mesh.dim
     if b is None:
         b = torch.empty(mesh.n_owned_vertices * d, dtype=torch.float64, device=mesh.device)
@@ -361,9 +366,9 @@ class LinearSolver:
                 sym = amg.AMGSymbolic(A.rowptr, A.col, A.nrows, A.ncols, dist=A.mesh.dist)
                 cls._amg_cache[skey] = sym
             h = amg.AMGHierarchy(
-                A, sym, smooth_degree=int(options.get("pc_amg_smooth_degree", 2)),
+                A, sym, smooth_degree=int(options.get("pc_amg_smooth_degree", 1)),
                 coarse_degree=int(options.get("pc_amg_coarse_degree", 16)),
-                smooth_ratio=float(options.get("pc_amg_smooth_ratio", 4.0)),
+                smooth_ratio=float(options.get("pc_amg_smooth_ratio", 10.0)),
                 coarse_ratio=float(options.get("pc_amg_coarse_ratio", 40.0)))
             cls._amg_cache[key] = h
         if h.version != (id(A), A.version):

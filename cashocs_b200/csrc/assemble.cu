@@ -35,7 +35,7 @@ k_assemble_scalar(int64_t c_begin, int64_t c_end, const int32_t* __restrict__ ce
                   int64_t nrows_owned, double c_stiff, double c_mass, double s_poly, cb_poly f,
                   cb_quad q, double s_nodal, const double* __restrict__ fnodal,
                   const uint8_t* __restrict__ bc_flag, const double* __restrict__ bc_val,
-                  double* __restrict__ val, double* __restrict__ rhs) {
+                  double* __restrict__ val, double* __restrict__ rhs, double* __restrict__ cell_out) {
   constexpr int K = D + 1;
   constexpr double MREF = 1.0 / ((D + 1) * (D + 2));
   for (int64_t c = c_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < c_end;
@@ -116,12 +116,43 @@ k_assemble_scalar(int64_t c_begin, int64_t c_end, const int32_t* __restrict__ ce
         }
       }
     }
-    if (rhs) {
+    if (cell_out) {  // gather path: local vector to scratch, summed per vertex by k_gather_cell_vectors
+#pragma unroll
+      for (int a = 0; a < K; ++a) cell_out[c * K + a] = be[a];
+    } else if (rhs) {
 #pragma unroll
       for (int a = 0; a < K; ++a) {
         if (cd.v[a] < nrows_owned) rhs[cd.v[a]] += be[a];
       }
     }
+  }
+}
+
+// out[v, :] = sum over the cells c of vertex v (ascending c) of cell_vec[c, local index of v, :]
+template <int D, int NC>
+__global__ void __launch_bounds__(256)
+k_gather_cell_vectors(int64_t nrows, const int64_t* __restrict__ v2c_ptr, const int32_t* __restrict__ v2c_idx,
+                      const int32_t* __restrict__ cells, const double* __restrict__ cell_vec,
+                      double* __restrict__ out) {
+  constexpr int K = D + 1;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nrows;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    double acc[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) acc[i] = 0.0;
+    for (int64_t k = v2c_ptr[v]; k < v2c_ptr[v + 1]; ++k) {
+      const int64_t c = v2c_idx[k];
+      int cv[K];
+      load_cell<D>(cells, c, cv);
+      int a = 0;
+#pragma unroll
+      for (int j = 1; j < K; ++j) a = (cv[j] == (int)v) ? j : a;
+      const double* src = cell_vec + (c * K + a) * NC;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) acc[i] += src[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) out[v * NC + i] = acc[i];
   }
 }
 
@@ -198,6 +229,135 @@ k_assemble_elasticity(int64_t c_begin, int64_t c_end, const int32_t* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ gather (nnz-centric) matrix assembly
+// One thread per block-nnz entry q = (row vertex, column vertex): it visits the cells sharing that
+// edge (n2c list, ascending cell id, ~6 cells in a Kuhn mesh), recomputes the cheap cell geometry
+// (cells of neighbouring entries coincide -> L1/L2 hits) and writes the finished d x d block once.
+// No colours, no read-modify-write, one launch; fixed summation order -> bit-reproducible.
+template <int D>
+__device__ __forceinline__ void entry_cell(const int32_t* __restrict__ cells, const double* __restrict__ coords,
+                                           int32_t t, CellData<D>& cd, int& a, int& b, int64_t& c) {
+  constexpr int K = D + 1;
+  constexpr int KK = K * K;
+  c = t / KK;
+  const int ab = t - (int32_t)c * KK;
+  a = ab / K;
+  b = ab - a * K;
+  load_cell_data<D>(cells, coords, c, cd);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_assemble_elasticity_gather(int64_t nnz, const int64_t* __restrict__ n2c_ptr, const int32_t* __restrict__ n2c_idx,
+                             const int32_t* __restrict__ cells, const double* __restrict__ coords,
+                             const double* __restrict__ mu, double lambda_lame, double damping,
+                             const double* __restrict__ cell_scale, const uint8_t* __restrict__ bc_flag,
+                             double* __restrict__ val) {
+  constexpr int K = D + 1;
+  constexpr double MREF = 1.0 / ((D + 1) * (D + 2));
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    double acc[D * D];
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) acc[i] = 0.0;
+    const int64_t kb = n2c_ptr[q], ke = n2c_ptr[q + 1];
+    for (int64_t k = kb; k < ke; ++k) {
+      CellData<D> cd;
+      int a, b;
+      int64_t c;
+      entry_cell<D>(cells, coords, __ldg(n2c_idx + k), cd, a, b, c);
+      double mubar = 0.0;
+#pragma unroll
+      for (int v = 0; v < K; ++v) mubar += mu[cd.v[v]];
+      mubar *= (1.0 / K);
+      const double scale = cell_scale ? cell_scale[c] : 1.0;
+      const double vol = cd.g.vol;
+      const double vm = scale * vol * mubar, vl = scale * vol * lambda_lame, dm = scale * damping * vol * MREF;
+      double Ga[D], Gb[D];
+      int va = 0, vb = 0;
+#pragma unroll
+      for (int v = 0; v < K; ++v) {
+        if (v == a) {
+          va = cd.v[v];
+#pragma unroll
+          for (int i = 0; i < D; ++i) Ga[i] = cd.g.G[v][i];
+        }
+        if (v == b) {
+          vb = cd.v[v];
+#pragma unroll
+          for (int i = 0; i < D; ++i) Gb[i] = cd.g.G[v][i];
+        }
+      }
+      unsigned bca = 0, bcb = 0;
+      if (bc_flag) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          if (bc_flag[(int64_t)va * D + i]) bca |= 1u << i;
+          if (bc_flag[(int64_t)vb * D + i]) bcb |= 1u << i;
+        }
+      }
+      double gg = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) gg += Ga[i] * Gb[i];
+      const double mass = (a == b) ? 2.0 * dm : dm;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          double e = vm * Ga[j] * Gb[i] + vl * Ga[i] * Gb[j];
+          if (i == j) e += vm * gg + mass;
+          if (((bca >> i) & 1u) || ((bcb >> j) & 1u)) e = (a == b && i == j) ? 1.0 : 0.0;
+          acc[i * D + j] += e;
+        }
+      }
+    }
+    double* blk = val + q * (D * D);
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) blk[i] = acc[i];
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_assemble_scalar_gather(int64_t nnz, const int64_t* __restrict__ n2c_ptr, const int32_t* __restrict__ n2c_idx,
+                         const int32_t* __restrict__ cells, const double* __restrict__ coords, double c_stiff,
+                         double c_mass, const uint8_t* __restrict__ bc_flag, double* __restrict__ val) {
+  constexpr int K = D + 1;
+  constexpr double MREF = 1.0 / ((D + 1) * (D + 2));
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    const int64_t kb = n2c_ptr[q], ke = n2c_ptr[q + 1];
+    for (int64_t k = kb; k < ke; ++k) {
+      CellData<D> cd;
+      int a, b;
+      int64_t c;
+      entry_cell<D>(cells, coords, __ldg(n2c_idx + k), cd, a, b, c);
+      double gg = 0.0;
+      int va = 0, vb = 0;
+#pragma unroll
+      for (int v = 0; v < K; ++v) {
+        if (v == a) va = cd.v[v];
+        if (v == b) vb = cd.v[v];
+      }
+#pragma unroll
+      for (int v = 0; v < K; ++v) {
+#pragma unroll
+        for (int w = 0; w < K; ++w) {
+          if (v == a && w == b) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) gg += cd.g.G[v][i] * cd.g.G[w][i];
+          }
+        }
+      }
+      double e = cd.g.vol * (c_stiff * gg + c_mass * (a == b ? 2.0 * MREF : MREF));
+      if (bc_flag && (bc_flag[va] || bc_flag[vb])) e = (a == b) ? 1.0 : 0.0;
+      acc += e;
+    }
+    val[q] = acc;
+  }
+}
+
 // ------------------------------------------------------------------ shape derivative (Poisson, J = c * int u)
 template <int D>
 __global__ void __launch_bounds__(128)
@@ -205,7 +365,8 @@ k_shape_derivative_poisson(int64_t c_begin, int64_t c_end, const int32_t* __rest
                            const double* __restrict__ coords, int64_t nrows_owned,
                            const double* __restrict__ u, const double* __restrict__ p, cb_poly f,
                            cb_poly gf0, cb_poly gf1, cb_poly gf2, cb_quad q, double c_int_u,
-                           const uint8_t* __restrict__ bc_flag, double* __restrict__ rhs) {
+                           const uint8_t* __restrict__ bc_flag, double* __restrict__ rhs,
+                           double* __restrict__ cell_out) {
   constexpr int K = D + 1;
   for (int64_t c = c_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < c_end;
        c += (int64_t)gridDim.x * blockDim.x) {
@@ -257,7 +418,7 @@ k_shape_derivative_poisson(int64_t c_begin, int64_t c_end, const int32_t* __rest
     const double s0 = c_int_u * vol * usum * (1.0 / K) + vol * gugp - vol * int_fp;
 #pragma unroll
     for (int a = 0; a < K; ++a) {
-      if (cd.v[a] >= nrows_owned) continue;
+      if (!cell_out && cd.v[a] >= nrows_owned) continue;
       double Ggu = 0.0, Ggp = 0.0;
 #pragma unroll
       for (int i = 0; i < D; ++i) { Ggu += cd.g.G[a][i] * gu[i]; Ggp += cd.g.G[a][i] * gp[i]; }
@@ -266,7 +427,8 @@ k_shape_derivative_poisson(int64_t c_begin, int64_t c_end, const int32_t* __rest
         double e = cd.g.G[a][i] * s0 - vol * (Ggu * gp[i] + Ggp * gu[i]) - vol * igf[a][i];
         const int64_t dof = (int64_t)cd.v[a] * D + i;
         if (bc_flag && bc_flag[dof]) e = 0.0;
-        rhs[dof] += e;
+        if (cell_out) cell_out[(c * K + a) * D + i] = e;
+        else rhs[dof] += e;
       }
     }
   }
@@ -328,23 +490,58 @@ extern "C" int cb_assemble_scalar(void* stream, const cb_mesh_view* m, double c_
   CB_REQUIRE(s_nodal == 0.0 || fnodal, "nodal source missing");
   CB_REQUIRE(bc_flag == nullptr || bc_val != nullptr, "bc_val missing");
   cudaStream_t s = as_stream(stream);
-  if (val) CB_CUDA_CHECK(cudaMemsetAsync(val, 0, sizeof(double) * m->nnz, s));
-  if (rhs) CB_CUDA_CHECK(cudaMemsetAsync(rhs, 0, sizeof(double) * m->nrows_owned, s));
+  if (val && m->n2c_ptr && m->n2c_idx && m->cells_orig) {
+    // matrix by gather (one launch); the rhs (with the BC lifting) keeps the coloured cell loop
+    const int grid = grid_for(m->nnz, 256, 8);
+    if (m->dim == 2)
+      k_assemble_scalar_gather<2><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->coords,
+                                                      c_stiff, c_mass, bc_flag, val);
+    else
+      k_assemble_scalar_gather<3><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->coords,
+                                                      c_stiff, c_mass, bc_flag, val);
+    CB_LAUNCH_CHECK();
+    val = nullptr;
+    if (!rhs) return CB_OK;
+  }
   cb_poly fz;
   memset(&fz, 0, sizeof(fz));
   cb_quad qz;
   memset(&qz, 0, sizeof(qz));
   const cb_poly& ff = f ? *f : fz;
   const cb_quad& qq = q ? *q : qz;
+  if (!val && rhs && m->cells_orig && m->v2c_ptr && m->v2c_idx && m->cell_scratch) {
+    // vector by gather: one launch over all cells (local vectors to scratch) + one per-vertex sum
+    const int64_t nc = m->colour_off[m->ncolours];
+    const int grid = grid_for(nc, 128, 12), vgrid = grid_for(m->nrows_owned, 256, 8);
+    if (m->dim == 2) {
+      k_assemble_scalar<2><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, nullptr, m->coords, m->nrows_owned, c_stiff,
+                                               c_mass, s_poly, ff, qq, s_nodal, fnodal, bc_flag, bc_val, nullptr,
+                                               rhs, m->cell_scratch);
+      CB_LAUNCH_CHECK();
+      k_gather_cell_vectors<2, 1><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
+                                                       m->cell_scratch, rhs);
+    } else {
+      k_assemble_scalar<3><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, nullptr, m->coords, m->nrows_owned, c_stiff,
+                                               c_mass, s_poly, ff, qq, s_nodal, fnodal, bc_flag, bc_val, nullptr,
+                                               rhs, m->cell_scratch);
+      CB_LAUNCH_CHECK();
+      k_gather_cell_vectors<3, 1><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
+                                                       m->cell_scratch, rhs);
+    }
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
+  if (val) CB_CUDA_CHECK(cudaMemsetAsync(val, 0, sizeof(double) * m->nnz, s));
+  if (rhs) CB_CUDA_CHECK(cudaMemsetAsync(rhs, 0, sizeof(double) * m->nrows_owned, s));
   return for_each_colour(m, [&](int64_t b, int64_t e, int grid) {
     if (m->dim == 2)
       k_assemble_scalar<2><<<grid, 128, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, m->nrows_owned,
                                                c_stiff, c_mass, s_poly, ff, qq, s_nodal, fnodal,
-                                               bc_flag, bc_val, val, rhs);
+                                               bc_flag, bc_val, val, rhs, nullptr);
     else
       k_assemble_scalar<3><<<grid, 128, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, m->nrows_owned,
                                                c_stiff, c_mass, s_poly, ff, qq, s_nodal, fnodal,
-                                               bc_flag, bc_val, val, rhs);
+                                               bc_flag, bc_val, val, rhs, nullptr);
   });
 }
 
@@ -354,6 +551,17 @@ extern "C" int cb_assemble_elasticity(void* stream, const cb_mesh_view* m, const
   if (int e = check_view(m)) return e;
   CB_REQUIRE(m->cell2nnz && mu && val, "cell2nnz / mu / val missing");
   cudaStream_t s = as_stream(stream);
+  if (m->n2c_ptr && m->n2c_idx && m->cells_orig) {
+    const int grid = grid_for(m->nnz, 256, 8);
+    if (m->dim == 2)
+      k_assemble_elasticity_gather<2><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->coords, mu,
+                                                          lambda_lame, damping, cell_scale, bc_flag, val);
+    else
+      k_assemble_elasticity_gather<3><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->coords, mu,
+                                                          lambda_lame, damping, cell_scale, bc_flag, val);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
   CB_CUDA_CHECK(cudaMemsetAsync(val, 0, sizeof(double) * m->nnz * m->dim * m->dim, s));
   return for_each_colour(m, [&](int64_t b, int64_t e, int grid) {
     if (m->dim == 2)
@@ -373,18 +581,39 @@ extern "C" int cb_assemble_shape_derivative_poisson(void* stream, const cb_mesh_
   if (int e = check_view(m)) return e;
   CB_REQUIRE(u && p && f && gradf && q && rhs, "missing argument");
   cudaStream_t s = as_stream(stream);
-  CB_CUDA_CHECK(cudaMemsetAsync(rhs, 0, sizeof(double) * m->nrows_owned * m->dim, s));
   cb_poly gz;
   memset(&gz, 0, sizeof(gz));
+  if (m->cells_orig && m->v2c_ptr && m->v2c_idx && m->cell_scratch) {
+    const int64_t nc = m->colour_off[m->ncolours];
+    const int grid = grid_for(nc, 128, 12), vgrid = grid_for(m->nrows_owned, 256, 8);
+    if (m->dim == 2) {
+      k_shape_derivative_poisson<2><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, m->coords, m->nrows_owned, u, p, *f,
+                                                        gradf[0], gradf[1], gz, *q, c_int_u, bc_flag, rhs,
+                                                        m->cell_scratch);
+      CB_LAUNCH_CHECK();
+      k_gather_cell_vectors<2, 2><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
+                                                       m->cell_scratch, rhs);
+    } else {
+      k_shape_derivative_poisson<3><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, m->coords, m->nrows_owned, u, p, *f,
+                                                        gradf[0], gradf[1], gradf[2], *q, c_int_u, bc_flag, rhs,
+                                                        m->cell_scratch);
+      CB_LAUNCH_CHECK();
+      k_gather_cell_vectors<3, 3><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
+                                                       m->cell_scratch, rhs);
+    }
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
+  CB_CUDA_CHECK(cudaMemsetAsync(rhs, 0, sizeof(double) * m->nrows_owned * m->dim, s));
   return for_each_colour(m, [&](int64_t b, int64_t e, int grid) {
     if (m->dim == 2)
       k_shape_derivative_poisson<2><<<grid, 128, 0, s>>>(b, e, m->cells, m->coords, m->nrows_owned, u, p,
                                                         *f, gradf[0], gradf[1], gz, *q, c_int_u,
-                                                        bc_flag, rhs);
+                                                        bc_flag, rhs, nullptr);
     else
       k_shape_derivative_poisson<3><<<grid, 128, 0, s>>>(b, e, m->cells, m->coords, m->nrows_owned, u, p,
                                                         *f, gradf[0], gradf[1], gradf[2], *q, c_int_u,
-                                                        bc_flag, rhs);
+                                                        bc_flag, rhs, nullptr);
   });
 }
 

@@ -52,6 +52,7 @@ class Mesh:
         self.coords_old: torch.Tensor | None = None
         self._pattern_ready = False
         self.scratch = None
+        self.cell_scratch = None
 
     # ------------------------------------------------------------------ boundary data
     def boundary_vertices(self, markers) -> torch.Tensor:
@@ -118,12 +119,23 @@ class Mesh:
         self.colour_perm = torch.sort(colour, stable=True).indices  # cell ids grouped by colour
         self.ccells = self.cells[self.colour_perm].contiguous()
         self.cc2n = cell2nnz.view(nc, k * k)[self.colour_perm].contiguous()
+        # gather data (nnz -> contributing (cell, a, b), original cell order) for the matrix kernels
+        self.n2c_ptr = self.n2c_idx = None
+        if nc * k * k < 2**31:
+            valid = torch.nonzero(cell2nnz >= 0).reshape(-1)
+            pos = cell2nnz[valid].long()
+            order = torch.sort(pos, stable=True).indices
+            self.n2c_idx = valid[order].to(torch.int32).contiguous()
+            self.n2c_ptr = torch.zeros(self.nnz + 1, dtype=torch.int64, device=dev)
+            self.n2c_ptr[1:] = torch.cumsum(torch.bincount(pos, minlength=self.nnz), 0)
+            del valid, pos, order
         del cell2nnz
         torch.cuda.current_stream().synchronize()
         self._pattern_ready = True
 
-    def view(self) -> _lib.cb_mesh_view:
-        """The struct the assembly entry points take (keeps no ownership)."""
+    def view(self, gather: bool = True) -> _lib.cb_mesh_view:
+        """The struct the assembly entry points take (keeps no ownership).  ``gather=False`` leaves out
+        the nnz-centric data, which selects the coloured cell-scatter kernels for the matrices."""
         self.build_pattern()
         v = _lib.cb_mesh_view()
         v.dim = self.dim
@@ -135,6 +147,16 @@ class Mesh:
         v.nv = self.num_vertices
         v.nrows_owned = self.n_owned_vertices
         v.nnz = self.nnz
+        if self.n2c_ptr is not None and gather:
+            v.cells_orig = self.cells.data_ptr()
+            v.n2c_ptr = self.n2c_ptr.data_ptr()
+            v.n2c_idx = self.n2c_idx.data_ptr()
+            if self.cell_scratch is None:
+                k = self.dim + 1
+                self.cell_scratch = torch.empty(self.num_cells * k * self.dim, dtype=torch.float64, device=self.device)
+            v.v2c_ptr = self.v2c_ptr.data_ptr()
+            v.v2c_idx = self.v2c_idx.data_ptr()
+            v.cell_scratch = self.cell_scratch.data_ptr()
         return v
 
 

@@ -114,6 +114,19 @@ typedef struct {
   int64_t nv;                /* vertices incl. ghosts */
   int64_t nrows_owned;       /* owned vertices (rows assembled) */
   int64_t nnz;               /* block nnz */
+  /* gather (nnz-centric) assembly data, nullable: for every block-nnz entry q the list
+   * n2c_idx[n2c_ptr[q] .. n2c_ptr[q+1]) of contributions t = cell * (dim+1)^2 + a*(dim+1) + b in
+   * ascending t (cell ids of the ORIGINAL cell order `cells_orig`).  When present the matrix
+   * kernels run one thread per nnz entry: no colours, no read-modify-write, fixed summation order. */
+  const int32_t* cells_orig; /* [nc, dim+1] original order */
+  const int64_t* n2c_ptr;    /* [nnz+1] */
+  const int32_t* n2c_idx;    /* [sum of valid cell2nnz entries] */
+  /* gather assembly of vectors, nullable: the cell kernel stores each cell's local vector in
+   * cell_scratch ([nc * (dim+1) * dim] doubles, original cell order, one launch over all cells),
+   * then one thread per owned vertex sums its incident cells (v2c lists, ascending cell id). */
+  const int64_t* v2c_ptr;    /* [nv+1] */
+  const int32_t* v2c_idx;    /* [nc*(dim+1)] */
+  double* cell_scratch;
 } cb_mesh_view;
 
 /* Scalar P1:  A = c_stiff*K + c_mass*M ;  rhs = s_poly*int(f phi) + s_nodal*M fnodal.
@@ -126,7 +139,8 @@ int cb_assemble_scalar(void* stream, const cb_mesh_view* m, double c_stiff, doub
 
 /* Vector P1 elasticity Riesz scalar product (cashocs/_forms/shape_form_handler.py:655-685):
  * 2 mu eps(U):eps(W) + lambda div U div W + delta U.W, mu a P1 nodal field, optional per-cell
- * scaling 1/vol^gamma (cell_scale [nc] colour-sorted, nullable).  Block-CSR bs = dim.
+ * scaling 1/vol^gamma (cell_scale [nc], nullable; colour-sorted for the scatter path, original
+ * cell order when the view carries the gather data).  Block-CSR bs = dim.
  * bc_flag / bc_val are per vector dof [dim*nv] (vertex-blocked dof = dim*v + c). */
 int cb_assemble_elasticity(void* stream, const cb_mesh_view* m, const double* mu,
                            double lambda_lame, double damping, const double* cell_scale,

@@ -325,3 +325,28 @@ def test_translation_moves_and_reverts():
     W = torch.from_numpy(np.random.RandomState(300696).uniform(-1e3, 1e3, size=tuple(dm.coords.shape))).cuda()
     assert not handler.move_mesh(W.reshape(-1))
     assert torch.equal(dm.coords, before)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_gather_and_scatter_assembly_agree(kind):
+    """The nnz-centric gather kernels and the coloured cell-scatter kernels assemble the same
+    matrices (different summation order -> round-off only), including the per-cell scaling."""
+    dm = device_mesh(kind)
+    d = dm.dim
+    dm.build_pattern()
+    assert dm.n2c_ptr is not None and int(dm.n2c_ptr[-1]) == dm.n2c_idx.numel()
+    mu = torch.from_numpy(0.5 + np.random.RandomState(3).rand(dm.num_vertices)).cuda()
+    scale = torch.from_numpy(0.5 + np.random.RandomState(4).rand(dm.num_cells)).cuda()
+    flag_v, _ = forms.bc_flag_arrays(dm, [cb.DirichletBC(0.0, (1,)), cb.DirichletBC(0.0, (2,), 1)], d)
+    flag_s, val_s = forms.bc_flag_arrays(dm, [cb.DirichletBC(0.3, (1, 3))], 1)
+    out = {}
+    try:
+        for gather in (True, False):
+            linalg.USE_GATHER_ASSEMBLY = gather
+            E = linalg.assemble_elasticity_matrix(dm, mu, 1.4, 0.2, bc_flag=flag_v, cell_scale=scale)
+            A, b = linalg.assemble_scalar_system(dm, 1.3, 0.4, f_poly=demo_poly(d), bc_flag=flag_s, bc_val=val_s)
+            out[gather] = (E.val.clone(), A.val.clone(), b.clone())
+    finally:
+        linalg.USE_GATHER_ASSEMBLY = True
+    for x, y in zip(out[True], out[False]):
+        assert float((x - y).abs().max() / y.abs().max()) < 1e-13
