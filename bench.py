@@ -250,6 +250,7 @@ def main() -> None:
         dist = distributed.DistContext(rank, world)
 
     lib = _lib.load()
+    t_setup = time.perf_counter()
     sop = build_problem(args.n, dist)
     mesh = sop.mesh
     h = 1.0 / args.n
@@ -292,6 +293,7 @@ def main() -> None:
         return ms, lib.cb_launch_count() - l0, its_acc, spmv_ms, spmv_prof, out
 
     timed(max(args.warmup, 3), False)
+    setup_s = time.perf_counter() - t_setup  # mesh + pattern + symbolic AMG + warm-up steps
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -340,6 +342,8 @@ def main() -> None:
             "gpu_launches": int(launches),
             "roofline": roofline,
             "check": {"gradient_norm_squared": out[0], "move_accepted": bool(out[1]), "mesh_quality": out[2]},
+            "hbm_peak_gb_rank0": round(torch.cuda.max_memory_allocated() / 1e9, 2),
+            "setup_s": round(setup_s, 1),
         }
         if not args.no_cpu_baseline and args.gpus == 1:
             line["cpu_baseline"] = cpu_baseline(args.n)

@@ -23,16 +23,29 @@ from cashocs_b200._forms import expressions
 
 
 class Function:
-    """A P1 finite-element function: a device vector plus its value size (1 = scalar, d = vector)."""
+    """A finite-element function: a device vector plus its value size (1 = scalar, d = vector).
 
-    def __init__(self, mesh, value_size: int = 1, name: str = "f") -> None:
+    ``degree`` = 1 (P1, dof == vertex; the only choice for vector functions, the deformation space of
+    the reference is CG1) or 2 (scalar P2: vertex dofs then edge dofs, see ``function_space.P2Space``).
+    """
+
+    def __init__(self, mesh, value_size: int = 1, name: str = "f", degree: int = 1) -> None:
         self.mesh = mesh
         self.value_size = int(value_size)
         self.name = name
+        self.degree = int(degree)
+        if self.degree not in (1, 2):
+            raise _exceptions.InputError("cashocs_b200.Function", "degree", "CG degree must be 1 or 2")
+        if self.degree == 2 and self.value_size != 1:
+            raise _exceptions.InputError("cashocs_b200.Function", "degree", "P2 functions are scalar (states / adjoints)")
+        self.space = mesh.p2_space() if self.degree == 2 else None
+        n = self.space.ndofs if self.degree == 2 else mesh.num_vertices
         # ghost entries (distributed meshes) live at the tail
-        self.vector = torch.zeros(mesh.num_vertices * self.value_size, dtype=torch.float64, device=mesh.device)
+        self.vector = torch.zeros(n * self.value_size, dtype=torch.float64, device=mesh.device)
 
     def owned(self) -> torch.Tensor:
+        if self.degree == 2:
+            return self.vector
         return self.vector[: self.mesh.n_owned_vertices * self.value_size]
 
     def assign(self, other) -> None:
@@ -40,12 +53,15 @@ class Function:
         self.vector.copy_(src)
 
     def copy(self) -> "Function":
-        f = Function(self.mesh, self.value_size, self.name)
+        f = Function(self.mesh, self.value_size, self.name, self.degree)
         f.vector.copy_(self.vector)
         return f
 
     def interpolate(self, expr) -> None:
-        """Nodal interpolation of a polynomial / callable of the vertex coordinates."""
+        """Nodal interpolation of a polynomial / callable of the node coordinates."""
+        if self.degree == 2:
+            self.vector.copy_(self.space.interpolate(expr))
+            return
         x = self.mesh.coords
         if isinstance(expr, expressions.Polynomial):
             out = torch.zeros(x.shape[0], dtype=torch.float64, device=x.device)
@@ -83,14 +99,15 @@ def create_dirichlet_bcs(value: float, markers, component: int | None = None) ->
     return [DirichletBC(value, (int(m),), component) for m in markers]
 
 
-def bc_flag_arrays(mesh, bcs: list[DirichletBC], value_size: int):
-    """Flag / value arrays over all dofs of a P1 space; later BCs overwrite earlier ones."""
-    n = mesh.num_vertices * value_size
+def bc_flag_arrays(mesh, bcs: list[DirichletBC], value_size: int, space=None):
+    """Flag / value arrays over all dofs of a P1 space (or of the scalar P2 ``space``); later BCs
+    overwrite earlier ones."""
+    n = (space.ndofs if space is not None else mesh.num_vertices) * value_size
     flag = torch.zeros(n, dtype=torch.uint8, device=mesh.device)
     val = torch.zeros(n, dtype=torch.float64, device=mesh.device)
     any_bc = False
     for bc in bcs:
-        verts = mesh.boundary_vertices(bc.markers)
+        verts = space.boundary_dofs(bc.markers) if space is not None else mesh.boundary_vertices(bc.markers)
         if verts.numel() == 0:
             continue
         any_bc = True

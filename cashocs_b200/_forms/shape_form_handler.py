@@ -156,6 +156,13 @@ class ShapeFormHandler:
 
         f = src if src is not None else expressions.Polynomial()
         f = f * self.state_form.source_scale
+        if self.state.degree != self.adjoint.degree:
+            raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "adjoint",
+                                         "state and adjoint must use the same CG degree")
+        if self.state.degree == 2:
+            return linalg.assemble_p2_shape_derivative(
+                self.state.space, self.state.vector, self.adjoint.vector, f, self.cost.c_state,
+                bc_flag=self.bc_flag, b=self.fe_shape_derivative_vector)
         return linalg.assemble_shape_derivative(
             self.mesh, self.state.vector, self.adjoint.vector, f, self.cost.c_state, bc_flag=self.bc_flag,
             b=self.fe_shape_derivative_vector,

@@ -60,6 +60,28 @@ class cb_mesh_view(C.Structure):
     ]
 
 
+class cb_p2_view(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32),
+        ("ndof_e", C.c_int32),
+        ("nc", C.c_int64),
+        ("nv", C.c_int64),
+        ("ndofs", C.c_int64),
+        ("nnz", C.c_int64),
+        ("cells", C.c_void_p),
+        ("cell_dofs", C.c_void_p),
+        ("coords", C.c_void_p),
+        ("rowptr", C.c_void_p),
+        ("col", C.c_void_p),
+        ("d2c_ptr", C.c_void_p),
+        ("d2c_idx", C.c_void_p),
+        ("ref_R", C.c_void_p),
+        ("ref_M", C.c_void_p),
+        ("ref_I", C.c_void_p),
+        ("cell_scratch", C.c_void_p),
+    ]
+
+
 class cb_mat(C.Structure):
     _fields_ = [
         ("nrows", C.c_int64),
@@ -159,6 +181,12 @@ SIGNATURES = {
     "cb_assemble_shape_derivative_poisson": (I32, [P, C.POINTER(cb_mesh_view), P, P, C.POINTER(cb_poly),
                                                    C.POINTER(cb_poly), C.POINTER(cb_quad), DBL, P, P]),
     "cb_ident_zeros": (I32, [P, I64, I32, P, P, P, P]),
+    "cb_p2_assemble_matrix": (I32, [P, C.POINTER(cb_p2_view), DBL, DBL, P, P]),
+    "cb_p2_assemble_rhs": (I32, [P, C.POINTER(cb_p2_view), DBL, DBL, DBL, C.POINTER(cb_poly), I32, P, DBL, DBL, P,
+                                 P, P, P]),
+    "cb_p2_shape_derivative_poisson": (I32, [P, C.POINTER(cb_p2_view), P, P, P, P, C.POINTER(cb_poly),
+                                             C.POINTER(cb_poly), I32, P, DBL, P, P]),
+    "cb_p2_functional": (I32, [P, C.POINTER(cb_p2_view), DBL, P, DBL, P, P, P, I64]),
     "cb_spmv": (I32, [P, C.POINTER(cb_mat), P, P]),
     "cb_scalar_product": (I32, [P, C.POINTER(cb_mat), P, P, P, P, I64]),
     "cb_dot": (I32, [P, I64, P, P, P, P, I64]),

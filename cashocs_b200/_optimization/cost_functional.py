@@ -20,6 +20,17 @@ class ReducedCostFunctional:
     def _integral(self, u, c_u, c_track, ud) -> float:
         mesh = self.mesh
         scratch = mesh.reduce_scratch()
+        space = self.states[0].space
+        if space is not None:  # P2 state
+            import ctypes as C
+
+            view = space.view()
+            _lib.check(
+                _lib.load().cb_p2_functional(_lib.stream_ptr(), C.byref(view), float(c_u), _lib.ptr(u), float(c_track),
+                                             _lib.ptr(ud), _lib.ptr(self._out), _lib.ptr(scratch), scratch.numel()),
+                "cb_p2_functional",
+            )
+            return float(self._out.item())
         _lib.check(
             _lib.load().cb_functional(_lib.stream_ptr(), mesh.dim, mesh.n_owned_cells, _lib.ptr(mesh.coords),
                                       _lib.ptr(mesh.cells), float(c_u), _lib.ptr(u), float(c_track), _lib.ptr(ud),

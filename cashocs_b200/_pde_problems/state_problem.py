@@ -31,9 +31,12 @@ class StateProblem(pde_problem.PDEProblem):
         self.number_of_solves = 0
         self.iterations = [0] * len(states)
         # tensors preallocated once, like A_tensors / b_tensors (state_problem.py:101-108)
-        self.A_tensors = [linalg.Matrix(mesh, 1) for _ in states]
-        self.b_tensors = [torch.zeros(mesh.n_owned_vertices, dtype=torch.float64, device=mesh.device) for _ in states]
-        self.bc_arrays = [forms.bc_flag_arrays(mesh, bcs, 1) for bcs in bcs_list]
+        # P2 states (BASELINE configs[4]) live on mesh.p2_space(); P1 states on the mesh's vertex space
+        self.spaces = [y.space for y in states]
+        self.A_tensors = [linalg.Matrix(sp if sp is not None else mesh, 1) for sp in self.spaces]
+        self.b_tensors = [torch.zeros(sp.ndofs if sp is not None else mesh.n_owned_vertices, dtype=torch.float64,
+                                      device=mesh.device) for sp in self.spaces]
+        self.bc_arrays = [forms.bc_flag_arrays(mesh, bcs, 1, space=sp) for bcs, sp in zip(bcs_list, self.spaces)]
         self._checkpoint = None
 
     def _generate_checkpoint(self) -> None:
@@ -54,7 +57,13 @@ class StateProblem(pde_problem.PDEProblem):
         if isinstance(src, expressions.Polynomial):
             kw = dict(f_poly=src, f_poly_scale=form.source_scale)
         elif isinstance(src, forms.Function):
+            if src.degree != self.states[i].degree:
+                raise _exceptions.InputError("cashocs_b200.StateProblem", "source",
+                                             "a Function source must live in the state's space")
             kw = dict(f_nodal=src.vector, f_nodal_scale=form.source_scale)
+        if self.spaces[i] is not None:
+            return linalg.assemble_p2_system(self.spaces[i], form.kappa, form.reaction, bc_flag=flag, bc_val=val,
+                                             A=self.A_tensors[i], b=self.b_tensors[i], **kw)
         return linalg.assemble_scalar_system(
             self.mesh, form.kappa, form.reaction, bc_flag=flag, bc_val=val,
             A=self.A_tensors[i], b=self.b_tensors[i], **kw,

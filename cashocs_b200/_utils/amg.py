@@ -399,7 +399,10 @@ class AMGHierarchy:
             else:
                 sval = val
             ms = self._mat(L, sval, 1)
-            lmax_s = self._diag_inv(ms, D.s_dinv, L, L.n)
+            if bs == 1:  # the strength matrix is the level operator itself
+                D.s_dinv, lmax_s = D.dinv, D.lmax
+            else:
+                lmax_s = self._diag_inv(ms, D.s_dinv, L, L.n)
             omega = (4.0 / 3.0) / lmax_s
             _lib.check(lib.cb_amg_smooth_prolongator(s, C.byref(ms), omega, _lib.ptr(L.agg), _lib.ptr(L.iface),
                                                      _lib.ptr(L.p_rowptr), _lib.ptr(L.p_col), _lib.ptr(D.p_val)),

@@ -331,6 +331,67 @@ def assemble_shape_derivative(mesh, u: torch.Tensor, p: torch.Tensor, f_poly: ex
     return b
 
 
+def assemble_p2_system(space, c_stiff: float = 1.0, c_mass: float = 0.0, f_poly: expressions.Polynomial | None = None,
+                       f_poly_scale: float = 1.0, f_const: float = 0.0, f_nodal: torch.Tensor | None = None,
+                       f_nodal_scale: float = 1.0, bc_flag: torch.Tensor | None = None,
+                       bc_val: torch.Tensor | None = None, A: "Matrix | None" = None, b: torch.Tensor | None = None,
+                       matrix: bool = True, rhs: bool = True):
+    """Scalar P2 system ``(c_stiff K + c_mass M) x = s_p int f phi + f_const int phi + s_n M f_h`` with
+    symmetric BCs -- ``assemble_petsc_system`` (``cashocs/_utils/linalg.py:107-188``) for
+    ``FunctionSpace(mesh, "CG", 2)`` (BASELINE configs[4])."""
+    lib = _lib.load()
+    view = space.view()
+    if matrix and A is None:
+        A = Matrix(space, 1)
+    if rhs and b is None:
+        b = torch.empty(space.ndofs, dtype=torch.float64, device=space.device)
+    _lib.require_cuda(f_nodal, bc_flag, bc_val, b)
+    if matrix:
+        _lib.check(lib.cb_p2_assemble_matrix(_lib.stream_ptr(), C.byref(view), float(c_stiff), float(c_mass),
+                                             _lib.ptr(bc_flag), _lib.ptr(A.val)), "cb_p2_assemble_matrix")
+        _lib.check(lib.cb_ident_zeros(_lib.stream_ptr(), A.nrows, 1, _lib.ptr(A.rowptr), _lib.ptr(A.col),
+                                      _lib.ptr(A.val), None), "cb_ident_zeros")
+        A.touch()
+    if rhs:
+        poly, nq, qtab, s_poly = None, 0, None, 0.0
+        if f_poly is not None:
+            poly = f_poly.struct()
+            nq, qtab = space.qtab(f_poly.degree + 2)
+            s_poly = float(f_poly_scale)
+        s_nodal = float(f_nodal_scale) if f_nodal is not None else 0.0
+        _lib.check(
+            lib.cb_p2_assemble_rhs(_lib.stream_ptr(), C.byref(view), float(c_stiff), float(c_mass), s_poly,
+                                   C.byref(poly) if poly is not None else None, nq, _lib.ptr(qtab), float(f_const),
+                                   s_nodal, _lib.ptr(f_nodal), _lib.ptr(bc_flag), _lib.ptr(bc_val), _lib.ptr(b)),
+            "cb_p2_assemble_rhs")
+    return (A if matrix else None), (b if rhs else None)
+
+
+def assemble_p2_shape_derivative(space, u: torch.Tensor, p: torch.Tensor, f_poly: expressions.Polynomial,
+                                 c_int_u: float = 1.0, bc_flag: torch.Tensor | None = None,
+                                 b: torch.Tensor | None = None) -> torch.Tensor:
+    """Shape-derivative vector (vector-P1 test functions) for P2 state / adjoint."""
+    lib = _lib.load()
+    mesh = space.mesh
+    mesh.build_pattern()
+    d = mesh.dim
+    if b is None:
+        b = torch.empty(mesh.num_vertices * d, dtype=torch.float64, device=mesh.device)
+    _lib.require_cuda(u, p, bc_flag, b)
+    view = space.view()
+    f = f_poly.struct()
+    grads = (_lib.cb_poly * 3)()
+    for i in range(d):
+        grads[i] = f_poly.derivative(i).struct()
+    nq, qtab = space.qtab(f_poly.degree + 2)
+    _lib.check(
+        lib.cb_p2_shape_derivative_poisson(_lib.stream_ptr(), C.byref(view), _lib.ptr(mesh.v2c_ptr),
+                                           _lib.ptr(mesh.v2c_idx), _lib.ptr(u), _lib.ptr(p), C.byref(f), grads, nq,
+                                           _lib.ptr(qtab), float(c_int_u), _lib.ptr(bc_flag), _lib.ptr(b)),
+        "cb_p2_shape_derivative_poisson")
+    return b
+
+
 class KSPResult:
     def __init__(self, reason: int, its: int, rnorm: float, rnorm0: float, history=None, spmv_ms: float = 0.0,
                  spmv_profiled: int = 0, spmv_launches: int = 0) -> None:

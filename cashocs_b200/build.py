@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(HERE, "..", "include")
 LIB = os.path.join(HERE, "libcashocs_b200.so")
 
-SOURCES = ["api.cu", "pattern.cu", "assemble.cu", "spmv.cu", "krylov.cu", "amg.cu", "meshops.cu", "dist.cu"]
+SOURCES = ["api.cu", "pattern.cu", "assemble.cu", "spmv.cu", "krylov.cu", "amg.cu", "meshops.cu", "dist.cu", "p2.cu"]
 # meshops.cu feeds accept/reject thresholds: no FMA contraction (see the file header)
 EXTRA = {"meshops.cu": ["-fmad=false"]}
 COMMON = [

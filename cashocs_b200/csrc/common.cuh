@@ -224,4 +224,32 @@ __device__ __forceinline__ double poly_eval(const cb_poly& p, double x, double y
   return s;
 }
 
+// out[v, :] = sum over the cells c of vertex v (ascending c) of cell_vec[c, local index of v, :]
+template <int D, int NC>
+__global__ void __launch_bounds__(256)
+k_gather_cell_vectors(int64_t nrows, const int64_t* __restrict__ v2c_ptr, const int32_t* __restrict__ v2c_idx,
+                      const int32_t* __restrict__ cells, const double* __restrict__ cell_vec,
+                      double* __restrict__ out) {
+  constexpr int K = D + 1;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nrows;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    double acc[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) acc[i] = 0.0;
+    for (int64_t k = v2c_ptr[v]; k < v2c_ptr[v + 1]; ++k) {
+      const int64_t c = v2c_idx[k];
+      int cv[K];
+      load_cell<D>(cells, c, cv);
+      int a = 0;
+#pragma unroll
+      for (int j = 1; j < K; ++j) a = (cv[j] == (int)v) ? j : a;
+      const double* src = cell_vec + (c * K + a) * NC;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) acc[i] += src[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) out[v * NC + i] = acc[i];
+  }
+}
+
 }  // namespace cb

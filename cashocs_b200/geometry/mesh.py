@@ -53,6 +53,8 @@ class Mesh:
         self._pattern_ready = False
         self.scratch = None
         self.cell_scratch = None
+        self.boundary_facets: dict[int, torch.Tensor] | None = None  # tagged facets (imported meshes)
+        self._p2_space = None
 
     # ------------------------------------------------------------------ boundary data
     def boundary_vertices(self, markers) -> torch.Tensor:
@@ -67,6 +69,14 @@ class Mesh:
         if not parts:
             return torch.zeros(0, dtype=torch.int64, device=self.device)
         return torch.unique(torch.cat(parts))
+
+    def p2_space(self):
+        """The scalar P2 space on this mesh (built once per mesh topology)."""
+        if self._p2_space is None:
+            from cashocs_b200._forms import function_space
+
+            self._p2_space = function_space.P2Space(self)
+        return self._p2_space
 
     @property
     def boundary_markers(self) -> list[int]:
@@ -269,11 +279,14 @@ def mesh_from_arrays(coords, cells, facets, facet_tags, device="cuda") -> Mesh:
         bverts[int(tag)] = torch.from_numpy(
             np.unique(facets[facet_tags == tag].reshape(-1)).astype(np.int64)
         ).to(dev)
-    return Mesh(
+    m = Mesh(
         torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64)).to(dev),
         torch.from_numpy(np.ascontiguousarray(cells, dtype=np.int32)).to(dev),
         bverts,
     )
+    m.boundary_facets = {int(tag): torch.from_numpy(np.ascontiguousarray(facets[facet_tags == tag], dtype=np.int64)).to(dev)
+                         for tag in np.unique(facet_tags)}
+    return m
 
 
 def import_mesh(path: str, device="cuda") -> Mesh:

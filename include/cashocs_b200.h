@@ -161,6 +161,53 @@ int cb_assemble_shape_derivative_poisson(void* stream, const cb_mesh_view* m, co
 int cb_ident_zeros(void* stream, int64_t nrows, int bs, const int64_t* rowptr,
                    const int32_t* col, double* val, int64_t* n_fixed);
 
+/* ------------------------------------------------------------------ P2 (quadratic Lagrange) spaces
+ * State / adjoint spaces FunctionSpace(mesh, "CG", 2) of BASELINE configs[4]; the deformation space
+ * stays vector CG1 (cashocs/_optimization/shape_optimization/shape_optimization_problem.py:251-256).
+ * dofs: vertex v -> v, edge e -> nv + e; local order: the dim+1 vertices, then the edges
+ * (0,1),(0,2),(0,3),(1,2),(1,3),(2,3) (2-D: (0,1),(0,2),(1,2)).  The pattern (rowptr/col) and the
+ * dof->cell adjacency come from cb_pattern_* / cb_v2c_build with k = ndof_e.  Reference tensors of the
+ * affine element (relative to |K|), computed once by the host layer:
+ *   ref_R[a][b][k][l] = int d(phi_a)/d(lam_k) d(phi_b)/d(lam_l),  K_ab = |K| sum_kl ref_R G_k.G_l
+ *   ref_M[a][b] = int phi_a phi_b,  ref_I[a] = int phi_a. */
+typedef struct {
+  int32_t dim;               /* 2 or 3 */
+  int32_t ndof_e;            /* 6 or 10 */
+  int64_t nc, nv, ndofs, nnz;
+  const int32_t* cells;      /* [nc, dim+1] vertex ids, ascending per cell */
+  const int32_t* cell_dofs;  /* [nc, ndof_e] */
+  const double* coords;      /* [nv, dim] */
+  const int64_t* rowptr;     /* [ndofs+1] */
+  const int32_t* col;        /* [nnz] */
+  const int64_t* d2c_ptr;    /* [ndofs+1] dof -> cells (ascending) */
+  const int32_t* d2c_idx;    /* [nc*ndof_e] */
+  const double* ref_R;       /* [ndof_e, ndof_e, dim+1, dim+1] */
+  const double* ref_M;       /* [ndof_e, ndof_e] */
+  const double* ref_I;       /* [ndof_e] */
+  double* cell_scratch;      /* [nc * max(ndof_e, (dim+1)*dim)] local vectors of the cell kernels */
+} cb_p2_view;
+
+/* A = c_stiff*K + c_mass*M on the P2 space, symmetric Dirichlet elimination per element tensor
+ * (bc_flag [ndofs], nullable) -- assemble_petsc_system (cashocs/_utils/linalg.py:107-188). */
+int cb_p2_assemble_matrix(void* stream, const cb_p2_view* m, double c_stiff, double c_mass,
+                          const uint8_t* bc_flag, double* val);
+/* rhs = s_poly*int(f phi) + s_const*int(phi) + s_nodal*M fnodal, with the BC lifting of the matrix
+ * c_stiff*K + c_mass*M.  qtab [nq][dim+1 + 1 + ndof_e]: barycentric point, weight (sum 1), basis
+ * values; the rule must be exact for degree(f) + 2. */
+int cb_p2_assemble_rhs(void* stream, const cb_p2_view* m, double c_stiff, double c_mass, double s_poly,
+                       const cb_poly* f, int nq, const double* qtab, double s_const, double s_nodal,
+                       const double* fnodal, const uint8_t* bc_flag, const double* bc_val, double* rhs);
+/* Shape derivative of the Poisson Lagrangian (cb_assemble_shape_derivative_poisson) for P2 u, p and
+ * vector-P1 test functions; v2c_* = vertex->cell adjacency of the mesh; bc_flag per P1 vector dof;
+ * rhs [nv*dim]; the rule must be exact for degree(f) + 2. */
+int cb_p2_shape_derivative_poisson(void* stream, const cb_p2_view* m, const int64_t* v2c_ptr,
+                                   const int32_t* v2c_idx, const double* u, const double* p,
+                                   const cb_poly* f, const cb_poly* gradf, int nq, const double* qtab,
+                                   double c_int_u, const uint8_t* bc_flag, double* rhs);
+/* int (c_u*u + c_track/2 (u-ud)^2) dx for P2 u, ud (IntegralFunctional.evaluate). */
+int cb_p2_functional(void* stream, const cb_p2_view* m, double c_u, const double* u, double c_track,
+                     const double* ud, double* result_dev, double* scratch, int64_t scratch_len);
+
 /* ------------------------------------------------------------------ SpMV / BLAS-1 */
 typedef struct {
   int64_t nrows;          /* owned block rows */

@@ -28,6 +28,7 @@ import numpy as np
 
 from oracle import fem
 from oracle import krylov
+from oracle import p2
 from oracle import quality
 
 
@@ -96,8 +97,10 @@ class PoissonShapeProblem:
         adjoint_ksp=None,
         gradient_ksp=None,
         mu_ksp=None,
+        state_degree: int = 1,
     ):
         self.mesh = mesh
+        self.state_degree = int(state_degree)  # CG degree of the state / adjoint space (configs[4]: 2)
         self.coords = mesh.coords  # moved in place by move_mesh
         self.cells = mesh.cells
         self.d = mesh.dim
@@ -118,6 +121,12 @@ class PoissonShapeProblem:
         self.its = {}
         self.u = np.zeros(self.nv)
         self.p = np.zeros(self.nv)
+        if self.state_degree == 2:
+            self.p2_dofs, self.p2_edges = p2.cell_dofs(self.cells, self.nv)
+            self.n_state = self.nv + len(self.p2_edges)
+            self.state_bc = p2.boundary_dofs(mesh, bc_markers, self.p2_edges)
+            self.u = np.zeros(self.n_state)
+            self.p = np.zeros(self.n_state)
         self.mu = np.ones(self.nv)
         self.A_elas = None
         self.current_mesh_quality = quality.compute_mesh_quality(
@@ -142,9 +151,14 @@ class PoissonShapeProblem:
     # -- state / adjoint (a3, a4)
     def solve_state(self):
         _, vol, G = self._geom()
-        Ke = fem.stiffness_elements(vol, G)
-        be = fem.load_elements_callable(self.coords, self.cells, vol, self.f, self.f_degree + 1)
-        A, b = fem.assemble_system(Ke, be, self.cells, self.nv, self.state_bc, 0.0)
+        if self.state_degree == 2:
+            Ke = p2.stiffness_elements(vol, G)
+            be = p2.load_elements_callable(self.coords, self.cells, vol, self.f, self.f_degree)
+            A, b = fem.assemble_system(Ke, be, self.p2_dofs, self.n_state, self.state_bc, 0.0)
+        else:
+            Ke = fem.stiffness_elements(vol, G)
+            be = fem.load_elements_callable(self.coords, self.cells, vol, self.f, self.f_degree + 1)
+            A, b = fem.assemble_system(Ke, be, self.cells, self.nv, self.state_bc, 0.0)
         self.u, reason, its, _ = krylov.solve(A, b, self.state_ksp)
         self._check(reason)
         self.its["state"] = its
@@ -153,9 +167,14 @@ class PoissonShapeProblem:
 
     def solve_adjoint(self):
         _, vol, G = self._geom()
-        Ke = fem.stiffness_elements(vol, G)
-        be = -fem.load_elements_p1(vol, self.cells, np.ones(self.nv), self.d)  # -dJ/du[v] = -int v
-        A, b = fem.assemble_system(Ke, be, self.cells, self.nv, self.state_bc, 0.0)
+        if self.state_degree == 2:
+            Ke = p2.stiffness_elements(vol, G)
+            be = -vol[:, None] * p2.reference_tensors(self.d)[2][None, :]  # -dJ/du[v] = -int v
+            A, b = fem.assemble_system(Ke, be, self.p2_dofs, self.n_state, self.state_bc, 0.0)
+        else:
+            Ke = fem.stiffness_elements(vol, G)
+            be = -fem.load_elements_p1(vol, self.cells, np.ones(self.nv), self.d)  # -dJ/du[v] = -int v
+            A, b = fem.assemble_system(Ke, be, self.cells, self.nv, self.state_bc, 0.0)
         self.p, reason, its, _ = krylov.solve(A, b, self.adjoint_ksp)
         self._check(reason)
         self.its["adjoint"] = its
@@ -170,6 +189,8 @@ class PoissonShapeProblem:
     def cost(self):
         """``IntegralFunctional.evaluate`` (``cashocs/_optimization/cost_functional.py:160-168``)."""
         _, vol, _ = self._geom()
+        if self.state_degree == 2:
+            return p2.integral(self.u, self.p2_dofs, vol, self.d)
         return float(np.sum(vol * self.u[self.cells].mean(axis=1)))
 
     # -- Lame mu (a5)
@@ -213,6 +234,9 @@ class PoissonShapeProblem:
     # -- shape derivative (a7)
     def shape_derivative_elements(self):
         d = self.d
+        if self.state_degree == 2:
+            return p2.shape_derivative_poisson(self.coords, self.cells, self.p2_dofs, self.u, self.p, self.f,
+                                               self.grad_f, self.f_degree)
         _, vol, G = self._geom()
         ue, pe = self.u[self.cells], self.p[self.cells]
         gu = np.einsum("ca,cai->ci", ue, G)

@@ -205,3 +205,47 @@ def test_collisions_equal_valence_on_valid_meshes():
     for m in (meshes.regular_mesh(5), meshes.regular_mesh(3, 1.0, 1.0, 1.0), meshes.load_npz(os.path.join(GOLDEN, "mesh2d.npz"))):
         assert np.array_equal(quality.compute_collisions(m.coords, m.cells), quality.vertex_valence(m.cells, m.num_vertices))
         assert quality.intersection_test(m.coords, m.cells)
+
+
+# ----------------------------------------------------------------------------- P2 states (BASELINE configs[4])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_p2_patch_test_and_reference_tensors(dim):
+    """Quadratics are reproduced exactly by the P2 stiffness / load tensors; the reference mass matrix
+    integrates 1; edge counts follow the closed formula of SURVEY.md 9.1."""
+    from oracle import p2
+
+    om = meshes.regular_mesh(4) if dim == 2 else meshes.regular_mesh(3, 1.0, 1.0, 1.0)
+    nv = om.num_vertices
+    dofs, edges = p2.cell_dofs(om.cells, nv)
+    if dim == 3:
+        n = 3
+        assert len(edges) == 3 * n * (n + 1) ** 2 + 3 * n * n * (n + 1) + n**3
+    nd = nv + len(edges)
+    _, vol, G = fem.cell_geometry(om.coords, om.cells)
+    K = fem.assemble_matrix(p2.stiffness_elements(vol, G), dofs, nd)
+    M = fem.assemble_matrix(p2.mass_elements(vol, dim), dofs, nd)
+    q = lambda x: x[..., 0] ** 2 + 2 * x[..., 0] * x[..., 1] - 0.5 * x[..., 1] ** 2 + x[..., 0] + (0.25 * x[..., 2] ** 2 if dim == 3 else 0.0)  # noqa: E731
+    lap = 2.0 - 1.0 + (0.5 if dim == 3 else 0.0)
+    u = p2.interpolate(q, om.coords, edges)
+    b = fem.assemble_vector(p2.load_elements_callable(om.coords, om.cells, vol, lambda x: -lap * np.ones(x.shape[:-1]), 0), dofs, nd)
+    bd = p2.boundary_dofs(om, np.unique(om.facet_tags), edges)
+    interior = np.setdiff1d(np.arange(nd), bd)
+    assert np.abs((K @ u - b)[interior]).max() < 1e-13
+    assert abs(M.sum() - 1.0) < 1e-13
+    assert abs(p2.integral(u, dofs, vol, dim) - u @ (M @ np.ones(nd))) < 1e-13
+
+
+@pytest.mark.parametrize("kind", ["square", "cube", "circle"])
+def test_p2_taylor_test(kind):
+    """Shape gradient with P2 state / adjoint passes the reference's Taylor test (rate > 1.9,
+    cashocs/verification.py:182-302; tests/test_shape_optimization.py:302-318)."""
+    if kind == "square":
+        om, mk = meshes.regular_mesh(10), (1, 2, 3, 4)
+    elif kind == "cube":
+        om, mk = meshes.regular_mesh(4, 1.0, 1.0, 1.0), (1, 2, 3, 4, 5, 6)
+    else:
+        om, mk = meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz")), (1,)
+    cfg = pipeline.ShapeConfig(shape_bdry_def=mk, test_for_intersections=False)
+    prob = pipeline.PoissonShapeProblem(om, bc_markers=mk, config=cfg, state_degree=2)
+    rate, rates, _ = pipeline.shape_gradient_test(prob)
+    assert rate > 1.9 and min(rates) > 1.9
