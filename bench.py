@@ -167,7 +167,7 @@ def run_reference_arm(args) -> None:
 
 
 # ----------------------------------------------------------------------------- B200 arm
-def build_problem(n: int, dist=None):
+def build_problem(n: int, dist=None, state_degree: int = 1):
     import cashocs_b200 as cb
 
     if dist is None:
@@ -185,7 +185,7 @@ def build_problem(n: int, dist=None):
     cfg.set("ShapeGradient", "damping_factor", repr(SHAPE["damping_factor"]))
     cfg.set("ShapeGradient", "mu_fix", repr(SHAPE["mu"]))
     cfg.set("ShapeGradient", "mu_def", repr(SHAPE["mu"]))
-    u, p = cb.Function(mesh), cb.Function(mesh)
+    u, p = cb.Function(mesh, degree=state_degree), cb.Function(mesh, degree=state_degree)
     gksp = dict(KSP)
     gksp["ksp_profile_every"] = 8
     sop = cb.ShapeOptimizationProblem(cb.PoissonForm(source=f), cb.create_dirichlet_bcs(0.0, ALL_MARKERS),
@@ -222,6 +222,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pc", default="hypre", choices=["hypre", "jacobi"],
                     help="pc_type of the three Krylov solves (hypre -> device smoothed-aggregation AMG on 1 GPU)")
+    ap.add_argument("--state-degree", type=int, default=1, choices=[1, 2],
+                    help="CG degree of the state / adjoint space (2 = BASELINE configs[4]; one GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     KSP["pc_type"] = args.pc
@@ -251,7 +253,7 @@ def main() -> None:
 
     lib = _lib.load()
     t_setup = time.perf_counter()
-    sop = build_problem(args.n, dist)
+    sop = build_problem(args.n, dist, args.state_degree)
     mesh = sop.mesh
     h = 1.0 / args.n
     n_tets, n_verts = 6 * args.n**3, (args.n + 1) ** 3
@@ -314,12 +316,27 @@ def main() -> None:
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (per launch; only
+    # valid for the workload it was captured on: n = 119 on one GPU)
+    traffic = None
+    cap = os.path.join(ROOT, "profiles", "r01_ncu_full_k_cg_spmv3.csv")
+    if args.n == 119 and world == 1 and os.path.exists(cap):
+        rd = wr = None
+        for row in open(cap):
+            f = row.strip().split(",")
+            if f[0] == "dram__bytes_read.sum":
+                rd = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+            if f[0] == "dram__bytes_write.sum":
+                wr = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+        if rd is not None and wr is not None:
+            traffic = rd + wr
     roofline = None
     if spmv_prof > 0:
         avg_ms = spmv_ms / spmv_prof
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_cg_spmv<3> (elasticity PCG: w = A p, fused p.w)", "achieved": achieved,
-                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": "profiles/r01_ncu_full_k_cg_spmv3.csv (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" if traffic else None,
                     "avg_launch_ms": avg_ms, "launches_profiled": spmv_prof, "algorithmic_bytes_per_launch": alg_bytes,
                     # fine-level launches per PCG iteration: 1 (w = A p) + 2 inside the AMG V(1,1)-cycle
                     "spmv_share_of_step": (avg_ms * sum(i[2] for i in its) *
@@ -330,7 +347,9 @@ def main() -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.n, args.gpus), "n": args.n, "tets": n_tets, "vertices": n_verts,
+            "config": {"workload": workload_name(args.n, args.gpus) + (" [P2 state/adjoint]" if args.state_degree == 2 else ""),
+                       "state_degree": args.state_degree, "state_dofs": int(sop.states[0].vector.numel()),
+                       "n": args.n, "tets": n_tets, "vertices": n_verts,
                        "block_nnz": nnzb_total, "krylov_its_state_adjoint_elasticity": list(its[-1]),
                        "ksp_options": {k: v for k, v in KSP.items()},
                        "pc_on_device": ("smoothed-aggregation AMG" if args.pc == "hypre" else "jacobi"),
