@@ -319,7 +319,7 @@ def main() -> None:
     # DRAM traffic of the same kernel from the committed `ncu --set full` capture (per launch; only
     # valid for the workload it was captured on: n = 119 on one GPU)
     traffic = None
-    cap = os.path.join(ROOT, "profiles", "r01_ncu_full_k_cg_spmv3.csv")
+    cap = os.path.join(ROOT, "profiles", "r01b_ncu_full_k_cg_spmv.csv")
     if args.n == 119 and world == 1 and os.path.exists(cap):
         rd = wr = None
         for row in open(cap):
@@ -336,7 +336,7 @@ def main() -> None:
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_cg_spmv<3> (elasticity PCG: w = A p, fused p.w)", "achieved": achieved,
                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "traffic_source": "profiles/r01_ncu_full_k_cg_spmv3.csv (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" if traffic else None,
+                    "traffic_source": "profiles/r01b_ncu_full_k_cg_spmv.csv (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" if traffic else None,
                     "avg_launch_ms": avg_ms, "launches_profiled": spmv_prof, "algorithmic_bytes_per_launch": alg_bytes,
                     # fine-level launches per PCG iteration: 1 (w = A p) + 2 inside the AMG V(1,1)-cycle
                     "spmv_share_of_step": (avg_ms * sum(i[2] for i in its) *
