@@ -354,7 +354,10 @@ def main() -> None:
                        "ksp_options": {k: v for k, v in KSP.items()},
                        "pc_on_device": ("smoothed-aggregation AMG" if args.pc == "hypre" else "jacobi"),
                        "l2_policy": "inputs larger than L2 (elasticity matrix %.2f GB, L2 126 MB)" % (76e-9 * nnzb_rank),
-                       "parallelism": "1 GPU" if dist is None else f"mesh partitioned into {world} vertex slabs, NCCL halo + allreduce"},
+                       "parallelism": "1 GPU" if dist is None else (
+                           f"mesh partitioned into {world} vertex slabs, " +
+                           ("halo exchange + Krylov all-reduces one-sided over NVLink peer memory (NCCL for the AMG agglomeration)"
+                            if dist.p2p else "NCCL halo + allreduce"))},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(coords_host.numel() * 8),
                     "d2h_bytes_per_step": int(grad_host.numel() * 8), "ms_per_step": ms_e2e / args.steps},

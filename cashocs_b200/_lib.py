@@ -209,6 +209,11 @@ SIGNATURES = {
     "cb_dist_create": (I32, [C.POINTER(P), P, I32, I32, I32, P, P, P, P, I64, I64]),
     "cb_dist_clone_plan": (I32, [P, C.POINTER(P), I32, P, P, P, P, I64, I64]),
     "cb_dist_destroy": (I32, [P]),
+    "cb_dist_p2p_export": (I32, [P, P]),
+    "cb_dist_p2p_ghost_cap": (I64, [P]),
+    "cb_dist_p2p_open": (I32, [P, P, P, P]),
+    "cb_dist_p2p_disable": (I32, [P]),
+    "cb_dist_p2p_error": (I32, [P]),
     "cb_dist_halo_exchange": (I32, [P, P, P, I32, P]),
     "cb_dist_allreduce": (I32, [P, P, P, I32, I32]),
 }

@@ -489,6 +489,8 @@ class LinearSolver:
                              dist, _lib.ptr(work), work.numel(), C.byref(res), _lib.ptr(hist), hist_len),
             "cb_ksp_solve",
         )
+        if A.mesh.dist is not None:
+            A.mesh.dist.check_p2p()
         history = hist[: res.its + 1].copy() if hist is not None else None
         self.last_result = KSPResult(int(res.reason), int(res.its), float(res.rnorm), float(res.rnorm0), history,
                                      float(res.spmv_ms), int(res.spmv_profiled), int(res.spmv_launches))

@@ -78,6 +78,21 @@ struct cb_dist {
   const int32_t* send_idx = nullptr;  // device
   int64_t n_owned = 0, n_ghost = 0;
   bool owns_comm = true;               // false for plans cloned from a parent (AMG coarse levels)
+  // ---- one-sided transport over NVLink peer memory (cb_dist_p2p_*), optional
+  // Window layout (doubles): [2 parities][ghost_cap] halo landing zone | [2][nranks][RED_W] reduction
+  // slots | uint64 flags: halo_flag[nranks], red_flag[nranks], ticket, error.
+  bool p2p = false;
+  unsigned char* window = nullptr;                 // my window (cudaMalloc, exported by IPC)
+  std::vector<unsigned char*> peer_window;         // [nranks] mapped peer windows (self = window)
+  int64_t ghost_cap = 0;                           // doubles per parity of the landing zone
+  unsigned long long halo_epoch = 0, red_epoch = 0;
+  // device copies of the plan for the put kernel
+  int64_t* d_send_off = nullptr;                   // [nneigh+1]
+  int64_t* d_remote_off = nullptr;                 // [nneigh] node offset of my data in the peer's ghost range
+  int64_t* d_remote_cap = nullptr;                 // [nneigh] parity stride (doubles) of the peer's landing zone
+  int64_t* d_recv_off = nullptr;                   // [nneigh+1]
+  int32_t* d_neigh = nullptr;                      // [nneigh]
+  unsigned char** d_peer_window = nullptr;         // [nranks]
 };
 
 namespace cb {
@@ -95,8 +110,177 @@ __global__ void k_pack(int64_t n, const int32_t* __restrict__ idx, const double*
 
 int64_t dist_send_len(const cb_dist* d) { return d ? d->send_off.back() : 0; }
 
+// ------------------------------------------------------------------ one-sided NVLink transport
+constexpr int RED_W = 8;  // doubles per reduction message
+// Every rank exports one cudaMalloc'ed window per halo plan through CUDA IPC; neighbours write their
+// boundary values straight into its landing zone with plain stores over NVLink (pack and transfer
+// are ONE kernel), then release a per-source flag holding the exchange epoch; the receiver's kernel
+// acquires the flags and copies the landing zone behind the owned part of the vector.  Landing zone
+// and reduction slots are double-buffered by epoch parity: a neighbour can be at most one exchange
+// ahead (it needs my next message to get further), so parity e+1 never overwrites data still read.
+// Window layout in doubles.  The header (flags, reduction slots) sits at FIXED offsets so a peer can
+// address it without knowing this rank's ghost count; the landing zone follows, its parity stride
+// (`ghost_cap`) is the RECEIVER's and is told to every sender at setup (d_remote_cap).
+struct WindowLayout {
+  int nranks;
+  __host__ __device__ int64_t flags_off() const { return 0; }                       // 2*nranks + 4 uint64
+  __host__ __device__ int64_t red_off() const { return 2LL * nranks + 4; }          // [2][nranks][RED_W]
+  __host__ __device__ int64_t land_off() const { return red_off() + 2LL * nranks * RED_W; }
+  __host__ __device__ int64_t total_doubles(int64_t ghost_cap) const { return land_off() + 2 * ghost_cap; }
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin until *flag >= epoch; gives up after ~4e9 cycles (a dead peer must not hang the GPU)
+__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long epoch,
+                                          unsigned long long* error) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < epoch) {
+    if (*reinterpret_cast<volatile unsigned long long*>(error)) return false;  // an earlier wait already failed
+    if (clock64() - t0 > 2000000000LL) {
+      atomicExch(error, 1ULL);
+      return false;
+    }
+    __nanosleep(64);
+  }
+  return true;
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_halo_put(int nneigh, const int64_t* __restrict__ send_off, const int64_t* __restrict__ remote_off,
+           const int32_t* __restrict__ neigh, const int32_t* __restrict__ send_idx,
+           const int64_t* __restrict__ remote_cap, const double* __restrict__ x,
+           unsigned char* const* __restrict__ peer_window, WindowLayout lay, int myrank,
+           unsigned long long epoch, unsigned char* my_window) {
+  const int64_t nsend = send_off[nneigh];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nsend * BS;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = i / BS;
+    const int c = (int)(i - v * BS);
+    int j = 0;
+    while (j + 1 < nneigh && v >= send_off[j + 1]) ++j;
+    double* dst = reinterpret_cast<double*>(peer_window[neigh[j]]) + lay.land_off() +
+                  (int64_t)(epoch & 1ULL) * remote_cap[j] + (remote_off[j] + (v - send_off[j])) * BS + c;
+    *dst = x[(int64_t)send_idx[v] * BS + c];
+  }
+  // the last block to finish releases the flags (all stores of all blocks are fenced before)
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  unsigned long long* flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(my_window) + lay.flags_off());
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(flags + 2 * lay.nranks);
+  if (threadIdx.x == 0) last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x < nneigh) {
+    __threadfence_system();
+    unsigned long long* pf = reinterpret_cast<unsigned long long*>(
+        reinterpret_cast<double*>(peer_window[neigh[threadIdx.x]]) + lay.flags_off());
+    st_release_sys(pf + myrank, epoch);
+  }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_halo_get(int nneigh, const int64_t* __restrict__ recv_off, const int32_t* __restrict__ neigh,
+           double* __restrict__ x, int64_t n_owned, unsigned char* my_window, WindowLayout lay,
+           int64_t ghost_cap, unsigned long long epoch) {
+  unsigned long long* flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(my_window) + lay.flags_off());
+  unsigned long long* error = flags + 2 * lay.nranks + 1;
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  if (threadIdx.x < nneigh && recv_off[threadIdx.x + 1] > recv_off[threadIdx.x]) {
+    if (!wait_flag(flags + neigh[threadIdx.x], epoch, error)) ok = 0;
+  }
+  __syncthreads();
+  if (!ok) return;
+  const double* src = reinterpret_cast<const double*>(my_window) + lay.land_off() + (int64_t)(epoch & 1ULL) * ghost_cap;
+  const int64_t n = recv_off[nneigh] * BS;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[n_owned * BS + i] = __ldcv(src + i);
+}
+
+// all-reduce of n <= RED_W doubles: every rank writes its message into every rank's slots, then sums
+// the nranks messages in rank order (bit-identical on all ranks, deterministic)
+__global__ void k_red_put(int n, const double* __restrict__ buf, unsigned char* const* __restrict__ peer_window,
+                          WindowLayout lay, int myrank, unsigned long long epoch) {
+  const int r = threadIdx.x;
+  if (r >= lay.nranks) return;
+  double* slots = reinterpret_cast<double*>(peer_window[r]) + lay.red_off() +
+                  ((int64_t)(epoch & 1ULL) * lay.nranks + myrank) * RED_W;
+  for (int i = 0; i < n; ++i) slots[i] = buf[i];
+  __threadfence_system();
+  unsigned long long* pf = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(peer_window[r]) + lay.flags_off());
+  st_release_sys(pf + lay.nranks + myrank, epoch);
+}
+
+__global__ void k_red_get(int n, double* __restrict__ buf, unsigned char* my_window, WindowLayout lay,
+                          unsigned long long epoch, int op) {
+  unsigned long long* flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(my_window) + lay.flags_off());
+  unsigned long long* error = flags + 2 * lay.nranks + 1;
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  if (threadIdx.x < lay.nranks) {
+    if (!wait_flag(flags + lay.nranks + threadIdx.x, epoch, error)) ok = 0;
+  }
+  __syncthreads();
+  if (!ok) return;
+  const double* slots = reinterpret_cast<const double*>(my_window) + lay.red_off() +
+                        (int64_t)(epoch & 1ULL) * lay.nranks * RED_W;
+  if (threadIdx.x < n) {
+    double acc = __ldcv(slots + threadIdx.x);
+    for (int r = 1; r < lay.nranks; ++r) {
+      const double v = __ldcv(slots + (int64_t)r * RED_W + threadIdx.x);
+      acc = (op == 0) ? acc + v : red_combine(acc, v, op == 1 ? RED_MIN : RED_MAX);
+    }
+    buf[threadIdx.x] = acc;
+  }
+}
+
+static int p2p_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs) {
+  const int nneigh = (int)d->neigh.size();
+  const WindowLayout lay{d->nranks};
+  const unsigned long long epoch = ++d->halo_epoch;
+  const int64_t nsend = d->send_off.back(), nrecv = d->recv_off.back();
+  if (nrecv * bs > d->ghost_cap) {
+    set_error("p2p halo exchange: landing zone too small");
+    return CB_ERR_ARG;
+  }
+  const int pgrid = grid_for(nsend * bs > 0 ? nsend * bs : 1, 256, 2);
+  const int ggrid = grid_for(nrecv * bs > 0 ? nrecv * bs : 1, 256, 2);
+#define CB_HALO(BS)                                                                                          \
+  k_halo_put<BS><<<pgrid, 256, 0, s>>>(nneigh, d->d_send_off, d->d_remote_off, d->d_neigh, d->send_idx,      \
+                                       d->d_remote_cap, x, d->d_peer_window, lay, d->rank, epoch, d->window); \
+  CB_LAUNCH_CHECK();                                                                                         \
+  k_halo_get<BS><<<ggrid, 256, 0, s>>>(nneigh, d->d_recv_off, d->d_neigh, x, d->n_owned, d->window, lay,     \
+                                       d->ghost_cap, epoch);                                                 \
+  CB_LAUNCH_CHECK();
+  if (bs == 1) { CB_HALO(1) } else if (bs == 2) { CB_HALO(2) } else { CB_HALO(3) }
+#undef CB_HALO
+  return CB_OK;
+}
+
+static int p2p_allreduce(cudaStream_t s, cb_dist* d, double* buf, int n, int op) {
+  const WindowLayout lay{d->nranks};
+  const unsigned long long epoch = ++d->red_epoch;
+  k_red_put<<<1, 32, 0, s>>>(n, buf, d->d_peer_window, lay, d->rank, epoch);
+  CB_LAUNCH_CHECK();
+  k_red_get<<<1, 32, 0, s>>>(n, buf, d->window, lay, epoch, op);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
 int dist_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs, double* sendbuf) {
   if (!d || d->neigh.empty()) return CB_OK;
+  if (d->p2p) return p2p_halo_exchange(s, d, x, bs);
   const int64_t nsend = d->send_off.back();
   if (nsend > 0) {
     const int grid = grid_for(nsend * bs, 256, 4);
@@ -120,6 +304,7 @@ int dist_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs, double* se
 
 int dist_allreduce_sum(cudaStream_t s, cb_dist* d, double* buf, int n) {
   if (!d) return CB_OK;
+  if (d->p2p && n <= RED_W && d->nranks <= 32) return p2p_allreduce(s, d, buf, n, 0);
   CB_NCCL_CHECK(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat64, ncclSum, d->comm, s));
   return CB_OK;
 }
@@ -182,8 +367,88 @@ extern "C" int cb_dist_clone_plan(cb_dist* parent, cb_dist** out, int nneigh, co
   return CB_OK;
 }
 
+// Allocate this plan's window and return its 64-byte CUDA IPC handle (host layer all-gathers them).
+extern "C" int cb_dist_p2p_export(cb_dist* d, char* handle64) {
+  CB_REQUIRE(d && handle64, "cb_dist_p2p_export: missing argument");
+  d->ghost_cap = ((d->n_ghost * 3 + 7) / 8) * 8 + 8;
+  const WindowLayout lay{d->nranks};
+  const size_t bytes = sizeof(double) * (size_t)lay.total_doubles(d->ghost_cap);
+  CB_CUDA_CHECK(cudaMalloc(&d->window, bytes));
+  CB_CUDA_CHECK(cudaMemset(d->window, 0, bytes));
+  CB_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CB_CUDA_CHECK(cudaIpcGetMemHandle(&h, d->window));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return CB_OK;
+}
+
+extern "C" int64_t cb_dist_p2p_ghost_cap(cb_dist* d) { return d ? d->ghost_cap : 0; }
+
+// Map the peers' windows (handles [nranks*64], rank order) and switch this plan to the one-sided
+// transport.  remote_off [nneigh]: node offset of my data inside neighbour j's ghost range.
+extern "C" int cb_dist_p2p_open(cb_dist* d, const char* handles, const int64_t* remote_off,
+                                const int64_t* remote_cap) {
+  CB_REQUIRE(d && handles && d->window, "cb_dist_p2p_open: export the window first");
+  const int nneigh = (int)d->neigh.size();
+  CB_REQUIRE(nneigh == 0 || (remote_off && remote_cap), "cb_dist_p2p_open: remote offsets missing");
+  d->peer_window.assign(d->nranks, nullptr);
+  for (int r = 0; r < d->nranks; ++r) {
+    if (r == d->rank) { d->peer_window[r] = d->window; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * r, 64);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return CB_ERR_CUDA;
+    }
+    d->peer_window[r] = static_cast<unsigned char*>(ptr);
+  }
+  CB_CUDA_CHECK(cudaMalloc(&d->d_send_off, sizeof(int64_t) * (nneigh + 1)));
+  CB_CUDA_CHECK(cudaMalloc(&d->d_recv_off, sizeof(int64_t) * (nneigh + 1)));
+  CB_CUDA_CHECK(cudaMalloc(&d->d_remote_off, sizeof(int64_t) * (nneigh + 1)));
+  CB_CUDA_CHECK(cudaMalloc(&d->d_remote_cap, sizeof(int64_t) * (nneigh + 1)));
+  CB_CUDA_CHECK(cudaMalloc(&d->d_neigh, sizeof(int32_t) * (nneigh + 1)));
+  CB_CUDA_CHECK(cudaMalloc(&d->d_peer_window, sizeof(unsigned char*) * d->nranks));
+  CB_CUDA_CHECK(cudaMemcpy(d->d_send_off, d->send_off.data(), sizeof(int64_t) * (nneigh + 1), cudaMemcpyHostToDevice));
+  CB_CUDA_CHECK(cudaMemcpy(d->d_recv_off, d->recv_off.data(), sizeof(int64_t) * (nneigh + 1), cudaMemcpyHostToDevice));
+  if (nneigh) {
+    CB_CUDA_CHECK(cudaMemcpy(d->d_remote_off, remote_off, sizeof(int64_t) * nneigh, cudaMemcpyHostToDevice));
+    CB_CUDA_CHECK(cudaMemcpy(d->d_remote_cap, remote_cap, sizeof(int64_t) * nneigh, cudaMemcpyHostToDevice));
+    std::vector<int32_t> ng(d->neigh.begin(), d->neigh.end());
+    CB_CUDA_CHECK(cudaMemcpy(d->d_neigh, ng.data(), sizeof(int32_t) * nneigh, cudaMemcpyHostToDevice));
+  }
+  CB_CUDA_CHECK(cudaMemcpy(d->d_peer_window, d->peer_window.data(), sizeof(unsigned char*) * d->nranks, cudaMemcpyHostToDevice));
+  d->p2p = true;
+  return CB_OK;
+}
+
+// Back to NCCL for this plan (collective decision of the host layer when a rank could not map a peer).
+extern "C" int cb_dist_p2p_disable(cb_dist* d) {
+  if (d) d->p2p = false;
+  return CB_OK;
+}
+
+// 1 if a peer timed out inside a one-sided wait (the solve result is then invalid), else 0.
+extern "C" int cb_dist_p2p_error(cb_dist* d) {
+  if (!d || !d->p2p) return 0;
+  const WindowLayout lay{d->nranks};
+  unsigned long long e = 0;
+  cudaMemcpy(&e, reinterpret_cast<double*>(d->window) + lay.flags_off() + 2 * d->nranks + 1, sizeof(e), cudaMemcpyDeviceToHost);
+  return e != 0;
+}
+
 extern "C" int cb_dist_destroy(cb_dist* d) {
   if (!d) return CB_OK;
+  if (d->p2p) {
+    for (int r = 0; r < d->nranks; ++r)
+      if (r != d->rank && d->peer_window[r]) cudaIpcCloseMemHandle(d->peer_window[r]);
+    cudaFree(d->d_send_off); cudaFree(d->d_recv_off); cudaFree(d->d_remote_off); cudaFree(d->d_remote_cap); cudaFree(d->d_neigh);
+    cudaFree(d->d_peer_window);
+  }
+  if (d->window) cudaFree(d->window);
   if (d->comm && d->owns_comm) g_nccl.CommDestroy(d->comm);
   delete d;
   return CB_OK;
@@ -197,6 +462,7 @@ extern "C" int cb_dist_halo_exchange(void* stream, cb_dist* d, double* x, int bs
 
 extern "C" int cb_dist_allreduce(void* stream, cb_dist* d, double* buf_dev, int n, int op) {
   CB_REQUIRE(d && buf_dev, "cb_dist_allreduce: missing argument");
+  if (d->p2p && n <= RED_W && d->nranks <= 32) return p2p_allreduce(as_stream(stream), d, buf_dev, n, op);
   const int nop = op == 0 ? ncclSum : (op == 1 ? ncclMin : ncclMax);
   CB_NCCL_CHECK(g_nccl.AllReduce(buf_dev, buf_dev, (size_t)n, ncclFloat64, nop, d->comm, as_stream(stream)));
   return CB_OK;

@@ -18,6 +18,7 @@ Two transports share one halo plan:
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -43,6 +44,7 @@ class DistContext:
         self._sendbuf: torch.Tensor | None = None
         self.cell_counts: list[int] | None = None
         self.parent: DistContext | None = None  # plans derived for AMG coarse levels share the communicator
+        self.p2p = False
 
     # ------------------------------------------------------------------ setup
     def set_plan(self, neigh, send_lists, recv_counts, n_owned: int, n_ghost: int, device) -> None:
@@ -73,6 +75,7 @@ class DistContext:
                 "cb_dist_clone_plan",
             )
             self.handle = handle
+            self._enable_p2p()
             return
         ident = [None]
         if self.rank == 0:
@@ -89,6 +92,41 @@ class DistContext:
             "cb_dist_create",
         )
         self.handle = handle
+        self._enable_p2p()
+
+    def _enable_p2p(self) -> None:
+        """Switch this plan to the one-sided NVLink transport (``csrc/dist.cu``): export this rank's
+        window, all-gather the CUDA IPC handles and the ghost offsets, map the peers' windows.
+        Collective; any rank failing to map a peer sends every rank back to NCCL.
+        ``CASHOCS_B200_P2P=0`` keeps NCCL send/recv + all-reduce."""
+        self.p2p = False
+        if os.environ.get("CASHOCS_B200_P2P", "1") == "0" or self.world > 32:
+            return
+        lib = _lib.load()
+        buf = C.create_string_buffer(64)
+        ok = lib.cb_dist_p2p_export(self.handle, buf) == 0
+        info = (bytes(buf.raw), {int(r): int(self.recv_off[j]) for j, r in enumerate(self.neigh)}, ok,
+                int(lib.cb_dist_p2p_ghost_cap(self.handle)))
+        allinfo = [None] * self.world
+        td.all_gather_object(allinfo, info)
+        if all(i[2] for i in allinfo):
+            handles = b"".join(i[0] for i in allinfo)
+            remote_off = np.array([allinfo[r][1][self.rank] for r in self.neigh] + [0], dtype=np.int64)
+            remote_cap = np.array([allinfo[r][3] for r in self.neigh] + [0], dtype=np.int64)
+            ok = lib.cb_dist_p2p_open(self.handle, handles, remote_off.ctypes.data, remote_cap.ctypes.data) == 0
+        else:
+            ok = False
+        oks = [None] * self.world
+        td.all_gather_object(oks, ok)
+        if all(oks):
+            self.p2p = True
+        else:
+            lib.cb_dist_p2p_disable(self.handle)
+
+    def check_p2p(self) -> None:
+        """Raise if a peer timed out inside a one-sided wait (the vectors are then invalid)."""
+        if self.p2p and _lib.load().cb_dist_p2p_error(self.handle):
+            raise _exceptions.CashocsException("one-sided halo exchange: a peer did not answer within the wait limit")
 
     def owner_of_ghost(self) -> torch.Tensor:
         """Owner rank of every ghost vertex (ghosts are ordered by owner)."""

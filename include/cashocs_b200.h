@@ -389,6 +389,18 @@ int cb_dist_clone_plan(cb_dist* parent, cb_dist** out, int nneigh, const int32_t
                        const int64_t* send_off, const int32_t* send_idx_dev, const int64_t* recv_off,
                        int64_t n_owned, int64_t n_ghost);
 int cb_dist_destroy(cb_dist* d);
+/* One-sided transport over NVLink peer memory (optional; NCCL send/recv + all-reduce otherwise).
+ * cb_dist_p2p_export allocates this plan's window (landing zone for ghost values, reduction slots,
+ * flags) and returns its 64-byte CUDA IPC handle; the host layer all-gathers the handles and the
+ * ghost offsets, cb_dist_p2p_open maps the peers' windows.  Afterwards cb_dist_halo_exchange is one
+ * put kernel (pack + store into the neighbours' windows + release flag) and one get kernel (acquire
+ * + copy behind the owned part), and all-reduces of <= 8 doubles are put + fixed-order local sum
+ * (bit-identical on every rank).  cb_dist_p2p_error: 1 after a peer timed out in a wait. */
+int cb_dist_p2p_export(cb_dist* d, char* handle64);
+int64_t cb_dist_p2p_ghost_cap(cb_dist* d); /* parity stride (doubles) of this rank's landing zone */
+int cb_dist_p2p_open(cb_dist* d, const char* handles, const int64_t* remote_off, const int64_t* remote_cap);
+int cb_dist_p2p_disable(cb_dist* d);
+int cb_dist_p2p_error(cb_dist* d);
 /* Ghost update of a vertex-blocked vector x [(n_owned+n_ghost)*bs] (Vec.ghostUpdate). */
 int cb_dist_halo_exchange(void* stream, cb_dist* d, double* x, int bs, double* sendbuf);
 /* In-place allreduce of n doubles (op: 0 sum, 1 min, 2 max). */
