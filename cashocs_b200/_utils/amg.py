@@ -131,12 +131,13 @@ class _Level:
 class AMGSymbolic:
     """Everything that depends only on the sparsity pattern (shared by all block sizes).
 
-    On a partitioned mesh (``dist`` given) aggregates never cross rank boundaries and the rows of
-    the partition interface (rows with ghost columns or in a send list) keep the *tentative*
-    prolongator row.  Then ``P`` maps owned fine nodes to owned coarse nodes only, the prolongator
-    row of every ghost node is known locally (``e_agg``), the Galerkin product of the owned coarse
-    rows needs no communication and the coarse operator stays globally symmetric.  Coarse ghost
-    nodes are the aggregates of the fine ghost nodes; every level gets its own halo plan.
+    On a partitioned mesh (``dist`` given) aggregates never cross rank boundaries and prolongator
+    rows are smoothed over local couplings only (ghost couplings lumped into the diagonal), so ``P``
+    maps owned fine nodes to owned coarse nodes only; the rows of the ghost nodes are imported from
+    their owners, the Galerkin product of the owned coarse rows then needs no further communication
+    and the coarse operator is the exact, globally symmetric ``P^T A P``.  Coarse ghost nodes are the
+    owners' aggregates appearing in imported rows; every level gets its own halo plan
+    (see ``_distributed_prolongator_pattern``).
     """
 
     MAX_DENSE = 256  # scalar rows of a coarsest level that is inverted densely (bs <= 3 -> <= 85 nodes)
@@ -176,35 +177,18 @@ class AMGSymbolic:
             if dist is None:
                 agg_ext, gc = agg, 0
                 pr, pc = rows, agg[col.long()]
+                nct = nc
+                key = torch.unique(pr * nct + pc)
+                p_rows = key // nct
+                L.p_rowptr = _rowptr_from_rows(p_rows, ncols)
+                L.p_col = (key % nct).to(torch.int32).contiguous()
+                L.nnzp_owned = int(L.p_col.numel())
+                L.pplan = None
             else:
-                iface = torch.zeros(n, dtype=torch.bool, device=dev)
-                iface[rows[~local]] = True
-                if dist.send_idx is not None and dist.send_idx.numel():
-                    iface[dist.send_idx.long()] = True
-                L.iface = iface.to(torch.uint8).contiguous()
-                # aggregate ids of the ghost nodes (owner-local numbering) through one halo exchange
-                v = torch.zeros(ncols, dtype=torch.float64, device=dev)
-                v[:n] = agg.to(torch.float64)
-                dist.halo_exchange(v, 1)
-                gid = v[n:].round().long()
-                owner = dist.owner_of_ghost().to(dev)
-                big = int(gid.max().item()) + 1 if gid.numel() else 1
-                ukey, inv = torch.unique(owner * big + gid, return_inverse=True)  # sorted by (owner, id)
-                gc = int(ukey.numel())
-                agg_ext = torch.cat([agg, nc + inv])
-                new_dist = dist.derive_plan(ukey // big, ukey % big, nc, dev)
-                # P rows: interior rows are smoothed (pattern = aggregates of all neighbours, all owned),
-                # interface rows stay tentative, ghost rows are the owners' tentative rows
-                interior_entry = ~iface[rows]
-                pr = torch.cat([rows[interior_entry], torch.nonzero(iface).reshape(-1), torch.arange(n, ncols, device=dev)])
-                pc = torch.cat([agg_ext[col.long()[interior_entry]], agg[iface], agg_ext[n:]])
-            nct = nc + gc
-            key = torch.unique(pr * nct + pc)
-            p_rows = key // nct
-            L.p_rowptr = _rowptr_from_rows(p_rows, ncols)
-            L.p_col = (key % nct).to(torch.int32).contiguous()
-            L.nnzp_owned = int(L.p_rowptr[n].item())
-            po_rows, po_col = p_rows[: L.nnzp_owned], L.p_col[: L.nnzp_owned].long()
+                gc, agg_ext, new_dist = self._distributed_prolongator_pattern(L, rows, col, local, agg, nc, dist)
+                nct = nc + gc
+            po_rows = _rows_of(L.p_rowptr[: n + 1])
+            po_col = L.p_col[: L.nnzp_owned].long()
             order = torch.argsort(po_col * n + po_rows)
             L.pt_perm = order
             L.pt_col = po_rows[order].to(torch.int32).contiguous()
@@ -218,6 +202,69 @@ class AMGSymbolic:
                 nc, nct)
             L.last = False
             rowptr, col, n, ncols, dist = c_rowptr, c_col, nc, nct, new_dist
+
+    @staticmethod
+    def _distributed_prolongator_pattern(L, rows, col, local, agg, nc, dist):
+        """Pattern of P on a partitioned level (collective).
+
+        Aggregates are rank-local.  Owned rows are smoothed over their *local* couplings only (the
+        numeric kernel lumps the dropped ghost couplings into the diagonal, so rows still sum to one):
+        row i holds the aggregates of its owned neighbours, all owned coarse nodes.  The rows of the
+        ghost nodes are imported from their owners (pattern here, values by ``L.pplan`` in every
+        numeric phase), so ``A P`` of the owned rows -- and with it the owned rows of ``P^T A P`` -- are
+        exact products with the global P and need no further communication.  Coarse ghost nodes are
+        the owners' aggregates that appear in imported rows; they get their own halo plan.
+        Returns (number of coarse ghosts, agg extended by a dummy ghost tail, coarse halo plan).
+        """
+        import numpy as np
+        import torch.distributed as td
+
+        from cashocs_b200 import distributed
+
+        dev = col.device
+        n, ncols = L.n, L.ncols
+        key = torch.unique(rows[local] * nc + agg[col[local].long()])
+        own_rows, own_cols = key // nc, key % nc
+        own_rowptr = _rowptr_from_rows(own_rows, n)
+        nnz_own = int(own_cols.numel())
+        # export the rows of my send nodes, neighbour by neighbour, in send (= the receiver's ghost) order
+        export, send_pos = {}, []
+        for j, r in enumerate(dist.neigh):
+            nodes = dist.send_idx[int(dist.send_off[j]): int(dist.send_off[j + 1])].long()
+            lens = own_rowptr[nodes + 1] - own_rowptr[nodes]
+            tot = int(lens.sum().item())
+            rep = torch.repeat_interleave(torch.arange(nodes.numel(), device=dev), lens)
+            start = torch.cumsum(lens, 0) - lens
+            pos = own_rowptr[nodes][rep] + (torch.arange(tot, device=dev) - start[rep])
+            send_pos.append(pos)
+            export[int(r)] = (lens.cpu(), own_cols[pos].cpu())
+        allexp = [None] * dist.world
+        td.all_gather_object(allexp, export)
+        g_lens, g_owner, g_id, recv_counts = [], [], [], []
+        for j, r in enumerate(dist.neigh):
+            lens, ids = allexp[int(r)][dist.rank]
+            assert lens.numel() == int(dist.recv_off[j + 1] - dist.recv_off[j])
+            g_lens.append(lens)
+            g_id.append(ids)
+            g_owner.append(torch.full((ids.numel(),), int(r), dtype=torch.int64))
+            recv_counts.append(int(ids.numel()))
+        g_lens = torch.cat(g_lens).to(dev) if g_lens else torch.zeros(0, dtype=torch.int64, device=dev)
+        g_id = torch.cat(g_id).to(dev) if g_id else torch.zeros(0, dtype=torch.int64, device=dev)
+        g_owner = torch.cat(g_owner).to(dev) if g_owner else torch.zeros(0, dtype=torch.int64, device=dev)
+        big = int(g_id.max().item()) + 1 if g_id.numel() else 1
+        ukey, inv = torch.unique(g_owner * big + g_id, return_inverse=True)  # sorted by (owner, id)
+        gc = int(ukey.numel())
+        new_dist = dist.derive_plan(ukey // big, ukey % big, nc, dev)
+        L.p_rowptr = torch.cat([own_rowptr, own_rowptr[-1] + torch.cumsum(g_lens, 0)])
+        L.p_col = torch.cat([own_cols, nc + inv]).to(torch.int32).contiguous()
+        L.nnzp_owned = nnz_own
+        # halo plan over prolongator ENTRIES: ghost-row values follow the owners' values
+        pplan = distributed.DistContext(dist.rank, dist.world, dist.transport)
+        pplan.parent = dist if dist.parent is None else dist.parent
+        pplan.set_plan(dist.neigh, send_pos, recv_counts, nnz_own, int(g_id.numel()), dev)
+        L.pplan = pplan
+        agg_ext = torch.cat([agg, torch.zeros(ncols - n, dtype=agg.dtype, device=dev)])
+        return gc, agg_ext, new_dist
 
     @staticmethod
     def _replicate(rowptr, col, n, ncols, n_glob, dist):
@@ -407,6 +454,8 @@ class AMGHierarchy:
             _lib.check(lib.cb_amg_smooth_prolongator(s, C.byref(ms), omega, _lib.ptr(L.agg), _lib.ptr(L.iface),
                                                      _lib.ptr(L.p_rowptr), _lib.ptr(L.p_col), _lib.ptr(D.p_val)),
                        "cb_amg_smooth_prolongator")
+            if L.pplan is not None:  # prolongator rows of the ghost nodes follow their owners' values
+                L.pplan.halo_exchange(D.p_val, 1)
             torch.index_select(D.p_val[: L.nnzp_owned], 0, L.pt_perm, out=D.pt_val)
             nxt, nxtL = self.data[li + 1], self.levels[li + 1]
             rep = nxtL.rep_dist is not None

@@ -31,7 +31,11 @@ __device__ __forceinline__ int64_t find_col(const int32_t* __restrict__ col, int
   return lo;
 }
 
-// P[i, J] = [J == agg[i]] - omega / S_ii * sum_{k : agg[k] == J} S_ik     (k restricted to k < nlocal)
+// P[i, J] = [J == agg[i]] - omega / S^F_ii * sum_{k < nlocal : agg[k] == J} S^F_ik, where S^F is S
+// filtered to the local columns with the dropped (ghost) couplings lumped into the diagonal:
+// S^F_ii = S_ii + sum_{k >= nlocal} S_ik.  Row sums of S are preserved, so the rows of P keep
+// summing to 1 - omega * rowsum(S) / S^F_ii (partition of unity for Laplace-like rows) although
+// aggregates and prolongator rows never reach across a partition boundary.
 __global__ void __launch_bounds__(128)
 k_smooth_prolongator(int64_t n, int64_t nlocal, const int64_t* __restrict__ s_rowptr,
                      const int32_t* __restrict__ s_col, const double* __restrict__ s_val, double omega,
@@ -41,20 +45,24 @@ k_smooth_prolongator(int64_t n, int64_t nlocal, const int64_t* __restrict__ s_ro
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pb = p_rowptr[i], pe = p_rowptr[i + 1];
-    if (tentative && tentative[i]) {  // interface row of a partitioned mesh: P[i, agg(i)] = 1
-      p_val[pb] = 1.0;
+    if (tentative && tentative[i]) {  // keep the unsmoothed row: P[i, agg(i)] = 1
+      for (int64_t k = pb; k < pe; ++k) p_val[k] = (p_col[k] == agg[i]) ? 1.0 : 0.0;
       continue;
     }
     for (int64_t k = pb; k < pe; ++k) p_val[k] = 0.0;
-    double sii = 0.0;
-    for (int64_t k = s_rowptr[i]; k < s_rowptr[i + 1]; ++k)
-      if (s_col[k] == i) sii = s_val[k];
-    const double w = (sii != 0.0) ? omega / sii : 0.0;
+    double sii = 0.0, lumped = 0.0;
+    for (int64_t k = s_rowptr[i]; k < s_rowptr[i + 1]; ++k) {
+      const int32_t c = s_col[k];
+      if (c == i) sii = s_val[k];
+      else if (c >= nlocal) lumped += s_val[k];
+    }
+    const double sf = sii + lumped;
+    const double w = (sf != 0.0) ? omega / sf : 0.0;
     for (int64_t k = s_rowptr[i]; k < s_rowptr[i + 1]; ++k) {
       const int32_t c = s_col[k];
       if (c >= nlocal) continue;
       const int64_t pos = find_col(p_col, pb, pe, agg[c]);
-      p_val[pos] -= w * s_val[k];
+      p_val[pos] -= w * ((c == i) ? sf : s_val[k]);
     }
     p_val[find_col(p_col, pb, pe, agg[i])] += 1.0;
   }
@@ -239,7 +247,7 @@ extern "C" int cb_amg_smooth_prolongator(void* stream, const cb_mat* S, double o
                                          const int32_t* p_col, double* p_val) {
   CB_REQUIRE(S && S->bs == 1 && agg && p_rowptr && p_col && p_val, "cb_amg_smooth_prolongator: bad argument");
   k_smooth_prolongator<<<grid_for(S->nrows, 128, 16), 128, 0, as_stream(stream)>>>(
-      S->nrows, S->ncols, S->rowptr, S->col, S->val, omega, agg, tentative, p_rowptr, p_col, p_val);
+      S->nrows, S->nrows, S->rowptr, S->col, S->val, omega, agg, tentative, p_rowptr, p_col, p_val);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }

@@ -323,9 +323,10 @@ int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, double* x,
 
 /* AMG numeric phase.  s_val [nnzb] = trace(A_blk)/bs (the scalar strength matrix S). */
 int cb_amg_block_trace(void* stream, const cb_mat* A, double* s_val);
-/* P = T - omega D_S^-1 S T for the piecewise-constant tentative prolongator T of `agg` [ncols]
- * (ghost columns carry their coarse ghost index).  Rows flagged in `tentative` (uint8 [nrows],
- * nullable: the partition-interface rows of a distributed mesh) keep the unsmoothed row e_agg. */
+/* P = T - omega D_F^-1 S^F T for the piecewise-constant tentative prolongator T of `agg` [nrows].
+ * S^F is S restricted to its local columns (col < nrows) with the dropped ghost couplings lumped into
+ * the diagonal (identity on one GPU), so prolongator rows never reference another rank's aggregates
+ * and still sum to one.  Rows flagged in `tentative` (uint8 [nrows], nullable) keep the row e_agg. */
 int cb_amg_smooth_prolongator(void* stream, const cb_mat* S, double omega, const int32_t* agg,
                               const uint8_t* tentative, const int64_t* p_rowptr, const int32_t* p_col,
                               double* p_val);

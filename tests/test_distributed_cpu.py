@@ -129,14 +129,14 @@ def _amg_worker(rank, world, port, n_mesh, agglomerate, rep_level, results):
         nglob = (n_mesh + 1) ** 3
         for li, L in enumerate(levels[:-1]):
             nxt = levels[li + 1]
-            # prolongator values: tentative on interface + ghost rows, arbitrary on interior rows
+            # prolongator values: arbitrary on owned rows, imported on ghost rows
             prp = L.p_rowptr.numpy()
             pval = np.ones(L.p_col.numel())
-            if L.dist is not None:
-                interior = np.repeat(L.iface.numpy() == 0, np.diff(prp[: L.n + 1]))
-                pval[: L.nnzp_owned][interior] = rng.rand(int(interior.sum())) + 0.1
-            else:
-                pval[:] = rng.rand(pval.size) + 0.1
+            pval[: L.nnzp_owned] = rng.rand(L.nnzp_owned) + 0.1
+            if L.dist is not None:  # rows of the ghost nodes carry their owners' values
+                pv = torch.from_numpy(pval)
+                L.pplan.halo_exchange(pv, 1)
+                pval = pv.numpy()
             ap = _terms(L.ap_seg, L.ap_sl, L.ap_sr, val, pval)
             ptval = pval[: L.nnzp_owned][L.pt_perm.numpy()]
             ac = _terms(L.ac_seg, L.ac_sl, L.ac_sr, ptval, ap)
@@ -200,8 +200,8 @@ def _amg_worker(rank, world, port, n_mesh, agglomerate, rep_level, results):
 
 @pytest.mark.parametrize("n_mesh,agglomerate,rep_level", [(14, 20000, 1), (16, 50, 2)])
 def test_distributed_amg_hierarchy_world2(n_mesh, agglomerate, rep_level):
-    """Rank-local aggregates + tentative interface rows + replicated coarse tail give the exact
-    global Galerkin operators P^T A P (symmetric) on every level."""
+    """Rank-local aggregates + imported prolongator rows of the ghost nodes + replicated coarse tail
+    give the exact global Galerkin operators P^T A P (symmetric) on every level."""
     world = 2
     port = 31500 + (os.getpid() % 2000) + rep_level
     mgr = mp.Manager()
