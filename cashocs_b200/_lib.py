@@ -14,7 +14,8 @@ import numpy as np
 from cashocs_b200 import _exceptions
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcashocs_b200.so")
+# CASHOCS_B200_LIB selects a tuning variant built by cashocs_b200.build.build(tag=...) (kernel experiments)
+LIB_PATH = os.environ.get("CASHOCS_B200_LIB") or os.path.join(_HERE, "libcashocs_b200.so")
 
 POLY_MAXT = 24
 QUAD_MAXQ = 64

@@ -27,11 +27,14 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(verbose: bool = False, force: bool = False) -> str:
+def build(verbose: bool = False, force: bool = False, extra_flags: list[str] | None = None, tag: str = "") -> str:
+    """``extra_flags`` / ``tag`` build a tuning variant ``libcashocs_b200<tag>.so`` (selected at run
+    time with ``CASHOCS_B200_LIB``); the product library is the untagged default."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(INCLUDE, "cashocs_b200.h"))
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + tag)
+    lib_path = LIB if not tag else LIB.replace(".so", f"{tag}.so")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
@@ -40,7 +43,8 @@ def build(verbose: bool = False, force: bool = False) -> str:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [spath] + headers):
-            cmd = [nvcc] + COMMON + EXTRA.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", spath, "-o", obj]
+            cmd = ([nvcc] + COMMON + EXTRA.get(src, []) + (extra_flags or []) + (["-Xptxas", "-v"] if verbose else [])
+                   + ["-c", spath, "-o", obj])
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
@@ -52,10 +56,10 @@ def build(verbose: bool = False, force: bool = False) -> str:
             sys.stderr.write(f"[cashocs_b200.build] {src}\n{out}\n")
     if failed:
         raise RuntimeError("nvcc failed")
-    if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
+    if force or procs or _stale(lib_path, objs):
+        cmd = [nvcc, "-shared", "-o", lib_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
         subprocess.run(cmd, check=True)
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":

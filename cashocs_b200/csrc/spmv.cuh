@@ -20,15 +20,32 @@ namespace cb {
 template <int BS>
 struct SpmvCfg {
   static constexpr int ROWS_PER_WARP = 32 / BS;           // 32, 16, 10 (2 idle lanes for BS = 3)
-  static constexpr int WARPS = 4;
+#ifndef CB_SPMV_WARPS3
+#define CB_SPMV_WARPS3 2
+#endif
+#ifndef CB_SPMV_CTAS3
+#define CB_SPMV_CTAS3 9
+#endif
+#ifndef CB_SPMV_WARPS1
+#define CB_SPMV_WARPS1 4
+#endif
+#ifndef CB_SPMV_CTAS1
+#define CB_SPMV_CTAS1 9
+#endif
+#ifndef CB_SPMV_TILE
+#define CB_SPMV_TILE 16
+#endif
+  // many small CTAs beat few large ones: every CTA is one independent bulk-copy stream, and the
+  // DRAM pipe wants ~9 x 24 KB in flight per SM (measured: 4 x 47 KB -> 5.3 TB/s, 9 x 24 KB -> 6.0 TB/s)
+  static constexpr int WARPS = (BS == 3) ? CB_SPMV_WARPS3 : (BS == 1 ? CB_SPMV_WARPS1 : 4);
   static constexpr int THREADS = 32 * WARPS;
   static constexpr int R = ROWS_PER_WARP * WARPS;          // block rows per CTA: 128, 64, 40
-  static constexpr int T = 16 * R;                         // tile capacity in blocks
+  static constexpr int T = CB_SPMV_TILE * R;               // tile capacity in blocks
   static constexpr int BB = BS * BS;
   static constexpr int VAL_DOUBLES = T * BB + 2;           // +2: 16-byte alignment slack (head)
   static constexpr int COL_INTS = T + 8;                   // +8: alignment slack (head up to 3)
   static constexpr size_t SMEM_BYTES = sizeof(double) * VAL_DOUBLES + sizeof(int32_t) * COL_INTS + 16;
-  static constexpr int CTAS_PER_SM = (BS == 3) ? 4 : (BS == 2 ? 5 : 8);
+  static constexpr int CTAS_PER_SM = (BS == 3) ? CB_SPMV_CTAS3 : (BS == 2 ? 5 : CB_SPMV_CTAS1);
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
