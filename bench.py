@@ -338,9 +338,10 @@ def main() -> None:
                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_source": "profiles/r01b_ncu_full_k_cg_spmv.csv (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" if traffic else None,
                     "avg_launch_ms": avg_ms, "launches_profiled": spmv_prof, "algorithmic_bytes_per_launch": alg_bytes,
-                    # fine-level launches per PCG iteration: 1 (w = A p) + 2 inside the AMG V(1,1)-cycle
+                    # fine-level launches over A per PCG iteration: w = A p and the residual after pre-smoothing
+                    # (the post-smoothing residual goes through A*P, k_spmv_post)
                     "spmv_share_of_step": (avg_ms * sum(i[2] for i in its) *
-                                           (3 if args.pc == "hypre" else 1)) / ms}
+                                           (2 if args.pc == "hypre" else 1)) / ms}
 
     if rank == 0:
         line = {

@@ -115,6 +115,9 @@ class cb_amg_level(C.Structure):
         ("sendbuf", C.c_void_p),
         ("rep_dist", C.c_void_p),
         ("rep_off", C.c_int64),
+        ("AP", cb_mat),
+        ("coarse_gid", C.c_void_p),
+        ("xc_local", C.c_void_p),
     ]
 
 

@@ -155,13 +155,15 @@ class AMGSymbolic:
                 # agglomeration: below this size halo latency dominates, so the level (and everything
                 # coarser) is replicated on every rank; the restriction all-reduces the rhs instead
                 L.rep_dist, L.rep_nnzb_local = dist, int(col.numel())
-                rowptr, col, L.rep_off, L.rep_pos = self._replicate(rowptr, col, n, ncols, n_glob, dist)
+                rowptr, col, L.rep_off, L.rep_pos, gid = self._replicate(rowptr, col, n, ncols, n_glob, dist)
+                self.levels[-1].coarse_gid = gid.to(torch.int32).contiguous()  # local coarse node -> replicated row
                 n = ncols = n_glob
                 dist = None
             L.n, L.ncols, L.rowptr, L.col, L.dist = n, ncols, rowptr, col, dist
             L.nnzb = int(rowptr[-1].item())
             L.last = True
             L.iface = None
+            L.coarse_gid = None
             self.levels.append(L)
             small = n_glob * 3 <= self.MAX_DENSE
             if small or len(self.levels) >= max_levels:
@@ -296,7 +298,7 @@ class AMGSymbolic:
         pos = inv[start: start + key.numel()].contiguous()
         g_rowptr = _rowptr_from_rows(skeys // n_glob, n_glob)
         g_col = (skeys % n_glob).to(torch.int32).contiguous()
-        return g_rowptr, g_col, off, pos
+        return g_rowptr, g_col, off, pos, gid
 
     @property
     def sizes(self):
@@ -322,6 +324,7 @@ class AMGHierarchy:
         self.distributed = self.levels[0].dist is not None
         self.version = None
         self.power_its = 12
+        self.use_ap = True  # first post-smoothing step through A*P (csrc/spmv.cu k_spmv_post)
         self._power_x: dict = {}
         f64 = dict(dtype=torch.float64, device=dev)
         self.data = []
@@ -344,6 +347,7 @@ class AMGHierarchy:
                 D.p_val = torch.ones(L.p_col.numel(), **f64)  # ghost rows stay 1.0 (tentative)
                 D.pt_val = torch.zeros(L.nnzp_owned, **f64)
                 D.ap_val = torch.zeros(L.ap_col.numel() * bs * bs, **f64)
+                D.xc_local = torch.zeros(L.coarse_gid.numel() * bs, **f64) if L.coarse_gid is not None else None
                 D.s_val = torch.zeros(L.nnzb, **f64) if bs > 1 else None
                 D.s_dinv = torch.zeros(L.n, **f64)
             self.data.append(D)
@@ -496,6 +500,17 @@ class AMGHierarchy:
             if L.rep_dist is not None:
                 e.rep_dist = L.rep_dist.handle
                 e.rep_off = L.rep_off
+            if not L.last and self.use_ap:
+                from cashocs_b200._utils import linalg
+
+                ap = _lib.cb_mat()
+                ap.nrows, ap.ncols, ap.bs = L.n, L.nc + L.gc, self.bs
+                ap.row_split = linalg.row_split_hint(L.ap_col.numel(), L.n)
+                ap.rowptr, ap.col, ap.val = L.ap_rowptr.data_ptr(), L.ap_col.data_ptr(), D.ap_val.data_ptr()
+                e.AP = ap
+                if L.coarse_gid is not None:
+                    e.coarse_gid = L.coarse_gid.data_ptr()
+                    e.xc_local = D.xc_local.data_ptr()
         h = _lib.cb_amg()
         h.nlevels = len(self.levels)
         h.smooth_degree, h.coarse_degree = self.smooth_degree, self.coarse_degree

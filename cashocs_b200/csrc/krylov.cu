@@ -29,6 +29,8 @@ int amg_restrict(cudaStream_t s, int bs, const cb_amg_level* L, const double* b,
 int amg_prolong(cudaStream_t s, int bs, const cb_amg_level* L, const double* xc, double* x, const int* done);
 int amg_dense_apply(cudaStream_t s, int n, const double* inv, const double* b, double* x, const int* done);
 int dist_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs, double* sendbuf);
+int spmv_post_dispatch(cudaStream_t s, const cb_mat* AP, const double* e, double* z, const double* b,
+                       const double* t, const double* dinv, double c2, double* dvec, const int* done);
 int dist_allreduce_sum(cudaStream_t s, cb_dist* d, double* buf, int n);
 int64_t dist_send_len(const cb_dist* d);
 
@@ -253,6 +255,18 @@ k_cheb_step(int64_t n, const double* __restrict__ r, const double* __restrict__ 
     const double di = c1 * dprev + c2 * dinv[i] * (r[i] - t[i]);
     d[i] = di;
     z[i] += di;
+  }
+}
+
+// out[i, :] = in[gid[i], :]  (local copy of a replicated coarse vector in this rank's coarse numbering)
+__global__ void __launch_bounds__(256)
+k_gather_nodes(int64_t n, int bs, const int32_t* __restrict__ gid, const double* __restrict__ in,
+               double* __restrict__ out, const KspState* st) {
+  if (st->done) return;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n * bs;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = q / bs;
+    out[q] = in[(int64_t)gid[i] * bs + (q - i * bs)];
   }
 }
 
@@ -584,7 +598,34 @@ struct Solver {
       double* xl = (l == 0) ? z : lev.x;
       const double* xc = nxt.rep_dist ? nxt.x + nxt.rep_off * bs : nxt.x;
       if (int e = amg_prolong(s, bs, &lev, xc, xl, &st->done)) return e;
-      if (int e = amg_smooth(lev, bl, xl, h->smooth_degree, h->smooth_ratio, false)) return e;
+      if (lev.AP.val) {
+        // first post-smoothing step through A P instead of A (see k_spmv_post): needs the coarse
+        // correction in this rank's coarse numbering (owned + ghost coarse nodes)
+        const double* xcl = nxt.x;
+        if (nxt.rep_dist) {
+          k_gather_nodes<<<grid_for(lev.AP.ncols * bs, 256, 4), 256, 0, s>>>(lev.AP.ncols, bs, lev.coarse_gid, nxt.x,
+                                                                          lev.xc_local, st);
+          CB_LAUNCH_CHECK();
+          xcl = lev.xc_local;
+        } else if (nxt.dist) {
+          if (int e = dist_halo_exchange(s, nxt.dist, nxt.x, bs, nxt.sendbuf)) return e;
+        }
+        const int degree = h->smooth_degree;
+        std::pair<double, double> coef[64];
+        double inv_theta = 0.0;
+        cheb_coefficients(lev.lmax, h->smooth_ratio, degree, inv_theta, coef);
+        if (int e = spmv_post_dispatch(s, &lev.AP, xcl, xl, bl, lev.t, lev.dinv, inv_theta,
+                                       degree > 1 ? lev.d : nullptr, &st->done)) return e;
+        const int64_t nl = lev.A.nrows * bs;
+        for (int j = 1; j < degree; ++j) {
+          if (int e = level_spmv(lev, xl)) return e;
+          k_cheb_step<<<grid_for(nl, 256, 4), 256, 0, s>>>(nl, bl, lev.t, lev.dinv, coef[j].first, coef[j].second,
+                                                          lev.d, xl, st);
+          CB_LAUNCH_CHECK();
+        }
+      } else {
+        if (int e = amg_smooth(lev, bl, xl, h->smooth_degree, h->smooth_ratio, false)) return e;
+      }
     }
     return CB_OK;
   }

@@ -274,6 +274,13 @@ typedef struct {
                              * global operator on every rank, b is all-reduced (sum) over this
                              * communicator after the restriction wrote this rank's rows */
   int64_t rep_off;          /* first node of this rank's rows inside the replicated level */
+  cb_mat AP;                /* A*P of this level (rows: fine nodes, columns: owned + ghost coarse nodes), a
+                             * by-product of the Galerkin product; val == NULL disables its use.  The first
+                             * post-smoothing step computes its residual as b - A x0 - (AP) e instead of
+                             * b - A (x0 + P e): one pass over AP (~1/3 of the bytes of A) */
+  const int32_t* coarse_gid;/* [AP.ncols] position of every local coarse node in the replicated next level
+                             * (only when the next level has rep_dist) */
+  double* xc_local;         /* [AP.ncols*bs] gather buffer for that case */
 } cb_amg_level;
 typedef struct {
   int32_t nlevels;

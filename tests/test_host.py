@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.cb_mat) == 48
     assert ctypes.sizeof(_lib.cb_mesh_view) == 112
     assert ctypes.sizeof(_lib.cb_ksp_opts) == 72
-    assert ctypes.sizeof(_lib.cb_amg_level) == 184
+    assert ctypes.sizeof(_lib.cb_amg_level) == 248
     assert ctypes.sizeof(_lib.cb_amg) == 48
     assert ctypes.sizeof(_lib.cb_ksp_result) == 40
 
