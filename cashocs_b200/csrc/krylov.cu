@@ -29,8 +29,6 @@ int amg_restrict(cudaStream_t s, int bs, const cb_amg_level* L, const double* b,
 int amg_prolong(cudaStream_t s, int bs, const cb_amg_level* L, const double* xc, double* x, const int* done);
 int amg_dense_apply(cudaStream_t s, int n, const double* inv, const double* b, double* x, const int* done);
 int dist_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs, double* sendbuf);
-int spmv_post_dispatch(cudaStream_t s, const cb_mat* AP, const double* e, double* z, const double* b,
-                       const double* t, const double* dinv, double c2, double* dvec, const int* done);
 int dist_allreduce_sum(cudaStream_t s, cb_dist* d, double* buf, int n);
 int64_t dist_send_len(const cb_dist* d);
 
@@ -201,7 +199,8 @@ template <bool FINALIZE>
 __global__ void __launch_bounds__(256)
 k_cg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ w,
         const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
-        double* __restrict__ z, bool fused_jacobi, KspState* st, double* hist, double* scratch) {
+        double* __restrict__ z, bool fused_jacobi, KspState* st, double* hist, double* scratch,
+        const double* __restrict__ pre_dinv = nullptr, double pre_scale = 0.0, double* __restrict__ pre_d = nullptr) {
   if (st->done) return;
   __shared__ double s_red[66];
   const double a = st->beta / st->dpi;
@@ -211,6 +210,11 @@ k_cg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ w,
     x[i] += a * p[i];
     const double ri = r[i] - a * w[i];
     r[i] = ri;
+    if (pre_dinv) {  // fused pre-smoothing of the AMG V-cycle (zero guess): z = dinv .* r / theta
+      const double zi = pre_scale * pre_dinv[i] * ri;
+      z[i] = zi;
+      if (pre_d) pre_d[i] = zi;
+    }
     if (fused_jacobi) {
       const double zi = dinv ? dinv[i] * ri : ri;
       z[i] = zi;
@@ -267,6 +271,57 @@ k_gather_nodes(int64_t n, int bs, const int32_t* __restrict__ gid, const double*
        q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = q / bs;
     out[q] = in[(int64_t)gid[i] * bs + (q - i * bs)];
+  }
+}
+
+// First post-smoothing step of the AMG V-cycle without touching A: after the coarse-grid correction
+// x1 = x0 + P e the residual is  b - A x1 = b - t - (A P) e  with t = A x0 already known, and (A P) --
+// a by-product of the Galerkin product -- has fewer bytes than A.  One pass over AP:
+//   z_i += c2 * dinv_i * (b_i - t_i - (AP e)_i)      [optionally d_i = that increment]
+// z is only touched at the row a lane owns (the gather reads e, the coarse vector): in place.
+// DOTS (fine level, last kernel of the cycle): also sums = (z.b, z.z) for the PCG recurrences.
+template <int BS, bool DOTS>
+__global__ void __launch_bounds__(SpmvCfg<BS>::THREADS)
+k_amg_post(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+           const double* __restrict__ val, const double* __restrict__ e, double* __restrict__ z,
+           const double* __restrict__ b, const double* __restrict__ t, const double* __restrict__ dinv,
+           double c2, double* __restrict__ dvec, KspState* st, double* hist, double* scratch,
+           int finalize_mode /* -1 none, 0 init, 1 iter */) {
+  if (st->done) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SpmvSmem<BS> sm = spmv_smem_init<BS>(smem_raw);
+  uint32_t phase = 0;
+  const int R = spmv_rows_per_cta<BS>(G);
+  const int64_t nrb = (nrows + R - 1) / R;
+  double zr = 0.0, zz = 0.0;
+  for (int64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+    const int64_t row0 = rb * R;
+    const int nr = (int)((nrows - row0 < R) ? (nrows - row0) : R);
+    double acc;
+    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, e, row0, nr, G, phase, acc);
+    if (i >= 0) {
+      const double bi = b[i];
+      const double di = c2 * dinv[i] * (bi - t[i] - acc);
+      if (dvec) dvec[i] = di;
+      const double zi = z[i] + di;
+      z[i] = zi;
+      if (DOTS) { zr += zi * bi; zz += zi * zi; }
+    }
+  }
+  if (DOTS) {
+    // the reduction scratch reuses the (now idle) tile buffer: 9 CTAs x 24.4 KB fill the SM's shared
+    // memory to within 1.4 KB, a static array would cost the ninth resident CTA
+    __syncthreads();
+    double* s_red = reinterpret_cast<double*>(smem_raw);
+    double v[2] = {zr, zz};
+    const int ops[2] = {RED_SUM, RED_SUM};
+    if (grid_reduce<2>(v, ops, scratch, s_red)) {
+      if (threadIdx.x == 0) {
+        st->sums[0] = v[0];
+        st->sums[1] = v[1];
+        if (finalize_mode >= 0) cg_after_zr(st, hist, finalize_mode == 0);
+      }
+    }
   }
 }
 
@@ -540,7 +595,8 @@ struct Solver {
   }
 
   // `degree` Chebyshev-Jacobi steps on A_l x = b (zero or current initial guess); local operator
-  int amg_smooth(const cb_amg_level& L, const double* bl, double* xl, int degree, double ratio, bool zero_guess) {
+  int amg_smooth(const cb_amg_level& L, const double* bl, double* xl, int degree, double ratio, bool zero_guess,
+                 bool first_done = false) {
     const int64_t nl = L.A.nrows * bs;
     int g = grid_for(nl, 256, 4);
     std::pair<double, double> coef[64];
@@ -548,8 +604,10 @@ struct Solver {
     cheb_coefficients(L.lmax, ratio, degree, inv_theta, coef);
     int j0 = 0;
     if (zero_guess) {
-      k_cheb_first<<<g, 256, 0, s>>>(nl, bl, L.dinv, inv_theta, L.d, xl, st);
-      CB_LAUNCH_CHECK();
+      if (!first_done) {  // else: fused into k_cg_xr by the caller
+        k_cheb_first<<<g, 256, 0, s>>>(nl, bl, L.dinv, inv_theta, L.d, xl, st);
+        CB_LAUNCH_CHECK();
+      }
       j0 = 1;
     }
     for (int j = j0; j < degree; ++j) {
@@ -562,9 +620,61 @@ struct Solver {
     return CB_OK;
   }
 
+  template <int BS>
+  int amg_post_bs(const cb_mat* AP, const double* e, double* z, const double* b, const double* t, const double* dinv,
+                  double c2, double* dvec, int dots_mode) {
+    using C = SpmvCfg<BS>;
+    const int G = spmv_sanitize_split(AP->row_split);
+    const int R = spmv_rows_per_cta<BS>(G);
+    const int64_t nrb = (AP->nrows + R - 1) / R;
+    int64_t cap = (int64_t)num_sms() * C::CTAS_PER_SM;
+    if (cap > RED_MAXP) cap = RED_MAXP;
+    const int grid = (int)(nrb < cap ? nrb : cap);
+    static bool configured = false;
+    if (!configured) {
+      const int co = (int)cudaSharedmemCarveoutMaxShared;
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_amg_post<BS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_amg_post<BS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+      configured = true;
+    }
+    if (dots_mode > -2)
+      k_amg_post<BS, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(AP->nrows, G, AP->rowptr, AP->col, AP->val, e, z, b, t,
+                                                                 dinv, c2, dvec, st, hist_dev, scratch, dots_mode);
+    else
+      k_amg_post<BS, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(AP->nrows, G, AP->rowptr, AP->col, AP->val, e, z, b, t,
+                                                                  dinv, c2, dvec, st, hist_dev, scratch, -1);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
+  int amg_post(const cb_mat* AP, const double* e, double* z, const double* b, const double* t, const double* dinv,
+               double c2, double* dvec, int dots_mode) {
+    return AP->bs == 1 ? amg_post_bs<1>(AP, e, z, b, t, dinv, c2, dvec, dots_mode)
+         : AP->bs == 2 ? amg_post_bs<2>(AP, e, z, b, t, dinv, c2, dvec, dots_mode)
+                       : amg_post_bs<3>(AP, e, z, b, t, dinv, c2, dvec, dots_mode);
+  }
+
+  // Fusion hooks of the V-cycle with the PCG loop around it:
+  //  * level-0 pre-smoothing from a zero guess is z = dinv .* r / theta -- k_cg_xr can write it while it
+  //    updates r (amg_presmooth_fusable / presmoothed);
+  //  * with one post-smoothing step through A*P the last kernel of the cycle touches every z_i, so it
+  //    also accumulates z.r and z.z (dots_mode > -2; dots_fused reports whether that happened).
+  bool dots_fused = false;
+  bool amg_presmooth_fusable(const cb_amg* h, const double** dinv0, double* scale, double** d0) const {
+    if (h->nlevels < 2) return false;
+    const cb_amg_level& lev = h->levels[0];
+    std::pair<double, double> coef[64];
+    double inv_theta = 0.0;
+    cheb_coefficients(lev.lmax, h->smooth_ratio, h->smooth_degree, inv_theta, coef);
+    *dinv0 = lev.dinv;
+    *scale = inv_theta;
+    *d0 = h->smooth_degree > 1 ? lev.d : nullptr;
+    return true;
+  }
+
   // z = M^-1 r : one symmetric V-cycle (pre/post Chebyshev smoothing, Chebyshev coarsest solve)
-  int amg_vcycle(const cb_amg* h, const double* r, double* z) {
+  int amg_vcycle(const cb_amg* h, const double* r, double* z, bool presmoothed = false, int dots_mode = -2) {
     const int L = h->nlevels;
+    dots_fused = false;
     for (int l = 0; l < L; ++l) {
       const cb_amg_level& lev = h->levels[l];
       const double* bl = (l == 0) ? r : lev.b;
@@ -577,7 +687,7 @@ struct Solver {
         }
         break;
       }
-      if (int e = amg_smooth(lev, bl, xl, h->smooth_degree, h->smooth_ratio, true)) return e;
+      if (int e = amg_smooth(lev, bl, xl, h->smooth_degree, h->smooth_ratio, true, l == 0 && presmoothed)) return e;
       if (int e = level_spmv(lev, xl)) return e;
       const cb_amg_level& nxt = h->levels[l + 1];
       if (nxt.rep_dist) {
@@ -614,8 +724,10 @@ struct Solver {
         std::pair<double, double> coef[64];
         double inv_theta = 0.0;
         cheb_coefficients(lev.lmax, h->smooth_ratio, degree, inv_theta, coef);
-        if (int e = spmv_post_dispatch(s, &lev.AP, xcl, xl, bl, lev.t, lev.dinv, inv_theta,
-                                       degree > 1 ? lev.d : nullptr, &st->done)) return e;
+        const bool fuse_dots = (l == 0 && degree == 1 && dots_mode > -2);
+        if (int e = amg_post(&lev.AP, xcl, xl, bl, lev.t, lev.dinv, inv_theta, degree > 1 ? lev.d : nullptr,
+                             fuse_dots ? dots_mode : -2)) return e;
+        if (fuse_dots) dots_fused = true;
         const int64_t nl = lev.A.nrows * bs;
         for (int j = 1; j < degree; ++j) {
           if (int e = level_spmv(lev, xl)) return e;
@@ -781,8 +893,14 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
         rho = rho_new;
       }
     }
+    const double* pre_dinv = nullptr;
+    double pre_scale = 0.0;
+    double* pre_d = nullptr;
+    const bool pre_fuse = amg && S.amg_presmooth_fusable(o->amg, &pre_dinv, &pre_scale, &pre_d);
+    bool presmoothed = false;
+    int dots_mode = -2;
     auto apply_cheb = [&]() -> int {  // z = P(r)
-      if (amg) return S.amg_vcycle(o->amg, r, z);
+      if (amg) return S.amg_vcycle(o->amg, r, z, presmoothed, dots_mode);
       k_cheb_first<<<vg, 256, 0, s>>>(n, r, dinv, inv_theta, cd, z, st);
       CB_LAUNCH_CHECK();
       for (int j = 1; j < o->cheb_degree; ++j) {
@@ -802,9 +920,12 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
     } else {
       k_cg_init<true><<<vg, 256, 0, s>>>(n, b, dinv_or_null, r, z, x, false, st, hist_dev, scratch);
       CB_LAUNCH_CHECK();
+      dots_mode = amg ? (dist ? -1 : 0) : -2;
       if ((rc = apply_cheb())) return rc;
-      k_dots_zr<<<vg, 256, 0, s>>>(n, z, r, st, hist_dev, scratch, dist ? -1 : 0);
-      CB_LAUNCH_CHECK();
+      if (!S.dots_fused) {
+        k_dots_zr<<<vg, 256, 0, s>>>(n, z, r, st, hist_dev, scratch, dist ? -1 : 0);
+        CB_LAUNCH_CHECK();
+      }
       if ((rc = S.reduce_and_step(2, 0, false))) return rc;
     }
     int enq = 0;
@@ -819,11 +940,16 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
           CB_LAUNCH_CHECK();
           if ((rc = S.reduce_and_step(2, 1, false))) return rc;
         } else {
-          k_cg_xr<false><<<vg, 256, 0, s>>>(n, p, w, dinv_or_null, x, r, z, false, st, hist_dev, scratch);
+          k_cg_xr<false><<<vg, 256, 0, s>>>(n, p, w, dinv_or_null, x, r, z, false, st, hist_dev, scratch,
+                                            pre_fuse ? pre_dinv : nullptr, pre_scale, pre_d);
           CB_LAUNCH_CHECK();
+          presmoothed = pre_fuse;
+          dots_mode = amg ? (dist ? -1 : 1) : -2;
           if ((rc = apply_cheb())) return rc;
-          k_dots_zr<<<vg, 256, 0, s>>>(n, z, r, st, hist_dev, scratch, dist ? -1 : 1);
-          CB_LAUNCH_CHECK();
+          if (!S.dots_fused) {
+            k_dots_zr<<<vg, 256, 0, s>>>(n, z, r, st, hist_dev, scratch, dist ? -1 : 1);
+            CB_LAUNCH_CHECK();
+          }
           if ((rc = S.reduce_and_step(2, 1, false))) return rc;
         }
       }

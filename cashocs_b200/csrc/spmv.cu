@@ -41,43 +41,6 @@ k_spmv(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32_t* 
   }
 }
 
-// First post-smoothing step of the AMG V-cycle without touching A: after the coarse-grid correction
-// x1 = x0 + P e the residual is  b - A x1 = b - t - (A P) e  with t = A x0 already known, and (A P) --
-// a by-product of the Galerkin product -- has ~3x fewer bytes than A.  One pass over AP:
-//   z_i += c2 * dinv_i * (b_i - t_i - (AP e)_i)      [optionally d_i = that increment]
-// z is only touched at the row a lane owns (the gather reads e, the coarse vector): in place.
-template <int BS>
-__global__ void __launch_bounds__(SpmvCfg<BS>::THREADS)
-k_spmv_post(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-            const double* __restrict__ val, const double* __restrict__ e, double* __restrict__ z,
-            const double* __restrict__ b, const double* __restrict__ t, const double* __restrict__ dinv,
-            double c2, double* __restrict__ dvec, const int* __restrict__ done) {
-  if (done && *done) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SpmvSmem<BS> sm = spmv_smem_init<BS>(smem_raw);
-  uint32_t phase = 0;
-  const int R = spmv_rows_per_cta<BS>(G);
-  const int64_t nrb = (nrows + R - 1) / R;
-  for (int64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
-    const int64_t row0 = rb * R;
-    const int nr = (int)((nrows - row0 < R) ? (nrows - row0) : R);
-    double acc;
-    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, e, row0, nr, G, phase, acc);
-    if (i >= 0) {
-      const double di = c2 * dinv[i] * (b[i] - t[i] - acc);
-      if (dvec) dvec[i] = di;
-      z[i] += di;
-    }
-  }
-}
-
-template <int BS>
-int launch_spmv_post(cudaStream_t s, const cb_mat* AP, const double* e, double* z, const double* b,
-                     const double* t, const double* dinv, double c2, double* dvec, const int* done);
-
-int spmv_post_dispatch(cudaStream_t s, const cb_mat* AP, const double* e, double* z, const double* b,
-                       const double* t, const double* dinv, double c2, double* dvec, const int* done);
-
 __global__ void __launch_bounds__(256)
 k_dot(int64_t n, const double* __restrict__ x, const double* __restrict__ y,
       double* __restrict__ result, double* __restrict__ scratch) {
@@ -160,34 +123,6 @@ int launch_spmv(cudaStream_t s, const cb_mat* A, const double* x, double* y, con
     k_spmv<BS, false, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, A->val, x, nullptr, w, result, scratch, done);
   CB_LAUNCH_CHECK();
   return CB_OK;
-}
-
-template <int BS>
-int launch_spmv_post(cudaStream_t s, const cb_mat* AP, const double* e, double* z, const double* b,
-                     const double* t, const double* dinv, double c2, double* dvec, const int* done) {
-  using C = SpmvCfg<BS>;
-  const int G = spmv_sanitize_split(AP->row_split);
-  const int grid = spmv_grid<BS>(AP->nrows, G);
-  static bool configured = false;
-  if (!configured) {
-    if (int err = prefer_smem(k_spmv_post<BS>)) return err;
-    configured = true;
-  }
-  k_spmv_post<BS><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(AP->nrows, G, AP->rowptr, AP->col, AP->val, e, z, b, t,
-                                                         dinv, c2, dvec, done);
-  CB_LAUNCH_CHECK();
-  return CB_OK;
-}
-
-int spmv_post_dispatch(cudaStream_t s, const cb_mat* AP, const double* e, double* z, const double* b,
-                       const double* t, const double* dinv, double c2, double* dvec, const int* done) {
-  switch (AP->bs) {
-    case 1: return launch_spmv_post<1>(s, AP, e, z, b, t, dinv, c2, dvec, done);
-    case 2: return launch_spmv_post<2>(s, AP, e, z, b, t, dinv, c2, dvec, done);
-    case 3: return launch_spmv_post<3>(s, AP, e, z, b, t, dinv, c2, dvec, done);
-  }
-  set_error("spmv_post: unsupported block size %d", AP->bs);
-  return CB_ERR_UNSUPPORTED;
 }
 
 int diag_inv_launch(cudaStream_t s, const cb_mat* A, double* dinv, double* lmax, double* scratch) {

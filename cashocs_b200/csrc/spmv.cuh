@@ -30,7 +30,7 @@ struct SpmvCfg {
 #define CB_SPMV_WARPS1 4
 #endif
 #ifndef CB_SPMV_CTAS1
-#define CB_SPMV_CTAS1 9
+#define CB_SPMV_CTAS1 8
 #endif
 #ifndef CB_SPMV_TILE
 #define CB_SPMV_TILE 16
