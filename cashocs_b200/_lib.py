@@ -58,6 +58,7 @@ class cb_mesh_view(C.Structure):
         ("v2c_ptr", C.c_void_p),
         ("v2c_idx", C.c_void_p),
         ("cell_scratch", C.c_void_p),
+        ("cell_geo", C.c_void_p),
     ]
 
 

@@ -206,79 +206,95 @@ k_assemble_elasticity(int64_t c_begin, int64_t c_end, const int32_t* __restrict_
 // edge (n2c list, ascending cell id, ~6 cells in a Kuhn mesh), recomputes the cheap cell geometry
 // (cells of neighbouring entries coincide -> L1/L2 hits) and writes the finished d x d block once.
 // No colours, no read-modify-write, one launch; fixed summation order -> bit-reproducible.
+// Per-cell geometry cache for the gather kernels: one 128-byte line per cell,
+//   geo[c] = { G[a][i] (a < D+1, i < D; 12 doubles in 3-D), w0, w1, w2, pad }
+// scalar:     w0 = |K|
+// elasticity: w0 = s |K| mubar, w1 = s |K| lambda, w2 = s delta |K| / ((D+1)(D+2))   (s = cell scale)
+// Written by one streaming pass over the cells (k_cell_geometry); an entry thread then needs 2 G rows
+// and the weights of each incident cell -- 7 to 9 loads from one line -- instead of re-deriving the
+// geometry (12 coordinate gathers, a 3x3 inverse) of ~6 cells per entry.
+constexpr int GEO_STRIDE = 16;
+
 template <int D>
-__device__ __forceinline__ void entry_cell(const int32_t* __restrict__ cells, const double* __restrict__ coords,
-                                           int32_t t, CellData<D>& cd, int& a, int& b, int64_t& c) {
+__global__ void __launch_bounds__(256)
+k_cell_geometry(int64_t nc, const int32_t* __restrict__ cells, const double* __restrict__ coords,
+                const double* __restrict__ mu, double lambda_lame, double damping,
+                const double* __restrict__ cell_scale, double* __restrict__ geo) {
   constexpr int K = D + 1;
-  constexpr int KK = K * K;
-  c = t / KK;
-  const int ab = t - (int32_t)c * KK;
-  a = ab / K;
-  b = ab - a * K;
-  load_cell_data<D>(cells, coords, c, cd);
+  constexpr double MREF = 1.0 / ((D + 1) * (D + 2));
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    CellData<D> cd;
+    load_cell_data<D>(cells, coords, c, cd);
+    double* g = geo + c * GEO_STRIDE;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) g[a * D + i] = cd.g.G[a][i];
+    }
+    const double vol = cd.g.vol;
+    if (mu) {
+      double mubar = 0.0;
+#pragma unroll
+      for (int v = 0; v < K; ++v) mubar += mu[cd.v[v]];
+      mubar *= (1.0 / K);
+      const double scale = cell_scale ? cell_scale[c] : 1.0;
+      g[12] = scale * vol * mubar;
+      g[13] = scale * vol * lambda_lame;
+      g[14] = scale * damping * vol * MREF;
+    } else {
+      g[12] = vol;
+    }
+  }
 }
 
 template <int D>
 __global__ void __launch_bounds__(256)
 k_assemble_elasticity_gather(int64_t nnz, const int64_t* __restrict__ n2c_ptr, const int32_t* __restrict__ n2c_idx,
-                             const int32_t* __restrict__ cells, const double* __restrict__ coords,
-                             const double* __restrict__ mu, double lambda_lame, double damping,
-                             const double* __restrict__ cell_scale, const uint8_t* __restrict__ bc_flag,
-                             double* __restrict__ val) {
+                             const int32_t* __restrict__ cells, const double* __restrict__ geo,
+                             const uint8_t* __restrict__ bc_flag, double* __restrict__ val) {
   constexpr int K = D + 1;
-  constexpr double MREF = 1.0 / ((D + 1) * (D + 2));
+  constexpr int KK = K * K;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz;
        q += (int64_t)gridDim.x * blockDim.x) {
     double acc[D * D];
 #pragma unroll
     for (int i = 0; i < D * D; ++i) acc[i] = 0.0;
     const int64_t kb = n2c_ptr[q], ke = n2c_ptr[q + 1];
+    unsigned bca = 0, bcb = 0;
+    bool diag = false;
     for (int64_t k = kb; k < ke; ++k) {
-      CellData<D> cd;
-      int a, b;
-      int64_t c;
-      entry_cell<D>(cells, coords, __ldg(n2c_idx + k), cd, a, b, c);
-      double mubar = 0.0;
-#pragma unroll
-      for (int v = 0; v < K; ++v) mubar += mu[cd.v[v]];
-      mubar *= (1.0 / K);
-      const double scale = cell_scale ? cell_scale[c] : 1.0;
-      const double vol = cd.g.vol;
-      const double vm = scale * vol * mubar, vl = scale * vol * lambda_lame, dm = scale * damping * vol * MREF;
+      const int32_t t = __ldg(n2c_idx + k);
+      const int64_t c = t / KK;
+      const int ab = t - (int32_t)c * KK;
+      const int a = ab / K, b = ab - a * K;
+      const double* g = geo + c * GEO_STRIDE;
       double Ga[D], Gb[D];
-      int va = 0, vb = 0;
 #pragma unroll
-      for (int v = 0; v < K; ++v) {
-        if (v == a) {
-          va = cd.v[v];
+      for (int i = 0; i < D; ++i) { Ga[i] = g[a * D + i]; Gb[i] = g[b * D + i]; }
+      const double vm = g[12], vl = g[13], dm = g[14];
+      if (k == kb) {
+        diag = (a == b);
+        if (bc_flag) {  // Dirichlet flags of the row vertex / column vertex (the same for every cell)
+          const int64_t va = cells[c * K + a], vb = cells[c * K + b];
 #pragma unroll
-          for (int i = 0; i < D; ++i) Ga[i] = cd.g.G[v][i];
-        }
-        if (v == b) {
-          vb = cd.v[v];
-#pragma unroll
-          for (int i = 0; i < D; ++i) Gb[i] = cd.g.G[v][i];
-        }
-      }
-      unsigned bca = 0, bcb = 0;
-      if (bc_flag) {
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-          if (bc_flag[(int64_t)va * D + i]) bca |= 1u << i;
-          if (bc_flag[(int64_t)vb * D + i]) bcb |= 1u << i;
+          for (int i = 0; i < D; ++i) {
+            if (bc_flag[va * D + i]) bca |= 1u << i;
+            if (bc_flag[vb * D + i]) bcb |= 1u << i;
+          }
         }
       }
       double gg = 0.0;
 #pragma unroll
       for (int i = 0; i < D; ++i) gg += Ga[i] * Gb[i];
-      const double mass = (a == b) ? 2.0 * dm : dm;
+      const double mass = diag ? 2.0 * dm : dm;
 #pragma unroll
       for (int i = 0; i < D; ++i) {
 #pragma unroll
         for (int j = 0; j < D; ++j) {
           double e = vm * Ga[j] * Gb[i] + vl * Ga[i] * Gb[j];
           if (i == j) e += vm * gg + mass;
-          if (((bca >> i) & 1u) || ((bcb >> j) & 1u)) e = (a == b && i == j) ? 1.0 : 0.0;
+          if (((bca >> i) & 1u) || ((bcb >> j) & 1u)) e = (diag && i == j) ? 1.0 : 0.0;
           acc[i * D + j] += e;
         }
       }
@@ -292,38 +308,31 @@ k_assemble_elasticity_gather(int64_t nnz, const int64_t* __restrict__ n2c_ptr, c
 template <int D>
 __global__ void __launch_bounds__(256)
 k_assemble_scalar_gather(int64_t nnz, const int64_t* __restrict__ n2c_ptr, const int32_t* __restrict__ n2c_idx,
-                         const int32_t* __restrict__ cells, const double* __restrict__ coords, double c_stiff,
+                         const int32_t* __restrict__ cells, const double* __restrict__ geo, double c_stiff,
                          double c_mass, const uint8_t* __restrict__ bc_flag, double* __restrict__ val) {
   constexpr int K = D + 1;
+  constexpr int KK = K * K;
   constexpr double MREF = 1.0 / ((D + 1) * (D + 2));
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz;
        q += (int64_t)gridDim.x * blockDim.x) {
     double acc = 0.0;
     const int64_t kb = n2c_ptr[q], ke = n2c_ptr[q + 1];
+    bool isbc = false, diag = false;
     for (int64_t k = kb; k < ke; ++k) {
-      CellData<D> cd;
-      int a, b;
-      int64_t c;
-      entry_cell<D>(cells, coords, __ldg(n2c_idx + k), cd, a, b, c);
+      const int32_t t = __ldg(n2c_idx + k);
+      const int64_t c = t / KK;
+      const int ab = t - (int32_t)c * KK;
+      const int a = ab / K, b = ab - a * K;
+      const double* g = geo + c * GEO_STRIDE;
+      if (k == kb) {
+        diag = (a == b);
+        if (bc_flag) isbc = bc_flag[cells[c * K + a]] || bc_flag[cells[c * K + b]];
+      }
       double gg = 0.0;
-      int va = 0, vb = 0;
 #pragma unroll
-      for (int v = 0; v < K; ++v) {
-        if (v == a) va = cd.v[v];
-        if (v == b) vb = cd.v[v];
-      }
-#pragma unroll
-      for (int v = 0; v < K; ++v) {
-#pragma unroll
-        for (int w = 0; w < K; ++w) {
-          if (v == a && w == b) {
-#pragma unroll
-            for (int i = 0; i < D; ++i) gg += cd.g.G[v][i] * cd.g.G[w][i];
-          }
-        }
-      }
-      double e = cd.g.vol * (c_stiff * gg + c_mass * (a == b ? 2.0 * MREF : MREF));
-      if (bc_flag && (bc_flag[va] || bc_flag[vb])) e = (a == b) ? 1.0 : 0.0;
+      for (int i = 0; i < D; ++i) gg += g[a * D + i] * g[b * D + i];
+      double e = g[12] * (c_stiff * gg + c_mass * (diag ? 2.0 * MREF : MREF));
+      if (isbc) e = diag ? 1.0 : 0.0;
       acc += e;
     }
     val[q] = acc;
@@ -462,15 +471,21 @@ extern "C" int cb_assemble_scalar(void* stream, const cb_mesh_view* m, double c_
   CB_REQUIRE(s_nodal == 0.0 || fnodal, "nodal source missing");
   CB_REQUIRE(bc_flag == nullptr || bc_val != nullptr, "bc_val missing");
   cudaStream_t s = as_stream(stream);
-  if (val && m->n2c_ptr && m->n2c_idx && m->cells_orig) {
-    // matrix by gather (one launch); the rhs (with the BC lifting) keeps the coloured cell loop
-    const int grid = grid_for(m->nnz, 256, 8);
-    if (m->dim == 2)
-      k_assemble_scalar_gather<2><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->coords,
+  if (val && m->n2c_ptr && m->n2c_idx && m->cells_orig && m->cell_geo) {
+    // matrix by gather: geometry cache pass + one thread per nnz entry
+    const int64_t nc = m->colour_off[m->ncolours];
+    const int cgrid = grid_for(nc, 256, 8), grid = grid_for(m->nnz, 256, 8);
+    if (m->dim == 2) {
+      k_cell_geometry<2><<<cgrid, 256, 0, s>>>(nc, m->cells_orig, m->coords, nullptr, 0.0, 0.0, nullptr, m->cell_geo);
+      CB_LAUNCH_CHECK();
+      k_assemble_scalar_gather<2><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->cell_geo,
                                                       c_stiff, c_mass, bc_flag, val);
-    else
-      k_assemble_scalar_gather<3><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->coords,
+    } else {
+      k_cell_geometry<3><<<cgrid, 256, 0, s>>>(nc, m->cells_orig, m->coords, nullptr, 0.0, 0.0, nullptr, m->cell_geo);
+      CB_LAUNCH_CHECK();
+      k_assemble_scalar_gather<3><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->cell_geo,
                                                       c_stiff, c_mass, bc_flag, val);
+    }
     CB_LAUNCH_CHECK();
     val = nullptr;
     if (!rhs) return CB_OK;
@@ -523,14 +538,18 @@ extern "C" int cb_assemble_elasticity(void* stream, const cb_mesh_view* m, const
   if (int e = check_view(m)) return e;
   CB_REQUIRE(m->cell2nnz && mu && val, "cell2nnz / mu / val missing");
   cudaStream_t s = as_stream(stream);
-  if (m->n2c_ptr && m->n2c_idx && m->cells_orig) {
-    const int grid = grid_for(m->nnz, 256, 8);
-    if (m->dim == 2)
-      k_assemble_elasticity_gather<2><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->coords, mu,
-                                                          lambda_lame, damping, cell_scale, bc_flag, val);
-    else
-      k_assemble_elasticity_gather<3><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->coords, mu,
-                                                          lambda_lame, damping, cell_scale, bc_flag, val);
+  if (m->n2c_ptr && m->n2c_idx && m->cells_orig && m->cell_geo) {
+    const int64_t nc = m->colour_off[m->ncolours];
+    const int cgrid = grid_for(nc, 256, 8), grid = grid_for(m->nnz, 256, 8);
+    if (m->dim == 2) {
+      k_cell_geometry<2><<<cgrid, 256, 0, s>>>(nc, m->cells_orig, m->coords, mu, lambda_lame, damping, cell_scale, m->cell_geo);
+      CB_LAUNCH_CHECK();
+      k_assemble_elasticity_gather<2><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->cell_geo, bc_flag, val);
+    } else {
+      k_cell_geometry<3><<<cgrid, 256, 0, s>>>(nc, m->cells_orig, m->coords, mu, lambda_lame, damping, cell_scale, m->cell_geo);
+      CB_LAUNCH_CHECK();
+      k_assemble_elasticity_gather<3><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->cell_geo, bc_flag, val);
+    }
     CB_LAUNCH_CHECK();
     return CB_OK;
   }

@@ -53,6 +53,7 @@ class Mesh:
         self._pattern_ready = False
         self.scratch = None
         self.cell_scratch = None
+        self.cell_geo = None
         self.boundary_facets: dict[int, torch.Tensor] | None = None  # tagged facets (imported meshes)
         self._p2_space = None
 
@@ -167,6 +168,9 @@ class Mesh:
             v.v2c_ptr = self.v2c_ptr.data_ptr()
             v.v2c_idx = self.v2c_idx.data_ptr()
             v.cell_scratch = self.cell_scratch.data_ptr()
+            if self.cell_geo is None:
+                self.cell_geo = torch.empty(self.num_cells * 16, dtype=torch.float64, device=self.device)
+            v.cell_geo = self.cell_geo.data_ptr()
         return v
 
 

@@ -127,6 +127,7 @@ typedef struct {
   const int64_t* v2c_ptr;    /* [nv+1] */
   const int32_t* v2c_idx;    /* [nc*(dim+1)] */
   double* cell_scratch;
+  double* cell_geo;          /* [nc * 16] per-cell geometry cache of the gather matrix kernels (scratch) */
 } cb_mesh_view;
 
 /* Scalar P1:  A = c_stiff*K + c_mass*M ;  rhs = s_poly*int(f phi) + s_nodal*M fnodal.
