@@ -319,7 +319,7 @@ def main() -> None:
     # DRAM traffic of the same kernel from the committed `ncu --set full` capture (per launch; only
     # valid for the workload it was captured on: n = 119 on one GPU)
     traffic = None
-    cap = os.path.join(ROOT, "profiles", "r01b_ncu_full_k_cg_spmv.csv")
+    cap = os.path.join(ROOT, "profiles", "r01c_ncu_full_k_cg_spmv.csv")
     if args.n == 119 and world == 1 and os.path.exists(cap):
         rd = wr = None
         for row in open(cap):
@@ -336,7 +336,7 @@ def main() -> None:
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_cg_spmv<3> (elasticity PCG: w = A p, fused p.w)", "achieved": achieved,
                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "traffic_source": "profiles/r01b_ncu_full_k_cg_spmv.csv (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" if traffic else None,
+                    "traffic_source": "profiles/r01c_ncu_full_k_cg_spmv.csv (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" if traffic else None,
                     "avg_launch_ms": avg_ms, "launches_profiled": spmv_prof, "algorithmic_bytes_per_launch": alg_bytes,
                     # fine-level launches over A per PCG iteration: w = A p and the residual after pre-smoothing
                     # (the post-smoothing residual goes through A*P, k_spmv_post)
