@@ -350,3 +350,40 @@ def test_gather_and_scatter_assembly_agree(kind):
         linalg.USE_GATHER_ASSEMBLY = True
     for x, y in zip(out[True], out[False]):
         assert float((x - y).abs().max() / y.abs().max()) < 1e-13
+
+
+def test_degenerate_inputs():
+    """Smallest meshes and degenerate data: one cell, all-Dirichlet systems, zero right-hand sides, NaNs."""
+    tri = cb.mesh_from_arrays(np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]), np.array([[0, 1, 2]]),
+                              np.array([[0, 1], [1, 2], [0, 2]]), np.array([1, 2, 3]))
+    tet = cb.mesh_from_arrays(np.array([[0.0, 0, 0], [1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0]]), np.array([[0, 1, 2, 3]]),
+                              np.array([[0, 1, 2], [0, 1, 3], [0, 2, 3], [1, 2, 3]]), np.array([1, 2, 3, 4]))
+    for m, vol in ((tri, 0.5), (tet, 1.0 / 6.0)):
+        d = m.dim
+        M, b = linalg.assemble_scalar_system(m, 0.0, 1.0, f_poly=cb.spatial_coordinate(d)[0] * 0.0 + 1.0)
+        assert M.nnzb == (d + 1) ** 2 and abs(float(M.val.sum()) - vol) < 1e-15 and abs(float(b.sum()) - vol) < 1e-15
+        assert cb.compute_mesh_quality(m, "min", "skewness") > 0.0
+        assert cb.IntersectionTester(m).test()
+        # every dof Dirichlet: identity system, solution = boundary value, zero iterations needed
+        flag, val = forms.bc_flag_arrays(m, [cb.DirichletBC(2.5, tuple(m.boundary_markers))], 1)
+        A, rhs = linalg.assemble_scalar_system(m, 1.0, 0.0, bc_flag=flag, bc_val=val)
+        x = torch.zeros(m.num_vertices, dtype=torch.float64, device="cuda")
+        cb.LinearSolver().solve(x, A=A, b=rhs, ksp_options={"ksp_type": "cg", "pc_type": "jacobi"})
+        assert float((x - 2.5).abs().max()) < 1e-14
+        # zero right-hand side: PETSc returns x = 0 with CONVERGED_ATOL
+        res = cb.LinearSolver().solve(x, A=A, b=torch.zeros_like(rhs), ksp_options={"ksp_type": "cg", "pc_type": "jacobi"})
+        assert res.reason > 0 and float(x.abs().max()) == 0.0
+        # P2 space of a single cell
+        sp2 = m.p2_space()
+        assert sp2.ndofs == (d + 1) + (3 if d == 2 else 6) and sp2.nnz == sp2.ndofs**2
+    # NaN coordinates: mesh measures propagate NaN (never silently pass a threshold), Krylov reports -9
+    bad = cb.regular_mesh(3)
+    bad.coords[5, 0] = float("nan")
+    assert np.isnan(cb.compute_mesh_quality(bad, "min", "skewness"))
+    V = torch.zeros(bad.num_vertices * 2, dtype=torch.float64, device="cuda")
+    assert not cb.APrioriMeshTester(bad).test(V, float("inf"))
+    A, b = linalg.assemble_scalar_system(bad, 1.0, 1.0, f_poly=cb.spatial_coordinate(2)[0])
+    x = torch.zeros(bad.num_vertices, dtype=torch.float64, device="cuda")
+    with pytest.raises(cb.PETScKSPError) as e:
+        cb.LinearSolver().solve(x, A=A, b=b, ksp_options={"ksp_type": "cg", "pc_type": "jacobi"})
+    assert e.value.error_code == -9
