@@ -148,7 +148,7 @@ class cb_ksp_opts(C.Structure):
         ("check_every", C.c_int32),
         ("monitor", C.c_int32),
         ("profile_every", C.c_int32),
-        ("pad", C.c_int32),
+        ("use_graph", C.c_int32),
         ("amg", C.c_void_p),
     ]
 

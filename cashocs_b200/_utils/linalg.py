@@ -104,7 +104,7 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None, distr
         )
     known = {"ksp_type", "pc_type", "ksp_rtol", "ksp_atol", "ksp_divtol", "ksp_max_it",
              "pc_chebyshev_degree", "pc_chebyshev_ratio", "ksp_check_every", "ksp_ksp_type",
-             "ksp_ksp_max_it", "ksp_pc_type", "ksp_profile_every", "pc_amg_smooth_degree",
+             "ksp_ksp_max_it", "ksp_pc_type", "ksp_profile_every", "ksp_use_graph", "pc_amg_smooth_degree",
              "pc_amg_coarse_degree", "pc_amg_smooth_ratio", "pc_amg_coarse_ratio", "pc_amg_min_coarse",
              "pc_gamg_type", "pc_gamg_agg_nsmooths"} | _IGNORED_KEYS
     unknown = set(opts) - known
@@ -124,6 +124,7 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None, distr
     o.check_every = int(opts.get("ksp_check_every", 0))
     o.monitor = 1 if ("ksp_monitor" in opts) else 0
     o.profile_every = int(opts.get("ksp_profile_every", 0))
+    o.use_graph = int(opts.get("ksp_use_graph", 0))
     return o
 
 

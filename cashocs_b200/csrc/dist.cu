@@ -85,7 +85,6 @@ struct cb_dist {
   unsigned char* window = nullptr;                 // my window (cudaMalloc, exported by IPC)
   std::vector<unsigned char*> peer_window;         // [nranks] mapped peer windows (self = window)
   int64_t ghost_cap = 0;                           // doubles per parity of the landing zone
-  unsigned long long halo_epoch = 0, red_epoch = 0;
   // device copies of the plan for the put kernel
   int64_t* d_send_off = nullptr;                   // [nneigh+1]
   int64_t* d_remote_off = nullptr;                 // [nneigh] node offset of my data in the peer's ghost range
@@ -158,7 +157,11 @@ k_halo_put(int nneigh, const int64_t* __restrict__ send_off, const int64_t* __re
            const int32_t* __restrict__ neigh, const int32_t* __restrict__ send_idx,
            const int64_t* __restrict__ remote_cap, const double* __restrict__ x,
            unsigned char* const* __restrict__ peer_window, WindowLayout lay, int myrank,
-           unsigned long long epoch, unsigned char* my_window) {
+           unsigned char* my_window) {
+  // the exchange epoch lives in the window (not in a kernel argument) so that a captured CUDA graph
+  // can replay the exchange: every thread reads it here, the last block bumps it at the end
+  unsigned long long* hdr = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(my_window) + lay.flags_off());
+  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(hdr + 2 * lay.nranks + 2) + 1ULL;
   const int64_t nsend = send_off[nneigh];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nsend * BS;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -184,15 +187,17 @@ k_halo_put(int nneigh, const int64_t* __restrict__ send_off, const int64_t* __re
         reinterpret_cast<double*>(peer_window[neigh[threadIdx.x]]) + lay.flags_off());
     st_release_sys(pf + myrank, epoch);
   }
+  if (last && threadIdx.x == 0) hdr[2 * lay.nranks + 2] = epoch;
 }
 
 template <int BS>
 __global__ void __launch_bounds__(256)
 k_halo_get(int nneigh, const int64_t* __restrict__ recv_off, const int32_t* __restrict__ neigh,
            double* __restrict__ x, int64_t n_owned, unsigned char* my_window, WindowLayout lay,
-           int64_t ghost_cap, unsigned long long epoch) {
+           int64_t ghost_cap) {
   unsigned long long* flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(my_window) + lay.flags_off());
   unsigned long long* error = flags + 2 * lay.nranks + 1;
+  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(flags + 2 * lay.nranks + 2);
   __shared__ int ok;
   if (threadIdx.x == 0) ok = 1;
   __syncthreads();
@@ -210,21 +215,26 @@ k_halo_get(int nneigh, const int64_t* __restrict__ recv_off, const int32_t* __re
 // all-reduce of n <= RED_W doubles: every rank writes its message into every rank's slots, then sums
 // the nranks messages in rank order (bit-identical on all ranks, deterministic)
 __global__ void k_red_put(int n, const double* __restrict__ buf, unsigned char* const* __restrict__ peer_window,
-                          WindowLayout lay, int myrank, unsigned long long epoch) {
+                          WindowLayout lay, int myrank, unsigned char* my_window) {
+  unsigned long long* hdr = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(my_window) + lay.flags_off());
+  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(hdr + 2 * lay.nranks + 3) + 1ULL;
+  __syncthreads();  // everybody has read the epoch before thread 0 bumps it
   const int r = threadIdx.x;
-  if (r >= lay.nranks) return;
-  double* slots = reinterpret_cast<double*>(peer_window[r]) + lay.red_off() +
-                  ((int64_t)(epoch & 1ULL) * lay.nranks + myrank) * RED_W;
-  for (int i = 0; i < n; ++i) slots[i] = buf[i];
-  __threadfence_system();
-  unsigned long long* pf = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(peer_window[r]) + lay.flags_off());
-  st_release_sys(pf + lay.nranks + myrank, epoch);
+  if (r < lay.nranks) {
+    double* slots = reinterpret_cast<double*>(peer_window[r]) + lay.red_off() +
+                    ((int64_t)(epoch & 1ULL) * lay.nranks + myrank) * RED_W;
+    for (int i = 0; i < n; ++i) slots[i] = buf[i];
+    __threadfence_system();
+    unsigned long long* pf = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(peer_window[r]) + lay.flags_off());
+    st_release_sys(pf + lay.nranks + myrank, epoch);
+  }
+  if (threadIdx.x == 0) hdr[2 * lay.nranks + 3] = epoch;
 }
 
-__global__ void k_red_get(int n, double* __restrict__ buf, unsigned char* my_window, WindowLayout lay,
-                          unsigned long long epoch, int op) {
+__global__ void k_red_get(int n, double* __restrict__ buf, unsigned char* my_window, WindowLayout lay, int op) {
   unsigned long long* flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(my_window) + lay.flags_off());
   unsigned long long* error = flags + 2 * lay.nranks + 1;
+  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(flags + 2 * lay.nranks + 3);
   __shared__ int ok;
   if (threadIdx.x == 0) ok = 1;
   __syncthreads();
@@ -248,7 +258,6 @@ __global__ void k_red_get(int n, double* __restrict__ buf, unsigned char* my_win
 static int p2p_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs) {
   const int nneigh = (int)d->neigh.size();
   const WindowLayout lay{d->nranks};
-  const unsigned long long epoch = ++d->halo_epoch;
   const int64_t nsend = d->send_off.back(), nrecv = d->recv_off.back();
   if (nrecv * bs > d->ghost_cap) {
     set_error("p2p halo exchange: landing zone too small");
@@ -258,10 +267,10 @@ static int p2p_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs) {
   const int ggrid = grid_for(nrecv * bs > 0 ? nrecv * bs : 1, 256, 2);
 #define CB_HALO(BS)                                                                                          \
   k_halo_put<BS><<<pgrid, 256, 0, s>>>(nneigh, d->d_send_off, d->d_remote_off, d->d_neigh, d->send_idx,      \
-                                       d->d_remote_cap, x, d->d_peer_window, lay, d->rank, epoch, d->window); \
+                                       d->d_remote_cap, x, d->d_peer_window, lay, d->rank, d->window);        \
   CB_LAUNCH_CHECK();                                                                                         \
   k_halo_get<BS><<<ggrid, 256, 0, s>>>(nneigh, d->d_recv_off, d->d_neigh, x, d->n_owned, d->window, lay,     \
-                                       d->ghost_cap, epoch);                                                 \
+                                       d->ghost_cap);                                                        \
   CB_LAUNCH_CHECK();
   if (bs == 1) { CB_HALO(1) } else if (bs == 2) { CB_HALO(2) } else { CB_HALO(3) }
 #undef CB_HALO
@@ -270,10 +279,9 @@ static int p2p_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs) {
 
 static int p2p_allreduce(cudaStream_t s, cb_dist* d, double* buf, int n, int op) {
   const WindowLayout lay{d->nranks};
-  const unsigned long long epoch = ++d->red_epoch;
-  k_red_put<<<1, 32, 0, s>>>(n, buf, d->d_peer_window, lay, d->rank, epoch);
+  k_red_put<<<1, 32, 0, s>>>(n, buf, d->d_peer_window, lay, d->rank, d->window);
   CB_LAUNCH_CHECK();
-  k_red_get<<<1, 32, 0, s>>>(n, buf, d->window, lay, epoch, op);
+  k_red_get<<<1, 32, 0, s>>>(n, buf, d->window, lay, op);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }

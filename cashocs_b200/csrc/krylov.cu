@@ -518,8 +518,9 @@ struct Solver {
   int profile_every = 0, spmv_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
 
+  bool capturing = false;  // inside a CUDA-graph capture: no event timing
   bool prof_begin() {
-    const bool on = profile_every > 0 && (spmv_launches % profile_every) == 0 && prof.size() < 1024;
+    const bool on = !capturing && profile_every > 0 && (spmv_launches % profile_every) == 0 && prof.size() < 1024;
     ++spmv_launches;
     if (!on) return false;
     cudaEvent_t a, b;
@@ -928,34 +929,86 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
       }
       if ((rc = S.reduce_and_step(2, 0, false))) return rc;
     }
-    int enq = 0;
-    while (true) {
-      for (int c = 0; c < check_every && enq < o->max_it; ++c, ++enq) {
-        k_cg_p<<<vg, 256, 0, s>>>(n, z, p, st);
+    // one PCG iteration; every argument is iteration-independent, so the body can be captured once
+    // into a CUDA graph and replayed (the one-sided halo / all-reduce kernels keep their epochs in
+    // device memory for exactly that reason)
+    auto iteration = [&]() -> int {
+      k_cg_p<<<vg, 256, 0, s>>>(n, z, p, st);
+      CB_LAUNCH_CHECK();
+      if (int e = S.cg_spmv(p, w)) return e;
+      if (!cheb) {
+        if (dist) k_cg_xr<false><<<vg, 256, 0, s>>>(n, p, w, dinv_or_null, x, r, z, true, st, hist_dev, scratch);
+        else k_cg_xr<true><<<vg, 256, 0, s>>>(n, p, w, dinv_or_null, x, r, z, true, st, hist_dev, scratch);
         CB_LAUNCH_CHECK();
-        if ((rc = S.cg_spmv(p, w))) return rc;
-        if (!cheb) {
-          if (dist) k_cg_xr<false><<<vg, 256, 0, s>>>(n, p, w, dinv_or_null, x, r, z, true, st, hist_dev, scratch);
-          else k_cg_xr<true><<<vg, 256, 0, s>>>(n, p, w, dinv_or_null, x, r, z, true, st, hist_dev, scratch);
+        if (int e = S.reduce_and_step(2, 1, false)) return e;
+      } else {
+        k_cg_xr<false><<<vg, 256, 0, s>>>(n, p, w, dinv_or_null, x, r, z, false, st, hist_dev, scratch,
+                                          pre_fuse ? pre_dinv : nullptr, pre_scale, pre_d);
+        CB_LAUNCH_CHECK();
+        presmoothed = pre_fuse;
+        dots_mode = amg ? (dist ? -1 : 1) : -2;
+        if (int e = apply_cheb()) return e;
+        if (!S.dots_fused) {
+          k_dots_zr<<<vg, 256, 0, s>>>(n, z, r, st, hist_dev, scratch, dist ? -1 : 1);
           CB_LAUNCH_CHECK();
-          if ((rc = S.reduce_and_step(2, 1, false))) return rc;
-        } else {
-          k_cg_xr<false><<<vg, 256, 0, s>>>(n, p, w, dinv_or_null, x, r, z, false, st, hist_dev, scratch,
-                                            pre_fuse ? pre_dinv : nullptr, pre_scale, pre_d);
-          CB_LAUNCH_CHECK();
-          presmoothed = pre_fuse;
-          dots_mode = amg ? (dist ? -1 : 1) : -2;
-          if ((rc = apply_cheb())) return rc;
-          if (!S.dots_fused) {
-            k_dots_zr<<<vg, 256, 0, s>>>(n, z, r, st, hist_dev, scratch, dist ? -1 : 1);
-            CB_LAUNCH_CHECK();
+        }
+        if (int e = S.reduce_and_step(2, 1, false)) return e;
+      }
+      return CB_OK;
+    };
+    const bool want_graph = o->use_graph >= 0;
+    // chunks run eagerly before the capture: warm-up (lazy kernel attributes, NCCL buffers) and, when
+    // the SpMV launches are being timed with events, enough of them for a sample
+    const int eager_chunks = o->profile_every > 0 ? (2 * o->profile_every + check_every - 1) / check_every : 1;
+    cudaGraphExec_t gexec = nullptr;
+    long long graph_kernels = 0;
+    int enq = 0, chunk = 0;
+    while (true) {
+      if (want_graph && chunk >= eager_chunks) {
+        if (!gexec) {
+          // capture on a private stream (the caller's may be the legacy default stream, which cannot
+          // be captured); the launches go to `s` / `S.s`, so both are redirected for the capture
+          cudaGraph_t graph = nullptr;
+          const long long before = g_launch_count;
+          cudaStream_t user_stream = s, cs = nullptr;
+          CB_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+          S.capturing = true;
+          s = cs;
+          S.s = cs;
+          cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+          int brc = CB_OK;
+          if (ce == cudaSuccess) {
+            brc = iteration();
+            ce = cudaStreamEndCapture(cs, &graph);
           }
-          if ((rc = S.reduce_and_step(2, 1, false))) return rc;
+          s = user_stream;
+          S.s = user_stream;
+          S.capturing = false;
+          cudaStreamDestroy(cs);
+          graph_kernels = g_launch_count - before;
+          g_launch_count = before;
+          if (brc) { if (graph) cudaGraphDestroy(graph); return brc; }
+          CB_CUDA_CHECK(ce);
+          const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
+          cudaGraphDestroy(graph);
+          CB_CUDA_CHECK(ie);
+        }
+        for (int c = 0; c < check_every && enq < o->max_it; ++c, ++enq) {
+          const cudaError_t le = cudaGraphLaunch(gexec, s);
+          if (le != cudaSuccess) { cudaGraphExecDestroy(gexec); CB_CUDA_CHECK(le); }
+          g_launch_count += graph_kernels;
+          S.spmv_launches += 1;
+        }
+      } else {
+        for (int c = 0; c < check_every && enq < o->max_it; ++c, ++enq) {
+          if ((rc = iteration())) return rc;
         }
       }
-      if ((rc = poll())) return rc;
+      ++chunk;
+      if ((rc = poll())) { if (gexec) cudaGraphExecDestroy(gexec); return rc; }
       if (hs.done || enq >= o->max_it) break;
     }
+    if (gexec) cudaGraphExecDestroy(gexec);
   } else if (o->ksp_type == CB_KSP_MINRES) {
     CB_REQUIRE(o->pc_type != CB_PC_CHEBYSHEV, "minres supports pc_type none / jacobi");
     // rotating roles: (r1, r2, y) and (w1, w2, w)
