@@ -224,7 +224,7 @@ def main() -> None:
     ap.add_argument("--pc", default="hypre", choices=["hypre", "jacobi"],
                     help="pc_type of the three Krylov solves (hypre -> device smoothed-aggregation AMG on 1 GPU)")
     ap.add_argument("--state-degree", type=int, default=1, choices=[1, 2],
-                    help="CG degree of the state / adjoint space (2 = BASELINE configs[4]; one GPU)")
+                    help="CG degree of the state / adjoint space (2 = BASELINE configs[4])")
     ap.add_argument("--graph", type=int, default=0, choices=[-1, 0, 1],
                     help="CUDA-graph replay of the PCG iteration: 0 / 1 on (default), -1 eager launches only")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -45,7 +45,7 @@ class Function:
 
     def owned(self) -> torch.Tensor:
         if self.degree == 2:
-            return self.vector
+            return self.vector[: self.space.n_owned_dofs]
         return self.vector[: self.mesh.n_owned_vertices * self.value_size]
 
     def assign(self, other) -> None:

@@ -11,7 +11,8 @@ element.  The object quacks like a mesh for :class:`cashocs_b200.Matrix` (``rowp
 
 The deformation space stays vector P1 (the reference forces it,
 ``cashocs/_optimization/shape_optimization/shape_optimization_problem.py:251-256``); P2 is the space
-of the states and adjoints.  One GPU for now (the partitioned P2 dofmap is the next row).
+of the states and adjoints.  On a partitioned mesh the space carries its own halo plan over vertex +
+edge dofs (``p2_numbering``).
 """
 
 from __future__ import annotations
@@ -45,49 +46,150 @@ def p2_basis(lam: np.ndarray):
     return phi, dphi
 
 
+def p2_numbering(mesh):
+    """Dof numbering of the scalar P2 space on a (partition of a) mesh -- pure index plumbing, runs on
+    CPU tensors too (``tests/test_distributed_cpu.py``).
+
+    Local edges are the unique vertex pairs of the local cells.  One GPU: dof = vertex, then
+    ``nv + edge``.  Partitioned mesh: an edge is owned by the owner of its end point with the smaller
+    *global* id, so every cell around an owned edge is a local cell (local cells = all cells touching an
+    owned vertex) and owned rows assemble without communication.  Numbering: owned vertices, owned
+    edges (by global key), then the ghosts grouped by owner -- per owner its ghost vertices (vertex-plan
+    order) followed by its ghost edges (by global key) -- which is the layout the halo plan needs.
+
+    Returns a dict: ``edges`` [ne, 2] (local vertex ids, lower first), ``cell_dofs`` [nc, nde] int32,
+    ``vertex_dof`` [nv], ``edge_dof`` [ne], ``ndofs``, ``n_owned``, ``dist`` (dof halo plan or None) and,
+    on a partitioned mesh, ``edge_gkey`` [ne, 2] (global end points, lower first).
+    """
+    import torch.distributed as td
+
+    d = mesh.dim
+    k = d + 1
+    loc = LOCAL_EDGES[d]
+    nv, nc = mesh.num_vertices, mesh.num_cells
+    dev = mesh.cells.device
+    cells = mesh.cells.long()
+    a = torch.stack([cells[:, i] for i, _ in loc], dim=1)
+    b = torch.stack([cells[:, j] for _, j in loc], dim=1)
+    lo, hi = torch.minimum(a, b), torch.maximum(a, b)
+    uniq, inv = torch.unique((lo * nv + hi).reshape(-1), return_inverse=True)
+    edges = torch.stack([uniq // nv, uniq % nv], dim=1)
+    ne = int(uniq.numel())
+    cell_edges = inv.view(nc, len(loc))
+    dist = mesh.dist
+    if dist is None:
+        vertex_dof = torch.arange(nv, device=dev)
+        edge_dof = nv + torch.arange(ne, device=dev)
+        out = dict(edges=edges, vertex_dof=vertex_dof, edge_dof=edge_dof, ndofs=nv + ne, n_owned=nv + ne, dist=None)
+    else:
+        from cashocs_b200 import distributed
+
+        n_ov = mesh.n_owned_vertices
+        gid = mesh.global_vertex_ids.to(dev)
+        ga, gb = gid[edges[:, 0]], gid[edges[:, 1]]
+        glo, ghi = torch.minimum(ga, gb), torch.maximum(ga, gb)
+        off_t = torch.as_tensor(mesh.global_offsets, device=dev)
+        owner = torch.searchsorted(off_t, glo, right=True) - 1
+        nglob = int(off_t[-1].item())
+        gkey = glo * nglob + ghi
+        mine = owner == dist.rank
+        own_idx = torch.nonzero(mine).reshape(-1)
+        own_idx = own_idx[torch.argsort(gkey[own_idx])]
+        n_oe = int(own_idx.numel())
+        # ghost edges per neighbour (sorted by global key); what I need from each owner
+        need = {}
+        ghost_idx = {}
+        for r in torch.unique(owner[~mine]).tolist():
+            idx = torch.nonzero(owner == r).reshape(-1)
+            idx = idx[torch.argsort(gkey[idx])]
+            ghost_idx[int(r)] = idx
+            need[int(r)] = gkey[idx].cpu()
+        all_need = [None] * dist.world
+        td.all_gather_object(all_need, need)
+        neigh = sorted(set(dist.neigh) | set(need) | {r for r in range(dist.world) if r != dist.rank and dist.rank in all_need[r]})
+        own_keys = gkey[own_idx]
+        vertex_dof = torch.empty(nv, dtype=torch.int64, device=dev)
+        vertex_dof[:n_ov] = torch.arange(n_ov, device=dev)
+        edge_dof = torch.empty(ne, dtype=torch.int64, device=dev)
+        edge_dof[own_idx] = n_ov + torch.arange(n_oe, device=dev)
+        n_owned = n_ov + n_oe
+        send_lists, recv_counts = [], []
+        cursor = n_owned
+        vneigh = {int(r): j for j, r in enumerate(dist.neigh)}
+        empty = torch.zeros(0, dtype=torch.int64, device=dev)
+        for r in neigh:
+            # what r needs from me: my owned vertices in its ghost list, then my owned edges it asked for
+            if r in vneigh:
+                j = vneigh[r]
+                sv = dist.send_idx[int(dist.send_off[j]): int(dist.send_off[j + 1])].long()
+                gv = n_ov + torch.arange(int(dist.recv_off[j]), int(dist.recv_off[j + 1]), device=dev)
+            else:
+                sv, gv = empty, empty
+            want = all_need[r].get(dist.rank)
+            if want is not None and want.numel():
+                pos = torch.searchsorted(own_keys, want.to(dev))
+                if bool((own_keys[pos.clamp(max=max(n_oe - 1, 0))] != want.to(dev)).any()):
+                    raise _exceptions.CashocsException("P2 halo plan: a requested edge is not owned here")
+                se = n_ov + pos
+            else:
+                se = empty
+            send_lists.append(torch.cat([sv, se]))
+            ge = ghost_idx.get(r, empty)
+            vertex_dof[gv] = cursor + torch.arange(gv.numel(), device=dev)
+            cursor += int(gv.numel())
+            edge_dof[ge] = cursor + torch.arange(ge.numel(), device=dev)
+            cursor += int(ge.numel())
+            recv_counts.append(int(gv.numel() + ge.numel()))
+        ndofs = nv + ne
+        assert cursor == ndofs
+        plan = distributed.DistContext(dist.rank, dist.world, dist.transport)
+        plan.parent = dist if dist.parent is None else dist.parent
+        plan.set_plan(neigh, send_lists, recv_counts, n_owned, ndofs - n_owned, dev)
+        out = dict(edges=edges, vertex_dof=vertex_dof, edge_dof=edge_dof, ndofs=ndofs, n_owned=n_owned, dist=plan,
+                   edge_gkey=torch.stack([glo, ghi], dim=1))
+    out["cell_dofs"] = torch.cat([out["vertex_dof"][cells], out["edge_dof"][cell_edges]], dim=1).to(torch.int32).contiguous()
+    return out
+
+
 class P2Space:
     degree = 2
 
     def __init__(self, mesh) -> None:
-        if mesh.dist is not None:
-            raise _exceptions.InputError("cashocs_b200.P2Space", "mesh",
-                                         "P2 spaces on a partitioned mesh are not implemented yet (one GPU)")
         _lib.require_cuda(mesh.coords, mesh.cells)
         lib = _lib.load()
         s = _lib.stream_ptr()
         self.mesh = mesh
         self.device = dev = mesh.device
         self.dim = d = mesh.dim
-        self.dist = None
         k = d + 1
-        loc = LOCAL_EDGES[d]
-        self.ndof_e = nde = k + len(loc)
-        nv, nc = mesh.num_vertices, mesh.num_cells
-        cells = mesh.cells.long()
-        # edges = sorted unique vertex pairs (cells are ascending per cell, so pairs are ordered)
-        key = torch.stack([cells[:, i] * nv + cells[:, j] for i, j in loc], dim=1)
-        uniq, inv = torch.unique(key.reshape(-1), return_inverse=True)
-        self.edges = torch.stack([uniq // nv, uniq % nv], dim=1)
-        self.num_edges = int(uniq.numel())
-        self.ndofs = nv + self.num_edges
+        self.ndof_e = nde = k + len(LOCAL_EDGES[d])
+        nc = mesh.num_cells
+        num = p2_numbering(mesh)
+        self.edges = num["edges"]              # [ne, 2] local vertex ids
+        self.vertex_dof = num["vertex_dof"]    # local vertex -> dof
+        self.edge_dof = num["edge_dof"]        # local edge -> dof
+        self.cell_dofs = num["cell_dofs"]
+        self.num_edges = int(self.edges.shape[0])
+        self.ndofs = int(num["ndofs"])          # owned + ghost dofs of this rank
+        self.n_owned_dofs = int(num["n_owned"])
+        self.dist = num["dist"]                 # halo plan over dofs (None on one GPU)
         if self.ndofs >= 2**31:
             raise _exceptions.CashocsException("P2 dof count exceeds int32")
-        self.cell_dofs = torch.cat([cells, nv + inv.view(nc, len(loc))], dim=1).to(torch.int32).contiguous()
-        del key, inv, cells
         # mesh-like attributes for Matrix / LinearSolver / AMG
-        self.num_vertices = self.n_owned_vertices = self.ndofs
+        self.num_vertices, self.n_owned_vertices = self.ndofs, self.n_owned_dofs
+        nrows = self.n_owned_dofs
         self.d2c_ptr = torch.empty(self.ndofs + 1, dtype=torch.int64, device=dev)
         self.d2c_idx = torch.empty(nc * nde, dtype=torch.int32, device=dev)
         _lib.check(lib.cb_v2c_build(s, self.ndofs, nc, nde, _lib.ptr(self.cell_dofs), _lib.ptr(self.d2c_ptr),
                                     _lib.ptr(self.d2c_idx)), "cb_v2c_build")
-        self.rowptr = torch.empty(self.ndofs + 1, dtype=torch.int64, device=dev)
-        _lib.check(lib.cb_pattern_rowptr(s, self.ndofs, nde, _lib.ptr(self.cell_dofs), _lib.ptr(self.d2c_ptr),
+        self.rowptr = torch.empty(nrows + 1, dtype=torch.int64, device=dev)
+        _lib.check(lib.cb_pattern_rowptr(s, nrows, nde, _lib.ptr(self.cell_dofs), _lib.ptr(self.d2c_ptr),
                                          _lib.ptr(self.d2c_idx), _lib.ptr(self.rowptr)), "cb_pattern_rowptr")
         self.nnz = int(self.rowptr[-1].item())
         if self.nnz >= 2**31:
             raise _exceptions.CashocsException("P2 nnz exceeds the int32 column-index range of one GPU")
         self.col = torch.empty(self.nnz, dtype=torch.int32, device=dev)
-        _lib.check(lib.cb_pattern_fill(s, self.ndofs, nc, nde, _lib.ptr(self.cell_dofs), _lib.ptr(self.d2c_ptr),
+        _lib.check(lib.cb_pattern_fill(s, nrows, nc, nde, _lib.ptr(self.cell_dofs), _lib.ptr(self.d2c_ptr),
                                        _lib.ptr(self.d2c_idx), _lib.ptr(self.rowptr), _lib.ptr(self.col), None),
                    "cb_pattern_fill")
         # reference tensors of the affine element (degree-4 exact rule)
@@ -114,6 +216,7 @@ class P2Space:
         m = self.mesh
         v.dim, v.ndof_e = self.dim, self.ndof_e
         v.nc, v.nv, v.ndofs, v.nnz = m.num_cells, m.num_vertices, self.ndofs, self.nnz
+        v.nrows_owned, v.nv_owned, v.nc_owned = self.n_owned_dofs, m.n_owned_vertices, m.n_owned_cells
         v.cells, v.cell_dofs, v.coords = m.cells.data_ptr(), self.cell_dofs.data_ptr(), m.coords.data_ptr()
         v.rowptr, v.col = self.rowptr.data_ptr(), self.col.data_ptr()
         v.d2c_ptr, v.d2c_idx = self.d2c_ptr.data_ptr(), self.d2c_idx.data_ptr()
@@ -138,7 +241,7 @@ class P2Space:
         planar and convex) use: an edge lies on a marked face iff both end points do."""
         m = self.mesh
         nv = m.num_vertices
-        verts = m.boundary_vertices(markers)
+        verts = self.vertex_dof[m.boundary_vertices(markers)]
         facets = getattr(m, "boundary_facets", None)
         ekey = self.edges[:, 0] * nv + self.edges[:, 1]
         if facets:
@@ -158,13 +261,14 @@ class P2Space:
                 on[m.boundary_vertices([mk])] = True
                 eids.append(torch.nonzero(on[self.edges[:, 0]] & on[self.edges[:, 1]]).reshape(-1))
             eid = torch.unique(torch.cat(eids)) if eids else torch.zeros(0, dtype=torch.int64, device=self.device)
-        return torch.cat([verts, nv + eid])
+        return torch.cat([verts, self.edge_dof[eid]])
 
     def interpolate(self, expr) -> torch.Tensor:
         """Nodal interpolant (vertex values, then edge-midpoint values) of a polynomial / callable."""
         x = self.mesh.coords
-        mid = 0.5 * (x[self.edges[:, 0]] + x[self.edges[:, 1]])
-        pts = torch.cat([x, mid])
+        pts = torch.empty(self.ndofs, x.shape[1], dtype=torch.float64, device=x.device)
+        pts[self.vertex_dof] = x
+        pts[self.edge_dof] = 0.5 * (x[self.edges[:, 0]] + x[self.edges[:, 1]])
         if isinstance(expr, expressions.Polynomial):
             out = torch.zeros(pts.shape[0], dtype=torch.float64, device=pts.device)
             for (a, b, c), v in expr.terms.items():

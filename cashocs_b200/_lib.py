@@ -70,6 +70,9 @@ class cb_p2_view(C.Structure):
         ("nv", C.c_int64),
         ("ndofs", C.c_int64),
         ("nnz", C.c_int64),
+        ("nrows_owned", C.c_int64),
+        ("nv_owned", C.c_int64),
+        ("nc_owned", C.c_int64),
         ("cells", C.c_void_p),
         ("cell_dofs", C.c_void_p),
         ("coords", C.c_void_p),

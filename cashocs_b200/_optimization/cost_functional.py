@@ -30,6 +30,8 @@ class ReducedCostFunctional:
                                              _lib.ptr(ud), _lib.ptr(self._out), _lib.ptr(scratch), scratch.numel()),
                 "cb_p2_functional",
             )
+            if mesh.dist is not None:
+                mesh.dist.allreduce(self._out, "sum")
             return float(self._out.item())
         _lib.check(
             _lib.load().cb_functional(_lib.stream_ptr(), mesh.dim, mesh.n_owned_cells, _lib.ptr(mesh.coords),

@@ -38,7 +38,7 @@ class AdjointProblem(pde_problem.PDEProblem):
             if y.degree != p.degree:
                 raise _exceptions.InputError("cashocs_b200.AdjointProblem", "adjoints",
                                              "state and adjoint must use the same CG degree")
-        self.b_tensors = [torch.zeros(sp.ndofs if sp is not None else mesh.n_owned_vertices, dtype=torch.float64,
+        self.b_tensors = [torch.zeros(sp.n_owned_dofs if sp is not None else mesh.n_owned_vertices, dtype=torch.float64,
                                       device=mesh.device) for sp in self.spaces]
         self.A_tensors = [None] * len(adjoints)
         nwork = max(sp.ndofs if sp is not None else mesh.num_vertices for sp in self.spaces)
@@ -74,6 +74,8 @@ class AdjointProblem(pde_problem.PDEProblem):
                         self.A_tensors[i] = A
                     res = self.linear_solver.solve(self.adjoints[i].vector, A=A, b=b, ksp_options=self.ksp_options[i])
                     self.iterations[i] = res.its
+                    if self.spaces[i].dist is not None:
+                        self.spaces[i].dist.halo_exchange(self.adjoints[i].vector, 1)
                     continue
                 A, b = linalg.assemble_scalar_system(
                     self.mesh, form.kappa, form.reaction, f_nodal=self._rhs_nodal(i), f_nodal_scale=1.0,

@@ -34,7 +34,7 @@ class StateProblem(pde_problem.PDEProblem):
         # P2 states (BASELINE configs[4]) live on mesh.p2_space(); P1 states on the mesh's vertex space
         self.spaces = [y.space for y in states]
         self.A_tensors = [linalg.Matrix(sp if sp is not None else mesh, 1) for sp in self.spaces]
-        self.b_tensors = [torch.zeros(sp.ndofs if sp is not None else mesh.n_owned_vertices, dtype=torch.float64,
+        self.b_tensors = [torch.zeros(sp.n_owned_dofs if sp is not None else mesh.n_owned_vertices, dtype=torch.float64,
                                       device=mesh.device) for sp in self.spaces]
         self.bc_arrays = [forms.bc_flag_arrays(mesh, bcs, 1, space=sp) for bcs, sp in zip(bcs_list, self.spaces)]
         self._checkpoint = None
@@ -76,8 +76,9 @@ class StateProblem(pde_problem.PDEProblem):
                 A, b = self.assemble(i)
                 res = self.linear_solver.solve(self.states[i].vector, A=A, b=b, ksp_options=self.ksp_options[i])
                 self.iterations[i] = res.its
-                if self.mesh.dist is not None:
-                    self.mesh.dist.halo_exchange(self.states[i].vector, 1)
+                plan = self.spaces[i].dist if self.spaces[i] is not None else self.mesh.dist
+                if plan is not None:
+                    plan.halo_exchange(self.states[i].vector, 1)
             self.has_solution = True
             self.number_of_solves += 1
         return self.states

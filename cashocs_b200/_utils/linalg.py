@@ -345,7 +345,7 @@ def assemble_p2_system(space, c_stiff: float = 1.0, c_mass: float = 0.0, f_poly:
     if matrix and A is None:
         A = Matrix(space, 1)
     if rhs and b is None:
-        b = torch.empty(space.ndofs, dtype=torch.float64, device=space.device)
+        b = torch.empty(space.n_owned_dofs, dtype=torch.float64, device=space.device)
     _lib.require_cuda(f_nodal, bc_flag, bc_val, b)
     if matrix:
         _lib.check(lib.cb_p2_assemble_matrix(_lib.stream_ptr(), C.byref(view), float(c_stiff), float(c_mass),
@@ -377,7 +377,7 @@ def assemble_p2_shape_derivative(space, u: torch.Tensor, p: torch.Tensor, f_poly
     mesh.build_pattern()
     d = mesh.dim
     if b is None:
-        b = torch.empty(mesh.num_vertices * d, dtype=torch.float64, device=mesh.device)
+        b = torch.empty(mesh.n_owned_vertices * d, dtype=torch.float64, device=mesh.device)
     _lib.require_cuda(u, p, bc_flag, b)
     view = space.view()
     f = f_poly.struct()

@@ -446,6 +446,8 @@ static int check_p2(const cb_p2_view* m) {
   CB_REQUIRE(m->dim == 2 || m->dim == 3, "dim must be 2 or 3");
   CB_REQUIRE(m->cells && m->cell_dofs && m->coords, "cells / cell_dofs / coords missing");
   CB_REQUIRE(m->ref_R && m->ref_M && m->ref_I, "reference tensors missing");
+  CB_REQUIRE(m->nrows_owned > 0 && m->nrows_owned <= m->ndofs && m->nv_owned <= m->nv && m->nc_owned <= m->nc,
+             "owned counts of the P2 view are inconsistent");
   return CB_OK;
 }
 
@@ -454,13 +456,13 @@ extern "C" int cb_p2_assemble_matrix(void* stream, const cb_p2_view* m, double c
   if (int e = check_p2(m)) return e;
   CB_REQUIRE(m->rowptr && m->col && m->d2c_ptr && m->d2c_idx && val, "pattern / adjacency / val missing");
   cudaStream_t s = as_stream(stream);
-  const int grid = grid_for(m->ndofs * 32, P2_WARPS * 32, 8);
+  const int grid = grid_for(m->nrows_owned * 32, P2_WARPS * 32, 8);
   if (m->dim == 2)
-    k_p2_matrix<2><<<grid, P2_WARPS * 32, 0, s>>>(m->ndofs, m->rowptr, m->col, m->d2c_ptr, m->d2c_idx, m->cells,
+    k_p2_matrix<2><<<grid, P2_WARPS * 32, 0, s>>>(m->nrows_owned, m->rowptr, m->col, m->d2c_ptr, m->d2c_idx, m->cells,
                                                  m->cell_dofs, m->coords, m->ref_R, m->ref_M, c_stiff, c_mass,
                                                  bc_flag, val);
   else
-    k_p2_matrix<3><<<grid, P2_WARPS * 32, 0, s>>>(m->ndofs, m->rowptr, m->col, m->d2c_ptr, m->d2c_idx, m->cells,
+    k_p2_matrix<3><<<grid, P2_WARPS * 32, 0, s>>>(m->nrows_owned, m->rowptr, m->col, m->d2c_ptr, m->d2c_idx, m->cells,
                                                  m->cell_dofs, m->coords, m->ref_R, m->ref_M, c_stiff, c_mass,
                                                  bc_flag, val);
   CB_LAUNCH_CHECK();
@@ -480,19 +482,19 @@ extern "C" int cb_p2_assemble_rhs(void* stream, const cb_p2_view* m, double c_st
   cb_poly fz;
   memset(&fz, 0, sizeof(fz));
   const cb_poly& ff = f ? *f : fz;
-  const int grid = grid_for(m->nc, 128, 12), dgrid = grid_for(m->ndofs, 256, 8);
+  const int grid = grid_for(m->nc, 128, 12), dgrid = grid_for(m->nrows_owned, 256, 8);
   if (m->dim == 2) {
     k_p2_rhs_cells<2><<<grid, 128, 0, s>>>(m->nc, m->cells, m->cell_dofs, m->coords, m->ref_R, m->ref_M, m->ref_I,
                                           c_stiff, c_mass, s_poly, ff, nq, qtab, s_const, s_nodal, fnodal,
                                           bc_flag, bc_val, m->cell_scratch);
     CB_LAUNCH_CHECK();
-    k_p2_gather_dofs<6><<<dgrid, 256, 0, s>>>(m->ndofs, m->d2c_ptr, m->d2c_idx, m->cell_dofs, m->cell_scratch, rhs);
+    k_p2_gather_dofs<6><<<dgrid, 256, 0, s>>>(m->nrows_owned, m->d2c_ptr, m->d2c_idx, m->cell_dofs, m->cell_scratch, rhs);
   } else {
     k_p2_rhs_cells<3><<<grid, 128, 0, s>>>(m->nc, m->cells, m->cell_dofs, m->coords, m->ref_R, m->ref_M, m->ref_I,
                                           c_stiff, c_mass, s_poly, ff, nq, qtab, s_const, s_nodal, fnodal,
                                           bc_flag, bc_val, m->cell_scratch);
     CB_LAUNCH_CHECK();
-    k_p2_gather_dofs<10><<<dgrid, 256, 0, s>>>(m->ndofs, m->d2c_ptr, m->d2c_idx, m->cell_dofs, m->cell_scratch, rhs);
+    k_p2_gather_dofs<10><<<dgrid, 256, 0, s>>>(m->nrows_owned, m->d2c_ptr, m->d2c_idx, m->cell_dofs, m->cell_scratch, rhs);
   }
   CB_LAUNCH_CHECK();
   return CB_OK;
@@ -509,18 +511,18 @@ extern "C" int cb_p2_shape_derivative_poisson(void* stream, const cb_p2_view* m,
   cudaStream_t s = as_stream(stream);
   cb_poly gz;
   memset(&gz, 0, sizeof(gz));
-  const int grid = grid_for(m->nc, 128, 12), vgrid = grid_for(m->nv, 256, 8);
+  const int grid = grid_for(m->nc, 128, 12), vgrid = grid_for(m->nv_owned, 256, 8);
   if (m->dim == 2) {
     k_p2_shape_derivative_cells<2><<<grid, 128, 0, s>>>(m->nc, m->cells, m->cell_dofs, m->coords, u, p, *f, gradf[0],
                                                        gradf[1], gz, nq, qtab, c_int_u, bc_flag, m->cell_scratch);
     CB_LAUNCH_CHECK();
-    k_gather_cell_vectors<2, 2><<<vgrid, 256, 0, s>>>(m->nv, v2c_ptr, v2c_idx, m->cells, m->cell_scratch, rhs);
+    k_gather_cell_vectors<2, 2><<<vgrid, 256, 0, s>>>(m->nv_owned, v2c_ptr, v2c_idx, m->cells, m->cell_scratch, rhs);
   } else {
     k_p2_shape_derivative_cells<3><<<grid, 128, 0, s>>>(m->nc, m->cells, m->cell_dofs, m->coords, u, p, *f, gradf[0],
                                                        gradf[1], gradf[2], nq, qtab, c_int_u, bc_flag,
                                                        m->cell_scratch);
     CB_LAUNCH_CHECK();
-    k_gather_cell_vectors<3, 3><<<vgrid, 256, 0, s>>>(m->nv, v2c_ptr, v2c_idx, m->cells, m->cell_scratch, rhs);
+    k_gather_cell_vectors<3, 3><<<vgrid, 256, 0, s>>>(m->nv_owned, v2c_ptr, v2c_idx, m->cells, m->cell_scratch, rhs);
   }
   CB_LAUNCH_CHECK();
   return CB_OK;
@@ -531,13 +533,13 @@ extern "C" int cb_p2_functional(void* stream, const cb_p2_view* m, double c_u, c
   if (int e = check_p2(m)) return e;
   CB_REQUIRE(u && result_dev && scratch && scratch_len >= RED_SCRATCH_LEN, "cb_p2_functional: missing argument");
   cudaStream_t s = as_stream(stream);
-  int grid = grid_for(m->nc, 256, 4);
+  int grid = grid_for(m->nc_owned, 256, 4);
   if (grid > RED_MAXP) grid = RED_MAXP;
   if (m->dim == 2)
-    k_p2_functional<2><<<grid, 256, 0, s>>>(m->nc, m->coords, m->cells, m->cell_dofs, m->ref_M, m->ref_I, c_u, u,
+    k_p2_functional<2><<<grid, 256, 0, s>>>(m->nc_owned, m->coords, m->cells, m->cell_dofs, m->ref_M, m->ref_I, c_u, u,
                                            c_track, ud, result_dev, scratch);
   else
-    k_p2_functional<3><<<grid, 256, 0, s>>>(m->nc, m->coords, m->cells, m->cell_dofs, m->ref_M, m->ref_I, c_u, u,
+    k_p2_functional<3><<<grid, 256, 0, s>>>(m->nc_owned, m->coords, m->cells, m->cell_dofs, m->ref_M, m->ref_I, c_u, u,
                                            c_track, ud, result_dev, scratch);
   CB_LAUNCH_CHECK();
   return CB_OK;

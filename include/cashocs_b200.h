@@ -175,7 +175,10 @@ typedef struct {
   int32_t dim;               /* 2 or 3 */
   int32_t ndof_e;            /* 6 or 10 */
   int64_t nc, nv, ndofs, nnz;
-  const int32_t* cells;      /* [nc, dim+1] vertex ids, ascending per cell */
+  int64_t nrows_owned;       /* owned dofs = matrix rows (== ndofs on one GPU; owned dofs come first) */
+  int64_t nv_owned;          /* owned vertices (rows of the vector-P1 shape derivative) */
+  int64_t nc_owned;          /* owned cells (cost functional) */
+  const int32_t* cells;      /* [nc, dim+1] vertex ids */
   const int32_t* cell_dofs;  /* [nc, ndof_e] */
   const double* coords;      /* [nv, dim] */
   const int64_t* rowptr;     /* [ndofs+1] */

@@ -208,3 +208,76 @@ def test_distributed_amg_hierarchy_world2(n_mesh, agglomerate, rep_level):
     results = mgr.dict()
     mp.spawn(_amg_worker, args=(world, port, n_mesh, agglomerate, rep_level, results), nprocs=world, join=True)
     assert dict(results) == {0: "ok", 1: "ok"}, dict(results)
+
+
+# ----------------------------------------------------------------------------- P2 dof numbering on a partition
+def _p2_worker(rank, world, port, results):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cashocs_b200 import distributed
+        from cashocs_b200._forms import function_space
+        from oracle import fem, meshes, p2
+
+        dist = distributed.DistContext(rank, world, transport="torch")
+        om = meshes.regular_mesh(4, 1.0, 1.0, 1.0)
+        lm = distributed.distributed_regular_mesh(4, dist, device="cpu")
+        num = function_space.p2_numbering(lm)
+        nvg = om.num_vertices
+        gdofs, gedges = p2.cell_dofs(om.cells, nvg)
+        nd_glob = nvg + len(gedges)
+        gid = lm.global_vertex_ids.numpy()
+        # global dof id of every local dof
+        gkey = gedges[:, 0] * nvg + gedges[:, 1]
+        ek = num["edge_gkey"].numpy()
+        eglob = nvg + np.searchsorted(gkey, ek[:, 0] * nvg + ek[:, 1])
+        assert np.array_equal(gkey[eglob - nvg], ek[:, 0] * nvg + ek[:, 1])
+        g_of = np.empty(num["ndofs"], dtype=np.int64)
+        g_of[num["vertex_dof"].numpy()] = gid
+        g_of[num["edge_dof"].numpy()] = eglob
+        n_owned = num["n_owned"]
+        # every global dof is owned by exactly one rank
+        owned = [None] * world
+        td.all_gather_object(owned, g_of[:n_owned])
+        allowned = np.concatenate(owned)
+        assert allowned.size == nd_glob and np.unique(allowned).size == nd_glob
+        # local cell dofs == the oracle's global cell dofs of the same cells (as sets per cell, local edge order kept)
+        gcells = gid[lm.cells.numpy()]
+        order = {tuple(sorted(c)): i for i, c in enumerate(map(tuple, om.cells))}
+        ci = np.array([order[tuple(sorted(c))] for c in map(tuple, gcells)])
+        assert np.array_equal(np.sort(g_of[num["cell_dofs"].numpy()], axis=1), np.sort(gdofs[ci], axis=1))
+        # halo exchange over dofs
+        plan = num["dist"]
+        xg = np.random.RandomState(3).rand(nd_glob)
+        x = torch.zeros(num["ndofs"], dtype=torch.float64)
+        x[:n_owned] = torch.from_numpy(xg[g_of[:n_owned]])
+        plan.halo_exchange(x, 1)
+        assert np.array_equal(x.numpy(), xg[g_of])
+        # owned rows of the locally assembled P2 operator == rows of the global operator
+        _, vol, G = fem.cell_geometry(om.coords, om.cells)
+        A = fem.assemble_matrix(p2.stiffness_elements(vol, G) + p2.mass_elements(vol, 3), gdofs, nd_glob)
+        _, lvol, lG = fem.cell_geometry(lm.coords.numpy(), lm.cells.numpy())
+        Aloc = fem.assemble_matrix(p2.stiffness_elements(lvol, lG) + p2.mass_elements(lvol, 3), num["cell_dofs"].numpy().astype(np.int64),
+                                   num["ndofs"])
+        y = (Aloc @ xg[g_of])[:n_owned]
+        assert np.allclose(y, (A @ xg)[g_of[:n_owned]], rtol=1e-12, atol=1e-14)
+        results[rank] = "ok"
+    except Exception as exc:  # pragma: no cover
+        import traceback
+
+        results[rank] = traceback.format_exc() + str(exc)
+    finally:
+        td.destroy_process_group()
+
+
+def test_p2_numbering_world2():
+    """P2 dofs on a 2-rank partition: unique ownership, halo plan over vertex + edge dofs, owned rows of the
+    locally assembled operator equal the global operator."""
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_p2_worker, args=(world, port, results), nprocs=world, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}, dict(results)
