@@ -206,6 +206,7 @@ SIGNATURES = {
     "cb_amg_block_trace": (I32, [P, C.POINTER(cb_mat), P]),
     "cb_amg_smooth_prolongator": (I32, [P, C.POINTER(cb_mat), DBL, P, P, P, P, P]),
     "cb_amg_spgemm_terms": (I32, [P, I32, I32, I64, P, P, P, P, P, P]),
+    "cb_amg_spgemm_rowwise": (I32, [P, I32, I32, I64, P, P, P, P, P, P, P, P, P]),
     "cb_amg_dense_inverse": (I32, [P, C.POINTER(cb_mat), P, P]),
     "cb_mesh_quality": (I32, [P, I32, I64, P, P, I32, P, P, P, I64]),
     "cb_det_check": (I32, [P, I32, I64, P, P, P, DBL, P, P, P, I64]),

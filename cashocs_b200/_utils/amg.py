@@ -18,6 +18,7 @@ block size and runs through the same SpMV kernel.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -124,6 +125,30 @@ def _expand_terms(lhs_rows, lhs_cols, lhs_index, rhs_rowptr, rhs_col, nrows_out,
             torch.cat(sl).contiguous(), torch.cat(sr).contiguous())
 
 
+def _expand_pattern(lhs_rows, lhs_cols, rhs_rowptr, rhs_col, nrows_out, ncols_out, chunk_rows=300_000):
+    """CSR pattern (rowptr, col) of L * R without the term lists (see ``_expand_terms``); ``lhs_rows``
+    ascending.  Peak memory is one chunk of keys."""
+    dev = lhs_rows.device
+    lens_all = rhs_rowptr[1:] - rhs_rowptr[:-1]
+    keys = []
+    bounds = torch.searchsorted(lhs_rows, torch.arange(0, nrows_out + chunk_rows, chunk_rows, device=dev)).tolist()
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        if b <= a:
+            continue
+        i, k = lhs_rows[a:b], lhs_cols[a:b]
+        lens = lens_all[k]
+        total = int(lens.sum().item())
+        if total == 0:
+            continue
+        rep = torch.repeat_interleave(torch.arange(b - a, device=dev), lens)
+        start = torch.cumsum(lens, 0) - lens
+        rpos = rhs_rowptr[k][rep] + (torch.arange(total, device=dev) - start[rep])
+        keys.append(torch.unique(i[rep] * ncols_out + rhs_col[rpos].long()))
+        del rep, start, rpos
+    key = torch.cat(keys)
+    return _rowptr_from_rows(key // ncols_out, nrows_out), (key % ncols_out).to(torch.int32).contiguous()
+
+
 class _Level:
     pass
 
@@ -143,6 +168,9 @@ class AMGSymbolic:
     MAX_DENSE = 256  # scalar rows of a coarsest level that is inverted densely (bs <= 3 -> <= 85 nodes)
     AGGLOMERATE = 20000  # global node count below which a distributed level is replicated on every rank
     DISTANCE = 2  # MIS(k) aggregation (see mis_aggregate)
+    # levels with more block entries than this use the search-based Galerkin products instead of term lists
+    # (8 bytes per scalar product term: 2-4x the operator itself)
+    TERM_LIST_MAX_NNZ = int(os.environ.get("CASHOCS_B200_TERM_LIST_MAX_NNZ", 60_000_000))
 
     def __init__(self, rowptr, col, n, ncols, dist=None, max_levels: int = 12) -> None:
         self.levels: list[_Level] = []
@@ -155,6 +183,7 @@ class AMGSymbolic:
                 # agglomeration: below this size halo latency dominates, so the level (and everything
                 # coarser) is replicated on every rank; the restriction all-reduces the rhs instead
                 L.rep_dist, L.rep_nnzb_local = dist, int(col.numel())
+                L.rep_rowptr_local, L.rep_col_local = rowptr, col  # this rank's rows in its own numbering
                 rowptr, col, L.rep_off, L.rep_pos, gid = self._replicate(rowptr, col, n, ncols, n_glob, dist)
                 self.levels[-1].coarse_gid = gid.to(torch.int32).contiguous()  # local coarse node -> replicated row
                 n = ncols = n_glob
@@ -197,11 +226,17 @@ class AMGSymbolic:
             L.pt_rowptr = _rowptr_from_rows(po_col[order], nc)
             L.agg, L.nc, L.gc = agg_ext.to(torch.int32).contiguous(), nc, gc
             nnza = col.numel()
-            L.ap_rowptr, L.ap_col, L.ap_seg, L.ap_sl, L.ap_sr = _expand_terms(
-                rows, col.long(), torch.arange(nnza, device=dev), L.p_rowptr, L.p_col, n, nct)
-            c_rowptr, c_col, L.ac_seg, L.ac_sl, L.ac_sr = _expand_terms(
-                _rows_of(L.pt_rowptr), L.pt_col.long(), torch.arange(L.nnzp_owned, device=dev), L.ap_rowptr, L.ap_col,
-                nc, nct)
+            L.rowwise = nnza > self.TERM_LIST_MAX_NNZ
+            if L.rowwise:  # patterns only; the numeric phase searches the output rows (cb_amg_spgemm_rowwise)
+                L.ap_rowptr, L.ap_col = _expand_pattern(rows, col.long(), L.p_rowptr, L.p_col, n, nct)
+                c_rowptr, c_col = _expand_pattern(_rows_of(L.pt_rowptr), L.pt_col.long(), L.ap_rowptr, L.ap_col, nc, nct)
+                L.ap_seg = L.ap_sl = L.ap_sr = L.ac_seg = L.ac_sl = L.ac_sr = None
+            else:
+                L.ap_rowptr, L.ap_col, L.ap_seg, L.ap_sl, L.ap_sr = _expand_terms(
+                    rows, col.long(), torch.arange(nnza, device=dev), L.p_rowptr, L.p_col, n, nct)
+                c_rowptr, c_col, L.ac_seg, L.ac_sl, L.ac_sr = _expand_terms(
+                    _rows_of(L.pt_rowptr), L.pt_col.long(), torch.arange(L.nnzp_owned, device=dev), L.ap_rowptr,
+                    L.ap_col, nc, nct)
             L.last = False
             rowptr, col, n, ncols, dist = c_rowptr, c_col, nc, nct, new_dist
 
@@ -464,12 +499,23 @@ class AMGHierarchy:
             nxt, nxtL = self.data[li + 1], self.levels[li + 1]
             rep = nxtL.rep_dist is not None
             out = nxt.val_local if rep else nxt.val
-            _lib.check(lib.cb_amg_spgemm_terms(s, bs, 1, L.ap_col.numel(), _lib.ptr(L.ap_seg), _lib.ptr(L.ap_sl),
-                                               _lib.ptr(L.ap_sr), _lib.ptr(val), _lib.ptr(D.p_val), _lib.ptr(D.ap_val)),
-                       "cb_amg_spgemm_terms(AP)")
-            _lib.check(lib.cb_amg_spgemm_terms(s, bs, 0, out.numel() // (bs * bs), _lib.ptr(L.ac_seg), _lib.ptr(L.ac_sl),
-                                               _lib.ptr(L.ac_sr), _lib.ptr(D.pt_val), _lib.ptr(D.ap_val), _lib.ptr(out)),
-                       "cb_amg_spgemm_terms(PtAP)")
+            if L.rowwise:
+                _lib.check(lib.cb_amg_spgemm_rowwise(s, bs, 1, L.n, _lib.ptr(L.rowptr), _lib.ptr(L.col), _lib.ptr(val),
+                                                     _lib.ptr(L.p_rowptr), _lib.ptr(L.p_col), _lib.ptr(D.p_val),
+                                                     _lib.ptr(L.ap_rowptr), _lib.ptr(L.ap_col), _lib.ptr(D.ap_val)),
+                           "cb_amg_spgemm_rowwise(AP)")
+                _lib.check(lib.cb_amg_spgemm_rowwise(s, bs, 0, L.nc, _lib.ptr(L.pt_rowptr), _lib.ptr(L.pt_col),
+                                                     _lib.ptr(D.pt_val), _lib.ptr(L.ap_rowptr), _lib.ptr(L.ap_col),
+                                                     _lib.ptr(D.ap_val), _lib.ptr(nxtL.rep_rowptr_local if rep else nxtL.rowptr),
+                                                     _lib.ptr(nxtL.rep_col_local if rep else nxtL.col), _lib.ptr(out)),
+                           "cb_amg_spgemm_rowwise(PtAP)")
+            else:
+                _lib.check(lib.cb_amg_spgemm_terms(s, bs, 1, L.ap_col.numel(), _lib.ptr(L.ap_seg), _lib.ptr(L.ap_sl),
+                                                   _lib.ptr(L.ap_sr), _lib.ptr(val), _lib.ptr(D.p_val), _lib.ptr(D.ap_val)),
+                           "cb_amg_spgemm_terms(AP)")
+                _lib.check(lib.cb_amg_spgemm_terms(s, bs, 0, out.numel() // (bs * bs), _lib.ptr(L.ac_seg), _lib.ptr(L.ac_sl),
+                                                   _lib.ptr(L.ac_sr), _lib.ptr(D.pt_val), _lib.ptr(D.ap_val), _lib.ptr(out)),
+                           "cb_amg_spgemm_terms(PtAP)")
             if rep:  # every rank contributes its rows of the replicated operator
                 nxt.val.zero_()
                 nxt.val.view(-1, bs * bs)[nxtL.rep_pos] = out.view(-1, bs * bs)

@@ -93,6 +93,38 @@ k_spgemm_terms(int64_t nnz_out, const int64_t* __restrict__ seg_ptr, const int32
   }
 }
 
+// The same product without term lists (they cost 8 bytes per scalar product term, i.e. 2-4x the matrix
+// itself, which does not fit for 10^9-nnz operators): thread (row i, block element e) walks row i of L
+// and the rows of R it references, finds the target column in the known pattern of the output row by
+// binary search and accumulates.  Same summation order as the term lists (L entries ascending, then R
+// entries ascending) -> bitwise the same result.
+template <int BS, bool LHS_BLOCK>
+__global__ void __launch_bounds__(256)
+k_spgemm_rowwise(int64_t nrows, const int64_t* __restrict__ l_rowptr, const int32_t* __restrict__ l_col,
+                 const double* __restrict__ l_val, const int64_t* __restrict__ r_rowptr,
+                 const int32_t* __restrict__ r_col, const double* __restrict__ r_val,
+                 const int64_t* __restrict__ o_rowptr, const int32_t* __restrict__ o_col,
+                 double* __restrict__ out) {
+  constexpr int BB = BS * BS;
+  const int64_t total = nrows * BB;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / BB;
+    const int e = (int)(t - i * BB);
+    const int64_t ob = o_rowptr[i], oe = o_rowptr[i + 1];
+    for (int64_t q = ob; q < oe; ++q) out[q * BB + e] = 0.0;
+    for (int64_t a = l_rowptr[i]; a < l_rowptr[i + 1]; ++a) {
+      const int64_t k = l_col[a];
+      const double lv = LHS_BLOCK ? l_val[a * BB + e] : l_val[a];
+      for (int64_t b = r_rowptr[k]; b < r_rowptr[k + 1]; ++b) {
+        const double rv = LHS_BLOCK ? r_val[b] : r_val[b * BB + e];
+        const int64_t pos = find_col(o_col, ob, oe, r_col[b]);
+        out[pos * BB + e] += lv * rv;
+      }
+    }
+  }
+}
+
 // Dense inverse of the coarsest operator (n <= 256 scalar rows): Gauss-Jordan without pivoting
 // (the matrix is SPD) by ONE CTA in global memory; `work` holds the n x 2n augmented matrix.
 __global__ void __launch_bounds__(256)
@@ -264,6 +296,26 @@ extern "C" int cb_amg_spgemm_terms(void* stream, int bs, int lhs_block, int64_t 
   else k_spgemm_terms<BS, false><<<grid, 256, 0, s>>>(nnz_out, seg_ptr, src_l, src_r, lhs, rhs, out);
   if (bs == 1) { CB_TERMS(1) } else if (bs == 2) { CB_TERMS(2) } else { CB_TERMS(3) }
 #undef CB_TERMS
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int cb_amg_spgemm_rowwise(void* stream, int bs, int lhs_block, int64_t nrows, const int64_t* l_rowptr,
+                                     const int32_t* l_col, const double* l_val, const int64_t* r_rowptr,
+                                     const int32_t* r_col, const double* r_val, const int64_t* o_rowptr,
+                                     const int32_t* o_col, double* out) {
+  CB_REQUIRE(l_rowptr && l_col && l_val && r_rowptr && r_col && r_val && o_rowptr && o_col && out,
+             "cb_amg_spgemm_rowwise: missing argument");
+  CB_REQUIRE(bs >= 1 && bs <= 3, "cb_amg_spgemm_rowwise: bs must be 1..3");
+  cudaStream_t s = as_stream(stream);
+  const int grid = grid_for(nrows * bs * bs, 256, 16);
+#define CB_ROWWISE(BS)                                                                                       \
+  if (lhs_block) k_spgemm_rowwise<BS, true><<<grid, 256, 0, s>>>(nrows, l_rowptr, l_col, l_val, r_rowptr,    \
+                                                                r_col, r_val, o_rowptr, o_col, out);        \
+  else k_spgemm_rowwise<BS, false><<<grid, 256, 0, s>>>(nrows, l_rowptr, l_col, l_val, r_rowptr, r_col,      \
+                                                       r_val, o_rowptr, o_col, out);
+  if (bs == 1) { CB_ROWWISE(1) } else if (bs == 2) { CB_ROWWISE(2) } else { CB_ROWWISE(3) }
+#undef CB_ROWWISE
   CB_LAUNCH_CHECK();
   return CB_OK;
 }

@@ -350,6 +350,13 @@ int cb_amg_spgemm_terms(void* stream, int bs, int lhs_block, int64_t nnz_out, co
                         const int32_t* src_l, const int32_t* src_r, const double* lhs,
                         const double* rhs, double* out);
 /* Dense inverse of the coarsest operator (<= 256 scalar rows); work [2 n^2], inv [n^2] row-major. */
+/* The same product without term lists, for operators whose lists would not fit (8 bytes per scalar
+ * product term): out (known pattern o_rowptr / o_col, sorted columns) = L * R with exactly one block-valued
+ * operand (lhs_block != 0: L), rows of L = rows of out.  Bitwise the result of cb_amg_spgemm_terms. */
+int cb_amg_spgemm_rowwise(void* stream, int bs, int lhs_block, int64_t nrows, const int64_t* l_rowptr,
+                          const int32_t* l_col, const double* l_val, const int64_t* r_rowptr,
+                          const int32_t* r_col, const double* r_val, const int64_t* o_rowptr,
+                          const int32_t* o_col, double* out);
 int cb_amg_dense_inverse(void* stream, const cb_mat* A, double* work, double* inv);
 
 /* ------------------------------------------------------------------ mesh kernels */

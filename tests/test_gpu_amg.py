@@ -134,3 +134,24 @@ def test_cuda_graph_replay_is_bitwise_identical(kind):
             assert out[(1, pc)][0] == out[(-1, pc)][0] > 3
             assert torch.equal(out[(1, pc)][1], out[(-1, pc)][1])
             assert np.array_equal(out[(1, pc)][2], out[(-1, pc)][2])
+
+
+@pytest.mark.parametrize("kind", ["cube", "mesh3d"])
+def test_rowwise_galerkin_products_match_term_lists(kind):
+    """Large operators build their Galerkin products by searching the output rows instead of term lists
+    (AMGSymbolic.TERM_LIST_MAX_NNZ): same summation order, bitwise the same coarse operators."""
+    dm, A, b, E, rhs = systems(kind)
+    for M in (A, E):
+        vals = {}
+        try:
+            for limit in (60_000_000, 0):
+                amg.AMGSymbolic.TERM_LIST_MAX_NNZ = limit
+                h = amg.AMGHierarchy(M)
+                h.numeric(M)
+                assert all(L.rowwise == (limit == 0) for L in h.levels[:-1])
+                vals[limit] = [D.val.clone() for D in h.data[1:]] + [D.ap_val.clone() for D in h.data[:-1]]
+        finally:
+            amg.AMGSymbolic.TERM_LIST_MAX_NNZ = 60_000_000
+        assert len(vals[0]) == len(vals[60_000_000]) >= 2
+        for x, y in zip(vals[0], vals[60_000_000]):
+            assert torch.equal(x, y)
