@@ -120,7 +120,7 @@ def test_polynomial_algebra_and_quadrature():
     for d in (2, 3):
         lam, w = expressions.simplex_quadrature(d, 5)
         lam0, w0 = fem.quadrature(d, 5)
-        assert abs(w.sum() - 1) < 1e-15 and len(w) == len(w0)
+        assert abs(w.sum() - 1) < 1e-15 and len(w) <= len(w0)  # symmetric 7- / 14-point rules vs the collapsed 3^d rule
         # same integrals as the oracle's independent rule
         g = lambda l: (l[:, 1] ** 2 * l[:, 2] ** 3 + l[:, 0])  # noqa: E731
         assert abs(np.sum(w * g(lam)) - np.sum(w0 * g(lam0))) < 1e-15
@@ -156,3 +156,24 @@ def test_bench_reference_arm_runs(tmp_path):
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_quadrature_rules_are_exact():
+    """Every rule the device kernels receive integrates all monomials up to its degree (relative to |K|):
+    int lam^alpha / |K| = d! alpha! / (|alpha| + d)!  -- in particular the 7- / 14-point degree-5 rules."""
+    from math import factorial
+
+    from cashocs_b200._forms import expressions
+
+    for dim in (2, 3):
+        for degree in range(0, 7):
+            lam, w = expressions.simplex_quadrature(dim, degree)
+            assert abs(w.sum() - 1.0) < 1e-15 and np.all(w > 0) and np.all(lam[:, : dim + 1] >= 0)
+            assert np.allclose(lam[:, : dim + 1].sum(axis=1), 1.0, atol=1e-15)
+            for a in range(degree + 1):
+                for b in range(degree + 1 - a):
+                    for c in (range(degree + 1 - a - b) if dim == 3 else [0]):
+                        exact = factorial(dim) * factorial(a) * factorial(b) * factorial(c) / factorial(a + b + c + dim)
+                        got = np.sum(w * lam[:, 1] ** a * lam[:, 2] ** b * (lam[:, 3] ** c if dim == 3 else 1.0))
+                        assert abs(got - exact) < 5e-16, (dim, degree, a, b, c)
+    assert len(expressions.simplex_quadrature(3, 5)[1]) == 14 and len(expressions.simplex_quadrature(2, 5)[1]) == 7
