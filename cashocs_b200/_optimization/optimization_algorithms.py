@@ -1,7 +1,7 @@
 """Optimisation algorithms driving the hot path (``cashocs/_optimization/optimization_algorithms/``).
 
-Gradient descent (``gradient_descent.py:28-60``) and L-BFGS with the two-loop recursion
-(``l_bfgs.py:91-300``); every inner product is ``form_handler.scalar_product`` (= fused SpMV + dot
+Gradient descent (``gradient_descent.py:28-60``), L-BFGS with the two-loop recursion
+(``l_bfgs.py:91-300``) and the nonlinear CG methods (``ncg.py``); every inner product is ``form_handler.scalar_product`` (= fused SpMV + dot
 on the device), vectors never leave HBM.  Convergence test and ascent check follow
 ``optimization_algorithm.py:281-331``.
 """
@@ -161,3 +161,84 @@ class LBFGSMethod(OptimizationAlgorithm):
                 break
             self.update_hessian_approximation()
         self._record()
+
+
+class NonlinearCGMethod(OptimizationAlgorithm):
+    """Nonlinear CG methods (``cashocs/_optimization/optimization_algorithms/ncg.py``): Fletcher-Reeves,
+    Polak-Ribiere, Hestenes-Stiefel, Dai-Yuan, Hager-Zhang (``[AlgoCG] cg_method``), periodic and relative
+    restarts (``:188-212``)."""
+
+    def __init__(self, problem, line_search) -> None:
+        super().__init__(problem, line_search)
+        cfg = self.config
+        self.gradient_prev = torch.zeros_like(self.gradient)
+        self.difference = torch.zeros_like(self.gradient)
+        self.cg_method = cfg.get("AlgoCG", "cg_method")
+        self.cg_periodic_restart = cfg.getboolean("AlgoCG", "cg_periodic_restart")
+        self.cg_periodic_its = cfg.getint("AlgoCG", "cg_periodic_its")
+        self.cg_relative_restart = cfg.getboolean("AlgoCG", "cg_relative_restart")
+        self.cg_restart_tol = cfg.getfloat("AlgoCG", "cg_restart_tol")
+        self.memory = 0
+        self.beta = 0.0
+
+    def compute_beta(self) -> None:
+        """``ncg.py:105-182``."""
+        if self.iteration == 0:
+            self.beta = 0.0
+            return
+        sp = self.form_handler.scalar_product
+        g, gp, d, y = self.gradient, self.gradient_prev, self.search_direction, self.difference
+        m = self.cg_method.casefold()
+        if m != "fr":
+            torch.sub(g, gp, out=y)
+        if m == "fr":
+            self.beta = sp(g, g) / sp(gp, gp)
+        elif m == "pr":
+            self.beta = sp(g, y) / sp(gp, gp)
+        elif m == "hs":
+            self.beta = sp(g, y) / sp(y, d)
+        elif m == "dy":
+            self.beta = sp(g, g) / sp(d, y)
+        elif m == "hz":
+            dy = sp(d, y)
+            y2 = sp(y, y)
+            y.add_(d, alpha=-2.0 * y2 / dy)
+            self.beta = sp(y, g) / dy
+        else:
+            from cashocs_b200 import _exceptions
+
+            raise _exceptions.ConfigError([f"[AlgoCG] cg_method = {self.cg_method!r} is not one of FR, PR, HS, DY, HZ"])
+
+    def restart(self) -> None:
+        """``ncg.py:188-212``."""
+        if self.cg_periodic_restart:
+            if self.memory < self.cg_periodic_its:
+                self.memory += 1
+            else:
+                torch.neg(self.gradient, out=self.search_direction)
+                self.memory = 0
+        if self.cg_relative_restart:
+            gg = abs(self.form_handler.scalar_product(self.gradient, self.gradient_prev))
+            if gg / self.gradient_norm**2 >= self.cg_restart_tol:
+                torch.neg(self.gradient, out=self.search_direction)
+
+    def run(self) -> None:
+        self.memory = 0
+        while True:
+            self.gradient_prev.copy_(self.gradient)
+            self.compute_gradient()
+            self.gradient_norm = self.ova.compute_gradient_norm()
+            self.compute_beta()
+            if self.convergence_test():
+                self._record()
+                break
+            # d = -g + beta d  (aypx)
+            self.search_direction.mul_(self.beta).sub_(self.gradient)
+            self.restart()
+            self.check_for_ascent()
+            self.evaluate_cost_functional()
+            self._record()
+            self.line_search.perform(self, self.search_direction, self.has_curvature_info)
+            self.iteration += 1
+            if self.nonconvergence():
+                break

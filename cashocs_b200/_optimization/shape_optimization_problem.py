@@ -120,9 +120,11 @@ class ShapeOptimizationProblem:
             self.solver = algs.GradientDescentMethod(self, line_search)
         elif algorithm == "bfgs":
             self.solver = algs.LBFGSMethod(self, line_search)
+        elif algorithm == "conjugate_gradient":
+            self.solver = algs.NonlinearCGMethod(self, line_search)
         else:
             raise _exceptions.InputError("cashocs_b200.ShapeOptimizationProblem.solve", "algorithm",
-                                         f"{algorithm!r}: the device path drives gradient_descent and bfgs")
+                                         f"{algorithm!r}: the device path drives gradient_descent, bfgs and conjugate_gradient")
         self.solver.run()
 
     def gradient_test(self, h=None, rng=None) -> float:

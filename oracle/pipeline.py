@@ -441,6 +441,66 @@ def lbfgs(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50, memory=3,
                     S.pop(0), Y.pop(0), RHO.pop(0)
 
 
+def ncg(prob: PoissonShapeProblem, method="DY", rtol=1e-2, atol=0.0, max_iter=50, periodic_restart=False,
+        periodic_its=10, relative_restart=False, restart_tol=0.25):
+    """``NonlinearCGMethod.run`` (``optimization_algorithms/ncg.py:71-103``): beta of Fletcher-Reeves,
+    Polak-Ribiere, Hestenes-Stiefel, Dai-Yuan or Hager-Zhang (``:105-169``), restarts (``:188-212``),
+    ascent check (``optimization_algorithm.py:315-331``); no curvature information for the line search."""
+    sp = prob.scalar_product
+    stepsize = prob.cfg.initial_stepsize
+    hist = []
+    g = np.zeros(prob.d * prob.nv)
+    d = np.zeros_like(g)
+    memory = 0
+    gnorm0 = None
+    for it in range(max_iter + 1):
+        g_prev = g
+        g = prob.compute_shape_gradient()
+        gnorm = np.sqrt(prob.gradient_norm_squared)
+        if gnorm0 is None:
+            gnorm0 = gnorm
+        beta = 0.0
+        if it > 0:
+            y = g - g_prev
+            m = method.casefold()
+            if m == "fr":
+                beta = sp(g, g) / sp(g_prev, g_prev)
+            elif m == "pr":
+                beta = sp(g, y) / sp(g_prev, g_prev)
+            elif m == "hs":
+                beta = sp(g, y) / sp(y, d)
+            elif m == "dy":
+                beta = sp(g, g) / sp(d, y)
+            elif m == "hz":
+                dy = sp(d, y)
+                y2 = sp(y, y)
+                beta = sp(y - 2.0 * y2 / dy * d, g) / dy
+            else:
+                raise ValueError(method)
+        J = prob.cost()
+        hist.append((it, J, gnorm / gnorm0, prob.current_mesh_quality, stepsize))
+        if gnorm <= atol + rtol * gnorm0:
+            return True, hist
+        if it == max_iter:
+            break
+        d = -g + beta * d
+        if periodic_restart:
+            if memory < periodic_its:
+                memory += 1
+            else:
+                d = -g
+                memory = 0
+        if relative_restart and abs(sp(g, g_prev)) / gnorm**2 >= restart_tol:
+            d = -g
+        if sp(g, d) >= 0:
+            d = -g
+        step, _, _ = armijo_step(prob, d, stepsize, J, iteration=it)
+        if step is None:
+            return False, hist
+        stepsize = step * prob.cfg.beta_armijo
+    return False, hist
+
+
 def shape_gradient_test(prob: PoissonShapeProblem, rng=None, h=None):
     """Taylor test of ``cashocs/verification.py:182-302``; returns the last convergence rate."""
     rng = rng or np.random.RandomState(300696)

@@ -132,6 +132,22 @@ def test_iteration_budgets_unit_circle(algorithm, budget):
     assert abs(sop.solver.objective_value - hist[-1][1]) < 1e-8 * abs(hist[-1][1])
 
 
+@pytest.mark.parametrize("method,budget", [("FR", 21), ("PR", 16), ("HS", 18), ("DY", 18), ("HZ", 18)])
+def test_ncg_iteration_budgets_unit_circle(method, budget):
+    """tests/test_shape_optimization.py:321-353: the NCG variants meet the reference's budgets and take exactly
+    the oracle's number of iterations (same accept / reject decisions in every line search)."""
+    dm, om = circle()
+    cfg = sop_config()
+    cfg.set("AlgoCG", "cg_method", method)
+    sop = make_sop(dm, cfg)
+    sop.solve(algorithm="ncg", rtol=1e-2, atol=0.0, max_iter=budget)
+    assert sop.solver.converged and sop.solver.relative_norm <= 1e-2
+    prob = pipeline.PoissonShapeProblem(om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02))
+    ok, hist = pipeline.ncg(prob, method=method, rtol=1e-2, max_iter=budget)
+    assert ok and len(hist) - 1 == sop.solver.iteration
+    assert abs(sop.solver.objective_value - hist[-1][1]) < 1e-8 * abs(hist[-1][1])
+
+
 def test_control_problem_matches_reference_definitions(rng):
     """tests/test_pde_problems.py:87-128: state, adjoint, gradient = textbook systems."""
     dm = cb.regular_mesh(10)

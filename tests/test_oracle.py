@@ -249,3 +249,13 @@ def test_p2_taylor_test(kind):
     prob = pipeline.PoissonShapeProblem(om, bc_markers=mk, config=cfg, state_degree=2)
     rate, rates, _ = pipeline.shape_gradient_test(prob)
     assert rate > 1.9 and min(rates) > 1.9
+
+
+@pytest.mark.parametrize("method,budget", [("FR", 21), ("PR", 16), ("HS", 18), ("DY", 18), ("HZ", 18)])
+def test_ncg_iteration_budgets_unit_circle(method, budget):
+    """tests/test_shape_optimization.py:321-353 (reference): NCG FR / PR / HS / DY / HZ reach rtol 1e-2 within
+    21 / 16 / 18 / 18 / 18 iterations on the unit-disc fixture."""
+    om = meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))
+    prob = pipeline.PoissonShapeProblem(om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02))
+    ok, hist = pipeline.ncg(prob, method=method, rtol=1e-2, max_iter=budget)
+    assert ok and hist[-1][2] <= 1e-2
