@@ -56,11 +56,54 @@ class ShapeVariableAbstractions:
         return bool(self.mesh_handler.current_mesh_quality < self.mesh_handler.mesh_quality_tol_upper)
 
 
+class ControlVariableAbstractions:
+    """Abstractions of the optimisation variables for optimal control without box constraints
+    (``cashocs/_optimization/optimal_control/control_variable_abstractions.py:36-205``)."""
+
+    def __init__(self, problem) -> None:
+        self.problem = problem
+        self.form_handler = problem.form_handler
+        self.control = problem.controls[0]
+        self.control_temp = self.control.vector.clone()
+        self.projected_difference = torch.zeros_like(self.control.vector)
+        self.deformation = None
+        self.decisions: list[tuple[str, float]] = []
+
+    def compute_decrease_measure(self, search_direction=None) -> float:
+        """``g . (u - u_temp)`` with the actual update (``:74-96``)."""
+        torch.sub(self.control.vector, self.control_temp, out=self.projected_difference)
+        return self.form_handler.scalar_product(self.problem.gradient.vector, self.projected_difference)
+
+    def compute_gradient_norm(self) -> float:
+        g = self.problem.gradient.vector
+        return float(np.sqrt(self.form_handler.scalar_product(g, g)))
+
+    def store_optimization_variables(self) -> None:
+        self.control_temp.copy_(self.control.vector)
+
+    def revert_variable_update(self) -> None:
+        self.control.vector.copy_(self.control_temp)
+
+    def update_optimization_variables(self, search_direction: torch.Tensor, stepsize: float, beta: float) -> float:
+        """``:109-150``: u = u_temp + stepsize * d (always admissible without constraints)."""
+        self.store_optimization_variables()
+        self.control.vector.add_(search_direction, alpha=stepsize)
+        self.decisions.append(("accept", stepsize))
+        return stepsize
+
+    def compute_a_priori_decreases(self, search_direction: torch.Tensor, stepsize: float) -> int:
+        return 0
+
+    def requires_remeshing(self) -> bool:
+        return False
+
+
 class ArmijoLineSearch:
     """Armijo backtracking (``armijo_line_search.py:36-245``)."""
 
     def __init__(self, problem) -> None:
         self.problem = problem
+        self.problem_type = getattr(problem, "problem_type", "shape")
         cfg = problem.config
         self.config = cfg
         self.form_handler = problem.form_handler
@@ -110,13 +153,17 @@ class ArmijoLineSearch:
             if self._check_for_nonconvergence(solver):
                 self.log.append(("fail_stepsize", self.stepsize))
                 return None
-            self.decrease_measure_w_o_step = self.ova.compute_decrease_measure(search_direction)
+            if self.problem_type == "shape":
+                self.decrease_measure_w_o_step = self.ova.compute_decrease_measure(search_direction)
             n0 = len(self.ova.decisions)
             self.stepsize = self.ova.update_optimization_variables(search_direction, self.stepsize, self.beta_armijo)
             self.log.extend(self.ova.decisions[n0:])
             current_function_value = solver.objective_value
             objective_step = self._compute_objective_at_new_iterate(current_function_value)
-            decrease_measure = self.decrease_measure_w_o_step * self.stepsize
+            if self.problem_type == "shape":  # armijo_line_search.py:204-223
+                decrease_measure = self.decrease_measure_w_o_step * self.stepsize
+            else:
+                decrease_measure = self.ova.compute_decrease_measure(search_direction)
             if objective_step < current_function_value + self.epsilon_armijo * decrease_measure:
                 self.log.append(("armijo_accept", self.stepsize))
                 if solver.iteration == 0:
@@ -144,6 +191,6 @@ class ArmijoLineSearch:
     def perform(self, solver, search_direction, has_curvature_info):
         """``line_search.py:95-150``: search, then ``post_line_search`` (scalar product update)."""
         deformation = self.search(solver, search_direction, has_curvature_info)
-        if deformation is not None:
+        if deformation is not None and self.problem_type == "shape":
             self.form_handler.update_scalar_product()  # line_search.py:247-249
         return deformation

@@ -12,6 +12,8 @@ import copy
 from cashocs_b200 import _exceptions
 from cashocs_b200._forms import forms
 from cashocs_b200._optimization import cost_functional
+from cashocs_b200._optimization import line_search as ls
+from cashocs_b200._optimization import optimization_algorithms as algs
 from cashocs_b200._pde_problems import adjoint_problem
 from cashocs_b200._pde_problems import control_gradient_problem
 from cashocs_b200._pde_problems import state_problem
@@ -59,6 +61,38 @@ class OptimalControlProblem:
             self.mesh, self.cost, self.states, self.state_problem, self.controls[0],
             self.gradient_problem.scalar_product)
 
+        # the optimisation loop sees the same surface as for shape problems
+        self.problem_type = "control"
+        self.form_handler = _ControlFormHandler(self.gradient_problem)
+        self.mesh_handler = None
+        self.optimization_variable_abstractions = ls.ControlVariableAbstractions(self)
+        self.solver = None
+
+    def solve(self, algorithm: str | None = None, rtol: float | None = None, atol: float | None = None,
+              max_iter: int | None = None) -> None:
+        """``OptimalControlProblem.solve`` (``optimal_control_problem.py:362-425``): gradient descent, L-BFGS and
+        the nonlinear CG methods with the Armijo rule; Newton is outside the hot path."""
+        from cashocs_b200._optimization.shape_optimization_problem import _algorithm_name
+
+        algorithm = _algorithm_name(algorithm or self.config.get("OptimizationRoutine", "algorithm"))
+        if rtol is not None:
+            self.config.set("OptimizationRoutine", "rtol", str(rtol))
+        if atol is not None:
+            self.config.set("OptimizationRoutine", "atol", str(atol))
+        if max_iter is not None:
+            self.config.set("OptimizationRoutine", "max_iter", str(max_iter))
+        line_search = ls.ArmijoLineSearch(self)
+        if algorithm == "gradient_descent":
+            self.solver = algs.GradientDescentMethod(self, line_search)
+        elif algorithm == "bfgs":
+            self.solver = algs.LBFGSMethod(self, line_search)
+        elif algorithm == "conjugate_gradient":
+            self.solver = algs.NonlinearCGMethod(self, line_search)
+        else:
+            raise _exceptions.InputError("cashocs_b200.OptimalControlProblem.solve", "algorithm",
+                                         f"{algorithm!r}: the device path drives gradient_descent, bfgs and conjugate_gradient")
+        self.solver.run()
+
     def compute_state_variables(self) -> None:
         self.state_problem.solve()
 
@@ -73,3 +107,17 @@ class OptimalControlProblem:
         self.state_problem.has_solution = False
         self.adjoint_problem.has_solution = False
         self.gradient_problem.has_solution = False
+
+
+class _ControlFormHandler:
+    """The part of ``ControlFormHandler`` the optimisation loop touches: the Riesz scalar product
+    (``control_form_handler.py:184-207``); the mass matrix never changes, so there is nothing to update."""
+
+    def __init__(self, gradient_problem) -> None:
+        self.gradient_problem = gradient_problem
+
+    def scalar_product(self, a, b) -> float:
+        return self.gradient_problem.scalar_product(a, b)
+
+    def update_scalar_product(self) -> None:
+        return None

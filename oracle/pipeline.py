@@ -354,7 +354,13 @@ def armijo_step(prob: PoissonShapeProblem, direction, stepsize, J_cur, iteration
         stepsize, dec = prob.update_optimization_variables(direction, stepsize)
         log.extend(dec)
         J_new = prob.evaluate_cost()
-        if J_new < J_cur + c.epsilon_armijo * dm * stepsize:
+        if getattr(prob, "is_control", False):
+            # control problems measure the decrease with the actual update (armijo_line_search.py:204-223,
+            # control_variable_abstractions.py:74-96): g . (u_new - u_old)
+            decrease = prob.scalar_product(prob.gradient, prob.u - prob.u_temp)
+        else:
+            decrease = dm * stepsize
+        if J_new < J_cur + c.epsilon_armijo * decrease:
             log.append(("armijo_accept", stepsize))
             prob.update_scalar_product()  # post_line_search (line_search.py:247-249)
             return stepsize, J_new, log
@@ -449,7 +455,7 @@ def ncg(prob: PoissonShapeProblem, method="DY", rtol=1e-2, atol=0.0, max_iter=50
     sp = prob.scalar_product
     stepsize = prob.cfg.initial_stepsize
     hist = []
-    g = np.zeros(prob.d * prob.nv)
+    g = np.zeros(prob.nv if getattr(prob, "is_control", False) else prob.d * prob.nv)
     d = np.zeros_like(g)
     memory = 0
     gnorm0 = None
@@ -580,3 +586,48 @@ class PoissonControlProblem:
         M = self.mass_matrix()
         e = self.y - self.y_d
         return 0.5 * float((M @ e) @ e) + 0.5 * self.alpha * float((M @ self.u) @ self.u)
+
+    # -- duck-typed surface of the optimisation loops (gradient_descent / lbfgs / ncg / armijo_step):
+    #    ControlVariableAbstractions (control_variable_abstractions.py:36-150) without box constraints
+    is_control = True
+    current_mesh_quality = None
+
+    @property
+    def cfg(self):
+        if not hasattr(self, "_cfg"):
+            self._cfg = ShapeConfig()
+        return self._cfg
+
+    @property
+    def gradient(self):
+        return self.g
+
+    @property
+    def nv_dofs(self):
+        return self.nv
+
+    def compute_shape_gradient(self):
+        return self.compute_gradient()
+
+    def scalar_product(self, a, b):
+        if not hasattr(self, "M"):
+            self.M = self.mass_matrix()
+        return float((self.M @ a) @ b)
+
+    def compute_decreases(self, direction, stepsize):
+        return 0
+
+    def update_optimization_variables(self, direction, stepsize):
+        self.u_temp = self.u.copy()
+        self.u = self.u_temp + stepsize * direction
+        return stepsize, [("accept", stepsize)]
+
+    def revert_transformation(self):
+        self.u = self.u_temp.copy()
+
+    def update_scalar_product(self):
+        return None
+
+    def evaluate_cost(self):
+        self.solve_state()
+        return self.cost()

@@ -169,3 +169,43 @@ def test_control_problem_matches_reference_definitions(rng):
     assert np.allclose(p.vector.cpu().numpy(), ref.p, rtol=1e-8, atol=1e-12)
     assert np.allclose(g, g0, rtol=1e-8, atol=1e-12)
     assert abs(ocp.reduced_cost_functional.evaluate() - ref.cost()) < 1e-10 * abs(ref.cost())
+
+
+CONTROL_BUDGETS = [("gd", {}, 46), ("bfgs", {}, 7), ("ncg", {"method": "FR"}, 20), ("ncg", {"method": "PR"}, 25),
+                   ("ncg", {"method": "HS"}, 27), ("ncg", {"method": "DY"}, 9), ("ncg", {"method": "HZ"}, 27),
+                   ("ncg", {"method": "DY", "periodic_restart": True, "periodic_its": 5}, 10),
+                   ("ncg", {"method": "DY", "relative_restart": True, "restart_tol": 1.0}, 24)]
+
+
+@pytest.mark.parametrize("algorithm,kwargs,budget", CONTROL_BUDGETS)
+def test_control_optimisation_budgets(algorithm, kwargs, budget):
+    """tests/test_optimal_control.py:147-195 of the reference: OptimalControlProblem.solve with gd / L-BFGS /
+    the NCG variants (incl. restarts) reaches rtol 1e-2 within the reference's budgets -- with exactly the
+    oracle's iteration counts and final cost."""
+    dm, om = cb.regular_mesh(10), meshes.regular_mesh(10)
+    yd_h = np.sin(2 * np.pi * om.coords[:, 0]) * np.sin(2 * np.pi * om.coords[:, 1])
+    y, p, u, y_d = (cb.Function(dm) for _ in range(4))
+    y_d.vector.copy_(torch.from_numpy(yd_h))
+    cfg = cb.Config()
+    cfg.set("StateSystem", "is_linear", "True")
+    cfg.set("AlgoLBFGS", "bfgs_memory_size", "3")
+    cfg.set("AlgoLBFGS", "use_bfgs_scaling", "True")
+    cfg.set("AlgoCG", "cg_method", kwargs.get("method", "PR"))
+    cfg.set("AlgoCG", "cg_periodic_restart", str(kwargs.get("periodic_restart", False)))
+    cfg.set("AlgoCG", "cg_periodic_its", str(kwargs.get("periodic_its", 5)))
+    cfg.set("AlgoCG", "cg_relative_restart", str(kwargs.get("relative_restart", False)))
+    cfg.set("AlgoCG", "cg_restart_tol", str(kwargs.get("restart_tol", 0.5)))
+    ocp = cb.OptimalControlProblem(cb.PoissonForm(source=u), cb.create_dirichlet_bcs(0.0, [1, 2, 3, 4]),
+                                   cb.IntegralFunctional(c_track=1.0, desired_state=y_d, c_control=1e-6), y, u, p, config=cfg)
+    ocp.solve(algorithm=algorithm, rtol=1e-2, atol=0.0, max_iter=budget)
+    assert ocp.solver.converged and ocp.solver.relative_norm <= 1e-2
+    prob = pipeline.PoissonControlProblem(om, yd_h, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4))
+    if algorithm == "gd":
+        ok, hist = pipeline.gradient_descent(prob, rtol=1e-2, max_iter=budget)
+    elif algorithm == "bfgs":
+        ok, hist = pipeline.lbfgs(prob, rtol=1e-2, max_iter=budget, memory=3, scaling=True)
+    else:
+        ok, hist = pipeline.ncg(prob, rtol=1e-2, max_iter=budget, **kwargs)
+    assert ok and len(hist) - 1 == ocp.solver.iteration
+    assert abs(ocp.solver.objective_value - hist[-1][1]) < 1e-8 * abs(hist[-1][1])
+    assert np.max(np.abs(u.vector.cpu().numpy() - prob.u)) < 1e-7 * np.max(np.abs(prob.u))

@@ -259,3 +259,31 @@ def test_ncg_iteration_budgets_unit_circle(method, budget):
     prob = pipeline.PoissonShapeProblem(om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02))
     ok, hist = pipeline.ncg(prob, method=method, rtol=1e-2, max_iter=budget)
     assert ok and hist[-1][2] <= 1e-2
+
+
+CONTROL_BUDGETS = [("gd", {}, 46), ("bfgs", {}, 7), ("ncg", {"method": "FR"}, 20), ("ncg", {"method": "PR"}, 25),
+                   ("ncg", {"method": "HS"}, 27), ("ncg", {"method": "DY"}, 9), ("ncg", {"method": "HZ"}, 27),
+                   ("ncg", {"method": "DY", "periodic_restart": True, "periodic_its": 5}, 10),
+                   ("ncg", {"method": "DY", "relative_restart": True, "restart_tol": 1.0}, 24)]
+
+
+def control_problem():
+    om = meshes.regular_mesh(10)
+    yd = np.sin(2 * np.pi * om.coords[:, 0]) * np.sin(2 * np.pi * om.coords[:, 1])
+    return pipeline.PoissonControlProblem(om, yd, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4))
+
+
+@pytest.mark.parametrize("algorithm,kwargs,budget", CONTROL_BUDGETS)
+def test_control_iteration_budgets(algorithm, kwargs, budget):
+    """tests/test_optimal_control.py:147-195 (reference, regular_mesh(10), y_d = sin(2 pi x) sin(2 pi y),
+    alpha = 1e-6, tests/config_ocp.ini): gd <= 46, L-BFGS(3) <= 7, NCG FR / PR / HS / DY / HZ <= 20 / 25 / 27 / 9 / 27,
+    DY with periodic restart (5) <= 10, DY with relative restart (1.0) <= 24 iterations to rtol 1e-2.
+    The oracle needs exactly one iteration less than every one of these nine budgets."""
+    prob = control_problem()
+    if algorithm == "gd":
+        ok, hist = pipeline.gradient_descent(prob, rtol=1e-2, max_iter=budget)
+    elif algorithm == "bfgs":
+        ok, hist = pipeline.lbfgs(prob, rtol=1e-2, max_iter=budget, memory=3, scaling=True)
+    else:
+        ok, hist = pipeline.ncg(prob, rtol=1e-2, max_iter=budget, **kwargs)
+    assert ok and hist[-1][2] <= 1e-2 and len(hist) - 1 == budget - 1
