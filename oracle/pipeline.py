@@ -63,6 +63,7 @@ class ShapeConfig:
     shape_bdry_fix_x: tuple = ()
     shape_bdry_fix_y: tuple = ()
     shape_bdry_fix_z: tuple = ()
+    fixed_dimensions: tuple = ()  # [ShapeGradient] fixed_dimensions (shape_form_handler.py:693-712)
     lambda_lame: float = 1.428571428571429
     damping_factor: float = 0.2
     mu_def: float = 0.35714285714285715
@@ -143,6 +144,8 @@ class PoissonShapeProblem:
             dofs.append(d * fix + k)
         for k, mk in enumerate((c.shape_bdry_fix_x, c.shape_bdry_fix_y, c.shape_bdry_fix_z)[:d]):
             dofs.append(d * self.mesh.boundary_vertices(mk) + k)
+        for k in c.fixed_dimensions:  # the whole component is removed from the scalar product
+            dofs.append(d * np.arange(self.nv) + int(k))
         return np.unique(np.concatenate(dofs)).astype(np.int64) if dofs else np.zeros(0, np.int64)
 
     def _geom(self):

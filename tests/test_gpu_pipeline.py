@@ -209,3 +209,30 @@ def test_control_optimisation_budgets(algorithm, kwargs, budget):
     assert ok and len(hist) - 1 == ocp.solver.iteration
     assert abs(ocp.solver.objective_value - hist[-1][1]) < 1e-8 * abs(hist[-1][1])
     assert np.max(np.abs(u.vector.cpu().numpy() - prob.u)) < 1e-7 * np.max(np.abs(prob.u))
+
+
+def test_angle_change_unit_circle():
+    """tests/test_shape_optimization.py:934-942: angle_change = 0.1, L-BFGS <= 15 iterations -- the a-priori step
+    reductions of _MeshHandler.compute_decreases (mesh_handler.py:329-377) included; same count as the oracle."""
+    dm, om = circle()
+    sop = make_sop(dm, sop_config(angle_change=0.1))
+    sop.solve(algorithm="bfgs", rtol=1e-2, atol=0.0, max_iter=15)
+    assert sop.solver.converged and sop.solver.relative_norm < 1e-2
+    prob = pipeline.PoissonShapeProblem(om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, angle_change=0.1))
+    ok, hist = pipeline.lbfgs(prob, rtol=1e-2, max_iter=15)
+    assert ok and len(hist) - 1 == sop.solver.iteration
+    assert np.max(np.abs(dm.coords.cpu().numpy() - prob.coords)) < 1e-8
+
+
+@pytest.mark.parametrize("k", [0, 1])
+def test_fixed_dimensions_unit_circle(k):
+    """tests/test_shape_optimization.py:945-968: fixed_dimensions = [k] -> component k of the gradient is exactly
+    zero, Taylor test rate > 1.9."""
+    dm, om = circle()
+    sop = make_sop(dm, sop_config(fixed_dimensions=[k]))
+    g = sop.compute_shape_gradient()[0].vector.view(-1, 2)
+    assert float(g[:, k].abs().max()) == 0.0 and float(g[:, 1 - k].abs().max()) > 0.0
+    prob = pipeline.PoissonShapeProblem(om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, fixed_dimensions=(k,)))
+    assert rel(g.reshape(-1).cpu().numpy(), prob.compute_shape_gradient()) < 1e-8
+    for _ in range(2):
+        assert sop.gradient_test(rng=np.random.RandomState(300696)) > 1.9

@@ -287,3 +287,19 @@ def test_control_iteration_budgets(algorithm, kwargs, budget):
     else:
         ok, hist = pipeline.ncg(prob, rtol=1e-2, max_iter=budget, **kwargs)
     assert ok and hist[-1][2] <= 1e-2 and len(hist) - 1 == budget - 1
+
+
+def test_angle_change_and_fixed_dimensions_unit_circle():
+    """tests/test_shape_optimization.py:934-968 (reference): with angle_change = 0.1 L-BFGS converges within 15
+    iterations; with fixed_dimensions = [k] component k of the shape gradient is exactly zero and the Taylor
+    test still has rate > 1.9."""
+    load = lambda: meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))  # noqa: E731
+    cfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, angle_change=0.1)
+    ok, hist = pipeline.lbfgs(pipeline.PoissonShapeProblem(load(), config=cfg), rtol=1e-2, max_iter=15)
+    assert ok and hist[-1][2] < 1e-2
+    for k in (0, 1):
+        cfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, fixed_dimensions=(k,))
+        prob = pipeline.PoissonShapeProblem(load(), config=cfg)
+        g = prob.compute_shape_gradient().reshape(-1, 2)
+        assert np.all(g[:, k] == 0.0) and np.abs(g[:, 1 - k]).max() > 0.0
+        assert pipeline.shape_gradient_test(prob)[0] > 1.9
