@@ -69,6 +69,9 @@ class ShapeConfig:
     mu_def: float = 0.35714285714285715
     mu_fix: float = 0.35714285714285715
     use_sqrt_mu: bool = False
+    inhomogeneous: bool = False          # scale the form by 1 / (|K| / max|K|)^exponent (shape_form_handler.py:628-646)
+    inhomogeneous_exponent: float = 1.0
+    update_inhomogeneous: bool = False
     volume_change: float = float("inf")
     angle_change: float = float("inf")
     tol_lower: float = 0.0
@@ -226,6 +229,11 @@ class PoissonShapeProblem:
         _, vol, G = self._geom()
         Ae = fem.elasticity_elements(vol, G, self.mu, self.cells, self.cfg.lambda_lame,
                                      self.cfg.damping_factor)
+        if self.cfg.inhomogeneous:
+            # volumes are computed at construction and only refreshed with update_inhomogeneous (:721-735)
+            if getattr(self, "_volumes", None) is None or self.cfg.update_inhomogeneous:
+                self._volumes = vol / vol.max()
+            Ae = Ae / (self._volumes ** self.cfg.inhomogeneous_exponent)[:, None, None]
         A, _ = fem.assemble_system(Ae, None, self.vcell_dofs, self.d * self.nv,
                                    self.shape_bc_dofs, 0.0)
         self.A_elas = A

@@ -236,3 +236,25 @@ def test_fixed_dimensions_unit_circle(k):
     assert rel(g.reshape(-1).cpu().numpy(), prob.compute_shape_gradient()) < 1e-8
     for _ in range(2):
         assert sop.gradient_test(rng=np.random.RandomState(300696)) > 1.9
+
+
+def test_inhomogeneous_scaling_and_sqrt_mu():
+    """tests/test_shape_optimization.py:645-670 (inhomogeneous = True, mu_fix = 1, mu_def = 10) on a mesh with
+    non-uniform cells, plus use_sqrt_mu and inhomogeneous_exponent: mu, elasticity matrix and gradient vs oracle."""
+    dm, om = cb.regular_mesh(12), meshes.regular_mesh(12)
+    pert = 0.2 / 12 * (np.random.RandomState(9).rand(*om.coords.shape) - 0.5) * (om.coords > 0) * (om.coords < 1)
+    om.coords += pert
+    dm.coords += torch.from_numpy(pert).cuda()
+    kw = dict(mu_def=10.0, mu_fix=1.0, inhomogeneous=True, inhomogeneous_exponent=0.7, use_sqrt_mu=True)
+    cfg = sop_config(shape_bdry_def="[1, 2]", shape_bdry_fix="[3, 4]", **kw)
+    sop = make_sop(dm, cfg, bc_markers=(1, 2, 3, 4))
+    prob = pipeline.PoissonShapeProblem(om, bc_markers=(1, 2, 3, 4),
+                                        config=pipeline.ShapeConfig(shape_bdry_def=(1, 2), shape_bdry_fix=(3, 4), **kw))
+    g0 = prob.compute_shape_gradient()
+    g1 = sop.compute_shape_gradient()[0].vector.cpu().numpy()
+    assert rel(sop.form_handler.mu_lame.vector.cpu().numpy(), prob.mu) < 1e-8
+    E = sop.form_handler.scalar_product_matrix.to_scipy()
+    E.sort_indices()
+    assert abs(E - prob.A_elas).max() < 1e-11 * abs(prob.A_elas).max()
+    assert rel(g1, g0) < 1e-8
+    assert sop.gradient_test(rng=np.random.RandomState(300696)) > 1.9

@@ -179,11 +179,17 @@ def test_taylor_test_and_iteration_budgets_unit_circle():
 def test_taylor_test_inhomogeneous_mu():
     """tests/test_shape_optimization.py:645-670 style: mu_fix=1, mu_def=10 on regular_mesh(20)."""
     m = meshes.regular_mesh(20)
-    cfg = pipeline.ShapeConfig(shape_bdry_def=(1, 2), shape_bdry_fix=(3, 4), mu_def=10.0, mu_fix=1.0)
+    cfg = pipeline.ShapeConfig(shape_bdry_def=(1, 2), shape_bdry_fix=(3, 4), mu_def=10.0, mu_fix=1.0, inhomogeneous=True)
     prob = pipeline.PoissonShapeProblem(m, bc_markers=(1, 2, 3, 4), config=cfg)
     assert prob.mu.min() >= 1.0 - 1e-12 and prob.mu.max() <= 10.0 + 1e-12
     rate, _, _ = pipeline.shape_gradient_test(prob)
     assert rate > 1.9
+    # non-uniform cells (the scaling 1 / (|K| / max|K|)^gamma is not constant), sqrt(mu), gamma = 0.7
+    m2 = meshes.regular_mesh(12)
+    m2.coords += 0.2 / 12 * (np.random.RandomState(9).rand(*m2.coords.shape) - 0.5) * (m2.coords > 0) * (m2.coords < 1)
+    cfg = pipeline.ShapeConfig(shape_bdry_def=(1, 2), shape_bdry_fix=(3, 4), mu_def=10.0, mu_fix=1.0, inhomogeneous=True,
+                               inhomogeneous_exponent=0.7, use_sqrt_mu=True)
+    assert pipeline.shape_gradient_test(pipeline.PoissonShapeProblem(m2, bc_markers=(1, 2, 3, 4), config=cfg))[0] > 1.9
 
 
 def test_move_revert_and_rejection(rng):
