@@ -7,6 +7,7 @@ a-posteriori mesh tests and ALE mesh moves -- hand-written CUDA for sm_100a behi
 """
 
 from cashocs_b200 import _exceptions
+from cashocs_b200 import log
 from cashocs_b200._exceptions import CashocsException, ConfigError, InputError, NotConvergedError, PETScKSPError
 from cashocs_b200._forms.expressions import Polynomial, spatial_coordinate
 from cashocs_b200._forms.forms import (DirichletBC, Function, IntegralFunctional, PoissonForm,
@@ -26,6 +27,6 @@ __all__ = [
     "APrioriMeshTester", "CashocsException", "Config", "ConfigError", "DeformationHandler", "DirichletBC",
     "Function", "InputError", "IntegralFunctional", "IntersectionTester", "LinearSolver", "Matrix", "Mesh",
     "NotConvergedError", "OptimalControlProblem", "PETScKSPError", "PoissonForm", "Polynomial",
-    "ShapeOptimizationProblem", "compute_mesh_quality", "create_dirichlet_bcs", "import_mesh", "load_config",
+    "ShapeOptimizationProblem", "compute_mesh_quality", "create_dirichlet_bcs", "import_mesh", "load_config", "log",
     "mesh_from_arrays", "regular_box_mesh", "regular_mesh", "spatial_coordinate",
 ]

@@ -22,6 +22,7 @@ import torch
 
 from cashocs_b200 import _exceptions
 from cashocs_b200 import _lib
+from cashocs_b200 import log
 from cashocs_b200._forms import expressions
 
 KspOption = dict[str, Any]
@@ -235,6 +236,7 @@ def _bc_arrays(n: int, bc_dofs, bc_vals, device):
     return flag, val
 
 
+@log.profile_execution_time("assembling the system")
 def assemble_scalar_system(
     mesh,
     c_stiff: float = 1.0,
@@ -286,6 +288,7 @@ def assemble_scalar_system(
     return (A if matrix else None), (b if rhs else None)
 
 
+@log.profile_execution_time("assembling the system")
 def assemble_elasticity_matrix(mesh, mu: torch.Tensor, lambda_lame: float, damping: float,
                                bc_flag: torch.Tensor | None = None, cell_scale: torch.Tensor | None = None,
                                A: Matrix | None = None) -> Matrix:
@@ -308,6 +311,7 @@ def assemble_elasticity_matrix(mesh, mu: torch.Tensor, lambda_lame: float, dampi
     return A
 
 
+@log.profile_execution_time("assembling the system")
 def assemble_shape_derivative(mesh, u: torch.Tensor, p: torch.Tensor, f_poly: expressions.Polynomial,
                               c_int_u: float = 1.0, bc_flag: torch.Tensor | None = None,
                               b: torch.Tensor | None = None) -> torch.Tensor:
@@ -332,6 +336,7 @@ def assemble_shape_derivative(mesh, u: torch.Tensor, p: torch.Tensor, f_poly: ex
     return b
 
 
+@log.profile_execution_time("assembling the system")
 def assemble_p2_system(space, c_stiff: float = 1.0, c_mass: float = 0.0, f_poly: expressions.Polynomial | None = None,
                        f_poly_scale: float = 1.0, f_const: float = 0.0, f_nodal: torch.Tensor | None = None,
                        f_nodal_scale: float = 1.0, bc_flag: torch.Tensor | None = None,
@@ -368,6 +373,7 @@ def assemble_p2_system(space, c_stiff: float = 1.0, c_mass: float = 0.0, f_poly:
     return (A if matrix else None), (b if rhs else None)
 
 
+@log.profile_execution_time("assembling the system")
 def assemble_p2_shape_derivative(space, u: torch.Tensor, p: torch.Tensor, f_poly: expressions.Polynomial,
                                  c_int_u: float = 1.0, bc_flag: torch.Tensor | None = None,
                                  b: torch.Tensor | None = None) -> torch.Tensor:
@@ -443,6 +449,7 @@ class LinearSolver:
             self._work = torch.empty(n_doubles, dtype=torch.float64, device=device)
         return self._work
 
+    @log.profile_execution_time("solving the linear system")
     def solve(
         self,
         function: torch.Tensor,

@@ -10,6 +10,7 @@ from __future__ import annotations
 import torch
 
 from cashocs_b200 import _lib
+from cashocs_b200 import log
 
 
 class APrioriMeshTester:
@@ -38,6 +39,7 @@ class APrioriMeshTester:
         r = red.cpu()
         return float(r[0]), float(r[1])
 
+    @log.profile_execution_time("a priori mesh testing")
     def test(self, transformation: torch.Tensor, volume_change: float, step: float = 1.0) -> bool:
         """``min_det >= 1/volume_change and max_det <= volume_change`` (``mesh_testing.py:84-132``)."""
         min_det, max_det = self.determinants(transformation, step)
@@ -75,6 +77,7 @@ class IntersectionTester:
         )
         return int(mism.item())
 
+    @log.profile_execution_time("intersection testing")
     def test(self) -> bool:
         bad = self._run() > 0
         if self.mesh.dist is not None:

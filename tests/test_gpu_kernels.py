@@ -387,3 +387,30 @@ def test_degenerate_inputs():
     with pytest.raises(cb.PETScKSPError) as e:
         cb.LinearSolver().solve(x, A=A, b=b, ksp_options={"ksp_type": "cg", "pc_type": "jacobi"})
     assert e.value.error_code == -9
+
+
+def test_trace_level_profiles_the_four_reference_timers():
+    """cashocs/log.py:361-389 wraps assemble / solve / a-priori test / intersection test
+    (linalg.py:107,483; mesh_testing.py:83,160); the same four actions are timed here with CUDA events at TRACE
+    level.  Also: a-priori test with a finite volume_change (mesh_testing.py:114-117) decides like the oracle."""
+    om, dm = oracle_mesh("cube4"), device_mesh("cube4")
+    cb.log.set_log_level(cb.log.TRACE)
+    cb.log.timings(reset=True)
+    try:
+        A, b = linalg.assemble_scalar_system(dm, 1.0, 1.0, f_poly=demo_poly(3))
+        x = torch.zeros(dm.num_vertices, dtype=torch.float64, device="cuda")
+        cb.LinearSolver().solve(x, A=A, b=b, ksp_options={"ksp_type": "cg", "pc_type": "jacobi"})
+        tester = cb.APrioriMeshTester(dm)
+        r = np.random.RandomState(11)
+        h = 0.25
+        for scale in (0.05, 0.3):
+            for vc in (1.05, 1.5, 4.0):
+                V = scale * h * (2 * r.rand(om.num_vertices, 3) - 1)
+                ok0, _, _ = quality.a_priori_test(om.coords, om.cells, V, vc)
+                assert tester.test(torch.from_numpy(V.reshape(-1)).cuda(), vc) == ok0
+        cb.IntersectionTester(dm).test()
+    finally:
+        cb.log.set_log_level(cb.log.WARNING)
+    t = cb.log.timings(reset=True)
+    assert set(t) == {"assembling the system", "solving the linear system", "a priori mesh testing", "intersection testing"}
+    assert all(n >= 1 and ms > 0.0 for n, ms in t.values()) and t["a priori mesh testing"][0] == 6

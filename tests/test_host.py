@@ -177,3 +177,24 @@ def test_quadrature_rules_are_exact():
                         got = np.sum(w * lam[:, 1] ** a * lam[:, 2] ** b * (lam[:, 3] ** c if dim == 3 else 1.0))
                         assert abs(got - exact) < 5e-16, (dim, degree, a, b, c)
     assert len(expressions.simplex_quadrature(3, 5)[1]) == 14 and len(expressions.simplex_quadrature(2, 5)[1]) == 7
+
+
+def test_log_profiling_is_off_by_default():
+    """cashocs/log.py:361-389: profiling only at TRACE level; otherwise the decorator is a plain call."""
+    from cashocs_b200 import log
+
+    calls = []
+
+    @log.profile_execution_time("unit test action")
+    def f(x):
+        calls.append(x)
+        return x + 1
+
+    log.set_log_level(log.WARNING)
+    assert f(1) == 2 and calls == [1] and "unit test action" not in log.timings()
+    log.set_log_level(log.TRACE)
+    try:
+        assert f(2) == 3  # no GPU here: still a plain call
+    finally:
+        log.set_log_level(log.WARNING)
+    assert f.__name__ == "f"
