@@ -108,6 +108,7 @@ __global__ void k_pack(int64_t n, const int32_t* __restrict__ idx, const double*
 }
 
 int64_t dist_send_len(const cb_dist* d) { return d ? d->send_off.back() : 0; }
+bool dist_is_one_sided(const cb_dist* d);
 
 // ------------------------------------------------------------------ one-sided NVLink transport
 constexpr int RED_W = 8;  // doubles per reduction message
@@ -285,6 +286,8 @@ static int p2p_allreduce(cudaStream_t s, cb_dist* d, double* buf, int n, int op)
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
+
+bool dist_is_one_sided(const cb_dist* d) { return d && d->p2p; }
 
 int dist_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs, double* sendbuf) {
   if (!d || d->neigh.empty()) return CB_OK;

@@ -30,6 +30,7 @@ int amg_prolong(cudaStream_t s, int bs, const cb_amg_level* L, const double* xc,
 int amg_dense_apply(cudaStream_t s, int n, const double* inv, const double* b, double* x, const int* done);
 int dist_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs, double* sendbuf);
 int dist_allreduce_sum(cudaStream_t s, cb_dist* d, double* buf, int n);
+bool dist_is_one_sided(const cb_dist* d);
 int64_t dist_send_len(const cb_dist* d);
 
 struct KspState {
@@ -956,7 +957,9 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
       }
       return CB_OK;
     };
-    const bool want_graph = o->use_graph >= 0;
+    // graph replay needs the one-sided transport on partitioned meshes (its exchanges are plain kernels with
+    // device-side epochs); with the NCCL send/recv fallback the loop stays eager unless forced (use_graph > 0)
+    const bool want_graph = o->use_graph > 0 || (o->use_graph == 0 && (!dist || dist_is_one_sided(dist)));
     // chunks run eagerly before the capture: warm-up (lazy kernel attributes, NCCL buffers) and, when
     // the SpMV launches are being timed with events, enough of them for a sample
     const int eager_chunks = o->profile_every > 0 ? (2 * o->profile_every + check_every - 1) / check_every : 1;

@@ -308,7 +308,8 @@ typedef struct {
   int32_t monitor;        /* 1: record the residual history (hist, up to hist_len) */
   int32_t profile_every;  /* >0: bracket every profile_every-th SpMV launch with CUDA events */
   int32_t use_graph;      /* PCG iteration as a CUDA graph (captured after the first eager chunk, replayed once
-                           * per iteration; bitwise the same result): >= 0 on (default), -1 = eager launches only */
+                           * per iteration; bitwise the same result): 0 = on (default; eager when a partitioned run
+                           * had to fall back from the one-sided transport to NCCL send/recv), 1 = always, -1 = never */
   const cb_amg* amg;      /* hierarchy for pc_type CB_PC_AMG (NULL otherwise) */
 } cb_ksp_opts;
 typedef struct {
