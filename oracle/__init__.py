@@ -26,7 +26,15 @@ test) and is pinned against everything the reference's own tests hold for this p
   against scipy ``spsolve`` of the textbook systems;
 * move / revert exactness and rejection of a +-1e3 random deformation
   ``tests/test_shape_optimization.py:157-179`` -> pinned;
-* mesh-import invariants ``tests/test_geometry.py:51-99`` on the reference's gmsh fixtures -> pinned.
+* mesh-import invariants ``tests/test_geometry.py:51-99`` on the reference's gmsh fixtures -> pinned;
+* optimiser iteration budgets: shape problems on the unit disc ``tests/test_shape_optimization.py:321-353``
+  (gd <= 32, NCG FR / PR / HS / DY / HZ <= 21 / 16 / 18 / 18 / 18, L-BFGS <= 7), ``:934-942`` (angle_change,
+  L-BFGS <= 15), ``:945-968`` (fixed dimensions) and control problems ``tests/test_optimal_control.py:147-195``
+  (gd <= 46, L-BFGS <= 7, NCG <= 20 / 25 / 27 / 9 / 27, restarts <= 10 / 24) -> pinned: the oracle needs exactly
+  one iteration less than each of these seventeen budgets, i.e. it reproduces the accept / reject sequences
+  of the reference's line searches;
+* P2 state / adjoint (``oracle/p2.py``): no reference test holds values -> validated by patch tests and
+  Taylor tests only ("parity unpinned" for the P2 element tensors).
 
 Assembled matrix entries, dof numbering, BC-row diagonals and Krylov iteration counts are
 NOT pinned by any reference test (the reference has no golden vectors): for those
