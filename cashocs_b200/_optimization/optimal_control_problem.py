@@ -92,6 +92,7 @@ class OptimalControlProblem:
             raise _exceptions.InputError("cashocs_b200.OptimalControlProblem.solve", "algorithm",
                                          f"{algorithm!r}: the device path drives gradient_descent, bfgs and conjugate_gradient")
         self.solver.run()
+        self.solver.post_processing()
 
     def compute_state_variables(self) -> None:
         self.state_problem.solve()

@@ -39,6 +39,7 @@ class OptimizationAlgorithm:
         self.stepsize = 1.0
         self.converged = False
         self.line_search_broken = False
+        self.converged_reason = 0
         self.has_curvature_info = False
         self.history: list[dict] = []
 
@@ -66,7 +67,33 @@ class OptimizationAlgorithm:
             self.has_curvature_info = False
 
     def nonconvergence(self) -> bool:
-        return self.iteration >= self.max_iter or self.line_search_broken
+        """``optimization_algorithm.py:221-236``: -1 iteration budget, -2 Armijo failure."""
+        if self.iteration >= self.max_iter:
+            self.converged_reason = -1
+        if self.line_search_broken:
+            self.converged_reason = -2
+        return self.converged_reason < 0
+
+    def post_processing(self) -> None:
+        """``optimization_algorithm.py:250-290``: a run that did not converge raises ``NotConvergedError``
+        ("Maximum number of iterations exceeded." / "Armijo rule failed.") unless ``soft_exit`` is set."""
+        if self.converged:
+            return
+        from cashocs_b200 import _exceptions
+        from cashocs_b200 import log
+
+        self.objective_value = self.cost_functional.evaluate()
+        self.gradient_norm = float("nan")
+        self.relative_norm = float("nan")
+        if self.converged_reason == -2:
+            self.iteration -= 1
+            message = "Armijo rule failed."
+        else:
+            message = "Maximum number of iterations exceeded."
+        if self.config.getboolean("OptimizationRoutine", "soft_exit"):
+            log.warning(message)
+        else:
+            raise _exceptions.NotConvergedError("Optimization Algorithm", message)
 
     def _record(self) -> None:
         self.history.append(

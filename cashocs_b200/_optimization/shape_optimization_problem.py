@@ -126,6 +126,7 @@ class ShapeOptimizationProblem:
             raise _exceptions.InputError("cashocs_b200.ShapeOptimizationProblem.solve", "algorithm",
                                          f"{algorithm!r}: the device path drives gradient_descent, bfgs and conjugate_gradient")
         self.solver.run()
+        self.solver.post_processing()
 
     def gradient_test(self, h=None, rng=None) -> float:
         from cashocs_b200 import verification

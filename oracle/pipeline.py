@@ -357,8 +357,10 @@ def armijo_step(prob: PoissonShapeProblem, direction, stepsize, J_cur, iteration
         nrm = np.sqrt(prob.scalar_product(direction, direction))
         stepsize = float(np.minimum(stepsize, 100.0 / (1.0 + nrm)))
     dinf = float(np.max(np.abs(direction)))
+    step0 = getattr(prob, "_armijo_stepsize_initial", c.initial_stepsize)
     for _ in range(max_trials):
-        if stepsize * dinf <= 1e-9:
+        # armijo_line_search.py:75-94: the step became too small, absolutely or relative to the first accepted one
+        if stepsize * dinf <= 1e-9 or stepsize / step0 <= 1e-9:
             log.append(("fail_stepsize", stepsize))
             return None, J_cur, log
         dm = prob.scalar_product(prob.gradient, direction)
@@ -373,6 +375,8 @@ def armijo_step(prob: PoissonShapeProblem, direction, stepsize, J_cur, iteration
             decrease = dm * stepsize
         if J_new < J_cur + c.epsilon_armijo * decrease:
             log.append(("armijo_accept", stepsize))
+            if iteration == 0:
+                prob._armijo_stepsize_initial = stepsize
             prob.update_scalar_product()  # post_line_search (line_search.py:247-249)
             return stepsize, J_new, log
         log.append(("armijo_reject", stepsize))

@@ -258,3 +258,32 @@ def test_inhomogeneous_scaling_and_sqrt_mu():
     assert abs(E - prob.A_elas).max() < 1e-11 * abs(prob.A_elas).max()
     assert rel(g1, g0) < 1e-8
     assert sop.gradient_test(rng=np.random.RandomState(300696)) > 1.9
+
+
+def test_nonconvergence_raises_like_the_reference():
+    """optimization_algorithm.py:238-290: a run that stops without convergence raises NotConvergedError --
+    "Armijo rule failed." for tests/test_shape_optimization.py:1003-1012 (initial_stepsize 1e-3, NCG, rtol 1e-3; same
+    number of iterations before the failure as the oracle), "Maximum number of iterations exceeded." when the budget
+    runs out -- unless soft_exit is set."""
+    dm, om = circle()
+    cfg = sop_config()
+    cfg.set("LineSearch", "initial_stepsize", "1e-3")
+    cfg.set("AlgoCG", "cg_method", "DY")
+    sop = make_sop(dm, cfg)
+    with pytest.raises(cb.NotConvergedError) as e:
+        sop.solve(algorithm="ncg", rtol=1e-3, atol=0.0, max_iter=1000)
+    assert "Armijo rule failed." in str(e.value)
+    ocfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, initial_stepsize=1e-3)
+    ok, hist = pipeline.ncg(pipeline.PoissonShapeProblem(om, config=ocfg), method="DY", rtol=1e-3, max_iter=1000)
+    assert not ok and len(hist) - 1 == sop.solver.iteration
+    dm2, _ = circle()
+    sop2 = make_sop(dm2, sop_config())
+    with pytest.raises(cb.NotConvergedError) as e:
+        sop2.solve(algorithm="gd", rtol=1e-6, atol=0.0, max_iter=2)
+    assert "Maximum number of iterations exceeded." in str(e.value)
+    dm3, _ = circle()
+    cfg3 = sop_config()
+    cfg3.set("OptimizationRoutine", "soft_exit", "True")
+    sop3 = make_sop(dm3, cfg3)
+    sop3.solve(algorithm="gd", rtol=1e-6, atol=0.0, max_iter=2)
+    assert not sop3.solver.converged and sop3.solver.iteration == 2

@@ -309,3 +309,12 @@ def test_angle_change_and_fixed_dimensions_unit_circle():
         g = prob.compute_shape_gradient().reshape(-1, 2)
         assert np.all(g[:, k] == 0.0) and np.abs(g[:, 1 - k]).max() > 0.0
         assert pipeline.shape_gradient_test(prob)[0] > 1.9
+
+
+def test_small_initial_stepsize_breaks_the_armijo_rule():
+    """tests/test_shape_optimization.py:1003-1012 (reference): initial_stepsize = 1e-3, NCG (DY), rtol 1e-3 ->
+    "Armijo rule failed." -- the step collapses below the limits of armijo_line_search.py:75-94."""
+    om = meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))
+    cfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, initial_stepsize=1e-3)
+    ok, hist = pipeline.ncg(pipeline.PoissonShapeProblem(om, config=cfg), method="DY", rtol=1e-3, max_iter=1000)
+    assert not ok and len(hist) - 1 < 1000 and hist[-1][2] > 1e-3
