@@ -287,3 +287,22 @@ def test_nonconvergence_raises_like_the_reference():
     sop3 = make_sop(dm3, cfg3)
     sop3.solve(algorithm="gd", rtol=1e-6, atol=0.0, max_iter=2)
     assert not sop3.solver.converged and sop3.solver.iteration == 2
+
+
+def test_documented_demo_shape_poisson():
+    """BASELINE configs[0]: the reference's documented shape_poisson demo (L-BFGS, rtol 5e-3, damping 0.5, default
+    direct solves) runs unchanged through the drop-in surface and converges with the oracle's iteration count."""
+    import importlib.util
+
+    path = os.path.join(os.path.dirname(GOLDEN), "..", "examples", "shape_poisson", "demo_shape_poisson.py")
+    spec = importlib.util.spec_from_file_location("demo_shape_poisson", path)
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    sop = demo.main(verbose=False)
+    assert sop.solver.converged and sop.solver.relative_norm <= 5e-3
+    om = meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))
+    ocfg = pipeline.ShapeConfig(damping_factor=0.5, lambda_lame=0.0, mu_def=1.0, mu_fix=1.0)
+    prob = pipeline.PoissonShapeProblem(om, config=ocfg)
+    ok, hist = pipeline.lbfgs(prob, rtol=5e-3, max_iter=100, memory=3, scaling=True)
+    assert ok and len(hist) - 1 == sop.solver.iteration
+    assert abs(sop.solver.objective_value - hist[-1][1]) < 1e-8 * abs(hist[-1][1])
