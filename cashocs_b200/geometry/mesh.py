@@ -294,11 +294,17 @@ def mesh_from_arrays(coords, cells, facets, facet_tags, device="cuda") -> Mesh:
 
 
 def import_mesh(path: str, device="cuda") -> Mesh:
-    """Load a mesh stored as ``.npz`` (coords, cells, facets, facet_tags).
+    """Load a mesh from a gmsh 4.1 ASCII ``.msh`` file (``cashocs_b200/io/mesh.py``) or from ``.npz``
+    (coords, cells, facets, facet_tags).
 
     The reference's ``cashocs.import_mesh`` reads XDMF/HDF5 (``cashocs/io/mesh.py:186-293``); that
     format is outside the hot path -- the committed fixtures are the
     reference's gmsh meshes converted by ``tests/golden/make_fixtures.py``.
     """
+    if str(path).endswith(".msh"):
+        from cashocs_b200.io import mesh as mesh_io
+
+        coords, cells, facets, facet_tags, _ = mesh_io.read_gmsh(path)
+        return mesh_from_arrays(coords, cells, facets, facet_tags, device=device)
     z = np.load(path)
     return mesh_from_arrays(z["coords"], z["cells"], z["facets"], z["facet_tags"], device=device)

@@ -224,3 +224,27 @@ def test_reference_config_files_load_unchanged():
     sop_cfg = cb.load_config("/root/reference/tests/config_sop.ini")
     assert sop_cfg.getfloat("ShapeGradient", "lambda_lame") == 1.428571428571429
     assert sop_cfg.getlist("ShapeGradient", "shape_bdry_def") == [1] and sop_cfg.getfloat("MeshQuality", "tol_upper") == 0.02
+
+
+def test_gmsh_reader():
+    """cashocs_b200.io.mesh.read_gmsh (the source format of cashocs-convert): a hand-written 4.1 ASCII file, and --
+    where the reference tree is present -- the reference's own mesh fixtures against the committed .npz goldens."""
+    from cashocs_b200.io import mesh as mesh_io
+
+    golden = os.path.join(os.path.dirname(__file__), "golden")
+    coords, cells, facets, ftags, ctags = mesh_io.read_gmsh(os.path.join(golden, "tiny_square.msh"))
+    assert coords.shape == (5, 2) and cells.shape == (4, 3) and np.all(ctags == 7)
+    assert np.array_equal(cells, [[0, 1, 4], [1, 2, 4], [2, 3, 4], [0, 3, 4]])
+    assert sorted(zip(map(tuple, facets), ftags)) == [((0, 1), 11), ((0, 3), 14), ((1, 2), 12), ((2, 3), 13)]
+    m = cb.import_mesh(os.path.join(golden, "tiny_square.msh"), device="cpu")
+    assert m.num_cells == 4 and m.boundary_markers == [11, 12, 13, 14]
+    assert m.boundary_vertices([11, 13]).tolist() == [0, 1, 2, 3]
+    ref = "/root/reference/tests/mesh"
+    if os.path.isdir(ref):
+        for name, rel in (("unit_circle", "unit_circle/mesh.msh"), ("mesh2d", "mesh.msh"), ("mesh3d", "mesh3.msh")):
+            c, ce, f, ft, _ = mesh_io.read_gmsh(os.path.join(ref, rel))
+            z = np.load(os.path.join(golden, name + ".npz"))
+            assert np.array_equal(c, z["coords"]) and np.array_equal(ce, np.sort(z["cells"], axis=1))
+            assert sorted(map(tuple, np.c_[f, ft])) == sorted(map(tuple, np.c_[np.sort(z["facets"], axis=1), z["facet_tags"]]))
+    with pytest.raises(cb.InputError):
+        mesh_io.read_gmsh(__file__)  # not a gmsh 4.1 ASCII file
