@@ -342,7 +342,7 @@ def main() -> None:
         avg_ms = spmv_ms / spmv_prof
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_cg_spmv<3> (elasticity PCG: w = A p, fused p.w)", "achieved": achieved,
-                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
                     "traffic_source": "profiles/r01c_ncu_full_k_cg_spmv.csv (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" if traffic else None,
                     "avg_launch_ms": avg_ms, "launches_profiled": spmv_prof, "algorithmic_bytes_per_launch": alg_bytes,
                     # fine-level launches over A per PCG iteration: w = A p and the residual after pre-smoothing
