@@ -17,8 +17,6 @@ edge dofs (``p2_numbering``).
 
 from __future__ import annotations
 
-import ctypes as C
-
 import numpy as np
 import torch
 

@@ -10,7 +10,6 @@ from __future__ import annotations
 
 import collections
 
-import numpy as np
 import torch
 
 

@@ -253,7 +253,6 @@ class AMGSymbolic:
         the owners' aggregates that appear in imported rows; they get their own halo plan.
         Returns (number of coarse ghosts, agg extended by a dummy ghost tail, coarse halo plan).
         """
-        import numpy as np
         import torch.distributed as td
 
         from cashocs_b200 import distributed

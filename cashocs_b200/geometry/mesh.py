@@ -17,7 +17,6 @@ Layout in HBM
 
 from __future__ import annotations
 
-import ctypes as C
 
 import numpy as np
 import torch
