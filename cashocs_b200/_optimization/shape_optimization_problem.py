@@ -115,6 +115,9 @@ class ShapeOptimizationProblem:
             self.config.set("OptimizationRoutine", "atol", str(atol))
         if max_iter is not None:
             self.config.set("OptimizationRoutine", "max_iter", str(max_iter))
+        from cashocs_b200.io import managers
+
+        self.output_manager = managers.OutputManager(self)
         line_search = ls.ArmijoLineSearch(self)
         if algorithm == "gradient_descent":
             self.solver = algs.GradientDescentMethod(self, line_search)

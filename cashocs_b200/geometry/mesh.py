@@ -303,7 +303,10 @@ def import_mesh(path: str, device="cuda") -> Mesh:
     if str(path).endswith(".msh"):
         from cashocs_b200.io import mesh as mesh_io
 
-        coords, cells, facets, facet_tags, _ = mesh_io.read_gmsh(path)
-        return mesh_from_arrays(coords, cells, facets, facet_tags, device=device)
+        coords, cells, facets, facet_tags, _, node_tags = mesh_io.read_gmsh(path, return_node_tags=True)
+        m = mesh_from_arrays(coords, cells, facets, facet_tags, device=device)
+        m.gmsh_node_tags = node_tags  # vertex -> gmsh node, for io.write_out_mesh
+        m.gmsh_file = str(path)
+        return m
     z = np.load(path)
     return mesh_from_arrays(z["coords"], z["cells"], z["facets"], z["facet_tags"], device=device)

@@ -37,12 +37,14 @@ def _blocks(path: str) -> dict[str, list[str]]:
     return out
 
 
-def read_gmsh(path: str):
+def read_gmsh(path: str, return_node_tags: bool = False):
     """Parse a gmsh 4.1 ASCII mesh.
 
     Returns ``(coords [Nv, d], cells [Nc, d+1], facets [Nf, d], facet_tags [Nf], cell_tags [Nc])`` with
     0-based, densely renumbered vertices (only vertices used by a cell are kept); ``d`` is the highest
-    simplex dimension present; facets are the ``d-1`` simplices carrying a physical tag.
+    simplex dimension present; facets are the ``d-1`` simplices carrying a physical tag.  With
+    ``return_node_tags`` the gmsh node tag of every kept vertex is appended (what :func:`write_out_mesh`
+    needs to put moved coordinates back into the file).
     """
     blk = _blocks(path)
     fmt = blk.get("MeshFormat", ["0"])[0].split()
@@ -113,4 +115,125 @@ def read_gmsh(path: str):
     coords = coord_of_tag[used][:, :d]
     if np.isnan(coords).any() or (facets.size and (lookup[facets] < 0).any()):
         raise _exceptions.InputError("cashocs_b200.io.mesh.read_gmsh", "path", "inconsistent node references")
-    return coords, np.sort(lookup[cells], axis=1), np.sort(lookup[facets], axis=1), facet_tags, cell_tags
+    out = (coords, np.sort(lookup[cells], axis=1), np.sort(lookup[facets], axis=1), facet_tags, cell_tags)
+    return out + (used,) if return_node_tags else out
+
+
+def gather_coordinates(mesh) -> np.ndarray | None:
+    """Global vertex coordinates on rank 0 as a host array (``cashocs/io/mesh.py:403-431``); ``None`` elsewhere.
+
+    One device->host copy of the owned vertices per rank; on a partitioned mesh the owned blocks are gathered
+    over the process group and placed by their global vertex ids.
+    """
+    owned = mesh.coords[: mesh.n_owned_vertices].detach().cpu().numpy()
+    dist = getattr(mesh, "dist", None)
+    if dist is None or dist.world == 1:
+        return owned.copy()
+    import torch.distributed as td
+
+    gids = np.asarray(mesh.global_vertex_ids[: mesh.n_owned_vertices])
+    gathered = [None] * dist.world if dist.rank == 0 else None
+    td.gather_object((gids, owned), gathered, dst=0)
+    if dist.rank != 0:
+        return None
+    n_global = int(mesh.global_offsets[-1])
+    points = np.zeros((n_global, owned.shape[1]))
+    for ids, xyz in gathered:
+        points[ids] = xyz
+    return points
+
+
+def _nodes_header(path: str) -> int:
+    with open(path, encoding="utf-8") as fh:
+        for line in fh:
+            if line.strip() == "$Nodes":
+                return int(fh.readline().split()[1])
+    raise _exceptions.InputError("cashocs_b200.io.mesh", "path", f"{path} has no $Nodes section")
+
+
+def check_mesh_compatibility(mesh, original_msh_file: str) -> None:
+    """``cashocs/io/mesh.py:489-523``: the file must hold as many nodes as the mesh has (global) vertices."""
+    dist = getattr(mesh, "dist", None)
+    n_global = int(mesh.global_offsets[-1]) if dist is not None and dist.world > 1 else mesh.num_vertices
+    n_file = _nodes_header(original_msh_file)
+    tags = getattr(mesh, "gmsh_node_tags", None)
+    if n_global != (n_file if tags is None else len(tags)) or (tags is not None and int(np.max(tags)) > _max_tag(original_msh_file)):
+        raise _exceptions.CashocsException(
+            "The mesh supplied in the configuration file is not compatible with the mesh used."
+        )
+
+
+def _max_tag(path: str) -> int:
+    with open(path, encoding="utf-8") as fh:
+        for line in fh:
+            if line.strip() == "$Nodes":
+                return int(fh.readline().split()[3])
+    return 0
+
+
+def write_out_mesh(mesh, original_msh_file: str, out_msh_file: str) -> None:
+    """Write the moved mesh as a gmsh ``.msh`` file (``cashocs/io/mesh.py:526-557``).
+
+    Only the coordinates in the ``$Nodes`` section of ``original_msh_file`` (format 4.1 ASCII) are replaced;
+    topology, entities and physical groups are copied verbatim, so the result can be handed to gmsh for
+    remeshing or re-imported.  Coordinates are printed with 17 significant digits like the reference
+    (``create_point_representation``, ``:366-401``: ``x y 0`` in 2-D), i.e. the file round-trips fp64 exactly.
+    Vertex ``v`` of the mesh belongs to gmsh node ``mesh.gmsh_node_tags[v]`` (meshes imported by
+    :func:`read_gmsh`) or to node ``v + 1`` (the reference's convention, meshes built from converted arrays).
+    """
+    import os
+
+    check_mesh_compatibility(mesh, original_msh_file)
+    points = gather_coordinates(mesh)
+    dist = getattr(mesh, "dist", None)
+    if points is not None:
+        os.makedirs(os.path.dirname(os.path.abspath(out_msh_file)), exist_ok=True)
+        tags = getattr(mesh, "gmsh_node_tags", None)
+        if tags is None:
+            vertex_of_tag = None
+        else:
+            vertex_of_tag = np.full(int(np.max(tags)) + 1, -1, dtype=np.int64)
+            vertex_of_tag[np.asarray(tags)] = np.arange(len(tags))
+        _rewrite_nodes(original_msh_file, out_msh_file, points, mesh.dim, vertex_of_tag)
+    if dist is not None and dist.world > 1:
+        import torch.distributed as td
+
+        td.barrier()
+
+
+def _rewrite_nodes(src: str, dst: str, points: np.ndarray, dim: int, vertex_of_tag) -> None:
+    with open(src, encoding="utf-8") as fh:
+        lines = fh.readlines()
+    try:
+        start = next(i for i, ln in enumerate(lines) if ln.strip() == "$Nodes")
+        stop = next(i for i, ln in enumerate(lines) if ln.strip() == "$EndNodes")
+    except StopIteration:
+        raise _exceptions.InputError("cashocs_b200.io.mesh.write_out_mesh", "original_msh_file",
+                                     "no $Nodes section") from None
+    out = lines[: start + 2]  # everything up to and including the section header line
+    nblocks = int(lines[start + 1].split()[0])
+    pos = start + 2
+    for _ in range(nblocks):
+        header = lines[pos]
+        _, _, parametric, nb = (int(t) for t in header.split())
+        if parametric:
+            raise _exceptions.InputError("cashocs_b200.io.mesh.write_out_mesh", "original_msh_file",
+                                         "parametric node blocks are not supported")
+        out.append(header)
+        out += lines[pos + 1: pos + 1 + nb]
+        for i in range(nb):
+            tag = int(lines[pos + 1 + i])
+            v = tag - 1 if vertex_of_tag is None else (int(vertex_of_tag[tag]) if tag < len(vertex_of_tag) else -1)
+            if v < 0:  # a node no cell uses (e.g. a circle centre): keep it where it was
+                out.append(lines[pos + 1 + nb + i])
+            elif dim == 2:
+                out.append(f"{points[v][0]:.16e} {points[v][1]:.16e} 0\n")
+            else:
+                out.append(f"{points[v][0]:.16e} {points[v][1]:.16e} {points[v][2]:.16e}\n")
+        pos += 1 + 2 * nb
+    if pos != stop:
+        raise _exceptions.InputError("cashocs_b200.io.mesh.write_out_mesh", "original_msh_file",
+                                     "malformed $Nodes section")
+    out += lines[stop:]
+    with open(dst, "w", encoding="utf-8") as fh:
+        fh.writelines(out)

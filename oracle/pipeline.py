@@ -375,7 +375,11 @@ def armijo_step(prob: PoissonShapeProblem, direction, stepsize, J_cur, iteration
             decrease = dm * stepsize
         if J_new < J_cur + c.epsilon_armijo * decrease:
             log.append(("armijo_accept", stepsize))
-            if iteration == 0:
+            # armijo_line_search.py:169-184: a step that leaves the mesh below tol_upper asks for remeshing (a no-op
+            # without `[Mesh] remesh`) and skips the update of the reference stepsize
+            needs_remesh = (not getattr(prob, "is_control", False)
+                            and prob.current_mesh_quality < prob.cfg.tol_upper)
+            if iteration == 0 and not needs_remesh:
                 prob._armijo_stepsize_initial = stepsize
             prob.update_scalar_product()  # post_line_search (line_search.py:247-249)
             return stepsize, J_new, log

@@ -23,6 +23,7 @@ def demo_poly(dim):
 
 def sop_config(**shape):
     cfg = cb.Config()
+    cfg.set("Output", "save_results", "False")
     cfg.set("StateSystem", "is_linear", "True")
     cfg.set("ShapeGradient", "shape_bdry_def", "[1]")
     cfg.set("ShapeGradient", "lambda_lame", "1.428571428571429")
@@ -159,6 +160,7 @@ def test_control_problem_matches_reference_definitions(rng):
     form = cb.PoissonForm(source=u)
     J = cb.IntegralFunctional(c_track=1.0, desired_state=y_d, c_control=1e-6)
     cfg = cb.Config()
+    cfg.set("Output", "save_results", "False")
     cfg.set("StateSystem", "is_linear", "True")
     ocp = cb.OptimalControlProblem(form, cb.create_dirichlet_bcs(0.0, [1, 2]), J, y, u, p, config=cfg,
                                    ksp_options=KSP, adjoint_ksp_options=KSP, gradient_ksp_options=KSP)
@@ -187,6 +189,7 @@ def test_control_optimisation_budgets(algorithm, kwargs, budget):
     y, p, u, y_d = (cb.Function(dm) for _ in range(4))
     y_d.vector.copy_(torch.from_numpy(yd_h))
     cfg = cb.Config()
+    cfg.set("Output", "save_results", "False")
     cfg.set("StateSystem", "is_linear", "True")
     cfg.set("AlgoLBFGS", "bfgs_memory_size", "3")
     cfg.set("AlgoLBFGS", "use_bfgs_scaling", "True")
@@ -306,3 +309,52 @@ def test_documented_demo_shape_poisson():
     ok, hist = pipeline.lbfgs(prob, rtol=5e-3, max_iter=100, memory=3, scaling=True)
     assert ok and len(hist) - 1 == sop.solver.iteration
     assert abs(sop.solver.objective_value - hist[-1][1]) < 1e-8 * abs(hist[-1][1])
+
+
+def test_default_is_linear_false_runs_newton_on_the_linear_state():
+    """The reference's default is ``is_linear = False`` (io/config.py:599): ``newton_solve``
+    (nonlinear_solvers/newton_solver.py:285-362).  For the linear form family Newton converges after one
+    linear solve and the state, adjoint and shape gradient equal the ``is_linear = True`` ones."""
+    dm, om = circle()
+    lin = make_sop(dm, sop_config())
+    g_lin = lin.compute_shape_gradient()[0].vector.clone()
+    y_lin = lin.states[0].vector.clone()
+
+    dm2, _ = circle()
+    cfg = sop_config()
+    cfg.set("StateSystem", "is_linear", "False")
+    sop = make_sop(dm2, cfg)
+    g = sop.compute_shape_gradient()[0].vector
+    assert sop.state_problem.newton_iterations == [1]
+    assert rel(sop.states[0].vector.cpu().numpy(), y_lin.cpu().numpy()) < 1e-9
+    assert rel(g.cpu().numpy(), g_lin.cpu().numpy()) < 1e-8
+    # an exhausted iteration budget raises like the reference does
+    sop.state_problem.newton_iter = 0
+    sop.states[0].vector.zero_()
+    sop.state_problem.has_solution = False
+    with pytest.raises(cb.NotConvergedError):
+        sop.state_problem.solve()
+
+
+def test_solve_writes_the_reference_result_files(tmp_path):
+    """io/output.py + io/managers.py: history.json / history.txt from a real run (cf. tests/test_output.py:96-107)."""
+    import json
+
+    dm, _ = circle()
+    cfg = sop_config()
+    cfg.set("Output", "save_results", "True")
+    cfg.set("Output", "save_txt", "True")
+    cfg.set("Output", "save_state", "True")
+    cfg.set("Output", "result_dir", str(tmp_path / "out"))
+    sop = make_sop(dm, cfg)
+    sop.solve(algorithm="bfgs", rtol=1e-2, atol=0.0, max_iter=7)
+    hist = json.load(open(tmp_path / "out" / "history.json"))
+    its = sop.solver.iteration
+    assert hist["iteration"] == list(range(its + 1))
+    assert hist["relative_norm"][0] == 1.0 and hist["relative_norm"][-1] <= 1e-2
+    assert hist["objective_value"] == [h["objective_value"] for h in sop.solver.history]
+    assert hist["no_state_solves"][-1] == sop.state_problem.number_of_solves
+    txt = (tmp_path / "out" / "history.txt").read_text()
+    assert "Optimization was successful." in txt and txt.count("\n") >= its + 1
+    y = np.load(tmp_path / "out" / "checkpoints" / f"state_0_{its}.npy")
+    assert np.array_equal(y, sop.states[0].vector.cpu().numpy())
