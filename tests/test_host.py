@@ -220,7 +220,10 @@ def test_reference_config_files_load_unchanged():
             rejected[f] = str(e)
     assert len(files) - len(rejected) >= 25
     for f, msg in rejected.items():
-        assert any(key in msg for key in ("use_p_laplacian", "use_distance_mu", "factor_")), (f, msg)
+        # every message is the device layer's own refusal (or a relative file path of the demo directory) --
+        # never one of the reference's validation errors
+        lines = [ln for ln in msg.splitlines() if ln.startswith(("Key", "The"))]
+        assert lines and all("outside the B200 hot path" in ln or "should point to a file" in ln for ln in lines), (f, msg)
     sop_cfg = cb.load_config("/root/reference/tests/config_sop.ini")
     assert sop_cfg.getfloat("ShapeGradient", "lambda_lame") == 1.428571428571429
     assert sop_cfg.getlist("ShapeGradient", "shape_bdry_def") == [1] and sop_cfg.getfloat("MeshQuality", "tol_upper") == 0.02

@@ -115,3 +115,62 @@ def test_time_suffix(tmp_path):
     om = managers.OutputManager(prob)
     assert om.result_dir.startswith(str(tmp_path / "out") + "_") and om.result_dir.endswith(om.suffix)
     assert os.path.isdir(om.result_dir)
+
+
+# ------------------------------------------------------------------ config boundary vs the reference's Config class
+def _config_cases():
+    text = open(os.path.join(GOLDEN, "config_cases.json")).read().replace("{GOLDEN}", GOLDEN)
+    return json.loads(text)
+
+
+def test_config_defaults_equal_the_reference():
+    ref = _config_cases()["defaults"]
+    ours = cb.Config()
+    assert ours.sections() == list(ref)
+    for section, keys in ref.items():
+        assert dict(ours[section]) == keys, section  # same keys, same order, same default strings
+
+
+def test_config_validation_matches_the_reference_case_by_case():
+    """798 configs through the reference's own ``validate_config``: same outcome (ok / ConfigError / escaping
+    ValueError), same messages in the same order, same ``getlist`` results.  The device layer may add its own
+    "outside the B200 hot path" errors after the reference's."""
+    cases = _config_cases()["cases"]
+    assert len(cases) == 798
+    for rec in cases:
+        cfg = cb.Config()
+        for sec, key, val in rec["overrides"]:
+            if not cfg.has_section(sec):
+                cfg.add_section(sec)
+            cfg.set(sec, key, val)
+        try:
+            cfg.validate_config()
+            outcome = "ok"
+        except cb.ConfigError:
+            outcome = "ConfigError"
+        except Exception as e:
+            outcome = type(e).__name__
+        extra = [e for e in cfg.config_errors if "outside the B200 hot path" in e]
+        mirrored = [e for e in cfg.config_errors if "outside the B200 hot path" not in e]
+        assert mirrored == rec["errors"], rec["overrides"]
+        if extra and rec["outcome"] == "ok":
+            assert outcome == "ConfigError", rec["overrides"]
+        else:
+            assert outcome == rec["outcome"], rec["overrides"]
+        if "getlist" in rec:
+            sec, key, _ = next(o for o in rec["overrides"] if cfg.config_scheme.get(o[0], {}).get(o[1], {}).get("type") == "list")
+            try:
+                got = cfg.getlist(sec, key)
+            except Exception as e:
+                got = "raises " + type(e).__name__
+            assert got == rec["getlist"], rec["overrides"]
+
+
+def test_unsupported_subsystems_are_refused_loudly():
+    for sec, key, val in (("ShapeGradient", "use_p_laplacian", "True"), ("Regularization", "factor_surface", "1.0"),
+                          ("LineSearch", "method", "polynomial"), ("AlgoLBFGS", "damped", "True"),
+                          ("ShapeGradient", "global_deformation", "True")):
+        cfg = cb.Config()
+        cfg.set(sec, key, val)
+        with pytest.raises(cb.ConfigError, match="outside the B200 hot path"):
+            cfg.validate_config()
