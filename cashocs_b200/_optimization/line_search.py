@@ -1,9 +1,12 @@
-"""Armijo line search (``cashocs/_optimization/line_search/armijo_line_search.py:97-245``,
-``line_search.py:152-214,251-279``) and the shape variable update loop
-(``shape_optimization/shape_variable_abstractions.py:91-135``).  Host Python: only scalars
-cross the PCIe bus, every vector operation is a device op."""
+"""Line searches (``cashocs/_optimization/line_search/``): Armijo backtracking (``armijo_line_search.py:97-245``),
+polynomial interpolation (``polynomial_line_search.py``), constant stepsize (``basic_line_search.py``), their
+common part (``line_search.py:152-214,251-279``) and the variable update loops
+(``shape_optimization/shape_variable_abstractions.py:91-135``, ``optimal_control/control_variable_abstractions.py``).
+Host Python: only scalars cross the PCIe bus, every vector operation is a device op."""
 
 from __future__ import annotations
+
+import collections
 
 import numpy as np
 import torch
@@ -98,8 +101,8 @@ class ControlVariableAbstractions:
         return False
 
 
-class ArmijoLineSearch:
-    """Armijo backtracking (``armijo_line_search.py:36-245``)."""
+class LineSearch:
+    """What all line searches share (``line_search.py:40-279``)."""
 
     def __init__(self, problem) -> None:
         self.problem = problem
@@ -117,6 +120,8 @@ class ArmijoLineSearch:
         self.armijo_stepsize_initial = self.stepsize
         self.search_direction_inf = 1.0
         self.decrease_measure_w_o_step = 1.0
+        # line_search.py:83-86: L-BFGS steps are "Newton-like", the relative stepsize criterion does not apply
+        self.is_newton_like = cfg.get("OptimizationRoutine", "algorithm").casefold() in ("bfgs", "lbfgs")
         self.log: list[tuple[str, float]] = []
 
     def initialize_stepsize(self, solver, search_direction: torch.Tensor, has_curvature_info: bool) -> None:
@@ -128,6 +133,8 @@ class ArmijoLineSearch:
             self.search_direction_inf = float(t.item())
         if has_curvature_info:
             self.stepsize = 1.0
+        if getattr(solver, "is_restarted", False):
+            self.stepsize = self.config.getfloat("LineSearch", "initial_stepsize")
         num_decreases = self.ova.compute_a_priori_decreases(search_direction, self.stepsize)
         self.stepsize /= pow(self.beta_armijo, num_decreases)
         if self.safeguard_stepsize and solver.iteration == 0:
@@ -135,20 +142,53 @@ class ArmijoLineSearch:
             self.stepsize = float(np.minimum(self.stepsize, 100.0 / (1.0 + nrm)))
 
     def _check_for_nonconvergence(self, solver) -> bool:
-        """``armijo_line_search.py:59-94``."""
+        """``armijo_line_search.py:59-94`` / ``polynomial_line_search.py:70-105``."""
         if solver.iteration >= solver.max_iter:
             return True
         if self.stepsize * self.search_direction_inf <= 1e-9:
             solver.line_search_broken = True
             return True
-        if self.stepsize / self.armijo_stepsize_initial <= 1e-9:
+        if not self.is_newton_like and self.stepsize / self.armijo_stepsize_initial <= 1e-9:
             solver.line_search_broken = True
             return True
         return False
 
+    def _compute_decrease_measure(self, search_direction) -> float:
+        """``armijo_line_search.py:204-223``."""
+        if self.problem_type == "shape":
+            return self.decrease_measure_w_o_step * self.stepsize
+        return self.ova.compute_decrease_measure(search_direction)
+
+    def search(self, solver, search_direction: torch.Tensor, has_curvature_info: bool):
+        raise NotImplementedError
+
+    def perform(self, solver, search_direction, has_curvature_info):
+        """``line_search.py:95-150``: search, then ``post_line_search`` (scalar product update)."""
+        deformation = self.search(solver, search_direction, has_curvature_info)
+        if self.problem_type == "shape":
+            self.form_handler.update_scalar_product()  # line_search.py:247-249
+        return deformation
+
+
+class ArmijoLineSearch(LineSearch):
+    """Armijo backtracking (``armijo_line_search.py:36-245``)."""
+
+    def _next_trial(self, current_function_value: float, decrease_measure: float) -> float:
+        return self.stepsize / self.beta_armijo
+
+    def _enlarge(self) -> float:
+        return self.stepsize * self.beta_armijo
+
+    def _begin(self) -> None:
+        pass
+
+    def _trial_done(self, objective_step: float) -> None:
+        pass
+
     def search(self, solver, search_direction: torch.Tensor, has_curvature_info: bool):
         """``armijo_line_search.py:97-202``; returns the accepted deformation or None."""
         self.initialize_stepsize(solver, search_direction, has_curvature_info)
+        self._begin()
         while True:
             if self._check_for_nonconvergence(solver):
                 self.log.append(("fail_stepsize", self.stepsize))
@@ -160,10 +200,8 @@ class ArmijoLineSearch:
             self.log.extend(self.ova.decisions[n0:])
             current_function_value = solver.objective_value
             objective_step = self._compute_objective_at_new_iterate(current_function_value)
-            if self.problem_type == "shape":  # armijo_line_search.py:204-223
-                decrease_measure = self.decrease_measure_w_o_step * self.stepsize
-            else:
-                decrease_measure = self.ova.compute_decrease_measure(search_direction)
+            self._trial_done(objective_step)
+            decrease_measure = self._compute_decrease_measure(search_direction)
             if objective_step < current_function_value + self.epsilon_armijo * decrease_measure:
                 self.log.append(("armijo_accept", self.stepsize))
                 if self.ova.requires_remeshing():
@@ -174,11 +212,11 @@ class ArmijoLineSearch:
                     self.armijo_stepsize_initial = self.stepsize
                 break
             self.log.append(("armijo_reject", self.stepsize))
-            self.stepsize /= self.beta_armijo
+            self.stepsize = self._next_trial(current_function_value, decrease_measure)
             self.ova.revert_variable_update()
         solver.stepsize = self.stepsize
         if not has_curvature_info:
-            self.stepsize *= self.beta_armijo
+            self.stepsize = self._enlarge()
         return self.ova.deformation
 
     def _compute_objective_at_new_iterate(self, current_function_value: float) -> float:
@@ -192,9 +230,96 @@ class ArmijoLineSearch:
             self.state_problem.revert_to_checkpoint()
             return 2.0 * abs(current_function_value)
 
-    def perform(self, solver, search_direction, has_curvature_info):
-        """``line_search.py:95-150``: search, then ``post_line_search`` (scalar product update)."""
-        deformation = self.search(solver, search_direction, has_curvature_info)
-        if deformation is not None and self.problem_type == "shape":
-            self.form_handler.update_scalar_product()  # line_search.py:247-249
-        return deformation
+
+class PolynomialLineSearch(ArmijoLineSearch):
+    """Armijo acceptance with the rejected steps replaced by the minimiser of a quadratic / cubic model through
+    the trial values (``polynomial_line_search.py:36-335``)."""
+
+    def __init__(self, problem) -> None:
+        super().__init__(problem)
+        self.factor_low = self.config.getfloat("LineSearch", "factor_low")
+        self.factor_high = self.config.getfloat("LineSearch", "factor_high")
+        self.polynomial_model = self.config.get("LineSearch", "polynomial_model").casefold()
+        self.f_vals: collections.deque[float] = collections.deque()
+        self.alpha_vals: collections.deque[float] = collections.deque()
+
+    def _begin(self) -> None:
+        self.f_vals.clear()
+        self.alpha_vals.clear()
+
+    def _trial_done(self, objective_step: float) -> None:
+        self.alpha_vals.append(self.stepsize)
+        self.f_vals.append(objective_step)
+
+    def _compute_objective_at_new_iterate(self, current_function_value: float) -> float:
+        # polynomial_line_search.py:170-172: no fallback for a failed state solve
+        self.state_problem.has_solution = False
+        return self.cost_functional.evaluate()
+
+    def _enlarge(self) -> float:
+        return self.stepsize / self.factor_high  # polynomial_line_search.py:222-223
+
+    def _next_trial(self, f_current: float, decrease_measure: float) -> float:
+        """``_compute_polynomial_stepsize`` (``:228-266``) with the two models (``:268-335``)."""
+        f, a = self.f_vals, self.alpha_vals
+        if len(f) == 1:
+            alpha = -(decrease_measure * self.stepsize**2) / (2.0 * (f[0] - f_current - decrease_measure * a[0]))
+        elif len(f) == 2:
+            r1 = f[1] - f_current - decrease_measure * a[1]
+            r0 = f[0] - f_current - decrease_measure * a[0]
+            scale = 1.0 / (a[0] ** 2 * a[1] ** 2 * (a[1] - a[0]))
+            coeffs = scale * np.array([[a[0] ** 2, -(a[1] ** 2)], [-(a[0] ** 3), a[1] ** 3]]) @ np.array([r1, r0])
+            ca, cb = coeffs
+            alpha = float((-cb + np.sqrt(cb**2 - 3 * ca * decrease_measure)) / (3 * ca))
+        else:
+            raise _exceptions.CashocsException("This code should not be reached.")
+        if alpha < self.factor_low * a[-1]:
+            stepsize = self.factor_low * a[-1]
+        elif alpha > self.factor_high * a[-1]:
+            stepsize = self.factor_high * a[-1]
+        else:
+            stepsize = alpha
+        if (self.polynomial_model == "quadratic" and len(f) == 1) or (self.polynomial_model == "cubic" and len(f) == 2):
+            f.popleft()
+            a.popleft()
+        return float(stepsize)
+
+
+class BasicLineSearch(LineSearch):
+    """Constant stepsize (``basic_line_search.py:39-172``): the configured stepsize is only reduced by the mesh
+    tests of the variable update or when the state equation cannot be solved."""
+
+    def __init__(self, problem) -> None:
+        super().__init__(problem)
+        self.constant_stepsize = self.stepsize
+
+    def search(self, solver, search_direction: torch.Tensor, has_curvature_info: bool):
+        self.stepsize = self.constant_stepsize
+        while True:
+            n0 = len(self.ova.decisions)
+            self.stepsize = self.ova.update_optimization_variables(search_direction, self.stepsize, self.beta_armijo)
+            self.log.extend(self.ova.decisions[n0:])
+            self.state_problem.has_solution = False
+            try:
+                self.cost_functional.evaluate()
+                break
+            except (_exceptions.PETScError, _exceptions.NotConvergedError):
+                if self.config.getboolean("LineSearch", "fail_if_not_converged"):
+                    raise
+                self.state_problem.revert_to_checkpoint()
+                self.stepsize /= self.beta_armijo
+                self.ova.revert_variable_update()
+        solver.stepsize = self.stepsize
+        return self.ova.deformation
+
+
+def create_line_search(problem) -> LineSearch:
+    """``[LineSearch] method`` (``cashocs/_optimization/optimization_problem.py``: armijo | polynomial | basic)."""
+    method = problem.config.get("LineSearch", "method").casefold()
+    if method == "armijo":
+        return ArmijoLineSearch(problem)
+    if method == "polynomial":
+        return PolynomialLineSearch(problem)
+    if method == "basic":
+        return BasicLineSearch(problem)
+    raise _exceptions.ConfigError([f"Key method in section LineSearch has a wrong value: {method}.\n"])

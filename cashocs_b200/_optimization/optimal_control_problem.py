@@ -84,7 +84,8 @@ class OptimalControlProblem:
         from cashocs_b200.io import managers
 
         self.output_manager = managers.OutputManager(self)
-        line_search = ls.ArmijoLineSearch(self)
+        self.config.set("OptimizationRoutine", "algorithm", algorithm)
+        line_search = ls.create_line_search(self)
         if algorithm == "gradient_descent":
             self.solver = algs.GradientDescentMethod(self, line_search)
         elif algorithm == "bfgs":

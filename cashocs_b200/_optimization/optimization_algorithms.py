@@ -40,6 +40,7 @@ class OptimizationAlgorithm:
         self.line_search_broken = False
         self.converged_reason = 0
         self.has_curvature_info = False
+        self.is_restarted = False
         self.history: list[dict] = []
         self.output_manager = getattr(problem, "output_manager", None)
 
@@ -148,6 +149,8 @@ class LBFGSMethod(OptimizationAlgorithm):
         super().__init__(problem, line_search)
         self.bfgs_memory_size = self.config.getint("AlgoLBFGS", "bfgs_memory_size")
         self.use_bfgs_scaling = self.config.getboolean("AlgoLBFGS", "use_bfgs_scaling")
+        self.bfgs_periodic_restart = self.config.getint("AlgoLBFGS", "bfgs_periodic_restart")
+        self.periodic_its = 0
         self.history_s: collections.deque = collections.deque()
         self.history_y: collections.deque = collections.deque()
         self.history_rho: collections.deque = collections.deque()
@@ -190,12 +193,28 @@ class LBFGSMethod(OptimizationAlgorithm):
         if len(self.history_s) > self.bfgs_memory_size:
             self.history_s.pop(), self.history_y.pop(), self.history_rho.pop()
 
+    def check_restart(self) -> None:
+        """``l_bfgs.py:312-334``: every ``bfgs_periodic_restart`` iterations the memory is dropped and the next
+        step is a gradient step from the configured stepsize."""
+        if self.bfgs_periodic_restart > 0:
+            if self.periodic_its < self.bfgs_periodic_restart:
+                self.periodic_its += 1
+                self.is_restarted = False
+            else:
+                torch.neg(self.gradient, out=self.search_direction)
+                self.periodic_its = 0
+                self.has_curvature_info = False
+                self.is_restarted = True
+                self.history_s.clear(), self.history_y.clear(), self.history_rho.clear()
+
     def run(self) -> None:
+        self.periodic_its = 0
         self.compute_gradient()
         self.gradient_norm = self.ova.compute_gradient_norm()
         self.converged = self.convergence_test()
         while not self.converged:
             self.compute_search_direction()
+            self.check_restart()
             self.check_for_ascent()
             self.evaluate_cost_functional()
             self._record()

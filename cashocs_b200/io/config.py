@@ -358,14 +358,10 @@ class Config(configparser.ConfigParser):
             flag("Mesh", "remesh", "remeshing needs the gmsh executable, it must be False")
         if (number("MeshQuality", "remesh_iter") or 0) > 0:
             flag("MeshQuality", "remesh_iter", "remeshing needs the gmsh executable, it must be 0")
-        if self.get("LineSearch", "method").casefold() in ("polynomial", "basic"):
-            flag("LineSearch", "method", "only the Armijo rule is built")
         if self.get("StateSystem", "backend").casefold() == "petsc":
             flag("StateSystem", "backend", "SNES is not built, use the cashocs backend")
         if boolean("AlgoLBFGS", "damped"):
             flag("AlgoLBFGS", "damped", "it must be False")
-        if (number("AlgoLBFGS", "bfgs_periodic_restart") or 0) > 0:
-            flag("AlgoLBFGS", "bfgs_periodic_restart", "it must be 0")
 
 
 def load_config(path: str) -> Config:

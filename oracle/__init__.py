@@ -33,6 +33,10 @@ test) and is pinned against everything the reference's own tests hold for this p
   (gd <= 46, L-BFGS <= 7, NCG <= 20 / 25 / 27 / 9 / 27, restarts <= 10 / 24) -> pinned: the oracle needs exactly
   one iteration less than each of these seventeen budgets, i.e. it reproduces the accept / reject sequences
   of the reference's line searches;
+* the other line searches and the restarted L-BFGS: polynomial line search ``tests/test_optimal_control.py:588-596``
+  (cubic <= 42, quadratic <= 44), constant stepsize ``:819-829`` (gd / ncg / bfgs <= 71 / 76 / 43) and
+  ``tests/test_shape_optimization.py:1144-1160`` (<= 45 / 12 / 33), ``bfgs_periodic_restart = 2``
+  ``tests/test_optimal_control.py:185-189`` (<= 17) -> pinned, again exactly budget - 1 for all nine;
 * P2 state / adjoint (``oracle/p2.py``): no reference test holds values -> validated by patch tests and
   Taylor tests only ("parity unpinned" for the P2 element tensors).
 

@@ -22,6 +22,7 @@ Restates, for the Poisson model problem of the reference's demos/tests
 
 from __future__ import annotations
 
+import collections
 import dataclasses
 
 import numpy as np
@@ -84,6 +85,10 @@ class ShapeConfig:
     epsilon_armijo: float = 1e-4
     initial_stepsize: float = 1.0
     safeguard_stepsize: bool = True
+    line_search: str = "armijo"          # [LineSearch] method: armijo | basic | polynomial
+    polynomial_model: str = "cubic"
+    factor_low: float = 0.1
+    factor_high: float = 0.5
 
 
 class PoissonShapeProblem:
@@ -347,10 +352,13 @@ class PoissonShapeProblem:
 
 
 def armijo_step(prob: PoissonShapeProblem, direction, stepsize, J_cur, iteration=0,
-                has_curvature_info=False, max_trials=60):
-    """One Armijo line search; returns (stepsize, J_new, log of decisions)."""
+                has_curvature_info=False, max_trials=60, newton_like=False, polynomial=False):
+    """One Armijo line search (``armijo_line_search.py:96-202``); returns (stepsize, J_new, log of decisions).
+    ``newton_like`` (L-BFGS) drops the relative stepsize criterion (``:79-83``).  ``polynomial`` replaces the
+    backtracking by the quadratic / cubic interpolation of ``polynomial_line_search.py:228-335``."""
     c = prob.cfg
     log = []
+    f_vals, alpha_vals = collections.deque(), collections.deque()
     ndec = prob.compute_decreases(direction, stepsize)
     stepsize /= c.beta_armijo**ndec
     if c.safeguard_stepsize and iteration == 0:
@@ -360,13 +368,15 @@ def armijo_step(prob: PoissonShapeProblem, direction, stepsize, J_cur, iteration
     step0 = getattr(prob, "_armijo_stepsize_initial", c.initial_stepsize)
     for _ in range(max_trials):
         # armijo_line_search.py:75-94: the step became too small, absolutely or relative to the first accepted one
-        if stepsize * dinf <= 1e-9 or stepsize / step0 <= 1e-9:
+        if stepsize * dinf <= 1e-9 or (not newton_like and stepsize / step0 <= 1e-9):
             log.append(("fail_stepsize", stepsize))
             return None, J_cur, log
         dm = prob.scalar_product(prob.gradient, direction)
         stepsize, dec = prob.update_optimization_variables(direction, stepsize)
         log.extend(dec)
         J_new = prob.evaluate_cost()
+        alpha_vals.append(stepsize)
+        f_vals.append(J_new)
         if getattr(prob, "is_control", False):
             # control problems measure the decrease with the actual update (armijo_line_search.py:204-223,
             # control_variable_abstractions.py:74-96): g . (u_new - u_old)
@@ -384,9 +394,64 @@ def armijo_step(prob: PoissonShapeProblem, direction, stepsize, J_cur, iteration
             prob.update_scalar_product()  # post_line_search (line_search.py:247-249)
             return stepsize, J_new, log
         log.append(("armijo_reject", stepsize))
-        stepsize /= c.beta_armijo
+        if polynomial:
+            stepsize = _polynomial_stepsize(c, J_cur, decrease, f_vals, alpha_vals, stepsize)
+        else:
+            stepsize /= c.beta_armijo
         prob.revert_transformation()
     return None, J_cur, log
+
+
+def _polynomial_stepsize(c, f_current, decrease_measure, f_vals, alpha_vals, stepsize):
+    """``polynomial_line_search.py:228-335``: minimiser of the quadratic (one trial value known) or cubic (two)
+    model through f(0), f'(0) and the trial values, clamped to [factor_low, factor_high] * last trial."""
+    if len(f_vals) == 1:
+        alpha = -(decrease_measure * stepsize**2) / (2.0 * (f_vals[0] - f_current - decrease_measure * alpha_vals[0]))
+    else:
+        a0, a1 = alpha_vals[0], alpha_vals[1]
+        coeffs = (1 / (a0**2 * a1**2 * (a1 - a0))
+                  * np.array([[a0**2, -(a1**2)], [-(a0**3), a1**3]])
+                  @ np.array([f_vals[1] - f_current - decrease_measure * a1, f_vals[0] - f_current - decrease_measure * a0]))
+        a, b = coeffs
+        alpha = float((-b + np.sqrt(b**2 - 3 * a * decrease_measure)) / (3 * a))
+    alpha = min(max(alpha, c.factor_low * alpha_vals[-1]), c.factor_high * alpha_vals[-1]) if alpha == alpha else alpha
+    if (c.polynomial_model == "quadratic" and len(f_vals) == 1) or (c.polynomial_model == "cubic" and len(f_vals) == 2):
+        f_vals.popleft()
+        alpha_vals.popleft()
+    return float(alpha)
+
+
+def basic_step(prob, direction, stepsize):
+    """``BasicLineSearch.search`` (``basic_line_search.py:58-141``): the constant stepsize of the config, reduced
+    only by the mesh tests (shape problems) or when the state equation cannot be solved."""
+    log = []
+    while True:
+        stepsize, dec = prob.update_optimization_variables(direction, stepsize)
+        log.extend(dec)
+        try:
+            J_new = prob.evaluate_cost()
+            return stepsize, J_new, log
+        except RuntimeError:
+            stepsize /= prob.cfg.beta_armijo
+            prob.revert_transformation()
+
+
+def line_search(prob, direction, stepsize, J_cur, iteration=0, has_curvature_info=False, newton_like=False):
+    """Dispatch on ``[LineSearch] method``; returns (accepted stepsize or None, trial stepsize of the next call)."""
+    c = prob.cfg
+    if c.line_search == "basic":
+        step, _, _ = basic_step(prob, direction, c.initial_stepsize)
+        prob.update_scalar_product()
+        return step, c.initial_stepsize
+    polynomial = c.line_search == "polynomial"
+    step, _, _ = armijo_step(prob, direction, stepsize, J_cur, iteration=iteration, has_curvature_info=has_curvature_info,
+                             newton_like=newton_like, polynomial=polynomial)
+    if step is None:
+        return None, stepsize
+    if has_curvature_info:
+        return step, step
+    # armijo_line_search.py:196-197 / polynomial_line_search.py:222-223: no curvature information -> enlarge
+    return step, (step / c.factor_high if polynomial else step * c.beta_armijo)
 
 
 def gradient_descent(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50):
@@ -405,16 +470,17 @@ def gradient_descent(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50
             return True, hist
         if it == max_iter:
             break
-        step, _, _ = armijo_step(prob, -g, stepsize, J, iteration=it)
+        step, stepsize = line_search(prob, -g, stepsize, J, iteration=it)
         if step is None:
             return False, hist
-        stepsize = step * prob.cfg.beta_armijo  # no curvature info -> enlarge (armijo_line_search.py:196-197)
     return False, hist
 
 
-def lbfgs(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50, memory=3, scaling=True):
-    """``LBFGSMethod.run`` (``optimization_algorithms/l_bfgs.py:91-135``) with the two-loop recursion."""
+def lbfgs(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50, memory=3, scaling=True, periodic_restart=0):
+    """``LBFGSMethod.run`` (``optimization_algorithms/l_bfgs.py:91-135``) with the two-loop recursion and the
+    periodic restart of ``check_restart`` (``:312-334``)."""
     S, Y, RHO = [], [], []
+    periodic_its = 0
     stepsize = prob.cfg.initial_stepsize
     hist = []
     g = prob.compute_shape_gradient()
@@ -441,15 +507,26 @@ def lbfgs(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50, memory=3,
             q = q + (a - b) * s
         d = -q
         has_curv = len(S) > 0
+        restarted = False
+        if periodic_restart > 0:
+            if periodic_its < periodic_restart:
+                periodic_its += 1
+            else:
+                d = -g
+                periodic_its = 0
+                has_curv = False
+                restarted = True
+                S, Y, RHO = [], [], []
         if prob.scalar_product(g, d) >= 0:  # check_for_ascent (optimization_algorithm.py:315-331)
             d = -g
             S, Y, RHO = [], [], []
             has_curv = False
         trial = 1.0 if has_curv else stepsize
-        step, _, _ = armijo_step(prob, d, trial, J, iteration=it, has_curvature_info=has_curv)
+        if restarted:  # line_search.py:176-181: a restarted solver starts from the configured stepsize again
+            trial = prob.cfg.initial_stepsize
+        step, stepsize = line_search(prob, d, trial, J, iteration=it, has_curvature_info=has_curv, newton_like=True)
         if step is None:
             return False, hist
-        stepsize = step if has_curv else step * prob.cfg.beta_armijo
         g_prev = g
         g = prob.compute_shape_gradient()
         gnorm = np.sqrt(prob.gradient_norm_squared)
@@ -519,10 +596,9 @@ def ncg(prob: PoissonShapeProblem, method="DY", rtol=1e-2, atol=0.0, max_iter=50
             d = -g
         if sp(g, d) >= 0:
             d = -g
-        step, _, _ = armijo_step(prob, d, stepsize, J, iteration=it)
+        step, stepsize = line_search(prob, d, stepsize, J, iteration=it)
         if step is None:
             return False, hist
-        stepsize = step * prob.cfg.beta_armijo
     return False, hist
 
 

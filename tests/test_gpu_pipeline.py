@@ -358,3 +358,52 @@ def test_solve_writes_the_reference_result_files(tmp_path):
     assert "Optimization was successful." in txt and txt.count("\n") >= its + 1
     y = np.load(tmp_path / "out" / "checkpoints" / f"state_0_{its}.npy")
     assert np.array_equal(y, sop.states[0].vector.cpu().numpy())
+
+
+LINE_SEARCH_BUDGETS = [
+    # (problem, algorithm, [LineSearch] keys, [AlgoLBFGS] restart, oracle loop, oracle kwargs, reference budget)
+    ("control", "gd", {"method": "polynomial", "polynomial_model": "cubic"}, 0, "gradient_descent", {}, 42),
+    ("control", "ncg", {"method": "basic", "initial_stepsize": "5e2"}, 0, "ncg", {"method": "PR"}, 76),
+    ("control", "bfgs", {}, 2, "lbfgs", {"memory": 3, "periodic_restart": 2}, 17),
+    ("shape", "ncg", {"method": "basic", "initial_stepsize": "0.25"}, 0, "ncg", {"method": "DY"}, 12),
+]
+
+
+@pytest.mark.parametrize("kind,algorithm,keys,restart,loop,loop_kw,budget", LINE_SEARCH_BUDGETS)
+def test_polynomial_and_basic_line_search_and_bfgs_restart(kind, algorithm, keys, restart, loop, loop_kw, budget):
+    """tests/test_optimal_control.py:185-189,588-596,819-829 and tests/test_shape_optimization.py:1144-1160 of the
+    reference: polynomial (cubic) and constant-stepsize line searches and the periodically restarted L-BFGS reach
+    rtol 1e-2 within the reference's budgets, with the oracle's iteration counts (= budget - 1)."""
+    ocfg = {"line_search": keys.get("method", "armijo"), "polynomial_model": keys.get("polynomial_model", "cubic"),
+            "initial_stepsize": float(keys.get("initial_stepsize", 1.0))}
+    if kind == "shape":
+        dm, om = circle()
+        cfg = sop_config()
+        cfg.set("AlgoCG", "cg_method", "DY")
+        oracle = pipeline.PoissonShapeProblem(om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, **ocfg))
+    else:
+        dm, om = cb.regular_mesh(10), meshes.regular_mesh(10)
+        yd_h = np.sin(2 * np.pi * om.coords[:, 0]) * np.sin(2 * np.pi * om.coords[:, 1])
+        y, p, u, y_d = (cb.Function(dm) for _ in range(4))
+        y_d.vector.copy_(torch.from_numpy(yd_h))
+        cfg = cb.Config()
+        cfg.set("Output", "save_results", "False")
+        cfg.set("StateSystem", "is_linear", "True")
+        cfg.set("AlgoLBFGS", "bfgs_memory_size", "3")
+        cfg.set("AlgoCG", "cg_method", "PR")
+        oracle = pipeline.PoissonControlProblem(om, yd_h, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4))
+        oracle._cfg = pipeline.ShapeConfig(**ocfg)
+    for k, v in keys.items():
+        cfg.set("LineSearch", k, v)
+    cfg.set("AlgoLBFGS", "bfgs_periodic_restart", str(restart))
+    if kind == "shape":
+        prob = make_sop(dm, cfg)
+    else:
+        prob = cb.OptimalControlProblem(cb.PoissonForm(source=u), cb.create_dirichlet_bcs(0.0, [1, 2, 3, 4]),
+                                        cb.IntegralFunctional(c_track=1.0, desired_state=y_d, c_control=1e-6), y, u, p,
+                                        config=cfg)
+    prob.solve(algorithm=algorithm, rtol=1e-2, atol=0.0, max_iter=budget)
+    ok, hist = getattr(pipeline, loop)(oracle, rtol=1e-2, max_iter=budget, **loop_kw)
+    assert ok and len(hist) - 1 == budget - 1
+    assert prob.solver.converged and prob.solver.iteration == len(hist) - 1
+    assert abs(prob.solver.objective_value - hist[-1][1]) <= 1e-6 * abs(hist[-1][1])

@@ -1,0 +1,92 @@
+"""The shipped host optimisation layer (algorithms + line searches of ``cashocs_b200/_optimization``) executed on
+the CPU stand-in backend of ``tests/cpu_backend.py`` and compared with the oracle's own loops: same reference
+iteration budgets, same iterates.  The GPU tests run the identical host code on the CUDA layer."""
+
+import os
+
+import numpy as np
+import pytest
+
+import cashocs_b200 as cb
+from oracle import meshes, pipeline
+from cpu_backend import HostProblem
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def control_oracle(**cfg):
+    om = meshes.regular_mesh(10)
+    yd = np.sin(2 * np.pi * om.coords[:, 0]) * np.sin(2 * np.pi * om.coords[:, 1])
+    prob = pipeline.PoissonControlProblem(om, yd, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4))
+    prob._cfg = pipeline.ShapeConfig(**cfg)
+    return prob
+
+
+def shape_oracle(**cfg):
+    om = meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))
+    return pipeline.PoissonShapeProblem(om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, **cfg))
+
+
+def host_config(shape: bool, **keys) -> cb.Config:
+    """tests/config_sop.ini / tests/config_ocp.ini of the reference, as far as the loops read them."""
+    cfg = cb.Config()
+    cfg.set("Output", "save_results", "False")
+    cfg.set("AlgoLBFGS", "bfgs_memory_size", "3")
+    cfg.set("AlgoCG", "cg_method", "DY" if shape else "PR")
+    if shape:
+        cfg.set("MeshQuality", "tol_lower", "0.01")
+        cfg.set("MeshQuality", "tol_upper", "0.02")
+    for k, v in keys.items():
+        section = {"method": "LineSearch", "polynomial_model": "LineSearch", "initial_stepsize": "LineSearch",
+                   "bfgs_periodic_restart": "AlgoLBFGS", "cg_method": "AlgoCG", "cg_periodic_restart": "AlgoCG",
+                   "cg_periodic_its": "AlgoCG", "cg_relative_restart": "AlgoCG", "cg_restart_tol": "AlgoCG"}[k]
+        cfg.set(section, k, str(v))
+    cfg.validate_config()
+    return cfg
+
+
+# (problem, algorithm, host config keys, oracle loop, oracle kwargs, oracle config, reference budget, reference test)
+CASES = [
+    ("control", "gd", {}, "gradient_descent", {}, {}, 46, "test_optimal_control.py:147"),
+    ("control", "bfgs", {}, "lbfgs", {"memory": 3}, {}, 7, "test_optimal_control.py:180"),
+    ("control", "bfgs", {"bfgs_periodic_restart": 2}, "lbfgs", {"memory": 3, "periodic_restart": 2}, {}, 17,
+     "test_optimal_control.py:185-189"),
+    ("control", "ncg", {"cg_method": "FR"}, "ncg", {"method": "FR"}, {}, 20, "test_optimal_control.py:152"),
+    ("control", "ncg", {"cg_method": "DY", "cg_periodic_restart": True, "cg_periodic_its": 5}, "ncg",
+     {"method": "DY", "periodic_restart": True, "periodic_its": 5}, {}, 10, "test_optimal_control.py:166"),
+    ("control", "gd", {"method": "polynomial", "polynomial_model": "cubic"}, "gradient_descent", {},
+     {"line_search": "polynomial", "polynomial_model": "cubic"}, 42, "test_optimal_control.py:588-596"),
+    ("control", "gd", {"method": "polynomial", "polynomial_model": "quadratic"}, "gradient_descent", {},
+     {"line_search": "polynomial", "polynomial_model": "quadratic"}, 44, "test_optimal_control.py:588-596"),
+    ("control", "gd", {"method": "basic", "initial_stepsize": 5e2}, "gradient_descent", {},
+     {"line_search": "basic", "initial_stepsize": 5e2}, 71, "test_optimal_control.py:819-829"),
+    ("control", "ncg", {"method": "basic", "initial_stepsize": 5e2}, "ncg", {"method": "PR"},
+     {"line_search": "basic", "initial_stepsize": 5e2}, 76, "test_optimal_control.py:819-829"),
+    ("control", "bfgs", {"method": "basic", "initial_stepsize": 0.1}, "lbfgs", {"memory": 3},
+     {"line_search": "basic", "initial_stepsize": 0.1}, 43, "test_optimal_control.py:819-829"),
+    ("shape", "bfgs", {}, "lbfgs", {"memory": 3}, {}, 7, "test_shape_optimization.py:326"),
+    ("shape", "ncg", {"cg_method": "PR"}, "ncg", {"method": "PR"}, {}, 16, "test_shape_optimization.py:336"),
+    ("shape", "gd", {"method": "basic", "initial_stepsize": 0.25}, "gradient_descent", {},
+     {"line_search": "basic", "initial_stepsize": 0.25}, 45, "test_shape_optimization.py:1144-1160"),
+    ("shape", "ncg", {"method": "basic", "initial_stepsize": 0.25}, "ncg", {"method": "DY"},
+     {"line_search": "basic", "initial_stepsize": 0.25}, 12, "test_shape_optimization.py:1144-1160"),
+    ("shape", "bfgs", {"method": "basic", "initial_stepsize": 0.1}, "lbfgs", {"memory": 3},
+     {"line_search": "basic", "initial_stepsize": 0.1}, 33, "test_shape_optimization.py:1144-1160"),
+]
+
+
+@pytest.mark.parametrize("kind,algorithm,keys,loop,loop_kw,ocfg,budget,ref", CASES,
+                         ids=[f"{c[0]}-{c[1]}-{c[6]}" for c in CASES])
+def test_host_layer_reproduces_oracle_and_reference_budgets(kind, algorithm, keys, loop, loop_kw, ocfg, budget, ref):
+    make = control_oracle if kind == "control" else shape_oracle
+    # the oracle's own loop: exactly one iteration less than the reference's budget
+    ok, hist = getattr(pipeline, loop)(make(**ocfg), rtol=1e-2, max_iter=budget, **loop_kw)
+    assert ok and len(hist) - 1 == budget - 1, ref
+    # the shipped host layer on the stand-in backend: converges within the reference's budget with the same iterates
+    host = HostProblem(make(**ocfg), host_config(kind == "shape", **keys))
+    host.solve(algorithm, rtol=1e-2, atol=0.0, max_iter=budget)
+    s = host.solver
+    assert s.converged and s.relative_norm <= 1e-2 and s.iteration == len(hist) - 1, ref
+    got = np.array([[h["objective_value"], h["relative_norm"], h["stepsize"]] for h in s.history])
+    want = np.array([[h[1], h[2], 0.0] for h in hist])
+    assert np.allclose(got[:, :2], want[:, :2], rtol=1e-9, atol=0.0), ref
