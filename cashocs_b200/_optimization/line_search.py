@@ -58,15 +58,51 @@ class ShapeVariableAbstractions:
     def requires_remeshing(self) -> bool:
         return bool(self.mesh_handler.current_mesh_quality < self.mesh_handler.mesh_quality_tol_upper)
 
+    has_box_constraints = False  # shape_variable_abstractions.py:176-232: the active-set hooks are no-ops
+
+
+class BoxConstraints:
+    """Box constraints ``u_a <= u <= u_b`` of an optimal control problem
+    (``cashocs/_optimization/optimal_control/box_constraints.py:29-346``): bounds are floats or control-type
+    functions, stored as vectors next to the control; projection, active / inactive sets as element-wise ops."""
+
+    def __init__(self, control, control_constraints) -> None:
+        u = control.vector
+        if control_constraints is None:
+            control_constraints = [float("-inf"), float("inf")]
+        if len(control_constraints) != 2:
+            raise _exceptions.InputError("cashocs_b200.OptimalControlProblem", "control_constraints",
+                                         "control_constraints is [lower bound, upper bound] for the one control")
+        bounds = []
+        for b in control_constraints:
+            bounds.append(b.vector.clone() if hasattr(b, "vector") else torch.full_like(u, float(b)))
+        self.lower, self.upper = bounds
+        if not bool(torch.all(self.lower < self.upper)):
+            raise _exceptions.InputError(
+                "cashocs._optimization.optimal_control.optimal_control_problem.OptimalControlProblem",
+                "control_constraints",
+                "The lower bound must always be smaller than the upper bound for the control_constraints.")
+        self.require_control_constraints = not (float(self.lower.max()) == float("-inf")
+                                                and float(self.upper.min()) == float("inf"))
+        self.inactive = None
+
+    def project_to_admissible_set(self, a: torch.Tensor) -> torch.Tensor:
+        if self.require_control_constraints:
+            torch.minimum(self.upper, a, out=a)
+            torch.maximum(a, self.lower, out=a)
+        return a
+
 
 class ControlVariableAbstractions:
-    """Abstractions of the optimisation variables for optimal control without box constraints
-    (``cashocs/_optimization/optimal_control/control_variable_abstractions.py:36-205``)."""
+    """Abstractions of the optimisation variables for optimal control, with box constraints
+    (``cashocs/_optimization/optimal_control/control_variable_abstractions.py:36-283``)."""
 
     def __init__(self, problem) -> None:
         self.problem = problem
         self.form_handler = problem.form_handler
         self.control = problem.controls[0]
+        self.box_constraints = getattr(problem, "box_constraints", None) or BoxConstraints(self.control, None)
+        self.has_box_constraints = self.box_constraints.require_control_constraints
         self.control_temp = self.control.vector.clone()
         self.projected_difference = torch.zeros_like(self.control.vector)
         self.deformation = None
@@ -78,8 +114,15 @@ class ControlVariableAbstractions:
         return self.form_handler.scalar_product(self.problem.gradient.vector, self.projected_difference)
 
     def compute_gradient_norm(self) -> float:
+        """The stationary measure ``|u - P(u - g)|`` (``:152-191``); the gradient norm without constraints."""
         g = self.problem.gradient.vector
-        return float(np.sqrt(self.form_handler.scalar_product(g, g)))
+        if not self.has_box_constraints:
+            return float(np.sqrt(self.form_handler.scalar_product(g, g)))
+        w = self.projected_difference
+        torch.sub(self.control.vector, g, out=w)
+        self.box_constraints.project_to_admissible_set(w)
+        torch.sub(self.control.vector, w, out=w)
+        return float(np.sqrt(self.form_handler.scalar_product(w, w)))
 
     def store_optimization_variables(self) -> None:
         self.control_temp.copy_(self.control.vector)
@@ -88,9 +131,10 @@ class ControlVariableAbstractions:
         self.control.vector.copy_(self.control_temp)
 
     def update_optimization_variables(self, search_direction: torch.Tensor, stepsize: float, beta: float) -> float:
-        """``:109-150``: u = u_temp + stepsize * d (always admissible without constraints)."""
+        """``:109-150``: u = P(u_temp + stepsize * d)."""
         self.store_optimization_variables()
         self.control.vector.add_(search_direction, alpha=stepsize)
+        self.box_constraints.project_to_admissible_set(self.control.vector)
         self.decisions.append(("accept", stepsize))
         return stepsize
 
@@ -99,6 +143,33 @@ class ControlVariableAbstractions:
 
     def requires_remeshing(self) -> bool:
         return False
+
+    # -- active / inactive sets (box_constraints.py:215-324)
+    def compute_active_sets(self) -> None:
+        if self.has_box_constraints:
+            u, bc = self.control.vector, self.box_constraints
+            bc.inactive = (u > bc.lower) & (u < bc.upper)
+
+    def restrict_to_inactive_set(self, a: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        if self.has_box_constraints:
+            out.copy_(torch.where(self.box_constraints.inactive, a, torch.zeros_like(a)))
+        elif out is not a:
+            out.copy_(a)
+        return out
+
+    def restrict_to_active_set(self, a: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        if self.has_box_constraints:
+            out.copy_(torch.where(self.box_constraints.inactive, torch.zeros_like(a), a))
+        else:
+            out.zero_()
+        return out
+
+    def project_ncg_search_direction(self, search_direction: torch.Tensor) -> None:
+        """``:212-243``: no component of the direction may point out of the admissible set."""
+        if self.has_box_constraints:
+            u, bc, d = self.control.vector, self.box_constraints, search_direction
+            blocked = ((u <= bc.lower) & (d < 0.0)) | ((u >= bc.upper) & (d > 0.0))
+            d.masked_fill_(blocked, 0.0)
 
 
 class LineSearch:

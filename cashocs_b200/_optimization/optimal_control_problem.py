@@ -28,7 +28,7 @@ def _enlist(x):
 class OptimalControlProblem:
     def __init__(self, state_forms, bcs_list, cost_functional_form, states, controls, adjoints, config=None,
                  ksp_options=None, adjoint_ksp_options=None, gradient_ksp_options=None, linear_solver=None,
-                 adjoint_linear_solver=None) -> None:
+                 adjoint_linear_solver=None, control_constraints=None) -> None:
         self.state_forms = _enlist(state_forms)
         self.states, self.controls, self.adjoints = _enlist(states), _enlist(controls), _enlist(adjoints)
         if not (len(self.states) == len(self.adjoints) == len(self.state_forms) == 1 and len(self.controls) == 1):
@@ -65,6 +65,8 @@ class OptimalControlProblem:
         self.problem_type = "control"
         self.form_handler = _ControlFormHandler(self.gradient_problem)
         self.mesh_handler = None
+        # u_a <= u <= u_b, floats or Functions (optimal_control_problem.py:185-187, box_constraints.py)
+        self.box_constraints = ls.BoxConstraints(self.controls[0], control_constraints)
         self.optimization_variable_abstractions = ls.ControlVariableAbstractions(self)
         self.solver = None
 

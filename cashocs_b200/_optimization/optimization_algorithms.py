@@ -159,8 +159,11 @@ class LBFGSMethod(OptimizationAlgorithm):
     def compute_search_direction(self) -> None:
         sp = self.form_handler.scalar_product
         d = self.search_direction
+        box = self.ova.has_box_constraints  # l_bfgs.py:182-222: recursion on the inactive set + active gradient
         if self.bfgs_memory_size > 0 and len(self.history_s) > 0:
             d.copy_(self.gradient)
+            if box:
+                self.ova.restrict_to_inactive_set(d, d)
             alphas = []
             for s, y, rho in zip(self.history_s, self.history_y, self.history_rho):
                 a = rho * sp(s, d)
@@ -168,10 +171,15 @@ class LBFGSMethod(OptimizationAlgorithm):
                 d.add_(y, alpha=-a)
             if self.use_bfgs_scaling and self.iteration > 0:
                 d.mul_(sp(self.history_y[0], self.history_s[0]) / sp(self.history_y[0], self.history_y[0]))
+            if box:
+                self.ova.restrict_to_inactive_set(d, d)
             m = len(self.history_s)
             for i in range(m):
                 b = self.history_rho[-1 - i] * sp(self.history_y[-1 - i], d)
                 d.add_(self.history_s[-1 - i], alpha=alphas[-1 - i] - b)
+            if box:
+                self.ova.restrict_to_inactive_set(d, d)
+                d.add_(self.ova.restrict_to_active_set(self.gradient, torch.empty_like(d)))
             d.neg_()
         else:
             torch.neg(self.gradient, out=d)
@@ -181,6 +189,9 @@ class LBFGSMethod(OptimizationAlgorithm):
             return
         y_k = self.gradient - self.gradient_prev
         s_k = self.stepsize * self.search_direction
+        if self.ova.has_box_constraints:
+            self.ova.restrict_to_inactive_set(y_k, y_k)
+            self.ova.restrict_to_inactive_set(s_k, s_k)
         curvature = self.form_handler.scalar_product(y_k, s_k)
         self.history_y.appendleft(y_k)
         self.history_s.appendleft(s_k)
@@ -192,6 +203,10 @@ class LBFGSMethod(OptimizationAlgorithm):
             self.history_rho.appendleft(1.0 / curvature)
         if len(self.history_s) > self.bfgs_memory_size:
             self.history_s.pop(), self.history_y.pop(), self.history_rho.pop()
+
+    def _compute_active_sets(self) -> None:
+        if self.ova.has_box_constraints:
+            self.ova.compute_active_sets()
 
     def check_restart(self) -> None:
         """``l_bfgs.py:312-334``: every ``bfgs_periodic_restart`` iterations the memory is dropped and the next
@@ -210,6 +225,7 @@ class LBFGSMethod(OptimizationAlgorithm):
     def run(self) -> None:
         self.periodic_its = 0
         self.compute_gradient()
+        self._compute_active_sets()
         self.gradient_norm = self.ova.compute_gradient_norm()
         self.converged = self.convergence_test()
         while not self.converged:
@@ -224,6 +240,7 @@ class LBFGSMethod(OptimizationAlgorithm):
                 break
             self.gradient_prev.copy_(self.gradient)
             self.compute_gradient()
+            self._compute_active_sets()
             self.gradient_norm = self.ova.compute_gradient_norm()
             self.relative_norm = self.gradient_norm / self.gradient_norm_initial
             if self.convergence_test():
@@ -304,6 +321,8 @@ class NonlinearCGMethod(OptimizationAlgorithm):
             # d = -g + beta d  (aypx)
             self.search_direction.mul_(self.beta).sub_(self.gradient)
             self.restart()
+            if self.ova.has_box_constraints:
+                self.ova.project_ncg_search_direction(self.search_direction)
             self.check_for_ascent()
             self.evaluate_cost_functional()
             self._record()

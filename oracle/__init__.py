@@ -37,6 +37,9 @@ test) and is pinned against everything the reference's own tests hold for this p
   (cubic <= 42, quadratic <= 44), constant stepsize ``:819-829`` (gd / ncg / bfgs <= 71 / 76 / 43) and
   ``tests/test_shape_optimization.py:1144-1160`` (<= 45 / 12 / 33), ``bfgs_periodic_restart = 2``
   ``tests/test_optimal_control.py:185-189`` (<= 17) -> pinned, again exactly budget - 1 for all nine;
+* box-constrained controls 0 <= u <= 100 ``tests/test_optimal_control.py:196-225`` (gd <= 22, L-BFGS <= 11,
+  NCG FR / PR / HS / DY / HZ <= 47 / 24 / 30 / 9 / 37) -> pinned, exactly budget - 1 for all seven
+  (33 reference iteration counts in total);
 * P2 state / adjoint (``oracle/p2.py``): no reference test holds values -> validated by patch tests and
   Taylor tests only ("parity unpinned" for the P2 element tensors).
 

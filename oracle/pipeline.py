@@ -493,8 +493,15 @@ def lbfgs(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50, memory=3,
             return True, hist
         if it >= max_iter:
             return False, hist
-        # two-loop
+        # two-loop; with box constraints the recursion acts on the inactive set and the active part of the
+        # gradient is added back (l_bfgs.py:182-222)
+        box = getattr(prob, "has_box_constraints", False)
+        if box:
+            prob.compute_active_sets()
+        inactive = prob.restrict_to_inactive_set if box else (lambda a: a)
         q = g.copy()
+        if S:
+            q = inactive(q)
         alphas = []
         for s, y, rho in zip(reversed(S), reversed(Y), reversed(RHO)):
             a = rho * prob.scalar_product(s, q)
@@ -502,9 +509,13 @@ def lbfgs(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50, memory=3,
             q = q - a * y
         if scaling and S:
             q = q * (prob.scalar_product(Y[-1], S[-1]) / prob.scalar_product(Y[-1], Y[-1]))
+        if S:
+            q = inactive(q)
         for (s, y, rho), a in zip(zip(S, Y, RHO), reversed(alphas)):
             b = rho * prob.scalar_product(y, q)
             q = q + (a - b) * s
+        if S and box:
+            q = inactive(q) + prob.restrict_to_active_set(g)
         d = -q
         has_curv = len(S) > 0
         restarted = False
@@ -531,9 +542,11 @@ def lbfgs(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50, memory=3,
         g = prob.compute_shape_gradient()
         gnorm = np.sqrt(prob.gradient_norm_squared)
         it += 1
-        if memory > 0:
-            y = g - g_prev
-            s = step * d
+        if memory > 0 and not gnorm <= atol + rtol * gnorm0:
+            if box:
+                prob.compute_active_sets()
+            y = inactive(g - g_prev)
+            s = inactive(step * d)
             curv = prob.scalar_product(y, s)
             if curv <= 0:
                 S, Y, RHO = [], [], []
@@ -594,6 +607,8 @@ def ncg(prob: PoissonShapeProblem, method="DY", rtol=1e-2, atol=0.0, max_iter=50
                 memory = 0
         if relative_restart and abs(sp(g, g_prev)) / gnorm**2 >= restart_tol:
             d = -g
+        if getattr(prob, "has_box_constraints", False):
+            d = prob.project_ncg_search_direction(d)
         if sp(g, d) >= 0:
             d = -g
         step, stepsize = line_search(prob, d, stepsize, J, iteration=it)
@@ -631,10 +646,17 @@ class PoissonControlProblem:
     """F = grad y . grad p - u p;  J = 1/2 |y - y_d|^2 + alpha/2 |u|^2  (tests/test_pde_problems.py:59-84)."""
 
     def __init__(self, mesh, y_d, u, alpha=1e-6, bc_markers=(1, 2), state_ksp=None, adjoint_ksp=None,
-                 riesz_ksp=None):
+                 riesz_ksp=None, control_constraints=None):
         self.mesh, self.coords, self.cells = mesh, mesh.coords, mesh.cells
         self.d, self.nv = mesh.dim, mesh.num_vertices
         self.y_d, self.u, self.alpha = y_d, u, alpha
+        # box constraints u_a <= u <= u_b (optimal_control/box_constraints.py:29-182); floats or nodal arrays
+        lo, hi = control_constraints if control_constraints is not None else (-np.inf, np.inf)
+        self.u_a = np.broadcast_to(np.asarray(lo, dtype=float), (self.nv,)).copy()
+        self.u_b = np.broadcast_to(np.asarray(hi, dtype=float), (self.nv,)).copy()
+        if not np.all(self.u_a < self.u_b):
+            raise ValueError("The lower bound must always be smaller than the upper bound for the control_constraints.")
+        self.has_box_constraints = not (self.u_a.max() == -np.inf and self.u_b.min() == np.inf)
         self.bc = mesh.boundary_vertices(bc_markers)
         self.state_ksp = state_ksp or DEFAULT_KSP
         self.adjoint_ksp = adjoint_ksp or DEFAULT_KSP
@@ -674,8 +696,37 @@ class PoissonControlProblem:
         self.M = self.mass_matrix()
         self.g, reason, self.its["gradient"], _ = krylov.solve(self.M, b, self.riesz_ksp)
         PoissonShapeProblem._check(reason)
-        self.gradient_norm_squared = float((self.M @ self.g) @ self.g)
+        # stationary measure |u - P(u - g)|^2 (control_variable_abstractions.py:163-191); = |g|^2 without constraints
+        w = self.u - self.project(self.u - self.g) if self.has_box_constraints else self.g
+        self.gradient_norm_squared = float((self.M @ w) @ w)
         return self.g
+
+    # -- box constraints (optimal_control/box_constraints.py:184-346)
+    def project(self, a):
+        return np.maximum(np.minimum(self.u_b, a), self.u_a)
+
+    def compute_active_sets(self):
+        self.idx_active = np.flatnonzero((self.u <= self.u_a) | (self.u >= self.u_b))
+        self.idx_inactive = np.flatnonzero((self.u > self.u_a) & (self.u < self.u_b))
+
+    def restrict_to_inactive_set(self, a):
+        if not self.has_box_constraints:
+            return a
+        b = np.zeros_like(a)
+        b[self.idx_inactive] = a[self.idx_inactive]
+        return b
+
+    def restrict_to_active_set(self, a):
+        b = np.zeros_like(a)
+        if self.has_box_constraints:
+            b[self.idx_active] = a[self.idx_active]
+        return b
+
+    def project_ncg_search_direction(self, d):
+        """``control_variable_abstractions.py:212-243``: no step out of the admissible set."""
+        d = d.copy()
+        d[((self.u <= self.u_a) & (d < 0.0)) | ((self.u >= self.u_b) & (d > 0.0))] = 0.0
+        return d
 
     def cost(self):
         M = self.mass_matrix()
@@ -714,7 +765,7 @@ class PoissonControlProblem:
 
     def update_optimization_variables(self, direction, stepsize):
         self.u_temp = self.u.copy()
-        self.u = self.u_temp + stepsize * direction
+        self.u = self.project(self.u_temp + stepsize * direction)
         return stepsize, [("accept", stepsize)]
 
     def revert_transformation(self):

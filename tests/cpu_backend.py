@@ -102,6 +102,8 @@ class HostProblem:
             self.controls = [_Function(n)]
             self.controls[0].vector.copy_(torch.from_numpy(oracle.u))
             self.mesh_handler = None
+            bounds = [types.SimpleNamespace(vector=torch.from_numpy(b.copy())) for b in (oracle.u_a, oracle.u_b)]
+            self.box_constraints = ls.BoxConstraints(self.controls[0], bounds)
             self.optimization_variable_abstractions = ls.ControlVariableAbstractions(self)
         else:
             self.mesh_handler = _MeshHandler(oracle)

@@ -366,6 +366,10 @@ LINE_SEARCH_BUDGETS = [
     ("control", "ncg", {"method": "basic", "initial_stepsize": "5e2"}, 0, "ncg", {"method": "PR"}, 76),
     ("control", "bfgs", {}, 2, "lbfgs", {"memory": 3, "periodic_restart": 2}, 17),
     ("shape", "ncg", {"method": "basic", "initial_stepsize": "0.25"}, 0, "ncg", {"method": "DY"}, 12),
+    # box constraints 0 <= u <= 100 (tests/test_optimal_control.py:196-225, fixture ocp_cc)
+    ("control-cc", "bfgs", {}, 0, "lbfgs", {"memory": 3}, 11),
+    ("control-cc", "ncg", {}, 0, "ncg", {"method": "PR"}, 24),
+    ("control-cc", "gd", {}, 0, "gradient_descent", {}, 22),
 ]
 
 
@@ -391,7 +395,9 @@ def test_polynomial_and_basic_line_search_and_bfgs_restart(kind, algorithm, keys
         cfg.set("StateSystem", "is_linear", "True")
         cfg.set("AlgoLBFGS", "bfgs_memory_size", "3")
         cfg.set("AlgoCG", "cg_method", "PR")
-        oracle = pipeline.PoissonControlProblem(om, yd_h, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4))
+        cc = [0, 100] if kind == "control-cc" else None
+        oracle = pipeline.PoissonControlProblem(om, yd_h, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4),
+                                                control_constraints=cc)
         oracle._cfg = pipeline.ShapeConfig(**ocfg)
     for k, v in keys.items():
         cfg.set("LineSearch", k, v)
@@ -401,9 +407,11 @@ def test_polynomial_and_basic_line_search_and_bfgs_restart(kind, algorithm, keys
     else:
         prob = cb.OptimalControlProblem(cb.PoissonForm(source=u), cb.create_dirichlet_bcs(0.0, [1, 2, 3, 4]),
                                         cb.IntegralFunctional(c_track=1.0, desired_state=y_d, c_control=1e-6), y, u, p,
-                                        config=cfg)
+                                        config=cfg, control_constraints=cc)
     prob.solve(algorithm=algorithm, rtol=1e-2, atol=0.0, max_iter=budget)
     ok, hist = getattr(pipeline, loop)(oracle, rtol=1e-2, max_iter=budget, **loop_kw)
     assert ok and len(hist) - 1 == budget - 1
     assert prob.solver.converged and prob.solver.iteration == len(hist) - 1
     assert abs(prob.solver.objective_value - hist[-1][1]) <= 1e-6 * abs(hist[-1][1])
+    if kind == "control-cc":
+        assert float(u.vector.min()) >= 0.0 and float(u.vector.max()) <= 100.0

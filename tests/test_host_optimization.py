@@ -14,10 +14,11 @@ from cpu_backend import HostProblem
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def control_oracle(**cfg):
+def control_oracle(cc=None, **cfg):
     om = meshes.regular_mesh(10)
     yd = np.sin(2 * np.pi * om.coords[:, 0]) * np.sin(2 * np.pi * om.coords[:, 1])
-    prob = pipeline.PoissonControlProblem(om, yd, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4))
+    prob = pipeline.PoissonControlProblem(om, yd, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4),
+                                          control_constraints=cc)
     prob._cfg = pipeline.ShapeConfig(**cfg)
     return prob
 
@@ -64,6 +65,14 @@ CASES = [
      {"line_search": "basic", "initial_stepsize": 5e2}, 76, "test_optimal_control.py:819-829"),
     ("control", "bfgs", {"method": "basic", "initial_stepsize": 0.1}, "lbfgs", {"memory": 3},
      {"line_search": "basic", "initial_stepsize": 0.1}, 43, "test_optimal_control.py:819-829"),
+    # box constraints 0 <= u <= 100 (fixture ocp_cc)
+    ("control", "gd", {}, "gradient_descent", {}, {"cc": (0, 100)}, 22, "test_optimal_control.py:196-200"),
+    ("control", "bfgs", {}, "lbfgs", {"memory": 3}, {"cc": (0, 100)}, 11, "test_optimal_control.py:221-225"),
+    ("control", "ncg", {"cg_method": "FR"}, "ncg", {"method": "FR"}, {"cc": (0, 100)}, 47, "test_optimal_control.py:203-218"),
+    ("control", "ncg", {"cg_method": "PR"}, "ncg", {"method": "PR"}, {"cc": (0, 100)}, 24, "test_optimal_control.py:203-218"),
+    ("control", "ncg", {"cg_method": "HS"}, "ncg", {"method": "HS"}, {"cc": (0, 100)}, 30, "test_optimal_control.py:203-218"),
+    ("control", "ncg", {"cg_method": "DY"}, "ncg", {"method": "DY"}, {"cc": (0, 100)}, 9, "test_optimal_control.py:203-218"),
+    ("control", "ncg", {"cg_method": "HZ"}, "ncg", {"method": "HZ"}, {"cc": (0, 100)}, 37, "test_optimal_control.py:203-218"),
     ("shape", "bfgs", {}, "lbfgs", {"memory": 3}, {}, 7, "test_shape_optimization.py:326"),
     ("shape", "ncg", {"cg_method": "PR"}, "ncg", {"method": "PR"}, {}, 16, "test_shape_optimization.py:336"),
     ("shape", "gd", {"method": "basic", "initial_stepsize": 0.25}, "gradient_descent", {},
@@ -76,7 +85,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("kind,algorithm,keys,loop,loop_kw,ocfg,budget,ref", CASES,
-                         ids=[f"{c[0]}-{c[1]}-{c[6]}" for c in CASES])
+                         ids=[f"{c[0]}-{c[1]}-{c[6]}{'-cc' if 'cc' in c[5] else ''}" for c in CASES])
 def test_host_layer_reproduces_oracle_and_reference_budgets(kind, algorithm, keys, loop, loop_kw, ocfg, budget, ref):
     make = control_oracle if kind == "control" else shape_oracle
     # the oracle's own loop: exactly one iteration less than the reference's budget
@@ -90,3 +99,32 @@ def test_host_layer_reproduces_oracle_and_reference_budgets(kind, algorithm, key
     got = np.array([[h["objective_value"], h["relative_norm"], h["stepsize"]] for h in s.history])
     want = np.array([[h[1], h[2], 0.0] for h in hist])
     assert np.allclose(got[:, :2], want[:, :2], rtol=1e-9, atol=0.0), ref
+    if "cc" in ocfg:  # the iterate is admissible (tests/test_optimal_control.py:199-200)
+        u = host.controls[0].vector.numpy()
+        assert u.min() >= ocfg["cc"][0] and u.max() <= ocfg["cc"][1] and (u == 0.0).sum() > 4 * 10
+
+
+def test_small_stepsize_fails_like_the_reference():
+    """tests/test_optimal_control.py:562-567: initial_stepsize 1e-8 -> NotConvergedError "Armijo rule failed."."""
+    cfg = host_config(False, initial_stepsize=1e-8)
+    host = HostProblem(control_oracle(initial_stepsize=1e-8), cfg)
+    with pytest.raises(cb.NotConvergedError, match="Armijo rule failed."):
+        host.solve("gd", rtol=1e-2, atol=0.0, max_iter=2)
+    ok, hist = pipeline.gradient_descent(control_oracle(initial_stepsize=1e-8), rtol=1e-2, max_iter=2)
+    assert not ok and host.solver.converged_reason == -2
+
+
+def test_box_constraints_are_validated():
+    """box_constraints.py:106-120: the lower bound must be below the upper bound."""
+    with pytest.raises(ValueError):
+        control_oracle(cc=(1.0, 0.0))
+    import torch
+    import types
+
+    from cashocs_b200._optimization import line_search as ls
+
+    u = types.SimpleNamespace(vector=torch.zeros(4, dtype=torch.float64))
+    with pytest.raises(cb.InputError, match="lower bound must always be smaller"):
+        ls.BoxConstraints(u, [1.0, 0.0])
+    assert not ls.BoxConstraints(u, None).require_control_constraints
+    assert ls.BoxConstraints(u, [float("-inf"), 3.0]).require_control_constraints
