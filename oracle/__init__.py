@@ -43,6 +43,9 @@ test) and is pinned against everything the reference's own tests hold for this p
 * P2 state / adjoint (``oracle/p2.py``): no reference test holds values -> validated by patch tests and
   Taylor tests only ("parity unpinned" for the P2 element tensors).
 
+``oracle/amg.py`` (smoothed-aggregation multigrid in scipy) stands in for hypre BoomerAMG in the timed CPU arm of
+``bench.py``; multigrid iteration counts are "parity unpinned" like all Krylov iteration counts.
+
 Assembled matrix entries, dof numbering, BC-row diagonals and Krylov iteration counts are
 NOT pinned by any reference test (the reference has no golden vectors): for those
 quantities this oracle is "parity unpinned" and says so in DESIGN.md.

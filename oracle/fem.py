@@ -107,9 +107,9 @@ def elasticity_elements(vol, G, mu_vertex, cells, lam, delta):
     mubar = mu_vertex[cells].mean(axis=1)
     gg = np.einsum("cak,cbk->cab", G, G)
     eye = np.eye(d)
-    A = np.einsum("c,cab,ij->caibj", vol * mubar, gg, eye)
-    A += np.einsum("c,caj,cbi->caibj", vol * mubar, G, G)
-    A += lam * np.einsum("c,cai,cbj->caibj", vol, G, G)
+    A = np.einsum("c,cab,ij->caibj", vol * mubar, gg, eye, optimize=True)
+    A += np.einsum("c,caj,cbi->caibj", vol * mubar, G, G, optimize=True)
+    A += lam * np.einsum("c,cai,cbj->caibj", vol, G, G, optimize=True)
     A += delta * np.einsum("cab,ij->caibj", mass_elements(vol, d), eye)
     return A.reshape(-1, n * d, n * d)
 
@@ -120,7 +120,7 @@ def load_elements_callable(coords, cells, vol, f, degree):
     lam, w = quadrature(d, degree)
     xq = np.einsum("qa,cad->cqd", lam, coords[cells])
     fq = f(xq)  # [Nc, nq]
-    return vol[:, None] * np.einsum("cq,q,qa->ca", fq, w, lam)
+    return vol[:, None] * np.einsum("cq,q,qa->ca", fq, w, lam, optimize=True)
 
 
 def load_elements_p1(vol, cells, f_vertex, d):

@@ -202,8 +202,10 @@ def direct(A, b):
     return spla.spsolve(A.tocsc(), b), CONVERGED_ITS, 1, 0.0
 
 
-def solve(A, b, ksp_options=None, rtol=None, atol=None, history=None):
-    """Dispatch on a cashocs ``ksp_options`` dict like ``LinearSolver.solve``; b None -> x = 0."""
+def solve(A, b, ksp_options=None, rtol=None, atol=None, history=None, block_size=1, coords=None):
+    """Dispatch on a cashocs ``ksp_options`` dict like ``LinearSolver.solve``; b None -> x = 0.
+    ``block_size`` / ``coords`` describe a vector problem to the multigrid preconditioner
+    (``pc_type`` hypre / gamg -> ``oracle/amg.py``)."""
     if b is None:
         return np.zeros(A.shape[0]), CONVERGED_ATOL, 0, 0.0
     opts = dict(ksp_options) if ksp_options is not None else {"ksp_type": "preonly", "pc_type": "lu"}
@@ -227,6 +229,10 @@ def solve(A, b, ksp_options=None, rtol=None, atol=None, history=None):
         pc = None
     elif pct == "chebyshev":
         pc = chebyshev_jacobi(A, int(opts.get("pc_chebyshev_degree", 3)))
+    elif pct in ("hypre", "gamg", "amg"):
+        from oracle import amg
+
+        pc = amg.SmoothedAggregation(A, bs=block_size, coords=coords)
     else:
         raise ValueError(f"oracle: unsupported pc_type {pct}")
     if ksp == "cg":

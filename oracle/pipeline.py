@@ -263,8 +263,8 @@ class PoissonShapeProblem:
         gfq = self.grad_f(xq)[..., :d]
         pq = np.einsum("qa,ca->cq", lam, pe)
         int_u = vol * ue.mean(axis=1)
-        int_fp = vol * np.einsum("cq,cq,q->c", fq, pq, w)
-        int_gf_phi_p = vol[:, None, None] * np.einsum("cqi,cq,q,qa->cai", gfq, pq, w, lam)
+        int_fp = vol * np.einsum("cq,cq,q->c", fq, pq, w, optimize=True)
+        int_gf_phi_p = vol[:, None, None] * np.einsum("cqi,cq,q,qa->cai", gfq, pq, w, lam, optimize=True)
         gugp = np.einsum("ci,ci->c", gu, gp)
         Ggu = np.einsum("cai,ci->ca", G, gu)
         Ggp = np.einsum("cai,ci->ca", G, gp)
@@ -287,7 +287,7 @@ class PoissonShapeProblem:
         self.solve_state()
         self.solve_adjoint()
         self.dJ = self.shape_derivative_vector()
-        g, reason, its, _ = krylov.solve(self.A_elas, self.dJ, self.gradient_ksp)
+        g, reason, its, _ = krylov.solve(self.A_elas, self.dJ, self.gradient_ksp, block_size=self.d, coords=self.coords)
         self._check(reason)
         self.its["gradient"] = its
         g[self.shape_bc_dofs] = 0.0  # apply_shape_bcs (shape_form_handler.py:825-841)

@@ -318,3 +318,38 @@ def test_small_initial_stepsize_breaks_the_armijo_rule():
     cfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, initial_stepsize=1e-3)
     ok, hist = pipeline.ncg(pipeline.PoissonShapeProblem(om, config=cfg), method="DY", rtol=1e-3, max_iter=1000)
     assert not ok and len(hist) - 1 < 1000 and hist[-1][2] > 1e-3
+
+
+def test_oracle_multigrid_preconditioner():
+    """oracle/amg.py (the CPU arm's stand-in for hypre): same solutions as the direct solver, iteration counts that
+    do not grow with the mesh, rigid-body modes for the elasticity system."""
+    from oracle import amg, krylov
+
+    its = {}
+    for n in (8, 14):
+        om = meshes.regular_mesh(n, 1.0, 1.0, 1.0)
+        cfg = pipeline.ShapeConfig(shape_bdry_def=(1, 2, 3, 4, 5, 6), test_for_intersections=False)
+        prob = pipeline.PoissonShapeProblem(om, bc_markers=(1, 2, 3, 4, 5, 6), config=cfg)
+        g_direct = prob.compute_shape_gradient().copy()
+        u_direct = prob.u.copy()
+        ksp = {"ksp_type": "cg", "pc_type": "hypre", "ksp_rtol": 1e-11, "ksp_atol": 1e-30}
+        prob2 = pipeline.PoissonShapeProblem(om, bc_markers=(1, 2, 3, 4, 5, 6), config=cfg, state_ksp=ksp,
+                                             adjoint_ksp=ksp, gradient_ksp=ksp)
+        g_amg = prob2.compute_shape_gradient()
+        assert np.max(np.abs(prob2.u - u_direct)) <= 1e-8 * np.max(np.abs(u_direct))
+        assert np.max(np.abs(g_amg - g_direct)) <= 1e-8 * np.max(np.abs(g_direct))
+        its[n] = dict(prob2.its)
+        M = amg.SmoothedAggregation(prob2.A_elas, bs=3, coords=om.coords, coarsest=100)
+        # the six rigid-body modes are reproduced by the coarse space: P maps some coarse vector onto each of them
+        P = M.levels[0]["P"]
+        c = om.coords - om.coords.mean(axis=0)
+        rot = np.zeros(3 * om.num_vertices)
+        rot[0::3], rot[1::3] = -c[:, 1], c[:, 0]
+        # smoothing changes the modes only where A B != 0, i.e. by the damping term; check the tentative part:
+        # the residual of the least-squares fit of the mode in range(P) is small compared with the mode itself
+        import scipy.sparse.linalg as spla
+
+        coef = spla.lsqr(P, rot, atol=1e-12, btol=1e-12, iter_lim=2000)[0]
+        assert np.linalg.norm(P @ coef - rot) <= 5e-2 * np.linalg.norm(rot)
+    assert its[14]["gradient"] <= its[8]["gradient"] + 8 and its[14]["gradient"] <= 40
+    assert its[14]["state"] <= 35
