@@ -105,6 +105,9 @@ class ShapeFormHandler:
         self.scalar_product_matrix = self.fe_scalar_product_matrix
         self.fe_shape_derivative_vector = torch.zeros(mesh.n_owned_vertices * d, dtype=torch.float64,
                                                       device=mesh.device)
+        from cashocs_b200._forms import shape_regularization
+
+        self.shape_regularization = shape_regularization.ShapeRegularization(mesh, config, self.bc_flag)
         self.update_scalar_product()
 
     def _setup_bcs_shape(self) -> list[forms.DirichletBC]:
@@ -160,13 +163,18 @@ class ShapeFormHandler:
             raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "adjoint",
                                          "state and adjoint must use the same CG degree")
         if self.state.degree == 2:
-            return linalg.assemble_p2_shape_derivative(
+            b = linalg.assemble_p2_shape_derivative(
                 self.state.space, self.state.vector, self.adjoint.vector, f, self.cost.c_state,
                 bc_flag=self.bc_flag, b=self.fe_shape_derivative_vector)
-        return linalg.assemble_shape_derivative(
-            self.mesh, self.state.vector, self.adjoint.vector, f, self.cost.c_state, bc_flag=self.bc_flag,
-            b=self.fe_shape_derivative_vector,
-        )
+        else:
+            b = linalg.assemble_shape_derivative(
+                self.mesh, self.state.vector, self.adjoint.vector, f, self.cost.c_state, bc_flag=self.bc_flag,
+                b=self.fe_shape_derivative_vector,
+            )
+        if self.shape_regularization.is_active:  # shape_gradient_problem.py:131 + shape_regularization.py:688-698
+            self.shape_regularization.update_geometric_quantities()
+            self.shape_regularization.add_shape_derivative(b)
+        return b
 
     def apply_shape_bcs(self, function: torch.Tensor) -> None:
         """Impose the geometric constraints on a deformation (``shape_form_handler.py:825-841``)."""

@@ -1,0 +1,115 @@
+"""Geometric regularisation of shape problems (``cashocs/_forms/shape_regularization.py``): the cell-integral
+terms -- volume (``:131-222``) and barycenter (``:318-510``).  Surface and curvature regularisation need facet
+integrals and stay outside the hot path (``Config._check_supported`` refuses them).
+
+No new kernels: everything is expressed through two existing device entry points.
+
+* ``int_Omega w dx`` for a P1 field ``w`` is ``cb_functional`` -- volume with ``w = 1``, first moments with the
+  coordinate fields.
+* For a polynomial ``f`` the shape derivative of ``int_Omega f dx`` in direction ``V = phi_a e_i`` is
+  ``int (f div V + grad f . V) dx``, which is what ``cb_assemble_shape_derivative_poisson`` computes from its source
+  terms ``-G_a[i] int_K f p - int_K (d_i f) phi_a p`` when the "adjoint" is the constant ``-1`` and the "state" is
+  zero.  Both regularisations are linear combinations of ``d(vol)`` (``f = 1``) and ``d(int x_k)`` (``f = x_k``), so
+  the whole regularisation derivative is ONE launch with the affine polynomial ``f = a_0 + sum_k a_k x_k``.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from cashocs_b200 import _lib
+from cashocs_b200._forms import expressions
+from cashocs_b200._utils import linalg
+
+
+class ShapeRegularization:
+    def __init__(self, mesh, config, bc_flag) -> None:
+        self.mesh, self.config, self.bc_flag = mesh, config, bc_flag
+        d = mesh.dim
+        self.mu_volume = config.getfloat("Regularization", "factor_volume")
+        self.mu_barycenter = config.getfloat("Regularization", "factor_barycenter")
+        self.is_active = self.mu_volume > 0.0 or self.mu_barycenter > 0.0
+        if not self.is_active:
+            return
+        f64 = dict(dtype=torch.float64, device=mesh.device)
+        self._ones = torch.ones(mesh.num_vertices, **f64)
+        self._minus_ones = -self._ones
+        self._zeros = torch.zeros(mesh.num_vertices, **f64)
+        self._field = torch.zeros(mesh.num_vertices, **f64)
+        self._out = torch.zeros(1, **f64)
+        self._vector = torch.zeros(mesh.n_owned_vertices * d, **f64)
+        self.target_volume = config.getfloat("Regularization", "target_volume")
+        if config.getboolean("Regularization", "use_initial_volume"):
+            self.target_volume = self.compute_volume()
+        target = [float(t) for t in config.getlist("Regularization", "target_barycenter")]
+        self.target_barycenter = (target + [0.0] * 3)[:3]
+        if config.getboolean("Regularization", "use_initial_barycenter"):
+            self.target_barycenter = self.compute_barycenter()
+        self.current_volume = 1.0
+        self.current_barycenter = [0.0, 0.0, 0.0]
+
+    # -- geometric quantities
+    def _integral(self, w: torch.Tensor) -> float:
+        mesh = self.mesh
+        scratch = mesh.reduce_scratch()
+        _lib.check(
+            _lib.load().cb_functional(_lib.stream_ptr(), mesh.dim, mesh.n_owned_cells, _lib.ptr(mesh.coords),
+                                      _lib.ptr(mesh.cells), 1.0, _lib.ptr(w), 0.0, None, _lib.ptr(self._out),
+                                      _lib.ptr(scratch), scratch.numel()),
+            "cb_functional",
+        )
+        if mesh.dist is not None:
+            mesh.dist.allreduce(self._out, "sum")
+        return float(self._out.item())
+
+    def compute_volume(self) -> float:
+        """``_compute_volume`` (``:213-222``)."""
+        return self._integral(self._ones)
+
+    def compute_barycenter(self) -> list[float]:
+        """``_compute_barycenter_list`` (``:486-510``); z = 0 in two dimensions."""
+        volume = self.compute_volume()
+        out = [0.0, 0.0, 0.0]
+        for k in range(self.mesh.dim):
+            self._field.copy_(self.mesh.coords[:, k])
+            out[k] = self._integral(self._field) / volume
+        return out
+
+    def update_geometric_quantities(self) -> None:
+        """``ShapeRegularization.update_geometric_quantities`` (``:670-673``)."""
+        if self.is_active:
+            self.current_volume = self.compute_volume()
+            if self.mu_barycenter > 0.0:
+                self.current_barycenter = self.compute_barycenter()
+
+    def compute_objective(self) -> float:
+        """``:180-192`` + ``:437-459``."""
+        value = 0.0
+        if not self.is_active:
+            return value
+        if self.mu_volume > 0.0:
+            value += 0.5 * self.mu_volume * (self.compute_volume() - self.target_volume) ** 2
+        if self.mu_barycenter > 0.0:
+            bc = self.compute_barycenter()
+            value += 0.5 * self.mu_barycenter * sum((bc[k] - self.target_barycenter[k]) ** 2 for k in range(3))
+        return value
+
+    def add_shape_derivative(self, b: torch.Tensor) -> torch.Tensor:
+        """``b += dJ_reg[V]`` with the forms of ``:154-174`` and ``:353-425`` (the barycenter form verbatim, i.e. with
+        the reference's ``+ bc_k / vol * div V``); call after :meth:`update_geometric_quantities`."""
+        if not self.is_active:
+            return b
+        d = self.mesh.dim
+        vol, bc, target = self.current_volume, self.current_barycenter, self.target_barycenter
+        a0 = self.mu_volume * (vol - self.target_volume) if self.mu_volume > 0.0 else 0.0
+        f = expressions.Polynomial.constant(0.0)
+        if self.mu_barycenter > 0.0:
+            for k in range(d):
+                w = self.mu_barycenter * (bc[k] - target[k])
+                a0 += w * bc[k] / vol
+                f = f + (w / vol) * expressions.Polynomial.coordinate(k)
+        f = f + a0
+        linalg.assemble_shape_derivative(self.mesh, self._zeros, self._minus_ones, f, 0.0, bc_flag=self.bc_flag,
+                                         b=self._vector)
+        b.add_(self._vector)
+        return b

@@ -16,6 +16,7 @@ class ReducedCostFunctional:
         self.control = control
         self.mass_scalar_product = mass_scalar_product
         self._out = torch.zeros(1, dtype=torch.float64, device=mesh.device)
+        self.shape_regularization = None  # set by ShapeOptimizationProblem (cost_functional.py:84-86)
 
     def _integral(self, u, c_u, c_track, ud) -> float:
         mesh = self.mesh
@@ -52,4 +53,6 @@ class ReducedCostFunctional:
         if c.c_control != 0.0 and self.control is not None:
             # alpha/2 int u^2 = alpha/2 u^T M u
             val += 0.5 * c.c_control * self.mass_scalar_product(self.control.vector, self.control.vector)
+        if self.shape_regularization is not None and self.shape_regularization.is_active:
+            val += self.shape_regularization.compute_objective()
         return val

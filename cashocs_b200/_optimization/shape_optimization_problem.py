@@ -85,6 +85,7 @@ class ShapeOptimizationProblem:
             self.gradient_ksp_options, gradient_linear_solver)
         self.reduced_cost_functional = cost_functional.ReducedCostFunctional(
             self.mesh, self.cost, self.states, self.state_problem)
+        self.reduced_cost_functional.shape_regularization = self.form_handler.shape_regularization
         self.optimization_variable_abstractions = ls.ShapeVariableAbstractions(self)
         self.solver = None
 

@@ -85,6 +85,13 @@ class ShapeConfig:
     epsilon_armijo: float = 1e-4
     initial_stepsize: float = 1.0
     safeguard_stepsize: bool = True
+    # [Regularization] (cashocs/_forms/shape_regularization.py:131-222,318-510); surface / curvature need facet terms
+    factor_volume: float = 0.0
+    target_volume: float = 0.0
+    use_initial_volume: bool = False
+    factor_barycenter: float = 0.0
+    target_barycenter: tuple = (0.0, 0.0, 0.0)
+    use_initial_barycenter: bool = False
     line_search: str = "armijo"          # [LineSearch] method: armijo | basic | polynomial
     polynomial_model: str = "cubic"
     factor_low: float = 0.1
@@ -107,8 +114,12 @@ class PoissonShapeProblem:
         gradient_ksp=None,
         mu_ksp=None,
         state_degree: int = 1,
+        c_state: float = 1.0,
     ):
         self.mesh = mesh
+        self.c_state = float(c_state)  # J = c_state * int u dx (tests with J = Constant(0)*dx use 0)
+        if state_degree == 2 and c_state != 1.0:
+            raise ValueError("oracle: the P2 shape derivative is written for J = int u")
         self.state_degree = int(state_degree)  # CG degree of the state / adjoint space (configs[4]: 2)
         self.coords = mesh.coords  # moved in place by move_mesh
         self.cells = mesh.cells
@@ -141,7 +152,50 @@ class PoissonShapeProblem:
         self.current_mesh_quality = quality.compute_mesh_quality(
             self.coords, self.cells, self.cfg.qtype, self.cfg.measure, self.cfg.quantile
         )
+        # targets of the geometric regularisation are fixed at construction (shape_regularization.py:141-146,334-339)
+        self.target_volume = self.volume() if self.cfg.use_initial_volume else self.cfg.target_volume
+        tb = list(self.cfg.target_barycenter) + [0.0] * 3
+        self.target_barycenter = self.barycenter() if self.cfg.use_initial_barycenter else np.asarray(tb[:3], dtype=float)
         self.update_scalar_product()
+
+    # -- geometric regularisation: volume and barycenter (shape_regularization.py)
+    def volume(self):
+        return float(np.sum(self._geom()[1]))
+
+    def barycenter(self):
+        """[3] (z = 0 in 2-D), ``_compute_barycenter_list`` (``:486-510``)."""
+        _, vol, _ = self._geom()
+        out = np.zeros(3)
+        out[: self.d] = (vol[:, None] * self.coords[self.cells].mean(axis=1)).sum(axis=0) / vol.sum()
+        return out
+
+    def regularization_objective(self):
+        c = self.cfg
+        val = 0.0
+        if c.factor_volume > 0.0:
+            val += 0.5 * c.factor_volume * (self.volume() - self.target_volume) ** 2
+        if c.factor_barycenter > 0.0:
+            val += 0.5 * c.factor_barycenter * float(np.sum((self.barycenter() - self.target_barycenter) ** 2))
+        return val
+
+    def regularization_derivative_elements(self):
+        """Element vectors [Nc, d+1, d] of the regularisation's shape derivative for V = phi_a e_i:
+        d(vol)[V] = int div V, d(int x_k)[V] = int (V_k + x_k div V); the barycenter term is the reference's
+        form verbatim (``:353-410``), including its ``+ bc_k / vol * div V``."""
+        c, d = self.cfg, self.d
+        _, vol, G = self._geom()
+        dvol = vol[:, None, None] * G                                              # |K| G_a[i]
+        be = np.zeros_like(dvol)
+        if c.factor_volume > 0.0:
+            be += c.factor_volume * (self.volume() - self.target_volume) * dvol
+        if c.factor_barycenter > 0.0:
+            v, bc = self.volume(), self.barycenter()
+            xbar = self.coords[self.cells].mean(axis=1)                              # [Nc, d]
+            for k in range(d):
+                dxk = dvol * xbar[:, k][:, None, None]                              # int_K x_k div V
+                dxk[:, :, k] += (vol / (d + 1))[:, None]                            # int_K V_k
+                be += c.factor_barycenter * (bc[k] - self.target_barycenter[k]) * (bc[k] / v * dvol + dxk / v)
+        return be
 
     # -- boundary conditions of the deformation space (shape_form_handler.py:551-588)
     def _shape_bc_dofs(self):
@@ -180,11 +234,11 @@ class PoissonShapeProblem:
         _, vol, G = self._geom()
         if self.state_degree == 2:
             Ke = p2.stiffness_elements(vol, G)
-            be = -vol[:, None] * p2.reference_tensors(self.d)[2][None, :]  # -dJ/du[v] = -int v
+            be = -self.c_state * vol[:, None] * p2.reference_tensors(self.d)[2][None, :]  # -dJ/du[v] = -c int v
             A, b = fem.assemble_system(Ke, be, self.p2_dofs, self.n_state, self.state_bc, 0.0)
         else:
             Ke = fem.stiffness_elements(vol, G)
-            be = -fem.load_elements_p1(vol, self.cells, np.ones(self.nv), self.d)  # -dJ/du[v] = -int v
+            be = -self.c_state * fem.load_elements_p1(vol, self.cells, np.ones(self.nv), self.d)  # -dJ/du[v] = -c int v
             A, b = fem.assemble_system(Ke, be, self.cells, self.nv, self.state_bc, 0.0)
         self.p, reason, its, _ = krylov.solve(A, b, self.adjoint_ksp)
         self._check(reason)
@@ -200,9 +254,10 @@ class PoissonShapeProblem:
     def cost(self):
         """``IntegralFunctional.evaluate`` (``cashocs/_optimization/cost_functional.py:160-168``)."""
         _, vol, _ = self._geom()
+        reg = self.regularization_objective()  # cost_functional.py:84-86
         if self.state_degree == 2:
-            return p2.integral(self.u, self.p2_dofs, vol, self.d)
-        return float(np.sum(vol * self.u[self.cells].mean(axis=1)))
+            return self.c_state * p2.integral(self.u, self.p2_dofs, vol, self.d) + reg
+        return self.c_state * float(np.sum(vol * self.u[self.cells].mean(axis=1))) + reg
 
     # -- Lame mu (a5)
     def compute_mu(self):
@@ -262,7 +317,7 @@ class PoissonShapeProblem:
         fq = self.f(xq)
         gfq = self.grad_f(xq)[..., :d]
         pq = np.einsum("qa,ca->cq", lam, pe)
-        int_u = vol * ue.mean(axis=1)
+        int_u = self.c_state * vol * ue.mean(axis=1)
         int_fp = vol * np.einsum("cq,cq,q->c", fq, pq, w, optimize=True)
         int_gf_phi_p = vol[:, None, None] * np.einsum("cqi,cq,q,qa->cai", gfq, pq, w, lam, optimize=True)
         gugp = np.einsum("ci,ci->c", gu, gp)
@@ -277,6 +332,8 @@ class PoissonShapeProblem:
 
     def shape_derivative_vector(self):
         be = self.shape_derivative_elements()
+        if self.cfg.factor_volume > 0.0 or self.cfg.factor_barycenter > 0.0:
+            be = be + self.regularization_derivative_elements().reshape(be.shape)
         if self.shape_bc_dofs.size:
             _, be = fem.apply_bcs_elementwise(None, be, self.vcell_dofs, self.shape_bc_dofs, 0.0,
                                               self.d * self.nv)

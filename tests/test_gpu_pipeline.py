@@ -415,3 +415,62 @@ def test_polynomial_and_basic_line_search_and_bfgs_restart(kind, algorithm, keys
     assert abs(prob.solver.objective_value - hist[-1][1]) <= 1e-6 * abs(hist[-1][1])
     if kind == "control-cc":
         assert float(u.vector.min()) >= 0.0 and float(u.vector.max()) <= 100.0
+
+
+def make_sop_zero_cost(mesh, cfg, ksp=KSP):
+    """J = Constant(0)*dx of the reference's regularisation tests: only the regularisation drives the shape."""
+    u, p = cb.Function(mesh), cb.Function(mesh)
+    return cb.ShapeOptimizationProblem(cb.PoissonForm(source=demo_poly(mesh.dim)), cb.create_dirichlet_bcs(0.0, [1]),
+                                       cb.IntegralFunctional(c_state=0.0), u, p, config=cfg, ksp_options=ksp,
+                                       adjoint_ksp_options=ksp, gradient_ksp_options=ksp)
+
+
+def test_volume_regularization_like_the_reference():
+    """tests/test_shape_optimization.py:356-378: factor_volume = 1, target = pi r^2 -> Taylor rate > 1.9, L-BFGS to
+    rtol 1e-6 within 50 iterations, the disc shrinks to radius r (5e-3) and 1/2 (vol - target)^2 < 1e-10; gradient and
+    cost agree with the oracle."""
+    rng = np.random.RandomState(300696)
+    radius = rng.uniform(0.33, 0.66)
+    target = np.pi * radius**2
+    dm, om = circle()
+    cfg = sop_config(volume_change=10)
+    cfg.set("Regularization", "factor_volume", "1.0")
+    cfg.set("Regularization", "target_volume", repr(target))
+    sop = make_sop_zero_cost(dm, cfg)
+    ocfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, factor_volume=1.0, target_volume=target, volume_change=10.0)
+    prob = pipeline.PoissonShapeProblem(om, config=ocfg, c_state=0.0)
+    g0 = prob.compute_shape_gradient()
+    g1 = sop.compute_shape_gradient()[0].vector.cpu().numpy()
+    assert rel(g1, g0) < 1e-8
+    assert abs(sop.reduced_cost_functional.evaluate() - prob.cost()) <= 1e-10 * abs(prob.cost())
+    assert sop.gradient_test(rng=rng) > 1.9
+    sop.solve(algorithm="bfgs", rtol=1e-6, atol=0.0, max_iter=50)
+    coords = dm.coords.cpu().numpy()
+    assert abs(coords.max() - radius) < 5e-3 and abs(-coords.min() - radius) < 5e-3
+    assert 0.5 * (sop.form_handler.shape_regularization.compute_volume() - target) ** 2 < 1e-10
+
+
+def test_barycenter_regularization_like_the_reference():
+    """tests/test_shape_optimization.py:406-434: factor_volume = 1e2 with the initial volume as target, barycenter
+    pulled to a random position: Taylor rate > 1.9, L-BFGS to rtol 1e-5, |bc - target| < 1e-4, volume kept (1e-2)."""
+    rng = np.random.RandomState(300696)
+    pos_x, pos_y = rng.uniform(0.2, 0.4), rng.uniform(-0.4, -0.2)
+    dm, om = circle()
+    cfg = sop_config(volume_change=10)
+    cfg.set("Regularization", "factor_volume", "1e2")
+    cfg.set("Regularization", "use_initial_volume", "True")
+    cfg.set("Regularization", "factor_barycenter", "1.0")
+    cfg.set("Regularization", "target_barycenter", str([pos_x, pos_y]))
+    sop = make_sop_zero_cost(dm, cfg)
+    reg = sop.form_handler.shape_regularization
+    initial_volume = reg.compute_volume()
+    ocfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, factor_volume=1e2, use_initial_volume=True,
+                                factor_barycenter=1.0, target_barycenter=(pos_x, pos_y), volume_change=10.0)
+    prob = pipeline.PoissonShapeProblem(om, config=ocfg, c_state=0.0)
+    assert abs(initial_volume - prob.volume()) <= 1e-13 * prob.volume()
+    assert rel(sop.compute_shape_gradient()[0].vector.cpu().numpy(), prob.compute_shape_gradient()) < 1e-8
+    assert sop.gradient_test(rng=rng) > 1.9
+    sop.solve(algorithm="bfgs", rtol=1e-5, atol=0.0, max_iter=50)
+    bc = reg.compute_barycenter()
+    assert abs(reg.compute_volume() - initial_volume) < 1e-2
+    assert abs(bc[0] - pos_x) < 1e-4 and abs(bc[1] - pos_y) < 1e-4

@@ -353,3 +353,30 @@ def test_oracle_multigrid_preconditioner():
         assert np.linalg.norm(P @ coef - rot) <= 5e-2 * np.linalg.norm(rot)
     assert its[14]["gradient"] <= its[8]["gradient"] + 8 and its[14]["gradient"] <= 40
     assert its[14]["state"] <= 35
+
+
+def test_volume_and_barycenter_regularization_reference_scenarios():
+    """tests/test_shape_optimization.py:356-378,406-434 (reference): Taylor rate > 1.9 with the regularisation terms,
+    L-BFGS drives the unit disc to the target radius / barycenter within the reference's tolerances."""
+    load = lambda: meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))  # noqa: E731
+    rng = np.random.RandomState(300696)
+    radius = rng.uniform(0.33, 0.66)
+    cfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, factor_volume=1.0, target_volume=np.pi * radius**2,
+                               volume_change=10.0)
+    prob = pipeline.PoissonShapeProblem(load(), config=cfg, c_state=0.0)
+    assert pipeline.shape_gradient_test(prob, rng=rng)[0] > 1.9
+    ok, hist = pipeline.lbfgs(prob, rtol=1e-6, max_iter=50, memory=3)
+    assert ok
+    assert abs(prob.coords.max() - radius) < 5e-3 and abs(-prob.coords.min() - radius) < 5e-3
+    assert 0.5 * (prob.volume() - np.pi * radius**2) ** 2 < 1e-10
+
+    rng = np.random.RandomState(300696)
+    pos_x, pos_y = rng.uniform(0.2, 0.4), rng.uniform(-0.4, -0.2)
+    cfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, factor_volume=1e2, use_initial_volume=True,
+                               factor_barycenter=1.0, target_barycenter=(pos_x, pos_y), volume_change=10.0)
+    prob = pipeline.PoissonShapeProblem(load(), config=cfg, c_state=0.0)
+    v0 = prob.volume()
+    assert pipeline.shape_gradient_test(prob, rng=rng)[0] > 1.9
+    ok, hist = pipeline.lbfgs(prob, rtol=1e-5, max_iter=50, memory=3)
+    bc = prob.barycenter()
+    assert ok and abs(prob.volume() - v0) < 1e-2 and abs(bc[0] - pos_x) < 1e-4 and abs(bc[1] - pos_y) < 1e-4
