@@ -1,8 +1,8 @@
-"""Geometric regularisation of shape problems (``cashocs/_forms/shape_regularization.py``): the cell-integral
-terms -- volume (``:131-222``) and barycenter (``:318-510``).  Surface and curvature regularisation need facet
-integrals and stay outside the hot path (``Config._check_supported`` refuses them).
+"""Geometric regularisation of shape problems (``cashocs/_forms/shape_regularization.py``): volume (``:131-222``),
+surface (``:224-316``) and barycenter (``:318-510``).  Curvature regularisation (a surface Laplace-Beltrami solve)
+stays outside the hot path (``Config._check_supported`` refuses it).
 
-No new kernels: everything is expressed through two existing device entry points.
+The cell-integral terms need no new kernels: everything is expressed through two existing device entry points.
 
 * ``int_Omega w dx`` for a P1 field ``w`` is ``cb_functional`` -- volume with ``w = 1``, first moments with the
   coordinate fields.
@@ -11,6 +11,10 @@ No new kernels: everything is expressed through two existing device entry points
   terms ``-G_a[i] int_K f p - int_K (d_i f) phi_a p`` when the "adjoint" is the constant ``-1`` and the "state" is
   zero.  Both regularisations are linear combinations of ``d(vol)`` (``f = 1``) and ``d(int x_k)`` (``f = x_k``), so
   the whole regularisation derivative is ONE launch with the affine polynomial ``f = a_0 + sum_k a_k x_k``.
+
+The surface term integrates over the boundary facets (``csrc/boundary.cu``): ``cb_boundary_measure`` and
+``cb_boundary_measure_gradient`` -- for P1 deformations ``int_F t_div(V, n) ds = d|F|[V]`` exactly, so the derivative
+vector is the gradient of the facet measures, gathered per vertex in a fixed order.
 """
 
 from __future__ import annotations
@@ -28,7 +32,8 @@ class ShapeRegularization:
         d = mesh.dim
         self.mu_volume = config.getfloat("Regularization", "factor_volume")
         self.mu_barycenter = config.getfloat("Regularization", "factor_barycenter")
-        self.is_active = self.mu_volume > 0.0 or self.mu_barycenter > 0.0
+        self.mu_surface = config.getfloat("Regularization", "factor_surface")
+        self.is_active = self.mu_volume > 0.0 or self.mu_barycenter > 0.0 or self.mu_surface > 0.0
         if not self.is_active:
             return
         f64 = dict(dtype=torch.float64, device=mesh.device)
@@ -47,6 +52,15 @@ class ShapeRegularization:
             self.target_barycenter = self.compute_barycenter()
         self.current_volume = 1.0
         self.current_barycenter = [0.0, 0.0, 0.0]
+        self.current_surface = 1.0
+        self.target_surface = config.getfloat("Regularization", "target_surface")
+        if self.mu_surface > 0.0:
+            self._facets, self._v2f_ptr, self._v2f_idx = mesh.boundary_facet_table()
+            nf = int(self._facets.shape[0])
+            self._facet_vec = torch.zeros(max(nf * d * d, 1), **f64)
+            self._surface_vector = torch.zeros(mesh.n_owned_vertices * d, **f64)
+            if config.getboolean("Regularization", "use_initial_surface"):
+                self.target_surface = self.compute_surface()
 
     # -- geometric quantities
     def _integral(self, w: torch.Tensor) -> float:
@@ -75,12 +89,25 @@ class ShapeRegularization:
             out[k] = self._integral(self._field) / volume
         return out
 
+    def compute_surface(self) -> float:
+        """``_compute_surface`` (``:307-316``)."""
+        mesh = self.mesh
+        scratch = mesh.reduce_scratch()
+        _lib.check(
+            _lib.load().cb_boundary_measure(_lib.stream_ptr(), mesh.dim, int(self._facets.shape[0]), _lib.ptr(mesh.coords),
+                                            _lib.ptr(self._facets), _lib.ptr(self._out), _lib.ptr(scratch), scratch.numel()),
+            "cb_boundary_measure",
+        )
+        return float(self._out.item())
+
     def update_geometric_quantities(self) -> None:
         """``ShapeRegularization.update_geometric_quantities`` (``:670-673``)."""
         if self.is_active:
             self.current_volume = self.compute_volume()
             if self.mu_barycenter > 0.0:
                 self.current_barycenter = self.compute_barycenter()
+            if self.mu_surface > 0.0:
+                self.current_surface = self.compute_surface()
 
     def compute_objective(self) -> float:
         """``:180-192`` + ``:437-459``."""
@@ -89,6 +116,8 @@ class ShapeRegularization:
             return value
         if self.mu_volume > 0.0:
             value += 0.5 * self.mu_volume * (self.compute_volume() - self.target_volume) ** 2
+        if self.mu_surface > 0.0:
+            value += 0.5 * self.mu_surface * (self.compute_surface() - self.target_surface) ** 2
         if self.mu_barycenter > 0.0:
             bc = self.compute_barycenter()
             value += 0.5 * self.mu_barycenter * sum((bc[k] - self.target_barycenter[k]) ** 2 for k in range(3))
@@ -100,6 +129,20 @@ class ShapeRegularization:
         if not self.is_active:
             return b
         d = self.mesh.dim
+        if self.mu_surface > 0.0:  # mu (surface - target) int_Gamma t_div(V, n) ds  (:248-269)
+            mesh = self.mesh
+            _lib.check(
+                _lib.load().cb_boundary_measure_gradient(
+                    _lib.stream_ptr(), d, int(self._facets.shape[0]), mesh.n_owned_vertices, _lib.ptr(mesh.coords),
+                    _lib.ptr(self._facets), _lib.ptr(self._v2f_ptr), _lib.ptr(self._v2f_idx), _lib.ptr(self._facet_vec),
+                    _lib.ptr(self._surface_vector)),
+                "cb_boundary_measure_gradient",
+            )
+            if self.bc_flag is not None:
+                self._surface_vector.masked_fill_(self.bc_flag[: self._surface_vector.numel()].bool(), 0.0)
+            b.add_(self._surface_vector, alpha=self.mu_surface * (self.current_surface - self.target_surface))
+        if self.mu_volume <= 0.0 and self.mu_barycenter <= 0.0:
+            return b
         vol, bc, target = self.current_volume, self.current_barycenter, self.target_barycenter
         a0 = self.mu_volume * (vol - self.target_volume) if self.mu_volume > 0.0 else 0.0
         f = expressions.Polynomial.constant(0.0)

@@ -213,6 +213,8 @@ SIGNATURES = {
     "cb_gradient_frobenius_max": (I32, [P, I32, I64, P, P, P, P, P, I64]),
     "cb_move_mesh": (I32, [P, I64, P, P, P, DBL]),
     "cb_functional": (I32, [P, I32, I64, P, P, DBL, P, DBL, P, P, P, I64]),
+    "cb_boundary_measure": (I32, [P, I32, I64, P, P, P, P, I64]),
+    "cb_boundary_measure_gradient": (I32, [P, I32, I64, I64, P, P, P, P, P, P]),
     "cb_intersection_test": (I32, [P, I32, I64, I64, P, P, P, P, P]),
     "cb_dist_unique_id": (I32, [P]),
     "cb_dist_create": (I32, [C.POINTER(P), P, I32, I32, I32, P, P, P, P, I64, I64]),

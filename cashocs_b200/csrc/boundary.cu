@@ -1,0 +1,131 @@
+// Boundary (facet) integrals of the geometric regularisation: the measure of the boundary
+// int_Gamma 1 ds (cashocs/_forms/shape_regularization.py:307-316) and its shape derivative
+// int_Gamma div_Gamma V ds (:248-269, t_div :63-74).  For the P1 deformation V = phi_a e_i the tangential
+// divergence integrated over a flat facet F is exactly d|F| / d x_a[i], so the derivative vector is the
+// gradient of the facet measures with respect to the vertex coordinates: one thread per facet writes its
+// d local vertex gradients, a per-vertex gather (fixed order, no atomics) sums them.
+//
+// Compiled with -fmad=false like meshops.cu: the measure enters the cost functional and with it the
+// Armijo accept / reject decisions.
+#include "common.cuh"
+
+namespace cb {
+
+// |F| and d|F|/dx_a for a facet with D vertices in R^D (D = 2: segment, D = 3: triangle)
+template <int D>
+__device__ __forceinline__ double facet_measure(const double (&x)[D][D], double (&grad)[D][D]) {
+  if constexpr (D == 2) {
+    const double ex = x[1][0] - x[0][0], ey = x[1][1] - x[0][1];
+    const double len = sqrt(ex * ex + ey * ey);
+    const double inv = len > 0.0 ? 1.0 / len : 0.0;
+    grad[1][0] = ex * inv; grad[1][1] = ey * inv;
+    grad[0][0] = -grad[1][0]; grad[0][1] = -grad[1][1];
+    return len;
+  } else {
+    double e1[3], e2[3], n[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { e1[i] = x[1][i] - x[0][i]; e2[i] = x[2][i] - x[0][i]; }
+    n[0] = e1[1] * e2[2] - e1[2] * e2[1];
+    n[1] = e1[2] * e2[0] - e1[0] * e2[2];
+    n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+    const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    const double inv = nn > 0.0 ? 1.0 / nn : 0.0;
+    const double nh[3] = {n[0] * inv, n[1] * inv, n[2] * inv};
+    // d(area)/dx_a = 1/2 (opposite edge, oriented) x n_hat: a = 0 -> x1 - x2, 1 -> x2 - x0, 2 -> x0 - x1
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int b = (a + 1) % 3, c = (a + 2) % 3;
+      const double e[3] = {x[b][0] - x[c][0], x[b][1] - x[c][1], x[b][2] - x[c][2]};
+      grad[a][0] = 0.5 * (e[1] * nh[2] - e[2] * nh[1]);
+      grad[a][1] = 0.5 * (e[2] * nh[0] - e[0] * nh[2]);
+      grad[a][2] = 0.5 * (e[0] * nh[1] - e[1] * nh[0]);
+    }
+    return 0.5 * nn;
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void load_facet(const double* __restrict__ coords, const int32_t* __restrict__ facets,
+                                           int64_t f, double (&x)[D][D]) {
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+    const int64_t v = __ldg(facets + f * D + a);
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[a][i] = __ldg(coords + v * D + i);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_boundary_measure(int64_t nf, const double* __restrict__ coords, const int32_t* __restrict__ facets,
+                   double* __restrict__ result, double* __restrict__ scratch) {
+  __shared__ double s_red[33];
+  double local = 0.0;
+  for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nf;
+       f += (int64_t)gridDim.x * blockDim.x) {
+    double x[D][D], g[D][D];
+    load_facet<D>(coords, facets, f, x);
+    local += facet_measure<D>(x, g);
+  }
+  double v1[1] = {local};
+  const int ops[1] = {RED_SUM};
+  if (grid_reduce<1>(v1, ops, scratch, s_red)) {
+    if (threadIdx.x == 0) *result = v1[0];
+  }
+}
+
+// facet_vec[f, a, :] = d|F_f| / d x_a
+template <int D>
+__global__ void __launch_bounds__(256)
+k_boundary_gradient(int64_t nf, const double* __restrict__ coords, const int32_t* __restrict__ facets,
+                    double* __restrict__ facet_vec) {
+  for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nf;
+       f += (int64_t)gridDim.x * blockDim.x) {
+    double x[D][D], g[D][D];
+    load_facet<D>(coords, facets, f, x);
+    facet_measure<D>(x, g);
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+      for (int i = 0; i < D; ++i) facet_vec[(f * D + a) * D + i] = g[a][i];
+  }
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int cb_boundary_measure(void* stream, int dim, int64_t nf, const double* coords, const int32_t* facets,
+                                   double* result_dev, double* scratch, int64_t scratch_len) {
+  CB_REQUIRE(dim == 2 || dim == 3, "cb_boundary_measure: dim must be 2 or 3");
+  CB_REQUIRE(coords && result_dev && scratch && scratch_len >= RED_SCRATCH_LEN && (facets || nf == 0),
+             "cb_boundary_measure: missing argument");
+  cudaStream_t s = as_stream(stream);
+  int grid = grid_for(nf, 256, 4);
+  if (grid > RED_MAXP) grid = RED_MAXP;
+  if (dim == 2) k_boundary_measure<2><<<grid, 256, 0, s>>>(nf, coords, facets, result_dev, scratch);
+  else k_boundary_measure<3><<<grid, 256, 0, s>>>(nf, coords, facets, result_dev, scratch);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int cb_boundary_measure_gradient(void* stream, int dim, int64_t nf, int64_t nrows, const double* coords,
+                                            const int32_t* facets, const int64_t* v2f_ptr, const int32_t* v2f_idx,
+                                            double* facet_vec, double* out) {
+  CB_REQUIRE(dim == 2 || dim == 3, "cb_boundary_measure_gradient: dim must be 2 or 3");
+  CB_REQUIRE(coords && v2f_ptr && out && (nf == 0 || (facets && v2f_idx && facet_vec)),
+             "cb_boundary_measure_gradient: missing argument");
+  cudaStream_t s = as_stream(stream);
+  if (nf > 0) {
+    const int grid = grid_for(nf, 256, 8);
+    if (dim == 2) k_boundary_gradient<2><<<grid, 256, 0, s>>>(nf, coords, facets, facet_vec);
+    else k_boundary_gradient<3><<<grid, 256, 0, s>>>(nf, coords, facets, facet_vec);
+    CB_LAUNCH_CHECK();
+  }
+  // a facet is a (dim-1)-simplex: the cell-vector gather with D = dim - 1 and dim components per vertex
+  const int grid = grid_for(nrows, 256, 8);
+  if (dim == 2) k_gather_cell_vectors<1, 2><<<grid, 256, 0, s>>>(nrows, v2f_ptr, v2f_idx, facets, facet_vec, out);
+  else k_gather_cell_vectors<2, 3><<<grid, 256, 0, s>>>(nrows, v2f_ptr, v2f_idx, facets, facet_vec, out);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}

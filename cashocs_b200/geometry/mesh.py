@@ -79,6 +79,33 @@ class Mesh:
         return self._p2_space
 
     @property
+    def boundary_facet_table(self):
+        """All boundary facets of the mesh (the ``ds`` measure): ``(facets [nf, d] int32, v2f_ptr, v2f_idx)`` with
+        the vertex -> facet adjacency over the owned vertices, built once from the topology -- a facet lies on the
+        boundary iff it belongs to exactly one cell."""
+        if getattr(self, "_facet_table", None) is not None:
+            return self._facet_table
+        if self.dist is not None:
+            raise _exceptions.InputError("cashocs_b200.Mesh.boundary_facet_table", "mesh",
+                                         "facet integrals are implemented for unpartitioned meshes")
+        import ctypes as C
+
+        d = self.dim
+        cells = self.cells.long()
+        keep = [[j for j in range(d + 1) if j != omit] for omit in range(d + 1)]
+        sub = torch.cat([cells[:, k] for k in keep], dim=0)  # ascending per facet because cells are
+        uniq, counts = torch.unique(sub, dim=0, return_counts=True)
+        facets = uniq[counts == 1].to(torch.int32).contiguous()
+        nf = int(facets.shape[0])
+        n = self.n_owned_vertices
+        ptr = torch.zeros(n + 1, dtype=torch.int64, device=self.device)
+        idx = torch.zeros(max(nf * d, 1), dtype=torch.int32, device=self.device)
+        if nf:
+            _lib.check(_lib.load().cb_v2c_build(_lib.stream_ptr(), n, nf, d, _lib.ptr(facets), _lib.ptr(ptr), _lib.ptr(idx)),
+                       "cb_v2c_build")
+        self._facet_table = (facets, ptr, idx)
+        return self._facet_table
+
     def boundary_markers(self) -> list[int]:
         return sorted(self._boundary_vertices)
 

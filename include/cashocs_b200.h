@@ -388,6 +388,16 @@ int cb_move_mesh(void* stream, int64_t n, double* coords, double* coords_old, co
 int cb_functional(void* stream, int dim, int64_t nc, const double* coords, const int32_t* cells,
                   double c_u, const double* u, double c_track, const double* ud,
                   double* result_dev, double* scratch, int64_t scratch_len);
+/* int_Gamma 1 ds over the boundary facets [nf, dim] (SurfaceRegularization._compute_surface,
+ * cashocs/_forms/shape_regularization.py:307-316); result_dev device double. */
+int cb_boundary_measure(void* stream, int dim, int64_t nf, const double* coords, const int32_t* facets,
+                        double* result_dev, double* scratch, int64_t scratch_len);
+/* out[v, :] = sum over the boundary facets F of vertex v of d|F|/dx_v, v < nrows -- the vector of
+ * int_Gamma t_div(V, n) ds for V = phi_v e_i (shape_regularization.py:63-74,248-269).  v2f_ptr [nrows+1] /
+ * v2f_idx: vertex -> facet adjacency (cb_v2c_build with k = dim); facet_vec [nf*dim*dim] scratch. */
+int cb_boundary_measure_gradient(void* stream, int dim, int64_t nf, int64_t nrows, const double* coords,
+                                 const int32_t* facets, const int64_t* v2f_ptr, const int32_t* v2f_idx,
+                                 double* facet_vec, double* out);
 /* Per-vertex collision counts (compute_collisions, cashocs/geometry/mesh_testing.py:201-241)
  * with a uniform-grid broad phase built on the device; mismatch_dev (device int64) receives the
  * number of vertices whose count differs from `valence`. */

@@ -92,6 +92,9 @@ class ShapeConfig:
     factor_barycenter: float = 0.0
     target_barycenter: tuple = (0.0, 0.0, 0.0)
     use_initial_barycenter: bool = False
+    factor_surface: float = 0.0          # :224-316, the only facet term restated here
+    target_surface: float = 0.0
+    use_initial_surface: bool = False
     line_search: str = "armijo"          # [LineSearch] method: armijo | basic | polynomial
     polynomial_model: str = "cubic"
     factor_low: float = 0.1
@@ -156,6 +159,7 @@ class PoissonShapeProblem:
         self.target_volume = self.volume() if self.cfg.use_initial_volume else self.cfg.target_volume
         tb = list(self.cfg.target_barycenter) + [0.0] * 3
         self.target_barycenter = self.barycenter() if self.cfg.use_initial_barycenter else np.asarray(tb[:3], dtype=float)
+        self.target_surface = self.surface() if self.cfg.use_initial_surface else self.cfg.target_surface
         self.update_scalar_product()
 
     # -- geometric regularisation: volume and barycenter (shape_regularization.py)
@@ -169,9 +173,50 @@ class PoissonShapeProblem:
         out[: self.d] = (vol[:, None] * self.coords[self.cells].mean(axis=1)).sum(axis=0) / vol.sum()
         return out
 
+    def boundary_facets(self):
+        """Facets belonging to exactly one cell (the ``ds`` measure)."""
+        if getattr(self, "_bfacets", None) is None:
+            d = self.d
+            sub = np.concatenate([np.delete(self.cells, k, axis=1) for k in range(d + 1)], axis=0)
+            uniq, counts = np.unique(np.sort(sub, axis=1), axis=0, return_counts=True)
+            self._bfacets = uniq[counts == 1]
+        return self._bfacets
+
+    def _facet_measures(self):
+        X = self.coords[self.boundary_facets()]  # [nf, d, d]
+        if self.d == 2:
+            return np.linalg.norm(X[:, 1] - X[:, 0], axis=1)
+        return 0.5 * np.linalg.norm(np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), axis=1)
+
+    def surface(self):
+        """``_compute_surface`` (``shape_regularization.py:307-316``)."""
+        return float(np.sum(self._facet_measures()))
+
+    def surface_derivative_vector(self):
+        """int_Gamma t_div(V, n) ds for V = phi_a e_i (``:63-74,248-269``): the gradient of the facet measures with
+        respect to the vertex positions, by central differences of the exact measure formula would be an option --
+        here the closed forms: segment (x1 - x0)/|F|; triangle 1/2 (n_hat x opposite edge)."""
+        F = self.boundary_facets()
+        X = self.coords[F]
+        out = np.zeros((self.nv, self.d))
+        if self.d == 2:
+            e = X[:, 1] - X[:, 0]
+            t = e / np.linalg.norm(e, axis=1)[:, None]
+            np.add.at(out, F[:, 1], t)
+            np.add.at(out, F[:, 0], -t)
+        else:
+            n = np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0])
+            nh = n / np.linalg.norm(n, axis=1)[:, None]
+            for a in range(3):
+                b, c = (a + 1) % 3, (a + 2) % 3
+                np.add.at(out, F[:, a], 0.5 * np.cross(X[:, b] - X[:, c], nh))
+        return out.reshape(-1)
+
     def regularization_objective(self):
         c = self.cfg
         val = 0.0
+        if c.factor_surface > 0.0:
+            val += 0.5 * c.factor_surface * (self.surface() - self.target_surface) ** 2
         if c.factor_volume > 0.0:
             val += 0.5 * c.factor_volume * (self.volume() - self.target_volume) ** 2
         if c.factor_barycenter > 0.0:
@@ -331,6 +376,14 @@ class PoissonShapeProblem:
         return be.reshape(self.cells.shape[0], -1)
 
     def shape_derivative_vector(self):
+        vec = self._cell_shape_derivative_vector()
+        if self.cfg.factor_surface > 0.0:
+            extra = self.cfg.factor_surface * (self.surface() - self.target_surface) * self.surface_derivative_vector()
+            extra[self.shape_bc_dofs] = 0.0
+            vec = vec + extra
+        return vec
+
+    def _cell_shape_derivative_vector(self):
         be = self.shape_derivative_elements()
         if self.cfg.factor_volume > 0.0 or self.cfg.factor_barycenter > 0.0:
             be = be + self.regularization_derivative_elements().reshape(be.shape)

@@ -474,3 +474,58 @@ def test_barycenter_regularization_like_the_reference():
     bc = reg.compute_barycenter()
     assert abs(reg.compute_volume() - initial_volume) < 1e-2
     assert abs(bc[0] - pos_x) < 1e-4 and abs(bc[1] - pos_y) < 1e-4
+
+
+def test_surface_regularization_like_the_reference():
+    """tests/test_shape_optimization.py:381-403: factor_surface = 1, target = 2 pi r -> Taylor rate > 1.9, L-BFGS to
+    rtol 1e-6, the disc shrinks to radius r (5e-3), 1/2 (surface - target)^2 < 1e-10; the boundary measure, the
+    gradient and the cost agree with the oracle (facet kernels of csrc/boundary.cu)."""
+    rng = np.random.RandomState(300696)
+    radius = rng.uniform(0.33, 0.66)
+    target = 2 * np.pi * radius
+    dm, om = circle()
+    cfg = sop_config(volume_change=10)
+    cfg.set("Regularization", "factor_surface", "1.0")
+    cfg.set("Regularization", "target_surface", repr(target))
+    sop = make_sop_zero_cost(dm, cfg)
+    reg = sop.form_handler.shape_regularization
+    ocfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, factor_surface=1.0, target_surface=target, volume_change=10.0)
+    prob = pipeline.PoissonShapeProblem(om, config=ocfg, c_state=0.0)
+    assert abs(reg.compute_surface() - prob.surface()) <= 1e-14 * prob.surface()
+    assert rel(sop.compute_shape_gradient()[0].vector.cpu().numpy(), prob.compute_shape_gradient()) < 1e-8
+    assert abs(sop.reduced_cost_functional.evaluate() - prob.cost()) <= 1e-10 * abs(prob.cost())
+    assert sop.gradient_test(rng=rng) > 1.9
+    sop.solve(algorithm="bfgs", rtol=1e-6, atol=0.0, max_iter=50)
+    coords = dm.coords.cpu().numpy()
+    assert abs(coords.max() - radius) < 5e-3 and abs(-coords.min() - radius) < 5e-3
+    assert 0.5 * (reg.compute_surface() - target) ** 2 < 1e-10
+
+
+def test_boundary_measure_and_gradient_3d():
+    """csrc/boundary.cu on the unit cube: |Gamma| = 6, facet table = the facets of exactly one cell, gradient of the
+    boundary measure against the oracle's closed form on a randomly perturbed mesh."""
+    n = 4
+    dm, om = cb.regular_mesh(n, 1.0, 1.0, 1.0), meshes.regular_mesh(n, 1.0, 1.0, 1.0)
+    cfg = sop_config(shape_bdry_def="[1, 2, 3, 4, 5, 6]")
+    cfg.set("Regularization", "factor_surface", "1.0")
+    cfg.set("Regularization", "target_surface", "1.0")
+    u, p = cb.Function(dm), cb.Function(dm)
+    sop = cb.ShapeOptimizationProblem(cb.PoissonForm(source=demo_poly(3)), cb.create_dirichlet_bcs(0.0, [1, 2, 3, 4, 5, 6]),
+                                      cb.IntegralFunctional(c_state=0.0), u, p, config=cfg, ksp_options=KSP,
+                                      adjoint_ksp_options=KSP, gradient_ksp_options=KSP)
+    reg = sop.form_handler.shape_regularization
+    prob = pipeline.PoissonShapeProblem(om, bc_markers=(1, 2, 3, 4, 5, 6), c_state=0.0,
+                                        config=pipeline.ShapeConfig(shape_bdry_def=(1, 2, 3, 4, 5, 6), factor_surface=1.0,
+                                                                    target_surface=1.0))
+    assert reg._facets.shape[0] == 12 * n * n == prob.boundary_facets().shape[0]
+    assert np.array_equal(reg._facets.cpu().numpy(), prob.boundary_facets())
+    assert abs(reg.compute_surface() - 6.0) < 1e-13
+    shift = 0.02 * np.random.RandomState(5).rand(om.num_vertices, 3)
+    om.coords += shift
+    dm.coords.add_(torch.from_numpy(shift).to(dm.coords.device))
+    assert abs(reg.compute_surface() - prob.surface()) <= 1e-14 * prob.surface()
+    reg.update_geometric_quantities()
+    b = torch.zeros(om.num_vertices * 3, dtype=torch.float64, device=dm.coords.device)
+    reg.add_shape_derivative(b)
+    want = (prob.surface() - 1.0) * prob.surface_derivative_vector()
+    assert np.max(np.abs(b.cpu().numpy() - want)) <= 1e-13 * np.max(np.abs(want))

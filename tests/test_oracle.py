@@ -380,3 +380,27 @@ def test_volume_and_barycenter_regularization_reference_scenarios():
     ok, hist = pipeline.lbfgs(prob, rtol=1e-5, max_iter=50, memory=3)
     bc = prob.barycenter()
     assert ok and abs(prob.volume() - v0) < 1e-2 and abs(bc[0] - pos_x) < 1e-4 and abs(bc[1] - pos_y) < 1e-4
+
+
+def test_surface_regularization_reference_scenario():
+    """tests/test_shape_optimization.py:381-403 (reference): surface regularisation with target 2 pi r."""
+    rng = np.random.RandomState(300696)
+    radius = rng.uniform(0.33, 0.66)
+    cfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, factor_surface=1.0, target_surface=2 * np.pi * radius,
+                               volume_change=10.0)
+    prob = pipeline.PoissonShapeProblem(meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz")), config=cfg, c_state=0.0)
+    assert pipeline.shape_gradient_test(prob, rng=rng)[0] > 1.9
+    ok, hist = pipeline.lbfgs(prob, rtol=1e-6, max_iter=50, memory=3)
+    assert ok
+    assert abs(prob.coords.max() - radius) < 5e-3 and abs(-prob.coords.min() - radius) < 5e-3
+    assert 0.5 * (prob.surface() - 2 * np.pi * radius) ** 2 < 1e-10
+    # 3-D: closed-form gradient of the boundary measure against a difference quotient
+    om = meshes.regular_mesh(3, 1.0, 1.0, 1.0)
+    p3 = pipeline.PoissonShapeProblem(om, bc_markers=(1, 2, 3, 4, 5, 6), c_state=0.0,
+                                      config=pipeline.ShapeConfig(shape_bdry_def=(1, 2, 3, 4, 5, 6), factor_surface=1.0))
+    assert abs(p3.surface() - 6.0) < 1e-13
+    g = p3.surface_derivative_vector()
+    h = 1e-6 * np.random.RandomState(1).rand(g.size)
+    s0 = p3.surface()
+    p3.coords += h.reshape(-1, 3)
+    assert abs((p3.surface() - s0) - g @ h) < 1e-9 * abs(g @ h) + 1e-11
