@@ -78,7 +78,6 @@ class Mesh:
             self._p2_space = function_space.P2Space(self)
         return self._p2_space
 
-    @property
     def boundary_facet_table(self):
         """All boundary facets of the mesh (the ``ds`` measure): ``(facets [nf, d] int32, v2f_ptr, v2f_idx)`` with
         the vertex -> facet adjacency over the owned vertices, built once from the topology -- a facet lies on the
@@ -106,6 +105,7 @@ class Mesh:
         self._facet_table = (facets, ptr, idx)
         return self._facet_table
 
+    @property
     def boundary_markers(self) -> list[int]:
         return sorted(self._boundary_vertices)
 
