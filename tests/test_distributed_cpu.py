@@ -281,3 +281,65 @@ def test_p2_numbering_world2():
     results = mgr.dict()
     mp.spawn(_p2_worker, args=(world, port, results), nprocs=world, join=True)
     assert dict(results) == {0: "ok", 1: "ok"}, dict(results)
+
+
+# ----------------------------------------------------------------------------- output on a partitioned mesh
+def _io_worker(rank, world, port, tmp, results):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import types
+
+        import cashocs_b200 as cb
+        from cashocs_b200 import distributed
+        from cashocs_b200.io import managers
+        from cashocs_b200.io import mesh as iomesh
+
+        dist = distributed.DistContext(rank, world, transport="torch")
+        src = os.path.join(ROOT, "tests", "golden", "tiny_square.msh")
+        g = cb.import_mesh(src, device="cpu")
+        off = distributed.vertex_offsets(g.num_vertices, world)
+        lm = distributed.partition_mesh(g.coords, g.cells, {k: g.boundary_vertices([k]) for k in g.boundary_markers}, off, dist)
+        # every rank moves its own copy of the vertices by a function of the global position
+        lm.coords.mul_(2.0).add_(0.125)
+        want = g.coords.numpy() * 2.0 + 0.125
+        pts = iomesh.gather_coordinates(lm)
+        if rank == 0:
+            assert np.array_equal(pts, want)
+        else:
+            assert pts is None
+        out = os.path.join(tmp, "moved.msh")
+        iomesh.write_out_mesh(lm, src, out)  # rank 0 writes, everybody waits
+        coords = iomesh.read_gmsh(out)[0]
+        assert np.array_equal(coords, want)
+        # output managers: files are written by rank 0 only
+        cfg = cb.Config()
+        cfg.set("Output", "result_dir", os.path.join(tmp, "res"))
+        cfg.set("Output", "save_txt", "True")
+        om = managers.OutputManager(types.SimpleNamespace(config=cfg, mesh=lm))
+        state = {"iteration": 0, "objective_value": 1.5, "relative_norm": 1.0, "gradient_norm": 2.0, "stepsize": 1.0}
+        om.output(state)
+        om.post_process(state)
+        td.barrier()
+        assert sorted(os.listdir(os.path.join(tmp, "res"))) == ["history.json", "history.txt"]
+        assert open(os.path.join(tmp, "res", "history.txt")).read().count("1.500e+00") == 1
+        results[rank] = "ok"
+    except Exception as exc:  # pragma: no cover
+        import traceback
+
+        results[rank] = traceback.format_exc() + str(exc)
+    finally:
+        td.destroy_process_group()
+
+
+def test_mesh_export_and_output_world2(tmp_path):
+    """``io.gather_coordinates`` / ``io.write_out_mesh`` / the output managers on a 2-rank partition: coordinates are
+    gathered by global vertex id on rank 0, which alone writes the files (``cashocs/io/mesh.py:403-431,526-557``)."""
+    world = 2
+    port = 35500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_io_worker, args=(world, port, str(tmp_path), results), nprocs=world, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}, dict(results)
