@@ -87,8 +87,6 @@ class Mesh:
         if self.dist is not None:
             raise _exceptions.InputError("cashocs_b200.Mesh.boundary_facet_table", "mesh",
                                          "facet integrals are implemented for unpartitioned meshes")
-        import ctypes as C
-
         d = self.dim
         cells = self.cells.long()
         keep = [[j for j in range(d + 1) if j != omit] for omit in range(d + 1)]

@@ -9,7 +9,7 @@ import scipy.sparse as sp
 import torch
 
 import cashocs_b200 as cb
-from cashocs_b200._forms import expressions, forms
+from cashocs_b200._forms import forms
 from cashocs_b200._utils import linalg
 from oracle import fem, krylov, meshes, pipeline, quality
 

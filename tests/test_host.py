@@ -7,7 +7,6 @@ import re
 
 import numpy as np
 import pytest
-import torch
 
 import cashocs_b200 as cb
 from cashocs_b200 import _lib

@@ -9,7 +9,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import bench  # noqa: E402
-import cashocs_b200 as cb  # noqa: E402
 from cashocs_b200._utils import linalg  # noqa: E402
 
 

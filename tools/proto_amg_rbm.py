@@ -17,7 +17,6 @@ import time
 
 import numpy as np
 import scipy.sparse as sp
-import scipy.sparse.linalg as spla
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
