@@ -153,6 +153,9 @@ class cb_ksp_opts(C.Structure):
         ("profile_every", C.c_int32),
         ("use_graph", C.c_int32),
         ("amg", C.c_void_p),
+        ("rbm_coords", C.c_void_p),
+        ("rbm_einv", C.c_void_p),
+        ("rbm_work", C.c_void_p),
     ]
 
 

@@ -107,6 +107,7 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None, distr
              "pc_chebyshev_degree", "pc_chebyshev_ratio", "ksp_check_every", "ksp_ksp_type",
              "ksp_ksp_max_it", "ksp_pc_type", "ksp_profile_every", "ksp_use_graph", "pc_amg_smooth_degree",
              "pc_amg_coarse_degree", "pc_amg_smooth_ratio", "pc_amg_coarse_ratio", "pc_amg_min_coarse",
+             "pc_amg_rigid_body_correction",
              "pc_gamg_type", "pc_gamg_agg_nsmooths"} | _IGNORED_KEYS
     unknown = set(opts) - known
     if unknown:
@@ -409,6 +410,10 @@ class KSPResult:
         return f"KSPResult(reason={self.reason}, its={self.its}, rnorm={self.rnorm:.3e}, rnorm0={self.rnorm0:.3e})"
 
 
+def _truthy(v) -> bool:
+    return v if isinstance(v, bool) else str(v).casefold() in ("1", "true", "yes", "on")
+
+
 class LinearSolver:
     """A solver for linear problems (``cashocs/_utils/linalg.py:480-546``), device resident."""
 
@@ -442,7 +447,45 @@ class LinearSolver:
         if h.version != (id(A), A.version):
             h.numeric(A)
             h.version = (id(A), A.version)
+            h.rbm = None
         return h
+
+    @staticmethod
+    def rigid_body_correction(A: "Matrix", h):
+        """Data of the coarse correction ``Z (Z^T A Z)^-1 Z^T`` with the global rigid-body modes (see
+        ``cb_ksp_opts.rbm_*``): centred node coordinates, the inverse of the k x k Galerkin matrix (k = 3 in 2-D,
+        6 in 3-D) and the work vector.  6 SpMVs and a 6 x 6 inverse per matrix version."""
+        if getattr(h, "rbm", None) is not None:
+            return h.rbm
+        mesh, bs = A.mesh, A.bs
+        if bs != mesh.dim or A.nrows != mesh.n_owned_vertices:
+            raise _exceptions.InputError("cashocs_b200.LinearSolver", "pc_amg_rigid_body_correction",
+                                         "needs a vertex-blocked vector operator (bs = dim) on the mesh vertices")
+        dist = mesh.dist
+        n_own, k = mesh.n_owned_vertices, (6 if bs == 3 else 3)
+        centre = mesh.coords[:n_own].sum(dim=0)
+        count = torch.tensor([float(n_own)], dtype=torch.float64, device=mesh.device)
+        if dist is not None:
+            dist.allreduce(centre, "sum")
+            dist.allreduce(count, "sum")
+        c = (mesh.coords - centre / count).contiguous()  # owned + ghost nodes
+        Z = torch.zeros(k, mesh.num_vertices, bs, dtype=torch.float64, device=mesh.device)
+        for a in range(bs):
+            Z[a, :, a] = 1.0
+        if bs == 3:
+            Z[3, :, 0], Z[3, :, 1] = -c[:, 1], c[:, 0]
+            Z[4, :, 1], Z[4, :, 2] = -c[:, 2], c[:, 1]
+            Z[5, :, 0], Z[5, :, 2] = c[:, 2], -c[:, 0]
+        else:
+            Z[2, :, 0], Z[2, :, 1] = -c[:, 1], c[:, 0]
+        Z = Z.reshape(k, -1)
+        W = torch.stack([A.mult(Z[j].contiguous()) for j in range(k)])  # [k, n_own * bs]
+        G = (Z[:, : n_own * bs] @ W.T).contiguous()
+        if dist is not None:
+            dist.allreduce(G.view(-1), "sum")
+        einv = torch.linalg.inv(G.cpu()).to(mesh.device).contiguous()  # k x k, on the host
+        h.rbm = (c[:n_own].contiguous(), einv, torch.zeros(8, dtype=torch.float64, device=mesh.device))
+        return h.rbm
 
     def _workspace(self, n_doubles: int, device) -> torch.Tensor:
         if self._work is None or self._work.numel() < n_doubles or self._work.device != device:
@@ -480,6 +523,9 @@ class LinearSolver:
             hierarchy = self.amg_hierarchy(A, ksp_options or {})
             hstruct = hierarchy.struct()
             opts.amg = C.cast(C.pointer(hstruct), C.c_void_p)
+            if _truthy((ksp_options or {}).get("pc_amg_rigid_body_correction", False)) and A.bs >= 2:
+                rbm = self.rigid_body_correction(A, hierarchy)
+                opts.rbm_coords, opts.rbm_einv, opts.rbm_work = (t.data_ptr() for t in rbm)
         n, nc = A.nrows * A.bs, A.ncols * A.bs
         if function.numel() < n or b.numel() < n:
             raise _exceptions.InputError("cashocs_b200.LinearSolver.solve", "function", "vector too short for the matrix")

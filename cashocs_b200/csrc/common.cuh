@@ -52,7 +52,7 @@ inline int grid_for(int64_t work_items, int threads, int ctas_per_sm) {
 // Scratch layout (doubles): [0, MAXP*NVMAX) block partials, then one 8-byte slot holding the
 // arrival counter.  The grid never exceeds MAXP blocks for reducing kernels.
 constexpr int RED_MAXP = 2048;
-constexpr int RED_NVMAX = 4;
+constexpr int RED_NVMAX = 8;
 constexpr int64_t RED_SCRATCH_LEN = (int64_t)RED_MAXP * RED_NVMAX + 8;
 
 enum RedOp { RED_SUM = 0, RED_MIN = 1, RED_MAX = 2 };

@@ -150,6 +150,100 @@ k_dots_zr(int64_t n, const double* __restrict__ z, const double* __restrict__ r,
   }
 }
 
+// ---- rigid-body coarse correction: z += Z (Z^T A Z)^-1 Z^T r ------------------------------------
+// modes (c = node position relative to the common centre): translations e_k, rotations (-c_y, c_x, 0),
+// (0, -c_z, c_y), (c_z, 0, -c_x) in 3-D; e_x, e_y and (-c_y, c_x) in 2-D
+template <int BS>
+struct Rbm {
+  static constexpr int K = BS == 3 ? 6 : 3;
+};
+
+// out[0..K) = Z^T r
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_rbm_project(int64_t nn, const double* __restrict__ r, const double* __restrict__ xc, double* __restrict__ out,
+              double* __restrict__ scratch, const KspState* st) {
+  if (st->done) return;
+  constexpr int K = Rbm<BS>::K;
+  __shared__ double s_red[32 * K + 1];
+  double v[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nn;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double ri[BS], c[BS];
+#pragma unroll
+    for (int a = 0; a < BS; ++a) { ri[a] = r[i * BS + a]; c[a] = xc[i * BS + a]; }
+#pragma unroll
+    for (int a = 0; a < BS; ++a) v[a] += ri[a];
+    if constexpr (BS == 3) {
+      v[3] += c[0] * ri[1] - c[1] * ri[0];
+      v[4] += c[1] * ri[2] - c[2] * ri[1];
+      v[5] += c[2] * ri[0] - c[0] * ri[2];
+    } else {
+      v[2] += c[0] * ri[1] - c[1] * ri[0];
+    }
+  }
+  int ops[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) ops[k] = RED_SUM;
+  if (grid_reduce<K>(v, ops, scratch, s_red)) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) out[k] = v[k];
+    }
+  }
+}
+
+// z += Z (einv * ztr);  sums = (z.r, z.z)
+template <int BS>
+__global__ void __launch_bounds__(256)
+k_rbm_correct(int64_t nn, const double* __restrict__ r, double* __restrict__ z, const double* __restrict__ xc,
+              const double* __restrict__ einv, const double* __restrict__ ztr, KspState* st, double* hist,
+              double* scratch, int finalize_mode /* -1 none, 0 init, 1 iter */) {
+  if (st->done) return;
+  constexpr int K = Rbm<BS>::K;
+  __shared__ double s_red[66];
+  __shared__ double y[K];
+  if (threadIdx.x < K) {
+    double acc = 0.0;
+    for (int j = 0; j < K; ++j) acc += einv[threadIdx.x * K + j] * ztr[j];
+    y[threadIdx.x] = acc;
+  }
+  __syncthreads();
+  double zr = 0.0, zz = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nn;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double c[BS], dz[BS];
+#pragma unroll
+    for (int a = 0; a < BS; ++a) c[a] = xc[i * BS + a];
+    if constexpr (BS == 3) {
+      dz[0] = y[0] - c[1] * y[3] + c[2] * y[5];
+      dz[1] = y[1] + c[0] * y[3] - c[2] * y[4];
+      dz[2] = y[2] + c[1] * y[4] - c[0] * y[5];
+    } else {
+      dz[0] = y[0] - c[1] * y[2];
+      dz[1] = y[1] + c[0] * y[2];
+    }
+#pragma unroll
+    for (int a = 0; a < BS; ++a) {
+      const double zi = z[i * BS + a] + dz[a];
+      z[i * BS + a] = zi;
+      zr += zi * r[i * BS + a];
+      zz += zi * zi;
+    }
+  }
+  double v[2] = {zr, zz};
+  const int ops[2] = {RED_SUM, RED_SUM};
+  if (grid_reduce<2>(v, ops, scratch, s_red)) {
+    if (threadIdx.x == 0) {
+      st->sums[0] = v[0];
+      st->sums[1] = v[1];
+      if (finalize_mode >= 0) cg_after_zr(st, hist, finalize_mode == 0);
+    }
+  }
+}
+
 // p = z + bcoef * p
 __global__ void __launch_bounds__(256)
 k_cg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const KspState* st) {
@@ -901,7 +995,25 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
     const bool pre_fuse = amg && S.amg_presmooth_fusable(o->amg, &pre_dinv, &pre_scale, &pre_d);
     bool presmoothed = false;
     int dots_mode = -2;
+    const bool rbm = amg && o->rbm_coords != nullptr;
+    if (rbm) CB_REQUIRE(S.bs >= 2 && o->rbm_einv && o->rbm_work, "rigid-body correction: bs must be 2 or 3, einv / work set");
     auto apply_cheb = [&]() -> int {  // z = P(r)
+      if (rbm) {
+        // V-cycle without the fused dots (z still changes), then z += Z (Z^T A Z)^-1 Z^T r with the dots
+        if (int e = S.amg_vcycle(o->amg, r, z, presmoothed, -2)) return e;
+        const int64_t nn = n / S.bs;
+        if (S.bs == 3) k_rbm_project<3><<<vg, 256, 0, s>>>(nn, r, o->rbm_coords, o->rbm_work, scratch, st);
+        else k_rbm_project<2><<<vg, 256, 0, s>>>(nn, r, o->rbm_coords, o->rbm_work, scratch, st);
+        CB_LAUNCH_CHECK();
+        if (dist) { if (int e = dist_allreduce_sum(s, dist, o->rbm_work, S.bs == 3 ? 6 : 3)) return e; }
+        if (S.bs == 3) k_rbm_correct<3><<<vg, 256, 0, s>>>(nn, r, z, o->rbm_coords, o->rbm_einv, o->rbm_work, st, hist_dev,
+                                                        scratch, dots_mode);
+        else k_rbm_correct<2><<<vg, 256, 0, s>>>(nn, r, z, o->rbm_coords, o->rbm_einv, o->rbm_work, st, hist_dev, scratch,
+                                                 dots_mode);
+        CB_LAUNCH_CHECK();
+        S.dots_fused = true;
+        return CB_OK;
+      }
       if (amg) return S.amg_vcycle(o->amg, r, z, presmoothed, dots_mode);
       k_cheb_first<<<vg, 256, 0, s>>>(n, r, dinv, inv_theta, cd, z, st);
       CB_LAUNCH_CHECK();

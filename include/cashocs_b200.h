@@ -311,6 +311,14 @@ typedef struct {
                            * per iteration; bitwise the same result): 0 = on (default; eager when a partitioned run
                            * had to fall back from the one-sided transport to NCCL send/recv), 1 = always, -1 = never */
   const cb_amg* amg;      /* hierarchy for pc_type CB_PC_AMG (NULL otherwise) */
+  /* Rigid-body coarse correction for vector problems (bs = 2: 3 modes, bs = 3: 6 modes): the AMG preconditioner
+   * M becomes M + Z (Z^T A Z)^-1 Z^T with Z the global translations and rotations -- the rotations are
+   * low-energy modes of the elasticity operator that the scalar prolongator does not interpolate.
+   * rbm_coords [nrows, bs]: coordinates of the owned nodes relative to a centre common to all ranks (NULL: off);
+   * rbm_einv (device, k x k, row-major): (Z^T A Z)^-1; rbm_work (device, >= 8 doubles): Z^T r. */
+  const double* rbm_coords;
+  const double* rbm_einv;
+  double* rbm_work;
 } cb_ksp_opts;
 typedef struct {
   int32_t reason;

@@ -79,8 +79,10 @@ class SmoothedAggregation:
     """``z = M r`` with ``M`` one V(1,1) cycle; ``bs`` = dofs per node, ``coords`` [n, d] switches the rigid-body
     modes on (vector problems)."""
 
-    def __init__(self, A, bs: int = 1, coords=None, coarsest: int = 500, max_levels: int = 12) -> None:
+    def __init__(self, A, bs: int = 1, coords=None, coarsest: int = 500, max_levels: int = 12,
+                 point_jacobi: bool = False) -> None:
         self.bs = bs
+        self.point_jacobi = point_jacobi  # diagonal instead of block-diagonal D (what the device smoothers use)
         self.levels = []
         A = sp.csr_matrix(A)
         rbm = coords is not None and bs in (2, 3)
@@ -101,6 +103,11 @@ class SmoothedAggregation:
                 for k in range(bs):
                     z = D[:, k, k] == 0.0
                     D[z, k, k] = 1.0
+                if point_jacobi:
+                    Dp = np.zeros_like(D)
+                    for k in range(bs):
+                        Dp[:, k, k] = D[:, k, k]
+                    D = Dp
                 dinv = np.linalg.inv(D)
             else:
                 dinv = 1.0 / G.data[diag]

@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.cb_quad) == 8 + 8 * 4 * 64 + 8 * 64
     assert ctypes.sizeof(_lib.cb_mat) == 48
     assert ctypes.sizeof(_lib.cb_mesh_view) == 120
-    assert ctypes.sizeof(_lib.cb_ksp_opts) == 72
+    assert ctypes.sizeof(_lib.cb_ksp_opts) == 96
     assert ctypes.sizeof(_lib.cb_amg_level) == 248
     assert ctypes.sizeof(_lib.cb_amg) == 48
     assert ctypes.sizeof(_lib.cb_ksp_result) == 40
