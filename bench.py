@@ -232,8 +232,15 @@ def main() -> None:
     ap.add_argument("--graph", type=int, default=0, choices=[-1, 0, 1],
                     help="CUDA-graph replay of the PCG iteration: 0 / 1 on (default), -1 eager launches only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rbm", default="auto", choices=["auto", "on", "off"],
+                    help="rigid-body coarse correction in the elasticity AMG preconditioner (pc_amg_rigid_body_correction); "
+                         "auto: on for 1 GPU (validated there), off on partitioned meshes")
     args = ap.parse_args()
     KSP["pc_type"] = args.pc
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    use_rbm = args.pc == "hypre" and (args.rbm == "on" or (args.rbm == "auto" and world_env == 1))
+    if use_rbm:
+        KSP["pc_amg_rigid_body_correction"] = True
     if args.graph != 0:
         KSP["ksp_use_graph"] = args.graph
     if args.impl == "reference":
@@ -364,7 +371,9 @@ def main() -> None:
                        "n": args.n, "tets": n_tets, "vertices": n_verts,
                        "block_nnz": nnzb_total, "krylov_its_state_adjoint_elasticity": list(its[-1]),
                        "ksp_options": {k: v for k, v in KSP.items()},
-                       "pc_on_device": ("smoothed-aggregation AMG" if args.pc == "hypre" else "jacobi"),
+                       "pc_on_device": (("smoothed-aggregation AMG" + (" + rigid-body coarse correction for the elasticity "
+                                                                       "system" if use_rbm else ""))
+                                        if args.pc == "hypre" else "jacobi"),
                        "l2_policy": "inputs larger than L2 (elasticity matrix %.2f GB, L2 126 MB)" % (76e-9 * nnzb_rank),
                        "parallelism": "1 GPU" if dist is None else (
                            f"mesh partitioned into {world} vertex slabs, " +
