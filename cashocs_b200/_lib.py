@@ -216,6 +216,13 @@ SIGNATURES = {
     "cb_gradient_frobenius_max": (I32, [P, I32, I64, P, P, P, P, P, I64]),
     "cb_move_mesh": (I32, [P, I64, P, P, P, DBL]),
     "cb_functional": (I32, [P, I32, I64, P, P, DBL, P, DBL, P, P, P, I64]),
+    "cb_amg_rbm_aggregate_geometry": (I32, [P, I64, P, P, P, P, P, P, P]),
+    "cb_amg_rbm_tentative": (I32, [P, I64, P, P, P, P, P, P, P, P]),
+    "cb_amg_rbm_spgemm_terms": (I32, [P, I32, I64, P, P, P, P, P, P]),
+    "cb_amg_rbm_prolongator_finish": (I32, [P, I64, P, I64, P, P, P, DBL, P]),
+    "cb_amg_rbm_transpose_blocks": (I32, [P, I64, P, P, P]),
+    "cb_amg_rbm_restrict": (I32, [P, I64, P, P, P, P, P, P]),
+    "cb_amg_rbm_prolong": (I32, [P, I64, P, P, P, P, P]),
     "cb_boundary_measure": (I32, [P, I32, I64, P, P, P, P, I64]),
     "cb_boundary_measure_gradient": (I32, [P, I32, I64, I64, P, P, P, P, P, P]),
     "cb_intersection_test": (I32, [P, I32, I64, I64, P, P, P, P, P]),

@@ -297,6 +297,30 @@ typedef struct {
   const double* coarse_inv;   /* dense inverse of the last level's operator (nullable) */
 } cb_amg;
 
+/* ---- Rigid-body modes inside the hierarchy (3-D, 3 x 3 blocks): WORK IN PROGRESS, not yet used by cb_ksp_solve.
+ * Every aggregate J is two coarse nodes (2J translations, 2J+1 rotations about its centroid scaled by its radius);
+ * layout and symbolic phase: cashocs_b200/_utils/amg_rbm.py; arithmetic checked on the CPU by
+ * tests/test_amg_rbm.py.  All value arrays hold row-major 3 x 3 blocks. */
+/* C [nc,3] centroid of the translation nodes, S [nc] radius max(|x_i - C| + s_i) of every aggregate. */
+int cb_amg_rbm_aggregate_geometry(void* stream, int64_t nc, const int64_t* member_ptr, const int32_t* member_idx,
+                                  const uint8_t* kind, const double* centre, const double* scale, double* C, double* S);
+/* Tentative prolongator blocks (translation node: I and cross(x - C)/S; rotation node: s/S I). */
+int cb_amg_rbm_tentative(void* stream, int64_t n, const int64_t* t_rowptr, const int32_t* agg, const uint8_t* kind,
+                         const double* centre, const double* scale, const double* C, const double* S, double* t_val);
+/* out[q] = sum over the term segment of q of op(lhs[src_l]) * rhs[src_r]; trans_l: op = transpose (P^T (A P)). */
+int cb_amg_rbm_spgemm_terms(void* stream, int trans_l, int64_t nnz_out, const int64_t* seg_ptr, const int32_t* src_l,
+                            const int32_t* src_r, const double* lhs, const double* rhs, double* out);
+/* p_val holds A*T on entry and P = T - omega D^-1 (A T) on exit (D = diag(A), dinv [3n]). */
+int cb_amg_rbm_prolongator_finish(void* stream, int64_t n, const int64_t* p_rowptr, int64_t nt, const int64_t* t2p,
+                                  const double* t_val, const double* dinv, double omega, double* p_val);
+/* pt_val[k] = transpose(p_val[perm[k]]). */
+int cb_amg_rbm_transpose_blocks(void* stream, int64_t nnz, const int64_t* perm, const double* p_val, double* pt_val);
+/* bc = P^T (b - t)  and  x += P xc. */
+int cb_amg_rbm_restrict(void* stream, int64_t ncn, const int64_t* pt_rowptr, const int32_t* pt_col, const double* pt_val,
+                        const double* b, const double* t, double* bc);
+int cb_amg_rbm_prolong(void* stream, int64_t n, const int64_t* p_rowptr, const int32_t* p_col, const double* p_val,
+                       const double* xc, double* x);
+
 typedef struct {
   int32_t ksp_type;
   int32_t pc_type;

@@ -1,0 +1,87 @@
+"""GPU: the kernels of ``csrc/amg_rbm.cu`` (rigid-body modes inside the AMG hierarchy, round-2 work in progress) against
+their numpy restatement in ``tests/test_amg_rbm.py``.
+
+The kernels were written when the GPU budget of round 1 was spent: they compile for sm_100a and their arithmetic is
+checked on the CPU, but they have never run on a device, so this module is opt-in (``CASHOCS_B200_WIP=1``) until its
+first green run -- the first thing to do in round 2."""
+
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cashocs_b200 import _lib
+
+import test_amg_rbm as ref
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("CASHOCS_B200_WIP") != "1",
+                                 reason="round-2 work in progress: kernels not yet validated on a GPU (set CASHOCS_B200_WIP=1)")]
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return (t if dtype is None else t.to(dtype)).cuda()
+
+
+def test_rbm_kernels_match_the_numpy_restatement():
+    om, A, _ = ref.elasticity(6)
+    sym, levels = ref.build_hierarchy(om, A)
+    lib, s = _lib.load(), _lib.stream_ptr()
+    centre, scale = om.coords.copy(), np.zeros(om.num_vertices)
+    val = A.data.copy()
+    for lv in levels[:-1]:
+        L = lv["L"]
+        g = {k: getattr(L, k).cuda() for k in ("member_ptr", "member_idx", "kind", "t_rowptr", "t_col", "agg", "p_rowptr", "p_col",
+                                               "t2p", "pt_perm", "pt_rowptr", "pt_col", "at_seg", "at_sl", "at_sr", "ap_seg",
+                                               "ap_sl", "ap_sr", "ac_seg", "ac_sl", "ac_sr")}
+        d_centre, d_scale, d_val = dev(centre), dev(scale), dev(val)
+        Cd = torch.zeros(L.nc, 3, dtype=torch.float64, device="cuda")
+        Sd = torch.zeros(L.nc, dtype=torch.float64, device="cuda")
+        _lib.check(lib.cb_amg_rbm_aggregate_geometry(s, L.nc, _lib.ptr(g["member_ptr"]), _lib.ptr(g["member_idx"]),
+                                                     _lib.ptr(g["kind"]), _lib.ptr(d_centre), _lib.ptr(d_scale), _lib.ptr(Cd),
+                                                     _lib.ptr(Sd)), "geometry")
+        assert np.allclose(Cd.cpu().numpy(), lv["C"], rtol=1e-14, atol=1e-15) and np.allclose(Sd.cpu().numpy(), lv["S"], rtol=1e-14)
+        nt = int(L.t_col.numel())
+        Td = torch.zeros(nt * 9, dtype=torch.float64, device="cuda")
+        _lib.check(lib.cb_amg_rbm_tentative(s, L.n, _lib.ptr(g["t_rowptr"]), _lib.ptr(g["agg"]), _lib.ptr(g["kind"]),
+                                            _lib.ptr(d_centre), _lib.ptr(d_scale), _lib.ptr(Cd), _lib.ptr(Sd), _lib.ptr(Td)), "tentative")
+        assert np.allclose(Td.cpu().numpy().reshape(-1, 3, 3), lv["T"], rtol=1e-13, atol=1e-15)
+        npz = int(L.p_col.numel())
+        Pd = torch.zeros(npz * 9, dtype=torch.float64, device="cuda")
+        _lib.check(lib.cb_amg_rbm_spgemm_terms(s, 0, npz, _lib.ptr(g["at_seg"]), _lib.ptr(g["at_sl"]), _lib.ptr(g["at_sr"]),
+                                               _lib.ptr(d_val), _lib.ptr(Td), _lib.ptr(Pd)), "A*T")
+        _lib.check(lib.cb_amg_rbm_prolongator_finish(s, L.n, _lib.ptr(g["p_rowptr"]), nt, _lib.ptr(g["t2p"]), _lib.ptr(Td),
+                                                     _lib.ptr(dev(lv["dinv"])), float(lv["omega"]), _lib.ptr(Pd)), "finish")
+        scale_p = np.max(np.abs(lv["P"]))
+        assert np.max(np.abs(Pd.cpu().numpy().reshape(-1, 3, 3) - lv["P"])) <= 1e-13 * scale_p
+        nap = int(L.ap_col.numel())
+        APd = torch.zeros(nap * 9, dtype=torch.float64, device="cuda")
+        _lib.check(lib.cb_amg_rbm_spgemm_terms(s, 0, nap, _lib.ptr(g["ap_seg"]), _lib.ptr(g["ap_sl"]), _lib.ptr(g["ap_sr"]),
+                                               _lib.ptr(d_val), _lib.ptr(Pd), _lib.ptr(APd)), "A*P")
+        assert np.max(np.abs(APd.cpu().numpy().reshape(-1, 3, 3) - lv["AP"])) <= 1e-12 * np.max(np.abs(lv["AP"]))
+        nac = lv["Ac"].shape[0]
+        Acd = torch.zeros(nac * 9, dtype=torch.float64, device="cuda")
+        _lib.check(lib.cb_amg_rbm_spgemm_terms(s, 1, nac, _lib.ptr(g["ac_seg"]), _lib.ptr(g["ac_sl"]), _lib.ptr(g["ac_sr"]),
+                                               _lib.ptr(Pd), _lib.ptr(APd), _lib.ptr(Acd)), "Pt*AP")
+        assert np.max(np.abs(Acd.cpu().numpy().reshape(-1, 3, 3) - lv["Ac"])) <= 1e-12 * np.max(np.abs(lv["Ac"]))
+        # transfer operators
+        Ps = ref.sp.csr_matrix(ref.bsr(L.p_rowptr, L.p_col, lv["P"], (3 * L.n, 6 * L.nc)))
+        Ptd = torch.zeros(npz * 9, dtype=torch.float64, device="cuda")
+        _lib.check(lib.cb_amg_rbm_transpose_blocks(s, npz, _lib.ptr(g["pt_perm"]), _lib.ptr(Pd), _lib.ptr(Ptd)), "transpose")
+        rng = np.random.RandomState(3)
+        b, t, xc, x = rng.rand(3 * L.n), rng.rand(3 * L.n), rng.rand(6 * L.nc), rng.rand(3 * L.n)
+        bcd = torch.zeros(6 * L.nc, dtype=torch.float64, device="cuda")
+        _lib.check(lib.cb_amg_rbm_restrict(s, 2 * L.nc, _lib.ptr(g["pt_rowptr"]), _lib.ptr(g["pt_col"]), _lib.ptr(Ptd),
+                                           _lib.ptr(dev(b)), _lib.ptr(dev(t)), _lib.ptr(bcd)), "restrict")
+        assert np.allclose(bcd.cpu().numpy(), Ps.T @ (b - t), rtol=1e-12, atol=1e-13)
+        xd = dev(x)
+        _lib.check(lib.cb_amg_rbm_prolong(s, L.n, _lib.ptr(g["p_rowptr"]), _lib.ptr(g["p_col"]), _lib.ptr(Pd), _lib.ptr(dev(xc)),
+                                          _lib.ptr(xd)), "prolong")
+        assert np.allclose(xd.cpu().numpy(), x + Ps @ xc, rtol=1e-12, atol=1e-13)
+        val = lv["Ac"]
+        centre = np.repeat(lv["C"], 2, axis=0)
+        scale = np.zeros(2 * L.nc)
+        scale[1::2] = lv["S"]
