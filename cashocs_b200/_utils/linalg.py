@@ -523,7 +523,12 @@ class LinearSolver:
             hierarchy = self.amg_hierarchy(A, ksp_options or {})
             hstruct = hierarchy.struct()
             opts.amg = C.cast(C.pointer(hstruct), C.c_void_p)
-            if _truthy((ksp_options or {}).get("pc_amg_rigid_body_correction", False)) and A.bs >= 2:
+            # rigid-body coarse correction: default for vertex-blocked vector operators (the elasticity Riesz
+            # problem) on one GPU, where it is validated; an explicit option overrides (True also on partitions)
+            applicable = A.bs >= 2 and A.bs == A.mesh.dim and A.nrows == A.mesh.n_owned_vertices
+            wanted = (ksp_options or {}).get("pc_amg_rigid_body_correction", None)
+            use_rbm = applicable and (A.mesh.dist is None if wanted is None else _truthy(wanted))
+            if use_rbm:
                 rbm = self.rigid_body_correction(A, hierarchy)
                 opts.rbm_coords, opts.rbm_einv, opts.rbm_work = (t.data_ptr() for t in rbm)
         n, nc = A.nrows * A.bs, A.ncols * A.bs
