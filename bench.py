@@ -239,8 +239,8 @@ def main() -> None:
     KSP["pc_type"] = args.pc
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
     use_rbm = args.pc == "hypre" and (args.rbm == "on" or (args.rbm == "auto" and world_env == 1))
-    if use_rbm:
-        KSP["pc_amg_rigid_body_correction"] = True
+    if args.pc == "hypre":
+        KSP["pc_amg_rigid_body_correction"] = use_rbm  # explicit either way (the library default is on for 1 GPU)
     if args.graph != 0:
         KSP["ksp_use_graph"] = args.graph
     if args.impl == "reference":

@@ -39,8 +39,7 @@ def main():
     ap.add_argument("--rbm", type=int, default=0, help="1: rigid-body coarse correction in the elasticity solve")
     args = ap.parse_args()
     bench.KSP["pc_type"] = args.pc
-    if args.rbm:
-        bench.KSP["pc_amg_rigid_body_correction"] = True
+    bench.KSP["pc_amg_rigid_body_correction"] = bool(args.rbm)
     sop = bench.build_problem(args.n)
     h = 1.0 / args.n
     bench.evaluation_step(sop, h)
