@@ -7,9 +7,9 @@ and PETSc's ``pc_type gamg`` map to on the device.  Unknown-based smoothed aggre
 scalar prolongator shared by all components, so every level is a block-CSR matrix of the fine
 block size and runs through the same SpMV kernel.
 
-* Symbolic (once per sparsity pattern, i.e. once per mesh topology): MIS(1) aggregation on the
+* Symbolic (once per sparsity pattern, i.e. once per mesh topology): MIS(2) aggregation on the
   matrix graph with hashed priorities (integer arithmetic only -> deterministic), patterns of
-  ``P``, ``P^T``, ``A P`` and ``P^T A P``.
+  ``P``, ``P^T``, ``A P`` and ``P^T A P`` with their term lists.
 * Numeric (every time the matrix values change): strength matrix ``S = tr(A_ij)/bs``, smoothed
   prolongator ``P = (I - 4/(3 lmax) D_S^-1 S) T``, Galerkin operators, inverse diagonals and
   Gershgorin bounds for the Chebyshev smoothers.
