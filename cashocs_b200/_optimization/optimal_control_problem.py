@@ -28,7 +28,7 @@ def _enlist(x):
 class OptimalControlProblem:
     def __init__(self, state_forms, bcs_list, cost_functional_form, states, controls, adjoints, config=None,
                  ksp_options=None, adjoint_ksp_options=None, gradient_ksp_options=None, linear_solver=None,
-                 adjoint_linear_solver=None, control_constraints=None) -> None:
+                 adjoint_linear_solver=None, control_constraints=None, control_bcs_list=None) -> None:
         self.state_forms = _enlist(state_forms)
         self.states, self.controls, self.adjoints = _enlist(states), _enlist(controls), _enlist(adjoints)
         if not (len(self.states) == len(self.adjoints) == len(self.state_forms) == 1 and len(self.controls) == 1):
@@ -53,13 +53,17 @@ class OptimalControlProblem:
         self.adjoint_problem = adjoint_problem.AdjointProblem(
             self.mesh, self.state_forms, self.bcs_list, self.cost, self.states, self.adjoints, self.state_problem,
             self.adjoint_ksp_options, adjoint_linear_solver)
+        # Dirichlet conditions on the control (optimal_control_problem.py:212-230): the Riesz problem uses the
+        # homogenised ones, `solve` imposes the values on the control (`_setup_control_bcs`, :306-311)
+        self.control_bcs_list = _enlist(control_bcs_list) if control_bcs_list is not None else []
         self.gradient_problem = control_gradient_problem.ControlGradientProblem(
             self.mesh, self.cost, self.state_forms[0], self.controls[0], self.adjoints[0], self.gradient,
             self.state_problem, self.adjoint_problem, self.config,
-            None if gradient_ksp_options is None else _enlist(gradient_ksp_options)[0])
+            None if gradient_ksp_options is None else _enlist(gradient_ksp_options)[0],
+            control_bcs=self.control_bcs_list)
         self.reduced_cost_functional = cost_functional.ReducedCostFunctional(
             self.mesh, self.cost, self.states, self.state_problem, self.controls[0],
-            self.gradient_problem.scalar_product)
+            self.gradient_problem.mass_product)
 
         # the optimisation loop sees the same surface as for shape problems
         self.problem_type = "control"
@@ -87,6 +91,7 @@ class OptimalControlProblem:
 
         self.output_manager = managers.OutputManager(self)
         self.config.set("OptimizationRoutine", "algorithm", algorithm)
+        self._setup_control_bcs()
         line_search = ls.create_line_search(self)
         if algorithm == "gradient_descent":
             self.solver = algs.GradientDescentMethod(self, line_search)
@@ -99,6 +104,17 @@ class OptimalControlProblem:
                                          f"{algorithm!r}: the device path drives gradient_descent, bfgs and conjugate_gradient")
         self.solver.run()
         self.solver.post_processing()
+
+    def _setup_control_bcs(self) -> None:
+        """``_setup_control_bcs`` (``optimal_control_problem.py:306-311``): the control takes its boundary values."""
+        if self.control_bcs_list:
+            import torch
+
+            flag, val = forms.bc_flag_arrays(self.mesh, self.control_bcs_list, 1)
+            if flag is not None:
+                u = self.controls[0].vector
+                u.copy_(torch.where(flag.bool(), val, u))
+                self._erase_pde_memory()
 
     def compute_state_variables(self) -> None:
         self.state_problem.solve()

@@ -756,8 +756,16 @@ class PoissonControlProblem:
     """F = grad y . grad p - u p;  J = 1/2 |y - y_d|^2 + alpha/2 |u|^2  (tests/test_pde_problems.py:59-84)."""
 
     def __init__(self, mesh, y_d, u, alpha=1e-6, bc_markers=(1, 2), state_ksp=None, adjoint_ksp=None,
-                 riesz_ksp=None, control_constraints=None):
+                 riesz_ksp=None, control_constraints=None, control_bcs=None):
         self.mesh, self.coords, self.cells = mesh, mesh.coords, mesh.cells
+        # Dirichlet conditions on the control (optimal_control_problem.py:212-230,306-311): (markers, value); the
+        # Riesz problem gets the homogenised conditions, the control itself the values (set by the solve loops)
+        self.control_bc_dofs = np.zeros(0, dtype=np.int64)
+        if control_bcs is not None:
+            markers, value = control_bcs
+            self.control_bc_dofs = mesh.boundary_vertices(markers)
+            u = np.array(u, dtype=float, copy=True)
+            u[self.control_bc_dofs] = value
         self.d, self.nv = mesh.dim, mesh.num_vertices
         self.y_d, self.u, self.alpha = y_d, u, alpha
         # box constraints u_a <= u <= u_b (optimal_control/box_constraints.py:29-182); floats or nodal arrays
@@ -791,9 +799,14 @@ class PoissonControlProblem:
         PoissonShapeProblem._check(reason)
         return self.p
 
-    def mass_matrix(self):
+    def mass_matrix(self, riesz=True):
+        """L2 mass matrix; ``riesz``: with the homogenised control BCs eliminated symmetrically
+        (``control_form_handler.py:82-137``) -- the Riesz matrix and the scalar product of the optimisation loop."""
         _, vol, _ = fem.cell_geometry(self.coords, self.cells)
-        M, _ = fem.assemble_system(fem.mass_elements(vol, self.d), None, self.cells, self.nv)
+        if riesz and self.control_bc_dofs.size:
+            M, _ = fem.assemble_system(fem.mass_elements(vol, self.d), None, self.cells, self.nv, self.control_bc_dofs, 0.0)
+        else:
+            M, _ = fem.assemble_system(fem.mass_elements(vol, self.d), None, self.cells, self.nv)
         return M
 
     def compute_gradient(self):
@@ -802,6 +815,8 @@ class PoissonControlProblem:
         self.solve_adjoint()
         _, vol, _ = fem.cell_geometry(self.coords, self.cells)
         be = fem.load_elements_p1(vol, self.cells, self.alpha * self.u - self.p, self.d)
+        if self.control_bc_dofs.size:
+            _, be = fem.apply_bcs_elementwise(None, be, self.cells, self.control_bc_dofs, 0.0, self.nv)
         b = fem.assemble_vector(be, self.cells, self.nv)
         self.M = self.mass_matrix()
         self.g, reason, self.its["gradient"], _ = krylov.solve(self.M, b, self.riesz_ksp)
@@ -839,7 +854,7 @@ class PoissonControlProblem:
         return d
 
     def cost(self):
-        M = self.mass_matrix()
+        M = self.mass_matrix(riesz=False)
         e = self.y - self.y_d
         return 0.5 * float((M @ e) @ e) + 0.5 * self.alpha * float((M @ self.u) @ self.u)
 

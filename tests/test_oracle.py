@@ -404,3 +404,18 @@ def test_surface_regularization_reference_scenario():
     s0 = p3.surface()
     p3.coords += h.reshape(-1, 3)
     assert abs((p3.surface() - s0) - g @ h) < 1e-9 * abs(g @ h) + 1e-11
+
+
+def test_control_bcs_reference_budget():
+    """tests/test_optimal_control.py:569-580 (reference): Dirichlet conditions on the control, L-BFGS <= 9 iterations,
+    the control keeps its boundary value exactly."""
+    value = np.random.RandomState(300696).rand()
+    om = meshes.regular_mesh(10)
+    yd = np.sin(2 * np.pi * om.coords[:, 0]) * np.sin(2 * np.pi * om.coords[:, 1])
+    prob = pipeline.PoissonControlProblem(om, yd, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4),
+                                          control_bcs=((1, 2, 3, 4), value))
+    ok, hist = pipeline.lbfgs(prob, rtol=1e-2, max_iter=9, memory=3)
+    b = om.boundary_vertices((1, 2, 3, 4))
+    assert ok and len(hist) - 1 <= 9 and np.all(prob.u[b] == value)
+    g = prob.compute_gradient()
+    assert np.all(g[b] == 0.0)
