@@ -90,7 +90,9 @@ def test_full_size_solves_have_small_true_residuals(mesh):
     g = torch.zeros(nv * 3, dtype=torch.float64, device="cuda")
     res = cb.LinearSolver().solve(g, A=E, b=rhs, ksp_options=ksp)
     assert res.reason == 2 and res.its < 250
-    assert float((E.mult(g) - rhs).norm() / rhs.norm()) < 1e-7
+    # the KSP test is on the preconditioned norm (PETSc's default): with the rigid-body coarse correction in the
+    # preconditioner |M b| is about twice as large, the true residual at convergence about three times (CPU oracle)
+    assert float((E.mult(g) - rhs).norm() / rhs.norm()) < 5e-7
 
 
 def test_full_size_move_revert_round_trip(mesh):
