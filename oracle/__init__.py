@@ -40,6 +40,10 @@ test) and is pinned against everything the reference's own tests hold for this p
 * box-constrained controls 0 <= u <= 100 ``tests/test_optimal_control.py:196-225`` (gd <= 22, L-BFGS <= 11,
   NCG FR / PR / HS / DY / HZ <= 47 / 24 / 30 / 9 / 37) -> pinned, exactly budget - 1 for all seven
   (33 reference iteration counts in total);
+* Newton's method for the semilinear state equation of the reference's tests (``oracle/nonlinear.py``;
+  ``tests/test_nonlinear_solvers.py:28-61``, ``tests/test_optimal_control.py:364-376``): solution equal to an independent
+  nonlinear solve, control-gradient Taylor rate > 1.9 -> pinned (the device layer does not have the nonlinear
+  kernels yet: this is the checker they will be held to);
 * P2 state / adjoint (``oracle/p2.py``): no reference test holds values -> validated by patch tests and
   Taylor tests only ("parity unpinned" for the P2 element tensors).
 

@@ -727,6 +727,27 @@ def ncg(prob: PoissonShapeProblem, method="DY", rtol=1e-2, atol=0.0, max_iter=50
     return False, hist
 
 
+def control_gradient_test(prob, rng=None, h=None):
+    """Taylor test of ``cashocs/verification.py:38-179`` for control problems; returns the last convergence rate."""
+    rng = rng or np.random.RandomState(300696)
+    u0 = prob.u.copy()
+    if h is None:
+        h = rng.rand(prob.nv)
+    prob.solve_state()
+    J0 = prob.cost()
+    g = prob.compute_gradient()
+    dJh = prob.scalar_product(g, h)
+    eps_list = [1e-2 / 2**i for i in range(4)]
+    res = []
+    for eps in eps_list:
+        prob.u = u0 + eps * h
+        prob.solve_state()
+        res.append(abs(prob.cost() - J0 - eps * dJh))
+    prob.u = u0
+    rates = [np.log(res[i] / res[i - 1]) / np.log(eps_list[i] / eps_list[i - 1]) for i in range(1, 4)]
+    return rates[-1], rates, res
+
+
 def shape_gradient_test(prob: PoissonShapeProblem, rng=None, h=None):
     """Taylor test of ``cashocs/verification.py:182-302``; returns the last convergence rate."""
     rng = rng or np.random.RandomState(300696)
@@ -756,8 +777,11 @@ class PoissonControlProblem:
     """F = grad y . grad p - u p;  J = 1/2 |y - y_d|^2 + alpha/2 |u|^2  (tests/test_pde_problems.py:59-84)."""
 
     def __init__(self, mesh, y_d, u, alpha=1e-6, bc_markers=(1, 2), state_ksp=None, adjoint_ksp=None,
-                 riesz_ksp=None, control_constraints=None, control_bcs=None):
+                 riesz_ksp=None, control_constraints=None, control_bcs=None, cubic=0.0):
         self.mesh, self.coords, self.cells = mesh, mesh.coords, mesh.cells
+        # semilinear state equation grad y . grad p + cubic y^3 p - u p (tests/test_optimal_control.py:364-376),
+        # solved by Newton's method (oracle/nonlinear.py) when cubic != 0
+        self.cubic = float(cubic)
         # Dirichlet conditions on the control (optimal_control_problem.py:212-230,306-311): (markers, value); the
         # Riesz problem gets the homogenised conditions, the control itself the values (set by the solve loops)
         self.control_bc_dofs = np.zeros(0, dtype=np.int64)
@@ -788,12 +812,29 @@ class PoissonControlProblem:
         return fem.assemble_system(Ke, be, self.cells, self.nv, self.bc, 0.0)
 
     def solve_state(self):
+        if self.cubic != 0.0:
+            from oracle import nonlinear
+
+            _, vol, _ = fem.cell_geometry(self.coords, self.cells)
+            load = fem.load_elements_p1(vol, self.cells, self.u, self.d)
+            self.y, self.its["newton"] = nonlinear.newton_solve(self.coords, self.cells, load, self.cubic, self.bc)
+            return self.y
         A, b = self._system(self.u, 1.0)
         self.y, reason, self.its["state"], _ = krylov.solve(A, b, self.state_ksp)
         PoissonShapeProblem._check(reason)
         return self.y
 
     def solve_adjoint(self):
+        if self.cubic != 0.0:  # linearised operator K + 3 c M[y^2] (self-adjoint)
+            from oracle import nonlinear
+
+            _, vol, G = fem.cell_geometry(self.coords, self.cells)
+            Ke = fem.stiffness_elements(vol, G) + nonlinear.weighted_mass_elements(vol, self.cells, self.y, self.d, self.cubic)
+            be = -fem.load_elements_p1(vol, self.cells, self.y - self.y_d, self.d)
+            A, b = fem.assemble_system(Ke, be, self.cells, self.nv, self.bc, 0.0)
+            self.p, reason, self.its["adjoint"], _ = krylov.solve(A, b, self.adjoint_ksp)
+            PoissonShapeProblem._check(reason)
+            return self.p
         A, b = self._system(self.y - self.y_d, -1.0)
         self.p, reason, self.its["adjoint"], _ = krylov.solve(A, b, self.adjoint_ksp)
         PoissonShapeProblem._check(reason)

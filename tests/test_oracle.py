@@ -419,3 +419,40 @@ def test_control_bcs_reference_budget():
     assert ok and len(hist) - 1 <= 9 and np.all(prob.u[b] == value)
     g = prob.compute_gradient()
     assert np.all(g[b] == 0.0)
+
+
+def test_newton_solver_and_semilinear_control_gradient():
+    """tests/test_nonlinear_solvers.py:28-61 (reference): -Laplace u + 1e2 u^3 = 1 on regular_mesh(5) by Newton from
+    zero with rtol 1e-9 / atol 1e-10 equals the solution of an independent nonlinear solve;
+    tests/test_optimal_control.py:364-376: control problem with the y^3 term, Taylor rate of the gradient > 1.9."""
+    import scipy.optimize
+
+    from oracle import fem, nonlinear
+
+    om = meshes.regular_mesh(5)
+    bc = om.boundary_vertices((1, 2, 3, 4))
+    _, vol, G = fem.cell_geometry(om.coords, om.cells)
+    load = fem.load_elements_p1(vol, om.cells, np.ones(om.num_vertices), 2)
+    u, its = nonlinear.newton_solve(om.coords, om.cells, load, 1e2, bc, rtol=1e-9, atol=1e-10, max_iter=50)
+    assert 2 <= its <= 10 and np.all(u[bc] == 0.0)
+    # independent check: scipy's hybrid Powell solver on the free unknowns of the same discrete residual
+    K = fem.assemble_matrix(fem.stiffness_elements(vol, G), om.cells, om.num_vertices)
+    free = np.setdiff1d(np.arange(om.num_vertices), bc)
+
+    def F(x):
+        w = np.zeros(om.num_vertices)
+        w[free] = x
+        r = K @ w + fem.assemble_vector(nonlinear.cubic_load_elements(vol, om.cells, w, 2, 1e2) - load, om.cells, om.num_vertices)
+        return r[free]
+
+    sol = scipy.optimize.root(F, np.zeros(free.size), method="hybr", tol=1e-13)
+    assert sol.success and np.allclose(u[free], sol.x, rtol=1e-5, atol=1e-8)
+    with pytest.raises(RuntimeError, match="Maximum number of iterations"):
+        nonlinear.newton_solve(om.coords, om.cells, load, 1e2, bc, rtol=1e-9, atol=1e-10, max_iter=1)
+
+    om = meshes.regular_mesh(10)
+    yd = np.sin(2 * np.pi * om.coords[:, 0]) * np.sin(2 * np.pi * om.coords[:, 1])
+    prob = pipeline.PoissonControlProblem(om, yd, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4), cubic=1.0)
+    assert pipeline.control_gradient_test(prob, rng=np.random.RandomState(300696))[0] > 1.9
+    lin = pipeline.PoissonControlProblem(om, yd, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4))
+    assert pipeline.control_gradient_test(lin, rng=np.random.RandomState(300696))[0] > 1.9
