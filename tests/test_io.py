@@ -174,3 +174,65 @@ def test_unsupported_subsystems_are_refused_loudly():
         cfg.set(sec, key, val)
         with pytest.raises(cb.ConfigError, match="outside the B200 hot path"):
             cfg.validate_config()
+
+
+# ------------------------------------------------------------------ the reference's own config tests (tests/test_config.py)
+def _sop_like_config():
+    """The keys of the reference's tests/config_sop.ini that matter for validation."""
+    cfg = cb.Config()
+    cfg.set("ShapeGradient", "shape_bdry_def", "[1]")
+    cfg.set("MeshQuality", "tol_lower", "0.01")
+    cfg.set("MeshQuality", "tol_upper", "0.02")
+    return cfg
+
+
+REFERENCE_CONFIG_ERRORS = [
+    # (tests/test_config.py line, overrides, expected message)
+    (109, [("Mesh", "remesh", "1.0")], "Key remesh in section Mesh has the wrong type. Required type is bool."),
+    (131, [("MeshQuality", "tol_lower", "0.5"), ("MeshQuality", "tol_upper", "0.1")],
+     "The value of key tol_upper in section MeshQuality is smaller than the value of key tol_lower in section "
+     "MeshQuality, but it should be larger."),
+    (144, [("ShapeGradient", "dist_max", "0.5")],
+     "The value of key dist_max in section ShapeGradient is smaller than the value of key dist_min in section "
+     "ShapeGradient, but it should be larger."),
+    (156, [("Regularization", "x_end", "-1.0")],
+     "The value of key x_end in section Regularization is smaller than the value of key x_start in section "
+     "Regularization, but it should be larger."),
+    (168, [("Mesh", "geo_file", "test.msh")],
+     "Key geo_file in section Mesh has the wrong file extension, it should end in .geo."),
+    (180, [("MeshQuality", "tol_lower", "-1e-1")], "Key tol_lower in section MeshQuality is negative, but it must not be."),
+    (192, [("MeshQuality", "tol_upper", "0.0")],
+     "Key tol_upper in section MeshQuality is non-positive, but it most be positive."),
+    (204, [("MeshQuality", "tol_upper", "2.0")],
+     "Key tol_upper in section MeshQuality is larger than one, but it must be smaller."),
+    (216, [("MeshQuality", "volume_change", "0.5")],
+     "Key volume_change in section MeshQuality is smaller than one, but it must be larger."),
+    (228, [("OptimizationRoutine", "gradient_method", "mymethod")],
+     "Key gradient_method in section OptimizationRoutine has a wrong value. Possible options are ['direct', 'iterative']."),
+    (240, [("Output", "save_mesh", "True")],
+     "Key save_mesh in section Output requires key gmsh_file in section Mesh to be present."),
+]
+
+
+@pytest.mark.parametrize("line,overrides,message", REFERENCE_CONFIG_ERRORS, ids=[str(c[0]) for c in REFERENCE_CONFIG_ERRORS])
+def test_reference_config_tests(line, overrides, message):
+    """tests/test_config.py of the reference, test by test: the same ConfigError with the same message."""
+    cfg = _sop_like_config()
+    cfg.validate_config()
+    for sec, key, val in overrides:
+        cfg.set(sec, key, val)
+    with pytest.raises(cb.ConfigError) as e:
+        cfg.validate_config()
+    assert "You have some error(s) in your config file" in str(e.value)
+    assert message in str(e.value)
+
+
+def test_reference_incorrect_config_file(tmp_path):
+    """tests/test_config.py:117-126 with a file shaped like tests/test_config.ini: unknown sections, misplaced key."""
+    path = tmp_path / "bad.ini"
+    path.write_text("[A]\na = 1\n\n[B]\nb = 2\n\n[StateSystem]\nalgorithm = False\n")
+    cfg = cb.load_config(str(path))
+    with pytest.raises(cb.ConfigError) as e:
+        cfg.validate_config()
+    assert ("The following section is not valid: <Section: A>\nThe following section is not valid: <Section: B>\n"
+            "Key algorithm is not valid for section StateSystem.") in str(e.value)
