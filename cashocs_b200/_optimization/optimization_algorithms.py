@@ -151,17 +151,20 @@ class LBFGSMethod(OptimizationAlgorithm):
         self.use_bfgs_scaling = self.config.getboolean("AlgoLBFGS", "use_bfgs_scaling")
         self.bfgs_periodic_restart = self.config.getint("AlgoLBFGS", "bfgs_periodic_restart")
         self.periodic_its = 0
+        self.damped = self.config.getboolean("AlgoLBFGS", "damped")
         self.history_s: collections.deque = collections.deque()
         self.history_y: collections.deque = collections.deque()
         self.history_rho: collections.deque = collections.deque()
         self.gradient_prev = torch.zeros_like(self.gradient)
 
-    def compute_search_direction(self) -> None:
+    def compute_search_direction(self, grad: torch.Tensor | None = None) -> None:
+        """``d = -H grad`` by the two-loop recursion (``l_bfgs.py:182-232``); ``grad`` defaults to the gradient."""
         sp = self.form_handler.scalar_product
         d = self.search_direction
+        grad = self.gradient if grad is None else grad
         box = self.ova.has_box_constraints  # l_bfgs.py:182-222: recursion on the inactive set + active gradient
         if self.bfgs_memory_size > 0 and len(self.history_s) > 0:
-            d.copy_(self.gradient)
+            d.copy_(grad)
             if box:
                 self.ova.restrict_to_inactive_set(d, d)
             alphas = []
@@ -182,7 +185,15 @@ class LBFGSMethod(OptimizationAlgorithm):
                 d.add_(self.ova.restrict_to_active_set(self.gradient, torch.empty_like(d)))
             d.neg_()
         else:
-            torch.neg(self.gradient, out=d)
+            torch.neg(grad, out=d)
+
+    def _apply_inverse_hessian(self, y: torch.Tensor) -> torch.Tensor:
+        """``H y`` with the current memory (``_compute_approximate_inverse_hessian_application``, ``l_bfgs.py:331-354``)."""
+        keep = self.search_direction.clone()
+        self.compute_search_direction(y)
+        out = -self.search_direction
+        self.search_direction.copy_(keep)
+        return out
 
     def update_hessian_approximation(self) -> None:
         if self.bfgs_memory_size <= 0:
@@ -193,14 +204,25 @@ class LBFGSMethod(OptimizationAlgorithm):
             self.ova.restrict_to_inactive_set(y_k, y_k)
             self.ova.restrict_to_inactive_set(s_k, s_k)
         curvature = self.form_handler.scalar_product(y_k, s_k)
-        self.history_y.appendleft(y_k)
-        self.history_s.appendleft(s_k)
-        if curvature <= 0.0:
-            self.has_curvature_info = False
-            self.history_s.clear(), self.history_y.clear(), self.history_rho.clear()
-        else:
+        if self.damped:
+            # Powell's damping (l_bfgs.py:284-304): s is blended with H y so that the pair keeps positive curvature
+            hy = self._apply_inverse_hessian(y_k)
+            gamma = self.form_handler.scalar_product(y_k, hy)
+            phi = 1.0 if curvature >= 0.2 * gamma else (0.8 * gamma) / (gamma - curvature)
+            r_k = phi * s_k + (1.0 - phi) * hy
+            self.history_s.appendleft(r_k)
+            self.history_y.appendleft(y_k)
             self.has_curvature_info = True
-            self.history_rho.appendleft(1.0 / curvature)
+            self.history_rho.appendleft(1.0 / self.form_handler.scalar_product(y_k, r_k))
+        else:
+            self.history_y.appendleft(y_k)
+            self.history_s.appendleft(s_k)
+            if curvature <= 0.0:
+                self.has_curvature_info = False
+                self.history_s.clear(), self.history_y.clear(), self.history_rho.clear()
+            else:
+                self.has_curvature_info = True
+                self.history_rho.appendleft(1.0 / curvature)
         if len(self.history_s) > self.bfgs_memory_size:
             self.history_s.pop(), self.history_y.pop(), self.history_rho.pop()
 

@@ -361,8 +361,6 @@ class Config(configparser.ConfigParser):
             flag("MeshQuality", "remesh_iter", "remeshing needs the gmsh executable, it must be 0")
         if self.get("StateSystem", "backend").casefold() == "petsc":
             flag("StateSystem", "backend", "SNES is not built, use the cashocs backend")
-        if boolean("AlgoLBFGS", "damped"):
-            flag("AlgoLBFGS", "damped", "it must be False")
 
 
 def load_config(path: str) -> Config:

@@ -586,9 +586,10 @@ def gradient_descent(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50
     return False, hist
 
 
-def lbfgs(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50, memory=3, scaling=True, periodic_restart=0):
-    """``LBFGSMethod.run`` (``optimization_algorithms/l_bfgs.py:91-135``) with the two-loop recursion and the
-    periodic restart of ``check_restart`` (``:312-334``)."""
+def lbfgs(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50, memory=3, scaling=True, periodic_restart=0,
+          damped=False):
+    """``LBFGSMethod.run`` (``optimization_algorithms/l_bfgs.py:91-135``) with the two-loop recursion, the
+    periodic restart of ``check_restart`` (``:312-334``) and Powell's damping (``:284-304``)."""
     S, Y, RHO = [], [], []
     periodic_its = 0
     stepsize = prob.cfg.initial_stepsize
@@ -658,12 +659,28 @@ def lbfgs(prob: PoissonShapeProblem, rtol=1e-2, atol=0.0, max_iter=50, memory=3,
             y = inactive(g - g_prev)
             s = inactive(step * d)
             curv = prob.scalar_product(y, s)
-            if curv <= 0:
+            if damped:
+                # H y with the current memory (l_bfgs.py:331-354), then s blended with it so that y . r > 0
+                hy = y.copy()
+                al = []
+                for s_, y_, rho in zip(reversed(S), reversed(Y), reversed(RHO)):
+                    a = rho * prob.scalar_product(s_, hy)
+                    al.append(a)
+                    hy = hy - a * y_
+                if scaling and S:
+                    hy = hy * (prob.scalar_product(Y[-1], S[-1]) / prob.scalar_product(Y[-1], Y[-1]))
+                for (s_, y_, rho), a in zip(zip(S, Y, RHO), reversed(al)):
+                    hy = hy + (a - rho * prob.scalar_product(y_, hy)) * s_
+                gamma = prob.scalar_product(y, hy)
+                phi = 1.0 if curv >= 0.2 * gamma else (0.8 * gamma) / (gamma - curv)
+                r = phi * s + (1.0 - phi) * hy
+                S.append(r), Y.append(y), RHO.append(1.0 / prob.scalar_product(y, r))
+            elif curv <= 0:
                 S, Y, RHO = [], [], []
             else:
                 S.append(s), Y.append(y), RHO.append(1.0 / curv)
-                if len(S) > memory:
-                    S.pop(0), Y.pop(0), RHO.pop(0)
+            if len(S) > memory:
+                S.pop(0), Y.pop(0), RHO.pop(0)
 
 
 def ncg(prob: PoissonShapeProblem, method="DY", rtol=1e-2, atol=0.0, max_iter=50, periodic_restart=False,

@@ -39,7 +39,7 @@ def host_config(shape: bool, **keys) -> cb.Config:
         cfg.set("MeshQuality", "tol_upper", "0.02")
     for k, v in keys.items():
         section = {"method": "LineSearch", "polynomial_model": "LineSearch", "initial_stepsize": "LineSearch",
-                   "bfgs_periodic_restart": "AlgoLBFGS", "cg_method": "AlgoCG", "cg_periodic_restart": "AlgoCG",
+                   "bfgs_periodic_restart": "AlgoLBFGS", "damped": "AlgoLBFGS", "cg_method": "AlgoCG", "cg_periodic_restart": "AlgoCG",
                    "cg_periodic_its": "AlgoCG", "cg_relative_restart": "AlgoCG", "cg_restart_tol": "AlgoCG"}[k]
         cfg.set(section, k, str(v))
     cfg.validate_config()
@@ -128,3 +128,22 @@ def test_box_constraints_are_validated():
         ls.BoxConstraints(u, [1.0, 0.0])
     assert not ls.BoxConstraints(u, None).require_control_constraints
     assert ls.BoxConstraints(u, [float("-inf"), 3.0]).require_control_constraints
+
+
+@pytest.mark.parametrize("kind", ["control", "shape"])
+def test_damped_bfgs_host_layer_equals_oracle(kind):
+    """``[AlgoLBFGS] damped = True`` (Powell's damping, l_bfgs.py:284-304): the shipped host layer and the oracle walk the
+    same iterates and converge.  (The reference's own test, tests/test_optimal_control.py:598-621, uses a cost
+    functional outside the form family, so there is no iteration count to pin.)"""
+    make = control_oracle if kind == "control" else shape_oracle
+    ok, hist = pipeline.lbfgs(make(), rtol=1e-2, max_iter=40, memory=3, damped=True)
+    assert ok
+    host = HostProblem(make(), host_config(kind == "shape", damped=True))
+    host.solve("bfgs", rtol=1e-2, atol=0.0, max_iter=40)
+    s = host.solver
+    assert s.converged and s.iteration == len(hist) - 1
+    got = np.array([[h["objective_value"], h["relative_norm"]] for h in s.history])
+    want = np.array([[h[1], h[2]] for h in hist])
+    assert np.allclose(got, want, rtol=1e-6, atol=0.0)
+    ok0, hist0 = pipeline.lbfgs(make(), rtol=1e-2, max_iter=40, memory=3)
+    assert abs(len(hist) - len(hist0)) <= 3  # damping only acts when the curvature condition is nearly violated
