@@ -193,6 +193,8 @@ class LineSearch:
         self.decrease_measure_w_o_step = 1.0
         # line_search.py:83-86: L-BFGS steps are "Newton-like", the relative stepsize criterion does not apply
         self.is_newton_like = cfg.get("OptimizationRoutine", "algorithm").casefold() in ("bfgs", "lbfgs")
+        self.global_deformation = (self.problem_type == "shape" and cfg.getboolean("ShapeGradient", "global_deformation")
+                                   and hasattr(problem, "global_deformation_function"))
         self.log: list[tuple[str, float]] = []
 
     def initialize_stepsize(self, solver, search_direction: torch.Tensor, has_curvature_info: bool) -> None:
@@ -236,6 +238,10 @@ class LineSearch:
     def perform(self, solver, search_direction, has_curvature_info):
         """``line_search.py:95-150``: search, then ``post_line_search`` (scalar product update)."""
         deformation = self.search(solver, search_direction, has_curvature_info)
+        if deformation is not None and self.problem_type == "shape" and self.global_deformation:
+            # line_search.py:133-148: accumulate the accepted deformations (the transfer matrix of the reference maps
+            # dofs to vertices; the vertex-blocked deformation vector of the device layer needs none)
+            self.problem.global_deformation_function.vector.add_(deformation)
         if self.problem_type == "shape":
             self.form_handler.update_scalar_product()  # line_search.py:247-249
         return deformation

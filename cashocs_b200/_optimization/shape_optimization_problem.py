@@ -70,6 +70,8 @@ class ShapeOptimizationProblem:
 
         self.mesh.build_pattern()
         self.gradient = forms.Function(self.mesh, self.mesh.dim, "gradient")
+        # sum of all accepted deformations ([ShapeGradient] global_deformation, shape_optimization_problem.py)
+        self.global_deformation_function = forms.Function(self.mesh, self.mesh.dim, "global_deformation")
         self.state_problem = state_problem.StateProblem(
             self.mesh, self.state_forms, self.bcs_list, self.states, self.ksp_options, self.config, linear_solver)
         self.adjoint_problem = adjoint_problem.AdjointProblem(

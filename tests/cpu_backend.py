@@ -92,6 +92,8 @@ class HostProblem:
         self.mesh = types.SimpleNamespace(dist=None)
         n = oracle.nv if self.is_control else oracle.d * oracle.nv
         self.gradient = _Function(n)
+        if not self.is_control:
+            self.global_deformation_function = _Function(n)
         p = _Problems(self)
         self.state_problem, self.adjoint_problem, self.gradient_problem = p.state, p.adjoint, p.gradient
         self.form_handler = types.SimpleNamespace(

@@ -147,3 +147,19 @@ def test_damped_bfgs_host_layer_equals_oracle(kind):
     assert np.allclose(got, want, rtol=1e-6, atol=0.0)
     ok0, hist0 = pipeline.lbfgs(make(), rtol=1e-2, max_iter=40, memory=3)
     assert abs(len(hist) - len(hist0)) <= 3  # damping only acts when the curvature condition is nearly violated
+
+
+def test_global_deformation_like_the_reference():
+    """tests/test_shape_optimization.py:1015-1030: with ``global_deformation = True`` the sum of the accepted
+    deformations moves the initial mesh onto the optimised one (1e-13)."""
+    oracle = shape_oracle()
+    x0 = oracle.coords.copy()
+    cfg = host_config(True)
+    cfg.set("ShapeGradient", "global_deformation", "True")
+    cfg.validate_config()
+    host = HostProblem(oracle, cfg)
+    host.solve("bfgs", rtol=1e-2, atol=0.0, max_iter=7)
+    assert host.solver.converged
+    total = host.global_deformation_function.vector.numpy().reshape(-1, 2)
+    assert np.max(np.abs(x0 + total - oracle.coords)) <= 1e-13
+    assert np.max(np.abs(total)) > 1e-2
