@@ -116,6 +116,26 @@ class OptimalControlProblem:
                 u.copy_(torch.where(flag.bool(), val, u))
                 self._erase_pde_memory()
 
+    # ------------------------------------------------------------------ callbacks (optimization_problem.py:600-640)
+    def inject_pre_callback(self, function) -> None:
+        """``function()`` is called before every solve of the state system."""
+        self.state_problem.pre_callback = function
+        self._forget_solutions()
+
+    def inject_post_callback(self, function) -> None:
+        """``function()`` is called after every computation of the gradient."""
+        self.gradient_problem.post_callback = function
+        self._forget_solutions()
+
+    def inject_pre_post_callback(self, pre_function, post_function) -> None:
+        self.inject_pre_callback(pre_function)
+        self.inject_post_callback(post_function)
+
+    def _forget_solutions(self) -> None:
+        self.state_problem.has_solution = False
+        self.adjoint_problem.has_solution = False
+        self.gradient_problem.has_solution = False
+
     def compute_state_variables(self) -> None:
         self.state_problem.solve()
 

@@ -135,6 +135,26 @@ class ShapeOptimizationProblem:
         self.solver.run()
         self.solver.post_processing()
 
+    # ------------------------------------------------------------------ callbacks (optimization_problem.py:600-640)
+    def inject_pre_callback(self, function) -> None:
+        """``function()`` is called before every solve of the state system."""
+        self.state_problem.pre_callback = function
+        self._forget_solutions()
+
+    def inject_post_callback(self, function) -> None:
+        """``function()`` is called after every computation of the gradient."""
+        self.gradient_problem.post_callback = function
+        self._forget_solutions()
+
+    def inject_pre_post_callback(self, pre_function, post_function) -> None:
+        self.inject_pre_callback(pre_function)
+        self.inject_post_callback(post_function)
+
+    def _forget_solutions(self) -> None:
+        self.state_problem.has_solution = False
+        self.adjoint_problem.has_solution = False
+        self.gradient_problem.has_solution = False
+
     def gradient_test(self, h=None, rng=None) -> float:
         from cashocs_b200 import verification
 

@@ -76,4 +76,6 @@ class ControlGradientProblem(pde_problem.PDEProblem):
                 self.mesh.dist.halo_exchange(self.gradient.vector, 1)
             self.has_solution = True
             self.gradient_norm_squared = self.scalar_product(self.gradient.vector, self.gradient.vector)
+            if self.post_callback is not None:
+                self.post_callback()
         return [self.gradient]

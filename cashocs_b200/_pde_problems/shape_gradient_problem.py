@@ -45,4 +45,6 @@ class ShapeGradientProblem(pde_problem.PDEProblem):
                 self.mesh.dist.halo_exchange(g, self.mesh.dim)
             self.has_solution = True
             self.gradient_norm_squared = fh.scalar_product(g, g)
+            if self.post_callback is not None:
+                self.post_callback()
         return [self.gradient]

@@ -117,6 +117,8 @@ class StateProblem(pde_problem.PDEProblem):
 
     def solve(self):
         if not self.has_solution:
+            if self.pre_callback is not None:
+                self.pre_callback()
             self._generate_checkpoint()
             for i in range(len(self.states)):
                 A, b = self.assemble(i)

@@ -556,3 +556,22 @@ def test_control_bcs_like_the_reference():
     b = om.boundary_vertices((1, 2, 3, 4))
     assert np.all(u.vector.cpu().numpy()[b] == value)
     assert abs(ocp.solver.objective_value - hist[-1][1]) <= 1e-6 * abs(hist[-1][1])
+
+
+def test_pre_and_post_callbacks():
+    """tests/test_optimal_control.py::test_callbacks of the reference: the pre callback runs before every solve of the
+    state system, the post callback after every gradient computation (optimization_problem.py:600-640)."""
+    dm, _ = circle()
+    sop = make_sop(dm, sop_config())
+    calls = {"pre": 0, "post": 0}
+    sop.inject_pre_post_callback(lambda: calls.__setitem__("pre", calls["pre"] + 1),
+                                 lambda: calls.__setitem__("post", calls["post"] + 1))
+    sop.compute_shape_gradient()
+    assert calls == {"pre": 1, "post": 1}
+    sop.compute_shape_gradient()  # cached: nothing is solved again
+    assert calls == {"pre": 1, "post": 1}
+    calls.update(pre=0, post=0)
+    solves_before = sop.state_problem.number_of_solves
+    sop.solve(algorithm="bfgs", rtol=1e-2, atol=0.0, max_iter=7)
+    assert calls["pre"] == sop.state_problem.number_of_solves - solves_before > 0
+    assert calls["post"] == sop.solver.iteration + 1  # one gradient per iterate, including the converged one
