@@ -55,7 +55,10 @@ class ShapeRegularization:
         self.current_surface = 1.0
         self.target_surface = config.getfloat("Regularization", "target_surface")
         if self.mu_surface > 0.0:
-            self._facets, self._v2f_ptr, self._v2f_idx = mesh.boundary_facet_table()
+            self._facets, self._v2f_ptr, self._v2f_idx, counted = mesh.boundary_facet_table()
+            # facets this rank adds to the global measure (all of them on one GPU; on a partition every boundary
+            # facet is counted by exactly one rank)
+            self._measure_facets = self._facets if bool(counted.all()) else self._facets[counted].contiguous()
             nf = int(self._facets.shape[0])
             self._facet_vec = torch.zeros(max(nf * d * d, 1), **f64)
             self._surface_vector = torch.zeros(mesh.n_owned_vertices * d, **f64)
@@ -94,10 +97,13 @@ class ShapeRegularization:
         mesh = self.mesh
         scratch = mesh.reduce_scratch()
         _lib.check(
-            _lib.load().cb_boundary_measure(_lib.stream_ptr(), mesh.dim, int(self._facets.shape[0]), _lib.ptr(mesh.coords),
-                                            _lib.ptr(self._facets), _lib.ptr(self._out), _lib.ptr(scratch), scratch.numel()),
+            _lib.load().cb_boundary_measure(_lib.stream_ptr(), mesh.dim, int(self._measure_facets.shape[0]),
+                                            _lib.ptr(mesh.coords), _lib.ptr(self._measure_facets), _lib.ptr(self._out),
+                                            _lib.ptr(scratch), scratch.numel()),
             "cb_boundary_measure",
         )
+        if mesh.dist is not None:
+            mesh.dist.allreduce(self._out, "sum")
         return float(self._out.item())
 
     def update_geometric_quantities(self) -> None:

@@ -78,29 +78,45 @@ class Mesh:
             self._p2_space = function_space.P2Space(self)
         return self._p2_space
 
-    def boundary_facet_table(self):
-        """All boundary facets of the mesh (the ``ds`` measure): ``(facets [nf, d] int32, v2f_ptr, v2f_idx)`` with
-        the vertex -> facet adjacency over the owned vertices, built once from the topology -- a facet lies on the
-        boundary iff it belongs to exactly one cell."""
-        if getattr(self, "_facet_table", None) is not None:
-            return self._facet_table
-        if self.dist is not None:
-            raise _exceptions.InputError("cashocs_b200.Mesh.boundary_facet_table", "mesh",
-                                         "facet integrals are implemented for unpartitioned meshes")
+    def boundary_facets_local(self):
+        """Boundary facets seen by this rank, from the topology alone: ``(facets [nf, d] int64, counted [nf] bool)``.
+
+        A facet lies on the boundary iff it belongs to exactly one cell.  On a partition (all cells touching an owned
+        vertex are local) that is decidable for every facet with at least one owned vertex -- both its cells touch
+        that vertex -- and those are exactly the facets whose measure gradients reach owned vertices.  ``counted``
+        marks the facets this rank adds to the global boundary measure: the owner of the facet's vertex with the
+        lowest global id counts it, so every boundary facet is counted exactly once."""
         d = self.dim
         cells = self.cells.long()
         keep = [[j for j in range(d + 1) if j != omit] for omit in range(d + 1)]
-        sub = torch.cat([cells[:, k] for k in keep], dim=0)  # ascending per facet because cells are
+        sub = torch.sort(torch.cat([cells[:, k] for k in keep], dim=0), dim=1).values  # a no-op for ascending cells
         uniq, counts = torch.unique(sub, dim=0, return_counts=True)
-        facets = uniq[counts == 1].to(torch.int32).contiguous()
+        facets = uniq[counts == 1]
+        if self.dist is None:
+            return facets, torch.ones(facets.shape[0], dtype=torch.bool, device=facets.device)
+        n_own = self.n_owned_vertices
+        facets = facets[(facets < n_own).any(dim=1)]
+        gid = torch.as_tensor(self.global_vertex_ids, device=facets.device).long()
+        first = torch.gather(facets, 1, torch.argmin(gid[facets], dim=1, keepdim=True)).squeeze(1)
+        return facets, first < n_own
+
+    def boundary_facet_table(self):
+        """The ``ds`` measure on the device: ``(facets [nf, d] int32, v2f_ptr, v2f_idx, counted)`` -- the boundary facets
+        of :meth:`boundary_facets_local`, their vertex -> facet adjacency (rows of the owned vertices are used) and the
+        facets this rank counts in the global measure (all of them on one GPU).  Built once per topology."""
+        if getattr(self, "_facet_table", None) is not None:
+            return self._facet_table
+        d = self.dim
+        facets64, counted = self.boundary_facets_local()
+        facets = facets64.to(torch.int32).contiguous()
         nf = int(facets.shape[0])
-        n = self.n_owned_vertices
+        n = self.num_vertices
         ptr = torch.zeros(n + 1, dtype=torch.int64, device=self.device)
         idx = torch.zeros(max(nf * d, 1), dtype=torch.int32, device=self.device)
         if nf:
             _lib.check(_lib.load().cb_v2c_build(_lib.stream_ptr(), n, nf, d, _lib.ptr(facets), _lib.ptr(ptr), _lib.ptr(idx)),
                        "cb_v2c_build")
-        self._facet_table = (facets, ptr, idx)
+        self._facet_table = (facets, ptr, idx, counted)
         return self._facet_table
 
     @property

@@ -343,3 +343,63 @@ def test_mesh_export_and_output_world2(tmp_path):
     results = mgr.dict()
     mp.spawn(_io_worker, args=(world, port, str(tmp_path), results), nprocs=world, join=True)
     assert dict(results) == {0: "ok", 1: "ok"}, dict(results)
+
+
+# ----------------------------------------------------------------------------- boundary facets on a partition
+def _facet_worker(rank, world, port, results):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import cashocs_b200 as cb
+        from cashocs_b200 import distributed
+        from oracle import meshes, pipeline
+
+        dist = distributed.DistContext(rank, world, transport="torch")
+        for dim in (2, 3):
+            if dim == 3:
+                om = meshes.regular_mesh(4, 1.0, 1.0, 1.0)
+                lm = distributed.distributed_regular_mesh(4, dist, device="cpu")
+                markers = (1, 2, 3, 4, 5, 6)
+            else:
+                om = meshes.regular_mesh(7)
+                g = cb.regular_mesh(7, device="cpu")
+                off = distributed.vertex_offsets(g.num_vertices, world)
+                lm = distributed.partition_mesh(g.coords, g.cells, {k: g.boundary_vertices([k]) for k in g.boundary_markers}, off, dist)
+                markers = (1, 2, 3, 4)
+            ref = pipeline.PoissonShapeProblem(om, bc_markers=markers, c_state=0.0,
+                                               config=pipeline.ShapeConfig(shape_bdry_def=markers)).boundary_facets()
+            want = {tuple(f) for f in ref.tolist()}
+            gid = lm.global_vertex_ids.numpy()
+            facets, counted = lm.boundary_facets_local()
+            glob = np.sort(gid[facets.numpy()], axis=1)
+            mine = {tuple(f) for f in glob.tolist()}
+            lo, hi = int(lm.global_offsets[rank]), int(lm.global_offsets[rank + 1])
+            # exactly the true boundary facets that touch an owned vertex
+            assert mine == {f for f in want if any(lo <= v < hi for v in f)}
+            # every boundary facet is counted by exactly one rank: the owner of its lowest vertex
+            cnt = {tuple(f) for f in glob[counted.numpy()].tolist()}
+            assert cnt == {f for f in want if lo <= min(f) < hi}
+            total = torch.tensor([float(len(cnt))], dtype=torch.float64)
+            dist.allreduce(total, "sum")
+            assert int(total.item()) == len(want)
+        results[rank] = "ok"
+    except Exception as exc:  # pragma: no cover
+        import traceback
+
+        results[rank] = traceback.format_exc() + str(exc)
+    finally:
+        td.destroy_process_group()
+
+
+def test_boundary_facets_world2():
+    """``Mesh.boundary_facets_local`` on a 2-rank partition (2-D ragged and 3-D slabs): the facets with exactly one
+    local cell and an owned vertex are the true boundary facets touching this rank; the 'counted' subsets partition
+    the global boundary."""
+    world = 2
+    port = 37500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_facet_worker, args=(world, port, results), nprocs=world, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}, dict(results)
