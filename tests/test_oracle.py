@@ -353,6 +353,14 @@ def test_oracle_multigrid_preconditioner():
         assert np.linalg.norm(P @ coef - rot) <= 5e-2 * np.linalg.norm(rot)
     assert its[14]["gradient"] <= its[8]["gradient"] + 8 and its[14]["gradient"] <= 40
     assert its[14]["state"] <= 35
+    # 2-D: two translations and one rotation per aggregate
+    load = lambda: meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))  # noqa: E731
+    cfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02)
+    g_direct = pipeline.PoissonShapeProblem(load(), config=cfg).compute_shape_gradient()
+    ksp = {"ksp_type": "cg", "pc_type": "hypre", "ksp_rtol": 1e-12, "ksp_atol": 1e-30}
+    prob = pipeline.PoissonShapeProblem(load(), config=cfg, state_ksp=ksp, adjoint_ksp=ksp, gradient_ksp=ksp)
+    g_amg = prob.compute_shape_gradient()
+    assert np.max(np.abs(g_amg - g_direct)) <= 1e-9 * np.max(np.abs(g_direct)) and prob.its["gradient"] <= 40
 
 
 def test_volume_and_barycenter_regularization_reference_scenarios():
