@@ -196,6 +196,10 @@ class LineSearch:
         self.global_deformation = (self.problem_type == "shape" and cfg.getboolean("ShapeGradient", "global_deformation")
                                    and hasattr(problem, "global_deformation_function"))
         self.log: list[tuple[str, float]] = []
+        # Armijo margins J_new - (J + eps * decrease), one per Armijo decision of `log`: a decision whose margin is at
+        # round-off level (|margin| <~ 1e-10 |J|) is not reproducible across summation orders -- parity tests compare
+        # decision sequences up to the first such trial
+        self.margins: list[float] = []
 
     def initialize_stepsize(self, solver, search_direction: torch.Tensor, has_curvature_info: bool) -> None:
         """``line_search.py:152-214``."""
@@ -279,6 +283,7 @@ class ArmijoLineSearch(LineSearch):
             objective_step = self._compute_objective_at_new_iterate(current_function_value)
             self._trial_done(objective_step)
             decrease_measure = self._compute_decrease_measure(search_direction)
+            self.margins.append(objective_step - (current_function_value + self.epsilon_armijo * decrease_measure))
             if objective_step < current_function_value + self.epsilon_armijo * decrease_measure:
                 self.log.append(("armijo_accept", self.stepsize))
                 if self.ova.requires_remeshing():

@@ -493,6 +493,9 @@ def armijo_step(prob: PoissonShapeProblem, direction, stepsize, J_cur, iteration
             decrease = prob.scalar_product(prob.gradient, prob.u - prob.u_temp)
         else:
             decrease = dm * stepsize
+        if not hasattr(prob, "armijo_margins"):
+            prob.armijo_margins = []
+        prob.armijo_margins.append(J_new - (J_cur + c.epsilon_armijo * decrease))
         if J_new < J_cur + c.epsilon_armijo * decrease:
             log.append(("armijo_accept", stepsize))
             # armijo_line_search.py:169-184: a step that leaves the mesh below tol_upper asks for remeshing (a no-op
@@ -554,8 +557,11 @@ def line_search(prob, direction, stepsize, J_cur, iteration=0, has_curvature_inf
         prob.update_scalar_product()
         return step, c.initial_stepsize
     polynomial = c.line_search == "polynomial"
-    step, _, _ = armijo_step(prob, direction, stepsize, J_cur, iteration=iteration, has_curvature_info=has_curvature_info,
-                             newton_like=newton_like, polynomial=polynomial)
+    step, _, log = armijo_step(prob, direction, stepsize, J_cur, iteration=iteration, has_curvature_info=has_curvature_info,
+                               newton_like=newton_like, polynomial=polynomial)
+    if not hasattr(prob, "decision_log"):
+        prob.decision_log = []
+    prob.decision_log.extend(log)  # every decision of the run, in order (what the device must reproduce)
     if step is None:
         return None, stepsize
     if has_curvature_info:

@@ -53,8 +53,9 @@ def test_rbm_kernels_match_the_numpy_restatement():
         Pd = torch.zeros(npz * 9, dtype=torch.float64, device="cuda")
         _lib.check(lib.cb_amg_rbm_spgemm_terms(s, 0, npz, _lib.ptr(g["at_seg"]), _lib.ptr(g["at_sl"]), _lib.ptr(g["at_sr"]),
                                                _lib.ptr(d_val), _lib.ptr(Td), _lib.ptr(Pd)), "A*T")
+        dinv_d = dev(lv["dinv"])
         _lib.check(lib.cb_amg_rbm_prolongator_finish(s, L.n, _lib.ptr(g["p_rowptr"]), nt, _lib.ptr(g["t2p"]), _lib.ptr(Td),
-                                                     _lib.ptr(dev(lv["dinv"])), float(lv["omega"]), _lib.ptr(Pd)), "finish")
+                                                     _lib.ptr(dinv_d), float(lv["omega"]), _lib.ptr(Pd)), "finish")
         scale_p = np.max(np.abs(lv["P"]))
         assert np.max(np.abs(Pd.cpu().numpy().reshape(-1, 3, 3) - lv["P"])) <= 1e-13 * scale_p
         nap = int(L.ap_col.numel())
@@ -74,11 +75,12 @@ def test_rbm_kernels_match_the_numpy_restatement():
         rng = np.random.RandomState(3)
         b, t, xc, x = rng.rand(3 * L.n), rng.rand(3 * L.n), rng.rand(6 * L.nc), rng.rand(3 * L.n)
         bcd = torch.zeros(6 * L.nc, dtype=torch.float64, device="cuda")
+        bd, td, xcd = dev(b), dev(t), dev(xc)  # named: a temporary's block would be recycled for the next argument
         _lib.check(lib.cb_amg_rbm_restrict(s, 2 * L.nc, _lib.ptr(g["pt_rowptr"]), _lib.ptr(g["pt_col"]), _lib.ptr(Ptd),
-                                           _lib.ptr(dev(b)), _lib.ptr(dev(t)), _lib.ptr(bcd)), "restrict")
+                                           _lib.ptr(bd), _lib.ptr(td), _lib.ptr(bcd)), "restrict")
         assert np.allclose(bcd.cpu().numpy(), Ps.T @ (b - t), rtol=1e-12, atol=1e-13)
         xd = dev(x)
-        _lib.check(lib.cb_amg_rbm_prolong(s, L.n, _lib.ptr(g["p_rowptr"]), _lib.ptr(g["p_col"]), _lib.ptr(Pd), _lib.ptr(dev(xc)),
+        _lib.check(lib.cb_amg_rbm_prolong(s, L.n, _lib.ptr(g["p_rowptr"]), _lib.ptr(g["p_col"]), _lib.ptr(Pd), _lib.ptr(xcd),
                                           _lib.ptr(xd)), "prolong")
         assert np.allclose(xd.cpu().numpy(), x + Ps @ xc, rtol=1e-12, atol=1e-13)
         val = lv["Ac"]
