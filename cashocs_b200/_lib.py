@@ -130,7 +130,7 @@ class cb_amg(C.Structure):
         ("nlevels", C.c_int32),
         ("smooth_degree", C.c_int32),
         ("coarse_degree", C.c_int32),
-        ("pad", C.c_int32),
+        ("p_block", C.c_int32),
         ("smooth_ratio", C.c_double),
         ("coarse_ratio", C.c_double),
         ("levels", C.c_void_p),

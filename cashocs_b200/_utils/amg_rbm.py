@@ -270,3 +270,46 @@ class RBMHierarchy:
             p.mul_(rz_new / rz).add_(z)
             rz = rz_new
         return x, max_it
+
+    # ------------------------------------------------------------------ the C struct for the fused V-cycle
+    def struct(self):
+        """``cb_amg`` with ``p_block = 1`` for ``cb_ksp_opts.amg``: the fused V-cycle of ``cb_ksp_solve`` then restricts
+        and prolongates with the block kernels and runs everything else (smoothers, A*P post-smoothing, dense
+        coarsest solve) unchanged."""
+        from cashocs_b200._utils import linalg
+
+        C, _lib = self._C, self._lib
+        f64 = dict(dtype=torch.float64, device=self.device)
+        arr = (_lib.cb_amg_level * len(self.levels))()
+        self._keep = []
+        for li, (L, D) in enumerate(zip(self.levels, self.data)):
+            e = arr[li]
+            m = self._mat(L, D.cur_val)
+            m.row_split = linalg.row_split_hint(L.nnzb, L.n)
+            e.A = m
+            e.dinv = D.dinv.data_ptr()
+            e.lmax = D.lmax
+            e.nc = 0 if L.last else 2 * L.nc
+            bufs = [torch.zeros(L.n * 3, **f64) for _ in range(4)]  # x, b, t, d
+            self._keep.append(bufs)
+            e.x = bufs[0].data_ptr() if li > 0 else None
+            e.b = bufs[1].data_ptr() if li > 0 else None
+            e.t, e.d = bufs[2].data_ptr(), bufs[3].data_ptr()
+            if not L.last:
+                e.p_rowptr, e.p_col, e.p_val = L.p_rowptr.data_ptr(), L.p_col.data_ptr(), D.p_val.data_ptr()
+                e.pt_rowptr, e.pt_col, e.pt_val = L.pt_rowptr.data_ptr(), L.pt_col.data_ptr(), D.pt_val.data_ptr()
+                ap = _lib.cb_mat()
+                ap.nrows, ap.ncols, ap.bs = L.n, 2 * L.nc, 3
+                ap.row_split = linalg.row_split_hint(L.ap_col.numel(), L.n)
+                ap.rowptr, ap.col, ap.val = L.ap_rowptr.data_ptr(), L.ap_col.data_ptr(), D.ap_val.data_ptr()
+                e.AP = ap
+        h = _lib.cb_amg()
+        h.nlevels = len(self.levels)
+        h.smooth_degree, h.coarse_degree = 1, 16
+        h.smooth_ratio, h.coarse_ratio = self.smooth_ratio, 40.0
+        h.p_block = 1
+        h.levels = C.cast(arr, C.c_void_p)
+        self._coarse_inv_flat = self.coarse_inv.contiguous().view(-1) if self.coarse_inv is not None else None
+        h.coarse_inv = self._coarse_inv_flat.data_ptr() if self._coarse_inv_flat is not None else None
+        self._level_array, self._struct = arr, h
+        return h

@@ -107,7 +107,7 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None, distr
              "pc_chebyshev_degree", "pc_chebyshev_ratio", "ksp_check_every", "ksp_ksp_type",
              "ksp_ksp_max_it", "ksp_pc_type", "ksp_profile_every", "ksp_use_graph", "pc_amg_smooth_degree",
              "pc_amg_coarse_degree", "pc_amg_smooth_ratio", "pc_amg_coarse_ratio", "pc_amg_min_coarse",
-             "pc_amg_rigid_body_correction",
+             "pc_amg_rigid_body_correction", "pc_amg_nullspace",
              "pc_gamg_type", "pc_gamg_agg_nsmooths"} | _IGNORED_KEYS
     unknown = set(opts) - known
     if unknown:
@@ -450,6 +450,22 @@ class LinearSolver:
             h.rbm = None
         return h
 
+    @classmethod
+    def rbm_hierarchy(cls, A: "Matrix"):
+        from cashocs_b200._utils import amg_rbm
+
+        key = (id(A.mesh), "rbm")
+        h = cls._amg_cache.get(key)
+        if h is None or h.levels[0].rowptr is not A.rowptr:
+            h = amg_rbm.RBMHierarchy(A)
+            h.version = None
+            cls._amg_cache[key] = h
+        if h.version != (id(A), A.version):
+            h.A = A
+            h.numeric(A.mesh.coords)
+            h.version = (id(A), A.version)
+        return h
+
     @staticmethod
     def rigid_body_correction(A: "Matrix", h):
         """Data of the coarse correction ``Z (Z^T A Z)^-1 Z^T`` with the global rigid-body modes (see
@@ -519,13 +535,23 @@ class LinearSolver:
         opts = parse_ksp_options(ksp_options, rtol, atol, distributed=A.mesh.dist is not None)
         lib = _lib.load()
         hierarchy = None
-        if opts.pc_type == _PC_TYPES["amg"]:
+        nullspace = str((ksp_options or {}).get("pc_amg_nullspace", "translations")).casefold()
+        if opts.pc_type == _PC_TYPES["amg"] and nullspace == "rigid_body":
+            # smoothed aggregation with the six rigid-body modes inside the hierarchy (block prolongator, p_block = 1)
+            if A.bs != 3 or A.mesh.dist is not None:
+                raise _exceptions.InputError("cashocs_b200.LinearSolver", "pc_amg_nullspace",
+                                             "rigid_body needs a 3 x 3 block operator on an unpartitioned mesh")
+            hierarchy = self.rbm_hierarchy(A)
+            hstruct = hierarchy.struct()
+            opts.amg = C.cast(C.pointer(hstruct), C.c_void_p)
+        elif opts.pc_type == _PC_TYPES["amg"]:
             hierarchy = self.amg_hierarchy(A, ksp_options or {})
             hstruct = hierarchy.struct()
             opts.amg = C.cast(C.pointer(hstruct), C.c_void_p)
             # rigid-body coarse correction: default for vertex-blocked vector operators (the elasticity Riesz
             # problem) on one GPU, where it is validated; an explicit option overrides (True also on partitions)
-            applicable = A.bs >= 2 and A.bs == A.mesh.dim and A.nrows == A.mesh.n_owned_vertices
+            applicable = (A.bs >= 2 and A.bs == A.mesh.dim and A.nrows == A.mesh.n_owned_vertices
+                          and nullspace != "rigid_body")
             wanted = (ksp_options or {}).get("pc_amg_rigid_body_correction", None)
             use_rbm = applicable and (A.mesh.dist is None if wanted is None else _truthy(wanted))
             if use_rbm:

@@ -239,8 +239,15 @@ k_prolong(int64_t n, const int64_t* __restrict__ p_rowptr, const int32_t* __rest
   }
 }
 
+// block-prolongator variants (csrc/amg_rbm.cu)
+int rbm_restrict_launch(cudaStream_t s, int64_t ncn, const int64_t* pt_rowptr, const int32_t* pt_col, const double* pt_val,
+                        const double* b, const double* t, double* bc, const int* done);
+int rbm_prolong_launch(cudaStream_t s, int64_t n, const int64_t* p_rowptr, const int32_t* p_col, const double* p_val,
+                       const double* xc, double* x, const int* done);
+
 int amg_restrict(cudaStream_t s, int bs, const cb_amg_level* L, const double* b, const double* t, double* bc,
-                 const int* done) {
+                 const int* done, int p_block) {
+  if (p_block) return rbm_restrict_launch(s, L->nc, L->pt_rowptr, L->pt_col, L->pt_val, b, t, bc, done);
   const int grid = grid_for(L->nc * 32, 256, 8);
   if (bs == 1) k_restrict<1><<<grid, 256, 0, s>>>(L->nc, L->pt_rowptr, L->pt_col, L->pt_val, b, t, bc, done);
   else if (bs == 2) k_restrict<2><<<grid, 256, 0, s>>>(L->nc, L->pt_rowptr, L->pt_col, L->pt_val, b, t, bc, done);
@@ -249,8 +256,9 @@ int amg_restrict(cudaStream_t s, int bs, const cb_amg_level* L, const double* b,
   return CB_OK;
 }
 
-int amg_prolong(cudaStream_t s, int bs, const cb_amg_level* L, const double* xc, double* x, const int* done) {
+int amg_prolong(cudaStream_t s, int bs, const cb_amg_level* L, const double* xc, double* x, const int* done, int p_block) {
   const int64_t n = L->A.nrows;
+  if (p_block) return rbm_prolong_launch(s, n, L->p_rowptr, L->p_col, L->p_val, xc, x, done);
   const int grid = grid_for(n * bs, 256, 8);
   if (bs == 1) k_prolong<1><<<grid, 256, 0, s>>>(n, L->p_rowptr, L->p_col, L->p_val, xc, x, done);
   else if (bs == 2) k_prolong<2><<<grid, 256, 0, s>>>(n, L->p_rowptr, L->p_col, L->p_val, xc, x, done);

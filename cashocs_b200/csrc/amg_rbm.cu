@@ -180,6 +180,20 @@ k_rbm_prolong(int64_t n, const int64_t* __restrict__ p_rowptr, const int32_t* __
   }
 }
 
+int rbm_restrict_launch(cudaStream_t s, int64_t ncn, const int64_t* pt_rowptr, const int32_t* pt_col, const double* pt_val,
+                        const double* b, const double* t, double* bc, const int* done) {
+  k_rbm_restrict<<<grid_for(ncn * 32, 256, 8), 256, 0, s>>>(ncn, pt_rowptr, pt_col, pt_val, b, t, bc, done);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+int rbm_prolong_launch(cudaStream_t s, int64_t n, const int64_t* p_rowptr, const int32_t* p_col, const double* p_val,
+                       const double* xc, double* x, const int* done) {
+  k_rbm_prolong<<<grid_for(n * 3, 256, 8), 256, 0, s>>>(n, p_rowptr, p_col, p_val, xc, x, done);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
 }  // namespace cb
 
 using namespace cb;
@@ -238,15 +252,11 @@ extern "C" int cb_amg_rbm_transpose_blocks(void* stream, int64_t nnz, const int6
 extern "C" int cb_amg_rbm_restrict(void* stream, int64_t ncn, const int64_t* pt_rowptr, const int32_t* pt_col,
                                    const double* pt_val, const double* b, const double* t, double* bc) {
   CB_REQUIRE(pt_rowptr && pt_col && pt_val && b && t && bc, "cb_amg_rbm_restrict: missing argument");
-  k_rbm_restrict<<<grid_for(ncn * 32, 256, 8), 256, 0, as_stream(stream)>>>(ncn, pt_rowptr, pt_col, pt_val, b, t, bc, nullptr);
-  CB_LAUNCH_CHECK();
-  return CB_OK;
+  return rbm_restrict_launch(as_stream(stream), ncn, pt_rowptr, pt_col, pt_val, b, t, bc, nullptr);
 }
 
 extern "C" int cb_amg_rbm_prolong(void* stream, int64_t n, const int64_t* p_rowptr, const int32_t* p_col,
                                   const double* p_val, const double* xc, double* x) {
   CB_REQUIRE(p_rowptr && p_col && p_val && xc && x, "cb_amg_rbm_prolong: missing argument");
-  k_rbm_prolong<<<grid_for(n * 3, 256, 8), 256, 0, as_stream(stream)>>>(n, p_rowptr, p_col, p_val, xc, x, nullptr);
-  CB_LAUNCH_CHECK();
-  return CB_OK;
+  return rbm_prolong_launch(as_stream(stream), n, p_rowptr, p_col, p_val, xc, x, nullptr);
 }

@@ -25,8 +25,8 @@ namespace cb {
 int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
                   double* result, double* scratch, const int* done = nullptr);
 int amg_restrict(cudaStream_t s, int bs, const cb_amg_level* L, const double* b, const double* t, double* bc,
-                 const int* done);
-int amg_prolong(cudaStream_t s, int bs, const cb_amg_level* L, const double* xc, double* x, const int* done);
+                 const int* done, int p_block);
+int amg_prolong(cudaStream_t s, int bs, const cb_amg_level* L, const double* xc, double* x, const int* done, int p_block);
 int amg_dense_apply(cudaStream_t s, int n, const double* inv, const double* b, double* x, const int* done);
 int dist_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs, double* sendbuf);
 int dist_allreduce_sum(cudaStream_t s, cb_dist* d, double* buf, int n);
@@ -791,10 +791,10 @@ struct Solver {
         // rows of the restricted residual, one all-reduce assembles the global vector everywhere
         const size_t len = sizeof(double) * (size_t)(nxt.A.nrows * bs);
         CB_CUDA_CHECK(cudaMemsetAsync(nxt.b, 0, len, s));
-        if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.b + nxt.rep_off * bs, &st->done)) return e;
+        if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.b + nxt.rep_off * bs, &st->done, h->p_block)) return e;
         if (int e = dist_allreduce_sum(s, nxt.rep_dist, nxt.b, (int)(nxt.A.nrows * bs))) return e;
       } else {
-        if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.b, &st->done)) return e;
+        if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.b, &st->done, h->p_block)) return e;
       }
     }
     for (int l = L - 2; l >= 0; --l) {
@@ -803,7 +803,7 @@ struct Solver {
       const double* bl = (l == 0) ? r : lev.b;
       double* xl = (l == 0) ? z : lev.x;
       const double* xc = nxt.rep_dist ? nxt.x + nxt.rep_off * bs : nxt.x;
-      if (int e = amg_prolong(s, bs, &lev, xc, xl, &st->done)) return e;
+      if (int e = amg_prolong(s, bs, &lev, xc, xl, &st->done, h->p_block)) return e;
       if (lev.AP.val) {
         // first post-smoothing step through A P instead of A (see k_spmv_post): needs the coarse
         // correction in this rank's coarse numbering (owned + ghost coarse nodes)

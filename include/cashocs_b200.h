@@ -290,7 +290,8 @@ typedef struct {
   int32_t nlevels;
   int32_t smooth_degree;    /* Chebyshev degree of the pre / post smoother */
   int32_t coarse_degree;    /* Chebyshev degree of the coarsest-level solve (coarse_inv == NULL) */
-  int32_t pad;
+  int32_t p_block;          /* 1: prolongator entries are 3 x 3 blocks (rigid-body hierarchy, cb_amg_rbm_*): p_val holds
+                             * the blocks of P, pt_val the TRANSPOSED blocks in P^T's entry order; 0: scalar P (x) I */
   double smooth_ratio;      /* smoother interval [lmax/ratio, lmax] */
   double coarse_ratio;
   const cb_amg_level* levels; /* host array */

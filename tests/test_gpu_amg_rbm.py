@@ -123,3 +123,30 @@ def test_rbm_hierarchy_end_to_end():
                                                                     "ksp_atol": 1e-30,
                                                                     "pc_amg_rigid_body_correction": False})
     assert its <= 0.6 * base.its, (its, base.its)
+
+
+def test_rbm_hierarchy_inside_cb_ksp_solve():
+    """``pc_amg_nullspace = rigid_body``: the fused V-cycle of ``cb_ksp_solve`` with the block prolongator (``p_block``):
+    direct-solve accuracy, about a third of the iterations of the scalar-prolongator hierarchy, eager loop and graph
+    replay bitwise identical."""
+    import scipy.sparse.linalg as spla
+
+    import cashocs_b200 as cb
+    from cashocs_b200._utils import linalg
+
+    dm = cb.regular_mesh(14, 1.0, 1.0, 1.0)
+    mu = torch.full((dm.num_vertices,), 0.35714285714285715, dtype=torch.float64, device="cuda")
+    E = linalg.assemble_elasticity_matrix(dm, mu, 1.428571428571429, 0.2)
+    rhs = torch.from_numpy(np.random.RandomState(1).rand(3 * dm.num_vertices) - 0.5).cuda()
+    want = spla.spsolve(E.to_scipy().tocsc(), rhs.cpu().numpy())
+    base = {"ksp_type": "cg", "pc_type": "hypre", "ksp_rtol": 1e-11, "ksp_atol": 1e-30, "ksp_max_it": 2000}
+    out = {}
+    for graph in (-1, 0):
+        x = torch.zeros_like(rhs)
+        res = linalg.LinearSolver().solve(x, A=E, b=rhs, ksp_options=dict(base, pc_amg_nullspace="rigid_body", ksp_use_graph=graph))
+        assert np.max(np.abs(x.cpu().numpy() - want)) <= 1e-8 * np.max(np.abs(want))
+        out[graph] = (res.its, x.clone())
+    assert out[-1][0] == out[0][0] and torch.equal(out[-1][1], out[0][1])
+    x0 = torch.zeros_like(rhs)
+    ref_its = linalg.LinearSolver().solve(x0, A=E, b=rhs, ksp_options=dict(base, pc_amg_rigid_body_correction=False)).its
+    assert out[0][0] <= 0.6 * ref_its, (out[0][0], ref_its)
