@@ -35,6 +35,7 @@ UNIT = "evals/s"
 # `--pc jacobi` selects the one-level variant of SURVEY.md 8d
 KSP = {"ksp_type": "cg", "pc_type": "hypre", "pc_hypre_type": "boomeramg", "ksp_rtol": 1e-10, "ksp_atol": 1e-30,
        "ksp_max_it": 20000}
+GRADIENT_KSP_EXTRA: dict = {}  # options of the elasticity Riesz solve only (vertex-blocked 3 x 3 operator)
 SHAPE = dict(lambda_lame=1.428571428571429, damping_factor=0.2, mu=0.35714285714285715)
 ALL_MARKERS = [1, 2, 3, 4, 5, 6]
 
@@ -202,6 +203,7 @@ def build_problem(n: int, dist=None, state_degree: int = 1):
     cfg.set("ShapeGradient", "mu_def", repr(SHAPE["mu"]))
     u, p = cb.Function(mesh, degree=state_degree), cb.Function(mesh, degree=state_degree)
     gksp = dict(KSP)
+    gksp.update(GRADIENT_KSP_EXTRA)
     gksp["ksp_profile_every"] = 8
     sop = cb.ShapeOptimizationProblem(cb.PoissonForm(source=f), cb.create_dirichlet_bcs(0.0, ALL_MARKERS),
                                       cb.IntegralFunctional(c_state=1.0), u, p, config=cfg, ksp_options=dict(KSP),
@@ -245,8 +247,12 @@ def main() -> None:
     ap.add_argument("--rbm", default="auto", choices=["auto", "on", "off"],
                     help="rigid-body coarse correction in the elasticity AMG preconditioner (pc_amg_rigid_body_correction); "
                          "auto: on for 1 GPU (validated there), off on partitioned meshes")
+    ap.add_argument("--nullspace", default="auto", choices=["auto", "translations", "rigid_body"],
+                    help="near-null-space carried by the elasticity AMG hierarchy (pc_amg_nullspace)")
     args = ap.parse_args()
     KSP["pc_type"] = args.pc
+    if args.nullspace != "auto" and args.pc == "hypre":
+        GRADIENT_KSP_EXTRA["pc_amg_nullspace"] = args.nullspace
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
     use_rbm = args.pc == "hypre" and (args.rbm == "on" or (args.rbm == "auto" and world_env == 1))
     if args.pc == "hypre":

@@ -37,7 +37,9 @@ def main():
     ap.add_argument("--pc", default="hypre")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--rbm", type=int, default=0, help="1: rigid-body coarse correction in the elasticity solve")
+    ap.add_argument("--nullspace", default="translations")
     args = ap.parse_args()
+    bench.GRADIENT_KSP_EXTRA["pc_amg_nullspace"] = args.nullspace
     bench.KSP["pc_type"] = args.pc
     bench.KSP["pc_amg_rigid_body_correction"] = bool(args.rbm)
     sop = bench.build_problem(args.n)
@@ -55,7 +57,10 @@ def main():
             with timer("amg numeric scalar"):
                 linalg.LinearSolver.amg_hierarchy(A, {})
             with timer("amg numeric elasticity"):
-                hE = linalg.LinearSolver.amg_hierarchy(fh.scalar_product_matrix, {})
+                if args.nullspace == "rigid_body":
+                    hE = linalg.LinearSolver.rbm_hierarchy(fh.scalar_product_matrix)
+                else:
+                    hE = linalg.LinearSolver.amg_hierarchy(fh.scalar_product_matrix, {})
         with timer("state solve"):
             sop.state_problem.linear_solver.solve(sop.states[0].vector, A=A, b=b, ksp_options=sop.ksp_options[0])
         sop.state_problem.has_solution = True
@@ -76,7 +81,11 @@ def main():
         print(f"{k:50s} {v / args.reps:10.2f} ms")
     print("its", sop.state_problem.linear_solver.last_result.its, sop.adjoint_problem.iterations, res.its)
     if args.pc == "hypre":
-        print("levels", hE.sizes, "opc %.3f" % hE.operator_complexity, [L.nnzb for L in hE.levels], [round(D.lmax, 3) for D in hE.data])
+        sym = getattr(hE, "symbolic", hE)
+        print("levels", sym.sizes, "opc %.3f" % sym.operator_complexity, [L.nnzb for L in hE.levels], [round(D.lmax, 3) for D in hE.data])
+        for L in hE.levels:
+            if hasattr(L, "p_col") and L.p_col is not None and not getattr(L, "last", False):
+                print("  level n", L.n, "nnzb", L.nnzb, "P entries", int(L.p_col.numel()), "AP entries", int(L.ap_col.numel()))
 
 
 if __name__ == "__main__":
