@@ -105,77 +105,104 @@ class ClockSampler:
 _ORACLE_THREADS = 1
 
 
-def oracle_eval_seconds(n_sample: int, repeats: int = 1):
-    """Time one shape-gradient evaluation of the CPU oracle on an n_sample cube; returns (s, its)."""
+def workload_config(n: int, state_degree: int = 1) -> dict:
+    """The part of `config` that names the workload -- identical in the B200 arm and in the reference arm."""
+    return {"workload": workload_name(n, 1).rsplit(";", 1)[0] + (" [P2 state/adjoint]" if state_degree == 2 else ""),
+            "n": n, "tets": 6 * n**3, "vertices": (n + 1) ** 3, "state_degree": state_degree,
+            "ksp": "cg + pc_type hypre (algebraic multigrid), ksp_rtol 1e-10, ksp_atol 1e-30"}
+
+
+def make_oracle_problem(n_sample: int):
     from oracle import meshes, pipeline
 
     om = meshes.regular_mesh(n_sample, 1.0, 1.0, 1.0)
+    # the same evaluation as the B200 arm, intersection test included (tree-based candidate search, oracle/quality.py)
     cfg = pipeline.ShapeConfig(shape_bdry_def=tuple(ALL_MARKERS), lambda_lame=SHAPE["lambda_lame"],
                                damping_factor=SHAPE["damping_factor"], mu_def=SHAPE["mu"], mu_fix=SHAPE["mu"],
-                               test_for_intersections=False)
+                               test_for_intersections=True)
     # the reference's iterative default is cg + hypre/boomeramg (cashocs/_utils/linalg.py:44-52); hypre is not
     # installable here, the oracle's multigrid of the same class (oracle/amg.py, scipy) stands in for it, so the
     # CPU arm has mesh-independent iteration counts like the reference and like the device path
     ksp = {"ksp_type": "cg", "pc_type": "hypre", "ksp_rtol": 1e-10, "ksp_atol": 1e-30, "ksp_max_it": 20000}
-    prob = pipeline.PoissonShapeProblem(om, bc_markers=tuple(ALL_MARKERS), config=cfg, state_ksp=ksp, adjoint_ksp=ksp,
-                                        gradient_ksp=ksp)
-    best = float("inf")
+    return pipeline.PoissonShapeProblem(om, bc_markers=tuple(ALL_MARKERS), config=cfg, state_ksp=ksp, adjoint_ksp=ksp,
+                                        gradient_ksp=ksp), om.num_cells
+
+
+def oracle_eval_seconds(n_sample: int, prob=None):
+    """Time ONE shape-gradient evaluation of the CPU oracle on an n_sample cube; returns (s, its, cells, problem)."""
     global _ORACLE_THREADS
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        c0 = time.process_time()
-        prob.update_scalar_product()
-        g = prob.compute_shape_gradient()
-        h = 1.0 / n_sample
-        scale = 0.1 * h / max(float(np.max(np.abs(g))), 1e-300)
-        if prob.move_mesh(-scale * g):
-            prob.revert_transformation()
-        wall = time.perf_counter() - t0
-        if wall < best:
-            best = wall
-            # threads actually kept busy: CPU time of the process / wall time (BLAS threads count, idle cores do not)
-            _ORACLE_THREADS = max(1, int(round((time.process_time() - c0) / wall)))
-    return best, dict(prob.its), om.num_cells
+    if prob is None:
+        prob, _ = make_oracle_problem(n_sample)
+    t0 = time.perf_counter()
+    c0 = time.process_time()
+    prob.update_scalar_product()
+    g = prob.compute_shape_gradient()
+    h = 1.0 / n_sample
+    scale = 0.1 * h / max(float(np.max(np.abs(g))), 1e-300)
+    if prob.move_mesh(-scale * g):
+        prob.revert_transformation()
+    wall = time.perf_counter() - t0
+    # threads actually kept busy: CPU time of the process / wall time (BLAS threads count, idle cores do not)
+    _ORACLE_THREADS = max(1, int(round((time.process_time() - c0) / wall)))
+    return wall, dict(prob.its), prob.cells.shape[0], prob
 
 
-def cpu_baseline(n_full: int, n_sample: int = 36) -> dict:
-    secs, its, nc = oracle_eval_seconds(n_sample)
-    # work per evaluation ~ cells (multigrid-preconditioned: iteration counts do not grow with the mesh)
-    scale = 6.0 * n_full**3 / nc
-    return {
-        "value": 1.0 / (secs * scale), "unit": UNIT, "cores": _ORACLE_THREADS, "kind": "port",
-        "sample": (f"numpy/scipy oracle (CPU restatement, not FEniCS/PETSc), one evaluation on regular_mesh({n_sample},1,1,1) "
-                   f"= {nc} tets took {secs:.3f} s (its {its}; cg + smoothed-aggregation AMG standing in for hypre, "
-                   f"numpy/BLAS may use all {os.cpu_count()} host threads, the sparse kernels of scipy are single-threaded: "
-                   f"`cores` is CPU time / wall time of the sample); "
-                   f"extrapolated to n={n_full} linearly in the number of cells"),
-        "sample_seconds": secs,
-    }
+def sample_size_for(budget_s: float, n_full: int) -> tuple[int, float]:
+    """Largest sample cube whose evaluation fits `budget_s` seconds on this host, from a calibration evaluation at
+    n = 16 (the evaluation is multigrid-preconditioned: its time grows linearly in the number of cells)."""
+    secs, _, _, _ = oracle_eval_seconds(16)
+    per_cell = secs / (6 * 16**3)
+    n = int((budget_s / per_cell / 6.0) ** (1.0 / 3.0))
+    return max(16, min(n, n_full)), secs
+
+
+def sample_string(n_sample, nc, secs, its, n_full):
+    frac = nc / (6.0 * n_full**3)
+    return (f"numpy/scipy oracle (CPU restatement; FEniCS/PETSc cannot be installed here), MEASURED: one full evaluation "
+            f"(assembly, cg + smoothed-aggregation AMG standing in for hypre, Krylov its {its}, det test, move, intersection "
+            f"test, quality) on regular_mesh({n_sample},1,1,1) = {nc} tets took {secs:.3f} s; that sample is {frac:.4f} of the "
+            f"{6 * n_full**3}-tet workload, `value` = {frac:.4f} evaluations of the workload per {secs:.3f} s (EXTRAPOLATION: "
+            f"linear in the number of cells; numpy/BLAS may use all {os.cpu_count()} host threads, scipy's sparse kernels are "
+            f"single-threaded, `cores` = CPU time / wall time of the sample)")
+
+
+def cpu_baseline(n_full: int, budget_s: float = 20.0) -> dict:
+    n_sample, _ = sample_size_for(budget_s, n_full)
+    secs, its, nc, _ = oracle_eval_seconds(n_sample)
+    frac = nc / (6.0 * n_full**3)
+    return {"value": frac / secs, "unit": UNIT, "cores": _ORACLE_THREADS, "kind": "port",
+            "sample": sample_string(n_sample, nc, secs, its, n_full), "sample_n": n_sample, "sample_seconds": secs,
+            "sample_fraction_of_workload": frac}
 
 
 def run_reference_arm(args) -> None:
+    """The CPU arm: every step is ONE measured evaluation of the oracle on a bounded sample of the workload (a smaller
+    cube of the same mesh family, sized so that warm-up + steps end within a few minutes on this host);
+    `ms_per_step` is the measured time of such a step, `value` the workload throughput it implies."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = 36
+    total_budget = 300.0  # seconds for all warm-up + timed steps
+    n_sample, calib = sample_size_for(total_budget / (args.warmup + args.steps), args.n)
+    prob, nc = make_oracle_problem(n_sample)
     times = []
     its = {}
     for i in range(args.warmup + args.steps):
-        secs, its, nc = oracle_eval_seconds(n_sample)
+        secs, its, nc, prob = oracle_eval_seconds(n_sample, prob)
         if i >= args.warmup:
             times.append(secs)
-    scale = 6.0 * args.n**3 / nc
-    per_eval = float(np.mean(times)) * scale
-    value = 1.0 / per_eval
+    frac = nc / (6.0 * args.n**3)
+    step_s = float(np.mean(times))
+    value = frac / step_s
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per_eval * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.n, args.gpus), "n": args.n},
+        "config": workload_config(args.n, args.state_degree),
+        "sample": {"n": n_sample, "tets": nc, "fraction_of_workload": frac, "measured_seconds_per_step": step_s,
+                   "krylov_its_state_adjoint_elasticity": [its.get("state"), its.get("adjoint"), its.get("gradient")]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": _ORACLE_THREADS, "kind": "port",
-                         "sample": (f"oracle (numpy/scipy restatement; FEniCS/PETSc not installable) on regular_mesh({n_sample},1,1,1) "
-                                    f"= {nc} tets: {np.mean(times):.3f} s/eval (its {its}; cg + smoothed-aggregation AMG "
-                                    f"standing in for hypre), extrapolated linearly in the number of cells")},
+                         "sample": sample_string(n_sample, nc, step_s, its, args.n)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -246,7 +273,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rbm", default="auto", choices=["auto", "on", "off"],
                     help="rigid-body coarse correction in the elasticity AMG preconditioner (pc_amg_rigid_body_correction); "
-                         "auto: on for 1 GPU (validated there), off on partitioned meshes")
+                         "auto = on (the library default, also on partitioned meshes)")
     ap.add_argument("--nullspace", default="auto", choices=["auto", "translations", "rigid_body"],
                     help="near-null-space carried by the elasticity AMG hierarchy (pc_amg_nullspace)")
     args = ap.parse_args()
@@ -254,7 +281,7 @@ def main() -> None:
     if args.nullspace != "auto" and args.pc == "hypre":
         GRADIENT_KSP_EXTRA["pc_amg_nullspace"] = args.nullspace
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
-    use_rbm = args.pc == "hypre" and (args.rbm == "on" or (args.rbm == "auto" and world_env == 1))
+    use_rbm = args.pc == "hypre" and args.rbm != "off"
     if args.pc == "hypre":
         KSP["pc_amg_rigid_body_correction"] = use_rbm  # explicit either way (the library default is on for 1 GPU)
     if args.graph != 0:
@@ -382,19 +409,19 @@ def main() -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.n, args.gpus) + (" [P2 state/adjoint]" if args.state_degree == 2 else ""),
-                       "state_degree": args.state_degree, "state_dofs": int(sop.states[0].vector.numel()),
-                       "n": args.n, "tets": n_tets, "vertices": n_verts,
-                       "block_nnz": nnzb_total, "krylov_its_state_adjoint_elasticity": list(its[-1]),
-                       "ksp_options": {k: v for k, v in KSP.items()},
-                       "pc_on_device": (("smoothed-aggregation AMG" + (" + rigid-body coarse correction for the elasticity "
-                                                                       "system" if use_rbm else ""))
-                                        if args.pc == "hypre" else "jacobi"),
-                       "l2_policy": "inputs larger than L2 (elasticity matrix %.2f GB, L2 126 MB)" % (76e-9 * nnzb_rank),
-                       "parallelism": "1 GPU" if dist is None else (
-                           f"mesh partitioned into {world} vertex slabs, " +
-                           ("halo exchange + Krylov all-reduces one-sided over NVLink peer memory (NCCL for the AMG agglomeration)"
-                            if dist.p2p else "NCCL halo + allreduce"))},
+            "config": dict(workload_config(args.n, args.state_degree), **{
+                "state_dofs": int(sop.states[0].vector.numel()),
+                "block_nnz": nnzb_total, "krylov_its_state_adjoint_elasticity": list(its[-1]),
+                "ksp_options": {k: v for k, v in KSP.items()}, "gradient_ksp_extra": dict(GRADIENT_KSP_EXTRA),
+                "pc_on_device": (("smoothed-aggregation AMG (fp32 copy of the fine operator for the residual pass, "
+                                  "degree-2 smoothing on the coarse levels of vector operators)" +
+                                  (" + rigid-body coarse correction for the elasticity system" if use_rbm else ""))
+                                 if args.pc == "hypre" else "jacobi"),
+                "l2_policy": "inputs larger than L2 (elasticity matrix %.2f GB, L2 126 MB)" % (76e-9 * nnzb_rank),
+                "parallelism": "1 GPU" if dist is None else (
+                    f"mesh partitioned into {world} vertex slabs, " +
+                    ("halo exchange + Krylov all-reduces one-sided over NVLink peer memory (NCCL for the AMG agglomeration)"
+                     if dist.p2p else "NCCL halo + allreduce"))}),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(coords_host.numel() * 8),
                     "d2h_bytes_per_step": int(grad_host.numel() * 8), "ms_per_step": ms_e2e / args.steps},

@@ -96,6 +96,7 @@ class cb_mat(C.Structure):
         ("rowptr", C.c_void_p),
         ("col", C.c_void_p),
         ("val", C.c_void_p),
+        ("val32", C.c_void_p),
     ]
 
 
@@ -133,6 +134,8 @@ class cb_amg(C.Structure):
         ("p_block", C.c_int32),
         ("smooth_ratio", C.c_double),
         ("coarse_ratio", C.c_double),
+        ("level_smooth_degree", C.c_int32),
+        ("pad3", C.c_int32),
         ("levels", C.c_void_p),
         ("coarse_inv", C.c_void_p),
     ]
@@ -156,6 +159,8 @@ class cb_ksp_opts(C.Structure):
         ("rbm_coords", C.c_void_p),
         ("rbm_einv", C.c_void_p),
         ("rbm_work", C.c_void_p),
+        ("flexible", C.c_int32),
+        ("pad2", C.c_int32),
     ]
 
 
@@ -180,6 +185,7 @@ DBL = C.c_double
 SIGNATURES = {
     "cb_last_error": (C.c_char_p, []),
     "cb_version": (I32, []),
+    "cb_struct_size": (I64, [I32]),
     "cb_num_sms": (I32, []),
     "cb_launch_count": (C.c_longlong, []),
     "cb_v2c_build": (I32, [P, I64, I64, I32, P, P, P]),
@@ -199,10 +205,13 @@ SIGNATURES = {
                                              C.POINTER(cb_poly), I32, P, DBL, P, P]),
     "cb_p2_functional": (I32, [P, C.POINTER(cb_p2_view), DBL, P, DBL, P, P, P, I64]),
     "cb_spmv": (I32, [P, C.POINTER(cb_mat), P, P]),
+    "cb_spmv_f32": (I32, [P, C.POINTER(cb_mat), P, P]),
     "cb_scalar_product": (I32, [P, C.POINTER(cb_mat), P, P, P, P, I64]),
     "cb_dot": (I32, [P, I64, P, P, P, P, I64]),
     "cb_reduce_scratch_len": (I64, []),
     "cb_extract_diag_inv": (I32, [P, C.POINTER(cb_mat), P, P, P, I64]),
+    "cb_rbm_galerkin": (I32, [P, C.POINTER(cb_mat), P, P, P, P, P, P, P, I64]),
+    "cb_rbm_invert": (I32, [P, I32, P, P]),
     "cb_ksp_workspace_len": (I64, [I64, I64, C.POINTER(cb_ksp_opts)]),
     "cb_ksp_solve": (I32, [P, C.POINTER(cb_mat), P, P, C.POINTER(cb_ksp_opts), P, P, I64,
                            C.POINTER(cb_ksp_result), P, I64]),
@@ -216,6 +225,8 @@ SIGNATURES = {
     "cb_gradient_frobenius_max": (I32, [P, I32, I64, P, P, P, P, P, I64]),
     "cb_move_mesh": (I32, [P, I64, P, P, P, DBL]),
     "cb_functional": (I32, [P, I32, I64, P, P, DBL, P, DBL, P, P, P, I64]),
+    "cb_to_f32": (I32, [P, I64, P, P]),
+    "cb_power_step": (I32, [P, C.POINTER(cb_mat), P, DBL, P, P, P, P, I64, I32]),
     "cb_amg_rbm_aggregate_geometry": (I32, [P, I64, P, P, P, P, P, P, P]),
     "cb_amg_rbm_tentative": (I32, [P, I64, P, P, P, P, P, P, P, P]),
     "cb_amg_rbm_spgemm_terms": (I32, [P, I32, I64, P, P, P, P, P, P]),
@@ -258,6 +269,12 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    # a stale .so (built from an older header) would silently misread every struct: refuse it
+    mirrors = [cb_poly, cb_quad, cb_mat, cb_mesh_view, cb_ksp_opts, cb_amg_level, cb_amg, cb_ksp_result, cb_p2_view]
+    for which, mirror in enumerate(mirrors):
+        if lib.cb_struct_size(which) != C.sizeof(mirror):
+            raise ImportError(f"{LIB_PATH} is stale: sizeof({mirror.__name__}) is {lib.cb_struct_size(which)} in the library, "
+                              f"{C.sizeof(mirror)} in the binding -- rebuild with `python -m cashocs_b200.build -f`")
     _lib = lib
     return lib
 

@@ -347,17 +347,28 @@ class AMGHierarchy:
     """Values of the hierarchy for one block size; ``numeric(A)`` refreshes them for new matrix values."""
 
     def __init__(self, A, symbolic: AMGSymbolic | None = None, smooth_degree: int = 1, coarse_degree: int = 16,
-                 smooth_ratio: float = 10.0, coarse_ratio: float = 40.0) -> None:
+                 smooth_ratio: float = 10.0, coarse_ratio: float = 40.0, mixed: bool = True,
+                 level_smooth_degree: int = 0, mixed_mask=None) -> None:
         self.bs = bs = A.bs
+        # Mixed precision: the fine-level operator gets an fp32 copy of its values, which is what the residual pass
+        # of the V-cycle streams (cb_mat.val32; vectors, products and sums stay fp64 -- see csrc/spmv.cuh).  Measured
+        # on the 10 M-tet elasticity operator (tools/sweep_precision.py): fp32 for the fine-level residual leaves the
+        # PCG iteration count alone (89 -> 86), fp32 copies of A*P ("ap0") or of the coarse operators ("coarse") do
+        # not (-> 110: the rounding defect of an entry is O(1e-7 |A|) while A e is O(|A| / kappa) for the smooth
+        # vectors those operators act on), so they stay fp64 unless asked for.
+        self.mixed = bool(mixed)
+        self.mixed_mask = set(mixed_mask) if mixed_mask is not None else {"a0"}
         self.device = dev = A.val.device
         self.smooth_degree, self.coarse_degree = int(smooth_degree), int(coarse_degree)
+        self.level_smooth_degree = int(level_smooth_degree)
         self.smooth_ratio, self.coarse_ratio = float(smooth_ratio), float(coarse_ratio)
         self.symbolic = symbolic if symbolic is not None else AMGSymbolic(A.rowptr, A.col, A.nrows, A.ncols,
                                                                          dist=A.mesh.dist)
         self.levels = self.symbolic.levels
         self.distributed = self.levels[0].dist is not None
         self.version = None
-        self.power_its = 12
+        self.power_its = 12      # power-method steps of the first numeric phase (cold start) ...
+        self.power_its_warm = 4  # ... and of the later ones (restart from the previous dominant vector)
         self.use_ap = True  # first post-smoothing step through A*P (csrc/spmv.cu k_spmv_post)
         self._power_x: dict = {}
         f64 = dict(dtype=torch.float64, device=dev)
@@ -368,6 +379,9 @@ class AMGHierarchy:
             D.val = None if li == 0 else torch.zeros(L.nnzb * bs * bs, **f64)
             # rows of a replicated level computed by this rank (scattered + all-reduced into D.val)
             D.val_local = torch.zeros(L.rep_nnzb_local * bs * bs, **f64) if L.rep_dist is not None else None
+            want32 = self.mixed and (("a0" in self.mixed_mask) if li == 0 else ("coarse" in self.mixed_mask))
+            D.val32 = torch.zeros(L.nnzb * bs * bs, dtype=torch.float32, device=dev) if want32 else None
+            D.ap_val32 = None
             D.dinv = torch.zeros(nb, **f64)
             D.t = torch.zeros(nb, **f64)
             D.d = torch.zeros(nb, **f64)
@@ -381,6 +395,8 @@ class AMGHierarchy:
                 D.p_val = torch.ones(L.p_col.numel(), **f64)  # ghost rows stay 1.0 (tentative)
                 D.pt_val = torch.zeros(L.nnzp_owned, **f64)
                 D.ap_val = torch.zeros(L.ap_col.numel() * bs * bs, **f64)
+                if self.mixed and (("ap0" in self.mixed_mask) if li == 0 else ("coarse" in self.mixed_mask)):
+                    D.ap_val32 = torch.zeros(L.ap_col.numel() * bs * bs, dtype=torch.float32, device=dev)
                 D.xc_local = torch.zeros(L.coarse_gid.numel() * bs, **f64) if L.coarse_gid is not None else None
                 D.s_val = torch.zeros(L.nnzb, **f64) if bs > 1 else None
                 D.s_dinv = torch.zeros(L.n, **f64)
@@ -405,14 +421,18 @@ class AMGHierarchy:
         return self.symbolic.operator_complexity
 
     # ------------------------------------------------------------------ numeric
-    def _mat(self, L, val, bs) -> _lib.cb_mat:
+    def _mat(self, L, val, bs, val32=None) -> _lib.cb_mat:
         from cashocs_b200._utils import linalg
 
         m = _lib.cb_mat()
         m.nrows, m.ncols, m.bs = L.n, L.ncols, bs
         m.row_split = linalg.row_split_hint(L.nnzb, L.n)
         m.rowptr, m.col, m.val = L.rowptr.data_ptr(), L.col.data_ptr(), val.data_ptr()
+        m.val32 = val32.data_ptr() if val32 is not None else None
         return m
+
+    def _to_f32(self, src: torch.Tensor, dst: torch.Tensor) -> None:
+        _lib.check(_lib.load().cb_to_f32(_lib.stream_ptr(), src.numel(), _lib.ptr(src), _lib.ptr(dst)), "cb_to_f32")
 
     def _diag_inv(self, m, dinv, L, nscalar: int, safe: bool = False) -> float:
         """Inverse diagonal and an upper estimate of lambda_max(D^-1 A).
@@ -436,31 +456,44 @@ class AMGHierarchy:
             return float(self.lmax_dev.item())
         comp = nscalar // L.n
         ncol = L.ncols * comp
-        x = self._power_x.get((id(L), nscalar))
-        if x is None:
+        st = self._power_x.get((id(L), nscalar))
+        if st is None:
             gen = torch.Generator(device="cpu").manual_seed(1234 + nscalar)
             x0 = (torch.rand(nscalar, generator=gen, dtype=torch.float64) + 0.5).to(self.device)
-            x = (torch.zeros(ncol, dtype=torch.float64, device=self.device), x0,
-                 torch.zeros(nscalar, dtype=torch.float64, device=self.device))
-            self._power_x[(id(L), nscalar)] = x
-        xin, x0, y = x
-        xin[:nscalar] = x0
-        nrm = None
-        for _ in range(self.power_its):
+            st = _Level()
+            st.bufs = [torch.zeros(ncol, dtype=torch.float64, device=self.device) for _ in range(2)]
+            st.bufs[0][:nscalar] = x0
+            st.cur, st.alpha, st.warm = 0, 1.0, False
+            st.norms = torch.zeros(max(self.power_its, self.power_its_warm) + 1, dtype=torch.float64, device=self.device)
+            self._power_x[(id(L), nscalar)] = st
+        # No normalisation between the steps (lambda^steps stays far from overflow): every step is ONE fused pass
+        # y = alpha D^-1 A x with |y|^2, and the estimate is the last growth factor.  After the first numeric phase
+        # the iteration restarts from the previous matrix's dominant vector (the mesh moved a little: it is still an
+        # excellent start), so a few steps reproduce what twelve cold ones give.
+        steps = self.power_its_warm if st.warm else self.power_its
+        alpha = st.alpha
+        for k in range(steps):
+            xin, y = st.bufs[st.cur], st.bufs[1 - st.cur]
             if L.dist is not None:
                 L.dist.halo_exchange(xin, comp)
-            _lib.check(lib.cb_spmv(s, C.byref(m), _lib.ptr(xin), _lib.ptr(y)), "cb_spmv")
-            y.mul_(dinv[:nscalar])
-            nrm2 = torch.sum(y * y).reshape(1)
-            if L.dist is not None:
-                L.dist.allreduce(nrm2, "sum")
-            nrm = torch.sqrt(nrm2[0])
-            torch.div(y, nrm, out=xin[:nscalar])
+            _lib.check(lib.cb_power_step(s, C.byref(m), _lib.ptr(dinv), alpha, _lib.ptr(xin), _lib.ptr(y),
+                                         _lib.ptr(st.norms[k:]), _lib.ptr(self.scratch), self.scratch.numel(), 1),
+                       "cb_power_step")
+            alpha = 1.0
+            st.cur = 1 - st.cur
         if L.dist is not None:
             L.dist.allreduce(self.lmax_dev, "max")
-        both = torch.stack([self.lmax_dev[0], nrm]).cpu()  # one host sync per estimate
-        # the first power step starts from an un-normalised vector; later steps are normalised
-        return min(float(both[0]), 1.15 * float(both[1]))
+            L.dist.allreduce(st.norms, "sum")
+        both = torch.cat([self.lmax_dev, st.norms[:steps]]).cpu()  # one host sync per estimate
+        n_last, n_prev = float(both[steps]), float(both[steps - 1])
+        if st.warm or steps >= 2:
+            # warm start: the input of the first step was normalised (alpha), so for steps == 1 the growth is sqrt(n_last)
+            lam = (n_last / n_prev) ** 0.5 if steps >= 2 else n_last ** 0.5
+        else:
+            lam = float("inf")
+        st.alpha = 1.0 / n_last ** 0.5 if n_last > 0.0 else 1.0
+        st.warm = True
+        return min(float(both[0]), 1.15 * lam)
 
     def numeric(self, A) -> None:
         """Recompute prolongator values, Galerkin operators and smoother data for the values of ``A``."""
@@ -470,7 +503,9 @@ class AMGHierarchy:
         val = A.val
         for li, (L, D) in enumerate(zip(self.levels, self.data)):
             D.cur_val = val
-            m = self._mat(L, val, bs)
+            if D.val32 is not None:
+                self._to_f32(val, D.val32)
+            m = self._mat(L, val, bs, D.val32)
             if L.last and self.coarse_inv is not None:
                 _lib.check(lib.cb_amg_dense_inverse(s, C.byref(m), _lib.ptr(self.coarse_work), _lib.ptr(self.coarse_inv)),
                            "cb_amg_dense_inverse")
@@ -515,6 +550,8 @@ class AMGHierarchy:
                 _lib.check(lib.cb_amg_spgemm_terms(s, bs, 0, out.numel() // (bs * bs), _lib.ptr(L.ac_seg), _lib.ptr(L.ac_sl),
                                                    _lib.ptr(L.ac_sr), _lib.ptr(D.pt_val), _lib.ptr(D.ap_val), _lib.ptr(out)),
                            "cb_amg_spgemm_terms(PtAP)")
+            if D.ap_val32 is not None:
+                self._to_f32(D.ap_val, D.ap_val32)
             if rep:  # every rank contributes its rows of the replicated operator
                 nxt.val.zero_()
                 nxt.val.view(-1, bs * bs)[nxtL.rep_pos] = out.view(-1, bs * bs)
@@ -529,7 +566,7 @@ class AMGHierarchy:
         arr = (_lib.cb_amg_level * len(self.levels))()
         for li, (L, D) in enumerate(zip(self.levels, self.data)):
             e = arr[li]
-            e.A = self._mat(L, D.cur_val, self.bs)
+            e.A = self._mat(L, D.cur_val, self.bs, D.val32)
             e.dinv = D.dinv.data_ptr()
             e.lmax = D.lmax
             e.nc = 0 if L.last else L.nc
@@ -552,6 +589,7 @@ class AMGHierarchy:
                 ap.nrows, ap.ncols, ap.bs = L.n, L.nc + L.gc, self.bs
                 ap.row_split = linalg.row_split_hint(L.ap_col.numel(), L.n)
                 ap.rowptr, ap.col, ap.val = L.ap_rowptr.data_ptr(), L.ap_col.data_ptr(), D.ap_val.data_ptr()
+                ap.val32 = D.ap_val32.data_ptr() if D.ap_val32 is not None else None
                 e.AP = ap
                 if L.coarse_gid is not None:
                     e.coarse_gid = L.coarse_gid.data_ptr()
@@ -560,6 +598,7 @@ class AMGHierarchy:
         h.nlevels = len(self.levels)
         h.smooth_degree, h.coarse_degree = self.smooth_degree, self.coarse_degree
         h.smooth_ratio, h.coarse_ratio = self.smooth_ratio, self.coarse_ratio
+        h.level_smooth_degree = self.level_smooth_degree
         h.levels = C.cast(arr, C.c_void_p)
         h.coarse_inv = self.coarse_inv.data_ptr() if self.coarse_inv is not None else None
         self._level_array = arr

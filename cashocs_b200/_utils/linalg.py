@@ -78,6 +78,9 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None, distr
     opts = copy.deepcopy(direct_ksp_options) if ksp_options is None else dict(ksp_options)
     ksp = str(opts.get("ksp_type", "gmres")).lower()
     pc = str(opts.get("pc_type", "none")).lower()
+    flexible = opts.get("ksp_cg_flexible", None)
+    if ksp == "fcg":  # PETSc KSPFCG (mmax = 1): CG with the Polak-Ribiere beta
+        ksp, flexible = "cg", True
     if ksp == "preonly" and pc in ("lu", "cholesky"):
         base = dict(DIRECT_EQUIVALENT)
         ksp, pc = base["ksp_type"], base["pc_type"]
@@ -107,7 +110,7 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None, distr
              "pc_chebyshev_degree", "pc_chebyshev_ratio", "ksp_check_every", "ksp_ksp_type",
              "ksp_ksp_max_it", "ksp_pc_type", "ksp_profile_every", "ksp_use_graph", "pc_amg_smooth_degree",
              "pc_amg_coarse_degree", "pc_amg_smooth_ratio", "pc_amg_coarse_ratio", "pc_amg_min_coarse",
-             "pc_amg_rigid_body_correction", "pc_amg_nullspace",
+             "pc_amg_rigid_body_correction", "pc_amg_nullspace", "pc_amg_precision", "ksp_cg_flexible", "pc_amg_level_smooth_degree",
              "pc_gamg_type", "pc_gamg_agg_nsmooths"} | _IGNORED_KEYS
     unknown = set(opts) - known
     if unknown:
@@ -127,6 +130,8 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None, distr
     o.monitor = 1 if ("ksp_monitor" in opts) else 0
     o.profile_every = int(opts.get("ksp_profile_every", 0))
     o.use_graph = int(opts.get("ksp_use_graph", 0))
+    # -1: unset (the solver turns it on for a mixed-precision AMG hierarchy), 0 / 1 explicit
+    o.flexible = -1 if flexible is None else int(_truthy(flexible))
     return o
 
 
@@ -182,6 +187,21 @@ class Matrix:
             y = torch.empty(self.nrows * self.bs, dtype=torch.float64, device=x.device)
         m = self.struct()
         _lib.check(_lib.load().cb_spmv(_lib.stream_ptr(), C.byref(m), _lib.ptr(x), _lib.ptr(y)), "cb_spmv")
+        return y
+
+    def mult_f32(self, x: torch.Tensor, y: torch.Tensor | None = None) -> torch.Tensor:
+        """y = fl32(A) x: the preconditioner's pass over the fp32 copy of the values (made on first use)."""
+        _lib.require_cuda(x, y)
+        if y is None:
+            y = torch.empty(self.nrows * self.bs, dtype=torch.float64, device=x.device)
+        v32 = self.__dict__.get("_val32")
+        if v32 is None or self.__dict__.get("_val32_version") != self.version:
+            v32 = self.__dict__.setdefault("_val32", torch.empty(self.val.numel(), dtype=torch.float32, device=self.val.device))
+            _lib.check(_lib.load().cb_to_f32(_lib.stream_ptr(), self.val.numel(), _lib.ptr(self.val), _lib.ptr(v32)), "cb_to_f32")
+            self._val32_version = self.version
+        m = self.struct()
+        m.val32 = v32.data_ptr()
+        _lib.check(_lib.load().cb_spmv_f32(_lib.stream_ptr(), C.byref(m), _lib.ptr(x), _lib.ptr(y)), "cb_spmv_f32")
         return y
 
     def scalar_product(self, x: torch.Tensor, y: torch.Tensor) -> float:
@@ -417,36 +437,52 @@ def _truthy(v) -> bool:
 class LinearSolver:
     """A solver for linear problems (``cashocs/_utils/linalg.py:480-546``), device resident."""
 
-    # AMG hierarchies are shared by all solvers: keyed by (mesh, block size); the symbolic phase
-    # runs once per mesh topology, the numeric phase once per matrix version
-    _amg_cache: dict = {}
-
     def __init__(self) -> None:
         self._work: torch.Tensor | None = None
         self.last_result: KSPResult | None = None
         self.total_iterations = 0
 
+    # AMG data lives on the objects it describes, so it is released with them: the *symbolic* phase (pattern-only) is an
+    # attribute of the mesh / function space that owns the sparsity pattern and is shared by every operator on it;
+    # the *values* of a hierarchy belong to one Matrix and one option set and are refreshed when the matrix version
+    # changes (state, mu-Laplace and mass matrices on one mesh no longer evict each other's numeric phase)
+    @staticmethod
+    def _amg_option_key(options: dict, bs: int) -> tuple:
+        prec = str(options.get("pc_amg_precision", "mixed")).casefold()
+        if not (prec in ("mixed", "double") or prec.startswith("mixed:")):
+            raise _exceptions.InputError("cashocs_b200.LinearSolver", "pc_amg_precision",
+                                         "mixed, double or mixed:<a0|ap0|coarse joined by +>")
+        # levels >= 1 hold a tenth of the fine level's bytes: vector operators smooth them with degree 2 (measured on
+        # the 10 M-tet elasticity solve: 89 -> 70 PCG iterations for 11 % more time per iteration); scalar ones gain
+        # nothing (35 -> 33)
+        lsd = int(options.get("pc_amg_level_smooth_degree", 2 if bs > 1 else 0))
+        return (int(options.get("pc_amg_smooth_degree", 1)), int(options.get("pc_amg_coarse_degree", 16)),
+                float(options.get("pc_amg_smooth_ratio", 10.0)), float(options.get("pc_amg_coarse_ratio", 40.0)), prec, lsd)
+
     @classmethod
     def amg_hierarchy(cls, A: "Matrix", options: dict):
         from cashocs_b200._utils import amg
 
-        key = (id(A.mesh), A.bs)
-        h = cls._amg_cache.get(key)
-        if h is None or h.levels[0].rowptr is not A.rowptr:
-            skey = (id(A.mesh), "symbolic")
-            sym = cls._amg_cache.get(skey)
-            if sym is None or sym.levels[0].rowptr is not A.rowptr:
-                sym = amg.AMGSymbolic(A.rowptr, A.col, A.nrows, A.ncols, dist=A.mesh.dist)
-                cls._amg_cache[skey] = sym
-            h = amg.AMGHierarchy(
-                A, sym, smooth_degree=int(options.get("pc_amg_smooth_degree", 1)),
-                coarse_degree=int(options.get("pc_amg_coarse_degree", 16)),
-                smooth_ratio=float(options.get("pc_amg_smooth_ratio", 10.0)),
-                coarse_ratio=float(options.get("pc_amg_coarse_ratio", 40.0)))
-            cls._amg_cache[key] = h
-        if h.version != (id(A), A.version):
+        key = cls._amg_option_key(options, A.bs)
+        holder = A.mesh
+        sym = getattr(holder, "_amg_symbolic", None)
+        if sym is None or sym.levels[0].rowptr is not A.rowptr or sym.distance != amg.AMGSymbolic.DISTANCE:
+            sym = amg.AMGSymbolic(A.rowptr, A.col, A.nrows, A.ncols, dist=holder.dist)
+            sym.distance = amg.AMGSymbolic.DISTANCE
+            holder._amg_symbolic = sym
+        cache = A.__dict__.setdefault("_amg", {})
+        h = cache.get(key)
+        if h is None or h.symbolic is not sym:
+            if len(cache) >= 2:  # option sweeps: keep the memory of at most two value sets per matrix
+                cache.clear()
+            prec = key[4]
+            h = amg.AMGHierarchy(A, sym, smooth_degree=key[0], coarse_degree=key[1], smooth_ratio=key[2],
+                                 coarse_ratio=key[3], mixed=prec != "double", level_smooth_degree=key[5],
+                                 mixed_mask=set(prec[6:].split("+")) if prec.startswith("mixed:") else None)
+            cache[key] = h
+        if h.version != A.version:
             h.numeric(A)
-            h.version = (id(A), A.version)
+            h.version = A.version
             h.rbm = None
         return h
 
@@ -454,23 +490,27 @@ class LinearSolver:
     def rbm_hierarchy(cls, A: "Matrix"):
         from cashocs_b200._utils import amg_rbm
 
-        key = (id(A.mesh), "rbm")
-        h = cls._amg_cache.get(key)
+        h = A.__dict__.get("_amg_rbm")
         if h is None or h.levels[0].rowptr is not A.rowptr:
-            h = amg_rbm.RBMHierarchy(A)
+            sym = getattr(A.mesh, "_amg_rbm_symbolic", None)
+            if sym is None or sym.levels[0].rowptr is not A.rowptr:
+                sym = amg_rbm.RBMSymbolic(A.rowptr, A.col, A.nrows)
+                A.mesh._amg_rbm_symbolic = sym
+            h = amg_rbm.RBMHierarchy(A, sym)
             h.version = None
-            cls._amg_cache[key] = h
-        if h.version != (id(A), A.version):
+            A._amg_rbm = h
+        if h.version != A.version:
             h.A = A
             h.numeric(A.mesh.coords)
-            h.version = (id(A), A.version)
+            h.version = A.version
         return h
 
     @staticmethod
     def rigid_body_correction(A: "Matrix", h):
         """Data of the coarse correction ``Z (Z^T A Z)^-1 Z^T`` with the global rigid-body modes (see
         ``cb_ksp_opts.rbm_*``): centred node coordinates, the inverse of the k x k Galerkin matrix (k = 3 in 2-D,
-        6 in 3-D) and the work vector.  6 SpMVs and a 6 x 6 inverse per matrix version."""
+        6 in 3-D) and the work vector.  Per matrix version: k SpMVs + k projections + one k x k inverse, all native
+        (``csrc/rbm.cu``); the only torch op is the one-off centre of the initial mesh."""
         if getattr(h, "rbm", None) is not None:
             return h.rbm
         mesh, bs = A.mesh, A.bs
@@ -479,28 +519,31 @@ class LinearSolver:
                                          "needs a vertex-blocked vector operator (bs = dim) on the mesh vertices")
         dist = mesh.dist
         n_own, k = mesh.n_owned_vertices, (6 if bs == 3 else 3)
-        centre = mesh.coords[:n_own].sum(dim=0)
-        count = torch.tensor([float(n_own)], dtype=torch.float64, device=mesh.device)
+        centre = mesh.__dict__.get("_rbm_centre")
+        if centre is None:
+            # any fixed point spans the same modes; the centroid of the initial mesh keeps the rotations well scaled
+            acc = torch.cat([mesh.coords[:n_own].sum(dim=0), torch.tensor([float(n_own)], dtype=torch.float64,
+                                                                          device=mesh.device)])
+            if dist is not None:
+                dist.allreduce(acc, "sum")
+            acc = acc.cpu()
+            centre = mesh._rbm_centre = (C.c_double * 3)(*[float(acc[a] / acc[bs]) for a in range(bs)])
+        buf = h.__dict__.get("_rbm_buf")
+        if buf is None:
+            f64 = dict(dtype=torch.float64, device=mesh.device)
+            buf = h._rbm_buf = dict(c=torch.zeros(A.ncols * bs, **f64), v=torch.zeros(A.ncols * bs, **f64),
+                                    w=torch.zeros(A.nrows * bs, **f64), G=torch.zeros(k * k, **f64),
+                                    einv=torch.zeros(k * k, **f64), work=torch.zeros(8, **f64))
+        lib, s = _lib.load(), _lib.stream_ptr()
+        scratch = mesh.reduce_scratch()
+        m = A.struct()
+        _lib.check(lib.cb_rbm_galerkin(s, C.byref(m), _lib.ptr(mesh.coords), C.cast(centre, C.c_void_p), _lib.ptr(buf["c"]),
+                                       _lib.ptr(buf["v"]), _lib.ptr(buf["w"]), _lib.ptr(buf["G"]), _lib.ptr(scratch),
+                                       scratch.numel()), "cb_rbm_galerkin")
         if dist is not None:
-            dist.allreduce(centre, "sum")
-            dist.allreduce(count, "sum")
-        c = (mesh.coords - centre / count).contiguous()  # owned + ghost nodes
-        Z = torch.zeros(k, mesh.num_vertices, bs, dtype=torch.float64, device=mesh.device)
-        for a in range(bs):
-            Z[a, :, a] = 1.0
-        if bs == 3:
-            Z[3, :, 0], Z[3, :, 1] = -c[:, 1], c[:, 0]
-            Z[4, :, 1], Z[4, :, 2] = -c[:, 2], c[:, 1]
-            Z[5, :, 0], Z[5, :, 2] = c[:, 2], -c[:, 0]
-        else:
-            Z[2, :, 0], Z[2, :, 1] = -c[:, 1], c[:, 0]
-        Z = Z.reshape(k, -1)
-        W = torch.stack([A.mult(Z[j].contiguous()) for j in range(k)])  # [k, n_own * bs]
-        G = (Z[:, : n_own * bs] @ W.T).contiguous()
-        if dist is not None:
-            dist.allreduce(G.view(-1), "sum")
-        einv = torch.linalg.inv(G.cpu()).to(mesh.device).contiguous()  # k x k, on the host
-        h.rbm = (c[:n_own].contiguous(), einv, torch.zeros(8, dtype=torch.float64, device=mesh.device))
+            dist.allreduce(buf["G"], "sum")
+        _lib.check(lib.cb_rbm_invert(s, k, _lib.ptr(buf["G"]), _lib.ptr(buf["einv"])), "cb_rbm_invert")
+        h.rbm = (buf["c"], buf["einv"], buf["work"])
         return h.rbm
 
     def _workspace(self, n_doubles: int, device) -> torch.Tensor:
@@ -548,15 +591,19 @@ class LinearSolver:
             hierarchy = self.amg_hierarchy(A, ksp_options or {})
             hstruct = hierarchy.struct()
             opts.amg = C.cast(C.pointer(hstruct), C.c_void_p)
+            if opts.flexible < 0:
+                opts.flexible = 1 if hierarchy.mixed else 0
             # rigid-body coarse correction: default for vertex-blocked vector operators (the elasticity Riesz
-            # problem) on one GPU, where it is validated; an explicit option overrides (True also on partitions)
+            # problem), on one GPU and on partitioned meshes (one extra 6-value all-reduce per iteration)
             applicable = (A.bs >= 2 and A.bs == A.mesh.dim and A.nrows == A.mesh.n_owned_vertices
                           and nullspace != "rigid_body")
             wanted = (ksp_options or {}).get("pc_amg_rigid_body_correction", None)
-            use_rbm = applicable and (A.mesh.dist is None if wanted is None else _truthy(wanted))
+            use_rbm = applicable and (True if wanted is None else _truthy(wanted))
             if use_rbm:
                 rbm = self.rigid_body_correction(A, hierarchy)
                 opts.rbm_coords, opts.rbm_einv, opts.rbm_work = (t.data_ptr() for t in rbm)
+        if opts.flexible < 0:
+            opts.flexible = 0
         n, nc = A.nrows * A.bs, A.ncols * A.bs
         if function.numel() < n or b.numel() < n:
             raise _exceptions.InputError("cashocs_b200.LinearSolver.solve", "function", "vector too short for the matrix")

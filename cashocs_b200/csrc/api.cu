@@ -43,7 +43,23 @@ int num_sms() {
 }  // namespace cb
 
 extern "C" const char* cb_last_error(void) { return cb::g_err; }
-extern "C" int cb_version(void) { return 100; }
+extern "C" int cb_version(void) { return 200; }
+// sizeof() of the structs of the header as THIS library was compiled: a binding (ctypes / cgo / JNI) checks its own
+// mirror against these before the first call instead of trusting a hand-counted constant
+extern "C" int64_t cb_struct_size(int which) {
+  switch (which) {
+    case 0: return (int64_t)sizeof(cb_poly);
+    case 1: return (int64_t)sizeof(cb_quad);
+    case 2: return (int64_t)sizeof(cb_mat);
+    case 3: return (int64_t)sizeof(cb_mesh_view);
+    case 4: return (int64_t)sizeof(cb_ksp_opts);
+    case 5: return (int64_t)sizeof(cb_amg_level);
+    case 6: return (int64_t)sizeof(cb_amg);
+    case 7: return (int64_t)sizeof(cb_ksp_result);
+    case 8: return (int64_t)sizeof(cb_p2_view);
+  }
+  return -1;
+}
 extern "C" int cb_num_sms(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cb::set_error("no CUDA device"); return CB_ERR_CUDA; }

@@ -23,7 +23,7 @@
 namespace cb {
 
 int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
-                  double* result, double* scratch, const int* done = nullptr);
+                  double* result, double* scratch, const int* done = nullptr, bool use32 = false);
 int amg_restrict(cudaStream_t s, int bs, const cb_amg_level* L, const double* b, const double* t, double* bc,
                  const int* done, int p_block);
 int amg_prolong(cudaStream_t s, int bs, const cb_amg_level* L, const double* xc, double* x, const int* done, int p_block);
@@ -42,7 +42,8 @@ struct KspState {
   // MINRES recurrences
   double oldb, mbeta, dbar, epsln, phibar, cs, sn, alfa, oldeps, delta, gamma, phi;
   int its, reason, done, max_it;
-  int hist_len, pad;
+  int hist_len, flexible;
+  double alpha;  // step length of the last x / r update (flexible beta)
 };
 constexpr int STATE_DOUBLES = 64;
 static_assert(sizeof(KspState) <= STATE_DOUBLES * sizeof(double), "state block too small");
@@ -75,7 +76,9 @@ __device__ void cg_after_zr(KspState* st, double* hist, int is_init) {
   // PETSc KSPCG: beta == 0 -> converged (happy breakdown), beta < 0 -> indefinite PC
   if (zr == 0.0) { st->reason = CB_KSP_CONVERGED_ATOL; st->done = 1; return; }
   if (zr < 0.0) { st->reason = CB_KSP_DIVERGED_INDEFINITE_PC; st->done = 1; return; }
-  st->bcoef = is_init ? 0.0 : st->beta / st->betaold;
+  // flexible (Polak-Ribiere): z_new.(r_new - r_old) = -alpha z_new.w since r_new = r_old - alpha w (sums[2] = z_new.w)
+  if (is_init) st->bcoef = 0.0;
+  else st->bcoef = st->flexible ? -st->alpha * st->sums[2] / st->betaold : st->beta / st->betaold;
 }
 
 // after p.Ap is known
@@ -129,22 +132,25 @@ k_cg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ di
 // sums = (z.r, z.z) for an already applied preconditioner
 __global__ void __launch_bounds__(256)
 k_dots_zr(int64_t n, const double* __restrict__ z, const double* __restrict__ r, KspState* st,
-          double* hist, double* scratch, int finalize_mode /* -1 none, 0 init, 1 iter */) {
+          double* hist, double* scratch, int finalize_mode /* -1 none, 0 init, 1 iter */,
+          const double* __restrict__ w = nullptr /* flexible beta: also z.w */) {
   if (st->done) return;
-  __shared__ double s_red[66];
-  double zr = 0.0, zz = 0.0;
+  __shared__ double s_red[99];
+  double zr = 0.0, zz = 0.0, zw = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     const double zi = z[i];
     zr += zi * r[i];
     zz += zi * zi;
+    if (w) zw += zi * w[i];
   }
-  double v[2] = {zr, zz};
-  const int ops[2] = {RED_SUM, RED_SUM};
-  if (grid_reduce<2>(v, ops, scratch, s_red)) {
+  double v[3] = {zr, zz, zw};
+  const int ops[3] = {RED_SUM, RED_SUM, RED_SUM};
+  if (grid_reduce<3>(v, ops, scratch, s_red)) {
     if (threadIdx.x == 0) {
       st->sums[0] = v[0];
       st->sums[1] = v[1];
+      st->sums[2] = v[2];
       if (finalize_mode >= 0) cg_after_zr(st, hist, finalize_mode == 0);
     }
   }
@@ -200,10 +206,10 @@ template <int BS>
 __global__ void __launch_bounds__(256)
 k_rbm_correct(int64_t nn, const double* __restrict__ r, double* __restrict__ z, const double* __restrict__ xc,
               const double* __restrict__ einv, const double* __restrict__ ztr, KspState* st, double* hist,
-              double* scratch, int finalize_mode /* -1 none, 0 init, 1 iter */) {
+              double* scratch, int finalize_mode /* -1 none, 0 init, 1 iter */, const double* __restrict__ w = nullptr) {
   if (st->done) return;
   constexpr int K = Rbm<BS>::K;
-  __shared__ double s_red[66];
+  __shared__ double s_red[99];
   __shared__ double y[K];
   if (threadIdx.x < K) {
     double acc = 0.0;
@@ -211,7 +217,7 @@ k_rbm_correct(int64_t nn, const double* __restrict__ r, double* __restrict__ z, 
     y[threadIdx.x] = acc;
   }
   __syncthreads();
-  double zr = 0.0, zz = 0.0;
+  double zr = 0.0, zz = 0.0, zw = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nn;
        i += (int64_t)gridDim.x * blockDim.x) {
     double c[BS], dz[BS];
@@ -231,14 +237,16 @@ k_rbm_correct(int64_t nn, const double* __restrict__ r, double* __restrict__ z, 
       z[i * BS + a] = zi;
       zr += zi * r[i * BS + a];
       zz += zi * zi;
+      if (w) zw += zi * w[i * BS + a];
     }
   }
-  double v[2] = {zr, zz};
-  const int ops[2] = {RED_SUM, RED_SUM};
-  if (grid_reduce<2>(v, ops, scratch, s_red)) {
+  double v[3] = {zr, zz, zw};
+  const int ops[3] = {RED_SUM, RED_SUM, RED_SUM};
+  if (grid_reduce<3>(v, ops, scratch, s_red)) {
     if (threadIdx.x == 0) {
       st->sums[0] = v[0];
       st->sums[1] = v[1];
+      st->sums[2] = v[2];
       if (finalize_mode >= 0) cg_after_zr(st, hist, finalize_mode == 0);
     }
   }
@@ -273,7 +281,7 @@ k_cg_spmv(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32_
     const int64_t row0 = rb * R;
     const int nr = (int)((nrows - row0 < R) ? (nrows - row0) : R);
     double acc;
-    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, p, row0, nr, G, phase, acc);
+    const int64_t i = spmv_row_block<BS, double>(sm, rowptr, col, val, p, row0, nr, G, phase, acc);
     if (i >= 0) {
       w[i] = acc;
       local += acc * p[i];
@@ -299,6 +307,7 @@ k_cg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ w,
   if (st->done) return;
   __shared__ double s_red[66];
   const double a = st->beta / st->dpi;
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->alpha = a;  // nobody reads it in this kernel
   double zr = 0.0, zz = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -375,32 +384,32 @@ k_gather_nodes(int64_t n, int bs, const int32_t* __restrict__ gid, const double*
 //   z_i += c2 * dinv_i * (b_i - t_i - (AP e)_i)      [optionally d_i = that increment]
 // z is only touched at the row a lane owns (the gather reads e, the coarse vector): in place.
 // DOTS (fine level, last kernel of the cycle): also sums = (z.b, z.z) for the PCG recurrences.
-template <int BS, bool DOTS>
-__global__ void __launch_bounds__(SpmvCfg<BS>::THREADS)
+template <int BS, bool DOTS, typename VT>
+__global__ void __launch_bounds__(SpmvCfg<BS, VT>::THREADS)
 k_amg_post(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-           const double* __restrict__ val, const double* __restrict__ e, double* __restrict__ z,
+           const VT* __restrict__ val, const double* __restrict__ e, double* __restrict__ z,
            const double* __restrict__ b, const double* __restrict__ t, const double* __restrict__ dinv,
            double c2, double* __restrict__ dvec, KspState* st, double* hist, double* scratch,
-           int finalize_mode /* -1 none, 0 init, 1 iter */) {
+           int finalize_mode /* -1 none, 0 init, 1 iter */, const double* __restrict__ w /* flexible beta: z.w */) {
   if (st->done) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SpmvSmem<BS> sm = spmv_smem_init<BS>(smem_raw);
+  const SpmvSmem<BS, VT> sm = spmv_smem_init<BS, VT>(smem_raw);
   uint32_t phase = 0;
   const int R = spmv_rows_per_cta<BS>(G);
   const int64_t nrb = (nrows + R - 1) / R;
-  double zr = 0.0, zz = 0.0;
+  double zr = 0.0, zz = 0.0, zw = 0.0;
   for (int64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
     const int64_t row0 = rb * R;
     const int nr = (int)((nrows - row0 < R) ? (nrows - row0) : R);
     double acc;
-    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, e, row0, nr, G, phase, acc);
+    const int64_t i = spmv_row_block<BS, VT>(sm, rowptr, col, val, e, row0, nr, G, phase, acc);
     if (i >= 0) {
       const double bi = b[i];
       const double di = c2 * dinv[i] * (bi - t[i] - acc);
       if (dvec) dvec[i] = di;
       const double zi = z[i] + di;
       z[i] = zi;
-      if (DOTS) { zr += zi * bi; zz += zi * zi; }
+      if (DOTS) { zr += zi * bi; zz += zi * zi; if (w) zw += zi * w[i]; }
     }
   }
   if (DOTS) {
@@ -408,12 +417,13 @@ k_amg_post(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32
     // memory to within 1.4 KB, a static array would cost the ninth resident CTA
     __syncthreads();
     double* s_red = reinterpret_cast<double*>(smem_raw);
-    double v[2] = {zr, zz};
-    const int ops[2] = {RED_SUM, RED_SUM};
-    if (grid_reduce<2>(v, ops, scratch, s_red)) {
+    double v[3] = {zr, zz, zw};
+    const int ops[3] = {RED_SUM, RED_SUM, RED_SUM};
+    if (grid_reduce<3>(v, ops, scratch, s_red)) {
       if (threadIdx.x == 0) {
         st->sums[0] = v[0];
         st->sums[1] = v[1];
+        st->sums[2] = v[2];
         if (finalize_mode >= 0) cg_after_zr(st, hist, finalize_mode == 0);
       }
     }
@@ -520,7 +530,7 @@ k_minres_spmv(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const in
     const int64_t row0 = rb * R;
     const int nr = (int)((nrows - row0 < R) ? (nrows - row0) : R);
     double acc;
-    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, v, row0, nr, G, phase, acc);
+    const int64_t i = spmv_row_block<BS, double>(sm, rowptr, col, val, v, row0, nr, G, phase, acc);
     if (i >= 0) {
       if (c != 0.0) acc -= c * r1[i];
       t[i] = acc;
@@ -613,6 +623,7 @@ struct Solver {
   int profile_every = 0, spmv_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
 
+  const double* flex_w = nullptr;  // flexible beta: the fused dots of the iteration also accumulate z.w
   bool capturing = false;  // inside a CUDA-graph capture: no event timing
   bool prof_begin() {
     const bool on = !capturing && profile_every > 0 && (spmv_launches % profile_every) == 0 && prof.size() < 1024;
@@ -687,7 +698,7 @@ struct Solver {
   // t_l = A_l x_l (ghost update of x_l first on a partitioned mesh)
   int level_spmv(const cb_amg_level& L, double* xl) {
     if (L.dist) { if (int e = dist_halo_exchange(s, L.dist, xl, bs, L.sendbuf)) return e; }
-    return spmv_dispatch(s, &L.A, xl, L.t, nullptr, nullptr, nullptr, &st->done);
+    return spmv_dispatch(s, &L.A, xl, L.t, nullptr, nullptr, nullptr, &st->done, /*use32=*/true);
   }
 
   // `degree` Chebyshev-Jacobi steps on A_l x = b (zero or current initial guess); local operator
@@ -716,10 +727,10 @@ struct Solver {
     return CB_OK;
   }
 
-  template <int BS>
-  int amg_post_bs(const cb_mat* AP, const double* e, double* z, const double* b, const double* t, const double* dinv,
-                  double c2, double* dvec, int dots_mode) {
-    using C = SpmvCfg<BS>;
+  template <int BS, typename VT>
+  int amg_post_bs(const cb_mat* AP, const VT* val, const double* e, double* z, const double* b, const double* t,
+                  const double* dinv, double c2, double* dvec, int dots_mode) {
+    using C = SpmvCfg<BS, VT>;
     const int G = spmv_sanitize_split(AP->row_split);
     const int R = spmv_rows_per_cta<BS>(G);
     const int64_t nrb = (AP->nrows + R - 1) / R;
@@ -729,24 +740,28 @@ struct Solver {
     static bool configured = false;
     if (!configured) {
       const int co = (int)cudaSharedmemCarveoutMaxShared;
-      CB_CUDA_CHECK(cudaFuncSetAttribute(k_amg_post<BS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-      CB_CUDA_CHECK(cudaFuncSetAttribute(k_amg_post<BS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_amg_post<BS, true, VT>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+      CB_CUDA_CHECK(cudaFuncSetAttribute(k_amg_post<BS, false, VT>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
       configured = true;
     }
     if (dots_mode > -2)
-      k_amg_post<BS, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(AP->nrows, G, AP->rowptr, AP->col, AP->val, e, z, b, t,
-                                                                 dinv, c2, dvec, st, hist_dev, scratch, dots_mode);
+      k_amg_post<BS, true, VT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(AP->nrows, G, AP->rowptr, AP->col, val, e, z, b, t,
+                                                                     dinv, c2, dvec, st, hist_dev, scratch, dots_mode, flex_w);
     else
-      k_amg_post<BS, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(AP->nrows, G, AP->rowptr, AP->col, AP->val, e, z, b, t,
-                                                                  dinv, c2, dvec, st, hist_dev, scratch, -1);
+      k_amg_post<BS, false, VT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(AP->nrows, G, AP->rowptr, AP->col, val, e, z, b, t,
+                                                                      dinv, c2, dvec, st, hist_dev, scratch, -1, nullptr);
     CB_LAUNCH_CHECK();
     return CB_OK;
   }
   int amg_post(const cb_mat* AP, const double* e, double* z, const double* b, const double* t, const double* dinv,
                double c2, double* dvec, int dots_mode) {
-    return AP->bs == 1 ? amg_post_bs<1>(AP, e, z, b, t, dinv, c2, dvec, dots_mode)
-         : AP->bs == 2 ? amg_post_bs<2>(AP, e, z, b, t, dinv, c2, dvec, dots_mode)
-                       : amg_post_bs<3>(AP, e, z, b, t, dinv, c2, dvec, dots_mode);
+    if (AP->val32)
+      return AP->bs == 1 ? amg_post_bs<1, float>(AP, AP->val32, e, z, b, t, dinv, c2, dvec, dots_mode)
+           : AP->bs == 2 ? amg_post_bs<2, float>(AP, AP->val32, e, z, b, t, dinv, c2, dvec, dots_mode)
+                         : amg_post_bs<3, float>(AP, AP->val32, e, z, b, t, dinv, c2, dvec, dots_mode);
+    return AP->bs == 1 ? amg_post_bs<1, double>(AP, AP->val, e, z, b, t, dinv, c2, dvec, dots_mode)
+         : AP->bs == 2 ? amg_post_bs<2, double>(AP, AP->val, e, z, b, t, dinv, c2, dvec, dots_mode)
+                       : amg_post_bs<3, double>(AP, AP->val, e, z, b, t, dinv, c2, dvec, dots_mode);
   }
 
   // Fusion hooks of the V-cycle with the PCG loop around it:
@@ -767,6 +782,12 @@ struct Solver {
     return true;
   }
 
+  // Chebyshev degree of the pre / post smoother of level l: the coarse levels (a tenth of the fine level's bytes) may
+  // smooth harder than the fine one
+  static int level_degree(const cb_amg* h, int l) {
+    return (l > 0 && h->level_smooth_degree > 0) ? h->level_smooth_degree : h->smooth_degree;
+  }
+
   // z = M^-1 r : one symmetric V-cycle (pre/post Chebyshev smoothing, Chebyshev coarsest solve)
   int amg_vcycle(const cb_amg* h, const double* r, double* z, bool presmoothed = false, int dots_mode = -2) {
     const int L = h->nlevels;
@@ -783,7 +804,7 @@ struct Solver {
         }
         break;
       }
-      if (int e = amg_smooth(lev, bl, xl, h->smooth_degree, h->smooth_ratio, true, l == 0 && presmoothed)) return e;
+      if (int e = amg_smooth(lev, bl, xl, level_degree(h, l), h->smooth_ratio, true, l == 0 && presmoothed)) return e;
       if (int e = level_spmv(lev, xl)) return e;
       const cb_amg_level& nxt = h->levels[l + 1];
       if (nxt.rep_dist) {
@@ -816,7 +837,7 @@ struct Solver {
         } else if (nxt.dist) {
           if (int e = dist_halo_exchange(s, nxt.dist, nxt.x, bs, nxt.sendbuf)) return e;
         }
-        const int degree = h->smooth_degree;
+        const int degree = level_degree(h, l);
         std::pair<double, double> coef[64];
         double inv_theta = 0.0;
         cheb_coefficients(lev.lmax, h->smooth_ratio, degree, inv_theta, coef);
@@ -832,7 +853,7 @@ struct Solver {
           CB_LAUNCH_CHECK();
         }
       } else {
-        if (int e = amg_smooth(lev, bl, xl, h->smooth_degree, h->smooth_ratio, false)) return e;
+        if (int e = amg_smooth(lev, bl, xl, level_degree(h, l), h->smooth_ratio, false)) return e;
       }
     }
     return CB_OK;
@@ -892,6 +913,7 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
   memset(&h0, 0, sizeof(h0));
   h0.rtol = o->rtol; h0.atol = o->atol; h0.dtol = o->dtol; h0.max_it = o->max_it;
   h0.hist_len = (int)hlen;
+  h0.flexible = (o->flexible != 0 && o->ksp_type == CB_KSP_CG && (o->pc_type == CB_PC_AMG || o->pc_type == CB_PC_CHEBYSHEV)) ? 1 : 0;
   CB_CUDA_CHECK(cudaMemcpyAsync(st, &h0, sizeof(h0), cudaMemcpyHostToDevice, s));
   CB_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * RED_SCRATCH_LEN, s));
 
@@ -970,7 +992,8 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
     if (amg) {
       CB_REQUIRE(o->amg && o->amg->nlevels >= 1 && o->amg->levels, "pc_type amg needs a hierarchy (cb_ksp_opts.amg)");
       CB_REQUIRE(o->amg->smooth_degree >= 1 && o->amg->smooth_degree <= 64 && o->amg->coarse_degree >= 1 &&
-                 o->amg->coarse_degree <= 64, "amg smoother degrees must be in 1..64");
+                 o->amg->coarse_degree <= 64 && o->amg->level_smooth_degree >= 0 && o->amg->level_smooth_degree <= 64,
+                 "amg smoother degrees must be in 1..64");
     }
     // Chebyshev coefficients (fixed polynomial -> a linear SPD preconditioner)
     std::pair<double, double> coef[64];
@@ -996,6 +1019,7 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
     bool presmoothed = false;
     int dots_mode = -2;
     const bool rbm = amg && o->rbm_coords != nullptr;
+    const bool flexible = cheb && o->flexible != 0;
     if (rbm) CB_REQUIRE(S.bs >= 2 && o->rbm_einv && o->rbm_work, "rigid-body correction: bs must be 2 or 3, einv / work set");
     auto apply_cheb = [&]() -> int {  // z = P(r)
       if (rbm) {
@@ -1007,9 +1031,9 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
         CB_LAUNCH_CHECK();
         if (dist) { if (int e = dist_allreduce_sum(s, dist, o->rbm_work, S.bs == 3 ? 6 : 3)) return e; }
         if (S.bs == 3) k_rbm_correct<3><<<vg, 256, 0, s>>>(nn, r, z, o->rbm_coords, o->rbm_einv, o->rbm_work, st, hist_dev,
-                                                        scratch, dots_mode);
+                                                        scratch, dots_mode, S.flex_w);
         else k_rbm_correct<2><<<vg, 256, 0, s>>>(nn, r, z, o->rbm_coords, o->rbm_einv, o->rbm_work, st, hist_dev, scratch,
-                                                 dots_mode);
+                                                 dots_mode, S.flex_w);
         CB_LAUNCH_CHECK();
         S.dots_fused = true;
         return CB_OK;
@@ -1046,6 +1070,7 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
     // into a CUDA graph and replayed (the one-sided halo / all-reduce kernels keep their epochs in
     // device memory for exactly that reason)
     auto iteration = [&]() -> int {
+      S.flex_w = flexible ? w : nullptr;  // (not during the initial application: w is not defined yet)
       k_cg_p<<<vg, 256, 0, s>>>(n, z, p, st);
       CB_LAUNCH_CHECK();
       if (int e = S.cg_spmv(p, w)) return e;
@@ -1062,10 +1087,10 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
         dots_mode = amg ? (dist ? -1 : 1) : -2;
         if (int e = apply_cheb()) return e;
         if (!S.dots_fused) {
-          k_dots_zr<<<vg, 256, 0, s>>>(n, z, r, st, hist_dev, scratch, dist ? -1 : 1);
+          k_dots_zr<<<vg, 256, 0, s>>>(n, z, r, st, hist_dev, scratch, dist ? -1 : 1, S.flex_w);
           CB_LAUNCH_CHECK();
         }
-        if (int e = S.reduce_and_step(2, 1, false)) return e;
+        if (int e = S.reduce_and_step(flexible ? 3 : 2, 1, false)) return e;
       }
       return CB_OK;
     };

@@ -5,19 +5,18 @@
 namespace cb {
 
 int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
-                  double* result, double* scratch, const int* done);
+                  double* result, double* scratch, const int* done, bool use32 = false);
 
-template <int BS, bool WRITE_Y, bool DOT>
-__global__ void __launch_bounds__(SpmvCfg<BS>::THREADS)
+template <int BS, bool WRITE_Y, bool DOT, typename VT>
+__global__ void __launch_bounds__(SpmvCfg<BS, VT>::THREADS)
 k_spmv(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-       const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+       const VT* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
        const double* __restrict__ w, double* __restrict__ result, double* __restrict__ scratch,
-       const int* __restrict__ done) {
+       const int* __restrict__ done, const double* __restrict__ dscale, double alpha) {
   if (done && *done) return;
-  using C = SpmvCfg<BS>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[33];
-  const SpmvSmem<BS> sm = spmv_smem_init<BS>(smem_raw);
+  const SpmvSmem<BS, VT> sm = spmv_smem_init<BS, VT>(smem_raw);
   uint32_t phase = 0;
   const int R = spmv_rows_per_cta<BS>(G);
   const int64_t nrb = (nrows + R - 1) / R;
@@ -26,10 +25,11 @@ k_spmv(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32_t* 
     const int64_t row0 = rb * R;
     const int nr = (int)((nrows - row0 < R) ? (nrows - row0) : R);
     double acc;
-    const int64_t i = spmv_row_block<BS>(sm, rowptr, col, val, x, row0, nr, G, phase, acc);
+    const int64_t i = spmv_row_block<BS, VT>(sm, rowptr, col, val, x, row0, nr, G, phase, acc);
     if (i >= 0) {
+      if (dscale) acc *= alpha * dscale[i];      // power method: y = alpha D^-1 A x ...
       if (WRITE_Y) y[i] = acc;
-      if (DOT) local += acc * w[i];
+      if (DOT) local += acc * (w ? w[i] : acc);  // ... with |y|^2 (w == NULL)
     }
   }
   if (DOT) {
@@ -85,9 +85,9 @@ k_diag_inv(int64_t nrows, int bs, const int64_t* __restrict__ rowptr, const int3
   }
 }
 
-template <int BS>
+template <int BS, typename VT>
 int spmv_grid(int64_t nrows, int G) {
-  using C = SpmvCfg<BS>;
+  using C = SpmvCfg<BS, VT>;
   const int R = spmv_rows_per_cta<BS>(G);
   const int64_t nrb = (nrows + R - 1) / R;
   int64_t cap = (int64_t)num_sms() * C::CTAS_PER_SM;
@@ -102,25 +102,25 @@ int prefer_smem(K kernel) {
   return CB_OK;
 }
 
-template <int BS>
-int launch_spmv(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
-                double* result, double* scratch, const int* done) {
-  using C = SpmvCfg<BS>;
+template <int BS, typename VT>
+int launch_spmv(cudaStream_t s, const cb_mat* A, const VT* val, const double* x, double* y, const double* w,
+                double* result, double* scratch, const int* done, const double* dscale = nullptr, double alpha = 1.0) {
+  using C = SpmvCfg<BS, VT>;
   const int G = spmv_sanitize_split(A->row_split);
-  const int grid = spmv_grid<BS>(A->nrows, G);
+  const int grid = spmv_grid<BS, VT>(A->nrows, G);
   static bool configured = false;
   if (!configured) {
-    if (int e = prefer_smem(k_spmv<BS, true, false>)) return e;
-    if (int e = prefer_smem(k_spmv<BS, true, true>)) return e;
-    if (int e = prefer_smem(k_spmv<BS, false, true>)) return e;
+    if (int e = prefer_smem(k_spmv<BS, true, false, VT>)) return e;
+    if (int e = prefer_smem(k_spmv<BS, true, true, VT>)) return e;
+    if (int e = prefer_smem(k_spmv<BS, false, true, VT>)) return e;
     configured = true;
   }
-  if (y && !w)
-    k_spmv<BS, true, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, A->val, x, y, nullptr, nullptr, nullptr, done);
-  else if (y && w)
-    k_spmv<BS, true, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, A->val, x, y, w, result, scratch, done);
+  if (y && !w && !result)
+    k_spmv<BS, true, false, VT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, val, x, y, nullptr, nullptr, nullptr, done, dscale, alpha);
+  else if (y)
+    k_spmv<BS, true, true, VT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, val, x, y, w, result, scratch, done, dscale, alpha);
   else
-    k_spmv<BS, false, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, A->val, x, nullptr, w, result, scratch, done);
+    k_spmv<BS, false, true, VT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, val, x, nullptr, w, result, scratch, done, dscale, alpha);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
@@ -133,16 +133,43 @@ int diag_inv_launch(cudaStream_t s, const cb_mat* A, double* dinv, double* lmax,
   return CB_OK;
 }
 
+// use32: read the fp32 copy of the values when the matrix carries one (preconditioner passes)
 int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
-                  double* result, double* scratch, const int* done) {
+                  double* result, double* scratch, const int* done, bool use32) {
   CB_REQUIRE(A && A->rowptr && A->col && A->val && x, "cb_spmv: missing argument");
+  if (use32 && A->val32) {
+    switch (A->bs) {
+      case 1: return launch_spmv<1, float>(s, A, A->val32, x, y, w, result, scratch, done);
+      case 2: return launch_spmv<2, float>(s, A, A->val32, x, y, w, result, scratch, done);
+      case 3: return launch_spmv<3, float>(s, A, A->val32, x, y, w, result, scratch, done);
+    }
+  }
   switch (A->bs) {
-    case 1: return launch_spmv<1>(s, A, x, y, w, result, scratch, done);
-    case 2: return launch_spmv<2>(s, A, x, y, w, result, scratch, done);
-    case 3: return launch_spmv<3>(s, A, x, y, w, result, scratch, done);
+    case 1: return launch_spmv<1, double>(s, A, A->val, x, y, w, result, scratch, done);
+    case 2: return launch_spmv<2, double>(s, A, A->val, x, y, w, result, scratch, done);
+    case 3: return launch_spmv<3, double>(s, A, A->val, x, y, w, result, scratch, done);
   }
   set_error("cb_spmv: unsupported block size %d", A->bs);
   return CB_ERR_UNSUPPORTED;
+}
+
+// dst = (float) src
+__global__ void __launch_bounds__(256)
+k_to_f32(int64_t n, const double* __restrict__ src, float* __restrict__ dst) {
+  const int64_t n2 = n >> 1;
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+  float2* d2 = reinterpret_cast<float2*>(dst);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 v = s2[i];
+    d2[i] = make_float2((float)v.x, (float)v.y);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[n - 1] = (float)src[n - 1];
+}
+
+int to_f32_launch(cudaStream_t s, int64_t n, const double* src, float* dst) {
+  k_to_f32<<<grid_for(n / 2 + 1, 256, 8), 256, 0, s>>>(n, src, dst);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
 }
 
 }  // namespace cb
@@ -156,11 +183,45 @@ extern "C" int cb_spmv(void* stream, const cb_mat* A, const double* x, double* y
   return spmv_dispatch(as_stream(stream), A, x, y, nullptr, nullptr, nullptr, nullptr);
 }
 
+extern "C" int cb_spmv_f32(void* stream, const cb_mat* A, const double* x, double* y) {
+  CB_REQUIRE(y != nullptr && A && A->val32, "cb_spmv_f32: y or A->val32 is NULL");
+  return spmv_dispatch(as_stream(stream), A, x, y, nullptr, nullptr, nullptr, nullptr, /*use32=*/true);
+}
+
+// One step of the power method for lambda_max(D^-1 A): y = alpha * dinv .* (A x), *norm2_dev = |y|^2 (this rank's rows).
+extern "C" int cb_power_step(void* stream, const cb_mat* A, const double* dinv, double alpha, const double* x, double* y,
+                             double* norm2_dev, double* scratch, int64_t scratch_len, int use32) {
+  CB_REQUIRE(A && dinv && x && y && norm2_dev, "cb_power_step: missing argument");
+  CB_REQUIRE(scratch && scratch_len >= RED_SCRATCH_LEN, "cb_power_step: scratch too small");
+  cudaStream_t s = as_stream(stream);
+  if (use32 && A->val32) {
+    switch (A->bs) {
+      case 1: return launch_spmv<1, float>(s, A, A->val32, x, y, nullptr, norm2_dev, scratch, nullptr, dinv, alpha);
+      case 2: return launch_spmv<2, float>(s, A, A->val32, x, y, nullptr, norm2_dev, scratch, nullptr, dinv, alpha);
+      case 3: return launch_spmv<3, float>(s, A, A->val32, x, y, nullptr, norm2_dev, scratch, nullptr, dinv, alpha);
+    }
+  }
+  switch (A->bs) {
+    case 1: return launch_spmv<1, double>(s, A, A->val, x, y, nullptr, norm2_dev, scratch, nullptr, dinv, alpha);
+    case 2: return launch_spmv<2, double>(s, A, A->val, x, y, nullptr, norm2_dev, scratch, nullptr, dinv, alpha);
+    case 3: return launch_spmv<3, double>(s, A, A->val, x, y, nullptr, norm2_dev, scratch, nullptr, dinv, alpha);
+  }
+  set_error("cb_power_step: unsupported block size %d", A->bs);
+  return CB_ERR_UNSUPPORTED;
+}
+
 extern "C" int cb_scalar_product(void* stream, const cb_mat* A, const double* x, const double* y,
                                  double* result_dev, double* scratch, int64_t scratch_len) {
   CB_REQUIRE(scratch && scratch_len >= RED_SCRATCH_LEN, "cb_scalar_product: scratch too small");
   CB_REQUIRE(y && result_dev, "cb_scalar_product: missing argument");
   return spmv_dispatch(as_stream(stream), A, x, nullptr, y, result_dev, scratch, nullptr);
+}
+
+extern "C" int cb_to_f32(void* stream, int64_t n, const double* src, float* dst) {
+  CB_REQUIRE(src && dst && n >= 0, "cb_to_f32: missing argument");
+  CB_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+             "cb_to_f32: src must be 16-byte and dst 8-byte aligned");
+  return to_f32_launch(as_stream(stream), n, src, dst);
 }
 
 extern "C" int cb_dot(void* stream, int64_t n, const double* x, const double* y, double* result_dev,

@@ -17,7 +17,10 @@
 
 namespace cb {
 
-template <int BS>
+// VT is the storage type of the matrix values: double for operators the Krylov method itself applies, float for
+// the copies the preconditioner reads (cb_mat.val32: half the bytes per pass; the products and sums are fp64
+// either way, so a V-cycle over rounded entries is still a fixed linear operator).
+template <int BS, typename VT = double>
 struct SpmvCfg {
   static constexpr int ROWS_PER_WARP = 32 / BS;           // 32, 16, 10 (2 idle lanes for BS = 3)
 #ifndef CB_SPMV_WARPS3
@@ -35,6 +38,13 @@ struct SpmvCfg {
 #ifndef CB_SPMV_TILE
 #define CB_SPMV_TILE 16
 #endif
+// float tiles are half as large, so twice as many CTAs keep the same number of bytes in flight per SM
+#ifndef CB_SPMV_CTAS3_F32
+#define CB_SPMV_CTAS3_F32 16
+#endif
+#ifndef CB_SPMV_CTAS1_F32
+#define CB_SPMV_CTAS1_F32 10
+#endif
   // many small CTAs beat few large ones: every CTA is one independent bulk-copy stream, and the
   // DRAM pipe wants ~9 x 24 KB in flight per SM (measured: 4 x 47 KB -> 5.3 TB/s, 9 x 24 KB -> 6.0 TB/s)
   static constexpr int WARPS = (BS == 3) ? CB_SPMV_WARPS3 : (BS == 1 ? CB_SPMV_WARPS1 : 4);
@@ -42,10 +52,13 @@ struct SpmvCfg {
   static constexpr int R = ROWS_PER_WARP * WARPS;          // block rows per CTA: 128, 64, 40
   static constexpr int T = CB_SPMV_TILE * R;               // tile capacity in blocks
   static constexpr int BB = BS * BS;
-  static constexpr int VAL_DOUBLES = T * BB + 2;           // +2: 16-byte alignment slack (head)
+  static constexpr bool F32 = sizeof(VT) == 4;
+  static constexpr int EPB = 16 / (int)sizeof(VT);         // values per 16-byte bulk-copy granule
+  static constexpr int VAL_ELEMS = T * BB + EPB;           // + alignment slack (head)
   static constexpr int COL_INTS = T + 8;                   // +8: alignment slack (head up to 3)
-  static constexpr size_t SMEM_BYTES = sizeof(double) * VAL_DOUBLES + sizeof(int32_t) * COL_INTS + 16;
-  static constexpr int CTAS_PER_SM = (BS == 3) ? CB_SPMV_CTAS3 : (BS == 2 ? 5 : CB_SPMV_CTAS1);
+  static constexpr size_t SMEM_BYTES = sizeof(VT) * VAL_ELEMS + sizeof(int32_t) * COL_INTS + 16;
+  static constexpr int CTAS_PER_SM = F32 ? ((BS == 3) ? CB_SPMV_CTAS3_F32 : (BS == 2 ? 8 : CB_SPMV_CTAS1_F32))
+                                         : ((BS == 3) ? CB_SPMV_CTAS3 : (BS == 2 ? 5 : CB_SPMV_CTAS1));
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -80,23 +93,23 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Per-CTA state for the streaming SpMV (dynamic shared memory carve-up).
-template <int BS>
+template <int BS, typename VT = double>
 struct SpmvSmem {
-  double* val;
+  VT* val;
   int32_t* col;
   uint64_t* bar;
   __device__ __forceinline__ explicit SpmvSmem(unsigned char* base) {
-    using C = SpmvCfg<BS>;
-    val = reinterpret_cast<double*>(base);
-    col = reinterpret_cast<int32_t*>(base + sizeof(double) * C::VAL_DOUBLES);
-    bar = reinterpret_cast<uint64_t*>(base + sizeof(double) * C::VAL_DOUBLES + sizeof(int32_t) * C::COL_INTS);
+    using C = SpmvCfg<BS, VT>;
+    val = reinterpret_cast<VT*>(base);
+    col = reinterpret_cast<int32_t*>(base + sizeof(VT) * C::VAL_ELEMS);
+    bar = reinterpret_cast<uint64_t*>(base + sizeof(VT) * C::VAL_ELEMS + sizeof(int32_t) * C::COL_INTS);
   }
 };
 
 // One-time per-CTA setup: carve dynamic shared memory, initialise the mbarrier.
-template <int BS>
-__device__ __forceinline__ SpmvSmem<BS> spmv_smem_init(unsigned char* base) {
-  SpmvSmem<BS> sm(base);
+template <int BS, typename VT = double>
+__device__ __forceinline__ SpmvSmem<BS, VT> spmv_smem_init(unsigned char* base) {
+  SpmvSmem<BS, VT> sm(base);
   if (threadIdx.x == 0) {
     mbar_init(sm.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -111,26 +124,28 @@ __device__ __forceinline__ SpmvSmem<BS> spmv_smem_init(unsigned char* base) {
 // double, three ints each side) are moved with plain loads by the same thread before it
 // arrives on the barrier (arrive = release, so waiters see them).  Returns nothing; the
 // element offsets (val_head, col_head) are recomputed by every thread with tile_heads().
-template <int BS>
-__device__ __forceinline__ void issue_tile(const SpmvSmem<BS>& sm, const double* __restrict__ val,
+template <int BS, typename VT>
+__device__ __forceinline__ void issue_tile(const SpmvSmem<BS, VT>& sm, const VT* __restrict__ val,
                                            const int32_t* __restrict__ col, int64_t s, int nblk) {
   constexpr int BB = BS * BS;
-  const double* vsrc = val + s * BB;
+  constexpr int EPB = 16 / (int)sizeof(VT);
+  const VT* vsrc = val + s * BB;
   const int32_t* csrc = col + s;
-  const int vhead = (int)((reinterpret_cast<uintptr_t>(vsrc) & 15) >> 3);  // 0 or 1 doubles
-  const int chead = (int)((reinterpret_cast<uintptr_t>(csrc) & 15) >> 2);  // 0..3 ints
+  const int vhead = (int)((reinterpret_cast<uintptr_t>(vsrc) & 15) / sizeof(VT));  // 0..EPB-1 values
+  const int chead = (int)((reinterpret_cast<uintptr_t>(csrc) & 15) >> 2);          // 0..3 ints
   const int nv = nblk * BB, ncol = nblk;
   // aligned interior in elements relative to the tile start
-  const int vb = vhead ? 1 : 0;                    // first element at a 16-byte boundary
-  const int ve = vb + ((nv - vb) & ~1);            // multiple of 2 doubles
+  const int vb0 = vhead ? (EPB - vhead) : 0;       // first element at a 16-byte boundary
+  const int vb = vb0 < nv ? vb0 : nv;
+  const int ve = vb + ((nv - vb) & ~(EPB - 1));    // whole granules
   const int cb = chead ? (4 - chead) : 0;
   const int cbeg = cb < ncol ? cb : ncol;
   const int cend = cbeg + ((ncol - cbeg) & ~3);
   uint32_t bytes = 0;
   fence_proxy_async();
   if (ve > vb) {
-    bulk_g2s(sm.val + vhead + vb, vsrc + vb, (uint32_t)(ve - vb) * 8u, sm.bar);
-    bytes += (uint32_t)(ve - vb) * 8u;
+    bulk_g2s(sm.val + vhead + vb, vsrc + vb, (uint32_t)(ve - vb) * (uint32_t)sizeof(VT), sm.bar);
+    bytes += (uint32_t)(ve - vb) * (uint32_t)sizeof(VT);
   }
   if (cend > cbeg) {
     bulk_g2s(sm.col + chead + cbeg, csrc + cbeg, (uint32_t)(cend - cbeg) * 4u, sm.bar);
@@ -156,13 +171,13 @@ __host__ __device__ __forceinline__ int spmv_sanitize_split(int g) { return g >=
 // g == 0 lanes hold in `acc_out` the result for scalar row (row0 + warp*rpw + r)*BS + j, which
 // is returned (-1 for all other lanes).  `phase` is the CTA's mbarrier parity (in/out).  All
 // threads of the CTA must call this together.
-template <int BS>
-__device__ __forceinline__ int64_t spmv_row_block(const SpmvSmem<BS>& sm, const int64_t* __restrict__ rowptr,
+template <int BS, typename VT>
+__device__ __forceinline__ int64_t spmv_row_block(const SpmvSmem<BS, VT>& sm, const int64_t* __restrict__ rowptr,
                                                   const int32_t* __restrict__ col,
-                                                  const double* __restrict__ val,
+                                                  const VT* __restrict__ val,
                                                   const double* __restrict__ x, int64_t row0, int nr, int G,
                                                   uint32_t& phase, double& acc_out) {
-  using C = SpmvCfg<BS>;
+  using C = SpmvCfg<BS, VT>;
   constexpr int BB = BS * BS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rpw = 32 / (BS * G);
@@ -178,22 +193,22 @@ __device__ __forceinline__ int64_t spmv_row_block(const SpmvSmem<BS>& sm, const 
   for (int i = 0; i < BS; ++i) acc[i] = 0.0;
   for (int64_t s = k0; s < k1; s += C::T) {
     const int nblk = (int)((k1 - s < C::T) ? (k1 - s) : C::T);
-    if (tid == 0) issue_tile<BS>(sm, val, col, s, nblk);
-    const int vhead = (int)((reinterpret_cast<uintptr_t>(val + s * BB) & 15) >> 3);
+    if (tid == 0) issue_tile<BS, VT>(sm, val, col, s, nblk);
+    const int vhead = (int)((reinterpret_cast<uintptr_t>(val + s * BB) & 15) / sizeof(VT));
     const int chead = (int)((reinterpret_cast<uintptr_t>(col + s) & 15) >> 2);
     mbar_wait(sm.bar, phase);
     phase ^= 1u;
     if (active) {
       const int b = (int)((rb > s ? rb : s) - s);
       const int e = (int)((re < s + nblk ? re : s + nblk) - s);
-      const double* sv = sm.val + vhead;
+      const VT* sv = sm.val + vhead;
       const int32_t* sc = sm.col + chead;
 #pragma unroll 4
       for (int k = b + g; k < e; k += G) {
         const int32_t c = sc[k];
         const double xv = __ldg(x + (int64_t)c * BS + j);
 #pragma unroll
-        for (int i = 0; i < BS; ++i) acc[i] = fma(sv[k * BB + i * BS + j], xv, acc[i]);
+        for (int i = 0; i < BS; ++i) acc[i] = fma((double)sv[k * BB + i * BS + j], xv, acc[i]);
       }
     }
     __syncthreads();  // the tile is consumed: the next bulk copy may overwrite it

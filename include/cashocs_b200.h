@@ -48,6 +48,10 @@ extern "C" {
 
 const char* cb_last_error(void);
 int cb_version(void);
+/* sizeof() of a header struct inside the compiled library: 0 cb_poly, 1 cb_quad, 2 cb_mat, 3 cb_mesh_view,
+ * 4 cb_ksp_opts, 5 cb_amg_level, 6 cb_amg, 7 cb_ksp_result, 8 cb_p2_view; -1 otherwise.  Bindings compare their
+ * mirrors with it at load time. */
+int64_t cb_struct_size(int which);
 /* Number of SMs of the current device (grid sizing); <0 on error. */
 int cb_num_sms(void);
 /* Total number of CUDA kernels this library has launched in this process (monotonic). */
@@ -221,10 +225,23 @@ typedef struct {
   const int64_t* rowptr;  /* [nrows+1] */
   const int32_t* col;     /* [nnzb] */
   const double* val;      /* [nnzb*bs*bs] */
+  const float* val32;     /* nullable: fp32 copy of val (cb_to_f32).  Read ONLY by preconditioner passes (AMG smoothers,
+                           * residuals and the A*P post-smoothing inside cb_ksp_solve): half the bytes per pass, products
+                           * and sums stay fp64.  The Krylov method's own operator is always `val`. */
 } cb_mat;
 
 /* y = A x  (PETSc Mat.mult; cashocs/_forms/shape_form_handler.py:776-777). */
 int cb_spmv(void* stream, const cb_mat* A, const double* x, double* y);
+/* y = A32 x with the fp32 copy of the values (A->val32 must be set): the pass the AMG V-cycle runs.  x, y, products
+ * and sums are fp64, so the result equals cb_spmv on the rounded matrix bit for bit. */
+int cb_spmv_f32(void* stream, const cb_mat* A, const double* x, double* y);
+/* One step of the power method on D^-1 A (AMG numeric phase: lambda_max for the Chebyshev smoothers and the prolongator
+ * damping): y = alpha * dinv .* (A x) and *norm2_dev = |y|^2 over this rank's rows, one fused pass (use32 != 0: over
+ * A->val32 when present). */
+int cb_power_step(void* stream, const cb_mat* A, const double* dinv, double alpha, const double* x, double* y,
+                  double* norm2_dev, double* scratch, int64_t scratch_len, int use32);
+/* dst = (float) src, element-wise (fills cb_mat.val32). */
+int cb_to_f32(void* stream, int64_t n, const double* src, float* dst);
 /* result (device double) = y^T A x without materialising A x
  * (ShapeFormHandler.scalar_product, cashocs/_forms/shape_form_handler.py:748-780). */
 int cb_scalar_product(void* stream, const cb_mat* A, const double* x, const double* y,
@@ -294,6 +311,8 @@ typedef struct {
                              * the blocks of P, pt_val the TRANSPOSED blocks in P^T's entry order; 0: scalar P (x) I */
   double smooth_ratio;      /* smoother interval [lmax/ratio, lmax] */
   double coarse_ratio;
+  int32_t level_smooth_degree; /* > 0: Chebyshev degree of the smoothers of the levels >= 1 (0: smooth_degree) */
+  int32_t pad3;
   const cb_amg_level* levels; /* host array */
   const double* coarse_inv;   /* dense inverse of the last level's operator (nullable) */
 } cb_amg;
@@ -344,7 +363,19 @@ typedef struct {
   const double* rbm_coords;
   const double* rbm_einv;
   double* rbm_work;
+  int32_t flexible;       /* 1: Polak-Ribiere beta = z_new.(r_new - r_old) / z_old.r_old (PETSc KSPFCG with mmax = 1): equal to
+                           * the Fletcher-Reeves beta for a fixed symmetric preconditioner, keeps PCG converging at the unperturbed
+                           * rate when the preconditioner is only symmetric to fp32 round-off (mixed-precision AMG) */
+  int32_t pad2;
 } cb_ksp_opts;
+/* Set-up of that correction for one matrix version, all on the device.  cb_rbm_galerkin: c_out [ncols, bs] = coords -
+ * centre (centre: HOST array of bs doubles, the same on all ranks; any fixed point spans the same modes), then row j of
+ * G_dev [k, k] = Z^T (A z_j) over this rank's rows (k launches of the SpMV; sum G over the ranks before inverting; G is
+ * symmetric, so rows = columns).  v_work [ncols*bs] and w_work [nrows*bs] are scratch vectors.  cb_rbm_invert: einv = G^-1
+ * (k <= 6, one small kernel).  rbm_coords of cb_ksp_opts is c_out (its first nrows nodes). */
+int cb_rbm_galerkin(void* stream, const cb_mat* A, const double* coords, const double* centre, double* c_out,
+                    double* v_work, double* w_work, double* G_dev, double* scratch, int64_t scratch_len);
+int cb_rbm_invert(void* stream, int k, const double* G_dev, double* einv_dev);
 typedef struct {
   int32_t reason;
   int32_t its;

@@ -425,8 +425,6 @@ class PoissonShapeProblem:
         return success
 
     def intersection_test(self):
-        if self.nv > 5000:  # brute force oracle is O(Nv*Nc); a-priori test already rules out inversion
-            return True
         return quality.intersection_test(self.coords, self.cells)
 
     def revert_transformation(self):

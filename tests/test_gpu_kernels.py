@@ -167,6 +167,25 @@ def test_spmv_and_scalar_product(kind):
     assert abs(E.scalar_product(torch.from_numpy(xv).cuda(), torch.from_numpy(yv).cuda()) - sp0) < 1e-13 * abs(sp0)
 
 
+@pytest.mark.parametrize("kind", ["sq8", "cube4", "circle", "mesh3d"])
+def test_fp32_value_pass_equals_fp64_pass_on_the_rounded_matrix(kind):
+    """cb_spmv_f32 (the pass the mixed-precision V-cycle runs over cb_mat.val32): values are stored in fp32, products
+    and sums are fp64 in the same order as cb_spmv, so it equals cb_spmv on the rounded matrix bit for bit and the
+    exact product to fp32 round-off of the entries."""
+    dm = device_mesh(kind)
+    r = np.random.RandomState(5)
+    A, _ = linalg.assemble_scalar_system(dm, 1.0, 1.0, rhs=False)
+    E = linalg.assemble_elasticity_matrix(dm, torch.ones(dm.num_vertices, dtype=torch.float64, device="cuda"), 1.4, 0.2)
+    for M in (A, E):
+        x = torch.from_numpy(r.rand(M.ncols * M.bs)).cuda()
+        y32 = M.mult_f32(x)
+        rounded = linalg.Matrix(dm, M.bs, val=M.val.to(torch.float32).to(torch.float64))
+        assert torch.equal(y32, rounded.mult(x))
+        y64 = M.mult(x)
+        assert float((y32 - y64).abs().max()) <= 1e-6 * float(y64.abs().max())
+        assert float((y32 - y64).abs().max()) > 0.0
+
+
 def _poisson_system(kind):
     om, dm = oracle_mesh(kind), device_mesh(kind)
     markers = [1] if kind == "circle" else [1, 2, 3, 4]

@@ -86,6 +86,40 @@ def test_shape_gradient_matches_oracle_cube_with_mu_problem(n):
     assert np.all(g1[fix] == 0.0)
 
 
+@pytest.mark.parametrize("n", [16, 32])
+@pytest.mark.parametrize("variant", ["homogeneous", "mu_poisson"])
+def test_parity_at_the_benchmarked_solver_settings(n, variant):
+    """The solver settings `bench.py` times (cg + `pc_type hypre` -> device smoothed-aggregation AMG with its defaults:
+    mixed-precision cycle, rigid-body coarse correction, flexible beta; `ksp_rtol` 1e-10 on the preconditioned norm) at
+    BASELINE.md's parity sizes n = 16, 32 on the unit cube: state, adjoint, Lame mu and shape gradient against the
+    oracle solved tight (rtol 1e-14), <= 1e-8 relative -- north_star's "solutions and shape gradients within 1e-8
+    relative at matched KSP rtol".  `mu_poisson` is the variant with the auxiliary mu solve
+    (`shape_form_handler.py:113-120,188-235`: mu_def = 5e2, mu_fix = 1)."""
+    import bench
+
+    ksp = dict(bench.KSP)
+    dm = cb.regular_mesh(n, 1.0, 1.0, 1.0)
+    om = meshes.regular_mesh(n, 1.0, 1.0, 1.0)
+    all_m = (1, 2, 3, 4, 5, 6)
+    if variant == "homogeneous":
+        cfg = sop_config(shape_bdry_def="[1, 2, 3, 4, 5, 6]")
+        ocfg = pipeline.ShapeConfig(shape_bdry_def=all_m)
+    else:
+        cfg = sop_config(shape_bdry_def="[2]", shape_bdry_fix="[1, 3, 4, 5, 6]", mu_def=5e2, mu_fix=1.0)
+        ocfg = pipeline.ShapeConfig(shape_bdry_def=(2,), shape_bdry_fix=(1, 3, 4, 5, 6), mu_def=5e2, mu_fix=1.0)
+    sop = make_sop(dm, cfg, bc_markers=all_m, ksp=ksp)
+    tight = {"ksp_type": "cg", "pc_type": "hypre", "ksp_rtol": 1e-14, "ksp_atol": 1e-30, "ksp_max_it": 20000}
+    prob = pipeline.PoissonShapeProblem(om, bc_markers=all_m, config=ocfg, state_ksp=tight, adjoint_ksp=tight,
+                                        gradient_ksp=tight)
+    g0 = prob.compute_shape_gradient()
+    g1 = sop.compute_shape_gradient()[0].vector.cpu().numpy()
+    errs = dict(u=rel(sop.states[0].vector.cpu().numpy(), prob.u), p=rel(sop.adjoints[0].vector.cpu().numpy(), prob.p),
+                mu=rel(sop.form_handler.mu_lame.vector.cpu().numpy(), prob.mu), g=rel(g1, g0))
+    print(f"parity n={n} {variant}: {errs} its {sop.state_problem.iterations} {sop.adjoint_problem.iterations} "
+          f"{sop.gradient_problem.iterations}")
+    assert max(errs.values()) < 1e-8, errs
+
+
 def test_taylor_test_rate():
     """tests/test_shape_optimization.py:302-318: rate > 1.9."""
     dm, _ = circle()

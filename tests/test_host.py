@@ -32,12 +32,19 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.cb_poly) == 8 + 8 * 24 + 3 * 24
     assert ctypes.sizeof(_lib.cb_quad) == 8 + 8 * 4 * 64 + 8 * 64
-    assert ctypes.sizeof(_lib.cb_mat) == 48
+    assert ctypes.sizeof(_lib.cb_mat) == 56
     assert ctypes.sizeof(_lib.cb_mesh_view) == 120
-    assert ctypes.sizeof(_lib.cb_ksp_opts) == 96
-    assert ctypes.sizeof(_lib.cb_amg_level) == 248
-    assert ctypes.sizeof(_lib.cb_amg) == 48
+    assert ctypes.sizeof(_lib.cb_ksp_opts) == 104
+    assert ctypes.sizeof(_lib.cb_amg_level) == 264
+    assert ctypes.sizeof(_lib.cb_amg) == 56
     assert ctypes.sizeof(_lib.cb_ksp_result) == 40
+    # ... and the ctypes mirrors agree with what the compiled library itself reports
+    lib = _lib.load()
+    mirrors = [_lib.cb_poly, _lib.cb_quad, _lib.cb_mat, _lib.cb_mesh_view, _lib.cb_ksp_opts, _lib.cb_amg_level, _lib.cb_amg,
+               _lib.cb_ksp_result, _lib.cb_p2_view]
+    for which, mirror in enumerate(mirrors):
+        assert lib.cb_struct_size(which) == ctypes.sizeof(mirror), (which, mirror.__name__)
+    assert lib.cb_struct_size(99) == -1
 
 
 def test_host_colouring_through_c_abi():

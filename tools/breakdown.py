@@ -38,7 +38,9 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--rbm", type=int, default=0, help="1: rigid-body coarse correction in the elasticity solve")
     ap.add_argument("--nullspace", default="translations")
+    ap.add_argument("--precision", default="mixed")
     args = ap.parse_args()
+    bench.KSP["pc_amg_precision"] = args.precision
     bench.GRADIENT_KSP_EXTRA["pc_amg_nullspace"] = args.nullspace
     bench.KSP["pc_type"] = args.pc
     bench.KSP["pc_amg_rigid_body_correction"] = bool(args.rbm)
@@ -55,12 +57,12 @@ def main():
             A, b = sop.state_problem.assemble(0)
         if args.pc == "hypre":
             with timer("amg numeric scalar"):
-                linalg.LinearSolver.amg_hierarchy(A, {})
+                linalg.LinearSolver.amg_hierarchy(A, bench.KSP)
             with timer("amg numeric elasticity"):
                 if args.nullspace == "rigid_body":
                     hE = linalg.LinearSolver.rbm_hierarchy(fh.scalar_product_matrix)
                 else:
-                    hE = linalg.LinearSolver.amg_hierarchy(fh.scalar_product_matrix, {})
+                    hE = linalg.LinearSolver.amg_hierarchy(fh.scalar_product_matrix, bench.KSP)
         with timer("state solve"):
             sop.state_problem.linear_solver.solve(sop.states[0].vector, A=A, b=b, ksp_options=sop.ksp_options[0])
         sop.state_problem.has_solution = True

@@ -37,7 +37,7 @@ for name, M in (("scalar", A), ("elasticity", E)):
             if rank == 0:
                 extra = ""
                 if pc == "gamg":
-                    h = [v for k, v in cb.LinearSolver._amg_cache.items() if isinstance(v, amg.AMGHierarchy) and v.bs == bs][-1]
+                    h = list(M._amg.values())[-1]
                     kinds = ["rep" if L.rep_dist is not None else ("dist" if L.dist is not None else "local") for L in h.levels]
                     extra = f" levels {h.sizes} {kinds} lmax {[round(D.lmax, 3) for D in h.data]}"
                 print(f"n={n} world={world} {name} {pc}: reason {res.reason} its {res.its}{extra}", flush=True)

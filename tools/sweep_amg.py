@@ -39,7 +39,7 @@ def main():
         dist, deg = int(parts[0]), int(parts[1])
         ratio = float(parts[2]) if len(parts) > 2 else 4.0
         amg.AMGSymbolic.DISTANCE = dist
-        linalg.LinearSolver._amg_cache.clear()
+        A.__dict__.pop("_amg", None); E.__dict__.pop("_amg", None)
         opts = dict(bench.KSP)
         opts.update({"pc_amg_smooth_degree": deg, "pc_amg_smooth_ratio": ratio})
         for rep in range(2):  # second repetition: symbolic cached, numeric redone
