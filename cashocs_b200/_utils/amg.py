@@ -347,8 +347,9 @@ class AMGHierarchy:
     """Values of the hierarchy for one block size; ``numeric(A)`` refreshes them for new matrix values."""
 
     def __init__(self, A, symbolic: AMGSymbolic | None = None, smooth_degree: int = 1, coarse_degree: int = 16,
-                 smooth_ratio: float = 10.0, coarse_ratio: float = 40.0, mixed: bool = True,
-                 level_smooth_degree: int = 0, mixed_mask=None) -> None:
+                 smooth_ratio: float = 20.0, coarse_ratio: float = 40.0, mixed: bool = True,
+                 level_smooth_degree: int = 0, mixed_mask=None, lambda_safety: float = 1.1,
+                 prolongator_damping: float = 1.6) -> None:
         self.bs = bs = A.bs
         # Mixed precision: the fine-level operator gets an fp32 copy of its values, which is what the residual pass
         # of the V-cycle streams (cb_mat.val32; vectors, products and sums stay fp64 -- see csrc/spmv.cuh).  Measured
@@ -361,6 +362,7 @@ class AMGHierarchy:
         self.device = dev = A.val.device
         self.smooth_degree, self.coarse_degree = int(smooth_degree), int(coarse_degree)
         self.level_smooth_degree = int(level_smooth_degree)
+        self.lambda_safety, self.prolongator_damping = float(lambda_safety), float(prolongator_damping)
         self.smooth_ratio, self.coarse_ratio = float(smooth_ratio), float(coarse_ratio)
         self.symbolic = symbolic if symbolic is not None else AMGSymbolic(A.rowptr, A.col, A.nrows, A.ncols,
                                                                          dist=A.mesh.dist)
@@ -493,7 +495,7 @@ class AMGHierarchy:
             lam = float("inf")
         st.alpha = 1.0 / n_last ** 0.5 if n_last > 0.0 else 1.0
         st.warm = True
-        return min(float(both[0]), 1.15 * lam)
+        return min(float(both[0]), self.lambda_safety * lam)
 
     def numeric(self, A) -> None:
         """Recompute prolongator values, Galerkin operators and smoother data for the values of ``A``."""
@@ -523,7 +525,7 @@ class AMGHierarchy:
                 D.s_dinv, lmax_s = D.dinv, D.lmax
             else:
                 lmax_s = self._diag_inv(ms, D.s_dinv, L, L.n)
-            omega = (4.0 / 3.0) / lmax_s
+            omega = self.prolongator_damping / lmax_s
             _lib.check(lib.cb_amg_smooth_prolongator(s, C.byref(ms), omega, _lib.ptr(L.agg), _lib.ptr(L.iface),
                                                      _lib.ptr(L.p_rowptr), _lib.ptr(L.p_col), _lib.ptr(D.p_val)),
                        "cb_amg_smooth_prolongator")

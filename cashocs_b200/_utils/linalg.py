@@ -61,7 +61,7 @@ _KSP_TYPES = {"cg": 0, "minres": 1, "preonly": 2}
 _PC_TYPES = {"none": 0, "jacobi": 1, "chebyshev": 2, "amg": 3}
 _IGNORED_KEYS = {
     "ksp_monitor", "ksp_monitor_true_residual", "ksp_converged_reason", "ksp_view",
-    "pc_jacobi_type", "ksp_norm_type", "ksp_initial_guess_nonzero", "mat_mumps_icntl_24",
+    "pc_jacobi_type", "mat_mumps_icntl_24",
     "pc_factor_mat_solver_type", "pc_hypre_type", "pc_hypre_boomeramg_strong_threshold",
     "ksp_cg_single_reduction",
 }
@@ -76,6 +76,19 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None, distr
     caller's tolerances; anything else that is unknown raises -- never a silent fallback.
     """
     opts = copy.deepcopy(direct_ksp_options) if ksp_options is None else dict(ksp_options)
+    # options whose semantics are fixed on the device: accepted only with the value that is implemented
+    # (zero initial guess, convergence test on the preconditioned residual norm) -- never silently dropped
+    if "ksp_initial_guess_nonzero" in opts:
+        v = opts.pop("ksp_initial_guess_nonzero")
+        if v is None or _truthy(v):
+            raise _exceptions.InputError("cashocs_b200.LinearSolver", "ksp_options",
+                                         "ksp_initial_guess_nonzero is not supported: cb_ksp_solve always starts from x = 0 "
+                                         "(as cashocs/_utils/linalg.py:480-546 does by default)")
+    if "ksp_norm_type" in opts:
+        v = str(opts.pop("ksp_norm_type")).casefold()
+        if v not in ("preconditioned", "default"):
+            raise _exceptions.InputError("cashocs_b200.LinearSolver", "ksp_options",
+                                         f"ksp_norm_type {v!r} is not supported: the device tests the preconditioned norm")
     ksp = str(opts.get("ksp_type", "gmres")).lower()
     pc = str(opts.get("pc_type", "none")).lower()
     flexible = opts.get("ksp_cg_flexible", None)
@@ -89,8 +102,6 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None, distr
         # algebraic multigrid -> the device smoothed-aggregation AMG (also on a partitioned mesh:
         # rank-local aggregates, tentative interface rows, per-level halo plans)
         pc = "amg"
-        if float(opts.get("ksp_rtol", 1e-5)) < 1e-14:
-            opts["ksp_rtol"] = 1e-14  # rtol 1e-16 / 1e-20 is below what fp64 round-off lets PCG reach
     if pc == "ksp":  # PETSc spelling of a polynomial preconditioner
         if str(opts.get("ksp_ksp_type", "")).lower() != "chebyshev":
             raise _exceptions.InputError("cashocs_b200.LinearSolver", "ksp_options", "pc_type ksp needs ksp_ksp_type chebyshev")
@@ -110,7 +121,8 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None, distr
              "pc_chebyshev_degree", "pc_chebyshev_ratio", "ksp_check_every", "ksp_ksp_type",
              "ksp_ksp_max_it", "ksp_pc_type", "ksp_profile_every", "ksp_use_graph", "pc_amg_smooth_degree",
              "pc_amg_coarse_degree", "pc_amg_smooth_ratio", "pc_amg_coarse_ratio", "pc_amg_min_coarse",
-             "pc_amg_rigid_body_correction", "pc_amg_nullspace", "pc_amg_precision", "ksp_cg_flexible", "pc_amg_level_smooth_degree",
+             "pc_amg_rigid_body_correction", "pc_amg_nullspace", "pc_amg_precision", "ksp_cg_flexible", "pc_amg_level_smooth_degree", "pc_amg_lambda_safety",
+             "pc_amg_prolongator_damping",
              "pc_gamg_type", "pc_gamg_agg_nsmooths"} | _IGNORED_KEYS
     unknown = set(opts) - known
     if unknown:
@@ -121,6 +133,8 @@ def parse_ksp_options(ksp_options: KspOption | None, rtol=None, atol=None, distr
     o.ksp_type = _KSP_TYPES[ksp]
     o.pc_type = _PC_TYPES[pc]
     o.rtol = float(opts.get("ksp_rtol", 1e-5)) if rtol is None else float(rtol)
+    if pc == "amg" and o.rtol < 1e-14:
+        o.rtol = 1e-14  # rtol 1e-16 / 1e-20 is below what fp64 round-off lets PCG reach (also for an explicit rtol argument)
     o.atol = float(opts.get("ksp_atol", 1e-50)) if atol is None else float(atol)
     o.dtol = float(opts.get("ksp_divtol", 1e5))
     o.max_it = int(opts.get("ksp_max_it", 10000))
@@ -452,12 +466,16 @@ class LinearSolver:
         if not (prec in ("mixed", "double") or prec.startswith("mixed:")):
             raise _exceptions.InputError("cashocs_b200.LinearSolver", "pc_amg_precision",
                                          "mixed, double or mixed:<a0|ap0|coarse joined by +>")
+        # Defaults from the sweeps on the 10 M-tet elasticity / Poisson systems (tools/sweep_precision.py, gpurun_out/r02_sweep*):
+        # smoother interval [lmax/20, lmax]; lmax = 1.1 x the (warm-started, hence converged) power-method estimate;
+        # prolongator damping 1.6 / lmax(D_S^-1 S) instead of the textbook 4/3 (89 -> 65 PCG iterations together).
         # levels >= 1 hold a tenth of the fine level's bytes: vector operators smooth them with degree 2 (measured on
         # the 10 M-tet elasticity solve: 89 -> 70 PCG iterations for 11 % more time per iteration); scalar ones gain
         # nothing (35 -> 33)
         lsd = int(options.get("pc_amg_level_smooth_degree", 2 if bs > 1 else 0))
         return (int(options.get("pc_amg_smooth_degree", 1)), int(options.get("pc_amg_coarse_degree", 16)),
-                float(options.get("pc_amg_smooth_ratio", 10.0)), float(options.get("pc_amg_coarse_ratio", 40.0)), prec, lsd)
+                float(options.get("pc_amg_smooth_ratio", 20.0)), float(options.get("pc_amg_coarse_ratio", 40.0)), prec, lsd,
+                float(options.get("pc_amg_lambda_safety", 1.1)), float(options.get("pc_amg_prolongator_damping", 1.6)))
 
     @classmethod
     def amg_hierarchy(cls, A: "Matrix", options: dict):
@@ -478,7 +496,8 @@ class LinearSolver:
             prec = key[4]
             h = amg.AMGHierarchy(A, sym, smooth_degree=key[0], coarse_degree=key[1], smooth_ratio=key[2],
                                  coarse_ratio=key[3], mixed=prec != "double", level_smooth_degree=key[5],
-                                 mixed_mask=set(prec[6:].split("+")) if prec.startswith("mixed:") else None)
+                                 mixed_mask=set(prec[6:].split("+")) if prec.startswith("mixed:") else None,
+                                 lambda_safety=key[6], prolongator_damping=key[7])
             cache[key] = h
         if h.version != A.version:
             h.numeric(A)

@@ -6,10 +6,11 @@
 // imported torch this is the torch-bundled NCCL -- so the library has no link-time
 // dependency and single-GPU use never touches NCCL.
 #include <dlfcn.h>
+#include <stdlib.h>
 
 #include <vector>
 
-#include "common.cuh"
+#include "p2p.cuh"
 
 namespace cb {
 
@@ -78,10 +79,14 @@ struct cb_dist {
   const int32_t* send_idx = nullptr;  // device
   int64_t n_owned = 0, n_ghost = 0;
   bool owns_comm = true;               // false for plans cloned from a parent (AMG coarse levels)
-  // ---- one-sided transport over NVLink peer memory (cb_dist_p2p_*), optional
-  // Window layout (doubles): [2 parities][ghost_cap] halo landing zone | [2][nranks][RED_W] reduction
-  // slots | uint64 flags: halo_flag[nranks], red_flag[nranks], ticket, error.
+  // ---- one-sided transport over NVLink peer memory (cb_dist_p2p_*), optional; window layout: p2p.cuh
   bool p2p = false;
+  // Error word of the communicator: pinned, mapped host memory owned by the root plan and shared by every plan cloned
+  // from it, so the host reads it without a copy or a synchronisation after any exchange.
+  unsigned long long* error_host = nullptr;
+  unsigned long long* error_dev = nullptr;
+  unsigned long long timeout_cycles = 0;
+  cb_dist* root = nullptr;                         // plan that owns communicator and error word (NULL: this one)
   unsigned char* window = nullptr;                 // my window (cudaMalloc, exported by IPC)
   std::vector<unsigned char*> peer_window;         // [nranks] mapped peer windows (self = window)
   int64_t ghost_cap = 0;                           // doubles per parity of the landing zone
@@ -110,168 +115,89 @@ __global__ void k_pack(int64_t n, const int32_t* __restrict__ idx, const double*
 int64_t dist_send_len(const cb_dist* d) { return d ? d->send_off.back() : 0; }
 bool dist_is_one_sided(const cb_dist* d);
 
-// ------------------------------------------------------------------ one-sided NVLink transport
-constexpr int RED_W = 8;  // doubles per reduction message
-// Every rank exports one cudaMalloc'ed window per halo plan through CUDA IPC; neighbours write their
-// boundary values straight into its landing zone with plain stores over NVLink (pack and transfer
-// are ONE kernel), then release a per-source flag holding the exchange epoch; the receiver's kernel
-// acquires the flags and copies the landing zone behind the owned part of the vector.  Landing zone
-// and reduction slots are double-buffered by epoch parity: a neighbour can be at most one exchange
-// ahead (it needs my next message to get further), so parity e+1 never overwrites data still read.
-// Window layout in doubles.  The header (flags, reduction slots) sits at FIXED offsets so a peer can
-// address it without knowing this rank's ghost count; the landing zone follows, its parity stride
-// (`ghost_cap`) is the RECEIVER's and is told to every sender at setup (d_remote_cap).
-struct WindowLayout {
-  int nranks;
-  __host__ __device__ int64_t flags_off() const { return 0; }                       // 2*nranks + 4 uint64
-  __host__ __device__ int64_t red_off() const { return 2LL * nranks + 4; }          // [2][nranks][RED_W]
-  __host__ __device__ int64_t land_off() const { return red_off() + 2LL * nranks * RED_W; }
-  __host__ __device__ int64_t total_doubles(int64_t ghost_cap) const { return land_off() + 2 * ghost_cap; }
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-// spin until *flag >= epoch; gives up after ~4e9 cycles (a dead peer must not hang the GPU)
-__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long epoch,
-                                          unsigned long long* error) {
-  const long long t0 = clock64();
-  while (ld_acquire_sys(flag) < epoch) {
-    if (*reinterpret_cast<volatile unsigned long long*>(error)) return false;  // an earlier wait already failed
-    if (clock64() - t0 > 2000000000LL) {
-      atomicExch(error, 1ULL);
-      return false;
-    }
-    __nanosleep(64);
-  }
-  return true;
-}
-
+// ------------------------------------------------------------------ one-sided NVLink transport (device side: p2p.cuh)
+// Halo exchange as ONE kernel.  Put phase: gather the boundary values and store them straight into the neighbours'
+// landing zones over NVLink; the last block to finish releases the per-source epoch flags.  Get phase: every block waits
+// for the neighbours' flags of this epoch and copies its share of the landing zone behind the owned part of x.  The
+// grid is at most 2 blocks per SM, so all blocks are co-resident and a block spinning on a flag cannot starve the
+// block that has to release ours.
 template <int BS>
 __global__ void __launch_bounds__(256)
-k_halo_put(int nneigh, const int64_t* __restrict__ send_off, const int64_t* __restrict__ remote_off,
-           const int32_t* __restrict__ neigh, const int32_t* __restrict__ send_idx,
-           const int64_t* __restrict__ remote_cap, const double* __restrict__ x,
-           unsigned char* const* __restrict__ peer_window, WindowLayout lay, int myrank,
-           unsigned char* my_window) {
+k_halo_exchange(int nneigh, const int64_t* __restrict__ send_off, const int64_t* __restrict__ remote_off,
+                const int32_t* __restrict__ neigh, const int32_t* __restrict__ send_idx,
+                const int64_t* __restrict__ remote_cap, const int64_t* __restrict__ recv_off, double* __restrict__ x,
+                int64_t n_owned, int64_t ghost_cap, P2PView v) {
   // the exchange epoch lives in the window (not in a kernel argument) so that a captured CUDA graph
-  // can replay the exchange: every thread reads it here, the last block bumps it at the end
-  unsigned long long* hdr = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(my_window) + lay.flags_off());
-  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(hdr + 2 * lay.nranks + 2) + 1ULL;
+  // can replay the exchange: every thread reads it here, the last block of the put phase bumps it
+  unsigned long long* hdr = window_header(v.window, v.lay);
+  const int nr = v.lay.nranks;
+  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(hdr + 2 * nr + 2) + 1ULL;
   const int64_t nsend = send_off[nneigh];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nsend * BS;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t v = i / BS;
-    const int c = (int)(i - v * BS);
+    const int64_t q = i / BS;
+    const int c = (int)(i - q * BS);
     int j = 0;
-    while (j + 1 < nneigh && v >= send_off[j + 1]) ++j;
-    double* dst = reinterpret_cast<double*>(peer_window[neigh[j]]) + lay.land_off() +
-                  (int64_t)(epoch & 1ULL) * remote_cap[j] + (remote_off[j] + (v - send_off[j])) * BS + c;
-    *dst = x[(int64_t)send_idx[v] * BS + c];
+    while (j + 1 < nneigh && q >= send_off[j + 1]) ++j;
+    double* dst = reinterpret_cast<double*>(v.peer_window[neigh[j]]) + v.lay.land_off() +
+                  (int64_t)(epoch & 1ULL) * remote_cap[j] + (remote_off[j] + (q - send_off[j])) * BS + c;
+    *dst = x[(int64_t)send_idx[q] * BS + c];
   }
   // the last block to finish releases the flags (all stores of all blocks are fenced before)
   __threadfence_system();
   __syncthreads();
   __shared__ bool last;
-  unsigned long long* flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(my_window) + lay.flags_off());
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(flags + 2 * lay.nranks);
-  if (threadIdx.x == 0) last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __shared__ int ok;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(hdr + 2 * nr);
+  if (threadIdx.x == 0) { last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1); ok = 1; }
   __syncthreads();
   if (last && threadIdx.x < nneigh) {
     __threadfence_system();
-    unsigned long long* pf = reinterpret_cast<unsigned long long*>(
-        reinterpret_cast<double*>(peer_window[neigh[threadIdx.x]]) + lay.flags_off());
-    st_release_sys(pf + myrank, epoch);
+    st_release_sys(window_header(v.peer_window[neigh[threadIdx.x]], v.lay) + v.rank, epoch);
   }
-  if (last && threadIdx.x == 0) hdr[2 * lay.nranks + 2] = epoch;
-}
-
-template <int BS>
-__global__ void __launch_bounds__(256)
-k_halo_get(int nneigh, const int64_t* __restrict__ recv_off, const int32_t* __restrict__ neigh,
-           double* __restrict__ x, int64_t n_owned, unsigned char* my_window, WindowLayout lay,
-           int64_t ghost_cap) {
-  unsigned long long* flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(my_window) + lay.flags_off());
-  unsigned long long* error = flags + 2 * lay.nranks + 1;
-  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(flags + 2 * lay.nranks + 2);
-  __shared__ int ok;
-  if (threadIdx.x == 0) ok = 1;
-  __syncthreads();
+  if (last && threadIdx.x == 0) hdr[2 * nr + 2] = epoch;
+  // get phase
   if (threadIdx.x < nneigh && recv_off[threadIdx.x + 1] > recv_off[threadIdx.x]) {
-    if (!wait_flag(flags + neigh[threadIdx.x], epoch, error)) ok = 0;
+    if (!wait_flag(hdr + neigh[threadIdx.x], epoch, v)) ok = 0;
   }
   __syncthreads();
   if (!ok) return;
-  const double* src = reinterpret_cast<const double*>(my_window) + lay.land_off() + (int64_t)(epoch & 1ULL) * ghost_cap;
+  const double* src = reinterpret_cast<const double*>(v.window) + v.lay.land_off() + (int64_t)(epoch & 1ULL) * ghost_cap;
   const int64_t n = recv_off[nneigh] * BS;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     x[n_owned * BS + i] = __ldcv(src + i);
 }
 
-// all-reduce of n <= RED_W doubles: every rank writes its message into every rank's slots, then sums
-// the nranks messages in rank order (bit-identical on all ranks, deterministic)
-__global__ void k_red_put(int n, const double* __restrict__ buf, unsigned char* const* __restrict__ peer_window,
-                          WindowLayout lay, int myrank, unsigned char* my_window) {
-  unsigned long long* hdr = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(my_window) + lay.flags_off());
-  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(hdr + 2 * lay.nranks + 3) + 1ULL;
-  __syncthreads();  // everybody has read the epoch before thread 0 bumps it
-  const int r = threadIdx.x;
-  if (r < lay.nranks) {
-    double* slots = reinterpret_cast<double*>(peer_window[r]) + lay.red_off() +
-                    ((int64_t)(epoch & 1ULL) * lay.nranks + myrank) * RED_W;
-    for (int i = 0; i < n; ++i) slots[i] = buf[i];
-    __threadfence_system();
-    unsigned long long* pf = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(peer_window[r]) + lay.flags_off());
-    st_release_sys(pf + lay.nranks + myrank, epoch);
-  }
-  if (threadIdx.x == 0) hdr[2 * lay.nranks + 3] = epoch;
+// all-reduce of n <= RED_W doubles as one kernel of one warp (p2p_allreduce_warp)
+__global__ void k_allreduce(int n, double* __restrict__ buf, P2PView v, int op) {
+  p2p_allreduce_warp(v, n, buf, op);
 }
 
-__global__ void k_red_get(int n, double* __restrict__ buf, unsigned char* my_window, WindowLayout lay, int op) {
-  unsigned long long* flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(my_window) + lay.flags_off());
-  unsigned long long* error = flags + 2 * lay.nranks + 1;
-  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(flags + 2 * lay.nranks + 3);
-  __shared__ int ok;
-  if (threadIdx.x == 0) ok = 1;
-  __syncthreads();
-  if (threadIdx.x < lay.nranks) {
-    if (!wait_flag(flags + lay.nranks + threadIdx.x, epoch, error)) ok = 0;
-  }
-  __syncthreads();
-  if (!ok) return;
-  const double* slots = reinterpret_cast<const double*>(my_window) + lay.red_off() +
-                        (int64_t)(epoch & 1ULL) * lay.nranks * RED_W;
-  if (threadIdx.x < n) {
-    double acc = __ldcv(slots + threadIdx.x);
-    for (int r = 1; r < lay.nranks; ++r) {
-      const double v = __ldcv(slots + (int64_t)r * RED_W + threadIdx.x);
-      acc = (op == 0) ? acc + v : red_combine(acc, v, op == 1 ? RED_MIN : RED_MAX);
-    }
-    buf[threadIdx.x] = acc;
-  }
+P2PView dist_p2p_view(const cb_dist* d) {
+  P2PView v;
+  v.peer_window = d->d_peer_window;
+  v.window = d->window;
+  v.error = d->error_dev;
+  v.timeout_cycles = d->timeout_cycles;
+  v.lay = WindowLayout{d->nranks};
+  v.rank = d->rank;
+  return v;
 }
 
 static int p2p_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs) {
   const int nneigh = (int)d->neigh.size();
-  const WindowLayout lay{d->nranks};
   const int64_t nsend = d->send_off.back(), nrecv = d->recv_off.back();
   if (nrecv * bs > d->ghost_cap) {
     set_error("p2p halo exchange: landing zone too small");
     return CB_ERR_ARG;
   }
-  const int pgrid = grid_for(nsend * bs > 0 ? nsend * bs : 1, 256, 2);
-  const int ggrid = grid_for(nrecv * bs > 0 ? nrecv * bs : 1, 256, 2);
-#define CB_HALO(BS)                                                                                          \
-  k_halo_put<BS><<<pgrid, 256, 0, s>>>(nneigh, d->d_send_off, d->d_remote_off, d->d_neigh, d->send_idx,      \
-                                       d->d_remote_cap, x, d->d_peer_window, lay, d->rank, d->window);        \
-  CB_LAUNCH_CHECK();                                                                                         \
-  k_halo_get<BS><<<ggrid, 256, 0, s>>>(nneigh, d->d_recv_off, d->d_neigh, x, d->n_owned, d->window, lay,     \
-                                       d->ghost_cap);                                                        \
+  if (nneigh > 256) { set_error("p2p halo exchange: more than 256 neighbours"); return CB_ERR_ARG; }
+  const int64_t work = (nsend > nrecv ? nsend : nrecv) * bs;
+  const int grid = grid_for(work > 0 ? work : 1, 256, 2);
+  const P2PView v = dist_p2p_view(d);
+#define CB_HALO(BS)                                                                                              \
+  k_halo_exchange<BS><<<grid, 256, 0, s>>>(nneigh, d->d_send_off, d->d_remote_off, d->d_neigh, d->send_idx,       \
+                                           d->d_remote_cap, d->d_recv_off, x, d->n_owned, d->ghost_cap, v);      \
   CB_LAUNCH_CHECK();
   if (bs == 1) { CB_HALO(1) } else if (bs == 2) { CB_HALO(2) } else { CB_HALO(3) }
 #undef CB_HALO
@@ -279,10 +205,7 @@ static int p2p_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs) {
 }
 
 static int p2p_allreduce(cudaStream_t s, cb_dist* d, double* buf, int n, int op) {
-  const WindowLayout lay{d->nranks};
-  k_red_put<<<1, 32, 0, s>>>(n, buf, d->d_peer_window, lay, d->rank, d->window);
-  CB_LAUNCH_CHECK();
-  k_red_get<<<1, 32, 0, s>>>(n, buf, d->window, lay, op);
+  k_allreduce<<<1, 32, 0, s>>>(n, buf, dist_p2p_view(d), op);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
@@ -324,6 +247,25 @@ int dist_allreduce_sum(cudaStream_t s, cb_dist* d, double* buf, int n) {
 
 using namespace cb;
 
+// The communicator's error word (pinned + mapped: device kernels raise it, the host polls it for free) and the wait
+// limit of the one-sided kernels: CASHOCS_B200_P2P_TIMEOUT_S seconds (default 60) of SM clock.
+static int dist_init_error_word(cb_dist* d) {
+  CB_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&d->error_host), sizeof(unsigned long long), cudaHostAllocMapped));
+  *d->error_host = 0ULL;
+  CB_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d->error_dev), d->error_host, 0));
+  double seconds = 60.0;
+  if (const char* env = getenv("CASHOCS_B200_P2P_TIMEOUT_S")) {
+    const double v = atof(env);
+    if (v > 0.0) seconds = v;
+  }
+  int dev = 0, khz = 0;
+  CB_CUDA_CHECK(cudaGetDevice(&dev));
+  CB_CUDA_CHECK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+  if (khz <= 0) khz = 1965000;
+  d->timeout_cycles = (unsigned long long)(seconds * 1e3 * (double)khz);
+  return CB_OK;
+}
+
 extern "C" int cb_dist_unique_id(char* id128) {
   if (int e = load_nccl()) return e;
   ncclUniqueId id;
@@ -355,6 +297,7 @@ extern "C" int cb_dist_create(cb_dist** out, const char* id128, int rank, int nr
     delete d;
     return CB_ERR_NCCL;
   }
+  if (int e = dist_init_error_word(d)) { delete d; return e; }
   *out = d;
   return CB_OK;
 }
@@ -366,6 +309,10 @@ extern "C" int cb_dist_clone_plan(cb_dist* parent, cb_dist** out, int nneigh, co
   cb_dist* d = new cb_dist();
   d->comm = parent->comm;
   d->owns_comm = false;
+  d->root = parent->root ? parent->root : parent;
+  d->error_host = d->root->error_host;
+  d->error_dev = d->root->error_dev;
+  d->timeout_cycles = d->root->timeout_cycles;
   d->rank = parent->rank;
   d->nranks = parent->nranks;
   d->neigh.assign(neigh_rank, neigh_rank + nneigh);
@@ -396,6 +343,8 @@ extern "C" int cb_dist_p2p_export(cb_dist* d, char* handle64) {
 
 extern "C" int64_t cb_dist_p2p_ghost_cap(cb_dist* d) { return d ? d->ghost_cap : 0; }
 
+static void dist_release_p2p(cb_dist* d);
+
 // Map the peers' windows (handles [nranks*64], rank order) and switch this plan to the one-sided
 // transport.  remote_off [nneigh]: node offset of my data inside neighbour j's ghost range.
 extern "C" int cb_dist_p2p_open(cb_dist* d, const char* handles, const int64_t* remote_off,
@@ -413,6 +362,7 @@ extern "C" int cb_dist_p2p_open(cb_dist* d, const char* handles, const int64_t* 
     if (e != cudaSuccess) {
       set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
       (void)cudaGetLastError();
+      dist_release_p2p(d);
       return CB_ERR_CUDA;
     }
     d->peer_window[r] = static_cast<unsigned char*>(ptr);
@@ -442,25 +392,35 @@ extern "C" int cb_dist_p2p_disable(cb_dist* d) {
   return CB_OK;
 }
 
-// 1 if a peer timed out inside a one-sided wait (the solve result is then invalid), else 0.
+// 1 if a peer timed out inside a one-sided wait on ANY plan of this communicator (results are then invalid), else 0.
+// A plain host load of the pinned error word: no copy, no synchronisation -- cheap enough to be called after every
+// exchange.  The word stays raised: a timed-out communicator is dead, the host layer raises.
 extern "C" int cb_dist_p2p_error(cb_dist* d) {
-  if (!d || !d->p2p) return 0;
-  const WindowLayout lay{d->nranks};
-  unsigned long long e = 0;
-  cudaMemcpy(&e, reinterpret_cast<double*>(d->window) + lay.flags_off() + 2 * d->nranks + 1, sizeof(e), cudaMemcpyDeviceToHost);
-  return e != 0;
+  if (!d || !d->error_host) return 0;
+  return *reinterpret_cast<volatile unsigned long long*>(d->error_host) != 0ULL;
+}
+
+static void dist_release_p2p(cb_dist* d) {
+  for (size_t r = 0; r < d->peer_window.size(); ++r)
+    if ((int)r != d->rank && d->peer_window[r]) cudaIpcCloseMemHandle(d->peer_window[r]);
+  d->peer_window.clear();
+  if (d->d_send_off) cudaFree(d->d_send_off);
+  if (d->d_recv_off) cudaFree(d->d_recv_off);
+  if (d->d_remote_off) cudaFree(d->d_remote_off);
+  if (d->d_remote_cap) cudaFree(d->d_remote_cap);
+  if (d->d_neigh) cudaFree(d->d_neigh);
+  if (d->d_peer_window) cudaFree(d->d_peer_window);
+  d->d_send_off = d->d_recv_off = d->d_remote_off = d->d_remote_cap = nullptr;
+  d->d_neigh = nullptr;
+  d->d_peer_window = nullptr;
 }
 
 extern "C" int cb_dist_destroy(cb_dist* d) {
   if (!d) return CB_OK;
-  if (d->p2p) {
-    for (int r = 0; r < d->nranks; ++r)
-      if (r != d->rank && d->peer_window[r]) cudaIpcCloseMemHandle(d->peer_window[r]);
-    cudaFree(d->d_send_off); cudaFree(d->d_recv_off); cudaFree(d->d_remote_off); cudaFree(d->d_remote_cap); cudaFree(d->d_neigh);
-    cudaFree(d->d_peer_window);
-  }
+  dist_release_p2p(d);  // by pointer, whether or not the one-sided transport ended up enabled
   if (d->window) cudaFree(d->window);
   if (d->comm && d->owns_comm) g_nccl.CommDestroy(d->comm);
+  if (d->error_host && !d->root) cudaFreeHost(d->error_host);
   delete d;
   return CB_OK;
 }

@@ -18,9 +18,15 @@
 #include <utility>
 #include <vector>
 
+#include <stdlib.h>
+
+#include "coarse_cycle.cuh"
+#include "p2p.cuh"
 #include "spmv.cuh"
 
 namespace cb {
+
+P2PView dist_p2p_view(const cb_dist* d);
 
 int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
                   double* result, double* scratch, const int* done = nullptr, bool use32 = false);
@@ -472,6 +478,29 @@ __global__ void k_minres_state(KspState* st, double* hist, int which) {
   else if (which == 2) st->alfa = st->sums[0];
 }
 
+// One reduction point of a partitioned Krylov iteration as ONE kernel of one warp: the one-sided all-reduce of
+// st->sums[0..n) over NVLink (rank-ordered sum, identical on all ranks) and then the scalar recurrences / convergence
+// test of that point.  Ranks stay in lock step even after convergence: the exchange always runs, only the recurrence
+// is skipped once `done` is raised (identically everywhere).
+__global__ void k_allreduce_state(int n, KspState* st, double* hist, P2PView v, int which, int minres) {
+  const bool ok = p2p_allreduce_warp(v, n, st->sums, 0);
+  if (threadIdx.x != 0) return;
+  if (!ok) {  // a peer timed out (the host raises on the communicator's error word)
+    if (!st->done) { st->reason = CB_KSP_DIVERGED_BREAKDOWN; st->done = 1; }
+    return;
+  }
+  if (st->done) return;
+  if (minres) {
+    if (which == 0) minres_after_beta(st, hist, 1);
+    else if (which == 1) minres_after_beta(st, hist, 0);
+    else if (which == 2) st->alfa = st->sums[0];
+  } else {
+    if (which == 0) cg_after_zr(st, hist, 1);
+    else if (which == 1) cg_after_zr(st, hist, 0);
+    else if (which == 2) cg_after_pw(st);
+  }
+}
+
 // r1 = b ; y = dinv .* r1 ; sums[0] = r1.y ; x = 0
 template <bool FINALIZE>
 __global__ void __launch_bounds__(256)
@@ -646,6 +675,7 @@ struct Solver {
       cudaEventDestroy(e.first);
       cudaEventDestroy(e.second);
     }
+    prof.clear();
     return total;
   }
 
@@ -662,12 +692,7 @@ struct Solver {
     int e = bs == 1 ? cg_spmv_bs<1>(p, w) : bs == 2 ? cg_spmv_bs<2>(p, w) : cg_spmv_bs<3>(p, w);
     prof_end(pr);
     if (e) return e;
-    if (dist) {
-      if (int e2 = dist_allreduce_sum(s, dist, st->sums, 1)) return e2;
-      k_state_step<<<1, 1, 0, s>>>(st, hist_dev, 2);
-      CB_LAUNCH_CHECK();
-    }
-    return CB_OK;
+    return reduce_and_step(1, 2, false);
   }
   template <int BS>
   int minres_spmv_bs(const double* v, const double* r1, double* t) {
@@ -788,14 +813,91 @@ struct Solver {
     return (l > 0 && h->level_smooth_degree > 0) ? h->level_smooth_degree : h->smooth_degree;
   }
 
+  // ---- levels >= fused_first as one persistent kernel (coarse_cycle.cuh)
+  int fused_first = 0;                 // 0: off
+  CoarseCycleDev* fused_dev = nullptr; // device copy of the descriptor (workspace)
+  int fused_grid = 1;
+
+  // Decide which levels the persistent kernel takes and upload its descriptor (once per solve, outside the graph).
+  // `buf` is a workspace slice of cc_workspace_doubles() doubles: descriptor, then the three barrier words.
+  static int64_t cc_workspace_doubles() { return (int64_t)((sizeof(CoarseCycleDev) + 7) / 8 + 8); }
+  int setup_fused_cycle(const cb_amg* h, double* buf) {
+    fused_first = 0;
+    const char* env = getenv("CASHOCS_B200_FUSED_COARSE");
+    if (env && env[0] == '0') return CB_OK;
+    const int L = h->nlevels;
+    if (L < 2 || h->p_block) return CB_OK;
+    // levels with more rows than this keep their own (TMA-staged) kernels: they are bandwidth-, not latency-bound
+    int64_t max_rows = 20000;
+    if (const char* mr = getenv("CASHOCS_B200_FUSED_MAX_ROWS")) max_rows = atoll(mr);
+    int first = L;  // smallest level from which on every operator is local (no halo plan)
+    for (int l = L - 1; l >= 1; --l) {
+      const cb_amg_level& lev = h->levels[l];
+      if (lev.dist || lev.A.nrows > max_rows) break;
+      if (l < L - 1 && (!lev.AP.val || lev.AP.val32 || h->levels[l + 1].rep_dist)) break;
+      first = l;
+    }
+    if (first >= L || L - first > CC_MAX_LEVELS) return CB_OK;
+    CoarseCycleDev cy;
+    memset(&cy, 0, sizeof(cy));
+    cy.nlevels = L - first;
+    const cb_amg_level& lastlev = h->levels[L - 1];
+    cy.dense_n = h->coarse_inv ? (int)(lastlev.A.nrows * bs) : 0;
+    cy.coarse_inv = h->coarse_inv;
+    for (int l = first; l < L; ++l) {
+      const cb_amg_level& lev = h->levels[l];
+      CoarseLevelDev& d = cy.lev[l - first];
+      const bool last = (l == L - 1);
+      d.n = lev.A.nrows;
+      d.nc = last ? 0 : h->levels[l + 1].A.nrows;
+      d.rowptr = lev.A.rowptr; d.col = lev.A.col; d.val = lev.A.val; d.dinv = lev.dinv;
+      d.p_rowptr = lev.p_rowptr; d.p_col = lev.p_col; d.p_val = lev.p_val;
+      d.pt_rowptr = lev.pt_rowptr; d.pt_col = lev.pt_col; d.pt_val = lev.pt_val;
+      d.ap_rowptr = lev.AP.rowptr; d.ap_col = lev.AP.col; d.ap_val = lev.AP.val;
+      d.x = lev.x; d.b = lev.b; d.t = lev.t; d.d = lev.d;
+      d.degree = (last && !h->coarse_inv) ? h->coarse_degree : level_degree(h, l);
+      if (d.degree > CC_MAX_DEGREE) return CB_OK;
+      std::pair<double, double> coef[64];
+      cheb_coefficients(lev.lmax, (last && !h->coarse_inv) ? h->coarse_ratio : h->smooth_ratio, d.degree, d.inv_theta, coef);
+      for (int j = 1; j < d.degree; ++j) { d.c1[j] = coef[j].first; d.c2[j] = coef[j].second; }
+      if (lev.A.ncols != lev.A.nrows) return CB_OK;  // ghost columns: not a local operator
+    }
+    fused_dev = reinterpret_cast<CoarseCycleDev*>(buf);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(buf + (sizeof(CoarseCycleDev) + 7) / 8);
+    cy.barrier = bar;
+    CB_CUDA_CHECK(cudaMemsetAsync(bar, 0, 8 * sizeof(double), s));
+    CB_CUDA_CHECK(cudaMemcpyAsync(fused_dev, &cy, sizeof(cy), cudaMemcpyHostToDevice, s));
+    CB_CUDA_CHECK(cudaStreamSynchronize(s));  // `cy` lives on this stack frame
+    const int64_t rows = cy.lev[0].n;
+    int64_t g = (rows + 31) / 32;  // 32 warps per CTA, one block row per warp and sweep
+    if (g < 1) g = 1;
+    if (g > num_sms()) g = num_sms();
+    fused_grid = (int)g;
+    fused_first = first;
+    return CB_OK;
+  }
+  int launch_fused_cycle() {
+    if (bs == 1) k_coarse_cycle<1><<<fused_grid, CC_THREADS, 0, s>>>(fused_dev, &st->done);
+    else if (bs == 2) k_coarse_cycle<2><<<fused_grid, CC_THREADS, 0, s>>>(fused_dev, &st->done);
+    else k_coarse_cycle<3><<<fused_grid, CC_THREADS, 0, s>>>(fused_dev, &st->done);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
+
   // z = M^-1 r : one symmetric V-cycle (pre/post Chebyshev smoothing, Chebyshev coarsest solve)
   int amg_vcycle(const cb_amg* h, const double* r, double* z, bool presmoothed = false, int dots_mode = -2) {
     const int L = h->nlevels;
     dots_fused = false;
+    int up_from = L - 2;  // first level of the upward sweep
     for (int l = 0; l < L; ++l) {
       const cb_amg_level& lev = h->levels[l];
       const double* bl = (l == 0) ? r : lev.b;
       double* xl = (l == 0) ? z : lev.x;
+      if (fused_first > 0 && l == fused_first) {  // everything from here down and back up is one kernel
+        if (int e = launch_fused_cycle()) return e;
+        up_from = l - 1;
+        break;
+      }
       if (l == L - 1) {
         if (h->coarse_inv) {
           if (int e = amg_dense_apply(s, (int)(lev.A.nrows * bs), h->coarse_inv, bl, xl, &st->done)) return e;
@@ -818,7 +920,7 @@ struct Solver {
         if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.b, &st->done, h->p_block)) return e;
       }
     }
-    for (int l = L - 2; l >= 0; --l) {
+    for (int l = up_from; l >= 0; --l) {
       const cb_amg_level& lev = h->levels[l];
       const cb_amg_level& nxt = h->levels[l + 1];
       const double* bl = (l == 0) ? r : lev.b;
@@ -860,6 +962,11 @@ struct Solver {
   }
   int reduce_and_step(int nsums, int which, bool minres) {
     if (!dist) return CB_OK;
+    if (dist_is_one_sided(dist) && nsums <= RED_W) {
+      k_allreduce_state<<<1, 32, 0, s>>>(nsums, st, hist_dev, dist_p2p_view(dist), which, minres ? 1 : 0);
+      CB_LAUNCH_CHECK();
+      return CB_OK;
+    }
     if (int e = dist_allreduce_sum(s, dist, st->sums, nsums)) return e;
     if (minres) k_minres_state<<<1, 1, 0, s>>>(st, hist_dev, which);
     else k_state_step<<<1, 1, 0, s>>>(st, hist_dev, which);
@@ -875,7 +982,7 @@ using namespace cb;
 extern "C" int64_t cb_ksp_workspace_len(int64_t n, int64_t nc, const cb_ksp_opts* opts) {
   (void)opts;
   // r, w, dinv, d, t : n ; z, p, (minres: 3 more with ghosts) : nc ; + state, scratch, send buffer
-  return 6 * n + 6 * nc + STATE_DOUBLES + RED_SCRATCH_LEN + nc + 64;
+  return 6 * n + 6 * nc + STATE_DOUBLES + RED_SCRATCH_LEN + nc + 64 + Solver::cc_workspace_doubles();
 }
 
 extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, double* x,
@@ -905,9 +1012,27 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
   double* m2 = take(nc);
   double* m3 = take(nc);
   double* sendbuf = take(nc);
+  double* cc_buf = take(Solver::cc_workspace_doubles());
   double* hist_dev = nullptr;
   const int64_t hlen = (o->monitor && hist && hist_len > 0) ? hist_len : 0;
   if (hlen) CB_CUDA_CHECK(cudaMallocAsync(&hist_dev, sizeof(double) * hlen, s));
+  Solver S;  // declared before the guard: the guard's destructor (which runs first) still sees S.prof
+  // everything this call acquires is released on EVERY return path (error returns included)
+  struct Cleanup {
+    cudaStream_t stream;
+    double* hist_dev = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* events = nullptr;
+    ~Cleanup() {
+      if (gexec) cudaGraphExecDestroy(gexec);
+      if (hist_dev) cudaFreeAsync(hist_dev, stream);
+      if (events) {
+        for (auto& e : *events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        events->clear();
+      }
+    }
+  } cleanup{s};
+  cleanup.hist_dev = hist_dev;
 
   KspState h0;
   memset(&h0, 0, sizeof(h0));
@@ -917,10 +1042,10 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
   CB_CUDA_CHECK(cudaMemcpyAsync(st, &h0, sizeof(h0), cudaMemcpyHostToDevice, s));
   CB_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * RED_SCRATCH_LEN, s));
 
-  Solver S;
   S.s = s; S.A = A; S.dist = dist; S.n = n; S.nc = nc; S.bs = A->bs; S.st = st;
   S.hist_dev = hist_dev; S.scratch = scratch; S.sendbuf = sendbuf;
   S.profile_every = o->profile_every;
+  cleanup.events = &S.prof;
   S.vgrid = grid_for(n, 256, 4);
   if (S.vgrid > RED_MAXP) S.vgrid = RED_MAXP;
   {
@@ -982,7 +1107,6 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
     CB_CUDA_CHECK(cudaStreamSynchronize(s));
     result->reason = CB_KSP_CONVERGED_ITS; result->its = 1; result->rnorm = 0.0; result->rnorm0 = 0.0;
     result->spmv_ms = 0.0; result->spmv_profiled = 0; result->spmv_launches = 0;
-    if (hist_dev) CB_CUDA_CHECK(cudaFreeAsync(hist_dev, s));
     return CB_OK;
   }
 
@@ -995,6 +1119,7 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
                  o->amg->coarse_degree <= 64 && o->amg->level_smooth_degree >= 0 && o->amg->level_smooth_degree <= 64,
                  "amg smoother degrees must be in 1..64");
     }
+    if (amg) { if ((rc = S.setup_fused_cycle(o->amg, cc_buf))) return rc; }
     // Chebyshev coefficients (fixed polynomial -> a linear SPD preconditioner)
     std::pair<double, double> coef[64];
     double inv_theta = 0.0;
@@ -1119,7 +1244,10 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
           int brc = CB_OK;
           if (ce == cudaSuccess) {
             brc = iteration();
-            ce = cudaStreamEndCapture(cs, &graph);
+            // always end the capture, also after a failed iteration(): the thread must not stay in capture mode
+            const cudaError_t ee = cudaStreamEndCapture(cs, &graph);
+            if (brc == CB_OK) ce = ee;
+            else (void)cudaGetLastError();
           }
           s = user_stream;
           S.s = user_stream;
@@ -1132,10 +1260,11 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
           const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
           cudaGraphDestroy(graph);
           CB_CUDA_CHECK(ie);
+          cleanup.gexec = gexec;
         }
         for (int c = 0; c < check_every && enq < o->max_it; ++c, ++enq) {
           const cudaError_t le = cudaGraphLaunch(gexec, s);
-          if (le != cudaSuccess) { cudaGraphExecDestroy(gexec); CB_CUDA_CHECK(le); }
+          CB_CUDA_CHECK(le);
           g_launch_count += graph_kernels;
           S.spmv_launches += 1;
         }
@@ -1145,10 +1274,9 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
         }
       }
       ++chunk;
-      if ((rc = poll())) { if (gexec) cudaGraphExecDestroy(gexec); return rc; }
+      if ((rc = poll())) return rc;
       if (hs.done || enq >= o->max_it) break;
     }
-    if (gexec) cudaGraphExecDestroy(gexec);
   } else if (o->ksp_type == CB_KSP_MINRES) {
     CB_REQUIRE(o->pc_type != CB_PC_CHEBYSHEV, "minres supports pc_type none / jacobi");
     // rotating roles: (r1, r2, y) and (w1, w2, w)
@@ -1212,7 +1340,6 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
     const int64_t ncopy = (hs.its + 1 < hlen) ? hs.its + 1 : hlen;
     CB_CUDA_CHECK(cudaMemcpyAsync(hist, hist_dev, sizeof(double) * ncopy, cudaMemcpyDeviceToHost, s));
     CB_CUDA_CHECK(cudaStreamSynchronize(s));
-    CB_CUDA_CHECK(cudaFreeAsync(hist_dev, s));
   }
   return CB_OK;
 }

@@ -124,9 +124,13 @@ class DistContext:
             lib.cb_dist_p2p_disable(self.handle)
 
     def check_p2p(self) -> None:
-        """Raise if a peer timed out inside a one-sided wait (the vectors are then invalid)."""
-        if self.p2p and _lib.load().cb_dist_p2p_error(self.handle):
-            raise _exceptions.CashocsException("one-sided halo exchange: a peer did not answer within the wait limit")
+        """Raise if a peer timed out inside a one-sided wait on any plan of this communicator (the vectors are then
+        invalid).  The error word is pinned host memory shared by the root plan and its clones: this is a plain load,
+        so it runs after every exchange, all-reduce and solve; the wait limit is ``CASHOCS_B200_P2P_TIMEOUT_S`` (60 s)."""
+        if self.handle is not None and self.transport == "native" and _lib.load().cb_dist_p2p_error(self.handle):
+            raise _exceptions.CashocsException(
+                "one-sided NVLink exchange: a peer did not answer within the wait limit (CASHOCS_B200_P2P_TIMEOUT_S); "
+                "the communicator is unusable")
 
     def owner_of_ghost(self) -> torch.Tensor:
         """Owner rank of every ghost vertex (ghosts are ordered by owner)."""
@@ -162,6 +166,7 @@ class DistContext:
             code = {"sum": 0, "min": 1, "max": 2}[op]
             _lib.check(_lib.load().cb_dist_allreduce(_lib.stream_ptr(), self.handle, _lib.ptr(t), t.numel(), code),
                        "cb_dist_allreduce")
+            self.check_p2p()
         else:
             td.all_reduce(t, {"sum": td.ReduceOp.SUM, "min": td.ReduceOp.MIN, "max": td.ReduceOp.MAX}[op])
         return t
@@ -169,7 +174,9 @@ class DistContext:
     def allreduce_scalar(self, v: float, op: str = "sum") -> float:
         dev = self.send_idx.device if self.send_idx is not None else "cpu"
         t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
-        return float(self.allreduce(t, op).item())
+        out = float(self.allreduce(t, op).item())
+        self.check_p2p()  # .item() synchronised: a time-out inside this very exchange is visible now
+        return out
 
     def halo_exchange(self, x: torch.Tensor, bs: int = 1) -> torch.Tensor:
         """Ghost update of a vertex-blocked vector ``[(n_owned + n_ghost) * bs]`` (``Vec.ghostUpdate``)."""
@@ -181,6 +188,7 @@ class DistContext:
                 self._sendbuf = torch.empty(max(need, 1), dtype=torch.float64, device=x.device)
             _lib.check(_lib.load().cb_dist_halo_exchange(_lib.stream_ptr(), self.handle, _lib.ptr(x), bs,
                                                          _lib.ptr(self._sendbuf)), "cb_dist_halo_exchange")
+            self.check_p2p()
             return x
         xv = x.view(-1, bs)
         reqs, bufs = [], []

@@ -157,6 +157,37 @@ def test_rowwise_galerkin_products_match_term_lists(kind):
             assert torch.equal(x, y)
 
 
+@pytest.mark.parametrize("kind", ["cube", "square", "mesh3d"])
+def test_fused_coarse_cycle_equals_the_launch_per_operation_cycle(kind):
+    """The levels >= 1 of the V-cycle as one persistent kernel (``csrc/coarse_cycle.cuh``, grid barriers between the
+    phases) against the same cycle launched operation by operation (``CASHOCS_B200_FUSED_COARSE=0``): same operators,
+    same Chebyshev coefficients, only the summation order inside a row differs -- same iteration counts, solutions
+    equal to round-off, and the fused path is bitwise reproducible (eager loop == graph replay, run == rerun)."""
+    import os
+
+    dm, A, b, E, rhs = systems(kind)
+    for M, f in ((A, b), (E, rhs)):
+        for lsd in (1, 2, 3):
+            opts = {"ksp_type": "cg", "pc_type": "hypre", "ksp_rtol": 1e-11, "ksp_atol": 1e-30, "ksp_max_it": 500,
+                    "pc_amg_level_smooth_degree": lsd}
+            sol = {}
+            for fused in ("1", "0"):
+                os.environ["CASHOCS_B200_FUSED_COARSE"] = fused
+                try:
+                    x = torch.zeros(M.nrows * M.bs, dtype=torch.float64, device="cuda")
+                    res = cb.LinearSolver().solve(x, A=M, b=f, ksp_options=opts)
+                finally:
+                    os.environ.pop("CASHOCS_B200_FUSED_COARSE", None)
+                sol[fused] = (res.its, x)
+            assert abs(sol["1"][0] - sol["0"][0]) <= 1, (sol["1"][0], sol["0"][0])
+            scale = float(sol["0"][1].abs().max())
+            assert float((sol["1"][1] - sol["0"][1]).abs().max()) <= 1e-9 * scale
+            for graph in (-1, 0):
+                x2 = torch.zeros_like(sol["1"][1])
+                res2 = cb.LinearSolver().solve(x2, A=M, b=f, ksp_options=dict(opts, ksp_use_graph=graph))
+                assert res2.its == sol["1"][0] and torch.equal(x2, sol["1"][1])
+
+
 @pytest.mark.parametrize("kind", ["cube", "square"])
 def test_rigid_body_coarse_correction(kind):
     """``pc_amg_rigid_body_correction``: M + Z (Z^T A Z)^-1 Z^T with the global rigid-body modes -- same solution as

@@ -122,7 +122,9 @@ def test_rbm_hierarchy_end_to_end():
     base = linalg.LinearSolver().solve(x0, A=E, b=rhs, ksp_options={"ksp_type": "cg", "pc_type": "hypre", "ksp_rtol": 1e-11,
                                                                     "ksp_atol": 1e-30,
                                                                     "pc_amg_rigid_body_correction": False})
-    assert its <= 0.6 * base.its, (its, base.its)
+    # (the scalar-prolongator hierarchy has been tuned since this was written: round 1 needed ~2.4x the iterations of
+    # the rigid-body hierarchy, now ~1.6x)
+    assert its <= 0.8 * base.its, (its, base.its)
 
 
 def test_rbm_hierarchy_inside_cb_ksp_solve():
@@ -149,4 +151,4 @@ def test_rbm_hierarchy_inside_cb_ksp_solve():
     assert out[-1][0] == out[0][0] and torch.equal(out[-1][1], out[0][1])
     x0 = torch.zeros_like(rhs)
     ref_its = linalg.LinearSolver().solve(x0, A=E, b=rhs, ksp_options=dict(base, pc_amg_rigid_body_correction=False)).its
-    assert out[0][0] <= 0.6 * ref_its, (out[0][0], ref_its)
+    assert out[0][0] <= 0.8 * ref_its, (out[0][0], ref_its)

@@ -44,7 +44,17 @@ def main():
     bench.GRADIENT_KSP_EXTRA["pc_amg_nullspace"] = args.nullspace
     bench.KSP["pc_type"] = args.pc
     bench.KSP["pc_amg_rigid_body_correction"] = bool(args.rbm)
-    sop = bench.build_problem(args.n)
+    dist = None
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:  # torchrun: the same phases on a partitioned mesh (times of rank 0)
+        import torch.distributed as td
+
+        from cashocs_b200 import distributed
+
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        td.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+        dist = distributed.DistContext(int(os.environ["RANK"]), world)
+    sop = bench.build_problem(args.n, dist)
     h = 1.0 / args.n
     bench.evaluation_step(sop, h)
     timer = T()
@@ -77,8 +87,18 @@ def main():
         with timer("gAg"):
             fh.scalar_product(g, g)
         with timer("move (det+move+intersection+quality) + revert"):
-            if sop.mesh_handler.move_mesh(g, step=-0.1 * h / float(g.abs().max())):
+            ginf = float(g.abs().max())
+            if dist is not None:
+                ginf = dist.allreduce_scalar(ginf, "max")
+            if sop.mesh_handler.move_mesh(g, step=-0.1 * h / ginf):
                 sop.mesh_handler.revert_transformation()
+    if dist is not None and dist.rank != 0:
+        import torch.distributed as td
+
+        td.barrier()
+        dist.destroy()
+        td.destroy_process_group()
+        return
     for k, v in timer.acc.items():
         print(f"{k:50s} {v / args.reps:10.2f} ms")
     print("its", sop.state_problem.linear_solver.last_result.its, sop.adjoint_problem.iterations, res.its)
@@ -88,6 +108,12 @@ def main():
         for L in hE.levels:
             if hasattr(L, "p_col") and L.p_col is not None and not getattr(L, "last", False):
                 print("  level n", L.n, "nnzb", L.nnzb, "P entries", int(L.p_col.numel()), "AP entries", int(L.ap_col.numel()))
+    if dist is not None:
+        import torch.distributed as td
+
+        td.barrier()
+        dist.destroy()
+        td.destroy_process_group()
 
 
 if __name__ == "__main__":

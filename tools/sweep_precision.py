@@ -24,6 +24,7 @@ def timed(fn):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mesh-n", dest="n", type=int, default=119)
+    ap.add_argument("--touch", type=int, default=0, help="extra numeric phases (matrix versions) before the timed solve")
     ap.add_argument("--variants", default="pc_amg_precision=double;pc_amg_precision=mixed:a0",
                     help="semicolon-separated option sets, each `key=value,key=value` on top of bench.KSP")
     args = ap.parse_args()
@@ -48,7 +49,10 @@ def main():
                     opts[k] = float(v)
                 except ValueError:
                     opts[k] = v
-        for rep in range(2):
+        for rep in range(2 + args.touch):
+            if rep < args.touch:
+                A.touch()
+                E.touch()
             x = torch.zeros(A.ncols, dtype=torch.float64, device="cuda")
             rA, tA = timed(lambda: linalg.LinearSolver().solve(x, A=A, b=b, ksp_options={k: v for k, v in opts.items() if k != "pc_amg_rigid_body_correction"}))
             g = torch.zeros(E.ncols * 3, dtype=torch.float64, device="cuda")
