@@ -152,9 +152,12 @@ class ShapeFormHandler:
         if not isinstance(src, (type(None),)) and not hasattr(src, "terms"):
             raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "source",
                                          "shape problems need a polynomial (coordinate) source term")
-        if self.cost.c_track != 0.0 or self.state_form.reaction != 0.0 or self.state_form.kappa != 1.0:
+        general = self.cost.c_track != 0.0 or self.state_form.reaction != 0.0 or self.state_form.kappa != 1.0
+        if general and self.state.degree == 2:
             raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "forms",
-                                         "shape derivative implemented for kappa=1, no reaction, J = c*int(u)")
+                                         "P2 states: shape derivative implemented for kappa=1, no reaction, J = c*int(u)")
+        if self.cost.c_track != 0.0 and self.cost.desired_state.degree != 1:
+            raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "desired_state", "u_d must be a P1 Function")
         from cashocs_b200._forms import expressions
 
         f = src if src is not None else expressions.Polynomial()
@@ -169,7 +172,10 @@ class ShapeFormHandler:
         else:
             b = linalg.assemble_shape_derivative(
                 self.mesh, self.state.vector, self.adjoint.vector, f, self.cost.c_state, bc_flag=self.bc_flag,
-                b=self.fe_shape_derivative_vector,
+                b=self.fe_shape_derivative_vector, kappa=self.state_form.kappa, reaction=self.state_form.reaction,
+                c_track=self.cost.c_track,
+                u_d=self.cost.desired_state.vector if self.cost.c_track != 0.0 else None,
+                pull_back=self.config.getboolean("ShapeGradient", "use_pull_back"),
             )
         if self.shape_regularization.is_active:  # shape_gradient_problem.py:131 + shape_regularization.py:688-698
             self.shape_regularization.update_geometric_quantities()

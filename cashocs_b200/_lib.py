@@ -123,6 +123,8 @@ class cb_amg_level(C.Structure):
         ("AP", cb_mat),
         ("coarse_gid", C.c_void_p),
         ("xc_local", C.c_void_p),
+        ("rep_gather", C.c_void_p),
+        ("rep_tmp", C.c_void_p),
     ]
 
 
@@ -197,6 +199,8 @@ SIGNATURES = {
     "cb_assemble_elasticity": (I32, [P, C.POINTER(cb_mesh_view), P, DBL, DBL, P, P, P]),
     "cb_assemble_shape_derivative_poisson": (I32, [P, C.POINTER(cb_mesh_view), P, P, C.POINTER(cb_poly),
                                                    C.POINTER(cb_poly), C.POINTER(cb_quad), DBL, P, P]),
+    "cb_assemble_shape_derivative": (I32, [P, C.POINTER(cb_mesh_view), P, P, C.POINTER(cb_poly), C.POINTER(cb_poly),
+                                           C.POINTER(cb_quad), DBL, DBL, DBL, DBL, P, I32, P, P]),
     "cb_ident_zeros": (I32, [P, I64, I32, P, P, P, P]),
     "cb_p2_assemble_matrix": (I32, [P, C.POINTER(cb_p2_view), DBL, DBL, P, P]),
     "cb_p2_assemble_rhs": (I32, [P, C.POINTER(cb_p2_view), DBL, DBL, DBL, C.POINTER(cb_poly), I32, P, DBL, DBL, P,

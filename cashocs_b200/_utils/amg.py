@@ -177,14 +177,20 @@ class AMGSymbolic:
         dev = col.device
         while True:
             L = _Level()
-            L.rep_dist, L.rep_off, L.rep_pos, L.rep_nnzb_local = None, 0, None, 0
+            L.rep_dist, L.rep_off, L.rep_pos, L.rep_nnzb_local, L.rep_gather = None, 0, None, 0, None
             n_glob = n if dist is None else int(round(dist.allreduce_scalar(float(n), "sum")))
             if dist is not None and self.levels and n_glob <= self.AGGLOMERATE:
                 # agglomeration: below this size halo latency dominates, so the level (and everything
                 # coarser) is replicated on every rank; the restriction all-reduces the rhs instead
                 L.rep_dist, L.rep_nnzb_local = dist, int(col.numel())
                 L.rep_rowptr_local, L.rep_col_local = rowptr, col  # this rank's rows in its own numbering
-                rowptr, col, L.rep_off, L.rep_pos, gid = self._replicate(rowptr, col, n, ncols, n_glob, dist)
+                rowptr, col, L.rep_off, L.rep_pos, gid, counts = self._replicate(rowptr, col, n, ncols, n_glob, dist)
+                # all-gather of the restricted residual as a halo plan: the "ghosts" are all other ranks' rows
+                owners = torch.cat([torch.full((c,), r, dtype=torch.int64) for r, c in enumerate(counts) if r != dist.rank]
+                                   + [torch.zeros(0, dtype=torch.int64)])
+                ids = torch.cat([torch.arange(c, dtype=torch.int64) for r, c in enumerate(counts) if r != dist.rank]
+                                + [torch.zeros(0, dtype=torch.int64)])
+                L.rep_gather = dist.derive_plan(owners, ids, n, dev)
                 self.levels[-1].coarse_gid = gid.to(torch.int32).contiguous()  # local coarse node -> replicated row
                 n = ncols = n_glob
                 dist = None
@@ -332,7 +338,7 @@ class AMGSymbolic:
         pos = inv[start: start + key.numel()].contiguous()
         g_rowptr = _rowptr_from_rows(skeys // n_glob, n_glob)
         g_col = (skeys % n_glob).to(torch.int32).contiguous()
-        return g_rowptr, g_col, off, pos, gid
+        return g_rowptr, g_col, off, pos, gid, [int(c) for c in counts]
 
     @property
     def sizes(self):
@@ -381,6 +387,7 @@ class AMGHierarchy:
             D.val = None if li == 0 else torch.zeros(L.nnzb * bs * bs, **f64)
             # rows of a replicated level computed by this rank (scattered + all-reduced into D.val)
             D.val_local = torch.zeros(L.rep_nnzb_local * bs * bs, **f64) if L.rep_dist is not None else None
+            D.rep_tmp = torch.zeros(nb, **f64) if L.rep_gather is not None else None
             want32 = self.mixed and (("a0" in self.mixed_mask) if li == 0 else ("coarse" in self.mixed_mask))
             D.val32 = torch.zeros(L.nnzb * bs * bs, dtype=torch.float32, device=dev) if want32 else None
             D.ap_val32 = None
@@ -584,6 +591,9 @@ class AMGHierarchy:
             if L.rep_dist is not None:
                 e.rep_dist = L.rep_dist.handle
                 e.rep_off = L.rep_off
+                if L.rep_gather is not None and L.rep_gather.handle is not None:
+                    e.rep_gather = L.rep_gather.handle
+                    e.rep_tmp = D.rep_tmp.data_ptr()
             if not L.last and self.use_ap:
                 from cashocs_b200._utils import linalg
 

@@ -349,24 +349,29 @@ def assemble_elasticity_matrix(mesh, mu: torch.Tensor, lambda_lame: float, dampi
 @log.profile_execution_time("assembling the system")
 def assemble_shape_derivative(mesh, u: torch.Tensor, p: torch.Tensor, f_poly: expressions.Polynomial,
                               c_int_u: float = 1.0, bc_flag: torch.Tensor | None = None,
-                              b: torch.Tensor | None = None) -> torch.Tensor:
-    """Shape-derivative vector of the Poisson Lagrangian (``shape_gradient_problem.py:142-144``)."""
+                              b: torch.Tensor | None = None, kappa: float = 1.0, reaction: float = 0.0,
+                              c_track: float = 0.0, u_d: torch.Tensor | None = None,
+                              pull_back: bool = True) -> torch.Tensor:
+    """Shape-derivative vector of the Lagrangian ``int c_int_u u + c_track/2 (u - u_d)^2 + kappa grad u . grad p +
+    reaction u p - f p`` (``shape_gradient_problem.py:142-144``, form ``shape_form_handler.py:533-549``); ``u_d`` is a P1
+    field whose gradient enters through the pull-back of ``shape_form_handler.py:507-531`` when ``pull_back``."""
     lib = _lib.load()
     view = mesh.view(gather=USE_GATHER_ASSEMBLY)
     d = mesh.dim
     if b is None:
         b = torch.empty(mesh.n_owned_vertices * d, dtype=torch.float64, device=mesh.device)
-    _lib.require_cuda(u, p, bc_flag, b)
+    _lib.require_cuda(u, p, bc_flag, b, u_d)
     f = f_poly.struct()
     grads = (_lib.cb_poly * 3)()
     for i in range(d):
         grads[i] = f_poly.derivative(i).struct()
     quad = expressions.quadrature_struct(d, f_poly.degree + 1)
     _lib.check(
-        lib.cb_assemble_shape_derivative_poisson(
+        lib.cb_assemble_shape_derivative(
             _lib.stream_ptr(), C.byref(view), _lib.ptr(u), _lib.ptr(p), C.byref(f), grads, C.byref(quad),
-            float(c_int_u), _lib.ptr(bc_flag), _lib.ptr(b)),
-        "cb_assemble_shape_derivative_poisson",
+            float(c_int_u), float(kappa), float(reaction), float(c_track), _lib.ptr(u_d), int(bool(pull_back)),
+            _lib.ptr(bc_flag), _lib.ptr(b)),
+        "cb_assemble_shape_derivative",
     )
     return b
 

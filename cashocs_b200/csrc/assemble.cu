@@ -339,24 +339,37 @@ k_assemble_scalar_gather(int64_t nnz, const int64_t* __restrict__ n2c_ptr, const
   }
 }
 
-// ------------------------------------------------------------------ shape derivative (Poisson, J = c * int u)
+// ------------------------------------------------------------------ shape derivative of the Poisson-type Lagrangian
+// L = int c_s u + c_t/2 (u - u_d)^2 + kappa grad u . grad p + c u p - f p dx with P1 u, p, u_d and polynomial f:
+//   dL[V] = int (density) div V - kappa (grad V + grad V^T) grad u . grad p - (grad f . V) p - c_t (u - u_d) (grad u_d . V)
+// (the last term is the pull-back of cashocs/_forms/shape_form_handler.py:507-531 for a Function u_d; analytic forms:
+// tests/test_shape_optimization.py:252-259 and :284-291).  Everything but the two f-integrals is in closed form.
+struct ShapeDerivCoef {
+  double c_int_u, kappa, reaction, c_track;
+  int pull_back;
+};
+
 template <int D>
 __global__ void __launch_bounds__(128)
 k_shape_derivative_poisson(int64_t c_begin, int64_t c_end, const int32_t* __restrict__ cells,
                            const double* __restrict__ coords, int64_t nrows_owned,
                            const double* __restrict__ u, const double* __restrict__ p, cb_poly f,
-                           cb_poly gf0, cb_poly gf1, cb_poly gf2, cb_quad q, double c_int_u,
-                           const uint8_t* __restrict__ bc_flag, double* __restrict__ rhs,
-                           double* __restrict__ cell_out) {
+                           cb_poly gf0, cb_poly gf1, cb_poly gf2, cb_quad q, ShapeDerivCoef co,
+                           const double* __restrict__ ud, const uint8_t* __restrict__ bc_flag,
+                           double* __restrict__ rhs, double* __restrict__ cell_out) {
   constexpr int K = D + 1;
+  constexpr double MREF = 1.0 / ((D + 1) * (D + 2));
   for (int64_t c = c_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < c_end;
        c += (int64_t)gridDim.x * blockDim.x) {
     CellData<D> cd;
     load_cell_data<D>(cells, coords, c, cd);
     const double vol = cd.g.vol;
-    double ue[K], pe[K], usum = 0.0;
+    double ue[K], pe[K], usum = 0.0, psum = 0.0, up = 0.0;
 #pragma unroll
-    for (int a = 0; a < K; ++a) { ue[a] = u[cd.v[a]]; pe[a] = p[cd.v[a]]; usum += ue[a]; }
+    for (int a = 0; a < K; ++a) {
+      ue[a] = u[cd.v[a]]; pe[a] = p[cd.v[a]];
+      usum += ue[a]; psum += pe[a]; up += ue[a] * pe[a];
+    }
     double gu[D], gp[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
@@ -375,28 +388,53 @@ k_shape_derivative_poisson(int64_t c_begin, int64_t c_end, const int32_t* __rest
 #pragma unroll
       for (int i = 0; i < D; ++i) igf[a][i] = 0.0;
     }
-    for (int iq = 0; iq < q.nq; ++iq) {
-      double xq[3] = {0.0, 0.0, 0.0};
-      double pq = 0.0;
+    if (f.nterms > 0) {
+      for (int iq = 0; iq < q.nq; ++iq) {
+        double xq[3] = {0.0, 0.0, 0.0};
+        double pq = 0.0;
 #pragma unroll
-      for (int a = 0; a < K; ++a) {
-        pq += q.lam[iq][a] * pe[a];
+        for (int a = 0; a < K; ++a) {
+          pq += q.lam[iq][a] * pe[a];
 #pragma unroll
-        for (int i = 0; i < D; ++i) xq[i] += q.lam[iq][a] * cd.x[a][i];
-      }
-      const double wp = q.w[iq] * pq;
-      int_fp += wp * poly_eval(f, xq[0], xq[1], xq[2]);
-      double gfq[3];
-      gfq[0] = poly_eval(gf0, xq[0], xq[1], xq[2]);
-      gfq[1] = poly_eval(gf1, xq[0], xq[1], xq[2]);
-      gfq[2] = (D == 3) ? poly_eval(gf2, xq[0], xq[1], xq[2]) : 0.0;
+          for (int i = 0; i < D; ++i) xq[i] += q.lam[iq][a] * cd.x[a][i];
+        }
+        const double wp = q.w[iq] * pq;
+        int_fp += wp * poly_eval(f, xq[0], xq[1], xq[2]);
+        double gfq[3];
+        gfq[0] = poly_eval(gf0, xq[0], xq[1], xq[2]);
+        gfq[1] = poly_eval(gf1, xq[0], xq[1], xq[2]);
+        gfq[2] = (D == 3) ? poly_eval(gf2, xq[0], xq[1], xq[2]) : 0.0;
 #pragma unroll
-      for (int a = 0; a < K; ++a) {
+        for (int a = 0; a < K; ++a) {
 #pragma unroll
-        for (int i = 0; i < D; ++i) igf[a][i] += wp * q.lam[iq][a] * gfq[i];
+          for (int i = 0; i < D; ++i) igf[a][i] += wp * q.lam[iq][a] * gfq[i];
+        }
       }
     }
-    const double s0 = c_int_u * vol * usum * (1.0 / K) + vol * gugp - vol * int_fp;
+    // Lagrangian density integrated over the cell (the factor of div V = G_a[i])
+    double s0 = co.c_int_u * vol * usum * (1.0 / K) + co.kappa * vol * gugp - vol * int_fp;
+    if (co.reaction != 0.0) s0 += co.reaction * vol * MREF * (usum * psum + up);
+    double gud[D], mw[K];
+#pragma unroll
+    for (int i = 0; i < D; ++i) gud[i] = 0.0;
+#pragma unroll
+    for (int a = 0; a < K; ++a) mw[a] = 0.0;
+    if (co.c_track != 0.0) {
+      double we[K], wsum = 0.0, ww = 0.0;
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        const double uda = ud[cd.v[a]];
+        we[a] = ue[a] - uda;
+        wsum += we[a]; ww += we[a] * we[a];
+#pragma unroll
+        for (int i = 0; i < D; ++i) gud[i] += uda * cd.g.G[a][i];
+      }
+      s0 += 0.5 * co.c_track * vol * MREF * (wsum * wsum + ww);
+      if (co.pull_back) {
+#pragma unroll
+        for (int a = 0; a < K; ++a) mw[a] = co.c_track * vol * MREF * (wsum + we[a]);  // c_t int (u - u_d) phi_a
+      }
+    }
 #pragma unroll
     for (int a = 0; a < K; ++a) {
       if (!cell_out && cd.v[a] >= nrows_owned) continue;
@@ -405,7 +443,7 @@ k_shape_derivative_poisson(int64_t c_begin, int64_t c_end, const int32_t* __rest
       for (int i = 0; i < D; ++i) { Ggu += cd.g.G[a][i] * gu[i]; Ggp += cd.g.G[a][i] * gp[i]; }
 #pragma unroll
       for (int i = 0; i < D; ++i) {
-        double e = cd.g.G[a][i] * s0 - vol * (Ggu * gp[i] + Ggp * gu[i]) - vol * igf[a][i];
+        double e = cd.g.G[a][i] * s0 - co.kappa * vol * (Ggu * gp[i] + Ggp * gu[i]) - vol * igf[a][i] - mw[a] * gud[i];
         const int64_t dof = (int64_t)cd.v[a] * D + i;
         if (bc_flag && bc_flag[dof]) e = 0.0;
         if (cell_out) cell_out[(c * K + a) * D + i] = e;
@@ -564,29 +602,30 @@ extern "C" int cb_assemble_elasticity(void* stream, const cb_mesh_view* m, const
   });
 }
 
-extern "C" int cb_assemble_shape_derivative_poisson(void* stream, const cb_mesh_view* m,
-                                                    const double* u, const double* p,
-                                                    const cb_poly* f, const cb_poly* gradf,
-                                                    const cb_quad* q, double c_int_u,
-                                                    const uint8_t* bc_flag, double* rhs) {
+extern "C" int cb_assemble_shape_derivative(void* stream, const cb_mesh_view* m, const double* u, const double* p,
+                                            const cb_poly* f, const cb_poly* gradf, const cb_quad* q, double c_int_u,
+                                            double kappa, double reaction, double c_track, const double* u_d,
+                                            int pull_back, const uint8_t* bc_flag, double* rhs) {
   if (int e = check_view(m)) return e;
   CB_REQUIRE(u && p && f && gradf && q && rhs, "missing argument");
+  CB_REQUIRE(c_track == 0.0 || u_d, "cb_assemble_shape_derivative: the tracking term needs u_d");
   cudaStream_t s = as_stream(stream);
   cb_poly gz;
   memset(&gz, 0, sizeof(gz));
+  const ShapeDerivCoef co{c_int_u, kappa, reaction, c_track, pull_back};
   if (m->cells_orig && m->v2c_ptr && m->v2c_idx && m->cell_scratch) {
     const int64_t nc = m->colour_off[m->ncolours];
     const int grid = grid_for(nc, 128, 12), vgrid = grid_for(m->nrows_owned, 256, 8);
     if (m->dim == 2) {
       k_shape_derivative_poisson<2><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, m->coords, m->nrows_owned, u, p, *f,
-                                                        gradf[0], gradf[1], gz, *q, c_int_u, bc_flag, rhs,
+                                                        gradf[0], gradf[1], gz, *q, co, u_d, bc_flag, rhs,
                                                         m->cell_scratch);
       CB_LAUNCH_CHECK();
       k_gather_cell_vectors<2, 2><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
                                                        m->cell_scratch, rhs);
     } else {
       k_shape_derivative_poisson<3><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, m->coords, m->nrows_owned, u, p, *f,
-                                                        gradf[0], gradf[1], gradf[2], *q, c_int_u, bc_flag, rhs,
+                                                        gradf[0], gradf[1], gradf[2], *q, co, u_d, bc_flag, rhs,
                                                         m->cell_scratch);
       CB_LAUNCH_CHECK();
       k_gather_cell_vectors<3, 3><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
@@ -599,13 +638,22 @@ extern "C" int cb_assemble_shape_derivative_poisson(void* stream, const cb_mesh_
   return for_each_colour(m, [&](int64_t b, int64_t e, int grid) {
     if (m->dim == 2)
       k_shape_derivative_poisson<2><<<grid, 128, 0, s>>>(b, e, m->cells, m->coords, m->nrows_owned, u, p,
-                                                        *f, gradf[0], gradf[1], gz, *q, c_int_u,
+                                                        *f, gradf[0], gradf[1], gz, *q, co, u_d,
                                                         bc_flag, rhs, nullptr);
     else
       k_shape_derivative_poisson<3><<<grid, 128, 0, s>>>(b, e, m->cells, m->coords, m->nrows_owned, u, p,
-                                                        *f, gradf[0], gradf[1], gradf[2], *q, c_int_u,
+                                                        *f, gradf[0], gradf[1], gradf[2], *q, co, u_d,
                                                         bc_flag, rhs, nullptr);
   });
+}
+
+// the special case the C-ABI started with: kappa = 1, no reaction, J = c int u
+extern "C" int cb_assemble_shape_derivative_poisson(void* stream, const cb_mesh_view* m,
+                                                    const double* u, const double* p,
+                                                    const cb_poly* f, const cb_poly* gradf,
+                                                    const cb_quad* q, double c_int_u,
+                                                    const uint8_t* bc_flag, double* rhs) {
+  return cb_assemble_shape_derivative(stream, m, u, p, f, gradf, q, c_int_u, 1.0, 0.0, 0.0, nullptr, 0, bc_flag, rhs);
 }
 
 extern "C" int cb_ident_zeros(void* stream, int64_t nrows, int bs, const int64_t* rowptr,

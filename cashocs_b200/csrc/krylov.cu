@@ -372,6 +372,19 @@ k_cheb_step(int64_t n, const double* __restrict__ r, const double* __restrict__ 
   }
 }
 
+// b (replicated level, global row order) from the all-gathered buffer [own rows | rows of the other ranks in rank order]
+__global__ void __launch_bounds__(256)
+k_unpack_allgather(int64_t n_total, int64_t n_own, int64_t lo, int bs, const double* __restrict__ tmp,
+                   double* __restrict__ b, const KspState* st) {
+  if (st->done) return;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n_total * bs;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = q / bs;
+    const int64_t src = (i < lo) ? (n_own + i) : (i < lo + n_own ? i - lo : i);
+    b[q] = tmp[src * bs + (q - i * bs)];
+  }
+}
+
 // out[i, :] = in[gid[i], :]  (local copy of a replicated coarse vector in this rank's coarse numbering)
 __global__ void __launch_bounds__(256)
 k_gather_nodes(int64_t n, int bs, const int32_t* __restrict__ gid, const double* __restrict__ in,
@@ -912,10 +925,20 @@ struct Solver {
       if (nxt.rep_dist) {
         // agglomeration: the next level is replicated on every rank; this rank contributes its
         // rows of the restricted residual, one all-reduce assembles the global vector everywhere
-        const size_t len = sizeof(double) * (size_t)(nxt.A.nrows * bs);
-        CB_CUDA_CHECK(cudaMemsetAsync(nxt.b, 0, len, s));
-        if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.b + nxt.rep_off * bs, &st->done, h->p_block)) return e;
-        if (int e = dist_allreduce_sum(s, nxt.rep_dist, nxt.b, (int)(nxt.A.nrows * bs))) return e;
+        if (nxt.rep_gather && dist_is_one_sided(nxt.rep_gather)) {
+          // every coarse row is produced by exactly one rank: one-sided all-gather (one exchange kernel) + unpack
+          if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.rep_tmp, &st->done, h->p_block)) return e;
+          if (int e = dist_halo_exchange(s, nxt.rep_gather, nxt.rep_tmp, bs, nullptr)) return e;
+          const int64_t n_own = lev.nc;
+          k_unpack_allgather<<<grid_for(nxt.A.nrows * bs, 256, 4), 256, 0, s>>>(nxt.A.nrows, n_own, nxt.rep_off, bs,
+                                                                              nxt.rep_tmp, nxt.b, st);
+          CB_LAUNCH_CHECK();
+        } else {
+          const size_t len = sizeof(double) * (size_t)(nxt.A.nrows * bs);
+          CB_CUDA_CHECK(cudaMemsetAsync(nxt.b, 0, len, s));
+          if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.b + nxt.rep_off * bs, &st->done, h->p_block)) return e;
+          if (int e = dist_allreduce_sum(s, nxt.rep_dist, nxt.b, (int)(nxt.A.nrows * bs))) return e;
+        }
       } else {
         if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.b, &st->done, h->p_block)) return e;
       }

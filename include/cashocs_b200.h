@@ -160,6 +160,18 @@ int cb_assemble_shape_derivative_poisson(void* stream, const cb_mesh_view* m, co
                                          const double* p, const cb_poly* f, const cb_poly* gradf,
                                          const cb_quad* q, double c_int_u,
                                          const uint8_t* bc_flag, double* rhs);
+/* The same for the whole supported Lagrangian family
+ *   L = int c_int_u u + c_track/2 (u - u_d)^2 + kappa grad u . grad p + reaction u p - f p dx
+ * with P1 u, p and a P1 (vertex-valued) desired state u_d (nullable when c_track = 0):
+ *   dL[V] = int (density of L) divV - kappa (gradV + gradV^T) gu.gp - (gradf.V) p
+ *           - [pull_back] c_track (u - u_d) (grad u_d . V)
+ * -- the last term is the pull-back the reference adds for coefficients that are Functions
+ * (cashocs/_forms/shape_form_handler.py:507-531, `[ShapeGradient] use_pull_back`); analytic forms:
+ * tests/test_shape_optimization.py:252-259, :284-291. */
+int cb_assemble_shape_derivative(void* stream, const cb_mesh_view* m, const double* u, const double* p,
+                                 const cb_poly* f, const cb_poly* gradf, const cb_quad* q, double c_int_u,
+                                 double kappa, double reaction, double c_track, const double* u_d,
+                                 int pull_back, const uint8_t* bc_flag, double* rhs);
 
 /* PETScMatrix.ident_zeros (cashocs/_utils/linalg.py:167): rows with |row|_1 < 3e-16 get a
  * unit diagonal.  n_fixed (device int64, nullable) receives the number of rows fixed. */
@@ -302,6 +314,12 @@ typedef struct {
   const int32_t* coarse_gid;/* [AP.ncols] position of every local coarse node in the replicated next level
                              * (only when the next level has rep_dist) */
   double* xc_local;         /* [AP.ncols*bs] gather buffer for that case */
+  /* One-sided all-gather of the restricted residual of a replicated level (replaces memset + NCCL all-reduce: aggregates
+   * never cross ranks, so every coarse row is produced by exactly one rank).  rep_gather: halo plan whose "ghosts" are
+   * all other ranks' rows, in rank order; rep_tmp [A.nrows*bs]: this rank's rows first, then the ghosts; rep_lo: number
+   * of rows owned by lower ranks (== rep_off).  NULL: the all-reduce path. */
+  cb_dist* rep_gather;
+  double* rep_tmp;
 } cb_amg_level;
 typedef struct {
   int32_t nlevels;

@@ -118,11 +118,26 @@ class PoissonShapeProblem:
         mu_ksp=None,
         state_degree: int = 1,
         c_state: float = 1.0,
+        kappa: float = 1.0,
+        reaction: float = 0.0,
+        c_track: float = 0.0,
+        u_d=None,
+        use_pull_back: bool = True,
     ):
+        """State ``kappa grad u . grad p + reaction u p - f p`` (= 0), cost
+        ``J = c_state int u + c_track / 2 int (u - u_d)^2`` with a P1 (vertex-valued) ``u_d`` that is transported with the
+        mesh -- the ``J_func`` case of ``tests/test_shape_optimization.py:247-299``; its gradient enters the shape
+        derivative through the pull-back of ``shape_form_handler.py:507-531`` unless ``use_pull_back`` is off."""
         self.mesh = mesh
         self.c_state = float(c_state)  # J = c_state * int u dx (tests with J = Constant(0)*dx use 0)
-        if state_degree == 2 and c_state != 1.0:
-            raise ValueError("oracle: the P2 shape derivative is written for J = int u")
+        self.kappa, self.reaction, self.c_track = float(kappa), float(reaction), float(c_track)
+        self.u_d = None if u_d is None else np.asarray(u_d, dtype=float)
+        self.use_pull_back = bool(use_pull_back)
+        if self.c_track != 0.0 and self.u_d is None:
+            raise ValueError("oracle: the tracking term needs u_d")
+        general = (self.kappa != 1.0 or self.reaction != 0.0 or self.c_track != 0.0)
+        if state_degree == 2 and (c_state != 1.0 or general):
+            raise ValueError("oracle: the P2 shape derivative is written for J = int u, kappa = 1, no reaction")
         self.state_degree = int(state_degree)  # CG degree of the state / adjoint space (configs[4]: 2)
         self.coords = mesh.coords  # moved in place by move_mesh
         self.cells = mesh.cells
@@ -266,7 +281,7 @@ class PoissonShapeProblem:
             be = p2.load_elements_callable(self.coords, self.cells, vol, self.f, self.f_degree)
             A, b = fem.assemble_system(Ke, be, self.p2_dofs, self.n_state, self.state_bc, 0.0)
         else:
-            Ke = fem.stiffness_elements(vol, G)
+            Ke = self.kappa * fem.stiffness_elements(vol, G) + self.reaction * fem.mass_elements(vol, self.d)
             be = fem.load_elements_callable(self.coords, self.cells, vol, self.f, self.f_degree + 1)
             A, b = fem.assemble_system(Ke, be, self.cells, self.nv, self.state_bc, 0.0)
         self.u, reason, its, _ = krylov.solve(A, b, self.state_ksp)
@@ -282,8 +297,10 @@ class PoissonShapeProblem:
             be = -self.c_state * vol[:, None] * p2.reference_tensors(self.d)[2][None, :]  # -dJ/du[v] = -c int v
             A, b = fem.assemble_system(Ke, be, self.p2_dofs, self.n_state, self.state_bc, 0.0)
         else:
-            Ke = fem.stiffness_elements(vol, G)
+            Ke = self.kappa * fem.stiffness_elements(vol, G) + self.reaction * fem.mass_elements(vol, self.d)
             be = -self.c_state * fem.load_elements_p1(vol, self.cells, np.ones(self.nv), self.d)  # -dJ/du[v] = -c int v
+            if self.c_track != 0.0:  # - c_track int (u - u_d) v
+                be = be - self.c_track * fem.load_elements_p1(vol, self.cells, self.u - self.u_d, self.d)
             A, b = fem.assemble_system(Ke, be, self.cells, self.nv, self.state_bc, 0.0)
         self.p, reason, its, _ = krylov.solve(A, b, self.adjoint_ksp)
         self._check(reason)
@@ -302,7 +319,11 @@ class PoissonShapeProblem:
         reg = self.regularization_objective()  # cost_functional.py:84-86
         if self.state_degree == 2:
             return self.c_state * p2.integral(self.u, self.p2_dofs, vol, self.d) + reg
-        return self.c_state * float(np.sum(vol * self.u[self.cells].mean(axis=1))) + reg
+        J = self.c_state * float(np.sum(vol * self.u[self.cells].mean(axis=1)))
+        if self.c_track != 0.0:
+            w = (self.u - self.u_d)[self.cells]
+            J += 0.5 * self.c_track * float(np.einsum("ca,cab,cb->", w, fem.mass_elements(vol, self.d), w))
+        return J + reg
 
     # -- Lame mu (a5)
     def compute_mu(self):
@@ -368,11 +389,23 @@ class PoissonShapeProblem:
         gugp = np.einsum("ci,ci->c", gu, gp)
         Ggu = np.einsum("cai,ci->ca", G, gu)
         Ggp = np.einsum("cai,ci->ca", G, gp)
+        # Lagrangian density integrated over the cell (multiplies div V = G_a[i]); SURVEY.md 9.2 generalised to
+        # kappa, a reaction term and the tracking functional
+        Me = fem.mass_elements(vol, d)
+        dens = int_u + self.kappa * vol * gugp - int_fp
+        if self.reaction != 0.0:
+            dens = dens + self.reaction * np.einsum("ca,cab,cb->c", ue, Me, pe)
         be = (
-            G * (int_u + vol * gugp - int_fp)[:, None, None]
-            - vol[:, None, None] * (Ggu[:, :, None] * gp[:, None, :] + Ggp[:, :, None] * gu[:, None, :])
+            - self.kappa * vol[:, None, None] * (Ggu[:, :, None] * gp[:, None, :] + Ggp[:, :, None] * gu[:, None, :])
             - int_gf_phi_p
         )
+        if self.c_track != 0.0:
+            we = ue - self.u_d[self.cells]
+            dens = dens + 0.5 * self.c_track * np.einsum("ca,cab,cb->c", we, Me, we)
+            if self.use_pull_back:  # - c_track int (u - u_d) (d_i u_d) phi_a   (u_d is P1: its gradient is cellwise constant)
+                gud = np.einsum("ca,cai->ci", self.u_d[self.cells], G)
+                be = be - self.c_track * np.einsum("cab,cb->ca", Me, we)[:, :, None] * gud[:, None, :]
+        be = be + G * dens[:, None, None]
         return be.reshape(self.cells.shape[0], -1)
 
     def shape_derivative_vector(self):

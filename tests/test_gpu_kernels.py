@@ -147,6 +147,27 @@ def test_shape_derivative_matches_oracle(kind):
 
 
 @pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("pull_back", [True, False])
+def test_general_shape_derivative_matches_oracle(kind, pull_back):
+    """cb_assemble_shape_derivative for the whole Lagrangian family: kappa != 1, a reaction term and the tracking
+    functional c_track/2 (u - u_d)^2 with a P1 u_d (the `J_func` case of tests/test_shape_optimization.py:247-299,
+    including the pull-back term of shape_form_handler.py:507-531) against the oracle, <= 1e-12."""
+    om, dm = oracle_mesh(kind), device_mesh(kind)
+    d = om.dim
+    r = np.random.RandomState(7)
+    ud = om.coords[:, 0] ** 2 + om.coords[:, 1] ** 4 - np.pi
+    prob = pipeline.PoissonShapeProblem(om, bc_markers=(1,), config=pipeline.ShapeConfig(shape_bdry_fix=(2,) if kind != "circle" else ()),
+                                        kappa=1.7, reaction=0.8, c_state=0.3, c_track=2.0, u_d=ud, use_pull_back=pull_back)
+    prob.u, prob.p = r.rand(om.num_vertices), r.rand(om.num_vertices)
+    b0 = prob.shape_derivative_vector()
+    flag, _ = forms.bc_flag_arrays(dm, forms.create_dirichlet_bcs(0.0, [2] if kind != "circle" else []), d)
+    b = linalg.assemble_shape_derivative(dm, torch.from_numpy(prob.u).cuda(), torch.from_numpy(prob.p).cuda(),
+                                         demo_poly(d), 0.3, bc_flag=flag, kappa=1.7, reaction=0.8, c_track=2.0,
+                                         u_d=torch.from_numpy(ud).cuda(), pull_back=pull_back)
+    assert rel(b.cpu().numpy(), b0) < 1e-12
+
+
+@pytest.mark.parametrize("kind", KINDS)
 def test_spmv_and_scalar_product(kind):
     om, dm = oracle_mesh(kind), device_mesh(kind)
     d = om.dim

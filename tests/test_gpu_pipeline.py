@@ -120,6 +120,38 @@ def test_parity_at_the_benchmarked_solver_settings(n, variant):
     assert max(errs.values()) < 1e-8, errs
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_tracking_reaction_kappa_pipeline(dim):
+    """Shape gradient of the general member of the form family -- kappa grad u . grad p + c u p - f p with the tracking
+    functional c_s int u + c_t/2 int (u - u_d)^2 (P1 u_d, `tests/test_shape_optimization.py:247-299`): state, adjoint,
+    cost and gradient against the oracle (<= 1e-8), and, with `use_pull_back = False` (u_d is transported with the mesh,
+    which is what the discrete cost functional does), the reference's Taylor criterion rate > 1.9."""
+    n = 10 if dim == 2 else 5
+    dm = cb.regular_mesh(n) if dim == 2 else cb.regular_mesh(n, 1.0, 1.0, 1.0)
+    om = meshes.regular_mesh(n) if dim == 2 else meshes.regular_mesh(n, 1.0, 1.0, 1.0)
+    markers = (1, 2, 3, 4) if dim == 2 else (1, 2, 3, 4, 5, 6)
+    ud_np = om.coords[:, 0] ** 2 + om.coords[:, 1] ** 4 - np.pi
+    for pull_back in (True, False):
+        cfg = sop_config(shape_bdry_def=str(list(markers)))
+        cfg.set("ShapeGradient", "use_pull_back", str(pull_back))
+        u, p, ud = cb.Function(dm), cb.Function(dm), cb.Function(dm)
+        ud.vector.copy_(torch.from_numpy(ud_np).cuda())
+        form = cb.PoissonForm(source=demo_poly(dim), kappa=1.7, reaction=0.8)
+        J = cb.IntegralFunctional(c_state=0.3, c_track=2.0, desired_state=ud)
+        sop = cb.ShapeOptimizationProblem(form, cb.create_dirichlet_bcs(0.0, list(markers)), J, u, p, config=cfg,
+                                          ksp_options=KSP, adjoint_ksp_options=KSP, gradient_ksp_options=KSP)
+        prob = pipeline.PoissonShapeProblem(om, bc_markers=markers, config=pipeline.ShapeConfig(shape_bdry_def=markers),
+                                            kappa=1.7, reaction=0.8, c_state=0.3, c_track=2.0, u_d=ud_np,
+                                            use_pull_back=pull_back)
+        g0 = prob.compute_shape_gradient()
+        g1 = sop.compute_shape_gradient()[0].vector.cpu().numpy()
+        assert rel(u.vector.cpu().numpy(), prob.u) < 1e-8 and rel(p.vector.cpu().numpy(), prob.p) < 1e-8
+        assert abs(sop.reduced_cost_functional.evaluate() - prob.cost()) <= 1e-10 * abs(prob.cost())
+        assert rel(g1, g0) < 1e-8
+        if not pull_back:
+            assert sop.gradient_test(rng=np.random.RandomState(300696)) > 1.9
+
+
 def test_taylor_test_rate():
     """tests/test_shape_optimization.py:302-318: rate > 1.9."""
     dm, _ = circle()

@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.cb_mat) == 56
     assert ctypes.sizeof(_lib.cb_mesh_view) == 120
     assert ctypes.sizeof(_lib.cb_ksp_opts) == 104
-    assert ctypes.sizeof(_lib.cb_amg_level) == 264
+    assert ctypes.sizeof(_lib.cb_amg_level) == 280
     assert ctypes.sizeof(_lib.cb_amg) == 56
     assert ctypes.sizeof(_lib.cb_ksp_result) == 40
     # ... and the ctypes mirrors agree with what the compiled library itself reports
