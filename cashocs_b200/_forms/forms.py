@@ -8,7 +8,7 @@ supported family they mean; the descriptors carry exactly the data the element k
 ``fenics_adapter`` recognises these forms in UFL input when FEniCS is importable.
 
 Supported family:
-    F(u, p) = kappa * grad(u).grad(p) dx + c * u p dx - f p dx ,   u = g on Dirichlet markers
+    F(u, p) = kappa * grad(u).grad(p) dx + c * u p dx + c3 * u^3 p dx - f p dx ,   u = g on Dirichlet markers
     J(u)    = int alpha_u * u dx  +  1/2 int (u - u_d)^2 dx  +  alpha/2 int control^2 dx
 """
 
@@ -131,10 +131,17 @@ class PoissonForm:
     kappa: float = 1.0
     reaction: float = 0.0
     source_scale: float = 1.0
+    # semilinear member of the family: + cubic * u**3 * p * dx (tests/test_nonlinear_solvers.py:28-61,
+    # tests/test_optimal_control.py:364-376); solved by Newton's method, the state config must have is_linear = False
+    cubic: float = 0.0
 
     @property
     def is_self_adjoint(self) -> bool:
         return True
+
+    @property
+    def is_nonlinear(self) -> bool:
+        return self.cubic != 0.0
 
 
 @dataclasses.dataclass

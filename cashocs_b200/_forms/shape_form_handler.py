@@ -152,6 +152,10 @@ class ShapeFormHandler:
         if not isinstance(src, (type(None),)) and not hasattr(src, "terms"):
             raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "source",
                                          "shape problems need a polynomial (coordinate) source term")
+        if getattr(self.state_form, "cubic", 0.0) != 0.0:
+            raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "forms",
+                                         "the shape derivative of the cubic term is not implemented (semilinear states: "
+                                         "optimal control problems)")
         general = self.cost.c_track != 0.0 or self.state_form.reaction != 0.0 or self.state_form.kappa != 1.0
         if general and self.state.degree == 2:
             raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "forms",

@@ -201,6 +201,7 @@ SIGNATURES = {
                                                    C.POINTER(cb_poly), C.POINTER(cb_quad), DBL, P, P]),
     "cb_assemble_shape_derivative": (I32, [P, C.POINTER(cb_mesh_view), P, P, C.POINTER(cb_poly), C.POINTER(cb_poly),
                                            C.POINTER(cb_quad), DBL, DBL, DBL, DBL, P, I32, P, P]),
+    "cb_assemble_cubic": (I32, [P, C.POINTER(cb_mesh_view), P, DBL, C.POINTER(cb_quad), P, P, P]),
     "cb_ident_zeros": (I32, [P, I64, I32, P, P, P, P]),
     "cb_p2_assemble_matrix": (I32, [P, C.POINTER(cb_p2_view), DBL, DBL, P, P]),
     "cb_p2_assemble_rhs": (I32, [P, C.POINTER(cb_p2_view), DBL, DBL, DBL, C.POINTER(cb_poly), I32, P, DBL, DBL, P,

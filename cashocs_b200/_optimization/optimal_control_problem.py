@@ -151,6 +151,12 @@ class OptimalControlProblem:
         self.adjoint_problem.has_solution = False
         self.gradient_problem.has_solution = False
 
+    def gradient_test(self, u=None, h=None, rng=None) -> float:
+        """``cashocs.verification.control_gradient_test`` on this problem."""
+        from cashocs_b200 import verification
+
+        return verification.control_gradient_test(self, u, h, rng)
+
 
 class _ControlFormHandler:
     """The part of ``ControlFormHandler`` the optimisation loop touches: the Riesz scalar product

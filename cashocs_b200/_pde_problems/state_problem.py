@@ -115,6 +115,60 @@ class StateProblem(pde_problem.PDEProblem):
         if not (res <= tol):
             raise _exceptions.NotConvergedError("Newton solver", "Maximum number of iterations were exceeded.")
 
+    def _newton_solve_semilinear(self, i: int, A, b) -> None:
+        """``newton_solve`` (``newton_solver.py:285-362``) for F(u) = A u + c int u^3 phi - b: residual and Jacobian
+        re-assembled on the device in every step (``cb_assemble_cubic``), undamped full steps, convergence on
+        ``||F(u)|| <= atol + rtol ||F(u_0)||`` ("combined"), ``NotConvergedError`` after ``newton_iter`` steps.  ``A``,
+        ``b`` hold the linear part with its Dirichlet elimination and lifting, so on the free rows A u - b is the
+        linear residual for an iterate that carries the boundary values."""
+        form = self.state_forms[i]
+        if self.spaces[i] is not None:
+            raise _exceptions.InputError("cashocs_b200.StateProblem", "state_forms", "semilinear states are P1")
+        mesh, plan = self.mesh, self.mesh.dist
+        n = A.nrows
+        u = self.states[i].vector
+        flag, val = self.bc_arrays[i]
+        if flag is not None:
+            u.copy_(torch.where(flag.bool(), val, u))
+        lin_val = A.val.clone()  # linear part of the Jacobian; the cubic part is added to a fresh copy per step
+        cub = torch.zeros(n, dtype=torch.float64, device=u.device)
+        free = None if flag is None else (~flag[:n].bool())
+
+        def residual():
+            if plan is not None:
+                plan.halo_exchange(u, 1)
+            linalg.assemble_cubic(mesh, u, form.cubic, vec=cub)
+            r = A_lin.mult(u) - b + cub
+            if free is not None:
+                r = r * free
+            nrm2 = torch.sum(r * r).reshape(1)
+            if plan is not None:
+                plan.allreduce(nrm2, "sum")
+            return r, float(nrm2.sqrt().item())
+
+        A_lin = linalg.Matrix(A.mesh, 1, val=lin_val)
+        r, res0 = residual()
+        self.newton_iterations[i] = 0
+        self.iterations[i] = 0
+        if res0 == 0.0:
+            return
+        tol = self.newton_atol + self.newton_rtol * res0
+        res = res0
+        du = torch.zeros_like(u)
+        while res > tol and self.newton_iterations[i] < self.newton_iter:
+            self.newton_iterations[i] += 1
+            A.val.copy_(lin_val)
+            linalg.assemble_cubic(mesh, u, form.cubic, bc_flag=flag, A=A)  # J(u) = A_lin + 3 c M[u^2]
+            out = self.linear_solver.solve(du, A=A, b=-r, ksp_options=self.ksp_options[i])
+            self.iterations[i] += out.its
+            u[:n].add_(du[:n])
+            r, res = residual()
+        if not (res <= tol):
+            raise _exceptions.NotConvergedError("Newton solver", "Maximum number of iterations were exceeded.")
+        # leave the Jacobian at the solution in A: the adjoint operator (self-adjoint linearisation)
+        A.val.copy_(lin_val)
+        linalg.assemble_cubic(mesh, u, form.cubic, bc_flag=flag, A=A)
+
     def solve(self):
         if not self.has_solution:
             if self.pre_callback is not None:
@@ -122,6 +176,12 @@ class StateProblem(pde_problem.PDEProblem):
             self._generate_checkpoint()
             for i in range(len(self.states)):
                 A, b = self.assemble(i)
+                if self.state_forms[i].is_nonlinear:
+                    if self.is_linear:
+                        raise _exceptions.InputError("cashocs_b200.StateProblem", "config",
+                                                     "the state equation is nonlinear: set [StateSystem] is_linear = False")
+                    self._newton_solve_semilinear(i, A, b)
+                    continue
                 if not self.is_linear:
                     self._newton_solve(i, A, b)
                     continue

@@ -323,6 +323,21 @@ def assemble_scalar_system(
     return (A if matrix else None), (b if rhs else None)
 
 
+def assemble_cubic(mesh, u: torch.Tensor, c: float, bc_flag: torch.Tensor | None = None, A: "Matrix | None" = None,
+                   vec: torch.Tensor | None = None) -> None:
+    """The cubic term ``c u^3 p`` of a semilinear state equation: adds its Jacobian ``3 c int u^2 phi_a phi_b`` to the
+    values of ``A`` (Dirichlet rows / columns untouched) and / or writes its load ``c int u^3 phi_a`` into ``vec`` --
+    what ``cashocs.newton_solve`` (``newton_solver.py:285-362``) re-assembles in every Newton step."""
+    lib = _lib.load()
+    view = mesh.view(gather=True)
+    _lib.require_cuda(u, bc_flag, vec)
+    quad = expressions.quadrature_struct(mesh.dim, 4)
+    _lib.check(lib.cb_assemble_cubic(_lib.stream_ptr(), C.byref(view), _lib.ptr(u), float(c), C.byref(quad), _lib.ptr(bc_flag),
+                                     _lib.ptr(A.val) if A is not None else None, _lib.ptr(vec)), "cb_assemble_cubic")
+    if A is not None:
+        A.touch()
+
+
 @log.profile_execution_time("assembling the system")
 def assemble_elasticity_matrix(mesh, mu: torch.Tensor, lambda_lame: float, damping: float,
                                bc_flag: torch.Tensor | None = None, cell_scale: torch.Tensor | None = None,

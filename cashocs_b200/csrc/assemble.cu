@@ -453,6 +453,81 @@ k_shape_derivative_poisson(int64_t c_begin, int64_t c_end, const int32_t* __rest
   }
 }
 
+// ------------------------------------------------------------------ semilinear states: c u^3 p
+// Residual and Jacobian of the cubic term of F(u)[v] = int kappa grad u . grad v + c0 u v + c u^3 v - f v dx
+// (the nonlinearity of the reference's tests: tests/test_nonlinear_solvers.py:28-61,
+// tests/test_optimal_control.py:364-376), which cashocs.newton_solve (nonlinear_solvers/newton_solver.py:285-362)
+// re-assembles in every Newton step:
+//   load_a  = c   |K| sum_q w_q u(x_q)^3 phi_a(x_q)                (k_cubic_load: one thread per cell -> scratch -> gather)
+//   M_ab   += 3 c |K| sum_q w_q u(x_q)^2 phi_a(x_q) phi_b(x_q)     (k_add_weighted_mass_gather: one thread per nnz entry)
+// with a rule exact for degree 4 (P1 u).  Entries of Dirichlet rows / columns are left alone: the symmetric
+// elimination of the linear part already made them identity rows, and the increment has homogeneous conditions.
+template <int D>
+__global__ void __launch_bounds__(256)
+k_cubic_load(int64_t nc, const int32_t* __restrict__ cells, const double* __restrict__ coords,
+             const double* __restrict__ u, double c, cb_quad q, double* __restrict__ cell_out) {
+  constexpr int K = D + 1;
+  for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < nc;
+       cell += (int64_t)gridDim.x * blockDim.x) {
+    CellData<D> cd;
+    load_cell_data<D>(cells, coords, cell, cd);
+    double ue[K], acc[K];
+#pragma unroll
+    for (int a = 0; a < K; ++a) { ue[a] = u[cd.v[a]]; acc[a] = 0.0; }
+    for (int iq = 0; iq < q.nq; ++iq) {
+      double uq = 0.0;
+#pragma unroll
+      for (int a = 0; a < K; ++a) uq += q.lam[iq][a] * ue[a];
+      const double w3 = q.w[iq] * uq * uq * uq;
+#pragma unroll
+      for (int a = 0; a < K; ++a) acc[a] += w3 * q.lam[iq][a];
+    }
+#pragma unroll
+    for (int a = 0; a < K; ++a) cell_out[cell * K + a] = c * cd.g.vol * acc[a];
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_add_weighted_mass_gather(int64_t nnz, const int64_t* __restrict__ n2c_ptr, const int32_t* __restrict__ n2c_idx,
+                           const int32_t* __restrict__ cells, const double* __restrict__ coords,
+                           const double* __restrict__ u, double c3, cb_quad q, const uint8_t* __restrict__ bc_flag,
+                           double* __restrict__ val) {
+  constexpr int K = D + 1;
+  constexpr int KK = K * K;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    const int64_t kb = n2c_ptr[e], ke = n2c_ptr[e + 1];
+    bool isbc = false;
+    for (int64_t k = kb; k < ke; ++k) {
+      const int32_t t = __ldg(n2c_idx + k);
+      const int64_t cell = t / KK;
+      const int ab = t - (int32_t)cell * KK;
+      const int a = ab / K, b = ab - a * K;
+      CellData<D> cd;
+      load_cell_data<D>(cells, coords, cell, cd);
+      if (k == kb && bc_flag) isbc = bc_flag[cd.v[a]] || bc_flag[cd.v[b]];
+      double ue[K];
+#pragma unroll
+      for (int v = 0; v < K; ++v) ue[v] = u[cd.v[v]];
+      double s = 0.0;
+      for (int iq = 0; iq < q.nq; ++iq) {
+        double uq = 0.0, la = 0.0, lb = 0.0;
+#pragma unroll
+        for (int v = 0; v < K; ++v) {
+          const double l = q.lam[iq][v];
+          uq += l * ue[v];
+          la = (v == a) ? l : la;
+          lb = (v == b) ? l : lb;
+        }
+        s += q.w[iq] * uq * uq * la * lb;
+      }
+      acc += c3 * cd.g.vol * s;
+    }
+    if (!isbc) val[e] += acc;
+  }
+}
+
 // ------------------------------------------------------------------ ident_zeros
 __global__ void k_ident_zeros(int64_t nrows, int bs, const int64_t* __restrict__ rowptr,
                               const int32_t* __restrict__ col, double* __restrict__ val,
@@ -654,6 +729,42 @@ extern "C" int cb_assemble_shape_derivative_poisson(void* stream, const cb_mesh_
                                                     const cb_quad* q, double c_int_u,
                                                     const uint8_t* bc_flag, double* rhs) {
   return cb_assemble_shape_derivative(stream, m, u, p, f, gradf, q, c_int_u, 1.0, 0.0, 0.0, nullptr, 0, bc_flag, rhs);
+}
+
+extern "C" int cb_assemble_cubic(void* stream, const cb_mesh_view* m, const double* u, double c, const cb_quad* q,
+                                 const uint8_t* bc_flag, double* val, double* vec) {
+  if (int e = check_view(m)) return e;
+  CB_REQUIRE(u && q, "cb_assemble_cubic: missing argument");
+  CB_REQUIRE(m->cells_orig && m->n2c_ptr && m->n2c_idx && m->v2c_ptr && m->v2c_idx && m->cell_scratch,
+             "cb_assemble_cubic needs the gather data of the mesh view");
+  cudaStream_t s = as_stream(stream);
+  const int64_t nc = m->colour_off[m->ncolours];
+  if (val) {
+    const int grid = grid_for(m->nnz, 256, 8);
+    if (m->dim == 2)
+      k_add_weighted_mass_gather<2><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->coords, u,
+                                                        3.0 * c, *q, bc_flag, val);
+    else
+      k_add_weighted_mass_gather<3><<<grid, 256, 0, s>>>(m->nnz, m->n2c_ptr, m->n2c_idx, m->cells_orig, m->coords, u,
+                                                        3.0 * c, *q, bc_flag, val);
+    CB_LAUNCH_CHECK();
+  }
+  if (vec) {
+    const int grid = grid_for(nc, 256, 8), vgrid = grid_for(m->nrows_owned, 256, 8);
+    if (m->dim == 2) {
+      k_cubic_load<2><<<grid, 256, 0, s>>>(nc, m->cells_orig, m->coords, u, c, *q, m->cell_scratch);
+      CB_LAUNCH_CHECK();
+      k_gather_cell_vectors<2, 1><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
+                                                       m->cell_scratch, vec);
+    } else {
+      k_cubic_load<3><<<grid, 256, 0, s>>>(nc, m->cells_orig, m->coords, u, c, *q, m->cell_scratch);
+      CB_LAUNCH_CHECK();
+      k_gather_cell_vectors<3, 1><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
+                                                       m->cell_scratch, vec);
+    }
+    CB_LAUNCH_CHECK();
+  }
+  return CB_OK;
 }
 
 extern "C" int cb_ident_zeros(void* stream, int64_t nrows, int bs, const int64_t* rowptr,

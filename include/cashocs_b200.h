@@ -173,6 +173,16 @@ int cb_assemble_shape_derivative(void* stream, const cb_mesh_view* m, const doub
                                  double kappa, double reaction, double c_track, const double* u_d,
                                  int pull_back, const uint8_t* bc_flag, double* rhs);
 
+/* Cubic term c u^3 p of a semilinear state equation, P1 u: what cashocs.newton_solve
+ * (cashocs/nonlinear_solvers/newton_solver.py:285-362) re-assembles per Newton step for the nonlinearity of
+ * tests/test_nonlinear_solvers.py:28-61 and tests/test_optimal_control.py:364-376.
+ *   val (nullable, scalar CSR of the mesh pattern): val += 3 c int u^2 phi_a phi_b  (the Jacobian of the term; entries
+ *       in Dirichlet rows / columns -- bc_flag, nullable -- are left alone: the linear part made them identity rows)
+ *   vec (nullable) [nrows_owned]: vec = c int u^3 phi_a  (overwritten; the caller zeroes Dirichlet rows)
+ * q: a rule exact for degree 4.  Needs the gather data of the view (cells_orig, n2c, v2c, cell_scratch). */
+int cb_assemble_cubic(void* stream, const cb_mesh_view* m, const double* u, double c, const cb_quad* q,
+                      const uint8_t* bc_flag, double* val, double* vec);
+
 /* PETScMatrix.ident_zeros (cashocs/_utils/linalg.py:167): rows with |row|_1 < 3e-16 get a
  * unit diagonal.  n_fixed (device int64, nullable) receives the number of rows fixed. */
 int cb_ident_zeros(void* stream, int64_t nrows, int bs, const int64_t* rowptr,

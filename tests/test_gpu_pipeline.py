@@ -239,6 +239,76 @@ def test_control_problem_matches_reference_definitions(rng):
     assert abs(ocp.reduced_cost_functional.evaluate() - ref.cost()) < 1e-10 * abs(ref.cost())
 
 
+def test_semilinear_state_newton_like_the_reference():
+    """SURVEY.md 8f row 1, the nonlinear state path on the device.
+    (i) tests/test_nonlinear_solvers.py:28-61: -Laplace u + 1e2 u^3 = 1 on regular_mesh(5), Newton from zero with
+    rtol 1e-9 / atol 1e-10: residual (`cb_assemble_cubic` load) and Jacobian (weighted mass) kernels against the
+    oracle's element tensors (<= 1e-12), the Newton iterates against `oracle.nonlinear.newton_solve` (same number of
+    steps, solution <= 1e-8).
+    (ii) tests/test_optimal_control.py:364-376: the semilinear control problem grad y . grad p + y^3 p - u p with
+    `is_linear = False`: state, adjoint (operator = Jacobian at the solution) and gradient against the oracle, and the
+    reference's own acceptance criterion, Taylor rate > 1.9."""
+    from cashocs_b200._utils import linalg
+    from oracle import fem, nonlinear
+
+    dm, om = cb.regular_mesh(5), meshes.regular_mesh(5)
+    rng = np.random.RandomState(11)
+    w = rng.rand(om.num_vertices)
+    _, vol, _ = fem.cell_geometry(om.coords, om.cells)
+    want_vec = fem.assemble_vector(nonlinear.cubic_load_elements(vol, om.cells, w, 2, 1e2), om.cells, om.num_vertices)
+    want_mat = fem.assemble_matrix(nonlinear.weighted_mass_elements(vol, om.cells, w, 2, 1e2), om.cells, om.num_vertices)
+    A = linalg.Matrix(dm, 1)
+    vec = torch.zeros(om.num_vertices, dtype=torch.float64, device="cuda")
+    linalg.assemble_cubic(dm, torch.from_numpy(w).cuda(), 1e2, A=A, vec=vec)
+    assert rel(vec.cpu().numpy(), want_vec) < 1e-12
+    got = A.to_scipy()
+    assert abs(got - want_mat).max() < 1e-12 * abs(want_mat).max()
+
+    # (i) Newton's method
+    cfg = cb.Config()
+    cfg.set("Output", "save_results", "False")
+    cfg.set("StateSystem", "is_linear", "False")
+    cfg.set("StateSystem", "newton_rtol", "1e-9")
+    cfg.set("StateSystem", "newton_atol", "1e-10")
+    cfg.set("StateSystem", "newton_iter", "50")
+    y, p, u, y_d = (cb.Function(dm) for _ in range(4))
+    u.vector.fill_(1.0)  # the source "Constant(1)" as the (P1) control
+    ocp = cb.OptimalControlProblem(cb.PoissonForm(source=u, cubic=1e2), cb.create_dirichlet_bcs(0.0, [1, 2, 3, 4]),
+                                   cb.IntegralFunctional(c_track=1.0, desired_state=y_d, c_control=1e-6), y, u, p, config=cfg,
+                                   ksp_options=KSP, adjoint_ksp_options=KSP, gradient_ksp_options=KSP)
+    ocp.state_problem.solve()
+    bc = om.boundary_vertices((1, 2, 3, 4))
+    load = fem.load_elements_p1(vol, om.cells, np.ones(om.num_vertices), 2)
+    u0, its0 = nonlinear.newton_solve(om.coords, om.cells, load, 1e2, bc, rtol=1e-9, atol=1e-10, max_iter=50)
+    assert ocp.state_problem.newton_iterations[0] == its0
+    assert rel(y.vector.cpu().numpy(), u0) < 1e-8
+
+    # (ii) the semilinear control problem
+    yd_h = np.sin(2 * np.pi * om.coords[:, 0]) * np.sin(2 * np.pi * om.coords[:, 1])
+    u_h = rng.rand(om.num_vertices)
+    y, p, u, y_d = (cb.Function(dm) for _ in range(4))
+    y_d.vector.copy_(torch.from_numpy(yd_h))
+    u.vector.copy_(torch.from_numpy(u_h))
+    cfg.set("StateSystem", "newton_rtol", "1e-11")
+    cfg.set("StateSystem", "newton_atol", "1e-13")
+    ocp = cb.OptimalControlProblem(cb.PoissonForm(source=u, cubic=1.0), cb.create_dirichlet_bcs(0.0, [1, 2, 3, 4]),
+                                   cb.IntegralFunctional(c_track=1.0, desired_state=y_d, c_control=1e-6), y, u, p, config=cfg,
+                                   ksp_options=KSP, adjoint_ksp_options=KSP, gradient_ksp_options=KSP)
+    g = ocp.compute_gradient()[0].vector.cpu().numpy()
+    ref = pipeline.PoissonControlProblem(om, yd_h, u_h, alpha=1e-6, bc_markers=(1, 2, 3, 4), cubic=1.0)
+    g0 = ref.compute_gradient()
+    assert np.allclose(y.vector.cpu().numpy(), ref.y, rtol=1e-8, atol=1e-12)
+    assert np.allclose(p.vector.cpu().numpy(), ref.p, rtol=1e-8, atol=1e-12)
+    assert np.allclose(g, g0, rtol=1e-8, atol=1e-12)
+    assert ocp.gradient_test(rng=np.random.RandomState(300696)) > 1.9
+    # a nonlinear form with is_linear = True is refused, as the reference's linear branch would silently mis-solve it
+    cfg.set("StateSystem", "is_linear", "True")
+    bad = cb.OptimalControlProblem(cb.PoissonForm(source=u, cubic=1.0), cb.create_dirichlet_bcs(0.0, [1, 2, 3, 4]),
+                                   cb.IntegralFunctional(c_track=1.0, desired_state=y_d, c_control=1e-6), y, u, p, config=cfg)
+    with pytest.raises(cb.InputError):
+        bad.state_problem.solve()
+
+
 CONTROL_BUDGETS = [("gd", {}, 46), ("bfgs", {}, 7), ("ncg", {"method": "FR"}, 20), ("ncg", {"method": "PR"}, 25),
                    ("ncg", {"method": "HS"}, 27), ("ncg", {"method": "DY"}, 9), ("ncg", {"method": "HZ"}, 27),
                    ("ncg", {"method": "DY", "periodic_restart": True, "periodic_its": 5}, 10),
