@@ -157,11 +157,19 @@ def test_bench_reference_arm_runs(tmp_path):
     import subprocess
     import sys
 
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-budget", "6"],
                          capture_output=True, text=True, check=True, timeout=600)
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+    # the line states what was measured: ms_per_step is the measured time of one sample evaluation, `value` the workload
+    # throughput it implies, `config` names the workload exactly like the B200 arm does
+    import bench
+
+    assert line["config"] == bench.workload_config(119, 1, "cube")
+    s_ = line["sample"]
+    assert abs(line["value"] - s_["fraction_of_workload"] / (line["ms_per_step"] * 1e-3)) <= 1e-9 * line["value"]
 
 
 def test_quadrature_rules_are_exact():
