@@ -123,10 +123,8 @@ class ShapeFormHandler:
         """Cell volumes normalised by their maximum (l2_projection of CellVolume, ``:629-644``)."""
         from cashocs_b200.geometry import measures
 
-        vol = measures.cell_volumes(self.mesh)
-        vmax = vol.max()
+        vol, vmax = measures.cell_volumes(self.mesh, with_max=True)
         if self.mesh.dist is not None:
-            vmax = vmax.reshape(1).clone()
             self.mesh.dist.allreduce(vmax, "max")
         expo = self.config.getfloat("ShapeGradient", "inhomogeneous_exponent")
         self.volumes = vol / vmax

@@ -228,6 +228,7 @@ SIGNATURES = {
     "cb_mesh_quality": (I32, [P, I32, I64, P, P, I32, P, P, P, I64]),
     "cb_det_check": (I32, [P, I32, I64, P, P, P, DBL, P, P, P, I64]),
     "cb_gradient_frobenius_max": (I32, [P, I32, I64, P, P, P, P, P, I64]),
+    "cb_cell_volumes": (I32, [P, I32, I64, P, P, P, P, P, I64]),
     "cb_move_mesh": (I32, [P, I64, P, P, P, DBL]),
     "cb_functional": (I32, [P, I32, I64, P, P, DBL, P, DBL, P, P, P, I64]),
     "cb_to_f32": (I32, [P, I64, P, P]),

@@ -203,6 +203,33 @@ __device__ __forceinline__ void field_gradient(const double* __restrict__ W, con
   }
 }
 
+// vol[c] = |K_c| and the maximum over the cells: CellVolume of the `inhomogeneous` elasticity scaling
+// (cashocs/_forms/shape_form_handler.py:629-644 projects it to DG0 with l2_projection, cashocs/_utils/linalg.py:768-809,
+// which is the identity for a cellwise constant; the form handler then divides by the maximum)
+template <int D>
+__global__ void __launch_bounds__(256)
+k_cell_volumes(int64_t nc, const double* __restrict__ coords, const int32_t* __restrict__ cells,
+               double* __restrict__ vol, double* __restrict__ red, double* __restrict__ scratch) {
+  __shared__ double s_red[33];
+  double mx = 0.0;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    int v[D + 1];
+    double x[D + 1][D];
+    load_cell<D>(cells, c, v);
+    load_coords<D>(coords, v, x);
+    Geo<D> g;
+    simplex_geometry(x, g);
+    vol[c] = g.vol;
+    mx = g.vol > mx ? g.vol : mx;
+  }
+  double v1[1] = {mx};
+  const int ops[1] = {RED_MAX};
+  if (grid_reduce<1>(v1, ops, scratch, s_red)) {
+    if (threadIdx.x == 0) red[0] = v1[0];
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(256)
 k_det_check(int64_t nc, const double* __restrict__ coords, const int32_t* __restrict__ cells,
@@ -477,6 +504,18 @@ extern "C" int cb_gradient_frobenius_max(void* stream, int dim, int64_t nc, cons
                                          const int32_t* cells, const double* D, double* red_dev,
                                          double* scratch, int64_t scratch_len) {
   return det_launch(stream, dim, nc, coords, cells, D, 1.0, nullptr, red_dev, scratch, scratch_len, 1);
+}
+
+extern "C" int cb_cell_volumes(void* stream, int dim, int64_t nc, const double* coords, const int32_t* cells, double* vol,
+                               double* max_dev, double* scratch, int64_t scratch_len) {
+  CB_REQUIRE(dim == 2 || dim == 3, "cb_cell_volumes: dim must be 2 or 3");
+  CB_REQUIRE(coords && cells && vol && max_dev, "cb_cell_volumes: missing argument");
+  CB_REQUIRE(scratch && scratch_len >= RED_SCRATCH_LEN, "cb_cell_volumes: scratch too small");
+  cudaStream_t s = as_stream(stream);
+  if (dim == 2) k_cell_volumes<2><<<red_grid(nc), 256, 0, s>>>(nc, coords, cells, vol, max_dev, scratch);
+  else k_cell_volumes<3><<<red_grid(nc), 256, 0, s>>>(nc, coords, cells, vol, max_dev, scratch);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
 }
 
 extern "C" int cb_move_mesh(void* stream, int64_t n, double* coords, double* coords_old,

@@ -279,6 +279,55 @@ def partition_mesh(coords: torch.Tensor, cells: torch.Tensor, boundary_vertices:
     return m
 
 
+def rcb_order(coords: np.ndarray, parts: int) -> tuple[np.ndarray, np.ndarray]:
+    """Recursive coordinate bisection of a point set into ``parts`` pieces of (nearly) equal size: returns the vertex
+    permutation ``order`` (old ids, grouped by part) and the part offsets.  The geometric stand-in for the graph
+    partitioner dolfin calls (SCOTCH / ParMETIS [third party]): compact parts with small interfaces for any mesh, no
+    structure assumed; deterministic (stable sorts), identical on every rank."""
+    coords = np.asarray(coords, dtype=np.float64)
+    n = coords.shape[0]
+    order = np.arange(n, dtype=np.int64)
+    offsets = [0]
+
+    def split(idx: np.ndarray, k: int) -> None:
+        if k == 1:
+            order[offsets[-1]: offsets[-1] + idx.size] = idx
+            offsets.append(offsets[-1] + idx.size)
+            return
+        pts = coords[idx]
+        axis = int(np.argmax(pts.max(axis=0) - pts.min(axis=0)))
+        k_lo = k // 2
+        cut = (idx.size * k_lo) // k
+        srt = idx[np.argsort(pts[:, axis], kind="stable")]
+        split(srt[:cut], k_lo)
+        split(srt[cut:], k - k_lo)
+
+    split(np.arange(n, dtype=np.int64), int(parts))
+    return order, np.asarray(offsets, dtype=np.int64)
+
+
+def distribute_mesh(coords, cells, facets, facet_tags, dist: DistContext, device=None) -> mesh_module.Mesh:
+    """Partition ANY simplicial mesh given by global host arrays (e.g. from ``io.mesh.read_gmsh``) over the ranks of
+    ``dist``: vertices are renumbered part by part along a recursive coordinate bisection, then every rank keeps its
+    contiguous vertex range plus the ghost layer (``partition_mesh``) -- what dolfin does at mesh import with a graph
+    partitioner (owned-then-ghost ordering, ``cashocs/geometry/quality.py:319-320``).  Collective."""
+    device = device or ("cuda" if torch.cuda.is_available() else "cpu")
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    cells = np.asarray(cells, dtype=np.int64)
+    order, offsets = rcb_order(coords, dist.world)
+    new_id = np.empty_like(order)
+    new_id[order] = np.arange(order.size)
+    ncells = np.sort(new_id[cells], axis=1)                       # ascending per cell: column 0 owns the cell
+    ncells = ncells[np.lexsort(ncells.T[::-1])]                    # deterministic cell order
+    nfacets = new_id[np.asarray(facets, dtype=np.int64)] if len(facets) else np.zeros((0, coords.shape[1]), dtype=np.int64)
+    tags = np.asarray(facet_tags)
+    bverts = {int(t): torch.from_numpy(np.unique(nfacets[tags == t].reshape(-1))) for t in np.unique(tags)}
+    m = partition_mesh(torch.from_numpy(coords[order]).to(device), torch.from_numpy(ncells).to(device), bverts, offsets, dist)
+    m.global_boundary_facets = {int(t): nfacets[tags == t] for t in np.unique(tags)}
+    m.rcb_order = order                                             # new global id -> id in the input arrays
+    return m
+
+
 def distributed_regular_mesh(n: int, dist: DistContext, lengths=(1.0, 1.0, 1.0), device=None) -> mesh_module.Mesh:
     """Unit-cube mesh partitioned into z-slabs of whole vertex layers (one halo layer per side)."""
     device = device or ("cuda" if torch.cuda.is_available() else "cpu")

@@ -471,6 +471,11 @@ int cb_det_check(void* stream, int dim, int64_t nc, const double* coords, const 
 int cb_gradient_frobenius_max(void* stream, int dim, int64_t nc, const double* coords,
                               const int32_t* cells, const double* D, double* red_dev,
                               double* scratch, int64_t scratch_len);
+/* vol [nc] = |K| per cell and *max_dev = max |K| over this rank's cells: `CellVolume` of the inhomogeneous elasticity
+ * scaling (cashocs/_forms/shape_form_handler.py:629-644; its l2_projection to DG0, cashocs/_utils/linalg.py:768-809,
+ * is the identity for cellwise constants). */
+int cb_cell_volumes(void* stream, int dim, int64_t nc, const double* coords, const int32_t* cells, double* vol,
+                    double* max_dev, double* scratch, int64_t scratch_len);
 /* coords_old = coords; coords += step * V  (DeformationHandler.move_mesh,
  * cashocs/geometry/deformations.py:132-133); n = nv*dim. */
 int cb_move_mesh(void* stream, int64_t n, double* coords, double* coords_old, const double* V,

@@ -27,6 +27,20 @@ def _worker(rank, world, port, kind, results):
         if kind == "cube":
             om = meshes.regular_mesh(4, 1.0, 1.0, 1.0)
             lm = distributed.distributed_regular_mesh(4, dist, device="cpu")
+        elif kind == "circle_rcb":
+            # an imported, unstructured mesh (the reference's unit-disc fixture) through the general partitioner:
+            # recursive coordinate bisection, then the same owned / ghost extraction
+            z = np.load(os.path.join(ROOT, "tests", "golden", "unit_circle.npz"))
+            lm = distributed.distribute_mesh(z["coords"], z["cells"], z["facets"], z["facet_tags"], dist, device="cpu")
+            order = lm.rcb_order
+            new_id = np.empty_like(order)
+            new_id[order] = np.arange(order.size)
+            om = meshes.Mesh(z["coords"][order], np.sort(new_id[z["cells"].astype(np.int64)], axis=1),
+                             new_id[z["facets"].astype(np.int64)], z["facet_tags"])
+            counts = np.diff(lm.global_offsets)
+            assert counts.sum() == om.num_vertices and abs(int(counts[0]) - int(counts[1])) <= 1
+            # a compact cut: the interface of a bisected disc is a few dozen vertices, not a band of them
+            assert 0 < lm.num_vertices - lm.n_owned_vertices < 0.12 * om.num_vertices
         else:
             om = meshes.regular_mesh(7)
             g = cb.regular_mesh(7, device="cpu")
@@ -78,10 +92,10 @@ def _worker(rank, world, port, kind, results):
         td.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["cube", "square_ragged"])
+@pytest.mark.parametrize("kind", ["cube", "square_ragged", "circle_rcb"])
 def test_partition_and_halo_world2(kind):
     world = 2
-    port = 29500 + (os.getpid() % 2000) + (0 if kind == "cube" else 1)
+    port = 29500 + (os.getpid() % 2000) + {"cube": 0, "square_ragged": 1, "circle_rcb": 2}[kind]
     mgr = mp.Manager()
     results = mgr.dict()
     mp.spawn(_worker, args=(world, port, kind, results), nprocs=world, join=True)

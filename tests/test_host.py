@@ -265,3 +265,24 @@ def test_gmsh_reader():
             assert sorted(map(tuple, np.c_[f, ft])) == sorted(map(tuple, np.c_[np.sort(z["facets"], axis=1), z["facet_tags"]]))
     with pytest.raises(cb.InputError):
         mesh_io.read_gmsh(__file__)  # not a gmsh 4.1 ASCII file
+
+
+def test_rcb_partition_is_a_balanced_permutation():
+    """``distributed.rcb_order``: recursive coordinate bisection into any number of parts -- a permutation of the
+    vertices, part sizes within one of each other, parts geometrically compact (each part's bounding box is a
+    fraction of the domain's)."""
+    from cashocs_b200 import distributed
+
+    rng = np.random.RandomState(3)
+    pts = rng.rand(1000, 3)
+    for parts in (1, 2, 3, 5, 8):
+        order, off = distributed.rcb_order(pts, parts)
+        assert np.array_equal(np.sort(order), np.arange(1000)) and off[0] == 0 and off[-1] == 1000
+        sizes = np.diff(off)
+        assert sizes.size == parts and sizes.max() - sizes.min() <= 1
+        if parts == 8:
+            vols = [np.prod(np.ptp(pts[order[off[r]:off[r + 1]]], axis=0)) for r in range(parts)]
+            assert max(vols) < 0.3
+    o1, _ = distributed.rcb_order(pts, 8)
+    o2, _ = distributed.rcb_order(pts, 8)
+    assert np.array_equal(o1, o2)
