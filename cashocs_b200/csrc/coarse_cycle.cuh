@@ -8,12 +8,17 @@
 // replays the kernel unchanged), every phase is a warp-per-row gather with a fixed summation order: bit-reproducible.
 //
 // Handles levels whose operators are local to this rank (one GPU: all of them; partitioned meshes: the replicated
-// levels below the agglomeration point).  Scalar prolongator (P (x) I), Chebyshev-Jacobi smoothers of any degree,
+// levels below the agglomeration point) AND distributed levels when the one-sided NVLink transport is on: the ghost
+// update of a level's iterate and the all-gather of the restricted residual at the agglomeration point are then phases
+// of the same kernel (p2p_halo_exchange_grid: boundary values are stored straight into the neighbours' landing zones,
+// flags released by the last CTA, every CTA waits and copies its share) -- compute and collective in one launch, no
+// NCCL call, no host involvement.  Scalar prolongator (P (x) I), Chebyshev-Jacobi smoothers of any degree,
 // first post-smoothing step through A*P, dense inverse or Chebyshev sweep on the last level -- the same arithmetic,
 // operation by operation, as the launch-per-operation path of Solver::amg_vcycle (which stays for distributed levels
 // and as the cross-check of the tests, CASHOCS_B200_FUSED_COARSE=0).
 #pragma once
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace cb {
 
@@ -32,6 +37,14 @@ struct CoarseLevelDev {
   int degree;            // Chebyshev degree of the pre / post smoother (last level without dense inverse: of the solve)
   double inv_theta;      // first step: d = inv_theta * dinv .* b
   double c1[CC_MAX_DEGREE], c2[CC_MAX_DEGREE];  // step j >= 1: d = c1[j] d + c2[j] dinv .* (b - t)
+  // ---- partitioned meshes (all zero on one GPU)
+  int has_halo;          // distributed level: x carries ghost nodes that are refreshed before every pass over A
+  int next_rep;          // the next level is the replicated entry level: its b is all-gathered from the ranks' rows
+  HaloDev halo;          // ghost update of this level's x
+  HaloDev gather;        // next_rep: all-gather plan ("ghosts" = the other ranks' rows, rank order)
+  double* rep_tmp;       // next_rep: [nx.n * BS] this rank's rows of the restricted residual first, then the others'
+  int64_t rep_off;       // next_rep: rows owned by lower ranks
+  const int32_t* coarse_gid;  // next_rep: local coarse node (column of A*P) -> row of the replicated level
 };
 
 struct CoarseCycleDev {
@@ -70,13 +83,14 @@ __device__ __forceinline__ void cc_grid_barrier(unsigned long long* counter, uns
 template <int BS>
 __device__ __forceinline__ void cc_row_times(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                              const double* __restrict__ val, const double* x, int64_t row,
-                                             int lane, double (&out)[BS]) {
+                                             int lane, double (&out)[BS], const int32_t* __restrict__ gid = nullptr) {
   double acc[BS];
 #pragma unroll
   for (int i = 0; i < BS; ++i) acc[i] = 0.0;
   const int64_t kb = rowptr[row], ke = rowptr[row + 1];
   for (int64_t k = kb + lane; k < ke; k += 32) {
-    const double* xb = x + (int64_t)col[k] * BS;
+    const int64_t cidx = gid ? (int64_t)gid[col[k]] : (int64_t)col[k];
+    const double* xb = x + cidx * BS;
     const double* a = val + k * (BS * BS);
     double xv[BS];
 #pragma unroll
@@ -143,6 +157,28 @@ k_coarse_cycle(const CoarseCycleDev* __restrict__ cyp, const int* __restrict__ d
   auto barrier = [&]() { target += gridDim.x; cc_grid_barrier(counter, target); };
 
   const int L = cy.nlevels;
+  // t = A x of a level: x complete (barrier), ghosts refreshed in place when the level is distributed, rows, barrier
+  auto spmv_phase = [&](const CoarseLevelDev& lv) {
+    barrier();
+    if (lv.has_halo) {
+      p2p_halo_exchange_grid<BS>(lv.halo, lv.x);
+      barrier();
+    }
+    for (int64_t r = warp0; r < lv.n; r += nwarps) {
+      double ax[BS];
+      cc_row_times<BS>(lv.rowptr, lv.col, lv.val, lv.x, r, lane, ax);
+      if (lane < BS) lv.t[r * BS + lane] = ax[lane];
+    }
+    barrier();
+  };
+  auto cheb_step = [&](const CoarseLevelDev& lv, int j) {
+    const int64_t ns = lv.n * BS;
+    for (int64_t i = tid0; i < ns; i += nthreads) {
+      const double di = lv.c1[j] * CC_LD(lv.d + i) + lv.c2[j] * lv.dinv[i] * (CC_LD(lv.b + i) - CC_LD(lv.t + i));
+      lv.d[i] = di;
+      lv.x[i] = CC_LD(lv.x + i) + di;
+    }
+  };
   // ---- down: pre-smoothing from a zero guess, residual, restriction.  b of the first level was written by the caller.
   for (int l = 0; l < L; ++l) {
     const CoarseLevelDev& lv = cy.lev[l];
@@ -161,55 +197,58 @@ k_coarse_cycle(const CoarseCycleDev* __restrict__ cyp, const int* __restrict__ d
       barrier();
       break;
     }
-    // first Chebyshev step: d = x = inv_theta * dinv .* b   (no barrier needed before: b is complete, see restrict)
+    // first Chebyshev step: d = x = inv_theta * dinv .* b   (b is complete: see the end of the previous level)
     for (int64_t i = tid0; i < ns; i += nthreads) {
       const double di = lv.inv_theta * lv.dinv[i] * CC_LD(lv.b + i);
       lv.d[i] = di;
       lv.x[i] = di;
     }
     for (int j = 1; j < lv.degree; ++j) {
-      barrier();  // x complete
-      for (int64_t r = warp0; r < lv.n; r += nwarps) {
-        double ax[BS];
-        cc_row_times<BS>(lv.rowptr, lv.col, lv.val, lv.x, r, lane, ax);
-        if (lane < BS) lv.t[r * BS + lane] = ax[lane];
-      }
-      barrier();  // t complete (x is read by other rows' gathers: update only after everybody is done)
-      for (int64_t i = tid0; i < ns; i += nthreads) {
-        const double di = lv.c1[j] * CC_LD(lv.d + i) + lv.c2[j] * lv.dinv[i] * (CC_LD(lv.b + i) - CC_LD(lv.t + i));
-        lv.d[i] = di;
-        lv.x[i] = CC_LD(lv.x + i) + di;
-      }
+      spmv_phase(lv);
+      cheb_step(lv, j);
     }
     if (last) {  // Chebyshev "solve" of the last level: done
       barrier();
       break;
     }
-    barrier();  // x complete
-    for (int64_t r = warp0; r < lv.n; r += nwarps) {
-      double ax[BS];
-      cc_row_times<BS>(lv.rowptr, lv.col, lv.val, lv.x, r, lane, ax);
-      if (lane < BS) lv.t[r * BS + lane] = ax[lane];
-    }
-    barrier();  // t complete
+    spmv_phase(lv);
     const CoarseLevelDev& nx = cy.lev[l + 1];
+    double* rc_out = lv.next_rep ? lv.rep_tmp : nx.b;
     for (int64_t r = warp0; r < lv.nc; r += nwarps) {
       double rc[BS];
       cc_row_transfer<BS, true>(lv.pt_rowptr, lv.pt_col, lv.pt_val, lv.b, lv.t, r, lane, rc);
-      if (lane < BS) nx.b[r * BS + lane] = rc[lane];
+      if (lane < BS) rc_out[r * BS + lane] = rc[lane];
     }
-    barrier();  // b of the next level complete
+    barrier();  // restricted residual complete
+    if (lv.next_rep) {
+      // every coarse row is produced by exactly one rank (aggregates never cross ranks): all-gather over NVLink,
+      // then reorder [own rows | other ranks' rows] into the global row order of the replicated level
+      p2p_halo_exchange_grid<BS>(lv.gather, lv.rep_tmp);
+      barrier();
+      const int64_t n_own = lv.nc, lo = lv.rep_off, total = nx.n * BS;
+      for (int64_t q = tid0; q < total; q += nthreads) {
+        const int64_t i = q / BS;
+        const int64_t src = (i < lo) ? (n_own + i) : (i < lo + n_own ? i - lo : i);
+        nx.b[q] = CC_LD(lv.rep_tmp + src * BS + (q - i * BS));
+      }
+      barrier();
+    }
   }
   // ---- up: coarse-grid correction + first post-smoothing step through A*P, further steps through A
   for (int l = L - 2; l >= 0; --l) {
     const CoarseLevelDev& lv = cy.lev[l];
     const CoarseLevelDev& nx = cy.lev[l + 1];
-    const int64_t ns = lv.n * BS;
     const double c2 = lv.inv_theta;
+    if (nx.has_halo) {  // A*P gathers from the ghost coarse nodes too
+      p2p_halo_exchange_grid<BS>(nx.halo, nx.x);
+      barrier();
+    }
+    const double* xc_own = lv.next_rep ? nx.x + lv.rep_off * BS : nx.x;  // P maps to this rank's coarse nodes only
+    const int32_t* gid = lv.next_rep ? lv.coarse_gid : nullptr;
     for (int64_t r = warp0; r < lv.n; r += nwarps) {
       double pe[BS], ape[BS];
-      cc_row_transfer<BS, false>(lv.p_rowptr, lv.p_col, lv.p_val, nx.x, nullptr, r, lane, pe);
-      cc_row_times<BS>(lv.ap_rowptr, lv.ap_col, lv.ap_val, nx.x, r, lane, ape);
+      cc_row_transfer<BS, false>(lv.p_rowptr, lv.p_col, lv.p_val, xc_own, nullptr, r, lane, pe);
+      cc_row_times<BS>(lv.ap_rowptr, lv.ap_col, lv.ap_val, nx.x, r, lane, ape, gid);
       if (lane < BS) {
         const int64_t i = r * BS + lane;
         const double xi = CC_LD(lv.x + i) + pe[lane];
@@ -219,18 +258,8 @@ k_coarse_cycle(const CoarseCycleDev* __restrict__ cyp, const int* __restrict__ d
       }
     }
     for (int j = 1; j < lv.degree; ++j) {
-      barrier();
-      for (int64_t r = warp0; r < lv.n; r += nwarps) {
-        double ax[BS];
-        cc_row_times<BS>(lv.rowptr, lv.col, lv.val, lv.x, r, lane, ax);
-        if (lane < BS) lv.t[r * BS + lane] = ax[lane];
-      }
-      barrier();
-      for (int64_t i = tid0; i < ns; i += nthreads) {
-        const double di = lv.c1[j] * CC_LD(lv.d + i) + lv.c2[j] * lv.dinv[i] * (CC_LD(lv.b + i) - CC_LD(lv.t + i));
-        lv.d[i] = di;
-        lv.x[i] = CC_LD(lv.x + i) + di;
-      }
+      spmv_phase(lv);
+      cheb_step(lv, j);
     }
     if (l > 0) barrier();  // x of this level complete before the level above gathers from it
   }

@@ -123,49 +123,8 @@ bool dist_is_one_sided(const cb_dist* d);
 // block that has to release ours.
 template <int BS>
 __global__ void __launch_bounds__(256)
-k_halo_exchange(int nneigh, const int64_t* __restrict__ send_off, const int64_t* __restrict__ remote_off,
-                const int32_t* __restrict__ neigh, const int32_t* __restrict__ send_idx,
-                const int64_t* __restrict__ remote_cap, const int64_t* __restrict__ recv_off, double* __restrict__ x,
-                int64_t n_owned, int64_t ghost_cap, P2PView v) {
-  // the exchange epoch lives in the window (not in a kernel argument) so that a captured CUDA graph
-  // can replay the exchange: every thread reads it here, the last block of the put phase bumps it
-  unsigned long long* hdr = window_header(v.window, v.lay);
-  const int nr = v.lay.nranks;
-  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(hdr + 2 * nr + 2) + 1ULL;
-  const int64_t nsend = send_off[nneigh];
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nsend * BS;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t q = i / BS;
-    const int c = (int)(i - q * BS);
-    int j = 0;
-    while (j + 1 < nneigh && q >= send_off[j + 1]) ++j;
-    double* dst = reinterpret_cast<double*>(v.peer_window[neigh[j]]) + v.lay.land_off() +
-                  (int64_t)(epoch & 1ULL) * remote_cap[j] + (remote_off[j] + (q - send_off[j])) * BS + c;
-    *dst = x[(int64_t)send_idx[q] * BS + c];
-  }
-  // the last block to finish releases the flags (all stores of all blocks are fenced before)
-  __threadfence_system();
-  __syncthreads();
-  __shared__ bool last;
-  __shared__ int ok;
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(hdr + 2 * nr);
-  if (threadIdx.x == 0) { last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1); ok = 1; }
-  __syncthreads();
-  if (last && threadIdx.x < nneigh) {
-    __threadfence_system();
-    st_release_sys(window_header(v.peer_window[neigh[threadIdx.x]], v.lay) + v.rank, epoch);
-  }
-  if (last && threadIdx.x == 0) hdr[2 * nr + 2] = epoch;
-  // get phase
-  if (threadIdx.x < nneigh && recv_off[threadIdx.x + 1] > recv_off[threadIdx.x]) {
-    if (!wait_flag(hdr + neigh[threadIdx.x], epoch, v)) ok = 0;
-  }
-  __syncthreads();
-  if (!ok) return;
-  const double* src = reinterpret_cast<const double*>(v.window) + v.lay.land_off() + (int64_t)(epoch & 1ULL) * ghost_cap;
-  const int64_t n = recv_off[nneigh] * BS;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    x[n_owned * BS + i] = __ldcv(src + i);
+k_halo_exchange(HaloDev h, double* __restrict__ x) {
+  p2p_halo_exchange_grid<BS>(h, x);
 }
 
 // all-reduce of n <= RED_W doubles as one kernel of one warp (p2p_allreduce_warp)
@@ -184,23 +143,38 @@ P2PView dist_p2p_view(const cb_dist* d) {
   return v;
 }
 
+HaloDev dist_halo_dev(const cb_dist* d) {
+  HaloDev h;
+  h.nneigh = (int)d->neigh.size();
+  h.send_off = d->d_send_off;
+  h.remote_off = d->d_remote_off;
+  h.neigh = d->d_neigh;
+  h.send_idx = d->send_idx;
+  h.remote_cap = d->d_remote_cap;
+  h.recv_off = d->d_recv_off;
+  h.n_owned = d->n_owned;
+  h.ghost_cap = d->ghost_cap;
+  h.v = dist_p2p_view(d);
+  return h;
+}
+
+// largest block size (doubles per node) a plan's landing zone holds
+int64_t dist_ghost_capacity(const cb_dist* d) { return d ? d->ghost_cap : 0; }
+int64_t dist_recv_len(const cb_dist* d) { return d ? d->recv_off.back() : 0; }
+
 static int p2p_halo_exchange(cudaStream_t s, cb_dist* d, double* x, int bs) {
-  const int nneigh = (int)d->neigh.size();
   const int64_t nsend = d->send_off.back(), nrecv = d->recv_off.back();
   if (nrecv * bs > d->ghost_cap) {
     set_error("p2p halo exchange: landing zone too small");
     return CB_ERR_ARG;
   }
-  if (nneigh > 256) { set_error("p2p halo exchange: more than 256 neighbours"); return CB_ERR_ARG; }
   const int64_t work = (nsend > nrecv ? nsend : nrecv) * bs;
   const int grid = grid_for(work > 0 ? work : 1, 256, 2);
-  const P2PView v = dist_p2p_view(d);
-#define CB_HALO(BS)                                                                                              \
-  k_halo_exchange<BS><<<grid, 256, 0, s>>>(nneigh, d->d_send_off, d->d_remote_off, d->d_neigh, d->send_idx,       \
-                                           d->d_remote_cap, d->d_recv_off, x, d->n_owned, d->ghost_cap, v);      \
+  const HaloDev h = dist_halo_dev(d);
+  if (bs == 1) k_halo_exchange<1><<<grid, 256, 0, s>>>(h, x);
+  else if (bs == 2) k_halo_exchange<2><<<grid, 256, 0, s>>>(h, x);
+  else k_halo_exchange<3><<<grid, 256, 0, s>>>(h, x);
   CB_LAUNCH_CHECK();
-  if (bs == 1) { CB_HALO(1) } else if (bs == 2) { CB_HALO(2) } else { CB_HALO(3) }
-#undef CB_HALO
   return CB_OK;
 }
 

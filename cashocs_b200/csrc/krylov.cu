@@ -27,6 +27,9 @@
 namespace cb {
 
 P2PView dist_p2p_view(const cb_dist* d);
+HaloDev dist_halo_dev(const cb_dist* d);
+int64_t dist_ghost_capacity(const cb_dist* d);
+int64_t dist_recv_len(const cb_dist* d);
 
 int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
                   double* result, double* scratch, const int* done = nullptr, bool use32 = false);
@@ -843,11 +846,30 @@ struct Solver {
     // levels with more rows than this keep their own (TMA-staged) kernels: they are bandwidth-, not latency-bound
     int64_t max_rows = 20000;
     if (const char* mr = getenv("CASHOCS_B200_FUSED_MAX_ROWS")) max_rows = atoll(mr);
-    int first = L;  // smallest level from which on every operator is local (no halo plan)
-    for (int l = L - 1; l >= 1; --l) {
+    // A level joins the persistent kernel if it is local / replicated, or distributed with the one-sided transport on
+    // (its ghost updates and the all-gather at the agglomeration point then run inside the kernel).
+    auto level_ok = [&](int l) -> bool {
       const cb_amg_level& lev = h->levels[l];
-      if (lev.dist || lev.A.nrows > max_rows) break;
-      if (l < L - 1 && (!lev.AP.val || lev.AP.val32 || h->levels[l + 1].rep_dist)) break;
+      if (lev.A.nrows > max_rows) return false;
+      if (lev.dist) {
+        if (!dist_is_one_sided(lev.dist)) return false;
+        if (dist_recv_len(lev.dist) * bs > dist_ghost_capacity(lev.dist)) return false;
+      } else if (lev.A.ncols != lev.A.nrows) {
+        return false;
+      }
+      if (l < L - 1) {
+        if (!lev.AP.val || lev.AP.val32) return false;
+        const cb_amg_level& nxt = h->levels[l + 1];
+        if (nxt.rep_dist) {  // agglomeration point: needs the one-sided all-gather plan and the coarse numbering map
+          if (!nxt.rep_gather || !dist_is_one_sided(nxt.rep_gather) || !nxt.rep_tmp || !lev.coarse_gid) return false;
+          if (dist_recv_len(nxt.rep_gather) * bs > dist_ghost_capacity(nxt.rep_gather)) return false;
+        }
+      }
+      return true;
+    };
+    int first = L;
+    for (int l = L - 1; l >= 1; --l) {
+      if (!level_ok(l)) break;
       first = l;
     }
     if (first >= L || L - first > CC_MAX_LEVELS) return CB_OK;
@@ -862,7 +884,7 @@ struct Solver {
       CoarseLevelDev& d = cy.lev[l - first];
       const bool last = (l == L - 1);
       d.n = lev.A.nrows;
-      d.nc = last ? 0 : h->levels[l + 1].A.nrows;
+      d.nc = last ? 0 : lev.nc;
       d.rowptr = lev.A.rowptr; d.col = lev.A.col; d.val = lev.A.val; d.dinv = lev.dinv;
       d.p_rowptr = lev.p_rowptr; d.p_col = lev.p_col; d.p_val = lev.p_val;
       d.pt_rowptr = lev.pt_rowptr; d.pt_col = lev.pt_col; d.pt_val = lev.pt_val;
@@ -873,7 +895,18 @@ struct Solver {
       std::pair<double, double> coef[64];
       cheb_coefficients(lev.lmax, (last && !h->coarse_inv) ? h->coarse_ratio : h->smooth_ratio, d.degree, d.inv_theta, coef);
       for (int j = 1; j < d.degree; ++j) { d.c1[j] = coef[j].first; d.c2[j] = coef[j].second; }
-      if (lev.A.ncols != lev.A.nrows) return CB_OK;  // ghost columns: not a local operator
+      if (lev.dist) {
+        d.has_halo = 1;
+        d.halo = dist_halo_dev(lev.dist);
+      }
+      if (!last && h->levels[l + 1].rep_dist) {
+        const cb_amg_level& nxt = h->levels[l + 1];
+        d.next_rep = 1;
+        d.gather = dist_halo_dev(nxt.rep_gather);
+        d.rep_tmp = nxt.rep_tmp;
+        d.rep_off = nxt.rep_off;
+        d.coarse_gid = lev.coarse_gid;
+      }
     }
     fused_dev = reinterpret_cast<CoarseCycleDev*>(buf);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(buf + (sizeof(CoarseCycleDev) + 7) / 8);

@@ -35,6 +35,20 @@ struct P2PView {
   int rank;
 };
 
+// device-side description of one halo plan (what k_halo_exchange / the persistent V-cycle kernel need of a cb_dist)
+struct HaloDev {
+  int nneigh;
+  const int64_t* send_off;    // [nneigh+1]
+  const int64_t* remote_off;  // [nneigh] node offset of my data in the peer's ghost range
+  const int32_t* neigh;       // [nneigh]
+  const int32_t* send_idx;    // [nsend] owned local nodes to send
+  const int64_t* remote_cap;  // [nneigh] parity stride of the peer's landing zone
+  const int64_t* recv_off;    // [nneigh+1]
+  int64_t n_owned;
+  int64_t ghost_cap;
+  P2PView v;
+};
+
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -69,6 +83,64 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsign
 
 __device__ __forceinline__ unsigned long long* window_header(unsigned char* window, const WindowLayout& lay) {
   return reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(window) + lay.flags_off());
+}
+
+// Halo exchange by ALL CTAs of the calling grid (every thread must call it; the grid's CTAs must be co-resident).
+// Put phase: gather the boundary values and store them straight into the neighbours' landing zones over NVLink; the
+// last CTA to finish releases the per-source epoch flags.  Get phase: every CTA waits for the neighbours' flags of this
+// epoch and copies its share of the landing zone behind the owned part of x.  x must be complete on entry (the
+// caller separates it from its producers by a kernel boundary or a grid barrier); on return THIS CTA's share of the
+// ghosts is in place.  Returns false after a time-out.
+template <int BS>
+__device__ __forceinline__ bool p2p_halo_exchange_grid(const HaloDev& h, double* x) {
+  // the exchange epoch lives in the window (not in a kernel argument) so that a captured CUDA graph
+  // can replay the exchange: every thread reads it here, the last CTA of the put phase bumps it
+  unsigned long long* hdr = window_header(h.v.window, h.v.lay);
+  const int nr = h.v.lay.nranks;
+  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(hdr + 2 * nr + 2) + 1ULL;
+  const int nneigh = h.nneigh;
+  const int64_t nsend = h.send_off[nneigh];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nsend * BS;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = i / BS;
+    const int c = (int)(i - q * BS);
+    int j = 0;
+    while (j + 1 < nneigh && q >= h.send_off[j + 1]) ++j;
+    double* dst = reinterpret_cast<double*>(h.v.peer_window[h.neigh[j]]) + h.v.lay.land_off() +
+                  (int64_t)(epoch & 1ULL) * h.remote_cap[j] + (h.remote_off[j] + (q - h.send_off[j])) * BS + c;
+    *dst = __ldcg(x + (int64_t)h.send_idx[q] * BS + c);
+  }
+  // the last CTA to finish releases the flags (all stores of all CTAs are fenced before)
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool s_last;
+  __shared__ int s_ok;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(hdr + 2 * nr);
+  if (threadIdx.x == 0) { s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1); s_ok = 1; }
+  __syncthreads();
+  if (s_last) {
+    for (int j = threadIdx.x; j < nneigh; j += blockDim.x) {
+      __threadfence_system();
+      st_release_sys(window_header(h.v.peer_window[h.neigh[j]], h.v.lay) + h.v.rank, epoch);
+    }
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(hdr + 2 * nr + 2) = epoch;
+  }
+  // get phase
+  for (int j = threadIdx.x; j < nneigh; j += blockDim.x) {
+    if (h.recv_off[j + 1] > h.recv_off[j]) {
+      if (!wait_flag(hdr + h.neigh[j], epoch, h.v)) s_ok = 0;
+    }
+  }
+  __syncthreads();
+  const bool ok = s_ok != 0;
+  if (ok) {
+    const double* src = reinterpret_cast<const double*>(h.v.window) + h.v.lay.land_off() + (int64_t)(epoch & 1ULL) * h.ghost_cap;
+    const int64_t n = h.recv_off[nneigh] * BS;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      x[h.n_owned * BS + i] = __ldcv(src + i);
+  }
+  __syncthreads();  // s_last / s_ok may be reused by the next call
+  return ok;
 }
 
 // All-reduce of n <= RED_W doubles by ONE warp of one block: every rank writes its message into every rank's slots,
