@@ -97,6 +97,8 @@ class cb_mat(C.Structure):
         ("col", C.c_void_p),
         ("val", C.c_void_p),
         ("val32", C.c_void_p),
+        ("cta_warps", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

@@ -388,7 +388,7 @@ class AMGHierarchy:
             # rows of a replicated level computed by this rank (scattered + all-reduced into D.val)
             D.val_local = torch.zeros(L.rep_nnzb_local * bs * bs, **f64) if L.rep_dist is not None else None
             D.rep_tmp = torch.zeros(nb, **f64) if L.rep_gather is not None else None
-            want32 = self.mixed and (("a0" in self.mixed_mask) if li == 0 else ("coarse" in self.mixed_mask))
+            want32 = self.mixed and (("a0" in self.mixed_mask) if li == 0 else ("coarse" in self.mixed_mask or "a1" in self.mixed_mask))
             D.val32 = torch.zeros(L.nnzb * bs * bs, dtype=torch.float32, device=dev) if want32 else None
             D.ap_val32 = None
             D.dinv = torch.zeros(nb, **f64)
@@ -600,6 +600,7 @@ class AMGHierarchy:
                 ap = _lib.cb_mat()
                 ap.nrows, ap.ncols, ap.bs = L.n, L.nc + L.gc, self.bs
                 ap.row_split = linalg.row_split_hint(L.ap_col.numel(), L.n)
+                ap.cta_warps = linalg.cta_warps_hint(L.ap_col.numel(), L.n, self.bs, ap.row_split)
                 ap.rowptr, ap.col, ap.val = L.ap_rowptr.data_ptr(), L.ap_col.data_ptr(), D.ap_val.data_ptr()
                 ap.val32 = D.ap_val32.data_ptr() if D.ap_val32 is not None else None
                 e.AP = ap

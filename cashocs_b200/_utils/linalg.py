@@ -156,6 +156,22 @@ def row_split_hint(nnzb: int, nrows: int) -> int:
     return 1 if avg <= 24 else (2 if avg <= 48 else (4 if avg <= 96 else 8))
 
 
+def cta_warps_hint(nnzb: int, nrows: int, bs: int, row_split: int = 1) -> int:
+    """Warps per CTA for the bulk-copy SpMV-type pass over an operator with short rows (``cb_mat.cta_warps``): a CTA
+    stages the values of all its rows with one bulk copy into a tile of 16 blocks per row of the default shape
+    (csrc/spmv.cuh: 2 warps x 10 rows for 3 x 3 blocks, 4 warps x 32 / 16 rows otherwise); with fewer blocks per row
+    more rows fit, which keeps the copy size -- the bytes in flight per SM -- where the sweeps found the DRAM pipe
+    saturated.  0 = default."""
+    default = 2 if bs == 3 else 4
+    g = max(int(row_split), 1)
+    rpw = 32 // (bs * g)
+    tile = 16 * rpw * default if g == 1 else 16 * (32 // bs) * default
+    avg = nnzb / max(nrows, 1)
+    want = int(0.9 * tile / max(avg * rpw, 1.0))
+    w = min(max(want, default), 2 * default)
+    return 0 if w == default else w
+
+
 # matrices are assembled by the nnz-centric gather kernels; False selects the coloured cell-scatter
 # kernels (kept for meshes whose scatter map exceeds int32 and as a cross-check in the tests)
 USE_GATHER_ASSEMBLY = True
@@ -485,7 +501,7 @@ class LinearSolver:
         prec = str(options.get("pc_amg_precision", "mixed")).casefold()
         if not (prec in ("mixed", "double") or prec.startswith("mixed:")):
             raise _exceptions.InputError("cashocs_b200.LinearSolver", "pc_amg_precision",
-                                         "mixed, double or mixed:<a0|ap0|coarse joined by +>")
+                                         "mixed, double or mixed:<a0|a1|ap0|coarse joined by +>")
         # Defaults from the sweeps on the 10 M-tet elasticity / Poisson systems (tools/sweep_precision.py, gpurun_out/r02_sweep*):
         # smoother interval [lmax/20, lmax]; lmax = 1.1 x the (warm-started, hence converged) power-method estimate;
         # prolongator damping 1.6 / lmax(D_S^-1 S) instead of the textbook 4/3 (89 -> 65 PCG iterations together).

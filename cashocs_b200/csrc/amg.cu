@@ -186,38 +186,50 @@ int amg_dense_apply(cudaStream_t s, int n, const double* inv, const double* b, d
   return CB_OK;
 }
 
-// bc[I, c] = sum_i Pt[I, i] * (b[i, c] - t[i, c])      (restriction of the residual)
+// bc[I, c] = sum_i Pt[I, i] * (b[i, c] - t[i, c])      (restriction of the residual; t == NULL: b is the residual)
 template <int BS>
 __global__ void __launch_bounds__(256)
 k_restrict(int64_t nc, const int64_t* __restrict__ pt_rowptr, const int32_t* __restrict__ pt_col,
            const double* __restrict__ pt_val, const double* __restrict__ b, const double* __restrict__ t,
            double* __restrict__ bc, const int* __restrict__ done) {
   if (done && *done) return;
-  // one warp per coarse node: lanes stride over the ~50 entries of the P^T row (coalesced index /
-  // weight loads), every lane accumulates all BS components, fixed-order shuffle tree at the end
+  // One warp per coarse node, lane = e * BS + c: a sweep covers EPW = 32 / BS entries of the P^T row (~100 per
+  // row) and lane (e, c) owns component c of entry e, so the gather of one vector is ONE load instruction whose
+  // addresses are EPW runs of BS contiguous doubles -- the kernel is bound by L1 wavefronts (sectors touched per
+  // load instruction), and one-lane-per-entry with BS loads per vector touched every sector BS times.
+  // Fixed-order shuffle tree over e at the end: bit-reproducible.
+  constexpr int EPW = 32 / BS;
   const int lane = threadIdx.x & 31;
+  const int e = lane / BS, c = lane - e * BS;
+  const bool active = e < EPW;
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t I = warp0; I < nc; I += nwarps) {
-    double s[BS];
-#pragma unroll
-    for (int c = 0; c < BS; ++c) s[c] = 0.0;
+    double s = 0.0;
     const int64_t kb = pt_rowptr[I], ke = pt_rowptr[I + 1];
-    for (int64_t k = kb + lane; k < ke; k += 32) {
-      const int64_t i = (int64_t)pt_col[k] * BS;
-      const double w = pt_val[k];
-#pragma unroll
-      for (int c = 0; c < BS; ++c) s[c] += w * (b[i + c] - t[i + c]);
+    if (active) {
+      if (t) {
+#pragma unroll 2
+        for (int64_t k = kb + e; k < ke; k += EPW) {
+          const int64_t i = (int64_t)__ldg(pt_col + k) * BS + c;
+          s = fma(__ldg(pt_val + k), b[i] - t[i], s);
+        }
+      } else {
+#pragma unroll 4
+        for (int64_t k = kb + e; k < ke; k += EPW) {
+          const int64_t i = (int64_t)__ldg(pt_col + k) * BS + c;
+          s = fma(__ldg(pt_val + k), b[i], s);
+        }
+      }
     }
 #pragma unroll
-    for (int c = 0; c < BS; ++c) {
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) s[c] += __shfl_down_sync(0xffffffffu, s[c], off);
+    for (int off = 16; off > 0; off >>= 1) {
+      if (off < EPW) {
+        const double o = __shfl_down_sync(0xffffffffu, s, off * BS);
+        if (lane + off * BS < 32) s += o;
+      }
     }
-    if (lane == 0) {
-#pragma unroll
-      for (int c = 0; c < BS; ++c) bc[I * BS + c] = s[c];
-    }
+    if (lane < BS) bc[I * BS + lane] = s;
   }
 }
 

@@ -28,11 +28,11 @@ __device__ __forceinline__ void load_cell_data(const int32_t* __restrict__ cells
 }
 
 // ------------------------------------------------------------------ scalar P1
-template <int D>
+template <int D, class P, int DEG, bool ZDEP>
 __global__ void __launch_bounds__(128)
 k_assemble_scalar(int64_t c_begin, int64_t c_end, const int32_t* __restrict__ cells,
                   const int32_t* __restrict__ cell2nnz, const double* __restrict__ coords,
-                  int64_t nrows_owned, double c_stiff, double c_mass, double s_poly, cb_poly f,
+                  int64_t nrows_owned, double c_stiff, double c_mass, double s_poly, P f,
                   cb_quad q, double s_nodal, const double* __restrict__ fnodal,
                   const uint8_t* __restrict__ bc_flag, const double* __restrict__ bc_val,
                   double* __restrict__ val, double* __restrict__ rhs, double* __restrict__ cell_out) {
@@ -75,7 +75,7 @@ k_assemble_scalar(int64_t c_begin, int64_t c_end, const int32_t* __restrict__ ce
 #pragma unroll
             for (int i = 0; i < D; ++i) xq[i] += q.lam[iq][a] * cd.x[a][i];
           }
-          const double fw = poly_eval(f, xq[0], xq[1], xq[2]) * q.w[iq];
+          const double fw = coef_eval<D, DEG, ZDEP>(f, xq[0], xq[1], xq[2]) * q.w[iq];
 #pragma unroll
           for (int a = 0; a < K; ++a) acc[a] += fw * q.lam[iq][a];
         }
@@ -349,12 +349,12 @@ struct ShapeDerivCoef {
   int pull_back;
 };
 
-template <int D>
+template <int D, class P, int DEG, bool ZDEP>
 __global__ void __launch_bounds__(128)
 k_shape_derivative_poisson(int64_t c_begin, int64_t c_end, const int32_t* __restrict__ cells,
                            const double* __restrict__ coords, int64_t nrows_owned,
-                           const double* __restrict__ u, const double* __restrict__ p, cb_poly f,
-                           cb_poly gf0, cb_poly gf1, cb_poly gf2, cb_quad q, ShapeDerivCoef co,
+                           const double* __restrict__ u, const double* __restrict__ p, P f,
+                           P gf0, P gf1, P gf2, cb_quad q, ShapeDerivCoef co,
                            const double* __restrict__ ud, const uint8_t* __restrict__ bc_flag,
                            double* __restrict__ rhs, double* __restrict__ cell_out) {
   constexpr int K = D + 1;
@@ -388,7 +388,7 @@ k_shape_derivative_poisson(int64_t c_begin, int64_t c_end, const int32_t* __rest
 #pragma unroll
       for (int i = 0; i < D; ++i) igf[a][i] = 0.0;
     }
-    if (f.nterms > 0) {
+    if (coef_nonzero(f)) {
       for (int iq = 0; iq < q.nq; ++iq) {
         double xq[3] = {0.0, 0.0, 0.0};
         double pq = 0.0;
@@ -399,11 +399,12 @@ k_shape_derivative_poisson(int64_t c_begin, int64_t c_end, const int32_t* __rest
           for (int i = 0; i < D; ++i) xq[i] += q.lam[iq][a] * cd.x[a][i];
         }
         const double wp = q.w[iq] * pq;
-        int_fp += wp * poly_eval(f, xq[0], xq[1], xq[2]);
+        constexpr int GDEG = DEG > 0 ? DEG - 1 : 0;  // the gradient tables hold one degree less
+        int_fp += wp * coef_eval<D, DEG, ZDEP>(f, xq[0], xq[1], xq[2]);
         double gfq[3];
-        gfq[0] = poly_eval(gf0, xq[0], xq[1], xq[2]);
-        gfq[1] = poly_eval(gf1, xq[0], xq[1], xq[2]);
-        gfq[2] = (D == 3) ? poly_eval(gf2, xq[0], xq[1], xq[2]) : 0.0;
+        gfq[0] = coef_eval<D, GDEG, ZDEP>(gf0, xq[0], xq[1], xq[2]);
+        gfq[1] = coef_eval<D, GDEG, ZDEP>(gf1, xq[0], xq[1], xq[2]);
+        gfq[2] = (D == 3 && ZDEP) ? coef_eval<D, GDEG, ZDEP>(gf2, xq[0], xq[1], xq[2]) : 0.0;
 #pragma unroll
         for (int a = 0; a < K; ++a) {
 #pragma unroll
@@ -574,6 +575,80 @@ static int check_view(const cb_mesh_view* m) {
   return CB_OK;
 }
 
+template <class P, int DEG, bool ZDEP>
+static int launch_assemble_scalar(cudaStream_t s, const cb_mesh_view* m, double c_stiff, double c_mass, double s_poly,
+                                  const P& ff, const cb_quad& qq, double s_nodal, const double* fnodal,
+                                  const uint8_t* bc_flag, const double* bc_val, double* val, double* rhs) {
+  if (!val && rhs && m->cells_orig && m->v2c_ptr && m->v2c_idx && m->cell_scratch) {
+    // vector by gather: one launch over all cells (local vectors to scratch) + one per-vertex sum
+    const int64_t nc = m->colour_off[m->ncolours];
+    const int grid = grid_for(nc, 128, 12), vgrid = grid_for(m->nrows_owned, 256, 8);
+    if (m->dim == 2) {
+      k_assemble_scalar<2, P, DEG, ZDEP><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, nullptr, m->coords, m->nrows_owned, c_stiff,
+                                                  c_mass, s_poly, ff, qq, s_nodal, fnodal, bc_flag, bc_val, nullptr,
+                                                  rhs, m->cell_scratch);
+      CB_LAUNCH_CHECK();
+      k_gather_cell_vectors<2, 1><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
+                                                       m->cell_scratch, rhs);
+    } else {
+      k_assemble_scalar<3, P, DEG, ZDEP><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, nullptr, m->coords, m->nrows_owned, c_stiff,
+                                                  c_mass, s_poly, ff, qq, s_nodal, fnodal, bc_flag, bc_val, nullptr,
+                                                  rhs, m->cell_scratch);
+      CB_LAUNCH_CHECK();
+      k_gather_cell_vectors<3, 1><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
+                                                       m->cell_scratch, rhs);
+    }
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
+  if (val) CB_CUDA_CHECK(cudaMemsetAsync(val, 0, sizeof(double) * m->nnz, s));
+  if (rhs) CB_CUDA_CHECK(cudaMemsetAsync(rhs, 0, sizeof(double) * m->nrows_owned, s));
+  return for_each_colour(m, [&](int64_t b, int64_t e, int grid) {
+    if (m->dim == 2)
+      k_assemble_scalar<2, P, DEG, ZDEP><<<grid, 128, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, m->nrows_owned,
+                                                  c_stiff, c_mass, s_poly, ff, qq, s_nodal, fnodal,
+                                                  bc_flag, bc_val, val, rhs, nullptr);
+    else
+      k_assemble_scalar<3, P, DEG, ZDEP><<<grid, 128, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, m->nrows_owned,
+                                                  c_stiff, c_mass, s_poly, ff, qq, s_nodal, fnodal,
+                                                  bc_flag, bc_val, val, rhs, nullptr);
+  });
+}
+
+template <class P, int DEG, bool ZDEP>
+static int launch_shape_derivative(cudaStream_t s, const cb_mesh_view* m, const double* u, const double* p, const P& f,
+                                   const P& g0, const P& g1, const P& g2, const cb_quad& q, const ShapeDerivCoef& co,
+                                   const double* u_d, const uint8_t* bc_flag, double* rhs) {
+  if (m->cells_orig && m->v2c_ptr && m->v2c_idx && m->cell_scratch) {
+    const int64_t nc = m->colour_off[m->ncolours];
+    const int grid = grid_for(nc, 128, 12), vgrid = grid_for(m->nrows_owned, 256, 8);
+    if (m->dim == 2) {
+      k_shape_derivative_poisson<2, P, DEG, ZDEP><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, m->coords, m->nrows_owned, u, p, f,
+                                                           g0, g1, g2, q, co, u_d, bc_flag, rhs, m->cell_scratch);
+      CB_LAUNCH_CHECK();
+      k_gather_cell_vectors<2, 2><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
+                                                       m->cell_scratch, rhs);
+    } else {
+      k_shape_derivative_poisson<3, P, DEG, ZDEP><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, m->coords, m->nrows_owned, u, p, f,
+                                                           g0, g1, g2, q, co, u_d, bc_flag, rhs, m->cell_scratch);
+      CB_LAUNCH_CHECK();
+      k_gather_cell_vectors<3, 3><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
+                                                       m->cell_scratch, rhs);
+    }
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
+  CB_CUDA_CHECK(cudaMemsetAsync(rhs, 0, sizeof(double) * m->nrows_owned * m->dim, s));
+  return for_each_colour(m, [&](int64_t b, int64_t e, int grid) {
+    if (m->dim == 2)
+      k_shape_derivative_poisson<2, P, DEG, ZDEP><<<grid, 128, 0, s>>>(b, e, m->cells, m->coords, m->nrows_owned, u, p, f, g0, g1,
+                                                           g2, q, co, u_d, bc_flag, rhs, nullptr);
+    else
+      k_shape_derivative_poisson<3, P, DEG, ZDEP><<<grid, 128, 0, s>>>(b, e, m->cells, m->coords, m->nrows_owned, u, p, f, g0, g1,
+                                                           g2, q, co, u_d, bc_flag, rhs, nullptr);
+  });
+}
+
 extern "C" int cb_assemble_scalar(void* stream, const cb_mesh_view* m, double c_stiff,
                                   double c_mass, double s_poly, const cb_poly* f, const cb_quad* q,
                                   double s_nodal, const double* fnodal, const uint8_t* bc_flag,
@@ -609,40 +684,19 @@ extern "C" int cb_assemble_scalar(void* stream, const cb_mesh_view* m, double c_
   memset(&qz, 0, sizeof(qz));
   const cb_poly& ff = f ? *f : fz;
   const cb_quad& qq = q ? *q : qz;
-  if (!val && rhs && m->cells_orig && m->v2c_ptr && m->v2c_idx && m->cell_scratch) {
-    // vector by gather: one launch over all cells (local vectors to scratch) + one per-vertex sum
-    const int64_t nc = m->colour_off[m->ncolours];
-    const int grid = grid_for(nc, 128, 12), vgrid = grid_for(m->nrows_owned, 256, 8);
-    if (m->dim == 2) {
-      k_assemble_scalar<2><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, nullptr, m->coords, m->nrows_owned, c_stiff,
-                                               c_mass, s_poly, ff, qq, s_nodal, fnodal, bc_flag, bc_val, nullptr,
-                                               rhs, m->cell_scratch);
-      CB_LAUNCH_CHECK();
-      k_gather_cell_vectors<2, 1><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
-                                                       m->cell_scratch, rhs);
-    } else {
-      k_assemble_scalar<3><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, nullptr, m->coords, m->nrows_owned, c_stiff,
-                                               c_mass, s_poly, ff, qq, s_nodal, fnodal, bc_flag, bc_val, nullptr,
-                                               rhs, m->cell_scratch);
-      CB_LAUNCH_CHECK();
-      k_gather_cell_vectors<3, 1><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
-                                                       m->cell_scratch, rhs);
-    }
-    CB_LAUNCH_CHECK();
-    return CB_OK;
+  // the quadrature loop evaluates the source through the dense degree-4 table when it fits (common.cuh)
+  DensePoly fd;
+  if (dense_from_poly(ff, fd)) {
+    bool zdep = false;
+    const int deg = dense_degree(fd, &zdep);
+#define CB_SCALAR_CASE(DEG, ZDEP) \
+  return launch_assemble_scalar<DensePoly, DEG, ZDEP>(s, m, c_stiff, c_mass, s_poly, fd, qq, s_nodal, fnodal, bc_flag, bc_val, val, rhs)
+    if (zdep && m->dim == 3) { if (deg <= 2) CB_SCALAR_CASE(2, true); CB_SCALAR_CASE(4, true); }
+    if (deg <= 2) CB_SCALAR_CASE(2, false);
+    CB_SCALAR_CASE(4, false);
+#undef CB_SCALAR_CASE
   }
-  if (val) CB_CUDA_CHECK(cudaMemsetAsync(val, 0, sizeof(double) * m->nnz, s));
-  if (rhs) CB_CUDA_CHECK(cudaMemsetAsync(rhs, 0, sizeof(double) * m->nrows_owned, s));
-  return for_each_colour(m, [&](int64_t b, int64_t e, int grid) {
-    if (m->dim == 2)
-      k_assemble_scalar<2><<<grid, 128, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, m->nrows_owned,
-                                               c_stiff, c_mass, s_poly, ff, qq, s_nodal, fnodal,
-                                               bc_flag, bc_val, val, rhs, nullptr);
-    else
-      k_assemble_scalar<3><<<grid, 128, 0, s>>>(b, e, m->cells, m->cell2nnz, m->coords, m->nrows_owned,
-                                               c_stiff, c_mass, s_poly, ff, qq, s_nodal, fnodal,
-                                               bc_flag, bc_val, val, rhs, nullptr);
-  });
+  return launch_assemble_scalar<cb_poly, 0, false>(s, m, c_stiff, c_mass, s_poly, ff, qq, s_nodal, fnodal, bc_flag, bc_val, val, rhs);
 }
 
 extern "C" int cb_assemble_elasticity(void* stream, const cb_mesh_view* m, const double* mu,
@@ -688,38 +742,27 @@ extern "C" int cb_assemble_shape_derivative(void* stream, const cb_mesh_view* m,
   cb_poly gz;
   memset(&gz, 0, sizeof(gz));
   const ShapeDerivCoef co{c_int_u, kappa, reaction, c_track, pull_back};
-  if (m->cells_orig && m->v2c_ptr && m->v2c_idx && m->cell_scratch) {
-    const int64_t nc = m->colour_off[m->ncolours];
-    const int grid = grid_for(nc, 128, 12), vgrid = grid_for(m->nrows_owned, 256, 8);
-    if (m->dim == 2) {
-      k_shape_derivative_poisson<2><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, m->coords, m->nrows_owned, u, p, *f,
-                                                        gradf[0], gradf[1], gz, *q, co, u_d, bc_flag, rhs,
-                                                        m->cell_scratch);
-      CB_LAUNCH_CHECK();
-      k_gather_cell_vectors<2, 2><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
-                                                       m->cell_scratch, rhs);
-    } else {
-      k_shape_derivative_poisson<3><<<grid, 128, 0, s>>>(0, nc, m->cells_orig, m->coords, m->nrows_owned, u, p, *f,
-                                                        gradf[0], gradf[1], gradf[2], *q, co, u_d, bc_flag, rhs,
-                                                        m->cell_scratch);
-      CB_LAUNCH_CHECK();
-      k_gather_cell_vectors<3, 3><<<vgrid, 256, 0, s>>>(m->nrows_owned, m->v2c_ptr, m->v2c_idx, m->cells_orig,
-                                                       m->cell_scratch, rhs);
+  const cb_poly& g2 = (m->dim == 3) ? gradf[2] : gz;
+  DensePoly fd, gd0, gd1, gd2;
+  if (dense_from_poly(*f, fd) && dense_from_poly(gradf[0], gd0) && dense_from_poly(gradf[1], gd1) &&
+      dense_from_poly(g2, gd2)) {
+    bool zdep = false;
+    int deg = dense_degree(fd, &zdep);
+    for (const DensePoly* g : {&gd0, &gd1, &gd2}) {
+      const int dg = dense_degree(*g, &zdep) + 1;
+      if (g->planes && dg > deg) deg = dg;
     }
-    CB_LAUNCH_CHECK();
-    return CB_OK;
+    if (gd2.planes) zdep = true;  // a z-derivative without z-dependence cannot come from one f, but honour it
+    if (deg <= DP_DEG) {
+#define CB_SHAPE_CASE(DEG, ZDEP) \
+  return launch_shape_derivative<DensePoly, DEG, ZDEP>(s, m, u, p, fd, gd0, gd1, gd2, *q, co, u_d, bc_flag, rhs)
+      if (zdep && m->dim == 3) { if (deg <= 2) CB_SHAPE_CASE(2, true); CB_SHAPE_CASE(4, true); }
+      if (deg <= 2) CB_SHAPE_CASE(2, false);
+      CB_SHAPE_CASE(4, false);
+#undef CB_SHAPE_CASE
+    }
   }
-  CB_CUDA_CHECK(cudaMemsetAsync(rhs, 0, sizeof(double) * m->nrows_owned * m->dim, s));
-  return for_each_colour(m, [&](int64_t b, int64_t e, int grid) {
-    if (m->dim == 2)
-      k_shape_derivative_poisson<2><<<grid, 128, 0, s>>>(b, e, m->cells, m->coords, m->nrows_owned, u, p,
-                                                        *f, gradf[0], gradf[1], gz, *q, co, u_d,
-                                                        bc_flag, rhs, nullptr);
-    else
-      k_shape_derivative_poisson<3><<<grid, 128, 0, s>>>(b, e, m->cells, m->coords, m->nrows_owned, u, p,
-                                                        *f, gradf[0], gradf[1], gradf[2], *q, co, u_d,
-                                                        bc_flag, rhs, nullptr);
-  });
+  return launch_shape_derivative<cb_poly, 0, false>(s, m, u, p, *f, gradf[0], gradf[1], g2, *q, co, u_d, bc_flag, rhs);
 }
 
 // the special case the C-ABI started with: kappa = 1, no reaction, J = c int u

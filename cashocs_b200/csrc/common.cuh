@@ -212,7 +212,7 @@ __device__ __forceinline__ void load_coords(const double* __restrict__ coords, c
   }
 }
 
-__device__ __forceinline__ double poly_eval(const cb_poly& p, double x, double y, double z) {
+__host__ __device__ __forceinline__ double poly_eval(const cb_poly& p, double x, double y, double z) {
   double s = 0.0;
   for (int t = 0; t < p.nterms; ++t) {
     double m = p.coef[t];
@@ -223,6 +223,82 @@ __device__ __forceinline__ double poly_eval(const cb_poly& p, double x, double y
   }
   return s;
 }
+
+// Dense coefficient table of a polynomial of total degree <= 4 (35 monomials): what the quadrature loops of the
+// element kernels evaluate when the coefficient fits (the source terms of the reference's demos and tests are of
+// degree <= 4).  The table lives in kernel-parameter space, the nested Horner scheme below is fully unrolled, so
+// every coefficient is an immediate constant-bank operand of one DFMA -- no term loop, no exponent loops, no
+// integer work (the generic monomial evaluator above costs ~10 instructions per multiply).  Rows x^0..x^n of one
+// (j, k) = (power of y, power of z) are contiguous.  The kernels are instantiated for degree <= 2 / <= 4 and for
+// z-independent sources (15 instead of 35 coefficients), chosen on the host from the table.
+constexpr int DP_DEG = 4;
+constexpr int DP_N = 35;
+__host__ __device__ constexpr int dp_offset(int k, int j) {
+  int off = 0;
+  for (int kk = 0; kk < k; ++kk)
+    for (int jj = 0; jj <= DP_DEG - kk; ++jj) off += DP_DEG - kk - jj + 1;
+  for (int jj = 0; jj < j; ++jj) off += DP_DEG - k - jj + 1;
+  return off;
+}
+struct DensePoly {
+  double c[DP_N];
+  uint32_t rows;    // bit k * 5 + j: row (j, k) holds a nonzero coefficient
+  uint32_t planes;  // bit k: some row of the plane z^k does
+};
+// false when the polynomial has a monomial of total degree > DP_DEG (callers then keep the generic evaluator)
+inline bool dense_from_poly(const cb_poly& p, DensePoly& d) {
+  memset(&d, 0, sizeof(d));
+  for (int t = 0; t < p.nterms; ++t) {
+    const int i = p.ex[t], j = p.ey[t], k = p.ez[t];
+    if (i < 0 || j < 0 || k < 0 || i + j + k > DP_DEG) return false;
+    if (p.coef[t] == 0.0) continue;
+    d.c[dp_offset(k, j) + i] += p.coef[t];
+    d.rows |= 1u << (k * 5 + j);
+    d.planes |= 1u << k;
+  }
+  return true;
+}
+// Horner scheme over the table, specialised at compile time on the degree (DEG <= DP_DEG: rows beyond it are not
+// touched) and on whether the polynomial depends on z: straight-line DFMAs with constant-bank operands.
+template <int D, int DEG, bool ZDEP>
+__host__ __device__ __forceinline__ double dense_eval(const DensePoly& p, double x, double y, double z) {
+  double sz = 0.0;
+#pragma unroll
+  for (int k = ((D == 3 && ZDEP) ? DEG : 0); k >= 0; --k) {
+    double sy = 0.0;
+#pragma unroll
+    for (int j = DEG - k; j >= 0; --j) {
+      const int o = dp_offset(k, j), n = DEG - k - j;
+      double sx = p.c[o + n];
+#pragma unroll
+      for (int i = n - 1; i >= 0; --i) sx = fma(sx, x, p.c[o + i]);
+      sy = (j == DEG - k) ? sx : fma(sy, y, sx);
+    }
+    sz = (k == ((D == 3 && ZDEP) ? DEG : 0)) ? sy : fma(sz, z, sy);
+  }
+  return sz;
+}
+// total degree and z-dependence of a table (host side: picks the kernel instantiation)
+inline int dense_degree(const DensePoly& p, bool* zdep) {
+  int deg = 0;
+  for (int k = 0; k <= DP_DEG; ++k)
+    for (int j = 0; j <= DP_DEG - k; ++j)
+      for (int i = 0; i <= DP_DEG - k - j; ++i)
+        if (p.c[dp_offset(k, j) + i] != 0.0) {
+          if (i + j + k > deg) deg = i + j + k;
+          if (k > 0 && zdep) *zdep = true;
+        }
+  return deg;
+}
+// one name for both representations, so the element kernels are templated on the coefficient type
+template <int D, int DEG, bool ZDEP>
+__device__ __forceinline__ double coef_eval(const cb_poly& p, double x, double y, double z) { return poly_eval(p, x, y, z); }
+template <int D, int DEG, bool ZDEP>
+__device__ __forceinline__ double coef_eval(const DensePoly& p, double x, double y, double z) {
+  return dense_eval<D, DEG, ZDEP>(p, x, y, z);
+}
+__device__ __forceinline__ bool coef_nonzero(const cb_poly& p) { return p.nterms > 0; }
+__device__ __forceinline__ bool coef_nonzero(const DensePoly& p) { return p.planes != 0u; }
 
 // out[v, :] = sum over the cells c of vertex v (ascending c) of cell_vec[c, local index of v, :]
 template <int D, int NC>

@@ -31,6 +31,8 @@ HaloDev dist_halo_dev(const cb_dist* d);
 int64_t dist_ghost_capacity(const cb_dist* d);
 int64_t dist_recv_len(const cb_dist* d);
 
+int spmv_residual_dispatch(cudaStream_t s, const cb_mat* A, const double* x, const double* b, double* y, const int* done,
+                           bool use32);
 int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, const double* w,
                   double* result, double* scratch, const int* done = nullptr, bool use32 = false);
 int amg_restrict(cudaStream_t s, int bs, const cb_amg_level* L, const double* b, const double* t, double* bc,
@@ -407,17 +409,18 @@ k_gather_nodes(int64_t n, int bs, const int32_t* __restrict__ gid, const double*
 // z is only touched at the row a lane owns (the gather reads e, the coarse vector): in place.
 // DOTS (fine level, last kernel of the cycle): also sums = (z.b, z.z) for the PCG recurrences.
 template <int BS, bool DOTS, typename VT>
-__global__ void __launch_bounds__(SpmvCfg<BS, VT>::THREADS)
+__global__ void __launch_bounds__(2 * SpmvCfg<BS, VT>::THREADS)
 k_amg_post(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
            const VT* __restrict__ val, const double* __restrict__ e, double* __restrict__ z,
            const double* __restrict__ b, const double* __restrict__ t, const double* __restrict__ dinv,
            double c2, double* __restrict__ dvec, KspState* st, double* hist, double* scratch,
-           int finalize_mode /* -1 none, 0 init, 1 iter */, const double* __restrict__ w /* flexible beta: z.w */) {
+           int finalize_mode /* -1 none, 0 init, 1 iter */, const double* __restrict__ w /* flexible beta: z.w */,
+           int t_is_residual /* t holds b - A x0 (level_spmv with residual_of) instead of A x0 */) {
   if (st->done) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SpmvSmem<BS, VT> sm = spmv_smem_init<BS, VT>(smem_raw);
   uint32_t phase = 0;
-  const int R = spmv_rows_per_cta<BS>(G);
+  const int R = (32 / (BS * G)) * (int)(blockDim.x >> 5);  // rows per CTA: the launcher picks the warps (cb_mat.cta_warps)
   const int64_t nrb = (nrows + R - 1) / R;
   double zr = 0.0, zz = 0.0, zw = 0.0;
   for (int64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
@@ -426,12 +429,12 @@ k_amg_post(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32
     double acc;
     const int64_t i = spmv_row_block<BS, VT>(sm, rowptr, col, val, e, row0, nr, G, phase, acc);
     if (i >= 0) {
-      const double bi = b[i];
-      const double di = c2 * dinv[i] * (bi - t[i] - acc);
+      const double ri = t_is_residual ? t[i] : b[i] - t[i];
+      const double di = c2 * dinv[i] * (ri - acc);
       if (dvec) dvec[i] = di;
       const double zi = z[i] + di;
       z[i] = zi;
-      if (DOTS) { zr += zi * bi; zz += zi * zi; if (w) zw += zi * w[i]; }
+      if (DOTS) { zr += zi * b[i]; zz += zi * zi; if (w) zw += zi * w[i]; }
     }
   }
   if (DOTS) {
@@ -737,8 +740,11 @@ struct Solver {
   }
 
   // t_l = A_l x_l (ghost update of x_l first on a partitioned mesh)
-  int level_spmv(const cb_amg_level& L, double* xl) {
+  // L.t = A_l x  -- or, with `residual_of` = the level's right-hand side, L.t = b - A_l x in the same pass (what the
+  // restriction and the first post-smoothing step read: one vector instead of two)
+  int level_spmv(const cb_amg_level& L, double* xl, const double* residual_of = nullptr) {
     if (L.dist) { if (int e = dist_halo_exchange(s, L.dist, xl, bs, L.sendbuf)) return e; }
+    if (residual_of) return spmv_residual_dispatch(s, &L.A, xl, residual_of, L.t, &st->done, /*use32=*/true);
     return spmv_dispatch(s, &L.A, xl, L.t, nullptr, nullptr, nullptr, &st->done, /*use32=*/true);
   }
 
@@ -768,12 +774,20 @@ struct Solver {
     return CB_OK;
   }
 
+  // the residual pass of the V-cycle writes lev.t = b - A x (scalar-prolongator hierarchies): restriction and the
+  // A*P post-smoothing step then read one vector instead of two
+  bool t_residual = false;
   template <int BS, typename VT>
   int amg_post_bs(const cb_mat* AP, const VT* val, const double* e, double* z, const double* b, const double* t,
                   const double* dinv, double c2, double* dvec, int dots_mode) {
     using C = SpmvCfg<BS, VT>;
     const int G = spmv_sanitize_split(AP->row_split);
-    const int R = spmv_rows_per_cta<BS>(G);
+    // short rows (A*P): more rows per CTA keep the bulk copies as large as those of A (cb_mat.cta_warps)
+    int warps = AP->cta_warps > 0 ? AP->cta_warps : C::WARPS;
+    if (warps < C::WARPS) warps = C::WARPS;
+    if (warps > 2 * C::WARPS) warps = 2 * C::WARPS;
+    const int threads = 32 * warps;
+    const int R = (32 / (BS * G)) * warps;
     const int64_t nrb = (AP->nrows + R - 1) / R;
     int64_t cap = (int64_t)num_sms() * C::CTAS_PER_SM;
     if (cap > RED_MAXP) cap = RED_MAXP;
@@ -786,11 +800,11 @@ struct Solver {
       configured = true;
     }
     if (dots_mode > -2)
-      k_amg_post<BS, true, VT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(AP->nrows, G, AP->rowptr, AP->col, val, e, z, b, t,
-                                                                     dinv, c2, dvec, st, hist_dev, scratch, dots_mode, flex_w);
+      k_amg_post<BS, true, VT><<<grid, threads, C::SMEM_BYTES, s>>>(AP->nrows, G, AP->rowptr, AP->col, val, e, z, b, t,
+                                                                     dinv, c2, dvec, st, hist_dev, scratch, dots_mode, flex_w, t_residual ? 1 : 0);
     else
-      k_amg_post<BS, false, VT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(AP->nrows, G, AP->rowptr, AP->col, val, e, z, b, t,
-                                                                      dinv, c2, dvec, st, hist_dev, scratch, -1, nullptr);
+      k_amg_post<BS, false, VT><<<grid, threads, C::SMEM_BYTES, s>>>(AP->nrows, G, AP->rowptr, AP->col, val, e, z, b, t,
+                                                                      dinv, c2, dvec, st, hist_dev, scratch, -1, nullptr, t_residual ? 1 : 0);
     CB_LAUNCH_CHECK();
     return CB_OK;
   }
@@ -934,6 +948,7 @@ struct Solver {
   int amg_vcycle(const cb_amg* h, const double* r, double* z, bool presmoothed = false, int dots_mode = -2) {
     const int L = h->nlevels;
     dots_fused = false;
+    t_residual = !h->p_block;
     int up_from = L - 2;  // first level of the upward sweep
     for (int l = 0; l < L; ++l) {
       const cb_amg_level& lev = h->levels[l];
@@ -953,14 +968,16 @@ struct Solver {
         break;
       }
       if (int e = amg_smooth(lev, bl, xl, level_degree(h, l), h->smooth_ratio, true, l == 0 && presmoothed)) return e;
-      if (int e = level_spmv(lev, xl)) return e;
+      if (int e = level_spmv(lev, xl, t_residual ? bl : nullptr)) return e;
+      const double* rb = t_residual ? lev.t : bl;       // what the restriction reads: the residual itself ...
+      const double* rt = t_residual ? nullptr : lev.t;  // ... or b and A x
       const cb_amg_level& nxt = h->levels[l + 1];
       if (nxt.rep_dist) {
         // agglomeration: the next level is replicated on every rank; this rank contributes its
         // rows of the restricted residual, one all-reduce assembles the global vector everywhere
         if (nxt.rep_gather && dist_is_one_sided(nxt.rep_gather)) {
           // every coarse row is produced by exactly one rank: one-sided all-gather (one exchange kernel) + unpack
-          if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.rep_tmp, &st->done, h->p_block)) return e;
+          if (int e = amg_restrict(s, bs, &lev, rb, rt, nxt.rep_tmp, &st->done, h->p_block)) return e;
           if (int e = dist_halo_exchange(s, nxt.rep_gather, nxt.rep_tmp, bs, nullptr)) return e;
           const int64_t n_own = lev.nc;
           k_unpack_allgather<<<grid_for(nxt.A.nrows * bs, 256, 4), 256, 0, s>>>(nxt.A.nrows, n_own, nxt.rep_off, bs,
@@ -969,11 +986,11 @@ struct Solver {
         } else {
           const size_t len = sizeof(double) * (size_t)(nxt.A.nrows * bs);
           CB_CUDA_CHECK(cudaMemsetAsync(nxt.b, 0, len, s));
-          if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.b + nxt.rep_off * bs, &st->done, h->p_block)) return e;
+          if (int e = amg_restrict(s, bs, &lev, rb, rt, nxt.b + nxt.rep_off * bs, &st->done, h->p_block)) return e;
           if (int e = dist_allreduce_sum(s, nxt.rep_dist, nxt.b, (int)(nxt.A.nrows * bs))) return e;
         }
       } else {
-        if (int e = amg_restrict(s, bs, &lev, bl, lev.t, nxt.b, &st->done, h->p_block)) return e;
+        if (int e = amg_restrict(s, bs, &lev, rb, rt, nxt.b, &st->done, h->p_block)) return e;
       }
     }
     for (int l = up_from; l >= 0; --l) {

@@ -12,7 +12,8 @@ __global__ void __launch_bounds__(SpmvCfg<BS, VT>::THREADS)
 k_spmv(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
        const VT* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
        const double* __restrict__ w, double* __restrict__ result, double* __restrict__ scratch,
-       const int* __restrict__ done, const double* __restrict__ dscale, double alpha) {
+       const int* __restrict__ done, const double* __restrict__ dscale, double alpha,
+       const double* __restrict__ bsub) {
   if (done && *done) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[33];
@@ -28,6 +29,7 @@ k_spmv(int64_t nrows, int G, const int64_t* __restrict__ rowptr, const int32_t* 
     const int64_t i = spmv_row_block<BS, VT>(sm, rowptr, col, val, x, row0, nr, G, phase, acc);
     if (i >= 0) {
       if (dscale) acc *= alpha * dscale[i];      // power method: y = alpha D^-1 A x ...
+      if (bsub) acc = bsub[i] - acc;             // residual pass of the V-cycle: y = b - A x
       if (WRITE_Y) y[i] = acc;
       if (DOT) local += acc * (w ? w[i] : acc);  // ... with |y|^2 (w == NULL)
     }
@@ -104,7 +106,8 @@ int prefer_smem(K kernel) {
 
 template <int BS, typename VT>
 int launch_spmv(cudaStream_t s, const cb_mat* A, const VT* val, const double* x, double* y, const double* w,
-                double* result, double* scratch, const int* done, const double* dscale = nullptr, double alpha = 1.0) {
+                double* result, double* scratch, const int* done, const double* dscale = nullptr, double alpha = 1.0,
+                const double* bsub = nullptr) {
   using C = SpmvCfg<BS, VT>;
   const int G = spmv_sanitize_split(A->row_split);
   const int grid = spmv_grid<BS, VT>(A->nrows, G);
@@ -116,11 +119,11 @@ int launch_spmv(cudaStream_t s, const cb_mat* A, const VT* val, const double* x,
     configured = true;
   }
   if (y && !w && !result)
-    k_spmv<BS, true, false, VT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, val, x, y, nullptr, nullptr, nullptr, done, dscale, alpha);
+    k_spmv<BS, true, false, VT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, val, x, y, nullptr, nullptr, nullptr, done, dscale, alpha, bsub);
   else if (y)
-    k_spmv<BS, true, true, VT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, val, x, y, w, result, scratch, done, dscale, alpha);
+    k_spmv<BS, true, true, VT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, val, x, y, w, result, scratch, done, dscale, alpha, bsub);
   else
-    k_spmv<BS, false, true, VT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, val, x, nullptr, w, result, scratch, done, dscale, alpha);
+    k_spmv<BS, false, true, VT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(A->nrows, G, A->rowptr, A->col, val, x, nullptr, w, result, scratch, done, dscale, alpha, nullptr);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
@@ -150,6 +153,26 @@ int spmv_dispatch(cudaStream_t s, const cb_mat* A, const double* x, double* y, c
     case 3: return launch_spmv<3, double>(s, A, A->val, x, y, w, result, scratch, done);
   }
   set_error("cb_spmv: unsupported block size %d", A->bs);
+  return CB_ERR_UNSUPPORTED;
+}
+
+// y = b - A x in one pass (the residual the V-cycle restricts); use32 as above
+int spmv_residual_dispatch(cudaStream_t s, const cb_mat* A, const double* x, const double* b, double* y, const int* done,
+                           bool use32) {
+  CB_REQUIRE(A && A->rowptr && A->col && A->val && x && b && y, "spmv_residual: missing argument");
+  if (use32 && A->val32) {
+    switch (A->bs) {
+      case 1: return launch_spmv<1, float>(s, A, A->val32, x, y, nullptr, nullptr, nullptr, done, nullptr, 1.0, b);
+      case 2: return launch_spmv<2, float>(s, A, A->val32, x, y, nullptr, nullptr, nullptr, done, nullptr, 1.0, b);
+      case 3: return launch_spmv<3, float>(s, A, A->val32, x, y, nullptr, nullptr, nullptr, done, nullptr, 1.0, b);
+    }
+  }
+  switch (A->bs) {
+    case 1: return launch_spmv<1, double>(s, A, A->val, x, y, nullptr, nullptr, nullptr, done, nullptr, 1.0, b);
+    case 2: return launch_spmv<2, double>(s, A, A->val, x, y, nullptr, nullptr, nullptr, done, nullptr, 1.0, b);
+    case 3: return launch_spmv<3, double>(s, A, A->val, x, y, nullptr, nullptr, nullptr, done, nullptr, 1.0, b);
+  }
+  set_error("spmv_residual: unsupported block size %d", A->bs);
   return CB_ERR_UNSUPPORTED;
 }
 

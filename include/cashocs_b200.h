@@ -250,6 +250,11 @@ typedef struct {
   const float* val32;     /* nullable: fp32 copy of val (cb_to_f32).  Read ONLY by preconditioner passes (AMG smoothers,
                            * residuals and the A*P post-smoothing inside cb_ksp_solve): half the bytes per pass, products
                            * and sums stay fp64.  The Krylov method's own operator is always `val`. */
+  int32_t cta_warps;      /* launch hint, 0 = default: warps per CTA of the A*P post-smoothing pass.  A CTA streams the
+                           * values of (rows per warp) x (warps) consecutive rows as ONE bulk copy; operators with short
+                           * rows (A*P: ~9 blocks per row against ~15 of A) need more rows per CTA to keep the copies
+                           * -- and with them the bytes in flight per SM -- as large as for A. */
+  int32_t reserved;
 } cb_mat;
 
 /* y = A x  (PETSc Mat.mult; cashocs/_forms/shape_form_handler.py:776-777). */

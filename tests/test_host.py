@@ -32,10 +32,10 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.cb_poly) == 8 + 8 * 24 + 3 * 24
     assert ctypes.sizeof(_lib.cb_quad) == 8 + 8 * 4 * 64 + 8 * 64
-    assert ctypes.sizeof(_lib.cb_mat) == 56
+    assert ctypes.sizeof(_lib.cb_mat) == 64
     assert ctypes.sizeof(_lib.cb_mesh_view) == 120
     assert ctypes.sizeof(_lib.cb_ksp_opts) == 104
-    assert ctypes.sizeof(_lib.cb_amg_level) == 280
+    assert ctypes.sizeof(_lib.cb_amg_level) == 296
     assert ctypes.sizeof(_lib.cb_amg) == 56
     assert ctypes.sizeof(_lib.cb_ksp_result) == 40
     # ... and the ctypes mirrors agree with what the compiled library itself reports
@@ -286,3 +286,22 @@ def test_rcb_partition_is_a_balanced_permutation():
     o1, _ = distributed.rcb_order(pts, 8)
     o2, _ = distributed.rcb_order(pts, 8)
     assert np.array_equal(o1, o2)
+
+
+def test_dense_polynomial_evaluator(tmp_path):
+    """The compile-time Horner tables of the quadrature kernels (csrc/common.cuh: dense_from_poly / dense_eval, every
+    (degree, z-dependence) instantiation the launchers select) agree with the generic monomial evaluator to round-off;
+    host build of the same header, no GPU involved."""
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "dense_poly")
+    subprocess.run([nvcc, "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", os.path.join(root, "include"), "-I",
+                    os.path.join(root, "cashocs_b200", "csrc"), "-o", exe,
+                    os.path.join(root, "tests", "native", "test_dense_poly.cu")], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "degree-5 rejected 1" in out
