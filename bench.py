@@ -475,7 +475,7 @@ def main() -> None:
     # DRAM traffic of the same kernel from the committed `ncu --set full` capture (per launch; only
     # valid for the workload it was captured on: n = 119 on one GPU)
     traffic = None
-    cap = os.path.join(ROOT, "profiles", "r01c_ncu_full_k_cg_spmv.csv")
+    cap = os.path.join(ROOT, "profiles", "r02_ncu_full_k_cg_spmv3.csv")
     if args.n == 119 and world == 1 and args.workload == "cube" and os.path.exists(cap):
         rd = wr = None
         for row in open(cap):
@@ -493,7 +493,7 @@ def main() -> None:
         roofline = {"bound": "hbm", "kernel": f"k_cg_spmv<{prof_bs}> ({'state' if is_control else 'elasticity'} PCG: w = A p, fused p.w)",
                     "achieved": achieved,
                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
-                    "traffic_source": "profiles/r01c_ncu_full_k_cg_spmv.csv (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" if traffic else None,
+                    "traffic_source": "profiles/r02_ncu_full_k_cg_spmv3.csv (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" if traffic else None,
                     "avg_launch_ms": avg_ms, "launches_profiled": spmv_prof, "algorithmic_bytes_per_launch": alg_bytes,
                     # fine-level launches over A per PCG iteration: w = A p and the residual after pre-smoothing
                     # (the post-smoothing residual goes through A*P, k_spmv_post)

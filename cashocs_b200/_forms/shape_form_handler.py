@@ -81,9 +81,13 @@ class ShapeFormHandler:
         self.shape_bdry_fix_z = g("shape_bdry_fix_z")
         self.fixed_dimensions = [int(i) for i in config.getlist("ShapeGradient", "fixed_dimensions")]
         self.use_fixed_dimensions = len(self.fixed_dimensions) > 0
-        for key in ("use_p_laplacian", "reextend_from_boundary", "inhomogeneous", "update_inhomogeneous"):
-            if config.getboolean("ShapeGradient", key) and key in ("use_p_laplacian", "reextend_from_boundary"):
-                raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", key, "outside the hot path (SURVEY.md 8a)")
+        if config.getboolean("ShapeGradient", "use_p_laplacian"):
+            raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "use_p_laplacian", "outside the hot path (SURVEY.md 8a)")
+        self.reextend_from_boundary = config.getboolean("ShapeGradient", "reextend_from_boundary")
+        if self.reextend_from_boundary and config.get("ShapeGradient", "reextension_mode") != "surface":
+            raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "reextension_mode",
+                                         "only the default mode `surface` is implemented (the facet-normal projection of "
+                                         "`normal`, shape_gradient_problem.py:225-299, is not)")
         self.inhomogeneous = config.getboolean("ShapeGradient", "inhomogeneous")
         self.update_inhomogeneous = config.getboolean("ShapeGradient", "update_inhomogeneous")
         self.lambda_lame = config.getfloat("ShapeGradient", "lambda_lame")
@@ -105,6 +109,16 @@ class ShapeFormHandler:
         self.scalar_product_matrix = self.fe_scalar_product_matrix
         self.fe_shape_derivative_vector = torch.zeros(mesh.n_owned_vertices * d, dtype=torch.float64,
                                                       device=mesh.device)
+        if self.reextend_from_boundary:  # shape_form_handler.py:343-367
+            self.bcs_extension = self._setup_bcs_extension()
+            self.bc_flag_ext, _ = forms.bc_flag_arrays(mesh, self.bcs_extension, d)
+            if self.bc_flag_ext is None:
+                self.bc_flag_ext = torch.zeros(mesh.num_vertices * d, dtype=torch.uint8, device=mesh.device)
+            for c in self.fixed_dimensions:
+                self.bc_flag_ext.view(-1, d)[:, c] = 1
+            self.fe_reextension_matrix = linalg.Matrix(mesh, d)
+            self.reextension_matrix = self.fe_reextension_matrix
+            self.fe_reextension_vector = torch.zeros(mesh.n_owned_vertices * d, dtype=torch.float64, device=mesh.device)
         from cashocs_b200._forms import shape_regularization
 
         self.shape_regularization = shape_regularization.ShapeRegularization(mesh, config, self.bc_flag)
@@ -118,6 +132,13 @@ class ShapeFormHandler:
         if self.mesh.dim == 3:
             bcs += forms.create_dirichlet_bcs(0.0, self.shape_bdry_fix_z, 2)
         return bcs
+
+    def _setup_bcs_extension(self) -> list[forms.DirichletBC]:
+        """``shape_form_handler.py:590-611``: every component on every boundary named in ``[ShapeGradient]`` (the values
+        are those of the current gradient deformation, supplied when the right-hand side is assembled)."""
+        all_boundaries = (self.shape_bdry_def + self.shape_bdry_fix + self.shape_bdry_fix_x + self.shape_bdry_fix_y
+                          + self.shape_bdry_fix_z)
+        return forms.create_dirichlet_bcs(0.0, all_boundaries)
 
     def _update_volumes(self) -> None:
         """Cell volumes normalised by their maximum (l2_projection of CellVolume, ``:629-644``)."""
@@ -139,6 +160,11 @@ class ShapeFormHandler:
             self.mesh, self.mu_lame.vector, self.lambda_lame, self.damping_factor, bc_flag=self.bc_flag,
             cell_scale=self.cell_scale if self.inhomogeneous else None, A=self.fe_scalar_product_matrix,
         )
+        if self.reextend_from_boundary:  # shape_form_handler.py:741-744
+            linalg.assemble_elasticity_matrix(
+                self.mesh, self.mu_lame.vector, self.lambda_lame, self.damping_factor, bc_flag=self.bc_flag_ext,
+                cell_scale=self.cell_scale if self.inhomogeneous else None, A=self.fe_reextension_matrix,
+            )
 
     def scalar_product(self, a: torch.Tensor, b: torch.Tensor) -> float:
         """``b^T A a`` (``shape_form_handler.py:748-780``)."""
@@ -183,6 +209,29 @@ class ShapeFormHandler:
             self.shape_regularization.update_geometric_quantities()
             self.shape_regularization.add_shape_derivative(b)
         return b
+
+    def assemble_reextension_vector(self, gradient: torch.Tensor) -> torch.Tensor:
+        """``assembler_extension.assemble(fe_reextension_vector)`` (``shape_gradient_problem.py:193-195``): the zero
+        source with the boundary values of ``gradient`` lifted symmetrically -- row i of a free dof gets
+        ``-sum_j A_ij g_j`` over the Dirichlet dofs j, a Dirichlet row its value times the diagonal the elimination
+        leaves there (the number of cells at the vertex).  The lifting is one SpMV with the scalar-product matrix:
+        its own Dirichlet rows / columns (``bcs_shape``) belong to dofs where the gradient deformation is zero."""
+        n, d = self.mesh.n_owned_vertices * self.mesh.dim, self.mesh.dim
+        flag = self.bc_flag_ext.bool()
+        gb = torch.where(flag, gradient, torch.zeros_like(gradient))
+        b = self.fe_reextension_vector
+        self.scalar_product_matrix.mult(gb, b)
+        b.neg_()
+        valence = self.mesh.valence[: self.mesh.n_owned_vertices].to(torch.float64).repeat_interleave(d)
+        b.copy_(torch.where(flag[:n], valence * gradient[:n], b))
+        return b
+
+    def apply_reextension_bcs(self, function: torch.Tensor, gradient: torch.Tensor) -> None:
+        """``shape_form_handler.py:843-862``: the boundary values of the gradient deformation (zero in the fixed
+        dimensions, where the gradient deformation vanishes already)."""
+        n = function.numel()
+        flag = self.bc_flag_ext[:n].bool()
+        function.copy_(torch.where(flag, gradient[:n], function))
 
     def apply_shape_bcs(self, function: torch.Tensor) -> None:
         """Impose the geometric constraints on a deformation (``shape_form_handler.py:825-841``)."""

@@ -59,6 +59,8 @@ class cb_mesh_view(C.Structure):
         ("v2c_idx", C.c_void_p),
         ("cell_scratch", C.c_void_p),
         ("cell_geo", C.c_void_p),
+        ("rowptr", C.c_void_p),
+        ("col", C.c_void_p),
     ]
 
 

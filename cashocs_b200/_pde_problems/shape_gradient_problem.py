@@ -43,8 +43,29 @@ class ShapeGradientProblem(pde_problem.PDEProblem):
             fh.apply_shape_bcs(g[: b.numel()])
             if self.mesh.dist is not None:
                 self.mesh.dist.halo_exchange(g, self.mesh.dim)
+            self.reextend_gradient_from_boundaries()
             self.has_solution = True
             self.gradient_norm_squared = fh.scalar_product(g, g)
             if self.post_callback is not None:
                 self.post_callback()
         return [self.gradient]
+
+    def reextend_gradient_from_boundaries(self) -> None:
+        """Re-extends the gradient deformation to the volume from its boundary values
+        (``shape_gradient_problem.py:175-223``, mode ``surface``): one more solve with the scalar product's operator,
+        now with Dirichlet conditions on every boundary; the result overwrites the gradient deformation."""
+        fh = self.form_handler
+        if not getattr(fh, "reextend_from_boundary", False):
+            return
+        g = self.gradient.vector
+        b = fh.assemble_reextension_vector(g)
+        x = getattr(self, "_reextended", None)
+        if x is None or x.numel() != g.numel():
+            x = self._reextended = g.new_zeros(g.numel())
+        x.zero_()
+        res = self.linear_solver.solve(x, A=fh.reextension_matrix, b=b, ksp_options=self.ksp_options)
+        self.reextension_iterations = res.its
+        fh.apply_reextension_bcs(x[: b.numel()], g)
+        g[: b.numel()].copy_(x[: b.numel()])
+        if self.mesh.dist is not None:
+            self.mesh.dist.halo_exchange(g, self.mesh.dim)

@@ -172,9 +172,10 @@ def cta_warps_hint(nnzb: int, nrows: int, bs: int, row_split: int = 1) -> int:
     return 0 if w == default else w
 
 
-# matrices are assembled by the nnz-centric gather kernels; False selects the coloured cell-scatter
-# kernels (kept for meshes whose scatter map exceeds int32 and as a cross-check in the tests)
-USE_GATHER_ASSEMBLY = True
+# matrices are assembled row by row (True; csrc/assemble.cu k_assemble_rows); "entries" selects the entry-centric
+# gather kernels over the nnz -> cell lists, False the coloured cell-scatter kernels (both kept as cross-checks in the
+# tests; the scatter kernels also serve meshes whose scatter map exceeds int32)
+USE_GATHER_ASSEMBLY: bool | str = True
 
 
 class Matrix:

@@ -248,6 +248,40 @@ k_cell_geometry(int64_t nc, const int32_t* __restrict__ cells, const double* __r
   }
 }
 
+// Diagonal entries visit every cell around their vertex (~24 in a Kuhn mesh) while off-diagonal ones visit the ~5
+// cells around an edge, and every warp holds two or three diagonal entries: with one thread per entry the whole warp
+// would idle through the diagonal lanes' long loops.  So a lane only walks the list of an OFF-diagonal entry itself;
+// the diagonal entries of a warp are then processed one after the other by the whole warp -- lanes stride over the
+// cell list, partial blocks are combined by a fixed xor-shuffle tree (bit-reproducible, like every other sum here).
+template <int D>
+__device__ __forceinline__ void elasticity_term(const double* __restrict__ geo, int32_t t, bool diag, unsigned bca,
+                                                unsigned bcb, double (&acc)[D * D]) {
+  constexpr int K = D + 1;
+  constexpr int KK = K * K;
+  const int64_t c = t / KK;
+  const int ab = t - (int32_t)c * KK;
+  const int a = ab / K, b = ab - a * K;
+  const double* g = geo + c * GEO_STRIDE;
+  double Ga[D], Gb[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) { Ga[i] = g[a * D + i]; Gb[i] = g[b * D + i]; }
+  const double vm = g[12], vl = g[13], dm = g[14];
+  double gg = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) gg += Ga[i] * Gb[i];
+  const double mass = diag ? 2.0 * dm : dm;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double e = vm * Ga[j] * Gb[i] + vl * Ga[i] * Gb[j];
+      if (i == j) e += vm * gg + mass;
+      if (((bca >> i) & 1u) || ((bcb >> j) & 1u)) e = (diag && i == j) ? 1.0 : 0.0;
+      acc[i * D + j] += e;
+    }
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(256)
 k_assemble_elasticity_gather(int64_t nnz, const int64_t* __restrict__ n2c_ptr, const int32_t* __restrict__ n2c_idx,
@@ -255,25 +289,21 @@ k_assemble_elasticity_gather(int64_t nnz, const int64_t* __restrict__ n2c_ptr, c
                              const uint8_t* __restrict__ bc_flag, double* __restrict__ val) {
   constexpr int K = D + 1;
   constexpr int KK = K * K;
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz;
+  const int lane = threadIdx.x & 31;
+  const int64_t nnz_up = (nnz + 31) & ~int64_t(31);  // warp-uniform trip count (the diagonal pass shuffles)
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz_up;
        q += (int64_t)gridDim.x * blockDim.x) {
-    double acc[D * D];
-#pragma unroll
-    for (int i = 0; i < D * D; ++i) acc[i] = 0.0;
-    const int64_t kb = n2c_ptr[q], ke = n2c_ptr[q + 1];
+    const bool valid = q < nnz;
+    int64_t kb = 0, ke = 0;
     unsigned bca = 0, bcb = 0;
     bool diag = false;
-    for (int64_t k = kb; k < ke; ++k) {
-      const int32_t t = __ldg(n2c_idx + k);
-      const int64_t c = t / KK;
-      const int ab = t - (int32_t)c * KK;
-      const int a = ab / K, b = ab - a * K;
-      const double* g = geo + c * GEO_STRIDE;
-      double Ga[D], Gb[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) { Ga[i] = g[a * D + i]; Gb[i] = g[b * D + i]; }
-      const double vm = g[12], vl = g[13], dm = g[14];
-      if (k == kb) {
+    if (valid) {
+      kb = n2c_ptr[q]; ke = n2c_ptr[q + 1];
+      if (ke > kb) {
+        const int32_t t = __ldg(n2c_idx + kb);
+        const int64_t c = t / KK;
+        const int ab = t - (int32_t)c * KK;
+        const int a = ab / K, b = ab - a * K;
         diag = (a == b);
         if (bc_flag) {  // Dirichlet flags of the row vertex / column vertex (the same for every cell)
           const int64_t va = cells[c * K + a], vb = cells[c * K + b];
@@ -284,24 +314,37 @@ k_assemble_elasticity_gather(int64_t nnz, const int64_t* __restrict__ n2c_ptr, c
           }
         }
       }
-      double gg = 0.0;
+    }
+    if (valid && !diag) {
+      double acc[D * D];
 #pragma unroll
-      for (int i = 0; i < D; ++i) gg += Ga[i] * Gb[i];
-      const double mass = diag ? 2.0 * dm : dm;
+      for (int i = 0; i < D * D; ++i) acc[i] = 0.0;
+      for (int64_t k = kb; k < ke; ++k) elasticity_term<D>(geo, __ldg(n2c_idx + k), false, bca, bcb, acc);
+      double* blk = val + q * (D * D);
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
+      for (int i = 0; i < D * D; ++i) blk[i] = acc[i];
+    }
+    unsigned dmask = __ballot_sync(0xffffffffu, diag);
+    while (dmask) {
+      const int src = __ffs(dmask) - 1;
+      dmask &= dmask - 1;
+      const int64_t skb = __shfl_sync(0xffffffffu, kb, src), ske = __shfl_sync(0xffffffffu, ke, src);
+      const unsigned sbc = __shfl_sync(0xffffffffu, bca, src);  // row vertex == column vertex
+      double acc[D * D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-          double e = vm * Ga[j] * Gb[i] + vl * Ga[i] * Gb[j];
-          if (i == j) e += vm * gg + mass;
-          if (((bca >> i) & 1u) || ((bcb >> j) & 1u)) e = (diag && i == j) ? 1.0 : 0.0;
-          acc[i * D + j] += e;
-        }
+      for (int i = 0; i < D * D; ++i) acc[i] = 0.0;
+      for (int64_t k = skb + lane; k < ske; k += 32) elasticity_term<D>(geo, __ldg(n2c_idx + k), true, sbc, sbc, acc);
+#pragma unroll
+      for (int i = 0; i < D * D; ++i) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+      }
+      if (lane == src) {
+        double* blk = val + q * (D * D);
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) blk[i] = acc[i];
       }
     }
-    double* blk = val + q * (D * D);
-#pragma unroll
-    for (int i = 0; i < D * D; ++i) blk[i] = acc[i];
   }
 }
 
@@ -313,30 +356,209 @@ k_assemble_scalar_gather(int64_t nnz, const int64_t* __restrict__ n2c_ptr, const
   constexpr int K = D + 1;
   constexpr int KK = K * K;
   constexpr double MREF = 1.0 / ((D + 1) * (D + 2));
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz;
+  const int lane = threadIdx.x & 31;
+  const int64_t nnz_up = (nnz + 31) & ~int64_t(31);
+  auto term = [&](int32_t t, bool diag, bool isbc) -> double {
+    const int64_t c = t / KK;
+    const int ab = t - (int32_t)c * KK;
+    const int a = ab / K, b = ab - a * K;
+    const double* g = geo + c * GEO_STRIDE;
+    double gg = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) gg += g[a * D + i] * g[b * D + i];
+    const double e = g[12] * (c_stiff * gg + c_mass * (diag ? 2.0 * MREF : MREF));
+    return isbc ? (diag ? 1.0 : 0.0) : e;
+  };
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz_up;
        q += (int64_t)gridDim.x * blockDim.x) {
-    double acc = 0.0;
-    const int64_t kb = n2c_ptr[q], ke = n2c_ptr[q + 1];
+    const bool valid = q < nnz;
+    int64_t kb = 0, ke = 0;
     bool isbc = false, diag = false;
-    for (int64_t k = kb; k < ke; ++k) {
-      const int32_t t = __ldg(n2c_idx + k);
-      const int64_t c = t / KK;
-      const int ab = t - (int32_t)c * KK;
-      const int a = ab / K, b = ab - a * K;
-      const double* g = geo + c * GEO_STRIDE;
-      if (k == kb) {
+    if (valid) {
+      kb = n2c_ptr[q]; ke = n2c_ptr[q + 1];
+      if (ke > kb) {
+        const int32_t t = __ldg(n2c_idx + kb);
+        const int64_t c = t / KK;
+        const int ab = t - (int32_t)c * KK;
+        const int a = ab / K, b = ab - a * K;
         diag = (a == b);
         if (bc_flag) isbc = bc_flag[cells[c * K + a]] || bc_flag[cells[c * K + b]];
       }
-      double gg = 0.0;
-#pragma unroll
-      for (int i = 0; i < D; ++i) gg += g[a * D + i] * g[b * D + i];
-      double e = g[12] * (c_stiff * gg + c_mass * (diag ? 2.0 * MREF : MREF));
-      if (isbc) e = diag ? 1.0 : 0.0;
-      acc += e;
     }
-    val[q] = acc;
+    if (valid && !diag) {
+      double acc = 0.0;
+      for (int64_t k = kb; k < ke; ++k) acc += term(__ldg(n2c_idx + k), false, isbc);
+      val[q] = acc;
+    }
+    unsigned dmask = __ballot_sync(0xffffffffu, diag);
+    while (dmask) {  // diagonal entries: the whole warp shares the long cell list (see the elasticity kernel)
+      const int src = __ffs(dmask) - 1;
+      dmask &= dmask - 1;
+      const int64_t skb = __shfl_sync(0xffffffffu, kb, src), ske = __shfl_sync(0xffffffffu, ke, src);
+      const bool sbc = __shfl_sync(0xffffffffu, (int)isbc, src) != 0;
+      double acc = 0.0;
+      for (int64_t k = skb + lane; k < ske; k += 32) acc += term(__ldg(n2c_idx + k), true, sbc);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (lane == src) val[q] = acc;
+    }
   }
+}
+
+// ------------------------------------------------------------------ row-centric matrix assembly
+// The entry-centric gather kernels above are bound by L2 traffic: every one of the 16 (a, b) pairs of a cell pulls
+// the cell's 128-byte geometry line again (161 M line requests at n = 119 for 10 M cells).  Here a group of GS lanes
+// (16 for mesh stencils of <= 16 entries per row, else 32) owns one ROW i:
+//   1. the lanes compute the geometry of the cells around vertex i (v2c list, ascending cell id) straight from the
+//      coordinates -- no geometry cache pass, no cache buffer -- into shared memory: each (vertex, cell) pair once;
+//   2. lane e owns entry (i, col[e]) of the row and walks the staged cells in order; a cell that contains the column
+//      vertex contributes its term (fixed summation order: ascending cell id, bit-reproducible and the order of the
+//      n2c lists);
+//   3. Dirichlet rows / columns are eliminated at the end: an eliminated diagonal entry is the number of cells at
+//      the vertex (what dolfin's SystemAssembler leaves there, summing one per cell), other eliminated entries 0.
+// Rows with more cells than a chunk holds (CH = 32) or more entries than the group has lanes are processed in chunks.
+template <int D>
+struct RowCellStage {
+  static constexpr int K = D + 1;
+  static constexpr int CH = 32;
+  int cv[CH][K];
+  double G[CH][K * D];
+  double w[CH][3];
+  int loc[CH];
+};
+
+template <int D, bool ELAST, int GS>
+__global__ void __launch_bounds__(8 * GS)
+k_assemble_rows(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                const int64_t* __restrict__ v2c_ptr, const int32_t* __restrict__ v2c_idx,
+                const int32_t* __restrict__ cells, const double* __restrict__ coords,
+                const double* __restrict__ mu, double p0 /* lambda | c_stiff */, double p1 /* damping | c_mass */,
+                const double* __restrict__ cell_scale, const uint8_t* __restrict__ bc_flag, double* __restrict__ val) {
+  constexpr int K = D + 1;
+  constexpr int NB = ELAST ? D * D : 1;
+  constexpr int CH = RowCellStage<D>::CH;
+  constexpr double MREF = 1.0 / ((D + 1) * (D + 2));
+  __shared__ RowCellStage<D> stage_all[8];
+  const int tile = threadIdx.x / GS, gl = threadIdx.x - tile * GS;
+  RowCellStage<D>& st = stage_all[tile];
+  const unsigned tmask = (GS == 32) ? 0xffffffffu : (0xffffu << (16 * ((threadIdx.x & 31) / 16)));
+  const int64_t tiles_total = (int64_t)gridDim.x * 8;
+  for (int64_t i = blockIdx.x * (int64_t)8 + tile; i < nrows; i += tiles_total) {
+    const int64_t cb0 = v2c_ptr[i], cb1 = v2c_ptr[i + 1];
+    const int64_t eb0 = rowptr[i], eb1 = rowptr[i + 1];
+    for (int64_t e0 = eb0; e0 < eb1; e0 += GS) {  // entry chunks (one for mesh stencils)
+      const bool has_entry = e0 + gl < eb1;
+      const int j = has_entry ? __ldg(col + e0 + gl) : -1;
+      const bool diag = (j == (int)i);
+      double acc[NB];
+#pragma unroll
+      for (int q = 0; q < NB; ++q) acc[q] = 0.0;
+      int count = 0;
+      for (int64_t c0 = cb0; c0 < cb1; c0 += CH) {  // cell chunks (one for mesh vertices of valence <= 32)
+        const int nch = (int)((cb1 - c0 < CH) ? (cb1 - c0) : CH);
+        __syncwarp(tmask);  // the previous chunk is consumed
+        for (int sidx = gl; sidx < nch; sidx += GS) {
+          const int64_t c = __ldg(v2c_idx + c0 + sidx);
+          CellData<D> cd;
+          load_cell_data<D>(cells, coords, c, cd);
+          int a = 0;
+#pragma unroll
+          for (int v = 0; v < K; ++v) {
+            st.cv[sidx][v] = cd.v[v];
+            a = (cd.v[v] == (int)i) ? v : a;
+#pragma unroll
+            for (int d = 0; d < D; ++d) st.G[sidx][v * D + d] = cd.g.G[v][d];
+          }
+          st.loc[sidx] = a;
+          const double vol = cd.g.vol;
+          if (ELAST) {
+            double mubar = 0.0;
+#pragma unroll
+            for (int v = 0; v < K; ++v) mubar += mu[cd.v[v]];
+            mubar *= (1.0 / K);
+            const double scale = cell_scale ? cell_scale[c] : 1.0;
+            st.w[sidx][0] = scale * vol * mubar;
+            st.w[sidx][1] = scale * vol * p0;
+            st.w[sidx][2] = scale * p1 * vol * MREF;
+          } else {
+            st.w[sidx][0] = vol;
+          }
+        }
+        __syncwarp(tmask);
+        if (has_entry) {
+          for (int sidx = 0; sidx < nch; ++sidx) {
+            int b = -1;
+#pragma unroll
+            for (int v = 0; v < K; ++v) b = (st.cv[sidx][v] == j) ? v : b;
+            if (b < 0) continue;
+            const int a = st.loc[sidx];
+            ++count;
+            double gg = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) gg += st.G[sidx][a * D + d] * st.G[sidx][b * D + d];
+            if (ELAST) {
+              const double vm = st.w[sidx][0], vl = st.w[sidx][1], dm = st.w[sidx][2];
+              const double mass = diag ? 2.0 * dm : dm;
+#pragma unroll
+              for (int r = 0; r < D; ++r) {
+#pragma unroll
+                for (int q = 0; q < D; ++q) {
+                  double e = vm * st.G[sidx][a * D + q] * st.G[sidx][b * D + r] +
+                             vl * st.G[sidx][a * D + r] * st.G[sidx][b * D + q];
+                  if (r == q) e += vm * gg + mass;
+                  acc[ELAST ? r * D + q : 0] += e;
+                }
+              }
+            } else {
+              acc[0] += st.w[sidx][0] * (p0 * gg + p1 * (diag ? 2.0 * MREF : MREF));
+            }
+          }
+        }
+      }
+      if (has_entry) {
+        if (ELAST) {
+          unsigned bca = 0, bcb = 0;
+          if (bc_flag) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              if (bc_flag[i * D + d]) bca |= 1u << d;
+              if (bc_flag[(int64_t)j * D + d]) bcb |= 1u << d;
+            }
+          }
+          double* blk = val + (e0 + gl) * NB;
+#pragma unroll
+          for (int r = 0; r < D; ++r) {
+#pragma unroll
+            for (int q = 0; q < D; ++q) {
+              double e = acc[ELAST ? r * D + q : 0];
+              if (((bca >> r) & 1u) || ((bcb >> q) & 1u)) e = (diag && r == q) ? (double)count : 0.0;
+              blk[r * D + q] = e;
+            }
+          }
+        } else {
+          double e = acc[0];
+          if (bc_flag && (bc_flag[i] || bc_flag[j])) e = diag ? (double)count : 0.0;
+          val[e0 + gl] = e;
+        }
+      }
+    }
+  }
+}
+
+template <int D, bool ELAST>
+static int launch_assemble_rows(cudaStream_t s, const cb_mesh_view* m, const double* mu, double p0, double p1,
+                                const double* cell_scale, const uint8_t* bc_flag, double* val) {
+  // mesh stencils (<= 16 entries per row on average with some slack): two rows per warp
+  const bool small = m->nnz <= 16 * m->nrows_owned;
+  const int grid = grid_for(m->nrows_owned, 8, 6);  // 8 rows per CTA and sweep; 6 CTAs x 36 KB of staging per SM
+  if (small)
+    k_assemble_rows<D, ELAST, 16><<<grid, 128, 0, s>>>(m->nrows_owned, m->rowptr, m->col, m->v2c_ptr, m->v2c_idx,
+                                                      m->cells_orig, m->coords, mu, p0, p1, cell_scale, bc_flag, val);
+  else
+    k_assemble_rows<D, ELAST, 32><<<grid, 256, 0, s>>>(m->nrows_owned, m->rowptr, m->col, m->v2c_ptr, m->v2c_idx,
+                                                      m->cells_orig, m->coords, mu, p0, p1, cell_scale, bc_flag, val);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
 }
 
 // ------------------------------------------------------------------ shape derivative of the Poisson-type Lagrangian
@@ -659,6 +881,14 @@ extern "C" int cb_assemble_scalar(void* stream, const cb_mesh_view* m, double c_
   CB_REQUIRE(s_nodal == 0.0 || fnodal, "nodal source missing");
   CB_REQUIRE(bc_flag == nullptr || bc_val != nullptr, "bc_val missing");
   cudaStream_t s = as_stream(stream);
+  if (val && m->rowptr && m->col && m->v2c_ptr && m->v2c_idx && m->cells_orig) {
+    // matrix row by row: the cells around a vertex staged once in shared memory (k_assemble_rows)
+    const int e = (m->dim == 2) ? launch_assemble_rows<2, false>(s, m, nullptr, c_stiff, c_mass, nullptr, bc_flag, val)
+                                : launch_assemble_rows<3, false>(s, m, nullptr, c_stiff, c_mass, nullptr, bc_flag, val);
+    if (e) return e;
+    val = nullptr;
+    if (!rhs) return CB_OK;
+  }
   if (val && m->n2c_ptr && m->n2c_idx && m->cells_orig && m->cell_geo) {
     // matrix by gather: geometry cache pass + one thread per nnz entry
     const int64_t nc = m->colour_off[m->ncolours];
@@ -703,8 +933,11 @@ extern "C" int cb_assemble_elasticity(void* stream, const cb_mesh_view* m, const
                                       double lambda_lame, double damping, const double* cell_scale,
                                       const uint8_t* bc_flag, double* val) {
   if (int e = check_view(m)) return e;
-  CB_REQUIRE(m->cell2nnz && mu && val, "cell2nnz / mu / val missing");
+  CB_REQUIRE((m->cell2nnz || m->rowptr) && mu && val, "cell2nnz / mu / val missing");
   cudaStream_t s = as_stream(stream);
+  if (m->rowptr && m->col && m->v2c_ptr && m->v2c_idx && m->cells_orig)
+    return (m->dim == 2) ? launch_assemble_rows<2, true>(s, m, mu, lambda_lame, damping, cell_scale, bc_flag, val)
+                         : launch_assemble_rows<3, true>(s, m, mu, lambda_lame, damping, cell_scale, bc_flag, val);
   if (m->n2c_ptr && m->n2c_idx && m->cells_orig && m->cell_geo) {
     const int64_t nc = m->colour_off[m->ncolours];
     const int cgrid = grid_for(nc, 256, 8), grid = grid_for(m->nnz, 256, 8);

@@ -184,9 +184,10 @@ class Mesh:
         torch.cuda.current_stream().synchronize()
         self._pattern_ready = True
 
-    def view(self, gather: bool = True) -> _lib.cb_mesh_view:
-        """The struct the assembly entry points take (keeps no ownership).  ``gather=False`` leaves out
-        the nnz-centric data, which selects the coloured cell-scatter kernels for the matrices."""
+    def view(self, gather: bool | str = True) -> _lib.cb_mesh_view:
+        """The struct the assembly entry points take (keeps no ownership).  ``gather=True``: matrices row by row
+        (the default), ``"entries"``: the entry-centric gather kernels over the nnz -> cell lists, ``False`` leaves
+        out all gather data, which selects the coloured cell-scatter kernels."""
         self.build_pattern()
         v = _lib.cb_mesh_view()
         v.dim = self.dim
@@ -211,6 +212,9 @@ class Mesh:
             if self.cell_geo is None:
                 self.cell_geo = torch.empty(self.num_cells * 16, dtype=torch.float64, device=self.device)
             v.cell_geo = self.cell_geo.data_ptr()
+            if gather is True:
+                v.rowptr = self.rowptr.data_ptr()
+                v.col = self.col.data_ptr()
         return v
 
 

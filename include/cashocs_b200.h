@@ -132,6 +132,11 @@ typedef struct {
   const int32_t* v2c_idx;    /* [nc*(dim+1)] */
   double* cell_scratch;
   double* cell_geo;          /* [nc * 16] per-cell geometry cache of the gather matrix kernels (scratch) */
+  /* row-centric matrix assembly, nullable: the CSR pattern itself (cb_pattern_rowptr / cb_pattern_fill).  When present
+   * (together with v2c_* and cells_orig) a group of lanes owns one row: the cells around its vertex are staged once in
+   * shared memory and every entry of the row sums the cells that contain its column vertex, ascending cell id. */
+  const int64_t* rowptr;     /* [nrows_owned+1] */
+  const int32_t* col;        /* [nnz] */
 } cb_mesh_view;
 
 /* Scalar P1:  A = c_stiff*K + c_mass*M ;  rhs = s_poly*int(f phi) + s_nodal*M fnodal.

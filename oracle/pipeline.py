@@ -96,6 +96,9 @@ class ShapeConfig:
     target_surface: float = 0.0
     use_initial_surface: bool = False
     line_search: str = "armijo"          # [LineSearch] method: armijo | basic | polynomial
+    # re-extension of the gradient deformation from its boundary values (shape_gradient_problem.py:175-223)
+    reextend_from_boundary: bool = False
+    reextension_mode: str = "surface"    # "normal" (the facet-normal projection, :225-299) is not restated
     polynomial_model: str = "cubic"
     factor_low: float = 0.1
     factor_high: float = 0.5
@@ -360,10 +363,39 @@ class PoissonShapeProblem:
             if getattr(self, "_volumes", None) is None or self.cfg.update_inhomogeneous:
                 self._volumes = vol / vol.max()
             Ae = Ae / (self._volumes ** self.cfg.inhomogeneous_exponent)[:, None, None]
+        self._Ae_elas = Ae  # the re-extension system eliminates other dofs from the same element tensors
         A, _ = fem.assemble_system(Ae, None, self.vcell_dofs, self.d * self.nv,
                                    self.shape_bc_dofs, 0.0)
         self.A_elas = A
         return A
+
+    def _reextension_bc_dofs(self):
+        """``_setup_bcs_extension`` (shape_form_handler.py:590-611): every component on every boundary the
+        [ShapeGradient] section names, plus the components removed by ``fixed_dimensions`` (:706-712)."""
+        d, c = self.d, self.cfg
+        markers = (tuple(c.shape_bdry_def) + tuple(c.shape_bdry_fix) + tuple(c.shape_bdry_fix_x)
+                   + tuple(c.shape_bdry_fix_y) + tuple(c.shape_bdry_fix_z))
+        bdry = self.mesh.boundary_vertices(markers)
+        dofs = [(d * bdry[:, None] + np.arange(d)[None, :]).reshape(-1)]
+        for k in c.fixed_dimensions:
+            dofs.append(d * np.arange(self.nv) + int(k))
+        return np.unique(np.concatenate(dofs)).astype(np.int64)
+
+    def reextend_gradient_from_boundaries(self, g):
+        """``ShapeGradientProblem.reextend_gradient_from_boundaries`` (shape_gradient_problem.py:175-223), mode
+        ``surface``: solve the homogeneous elasticity equation of the scalar product with the boundary values of the
+        gradient deformation as Dirichlet data (symmetric elimination with those values: ``setup_assembler`` with
+        ``bcs_extension``, shape_form_handler.py:343-367) and take the solution as the new gradient deformation."""
+        if self.cfg.reextension_mode != "surface":
+            raise NotImplementedError("reextension_mode = normal is not restated")
+        dofs = self._reextension_bc_dofs()
+        A, b = fem.assemble_system(self._Ae_elas.copy(), np.zeros(self.vcell_dofs.shape), self.vcell_dofs,
+                                   self.d * self.nv, dofs, g[dofs])
+        x, reason, its, _ = krylov.solve(A, b, self.gradient_ksp, block_size=self.d, coords=self.coords)
+        self._check(reason)
+        self.its["reextension"] = its
+        x[dofs] = g[dofs]  # apply_reextension_bcs (shape_form_handler.py:843-862)
+        return x
 
     def scalar_product(self, a, b):
         return float((self.A_elas @ a) @ b)
@@ -434,6 +466,8 @@ class PoissonShapeProblem:
         self._check(reason)
         self.its["gradient"] = its
         g[self.shape_bc_dofs] = 0.0  # apply_shape_bcs (shape_form_handler.py:825-841)
+        if self.cfg.reextend_from_boundary:
+            g = self.reextend_gradient_from_boundaries(g)
         self.gradient = g
         self.gradient_norm_squared = self.scalar_product(g, g)
         return g

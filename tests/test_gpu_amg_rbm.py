@@ -1,9 +1,6 @@
-"""GPU: the kernels of ``csrc/amg_rbm.cu`` (rigid-body modes inside the AMG hierarchy, round-2 work in progress) against
-their numpy restatement in ``tests/test_amg_rbm.py``.
-
-The kernels were written when the GPU budget of round 1 was spent: they compile for sm_100a and their arithmetic is
-checked on the CPU, but they have never run on a device, so this module is opt-in (``CASHOCS_B200_WIP=1``) until its
-first green run -- the first thing to do in round 2."""
+"""GPU: the kernels of ``csrc/amg_rbm.cu`` (rigid-body modes inside the AMG hierarchy, ``pc_amg_nullspace = rigid_body``)
+against their numpy restatement in ``tests/test_amg_rbm.py``, the host-driven V-cycle harness and the block-prolongator
+switch of the fused V-cycle inside ``cb_ksp_solve`` (first green run on a B200: round 2)."""
 
 import ctypes as C
 import os
@@ -16,9 +13,7 @@ from cashocs_b200 import _lib
 
 import test_amg_rbm as ref
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CASHOCS_B200_WIP") != "1",
-                                 reason="round-2 work in progress: kernels not yet validated on a GPU (set CASHOCS_B200_WIP=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def dev(a, dtype=None):

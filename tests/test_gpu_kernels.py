@@ -369,8 +369,8 @@ def test_translation_moves_and_reverts():
 
 @pytest.mark.parametrize("kind", KINDS)
 def test_gather_and_scatter_assembly_agree(kind):
-    """The nnz-centric gather kernels and the coloured cell-scatter kernels assemble the same
-    matrices (different summation order -> round-off only), including the per-cell scaling."""
+    """The row-centric kernel, the entry-centric gather kernels and the coloured cell-scatter kernels assemble the
+    same matrices (different summation order -> round-off only), including the per-cell scaling."""
     dm = device_mesh(kind)
     d = dm.dim
     dm.build_pattern()
@@ -381,15 +381,18 @@ def test_gather_and_scatter_assembly_agree(kind):
     flag_s, val_s = forms.bc_flag_arrays(dm, [cb.DirichletBC(0.3, (1, 3))], 1)
     out = {}
     try:
-        for gather in (True, False):
+        for gather in (True, "entries", False):  # row-centric (default), entry-centric gather, coloured scatter
             linalg.USE_GATHER_ASSEMBLY = gather
             E = linalg.assemble_elasticity_matrix(dm, mu, 1.4, 0.2, bc_flag=flag_v, cell_scale=scale)
             A, b = linalg.assemble_scalar_system(dm, 1.3, 0.4, f_poly=demo_poly(d), bc_flag=flag_s, bc_val=val_s)
             out[gather] = (E.val.clone(), A.val.clone(), b.clone())
+            E2 = linalg.assemble_elasticity_matrix(dm, mu, 1.4, 0.2, bc_flag=flag_v, cell_scale=scale)
+            assert torch.equal(E2.val, E.val)  # bitwise repeatable
     finally:
         linalg.USE_GATHER_ASSEMBLY = True
-    for x, y in zip(out[True], out[False]):
-        assert float((x - y).abs().max() / y.abs().max()) < 1e-13
+    for other in ("entries", False):
+        for x, y in zip(out[True], out[other]):
+            assert float((x - y).abs().max() / y.abs().max()) < 1e-13
 
 
 def test_degenerate_inputs():

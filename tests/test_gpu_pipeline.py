@@ -199,6 +199,34 @@ def test_iteration_budgets_unit_circle(algorithm, budget):
     assert abs(sop.solver.objective_value - hist[-1][1]) < 1e-8 * abs(hist[-1][1])
 
 
+def test_reextension_surface_like_the_reference():
+    """tests/test_shape_optimization.py:1072-1081: ``reextend_from_boundary`` (mode ``surface``) -- the re-extended
+    gradient deformation equals the oracle's, keeps the boundary values of the Riesz gradient, and L-BFGS meets the
+    reference's budget of 7 iterations with the oracle's iteration count."""
+    dm, om = circle()
+    sop = make_sop(dm, sop_config(reextend_from_boundary=True))
+    ocfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, reextend_from_boundary=True)
+    prob = pipeline.PoissonShapeProblem(om, config=ocfg)
+    g0 = prob.compute_shape_gradient()
+    g1 = sop.compute_shape_gradient()[0].vector.cpu().numpy()
+    assert rel(g1, g0) < 1e-8
+    assert abs(sop.gradient_problem.gradient_norm_squared - prob.gradient_norm_squared) < 1e-8 * prob.gradient_norm_squared
+    plain = make_sop(cb.import_mesh(os.path.join(GOLDEN, "unit_circle.npz")), sop_config())
+    gp = plain.compute_shape_gradient()[0].vector.cpu().numpy()
+    bdry = om.boundary_vertices((1,))
+    bd = (2 * bdry[:, None] + np.arange(2)[None, :]).reshape(-1)
+    assert np.array_equal(g1[bd], gp[bd]) and np.max(np.abs(g1 - gp)) > 1e-6
+    dm2, om2 = circle()
+    sop = make_sop(dm2, sop_config(reextend_from_boundary=True))
+    sop.solve(algorithm="bfgs", rtol=1e-2, atol=0.0, max_iter=7)
+    assert sop.solver.converged and sop.solver.relative_norm <= 1e-2
+    ok, hist = pipeline.lbfgs(pipeline.PoissonShapeProblem(om2, config=ocfg), rtol=1e-2, max_iter=7)
+    assert ok and len(hist) - 1 == sop.solver.iteration
+    assert abs(sop.solver.objective_value - hist[-1][1]) < 1e-8 * abs(hist[-1][1])
+    with pytest.raises(cb.InputError):
+        make_sop(dm2, sop_config(reextend_from_boundary=True, reextension_mode="normal"))
+
+
 @pytest.mark.parametrize("method,budget", [("FR", 21), ("PR", 16), ("HS", 18), ("DY", 18), ("HZ", 18)])
 def test_ncg_iteration_budgets_unit_circle(method, budget):
     """tests/test_shape_optimization.py:321-353: the NCG variants meet the reference's budgets and take exactly
@@ -690,8 +718,6 @@ def test_boundary_measure_and_gradient_3d():
     assert np.max(np.abs(b.cpu().numpy() - want)) <= 1e-12 * np.max(np.abs(want))
 
 
-@pytest.mark.skipif(os.environ.get("CASHOCS_B200_WIP") != "1",
-                    reason="written after the round's GPU budget was spent; first run pending (set CASHOCS_B200_WIP=1)")
 def test_control_bcs_like_the_reference():
     """tests/test_optimal_control.py:569-580: Dirichlet conditions on the control -- the control keeps its boundary
     value exactly, L-BFGS converges within the reference's budget of 9 iterations with the oracle's iteration count."""

@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.cb_poly) == 8 + 8 * 24 + 3 * 24
     assert ctypes.sizeof(_lib.cb_quad) == 8 + 8 * 4 * 64 + 8 * 64
     assert ctypes.sizeof(_lib.cb_mat) == 64
-    assert ctypes.sizeof(_lib.cb_mesh_view) == 120
+    assert ctypes.sizeof(_lib.cb_mesh_view) == 136
     assert ctypes.sizeof(_lib.cb_ksp_opts) == 104
     assert ctypes.sizeof(_lib.cb_amg_level) == 296
     assert ctypes.sizeof(_lib.cb_amg) == 56

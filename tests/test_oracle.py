@@ -176,6 +176,26 @@ def test_taylor_test_and_iteration_budgets_unit_circle():
     assert ok and hist[-1][2] <= 1e-2
 
 
+def test_reextension_surface_reference_budget():
+    """tests/test_shape_optimization.py:1072-1081 (``reextend_from_boundary``, mode ``surface``): L-BFGS reaches
+    rtol 1e-2 within the reference's 7 iterations; the re-extended deformation keeps the boundary values of the
+    Riesz gradient and solves the homogeneous elasticity equation in the interior."""
+    load = lambda: meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))  # noqa: E731
+    cfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, reextend_from_boundary=True)
+    prob = pipeline.PoissonShapeProblem(load(), config=cfg)
+    g = prob.compute_shape_gradient()
+    g0 = pipeline.PoissonShapeProblem(load(), config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02)).compute_shape_gradient()
+    bdry = prob.mesh.boundary_vertices((1,))
+    bd = (2 * bdry[:, None] + np.arange(2)[None, :]).reshape(-1)
+    assert np.array_equal(g[bd], g0[bd]) and np.max(np.abs(g - g0)) > 1e-6
+    interior = np.setdiff1d(np.arange(g.size), bd)
+    free = pipeline.PoissonShapeProblem(load(), config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02))
+    r = free.A_elas @ g  # shape_bdry_fix is empty here: A_elas is the unconstrained operator
+    assert np.max(np.abs(r[interior])) <= 1e-9 * np.max(np.abs(r[bd]))
+    ok, hist = pipeline.lbfgs(pipeline.PoissonShapeProblem(load(), config=cfg), rtol=1e-2, max_iter=7)
+    assert ok and len(hist) - 1 == 6 and hist[-1][2] <= 1e-2
+
+
 def test_taylor_test_inhomogeneous_mu():
     """tests/test_shape_optimization.py:645-670 style: mu_fix=1, mu_def=10 on regular_mesh(20)."""
     m = meshes.regular_mesh(20)
