@@ -345,7 +345,7 @@ class Config(configparser.ConfigParser):
             except ValueError:
                 return None
 
-        for key in ("use_p_laplacian", "use_distance_mu", "reextend_from_boundary", "smooth_mu"):
+        for key in ("use_p_laplacian", "use_distance_mu", "smooth_mu"):
             if boolean("ShapeGradient", key):
                 flag("ShapeGradient", key, "it must be False")
         if self.get("ShapeGradient", "shape_volume_fix").replace(" ", "") != "[]":
