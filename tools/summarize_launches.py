@@ -11,7 +11,7 @@ import sys
 
 
 def short(name: str) -> str:
-    name = name.replace("void ", "")
+    name = name.replace("void ", "").replace("cb::", "")  # ncu prints the namespace only for some builds
     cut = name.find("(")
     return name if cut < 0 else name[:cut]
 
@@ -38,9 +38,9 @@ def main():
         w = csv.writer(f)
         w.writerow(["kernel", "own", "launches", "total_us", "avg_us", "share_of_listed_time"])
         for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            w.writerow([name, int(name.startswith("cb::")), n, f"{t:.1f}", f"{t / n:.2f}", f"{t / total:.4f}"])
+            w.writerow([name, int(name.startswith("k_")), n, f"{t:.1f}", f"{t / n:.2f}", f"{t / total:.4f}"])
         w.writerow(["TOTAL", "", len(launches), f"{total:.1f}", "", "1.0"])
-    idx = [i for i, l in enumerate(launches) if l[0].startswith("cb::k_cg_spmv<3")]
+    idx = [i for i, l in enumerate(launches) if l[0].startswith("k_cg_spmv<3")]
     if len(idx) >= 3:
         a, b = idx[-3], idx[-2]
         with open(out + "_iteration.csv", "w", newline="") as f:
@@ -49,7 +49,7 @@ def main():
             for k, (name, us, g, bl) in enumerate(launches[a:b]):
                 w.writerow([k, name, f"{us:.2f}", g, bl])
             w.writerow(["", "ITERATION TOTAL", f"{sum(l[1] for l in launches[a:b]):.2f}", "", ""])
-    own = sum(n for name, (n, t) in agg.items() if name.startswith("cb::"))
+    own = sum(n for name, (n, t) in agg.items() if name.startswith("k_"))
     print(f"{len(launches)} launches ({own} own), {total / 1e3:.2f} ms listed -> {out}_summary.csv, {out}_iteration.csv")
 
 
