@@ -193,6 +193,9 @@ class LineSearch:
         self.decrease_measure_w_o_step = 1.0
         # line_search.py:83-86: L-BFGS steps are "Newton-like", the relative stepsize criterion does not apply
         self.is_newton_like = cfg.get("OptimizationRoutine", "algorithm").casefold() in ("bfgs", "lbfgs")
+        self.is_newton = cfg.get("OptimizationRoutine", "algorithm").casefold() == "newton"
+        if self.is_newton:  # line_search.py:92-93
+            self.stepsize = 1.0
         self.global_deformation = (self.problem_type == "shape" and cfg.getboolean("ShapeGradient", "global_deformation")
                                    and hasattr(problem, "global_deformation_function"))
         self.log: list[tuple[str, float]] = []
@@ -225,7 +228,7 @@ class LineSearch:
         if self.stepsize * self.search_direction_inf <= 1e-9:
             solver.line_search_broken = True
             return True
-        if not self.is_newton_like and self.stepsize / self.armijo_stepsize_initial <= 1e-9:
+        if not self.is_newton_like and not self.is_newton and self.stepsize / self.armijo_stepsize_initial <= 1e-9:
             solver.line_search_broken = True
             return True
         return False

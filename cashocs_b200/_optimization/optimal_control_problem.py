@@ -77,7 +77,7 @@ class OptimalControlProblem:
     def solve(self, algorithm: str | None = None, rtol: float | None = None, atol: float | None = None,
               max_iter: int | None = None) -> None:
         """``OptimalControlProblem.solve`` (``optimal_control_problem.py:362-425``): gradient descent, L-BFGS and
-        the nonlinear CG methods with the Armijo rule; Newton is outside the hot path."""
+        the nonlinear CG methods and the truncated Newton method (``:324-325,346-349``)."""
         from cashocs_b200._optimization.shape_optimization_problem import _algorithm_name
 
         algorithm = _algorithm_name(algorithm or self.config.get("OptimizationRoutine", "algorithm"))
@@ -99,9 +99,15 @@ class OptimalControlProblem:
             self.solver = algs.LBFGSMethod(self, line_search)
         elif algorithm == "conjugate_gradient":
             self.solver = algs.NonlinearCGMethod(self, line_search)
+        elif algorithm == "newton":
+            from cashocs_b200._pde_problems import hessian_problems
+
+            self.hessian_problem = hessian_problems.HessianProblem(self)
+            self.solver = algs.NewtonMethod(self, line_search)
         else:
-            raise _exceptions.InputError("cashocs_b200.OptimalControlProblem.solve", "algorithm",
-                                         f"{algorithm!r}: the device path drives gradient_descent, bfgs and conjugate_gradient")
+            raise _exceptions.InputError(
+                "cashocs_b200.OptimalControlProblem.solve", "algorithm",
+                f"{algorithm!r}: the device path drives gradient_descent, bfgs, conjugate_gradient and newton")
         self.solver.run()
         self.solver.post_processing()
 

@@ -1,7 +1,7 @@
 """Optimisation algorithms driving the hot path (``cashocs/_optimization/optimization_algorithms/``).
 
 Gradient descent (``gradient_descent.py:28-60``), L-BFGS with the two-loop recursion
-(``l_bfgs.py:91-300``) and the nonlinear CG methods (``ncg.py``); every inner product is ``form_handler.scalar_product`` (= fused SpMV + dot
+(``l_bfgs.py:91-300``), the nonlinear CG methods (``ncg.py``) and the truncated Newton method (``newton.py``); every inner product is ``form_handler.scalar_product`` (= fused SpMV + dot
 on the device), vectors never leave HBM.  Convergence test and ascent check follow
 ``optimization_algorithm.py:281-331``.
 """
@@ -139,6 +139,42 @@ class GradientDescentMethod(OptimizationAlgorithm):
             self._record()
             torch.neg(self.gradient, out=self.search_direction)
             self.line_search.perform(self, self.search_direction, self.has_curvature_info)
+            self.iteration += 1
+            if self.nonconvergence():
+                break
+
+
+class NewtonMethod(OptimizationAlgorithm):
+    """A truncated Newton method (``optimization_algorithms/newton.py:30-101``): the search direction solves
+    ``J''(u) d = -J'(u)`` inexactly with the CG / CR iterations of the Hessian problem."""
+
+    def __init__(self, problem, line_search) -> None:
+        super().__init__(problem, line_search)
+        self.hessian_problem = problem.hessian_problem
+        self.stepsize = 1.0
+
+    def compute_search_direction(self) -> None:
+        self.search_direction.copy_(self.hessian_problem.newton_solve())
+        self.has_curvature_info = True
+
+    def run(self) -> None:
+        while True:
+            self.compute_gradient()
+            self.gradient_norm = self.ova.compute_gradient_norm()
+            if self.convergence_test():
+                self._record()
+                break
+            self.compute_search_direction()
+            self.check_for_ascent()
+            self.evaluate_cost_functional()
+            self._record()
+            self.line_search.perform(self, self.search_direction, self.has_curvature_info)
+            if self.line_search_broken and self.has_curvature_info:
+                # newton.py:80-92: the Newton direction failed, try the negative gradient once
+                torch.neg(self.gradient, out=self.search_direction)
+                self.has_curvature_info = False
+                self.line_search_broken = False
+                self.line_search.perform(self, self.search_direction, self.has_curvature_info)
             self.iteration += 1
             if self.nonconvergence():
                 break

@@ -815,6 +815,89 @@ def ncg(prob: PoissonShapeProblem, method="DY", rtol=1e-2, atol=0.0, max_iter=50
     return False, hist
 
 
+def truncated_newton(prob, inner="cg", rtol=1e-2, atol=0.0, max_iter=50, inner_rtol=1e-7, inner_atol=0.0, inner_max_it=20):
+    """``NewtonMethod.run`` (``optimization_algorithms/newton.py:57-101``) with the inner Krylov solvers of
+    ``HessianProblem`` (``_pde_problems/hessian_problems.py:237-431``: ``newton_solve``, ``cg``, ``cr`` on the reduced
+    Hessian of ``reduced_hessian_application``: identity on the active set, ``H`` restricted to the inactive set).
+    Defaults of the inner solver = ``tests/config_ocp.ini:24-28``.  Returns (converged, history)."""
+    sp = prob.scalar_product
+    act, inact = prob.restrict_to_active_set, prob.restrict_to_inactive_set
+
+    def reduced_hessian(h):
+        """:237-265."""
+        return act(h) + inact(prob.hessian_application(inact(h)))
+
+    def split_product(a, b):
+        """The reference evaluates products of the CG / CR recurrences set by set (:304-310, :357-366)."""
+        return sp(act(a), act(b)) + sp(inact(a), inact(b))
+
+    def newton_step(g):
+        prob.compute_active_sets()
+        delta = np.zeros_like(g)
+        r = -g
+        d = r.copy()
+        eps0 = np.sqrt(sp(r, r))
+        if inner == "cg":  # :282-343
+            rs_old = sp(r, r)
+            for _ in range(inner_max_it):
+                q = reduced_hessian(d)
+                # <p_A, p_A> + <p_I, q_I> (:304-310)
+                alpha = rs_old / (sp(act(d), act(d)) + sp(inact(d), inact(q)))
+                delta = delta + alpha * d
+                r = r - alpha * q
+                rs_new = sp(r, r)
+                if np.sqrt(rs_new) < inner_atol + inner_rtol * eps0:
+                    break
+                d = r + (rs_new / rs_old) * d
+                rs_old = rs_new
+            return delta
+        s = reduced_hessian(r)  # conjugate residuals, :345-431
+        q = s.copy()
+        rar = split_product(r, s)
+        for i in range(inner_max_it):
+            alpha = rar / split_product(q, q)
+            delta = delta + alpha * d
+            r = r - alpha * q
+            if np.sqrt(sp(r, r)) < inner_atol + inner_rtol * eps0 or i == inner_max_it - 1:
+                break
+            s = reduced_hessian(r)
+            rar_new = split_product(r, s)
+            beta = rar_new / rar
+            d = r + beta * d
+            q = s + beta * q
+            rar = rar_new
+        return delta
+
+    hist = []
+    gnorm0 = None
+    stepsize = 1.0  # line_search.py:92-93
+    for it in range(max_iter + 1):
+        g = prob.compute_gradient()
+        gnorm = np.sqrt(prob.gradient_norm_squared)
+        if gnorm0 is None:
+            gnorm0 = gnorm
+        if gnorm <= atol + rtol * gnorm0:
+            hist.append((it, prob.cost(), gnorm / gnorm0, None, stepsize))
+            return True, hist
+        if it == max_iter:
+            hist.append((it, prob.cost(), gnorm / gnorm0, None, stepsize))
+            break
+        d = newton_step(g)
+        has_curv = True
+        if sp(g, d) >= 0:  # check_for_ascent (optimization_algorithm.py:315-331)
+            d, has_curv = -g, False
+        J = prob.cost()
+        hist.append((it, J, gnorm / gnorm0, None, stepsize))
+        step, nxt = line_search(prob, d, 1.0 if has_curv else stepsize, J, iteration=it, has_curvature_info=has_curv,
+                                newton_like=True)
+        if step is None and has_curv:  # newton.py:80-92: fall back to the negative gradient once
+            step, nxt = line_search(prob, -g, nxt, J, iteration=it, has_curvature_info=False, newton_like=True)
+        if step is None:
+            return False, hist
+        stepsize = nxt
+    return False, hist
+
+
 def control_gradient_test(prob, rng=None, h=None):
     """Taylor test of ``cashocs/verification.py:38-179`` for control problems; returns the last convergence rate."""
     rng = rng or np.random.RandomState(300696)
@@ -954,6 +1037,32 @@ class PoissonControlProblem:
         w = self.u - self.project(self.u - self.g) if self.has_box_constraints else self.g
         self.gradient_norm_squared = float((self.M @ w) @ w)
         return self.g
+
+    def hessian_application(self, h):
+        """``HessianProblem.hessian_application`` (``_pde_problems/hessian_problems.py:149-235``) with the forms of
+        ``HessianFormHandler.compute_newton_forms`` (``_forms/control_form_handler.py:281-360,425-542``) worked out for
+        this Lagrangian: sensitivity ``K y' = M h``, adjoint sensitivity ``K p' = w_1 = M y'`` (L_yy = mass form, L_uy = 0),
+        ``hessian_rhs = w_2 + w_3 = alpha M h + M p'`` (L_uu = alpha * mass form, L_yu = 0, w_3 = -d/du[-u p']), then the
+        Riesz solve with the control's scalar product -- all with homogenised state / control conditions."""
+        if self.cubic != 0.0:
+            raise NotImplementedError("second-order forms of the semilinear state equation are not restated")
+        A, b = self._system(np.asarray(h, dtype=float), 1.0)
+        y_prime, reason, _, _ = krylov.solve(A, b, self.state_ksp)
+        PoissonShapeProblem._check(reason)
+        A, b = self._system(y_prime, 1.0)
+        p_prime, reason, _, _ = krylov.solve(A, b, self.adjoint_ksp)
+        PoissonShapeProblem._check(reason)
+        _, vol, _ = fem.cell_geometry(self.coords, self.cells)
+        be = fem.load_elements_p1(vol, self.cells, self.alpha * h + p_prime, self.d)
+        if self.control_bc_dofs.size:
+            _, be = fem.apply_bcs_elementwise(None, be, self.cells, self.control_bc_dofs, 0.0, self.nv)
+        rhs = fem.assemble_vector(be, self.cells, self.nv)
+        if not hasattr(self, "M"):
+            self.M = self.mass_matrix()
+        out, reason, _, _ = krylov.solve(self.M, rhs, self.riesz_ksp)
+        PoissonShapeProblem._check(reason)
+        self.no_sensitivity_solves = getattr(self, "no_sensitivity_solves", 0) + 2
+        return out
 
     # -- box constraints (optimal_control/box_constraints.py:184-346)
     def project(self, a):

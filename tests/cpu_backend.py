@@ -18,6 +18,7 @@ import torch
 import cashocs_b200 as cb
 from cashocs_b200._optimization import line_search as ls
 from cashocs_b200._optimization import optimization_algorithms as algs
+from cashocs_b200._pde_problems import hessian_problems
 from cashocs_b200.io import managers
 
 
@@ -81,6 +82,19 @@ class _MeshHandler:
         return self.oracle.compute_decreases(_np(search_direction), stepsize)
 
 
+class _OracleHessianProblem(hessian_problems.HessianProblem):
+    """The shipped inner CG / CR iterations and active-set splitting, with the Hessian application itself (the
+    three device solves) taken from the oracle."""
+
+    def _setup_device(self) -> None:
+        pass
+
+    def hessian_application(self, h: torch.Tensor, out: torch.Tensor) -> None:
+        self.problem.sync_to_oracle()
+        out.copy_(torch.from_numpy(np.asarray(self.problem.oracle.hessian_application(_np(h).copy()))))
+        self.no_sensitivity_solves += 2
+
+
 class HostProblem:
     """Looks like ``ShapeOptimizationProblem`` / ``OptimalControlProblem`` to the host optimisation layer."""
 
@@ -130,7 +144,9 @@ class HostProblem:
         self.output_manager = managers.OutputManager(self)
         search = ls.create_line_search(self)
         cls = {"gradient_descent": algs.GradientDescentMethod, "bfgs": algs.LBFGSMethod,
-               "conjugate_gradient": algs.NonlinearCGMethod}[algorithm]
+               "conjugate_gradient": algs.NonlinearCGMethod, "newton": algs.NewtonMethod}[algorithm]
+        if algorithm == "newton":
+            self.hessian_problem = _OracleHessianProblem(self)
         self.solver = cls(self, search)
         self.solver.run()
         self.solver.post_processing()

@@ -718,6 +718,57 @@ def test_boundary_measure_and_gradient_3d():
     assert np.max(np.abs(b.cpu().numpy() - want)) <= 1e-12 * np.max(np.abs(want))
 
 
+@pytest.mark.parametrize("inner", ["cg", "cr"])
+@pytest.mark.parametrize("cc,budget", [(None, 2), ((0.0, 100.0), 9)])
+def test_truncated_newton_like_the_reference(inner, cc, budget, rng):
+    """tests/test_optimal_control.py:193-195,228-232: ``solve(algorithm="newton")`` with the inner
+    CG / CR solver of tests/config_ocp.ini:24-28.  The device Hessian application (two solves with the state operator
+    + one mass solve, hessian_problems.py:149-235) equals the oracle's on a random direction; the unconstrained
+    problem is solved to 1e-6 by ONE Newton step (budget 2), the box-constrained one within the budget of 9 with
+    the oracle's iteration count and an admissible control."""
+    dm, om = cb.regular_mesh(10), meshes.regular_mesh(10)
+    yd_h = np.sin(2 * np.pi * om.coords[:, 0]) * np.sin(2 * np.pi * om.coords[:, 1])
+    y, p, u, y_d = (cb.Function(dm) for _ in range(4))
+    y_d.vector.copy_(torch.from_numpy(yd_h))
+    cfg = cb.Config()
+    cfg.set("Output", "save_results", "False")
+    cfg.set("StateSystem", "is_linear", "True")
+    for k, v in (("inner_newton", inner), ("max_it_inner_newton", 20), ("inner_newton_rtol", 1e-7), ("inner_newton_atol", 0.0)):
+        cfg.set("AlgoTNM", k, str(v))
+    ocp = cb.OptimalControlProblem(cb.PoissonForm(source=u), cb.create_dirichlet_bcs(0.0, [1, 2, 3, 4]),
+                                   cb.IntegralFunctional(c_track=1.0, desired_state=y_d, c_control=1e-6), y, u, p, config=cfg,
+                                   control_constraints=None if cc is None else list(cc))
+    oracle = pipeline.PoissonControlProblem(om, yd_h, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4),
+                                            control_constraints=cc)
+    # one Hessian application on a random direction
+    from cashocs_b200._pde_problems import hessian_problems
+
+    hp = hessian_problems.HessianProblem(ocp)
+    h_h = rng.rand(om.num_vertices)
+    h = torch.from_numpy(h_h).to(u.vector.device)
+    out = torch.zeros_like(h)
+    hp.hessian_application(h, out)
+    oracle.solve_state()
+    assert rel(out.cpu().numpy(), oracle.hessian_application(h_h)) < 1e-8
+    # symmetric and positive definite in the control's scalar product
+    h2 = torch.from_numpy(rng.rand(om.num_vertices)).to(h.device)
+    out2 = torch.zeros_like(h)
+    hp.hessian_application(h2, out2)
+    sp = ocp.form_handler.scalar_product
+    assert abs(sp(out, h2) - sp(h, out2)) <= 1e-9 * abs(sp(out, h2)) and sp(out, h) > 0.0
+    ocp.solve(algorithm="newton", rtol=1e-2, atol=0.0, max_iter=budget)
+    ok, hist = pipeline.truncated_newton(oracle, inner=inner, rtol=1e-2, max_iter=budget)
+    s = ocp.solver
+    assert ok and s.converged and s.iteration == len(hist) - 1
+    assert abs(s.objective_value - hist[-1][1]) <= 1e-6 * abs(hist[-1][1])
+    if cc is None:
+        assert s.iteration == 1 and s.relative_norm <= 1e-6
+    else:
+        un = u.vector.cpu().numpy()
+        assert s.relative_norm <= 1e-2 and un.min() >= cc[0] and un.max() <= cc[1] and (un == 0.0).sum() > 0
+    assert ocp.hessian_problem.no_sensitivity_solves > 0
+
+
 def test_control_bcs_like_the_reference():
     """tests/test_optimal_control.py:569-580: Dirichlet conditions on the control -- the control keeps its boundary
     value exactly, L-BFGS converges within the reference's budget of 9 iterations with the oracle's iteration count."""

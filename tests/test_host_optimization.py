@@ -104,6 +104,39 @@ def test_host_layer_reproduces_oracle_and_reference_budgets(kind, algorithm, key
         assert u.min() >= ocfg["cc"][0] and u.max() <= ocfg["cc"][1] and (u == 0.0).sum() > 4 * 10
 
 
+@pytest.mark.parametrize("inner", ["cg", "cr"])
+@pytest.mark.parametrize("cc,budget,ref", [(None, 2, "test_optimal_control.py:193-195"), ((0, 100), 9, "test_optimal_control.py:228-232")])
+def test_truncated_newton_host_layer(inner, cc, budget, ref):
+    """The truncated Newton method (newton.py:57-101) with the inner CG / CR solvers of the Hessian problem
+    (hessian_problems.py:267-431) and the settings of tests/config_ocp.ini:24-28: the oracle's loop meets the
+    reference's budgets (unconstrained: converged to 1e-6 after ONE step; box constraints: 7 (cg) / 8 (cr) of the 9
+    iterations), the shipped host layer walks the same iterates on the stand-in backend."""
+    ocfg = {} if cc is None else {"cc": cc}
+    ok, hist = pipeline.truncated_newton(control_oracle(**ocfg), inner=inner, rtol=1e-2, max_iter=budget)
+    assert ok and len(hist) - 1 < budget, ref
+    if cc is None:
+        assert len(hist) - 1 == 1 and hist[-1][2] <= 1e-6, ref
+    else:
+        assert len(hist) - 1 == {"cg": 7, "cr": 8}[inner], ref
+    cfg = host_config(False)
+    for k, v in (("inner_newton", inner), ("max_it_inner_newton", 20), ("inner_newton_rtol", 1e-7), ("inner_newton_atol", 0.0)):
+        cfg.set("AlgoTNM", k, str(v))
+    host = HostProblem(control_oracle(**ocfg), cfg)
+    host.solve("newton", rtol=1e-2, atol=0.0, max_iter=budget)
+    s = host.solver
+    assert s.converged and s.iteration == len(hist) - 1, ref
+    got = np.array([[h["objective_value"], h["relative_norm"]] for h in s.history])
+    want = np.array([[h[1], h[2]] for h in hist])
+    # the inner solves stop at rtol 1e-7: iterates agree to a few times that, not to round-off
+    assert np.allclose(got[:-1], want[:-1], rtol=1e-5, atol=0.0), ref
+    # the last relative norm is at the level of the inner tolerance: compare it on that scale
+    assert abs(got[-1, 1] - want[-1, 1]) <= 1e-6 and abs(got[-1, 0] - want[-1, 0]) <= 1e-6 * abs(want[-1, 0]), ref
+    assert host.hessian_problem.no_sensitivity_solves > 0
+    if cc is not None:
+        u = host.controls[0].vector.numpy()
+        assert u.min() >= cc[0] and u.max() <= cc[1]
+
+
 def test_small_stepsize_fails_like_the_reference():
     """tests/test_optimal_control.py:562-567: initial_stepsize 1e-8 -> NotConvergedError "Armijo rule failed."."""
     cfg = host_config(False, initial_stepsize=1e-8)
