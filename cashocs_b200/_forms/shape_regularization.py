@@ -1,6 +1,5 @@
 """Geometric regularisation of shape problems (``cashocs/_forms/shape_regularization.py``): volume (``:131-222``),
-surface (``:224-316``) and barycenter (``:318-510``).  Curvature regularisation (a surface Laplace-Beltrami solve)
-stays outside the hot path (``Config._check_supported`` refuses it).
+surface (``:224-316``), barycenter (``:318-510``) and curvature (``:512-646``).
 
 The cell-integral terms need no new kernels: everything is expressed through two existing device entry points.
 
@@ -15,15 +14,43 @@ The cell-integral terms need no new kernels: everything is expressed through two
 The surface term integrates over the boundary facets (``csrc/boundary.cu``): ``cb_boundary_measure`` and
 ``cb_boundary_measure_gradient`` -- for P1 deformations ``int_F t_div(V, n) ds = d|F|[V]`` exactly, so the derivative
 vector is the gradient of the facet measures, gathered per vertex in a fixed order.
+
+The curvature term ``mu/2 int_Gamma |kappa|^2 ds`` needs the mean-curvature vector ``kappa``:
+``int kappa . W ds = int t_grad(x, n) : t_grad(W, n) ds`` for all vector-P1 ``W`` (``_compute_curvature``, ``:596-613``).
+The right-hand side equals ``int t_div(W, n) ds`` (``t_grad(x, n)`` is the tangential projector), i.e. the facet-measure
+gradient again; the matrix is the P1 mass matrix of the boundary, the same for every component, which lives on the
+boundary vertices only (the reference assembles it on all vertices and ``ident_zeros`` the interior rows, where
+``kappa`` is therefore zero): ``cb_boundary_mass`` on the compressed boundary numbering, d solves with the device CG
+(the reference's default direct solver is replaced like everywhere else, ``_utils/linalg.py``), then one facet
+kernel for the derivative (``cb_boundary_curvature_derivative``).
 """
 
 from __future__ import annotations
 
 import torch
 
+from cashocs_b200 import _exceptions
 from cashocs_b200 import _lib
 from cashocs_b200._forms import expressions
 from cashocs_b200._utils import linalg
+
+
+class _BoundarySpace:
+    """What ``linalg.Matrix`` / ``LinearSolver`` read from a mesh, for the P1 space on the boundary vertices."""
+
+    def __init__(self, mesh, nb: int, rowptr: torch.Tensor, col: torch.Tensor, nnz: int) -> None:
+        self._mesh = mesh
+        self.dim = mesh.dim
+        self.device = mesh.device
+        self.dist = None
+        self.n_owned_vertices = self.num_vertices = nb
+        self.rowptr, self.col, self.nnz = rowptr, col, nnz
+
+    def build_pattern(self) -> None:
+        return None
+
+    def reduce_scratch(self) -> torch.Tensor:
+        return self._mesh.reduce_scratch()
 
 
 class ShapeRegularization:
@@ -33,7 +60,9 @@ class ShapeRegularization:
         self.mu_volume = config.getfloat("Regularization", "factor_volume")
         self.mu_barycenter = config.getfloat("Regularization", "factor_barycenter")
         self.mu_surface = config.getfloat("Regularization", "factor_surface")
-        self.is_active = self.mu_volume > 0.0 or self.mu_barycenter > 0.0 or self.mu_surface > 0.0
+        self.mu_curvature = config.getfloat("Regularization", "factor_curvature")
+        self.is_active = (self.mu_volume > 0.0 or self.mu_barycenter > 0.0 or self.mu_surface > 0.0
+                          or self.mu_curvature > 0.0)
         if not self.is_active:
             return
         f64 = dict(dtype=torch.float64, device=mesh.device)
@@ -54,7 +83,7 @@ class ShapeRegularization:
         self.current_barycenter = [0.0, 0.0, 0.0]
         self.current_surface = 1.0
         self.target_surface = config.getfloat("Regularization", "target_surface")
-        if self.mu_surface > 0.0:
+        if self.mu_surface > 0.0 or self.mu_curvature > 0.0:
             self._facets, self._v2f_ptr, self._v2f_idx, counted = mesh.boundary_facet_table()
             # facets this rank adds to the global measure (all of them on one GPU; on a partition every boundary
             # facet is counted by exactly one rank)
@@ -62,8 +91,10 @@ class ShapeRegularization:
             nf = int(self._facets.shape[0])
             self._facet_vec = torch.zeros(max(nf * d * d, 1), **f64)
             self._surface_vector = torch.zeros(mesh.n_owned_vertices * d, **f64)
-            if config.getboolean("Regularization", "use_initial_surface"):
+            if self.mu_surface > 0.0 and config.getboolean("Regularization", "use_initial_surface"):
                 self.target_surface = self.compute_surface()
+        if self.mu_curvature > 0.0:
+            self._setup_curvature()
 
     # -- geometric quantities
     def _integral(self, w: torch.Tensor) -> float:
@@ -106,6 +137,83 @@ class ShapeRegularization:
             mesh.dist.allreduce(self._out, "sum")
         return float(self._out.item())
 
+    # -- curvature (shape_regularization.py:512-646)
+    def _setup_curvature(self) -> None:
+        """Topology-only data of the boundary mass matrix: compressed boundary vertices, their facet graph, its CSR
+        pattern (the pattern builder of the volume meshes with the facets as cells)."""
+        mesh = self.mesh
+        if mesh.dist is not None:
+            raise _exceptions.InputError("cashocs_b200.ShapeRegularization", "factor_curvature",
+                                         "curvature regularisation runs on unpartitioned meshes")
+        d, dev = mesh.dim, mesh.device
+        lib, s = _lib.load(), _lib.stream_ptr()
+        f64 = dict(dtype=torch.float64, device=dev)
+        facets = self._facets.long()
+        bvert = torch.unique(facets.reshape(-1))  # sorted
+        nb, nf = int(bvert.numel()), int(facets.shape[0])
+        facets_c = torch.searchsorted(bvert, facets.reshape(-1)).to(torch.int32).reshape(nf, d).contiguous()
+        v2f_ptr = torch.zeros(nb + 1, dtype=torch.int64, device=dev)
+        v2f_idx = torch.zeros(max(nf * d, 1), dtype=torch.int32, device=dev)
+        _lib.check(lib.cb_v2c_build(s, nb, nf, d, _lib.ptr(facets_c), _lib.ptr(v2f_ptr), _lib.ptr(v2f_idx)), "cb_v2c_build")
+        rowptr = torch.empty(nb + 1, dtype=torch.int64, device=dev)
+        _lib.check(lib.cb_pattern_rowptr(s, nb, d, _lib.ptr(facets_c), _lib.ptr(v2f_ptr), _lib.ptr(v2f_idx),
+                                         _lib.ptr(rowptr)), "cb_pattern_rowptr")
+        nnz = int(rowptr[-1].item())
+        col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        f2n = torch.empty(nf * d * d, dtype=torch.int32, device=dev)
+        _lib.check(lib.cb_pattern_fill(s, nb, nf, d, _lib.ptr(facets_c), _lib.ptr(v2f_ptr), _lib.ptr(v2f_idx),
+                                       _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(f2n)), "cb_pattern_fill")
+        self._bvert, self._bvert32 = bvert, bvert.to(torch.int32).contiguous()
+        self._facets_c, self._bv2f_ptr, self._bv2f_idx = facets_c, v2f_ptr, v2f_idx
+        self._boundary_space = _BoundarySpace(mesh, nb, rowptr, col, nnz)
+        self.boundary_mass = linalg.Matrix(self._boundary_space, 1)
+        self.kappa_curvature = torch.zeros(mesh.num_vertices * d, **f64)
+        self._kappa_b = [torch.zeros(nb, **f64) for _ in range(d)]
+        self._rhs_b = torch.zeros(nb, **f64)
+        self._curv_vector = torch.zeros(mesh.n_owned_vertices * d, **f64)
+        if not hasattr(self, "_facet_vec"):
+            self._facet_vec = torch.zeros(max(nf * d * d, 1), **f64)
+        self._curv_solver = linalg.LinearSolver()
+        self.curvature_iterations = 0
+
+    def _facet_measure_gradient(self, out: torch.Tensor) -> torch.Tensor:
+        mesh = self.mesh
+        _lib.check(
+            _lib.load().cb_boundary_measure_gradient(
+                _lib.stream_ptr(), mesh.dim, int(self._facets.shape[0]), mesh.n_owned_vertices, _lib.ptr(mesh.coords),
+                _lib.ptr(self._facets), _lib.ptr(self._v2f_ptr), _lib.ptr(self._v2f_idx), _lib.ptr(self._facet_vec),
+                _lib.ptr(out)),
+            "cb_boundary_measure_gradient",
+        )
+        return out
+
+    def compute_curvature(self) -> torch.Tensor:
+        """``_compute_curvature`` (``:596-613``): the mean-curvature vector, zero at the interior vertices."""
+        mesh, d = self.mesh, self.mesh.dim
+        A = self.boundary_mass
+        _lib.check(
+            _lib.load().cb_boundary_mass(_lib.stream_ptr(), d, A.nrows, _lib.ptr(mesh.coords), _lib.ptr(self._bvert32),
+                                         _lib.ptr(self._facets_c), _lib.ptr(self._bv2f_ptr), _lib.ptr(self._bv2f_idx),
+                                         _lib.ptr(A.rowptr), _lib.ptr(A.col), _lib.ptr(A.val)),
+            "cb_boundary_mass",
+        )
+        A.touch()
+        b = self._facet_measure_gradient(self._curv_vector).view(-1, d)
+        kappa = self.kappa_curvature.view(-1, d)
+        self.curvature_iterations = 0
+        for c in range(d):
+            torch.index_select(b[:, c], 0, self._bvert, out=self._rhs_b)
+            res = self._curv_solver.solve(self._kappa_b[c], A=A, b=self._rhs_b, ksp_options=None)
+            self.curvature_iterations += res.its
+            kappa[:, c].index_copy_(0, self._bvert, self._kappa_b[c])
+        return self.kappa_curvature
+
+    def compute_curvature_objective(self) -> float:
+        """``mu/2 int_Gamma kappa . kappa ds`` (``:577-594``)."""
+        self.compute_curvature()
+        A = self.boundary_mass
+        return 0.5 * self.mu_curvature * sum(A.scalar_product(k, k) for k in self._kappa_b)
+
     def update_geometric_quantities(self) -> None:
         """``ShapeRegularization.update_geometric_quantities`` (``:670-673``)."""
         if self.is_active:
@@ -127,6 +235,8 @@ class ShapeRegularization:
         if self.mu_barycenter > 0.0:
             bc = self.compute_barycenter()
             value += 0.5 * self.mu_barycenter * sum((bc[k] - self.target_barycenter[k]) ** 2 for k in range(3))
+        if self.mu_curvature > 0.0:
+            value += self.compute_curvature_objective()
         return value
 
     def add_shape_derivative(self, b: torch.Tensor) -> torch.Tensor:
@@ -147,6 +257,19 @@ class ShapeRegularization:
             if self.bc_flag is not None:
                 self._surface_vector.masked_fill_(self.bc_flag[: self._surface_vector.numel()].bool(), 0.0)
             b.add_(self._surface_vector, alpha=self.mu_surface * (self.current_surface - self.target_surface))
+        if self.mu_curvature > 0.0:  # :554-575 with the mean-curvature vector of the current mesh
+            mesh = self.mesh
+            self.compute_curvature()
+            _lib.check(
+                _lib.load().cb_boundary_curvature_derivative(
+                    _lib.stream_ptr(), d, int(self._facets.shape[0]), mesh.n_owned_vertices, _lib.ptr(mesh.coords),
+                    _lib.ptr(self._facets), _lib.ptr(self.kappa_curvature), _lib.ptr(self._v2f_ptr),
+                    _lib.ptr(self._v2f_idx), _lib.ptr(self._facet_vec), _lib.ptr(self._curv_vector)),
+                "cb_boundary_curvature_derivative",
+            )
+            if self.bc_flag is not None:
+                self._curv_vector.masked_fill_(self.bc_flag[: self._curv_vector.numel()].bool(), 0.0)
+            b.add_(self._curv_vector, alpha=self.mu_curvature)
         if self.mu_volume <= 0.0 and self.mu_barycenter <= 0.0:
             return b
         vol, bc, target = self.current_volume, self.current_barycenter, self.target_barycenter

@@ -350,9 +350,6 @@ class Config(configparser.ConfigParser):
                 flag("ShapeGradient", key, "it must be False")
         if self.get("ShapeGradient", "shape_volume_fix").replace(" ", "") != "[]":
             flag("ShapeGradient", "shape_volume_fix", "it must be empty")
-        v = number("Regularization", "factor_curvature")  # volume / surface / barycenter are built
-        if v is not None and v != 0.0:
-            flag("Regularization", "factor_curvature", "curvature regularisation is not built, it must be 0")
         if boolean("Regularization", "use_relative_scaling"):
             flag("Regularization", "use_relative_scaling", "it must be False")
         if boolean("Mesh", "remesh"):

@@ -505,6 +505,20 @@ int cb_boundary_measure(void* stream, int dim, int64_t nf, const double* coords,
 int cb_boundary_measure_gradient(void* stream, int dim, int64_t nf, int64_t nrows, const double* coords,
                                  const int32_t* facets, const int64_t* v2f_ptr, const int32_t* v2f_idx,
                                  double* facet_vec, double* out);
+/* Mass matrix of the boundary, int_Gamma phi_a phi_b ds (CurvatureRegularization.a_curvature per component,
+ * cashocs/_forms/shape_regularization.py:536-542,596-601), on the compressed numbering of the nb boundary
+ * vertices: bvert [nb] compressed -> mesh vertex, facets_c [nf, dim] compressed ids, v2f_* their vertex -> facet
+ * adjacency, rowptr / col the CSR pattern of the facet graph (cb_pattern_* with the facets as cells); val [nnz]. */
+int cb_boundary_mass(void* stream, int dim, int64_t nb, const double* coords, const int32_t* bvert,
+                     const int32_t* facets_c, const int64_t* v2f_ptr, const int32_t* v2f_idx,
+                     const int64_t* rowptr, const int32_t* col, double* val);
+/* out[v, :] = vector of int_Gamma inner((I - (P + P^T)) t_grad(V, n), t_grad(kappa, n)) + 1/2 t_div(V, n)
+ * t_div(kappa, n) ds for V = phi_v e_i, P = t_grad(x, n)  (CurvatureRegularization.compute_shape_derivative,
+ * shape_regularization.py:554-575; the factor mu is applied by the caller); kappa [nv*dim] the mean-curvature
+ * vector; other arguments as cb_boundary_measure_gradient. */
+int cb_boundary_curvature_derivative(void* stream, int dim, int64_t nf, int64_t nrows, const double* coords,
+                                     const int32_t* facets, const double* kappa, const int64_t* v2f_ptr,
+                                     const int32_t* v2f_idx, double* facet_vec, double* out);
 /* Per-vertex collision counts (compute_collisions, cashocs/geometry/mesh_testing.py:201-241)
  * with a uniform-grid broad phase built on the device; mismatch_dev (device int64) receives the
  * number of vertices whose count differs from `valence`. */

@@ -92,7 +92,8 @@ class ShapeConfig:
     factor_barycenter: float = 0.0
     target_barycenter: tuple = (0.0, 0.0, 0.0)
     use_initial_barycenter: bool = False
-    factor_surface: float = 0.0          # :224-316, the only facet term restated here
+    factor_surface: float = 0.0          # :224-316
+    factor_curvature: float = 0.0        # :512-646 (boundary mass solve for the mean-curvature vector)
     target_surface: float = 0.0
     use_initial_surface: bool = False
     line_search: str = "armijo"          # [LineSearch] method: armijo | basic | polynomial
@@ -230,6 +231,87 @@ class PoissonShapeProblem:
                 np.add.at(out, F[:, a], 0.5 * np.cross(X[:, b] - X[:, c], nh))
         return out.reshape(-1)
 
+    # -- curvature regularisation (shape_regularization.py:512-646)
+    def _boundary_frames(self):
+        """For every boundary facet: its vertices F [nf, d], the adjacent cell's vertices C [nf, d+1], the tangential
+        gradients tg [nf, d+1, d] of that cell's hat functions, ``t_grad(phi, n) = grad phi - (grad phi . n) n``
+        (``:49-60``; the reference evaluates ``grad`` in the adjacent cell), the projector P = t_grad(x, n) = I - n n^T
+        [nf, d, d] and the facet measures."""
+        d = self.d
+        F = self.boundary_facets()
+        sub = np.concatenate([np.sort(np.delete(self.cells, k, axis=1), axis=1) for k in range(d + 1)], axis=0)
+        owner = np.tile(np.arange(len(self.cells)), d + 1)
+        key = lambda a: np.ascontiguousarray(a).view([("", a.dtype)] * d).reshape(-1)  # noqa: E731
+        order = np.argsort(key(sub))
+        pos = np.searchsorted(key(sub)[order], key(np.sort(F, axis=1)))
+        cell = owner[order[pos]]
+        C = self.cells[cell]
+        _, _, G = fem.cell_geometry(self.coords, self.cells)
+        G = G[cell]  # [nf, d+1, d]
+        # the hat function of the vertex opposite to the facet is constant zero on it: its gradient is normal
+        opp = np.array([[v not in set(f) for v in c] for c, f in zip(C, F)])
+        nrm = -G[opp]
+        nrm = nrm / np.linalg.norm(nrm, axis=1)[:, None]
+        tg = G - np.einsum("fad,fd->fa", G, nrm)[:, :, None] * nrm[:, None, :]
+        P = np.eye(d)[None] - nrm[:, :, None] * nrm[:, None, :]
+        return F, C, tg, P, self._facet_measures()
+
+    def boundary_mass_matrix(self):
+        """``a_curvature = inner(trial, test) * ds`` per component (``:536-542``) on all vertices, ``ident_zeros``
+        (``:601``) for the interior rows; the exact P1 facet mass matrix |F| (1 + delta_ab) / (d (d + 1))."""
+        import scipy.sparse as sps
+
+        d = self.d
+        F = self.boundary_facets()
+        m = self._facet_measures()
+        loc = (np.ones((d, d)) + np.eye(d)) / (d * (d + 1))
+        rows = np.repeat(F, d, axis=1).reshape(-1)
+        cols = np.tile(F, (1, d)).reshape(-1)
+        vals = (m[:, None, None] * loc[None]).reshape(-1)
+        M = sps.coo_matrix((vals, (rows, cols)), shape=(self.nv, self.nv)).tocsr()
+        interior = np.setdiff1d(np.arange(self.nv), np.unique(F))
+        return M + sps.coo_matrix((np.ones(len(interior)), (interior, interior)), shape=(self.nv, self.nv)).tocsr()
+
+    def compute_curvature(self):
+        """``_compute_curvature`` (``:596-613``): ``M_Gamma kappa = l_curvature`` with
+        ``l_curvature[V] = int inner(t_grad(x, n), t_grad(V, n)) ds`` (``:543-549``); returns kappa [nv, d]."""
+        import scipy.sparse.linalg as spla
+
+        F, C, tg, P, m = self._boundary_frames()
+        d = self.d
+        b = np.zeros((self.nv, d))
+        # inner(P, e_i (x) tg_a) = (P tg_a)_i
+        np.add.at(b, C.reshape(-1), (m[:, None, None] * np.einsum("fij,faj->fai", P, tg)).reshape(-1, d))
+        M = self.boundary_mass_matrix().tocsc()
+        self.kappa_curvature = np.column_stack([spla.spsolve(M, b[:, i]) for i in range(d)])
+        self._boundary_mass = M
+        return self.kappa_curvature
+
+    def curvature_objective(self):
+        """``1/2 mu int kappa . kappa ds`` (``:577-594``)."""
+        k = self.compute_curvature()
+        F = self.boundary_facets()
+        interior = np.setdiff1d(np.arange(self.nv), np.unique(F))
+        kb = k.copy()
+        kb[interior] = 0.0
+        M = self._boundary_mass
+        return 0.5 * self.cfg.factor_curvature * float(sum((M @ kb[:, i]) @ kb[:, i] for i in range(self.d)))
+
+    def curvature_derivative_vector(self):
+        """``compute_shape_derivative`` (``:554-575``) for V = phi_a e_i with the current kappa:
+        ``mu int inner((I - (P + P^T)) t_grad(V), t_grad(kappa)) + 1/2 t_div(V) t_div(kappa) ds``."""
+        F, C, tg, P, m = self._boundary_frames()
+        d = self.d
+        kap = self.kappa_curvature[C]                                # [nf, d+1, d]
+        tK = np.einsum("fbi,fbj->fij", kap, tg)                      # t_grad(kappa) = sum_b kappa_b (x) tg_b
+        R = np.eye(d)[None] - (P + np.transpose(P, (0, 2, 1)))
+        # t_grad(V) = e_i (x) tg_a: inner(R (e_i (x) tg_a), tK) = (R^T tK tg_a)_i ; t_div(V) = tg_a[i]
+        first = np.einsum("fji,fjk,fak->fai", R, tK, tg)
+        second = 0.5 * np.einsum("fii->f", tK)[:, None, None] * tg
+        out = np.zeros((self.nv, d))
+        np.add.at(out, C.reshape(-1), (m[:, None, None] * (first + second)).reshape(-1, d))
+        return self.cfg.factor_curvature * out.reshape(-1)
+
     def regularization_objective(self):
         c = self.cfg
         val = 0.0
@@ -239,6 +321,8 @@ class PoissonShapeProblem:
             val += 0.5 * c.factor_volume * (self.volume() - self.target_volume) ** 2
         if c.factor_barycenter > 0.0:
             val += 0.5 * c.factor_barycenter * float(np.sum((self.barycenter() - self.target_barycenter) ** 2))
+        if c.factor_curvature > 0.0:
+            val += self.curvature_objective()
         return val
 
     def regularization_derivative_elements(self):
@@ -444,6 +528,11 @@ class PoissonShapeProblem:
         vec = self._cell_shape_derivative_vector()
         if self.cfg.factor_surface > 0.0:
             extra = self.cfg.factor_surface * (self.surface() - self.target_surface) * self.surface_derivative_vector()
+            extra[self.shape_bc_dofs] = 0.0
+            vec = vec + extra
+        if self.cfg.factor_curvature > 0.0:
+            self.compute_curvature()  # update_geometric_quantities is not needed: the form holds kappa itself
+            extra = self.curvature_derivative_vector()
             extra[self.shape_bc_dofs] = 0.0
             vec = vec + extra
         return vec

@@ -688,6 +688,81 @@ def test_surface_regularization_like_the_reference():
     assert 0.5 * (reg.compute_surface() - target) ** 2 < 1e-10
 
 
+def test_curvature_regularization_like_the_reference():
+    """tests/test_shape_optimization.py:528-546 (``factor_curvature``, shape_regularization.py:512-646): on the unit
+    disc the mean-curvature vector from the boundary mass solve has mean norm 1 (1e-3) -- the reference's known
+    answer; kappa, the objective 1/2 int |kappa|^2 ds, the shape derivative and the gradient deformation agree with
+    the oracle; the Taylor test of the regularised functional has rate > 1.9; a few gradient steps walk the oracle's
+    iterates."""
+    rng = np.random.RandomState(300696)
+    dm, om = circle()
+    cfg = sop_config(volume_change=10)
+    cfg.set("Regularization", "factor_curvature", "1.0")
+    cfg.set("OptimizationRoutine", "soft_exit", "True")  # the three gradient steps below end at max_iter
+    sop = make_sop_zero_cost(dm, cfg)
+    reg = sop.form_handler.shape_regularization
+    ocfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, factor_curvature=1.0, volume_change=10.0)
+    prob = pipeline.PoissonShapeProblem(om, config=ocfg, c_state=0.0)
+    kappa = reg.compute_curvature().cpu().numpy().reshape(-1, 2)
+    k0 = prob.compute_curvature()
+    F = prob.boundary_facets()
+    interior = np.setdiff1d(np.arange(om.num_vertices), np.unique(F))
+    assert np.all(kappa[interior] == 0.0)
+    bv = np.unique(F)
+    assert rel(kappa[bv], k0[bv]) < 1e-10
+    # the reference's check: int sqrt(kappa . kappa) ds / int 1 ds = 1 (3-point Gauss per segment)
+    m = prob._facet_measures()
+    gp, gw = np.array([0.5 - np.sqrt(0.15), 0.5, 0.5 + np.sqrt(0.15)]), np.array([5.0, 8.0, 5.0]) / 18.0
+    mean = sum(w * np.sum(m * np.linalg.norm((1 - t) * kappa[F[:, 0]] + t * kappa[F[:, 1]], axis=1)) for t, w in zip(gp, gw))
+    assert abs(mean / m.sum() - 1.0) < 1e-3
+    assert abs(reg.compute_curvature_objective() - prob.curvature_objective()) <= 1e-10 * prob.curvature_objective()
+    b = torch.zeros(om.num_vertices * 2, dtype=torch.float64, device=dm.coords.device)
+    reg.add_shape_derivative(b)
+    want = prob.curvature_derivative_vector()
+    want[prob.shape_bc_dofs] = 0.0
+    assert np.max(np.abs(b.cpu().numpy() - want)) <= 1e-10 * np.max(np.abs(want))
+    assert rel(sop.compute_shape_gradient()[0].vector.cpu().numpy(), prob.compute_shape_gradient()) < 1e-8
+    assert abs(sop.reduced_cost_functional.evaluate() - prob.cost()) <= 1e-10 * abs(prob.cost())
+    assert sop.gradient_test(rng=rng) > 1.9
+    sop.solve(algorithm="gd", rtol=0.0, atol=0.0, max_iter=3)
+    ok, hist = pipeline.gradient_descent(prob, rtol=0.0, max_iter=3)
+    got = np.array([h["objective_value"] for h in sop.solver.history])
+    assert len(got) == len(hist) == 4 and np.allclose(got, [h[1] for h in hist], rtol=1e-8) and got[-1] < got[0]
+
+
+def test_curvature_kernels_3d():
+    """The facet kernels of the curvature term on a perturbed unit cube: boundary mass matrix (row sums = vertex shares
+    of the boundary measure, total = |Gamma|), kappa, objective and derivative against the oracle."""
+    n = 4
+    dm, om = cb.regular_mesh(n, 1.0, 1.0, 1.0), meshes.regular_mesh(n, 1.0, 1.0, 1.0)
+    cfg = sop_config(shape_bdry_def="[1, 2, 3, 4, 5, 6]")
+    cfg.set("Regularization", "factor_curvature", "0.5")
+    u, p = cb.Function(dm), cb.Function(dm)
+    sop = cb.ShapeOptimizationProblem(cb.PoissonForm(source=demo_poly(3)), cb.create_dirichlet_bcs(0.0, [1, 2, 3, 4, 5, 6]),
+                                      cb.IntegralFunctional(c_state=0.0), u, p, config=cfg, ksp_options=KSP,
+                                      adjoint_ksp_options=KSP, gradient_ksp_options=KSP)
+    reg = sop.form_handler.shape_regularization
+    prob = pipeline.PoissonShapeProblem(om, bc_markers=(1, 2, 3, 4, 5, 6), c_state=0.0,
+                                        config=pipeline.ShapeConfig(shape_bdry_def=(1, 2, 3, 4, 5, 6), factor_curvature=0.5))
+    shift = 0.02 * np.random.RandomState(5).rand(om.num_vertices, 3)
+    om.coords += shift
+    dm.coords.add_(torch.from_numpy(shift).to(dm.coords.device))
+    kappa = reg.compute_curvature().cpu().numpy().reshape(-1, 3)
+    k0 = prob.compute_curvature()
+    bv = np.unique(prob.boundary_facets())
+    assert rel(kappa[bv], k0[bv]) < 1e-10
+    A = reg.boundary_mass
+    ones = torch.ones(A.nrows, dtype=torch.float64, device=dm.coords.device)
+    assert abs(A.scalar_product(ones, ones) - prob.surface()) <= 1e-12 * prob.surface()
+    M = prob.boundary_mass_matrix()
+    assert np.allclose(A.mult(ones).cpu().numpy(), np.asarray(M[bv][:, bv].sum(axis=1)).ravel(), rtol=1e-12)
+    assert abs(reg.compute_curvature_objective() - prob.curvature_objective()) <= 1e-10 * prob.curvature_objective()
+    b = torch.zeros(om.num_vertices * 3, dtype=torch.float64, device=dm.coords.device)
+    reg.add_shape_derivative(b)
+    want = prob.curvature_derivative_vector()
+    assert np.max(np.abs(b.cpu().numpy() - want)) <= 1e-10 * np.max(np.abs(want))
+
+
 def test_boundary_measure_and_gradient_3d():
     """csrc/boundary.cu on the unit cube: |Gamma| = 6, facet table = the facets of exactly one cell, gradient of the
     boundary measure against the oracle's closed form on a randomly perturbed mesh."""

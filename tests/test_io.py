@@ -167,7 +167,7 @@ def test_config_validation_matches_the_reference_case_by_case():
 
 
 def test_unsupported_subsystems_are_refused_loudly():
-    for sec, key, val in (("ShapeGradient", "use_p_laplacian", "True"), ("Regularization", "factor_curvature", "1.0"),
+    for sec, key, val in (("ShapeGradient", "use_p_laplacian", "True"), ("Regularization", "use_relative_scaling", "True"),
                           ("StateSystem", "backend", "petsc"), ("Mesh", "remesh", "True"),
                           ("ShapeGradient", "smooth_mu", "True")):
         cfg = cb.Config()

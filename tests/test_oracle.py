@@ -484,3 +484,31 @@ def test_newton_solver_and_semilinear_control_gradient():
     assert pipeline.control_gradient_test(prob, rng=np.random.RandomState(300696))[0] > 1.9
     lin = pipeline.PoissonControlProblem(om, yd, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4))
     assert pipeline.control_gradient_test(lin, rng=np.random.RandomState(300696))[0] > 1.9
+
+
+def test_curvature_regularization_known_answer():
+    """tests/test_shape_optimization.py:528-546: on the reference's unit-disc fixture the mean-curvature vector of
+    ``CurvatureRegularization._compute_curvature`` (shape_regularization.py:596-613) has mean norm 1 to 1e-3; the
+    objective is then 1/2 int 1 ds = pi, and the oracle's derivative vector (``:554-575``) passes a Taylor test of the
+    discrete functional with rate 2."""
+    om = meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))
+    prob = pipeline.PoissonShapeProblem(om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, factor_curvature=1.0))
+    k = prob.compute_curvature()
+    F, m = prob.boundary_facets(), prob._facet_measures()
+    gp, gw = np.array([0.5 - np.sqrt(0.15), 0.5, 0.5 + np.sqrt(0.15)]), np.array([5.0, 8.0, 5.0]) / 18.0
+    mean = sum(w * np.sum(m * np.linalg.norm((1 - t) * k[F[:, 0]] + t * k[F[:, 1]], axis=1)) for t, w in zip(gp, gw))
+    assert abs(mean / m.sum() - 1.0) < 1e-3
+    assert abs(prob.curvature_objective() - np.pi) < 5e-3
+    interior = np.setdiff1d(np.arange(om.num_vertices), np.unique(F))
+    assert np.max(np.abs(k[interior])) < 1e-14  # round-off of the normal projection of the opposite hat function
+    rng = np.random.RandomState(300696)
+    dJ = prob.curvature_derivative_vector()
+    h = rng.rand(2 * om.num_vertices)
+    J0, x0 = prob.curvature_objective(), prob.coords.copy()
+    res = []
+    eps = [1e-2 / 2**i for i in range(4)]
+    for e in eps:
+        prob.coords[:] = x0 + e * h.reshape(-1, 2)
+        res.append(abs(prob.curvature_objective() - J0 - e * (dJ @ h)))
+    prob.coords[:] = x0
+    assert np.log(res[-1] / res[-2]) / np.log(0.5) > 1.9
