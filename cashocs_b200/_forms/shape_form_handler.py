@@ -30,8 +30,11 @@ class Stiffness:
         self.shape_bdry_fix = list(shape_bdry_fix)
         self.linear_solver = linear_solver or linalg.LinearSolver()
         self.inhomogeneous_mu = False
-        if config.getboolean("ShapeGradient", "use_distance_mu"):
-            raise _exceptions.InputError("cashocs_b200.Stiffness", "use_distance_mu", "outside the hot path (SURVEY.md 8a)")
+        self.use_distance_mu = config.getboolean("ShapeGradient", "use_distance_mu")
+        self.distance = None
+        if self.use_distance_mu:
+            self._setup_distance_mu()
+            return
         mu_def = config.getfloat("ShapeGradient", "mu_def")
         mu_fix = config.getfloat("ShapeGradient", "mu_fix")
         self.options_mu = ksp_options or {
@@ -47,8 +50,45 @@ class Stiffness:
             self.b_mu = torch.zeros(mesh.n_owned_vertices, dtype=torch.float64, device=mesh.device)
         self.last_its = 0
 
+    def _setup_distance_mu(self) -> None:
+        """``_setup_mu_computation``, distance branch (``shape_form_handler.py:141-186``): mu_min within dist_min of
+        the boundaries ``boundaries_dist``, mu_max beyond dist_max, a linear (or, ``smooth_mu``, cubic) blend between."""
+        from cashocs_b200.geometry import boundary_distance
+
+        cfg = self.config
+        self.mu_min, self.mu_max = cfg.getfloat("ShapeGradient", "mu_min"), cfg.getfloat("ShapeGradient", "mu_max")
+        self.dist_min, self.dist_max = cfg.getfloat("ShapeGradient", "dist_min"), cfg.getfloat("ShapeGradient", "dist_max")
+        self.smooth_mu = cfg.getboolean("ShapeGradient", "smooth_mu")
+        self.last_its = 0
+        self.distance_active = np.abs(self.mu_min - self.mu_max) / self.mu_min > 1e-2
+        method = cfg.get("ShapeGradient", "distance_method")
+        if method != "eikonal":
+            raise _exceptions.InputError("cashocs_b200.Stiffness", "distance_method",
+                                         "the device path computes the distance with the eikonal iteration")
+        if self.distance_active:
+            idcs = [int(m) for m in cfg.getlist("ShapeGradient", "boundaries_dist")]
+            self.eikonal = boundary_distance.EikonalDistance(self.mesh, idcs, linear_solver=self.linear_solver)
+
+    def _compute_distance_mu(self) -> None:
+        """``Stiffness.compute``, distance branch (``shape_form_handler.py:216-235``)."""
+        from cashocs_b200 import _lib
+
+        if not self.distance_active:
+            # the reference leaves mu_expression undefined in this case (:148) and fails at the first compute
+            raise _exceptions.InputError("cashocs_b200.Stiffness", "mu_max",
+                                         "use_distance_mu needs |mu_min - mu_max| / mu_min > 1e-2")
+        self.distance = self.eikonal.compute()
+        self.last_its = self.eikonal.iterations
+        mu = self.mu_lame.vector
+        _lib.check(_lib.load().cb_distance_mu(_lib.stream_ptr(), mu.numel(), _lib.ptr(self.distance), self.dist_min,
+                                              self.dist_max, self.mu_min, self.mu_max, int(self.smooth_mu), _lib.ptr(mu)),
+                   "cb_distance_mu")
+
     def compute(self) -> None:
         """Computes the elasticity parameter mu (``shape_form_handler.py:188-235``)."""
+        if self.use_distance_mu:
+            self._compute_distance_mu()
+            return
         if self.inhomogeneous_mu:
             linalg.assemble_scalar_system(self.mesh, 1.0, 0.0, bc_flag=self.bc_flag, bc_val=self.bc_val,
                                           A=self.A_mu_matrix, b=self.b_mu)

@@ -246,6 +246,9 @@ SIGNATURES = {
     "cb_amg_rbm_prolong": (I32, [P, I64, P, P, P, P, P]),
     "cb_boundary_measure": (I32, [P, I32, I64, P, P, P, P, I64]),
     "cb_boundary_measure_gradient": (I32, [P, I32, I64, I64, P, P, P, P, P, P]),
+    "cb_eikonal_rhs": (I32, [P, I32, I64, P, P, P, P, P, P, P]),
+    "cb_eikonal_residual": (I32, [P, I32, I64, P, P, P, P, P, I64]),
+    "cb_distance_mu": (I32, [P, I64, P, DBL, DBL, DBL, DBL, I32, P]),
     "cb_boundary_mass": (I32, [P, I32, I64, P, P, P, P, P, P, P, P]),
     "cb_boundary_curvature_derivative": (I32, [P, I32, I64, I64, P, P, P, P, P, P, P]),
     "cb_intersection_test": (I32, [P, I32, I64, I64, P, P, P, P, P]),

@@ -12,9 +12,9 @@ INCLUDE = os.path.join(HERE, "..", "include")
 LIB = os.path.join(HERE, "libcashocs_b200.so")
 
 SOURCES = ["api.cu", "pattern.cu", "assemble.cu", "spmv.cu", "krylov.cu", "amg.cu", "meshops.cu", "dist.cu", "p2.cu",
-           "boundary.cu", "amg_rbm.cu", "rbm.cu"]
-# meshops.cu / boundary.cu feed accept/reject thresholds: no FMA contraction (see the file headers)
-EXTRA = {"meshops.cu": ["-fmad=false"], "boundary.cu": ["-fmad=false"]}
+           "boundary.cu", "amg_rbm.cu", "rbm.cu", "distance.cu"]
+# meshops.cu / boundary.cu / distance.cu feed accept/reject thresholds: no FMA contraction (see the file headers)
+EXTRA = {"meshops.cu": ["-fmad=false"], "boundary.cu": ["-fmad=false"], "distance.cu": ["-fmad=false"]}
 COMMON = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC,

@@ -345,9 +345,10 @@ class Config(configparser.ConfigParser):
             except ValueError:
                 return None
 
-        for key in ("use_p_laplacian", "use_distance_mu", "smooth_mu"):
-            if boolean("ShapeGradient", key):
-                flag("ShapeGradient", key, "it must be False")
+        if boolean("ShapeGradient", "use_p_laplacian"):
+            flag("ShapeGradient", "use_p_laplacian", "it must be False")
+        if boolean("ShapeGradient", "use_distance_mu") and self.get("ShapeGradient", "distance_method") != "eikonal":
+            flag("ShapeGradient", "distance_method", "the device path computes boundary distances with eikonal")
         if self.get("ShapeGradient", "shape_volume_fix").replace(" ", "") != "[]":
             flag("ShapeGradient", "shape_volume_fix", "it must be empty")
         if boolean("Regularization", "use_relative_scaling"):

@@ -519,6 +519,21 @@ int cb_boundary_mass(void* stream, int dim, int64_t nb, const double* coords, co
 int cb_boundary_curvature_derivative(void* stream, int dim, int64_t nf, int64_t nrows, const double* coords,
                                      const int32_t* facets, const double* kappa, const int64_t* v2f_ptr,
                                      const int32_t* v2f_idx, double* facet_vec, double* out);
+/* Right-hand side of one sweep of the eikonal iteration, out[v] = int (grad u / |grad u|) . grad phi_v dx for the
+ * owned vertices v < nrows, 0 where bc_flag (uint8, nullable) is set  (compute_boundary_distance_eikonal,
+ * cashocs/geometry/boundary_distance.py:262); v2c_* the vertex -> cell adjacency. */
+int cb_eikonal_rhs(void* stream, int dim, int64_t nrows, const int64_t* v2c_ptr, const int32_t* v2c_idx,
+                   const int32_t* cells, const double* coords, const double* u, const uint8_t* bc_flag,
+                   double* out);
+/* int (|grad u| - 1)^2 dx over the nc (owned) cells, the stopping criterion of the same iteration
+ * (boundary_distance.py:264-279); result_dev device double. */
+int cb_eikonal_residual(void* stream, int dim, int64_t nc, const double* coords, const int32_t* cells,
+                        const double* u, double* result_dev, double* scratch, int64_t scratch_len);
+/* mu[i] = the reference's mu_expression at dist[i]: mu_min below dist_min, mu_max above dist_max, the linear
+ * (smooth = 0) or cubic (smooth = 1) blend in between (Stiffness._setup_mu_computation,
+ * cashocs/_forms/shape_form_handler.py:141-186). */
+int cb_distance_mu(void* stream, int64_t n, const double* dist, double dist_min, double dist_max,
+                   double mu_min, double mu_max, int smooth, double* mu);
 /* Per-vertex collision counts (compute_collisions, cashocs/geometry/mesh_testing.py:201-241)
  * with a uniform-grid broad phase built on the device; mismatch_dev (device int64) receives the
  * number of vertices whose count differs from `valence`. */

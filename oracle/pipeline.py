@@ -70,6 +70,14 @@ class ShapeConfig:
     mu_def: float = 0.35714285714285715
     mu_fix: float = 0.35714285714285715
     use_sqrt_mu: bool = False
+    # distance-based mu (shape_form_handler.py:141-186,216-235; geometry/boundary_distance.py:191-282)
+    use_distance_mu: bool = False
+    dist_min: float = 1.0
+    dist_max: float = 1.0
+    mu_min: float = 1.0
+    mu_max: float = 1.0
+    boundaries_dist: tuple = ()
+    smooth_mu: bool = False
     inhomogeneous: bool = False          # scale the form by 1 / (|K| / max|K|)^exponent (shape_form_handler.py:628-646)
     inhomogeneous_exponent: float = 1.0
     update_inhomogeneous: bool = False
@@ -415,6 +423,10 @@ class PoissonShapeProblem:
     # -- Lame mu (a5)
     def compute_mu(self):
         c = self.cfg
+        if c.use_distance_mu:
+            self.distance = boundary_distance_eikonal(self.mesh, self.coords, self.cells, c.boundaries_dist, its=self.its)
+            self.mu = distance_mu(self.distance, c.dist_min, c.dist_max, c.mu_min, c.mu_max, c.smooth_mu)
+            return self.mu
         if abs(c.mu_def - c.mu_fix) / c.mu_fix > 1e-2:
             _, vol, G = self._geom()
             Ke = fem.stiffness_elements(vol, G)
@@ -902,6 +914,62 @@ def ncg(prob: PoissonShapeProblem, method="DY", rtol=1e-2, atol=0.0, max_iter=50
         if step is None:
             return False, hist
     return False, hist
+
+
+def boundary_distance_eikonal(mesh, coords, cells, boundary_idcs=(), tol=1e-1, max_iter=10, ksp=None, its=None):
+    """``compute_boundary_distance_eikonal`` (``cashocs/geometry/boundary_distance.py:191-282``): ``-Laplace u = 1``,
+    then sweeps ``int grad u . grad v = int grad u_prev / |grad u_prev| . grad v`` with ``u = 0`` on the boundaries
+    ``boundary_idcs`` (all boundary vertices if empty) until ``sqrt(int (|grad u| - 1)^2)`` fell by ``tol``."""
+    d, nv = coords.shape[1], coords.shape[0]
+    if len(boundary_idcs) > 0:
+        bc = mesh.boundary_vertices(tuple(boundary_idcs))
+    else:
+        sub = np.concatenate([np.delete(cells, k, axis=1) for k in range(d + 1)], axis=0)
+        uniq, counts = np.unique(np.sort(sub, axis=1), axis=0, return_counts=True)
+        bc = np.unique(uniq[counts == 1])
+    _, vol, G = fem.cell_geometry(coords, cells)
+    Ke = fem.stiffness_elements(vol, G)
+    ksp = ksp or DEFAULT_KSP
+
+    def solve(be):
+        A, b = fem.assemble_system(Ke, be, cells, nv, bc, 0.0)
+        u, reason, n_its, _ = krylov.solve(A, b, ksp)
+        PoissonShapeProblem._check(reason)
+        if its is not None:
+            its["distance"] = its.get("distance", 0) + n_its
+        return u
+
+    def grad(u):
+        return np.einsum("ca,cai->ci", u[cells], G)
+
+    def residual(u):
+        return np.sqrt(np.sum(vol * (np.linalg.norm(grad(u), axis=1) - 1.0) ** 2))
+
+    u = solve(fem.load_elements_p1(vol, cells, np.ones(nv), d))
+    res_0 = residual(u)
+    for _ in range(max_iter):
+        gu = grad(u)
+        # cells with all vertices on the boundary have grad u = 0: their 0 / 0 only reaches boundary rows, which the
+        # Dirichlet elimination overwrites (as in the reference)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            direction = gu / np.linalg.norm(gu, axis=1)[:, None]
+        u = solve(vol[:, None] * np.einsum("ci,cai->ca", direction, G))
+        if residual(u) <= res_0 * tol:
+            break
+    return u
+
+
+def distance_mu(dist, dist_min, dist_max, mu_min, mu_max, smooth=False):
+    """The ``mu_expression`` of ``Stiffness._setup_mu_computation`` (``shape_form_handler.py:150-186``) interpolated
+    to CG1, i.e. evaluated at the vertices."""
+    w, dm = dist_max - dist_min, mu_max - mu_min
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if not smooth:
+            mid = mu_min + (dist - dist_min) / w * dm
+        else:
+            mid = (mu_min + dm / w * (dist - dist_min) - dm / w**2 * (dist - dist_min) * (dist - dist_max)
+                   - 2.0 * dm / w**3 * (dist - dist_min) * (dist - dist_max) ** 2)
+    return np.where(dist <= dist_min, mu_min, np.where(dist <= dist_max, mid, mu_max))
 
 
 def truncated_newton(prob, inner="cg", rtol=1e-2, atol=0.0, max_iter=50, inner_rtol=1e-7, inner_atol=0.0, inner_max_it=20):

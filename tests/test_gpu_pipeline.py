@@ -86,6 +86,46 @@ def test_shape_gradient_matches_oracle_cube_with_mu_problem(n):
     assert np.all(g1[fix] == 0.0)
 
 
+@pytest.mark.parametrize("dim,n,smooth", [(2, 64, False), (2, 24, True), (3, 10, False)])
+def test_distance_mu_like_the_reference(dim, n, smooth):
+    """tests/test_shape_optimization.py:707-771 (``use_distance_mu``): the eikonal distance (csrc/distance.cu +
+    the state path's assembly / AMG-PCG) and the distance-based Lame parameter against the oracle; in 2-D at n = 64
+    the reference's ten point values (mu = 1 within 0.09 of a side, mu = 10 from 0.26 on) hold to 1e-10; the shape
+    gradient computed with that mu agrees with the oracle's."""
+    dm = cb.regular_mesh(n) if dim == 2 else cb.regular_mesh(n, 1.0, 1.0, 1.0)
+    om = meshes.regular_mesh(n) if dim == 2 else meshes.regular_mesh(n, 1.0, 1.0, 1.0)
+    markers = (1, 2, 3, 4) if dim == 2 else (1, 2, 3, 4, 5, 6)
+    cfg = sop_config(shape_bdry_def=str(list(markers)), use_distance_mu=True, dist_min=0.1, dist_max=0.25, mu_min=1.0,
+                     mu_max=10.0, boundaries_dist="[]", smooth_mu=smooth)
+    sop = make_sop(dm, cfg, bc_markers=markers)
+    ocfg = pipeline.ShapeConfig(shape_bdry_def=markers, use_distance_mu=True, dist_min=0.1, dist_max=0.25, mu_min=1.0,
+                                mu_max=10.0, smooth_mu=smooth)
+    prob = pipeline.PoissonShapeProblem(om, bc_markers=markers, config=ocfg)
+    g0 = prob.compute_shape_gradient()
+    g1 = sop.compute_shape_gradient()[0].vector.cpu().numpy()
+    st = sop.form_handler.stiffness
+    assert rel(st.distance.cpu().numpy(), prob.distance) < 1e-8
+    mu = sop.form_handler.mu_lame.vector.cpu().numpy()
+    assert rel(mu, prob.mu) < 1e-7 and mu.min() == 1.0 and mu.max() == 10.0
+    assert 1 <= st.eikonal.sweeps <= 10 and st.eikonal.residuals[-1] < st.eikonal.residuals[0]
+    assert rel(g1, g0) < 1e-7
+    if dim == 2 and n == 64:
+        from test_oracle import _p1_eval
+
+        want = {(0.5, 0.5): 10.0, (0.05, 0.5): 1.0, (0.09, 0.5): 1.0, (0.91, 0.5): 1.0, (0.5, 0.09): 1.0, (0.5, 0.91): 1.0,
+                (0.5, 0.26): 10.0, (0.5, 0.74): 10.0, (0.26, 0.5): 10.0, (0.74, 0.5): 10.0}
+        for pt, val in want.items():
+            assert abs(_p1_eval(om.coords, om.cells, mu, pt) - val) / val < 1e-10, pt
+    # only one side counts (boundaries_dist = [1]): the distance grows with x
+    from cashocs_b200.geometry import boundary_distance
+
+    d1 = boundary_distance.compute_boundary_distance(dm, boundary_idcs=[1]).cpu().numpy()
+    d0 = pipeline.boundary_distance_eikonal(om, om.coords, om.cells, (1,))
+    assert rel(d1, d0) < 1e-8 and abs(d1[np.argmax(om.coords[:, 0])] - 1.0) < 0.05
+    with pytest.raises(cb.InputError):
+        boundary_distance.compute_boundary_distance(dm, method="poisson")
+
+
 @pytest.mark.parametrize("n", [16, 32])
 @pytest.mark.parametrize("variant", ["homogeneous", "mu_poisson"])
 def test_parity_at_the_benchmarked_solver_settings(n, variant):

@@ -512,3 +512,39 @@ def test_curvature_regularization_known_answer():
         res.append(abs(prob.curvature_objective() - J0 - e * (dJ @ h)))
     prob.coords[:] = x0
     assert np.log(res[-1] / res[-2]) / np.log(0.5) > 1.9
+
+
+def _p1_eval(coords, cells, values, point):
+    """Value of a P1 function at a point (any cell containing it)."""
+    x = np.asarray(point, dtype=float)
+    T = coords[cells]
+    M = np.transpose(T[:, 1:] - T[:, :1], (0, 2, 1))
+    lam = np.linalg.solve(M, np.broadcast_to(x - T[:, 0], (len(cells), len(x)))[..., None])[..., 0]
+    bary = np.concatenate([1.0 - lam.sum(axis=1, keepdims=True), lam], axis=1)
+    c = int(np.argmax(bary.min(axis=1)))
+    assert bary[c].min() > -1e-12
+    return float(bary[c] @ values[cells[c]])
+
+
+def test_distance_mu_known_answers():
+    """tests/test_shape_optimization.py:707-771 (``use_distance_mu``, eikonal distance): on ``regular_mesh(64)`` with
+    dist_min 0.1, dist_max 0.25, mu_min 1, mu_max 10 the Lame parameter is exactly 10 at the centre and at distance
+    0.26 from the sides, exactly 1 at distance 0.05 and 0.09 -- the reference's ten point evaluations to 1e-10."""
+    om = meshes.regular_mesh(64)
+    cfg = pipeline.ShapeConfig(use_distance_mu=True, dist_min=0.1, dist_max=0.25, mu_min=1.0, mu_max=10.0)
+    prob = pipeline.PoissonShapeProblem(om, config=cfg)
+    want = {(0.5, 0.5): 10.0, (0.05, 0.5): 1.0, (0.09, 0.5): 1.0, (0.91, 0.5): 1.0, (0.5, 0.09): 1.0, (0.5, 0.91): 1.0,
+            (0.5, 0.26): 10.0, (0.5, 0.74): 10.0, (0.26, 0.5): 10.0, (0.74, 0.5): 10.0}
+    for pt, mu in want.items():
+        assert abs(_p1_eval(om.coords, om.cells, prob.mu, pt) - mu) / mu < 1e-10, pt
+    # a distance: zero on the boundary, close to the true distance near the walls, 1-Lipschitz-ish in the bulk
+    d = prob.distance
+    assert np.all(d[om.boundary_vertices((1, 2, 3, 4))] == 0.0) and d.min() >= 0.0
+    near = np.minimum.reduce([om.coords[:, 0], 1 - om.coords[:, 0], om.coords[:, 1], 1 - om.coords[:, 1]])
+    sel = near < 0.1
+    assert np.max(np.abs(d[sel] - near[sel])) < 0.01
+    # the blend itself (both variants) at hand-computed points
+    dist = np.array([0.0, 0.1, 0.175, 0.25, 0.3])
+    assert np.allclose(pipeline.distance_mu(dist, 0.1, 0.25, 1.0, 10.0), [1.0, 1.0, 5.5, 10.0, 10.0])
+    sm = pipeline.distance_mu(dist, 0.1, 0.25, 1.0, 10.0, smooth=True)
+    assert np.allclose(sm[[0, 1, 3, 4]], [1.0, 1.0, 10.0, 10.0]) and abs(sm[2] - 5.5) < 1e-12  # odd about the midpoint
