@@ -121,8 +121,20 @@ class ShapeFormHandler:
         self.shape_bdry_fix_z = g("shape_bdry_fix_z")
         self.fixed_dimensions = [int(i) for i in config.getlist("ShapeGradient", "fixed_dimensions")]
         self.use_fixed_dimensions = len(self.fixed_dimensions) > 0
-        if config.getboolean("ShapeGradient", "use_p_laplacian"):
-            raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "use_p_laplacian", "outside the hot path (SURVEY.md 8a)")
+        # p-Laplace projection (shape_gradient_problem.py:93-115): incompatible with fixed dimensions, where the
+        # reference falls back to the linear-elasticity projection with a warning
+        self.use_p_laplacian = config.getboolean("ShapeGradient", "use_p_laplacian")
+        if self.use_p_laplacian and self.use_fixed_dimensions:
+            from cashocs_b200 import log
+
+            log.warning("Incompatible config settings: use_p_laplacian and fixed_dimensions are incompatible. "
+                        "Falling back to use_p_laplacian=False.")
+            self.use_p_laplacian = False
+        if self.use_p_laplacian and mesh.dist is not None:
+            raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "use_p_laplacian",
+                                         "the p-Laplace projection runs on unpartitioned meshes")
+        self.p_laplacian_power = config.getint("ShapeGradient", "p_laplacian_power")
+        self.p_laplacian_stabilization = config.getfloat("ShapeGradient", "p_laplacian_stabilization")
         self.reextend_from_boundary = config.getboolean("ShapeGradient", "reextend_from_boundary")
         if self.reextend_from_boundary and config.get("ShapeGradient", "reextension_mode") != "surface":
             raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "reextension_mode",
@@ -207,7 +219,23 @@ class ShapeFormHandler:
             )
 
     def scalar_product(self, a: torch.Tensor, b: torch.Tensor) -> float:
-        """``b^T A a`` (``shape_form_handler.py:748-780``)."""
+        """``b^T A a`` (``shape_form_handler.py:748-780``); with the p-Laplace projection the p-Laplace form with
+        the gradient replaced by ``a`` and the test function by ``b`` (``:761-770,785-815``) -- nonlinear in ``a``."""
+        if self.use_p_laplacian:
+            from cashocs_b200 import _lib
+
+            mesh = self.mesh
+            out = torch.empty(1, dtype=torch.float64, device=mesh.device)
+            scratch = mesh.reduce_scratch()
+            _lib.require_cuda(a, b)
+            _lib.check(
+                _lib.load().cb_plaplace_product(
+                    _lib.stream_ptr(), mesh.dim, mesh.n_owned_cells, _lib.ptr(mesh.coords), _lib.ptr(mesh.cells),
+                    _lib.ptr(a), _lib.ptr(b), _lib.ptr(self.mu_lame.vector), self.p_laplacian_power,
+                    self.p_laplacian_stabilization, self.damping_factor, _lib.ptr(out), _lib.ptr(scratch), scratch.numel()),
+                "cb_plaplace_product",
+            )
+            return float(out.item())
         return self.scalar_product_matrix.scalar_product(a, b)
 
     def assemble_shape_derivative(self) -> torch.Tensor:

@@ -246,6 +246,9 @@ SIGNATURES = {
     "cb_amg_rbm_prolong": (I32, [P, I64, P, P, P, P, P]),
     "cb_boundary_measure": (I32, [P, I32, I64, P, P, P, P, I64]),
     "cb_boundary_measure_gradient": (I32, [P, I32, I64, I64, P, P, P, P, P, P]),
+    "cb_plaplace_residual": (I32, [P, I32, I64, P, P, P, P, P, P, I32, DBL, DBL, P, P, P]),
+    "cb_plaplace_jacobian": (I32, [P, I32, I64, P, P, P, P, P, P, I32, DBL, DBL, P, P, P, P]),
+    "cb_plaplace_product": (I32, [P, I32, I64, P, P, P, P, P, I32, DBL, DBL, P, P, I64]),
     "cb_eikonal_rhs": (I32, [P, I32, I64, P, P, P, P, P, P, P]),
     "cb_eikonal_residual": (I32, [P, I32, I64, P, P, P, P, P, I64]),
     "cb_distance_mu": (I32, [P, I64, P, DBL, DBL, DBL, DBL, I32, P]),

@@ -12,7 +12,7 @@ INCLUDE = os.path.join(HERE, "..", "include")
 LIB = os.path.join(HERE, "libcashocs_b200.so")
 
 SOURCES = ["api.cu", "pattern.cu", "assemble.cu", "spmv.cu", "krylov.cu", "amg.cu", "meshops.cu", "dist.cu", "p2.cu",
-           "boundary.cu", "amg_rbm.cu", "rbm.cu", "distance.cu"]
+           "boundary.cu", "amg_rbm.cu", "rbm.cu", "distance.cu", "plaplace.cu"]
 # meshops.cu / boundary.cu / distance.cu feed accept/reject thresholds: no FMA contraction (see the file headers)
 EXTRA = {"meshops.cu": ["-fmad=false"], "boundary.cu": ["-fmad=false"], "distance.cu": ["-fmad=false"]}
 COMMON = [

@@ -345,8 +345,6 @@ class Config(configparser.ConfigParser):
             except ValueError:
                 return None
 
-        if boolean("ShapeGradient", "use_p_laplacian"):
-            flag("ShapeGradient", "use_p_laplacian", "it must be False")
         if boolean("ShapeGradient", "use_distance_mu") and self.get("ShapeGradient", "distance_method") != "eikonal":
             flag("ShapeGradient", "distance_method", "the device path computes boundary distances with eikonal")
         if self.get("ShapeGradient", "shape_volume_fix").replace(" ", "") != "[]":

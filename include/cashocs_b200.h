@@ -534,6 +534,27 @@ int cb_eikonal_residual(void* stream, int dim, int64_t nc, const double* coords,
  * cashocs/_forms/shape_form_handler.py:141-186). */
 int cb_distance_mu(void* stream, int64_t n, const double* dist, double dist_min, double dist_max,
                    double mu_min, double mu_max, int smooth, double* mu);
+/* p-Laplace projection of the shape derivative (_PLaplaceProjector,
+ * cashocs/_pde_problems/shape_gradient_problem.py:329-427).  Residual of
+ * int mu (eps + |grad U|^(p-2)) grad U : grad W + delta U . W dx - shift[W] for the vector-P1 field U [nv*dim] and
+ * the owned vertices (rows) < nrows; mu [nv] the P1 Lame parameter, shift [nrows*dim] the assembled shape derivative
+ * (nullable), bc_flag (uint8 per dof, nullable): Dirichlet rows are 0.  v2c_*: vertex -> cell adjacency. */
+int cb_plaplace_residual(void* stream, int dim, int64_t nrows, const int64_t* v2c_ptr, const int32_t* v2c_idx,
+                         const int32_t* cells, const double* coords, const double* U, const double* mu, int p,
+                         double eps, double delta, const double* shift, const uint8_t* bc_flag, double* out);
+/* Jacobian of the same form at U (fenics.derivative of the nonlinear form, nonlinear_solvers/snes.py:121-131) as
+ * dim x dim blocks on the P1 pattern rowptr / col, symmetric Dirichlet elimination like dolfin's SystemAssembler;
+ * val [nnz*dim*dim]. */
+int cb_plaplace_jacobian(void* stream, int dim, int64_t nrows, const int64_t* v2c_ptr, const int32_t* v2c_idx,
+                         const int32_t* cells, const double* coords, const double* U, const double* mu, int p,
+                         double eps, double delta, const uint8_t* bc_flag, const int64_t* rowptr, const int32_t* col,
+                         double* val);
+/* int mu (eps + |grad a|^(p-2)) grad a : grad b + delta a . b dx over the nc (owned) cells: the scalar product of
+ * deformations while the p-Laplace projection is on (ShapeFormHandler.scalar_product,
+ * cashocs/_forms/shape_form_handler.py:761-770,785-815); a, b [nv*dim]; result_dev device double. */
+int cb_plaplace_product(void* stream, int dim, int64_t nc, const double* coords, const int32_t* cells,
+                        const double* a, const double* b, const double* mu, int p, double eps, double delta,
+                        double* result_dev, double* scratch, int64_t scratch_len);
 /* Per-vertex collision counts (compute_collisions, cashocs/geometry/mesh_testing.py:201-241)
  * with a uniform-grid broad phase built on the device; mismatch_dev (device int64) receives the
  * number of vertices whose count differs from `valence`. */

@@ -105,6 +105,10 @@ class ShapeConfig:
     target_surface: float = 0.0
     use_initial_surface: bool = False
     line_search: str = "armijo"          # [LineSearch] method: armijo | basic | polynomial
+    # p-Laplace projection of the shape derivative (shape_gradient_problem.py:329-427)
+    use_p_laplacian: bool = False
+    p_laplacian_power: int = 2
+    p_laplacian_stabilization: float = 0.0
     # re-extension of the gradient deformation from its boundary values (shape_gradient_problem.py:175-223)
     reextend_from_boundary: bool = False
     reextension_mode: str = "surface"    # "normal" (the facet-normal projection, :225-299) is not restated
@@ -493,7 +497,25 @@ class PoissonShapeProblem:
         x[dofs] = g[dofs]  # apply_reextension_bcs (shape_form_handler.py:843-862)
         return x
 
+    def p_laplace_product(self, a, b):
+        """``ShapeFormHandler.scalar_product`` with ``use_p_laplacian`` (``shape_form_handler.py:761-770,785-815``):
+        the p-Laplace form with the gradient replaced by ``a`` and the test function by ``b`` -- nonlinear in ``a``."""
+        d, c = self.d, self.cfg
+        p = int(c.p_laplacian_power)
+        _, vol, G = self._geom()
+        ae, be = a.reshape(-1, d)[self.cells], b.reshape(-1, d)[self.cells]
+        Ha = np.einsum("cai,caj->cij", ae, G)
+        Hb = np.einsum("cai,caj->cij", be, G)
+        s = np.einsum("cij,cij->c", Ha, Ha)
+        kappa = np.ones_like(s) if p == 2 else s ** (0.5 * (p - 2))
+        w = vol * self.mu[self.cells].mean(axis=1) * (c.p_laplacian_stabilization + kappa)
+        M = fem.mass_elements(vol, d)
+        return float(np.sum(w * np.einsum("cij,cij->c", Ha, Hb))
+                     + c.damping_factor * np.einsum("cab,cai,cbi->", M, ae, be))
+
     def scalar_product(self, a, b):
+        if self.cfg.use_p_laplacian and not self.cfg.fixed_dimensions:
+            return self.p_laplace_product(a, b)
         return float((self.A_elas @ a) @ b)
 
     # -- shape derivative (a7)
@@ -563,15 +585,78 @@ class PoissonShapeProblem:
         self.solve_state()
         self.solve_adjoint()
         self.dJ = self.shape_derivative_vector()
-        g, reason, its, _ = krylov.solve(self.A_elas, self.dJ, self.gradient_ksp, block_size=self.d, coords=self.coords)
-        self._check(reason)
-        self.its["gradient"] = its
-        g[self.shape_bc_dofs] = 0.0  # apply_shape_bcs (shape_form_handler.py:825-841)
+        if self.cfg.use_p_laplacian and not self.cfg.fixed_dimensions:  # shape_gradient_problem.py:133-139
+            g = self.p_laplace_projection(self.dJ)
+        else:
+            g, reason, its, _ = krylov.solve(self.A_elas, self.dJ, self.gradient_ksp, block_size=self.d, coords=self.coords)
+            self._check(reason)
+            self.its["gradient"] = its
+            g[self.shape_bc_dofs] = 0.0  # apply_shape_bcs (shape_form_handler.py:825-841)
         if self.cfg.reextend_from_boundary:
             g = self.reextend_gradient_from_boundaries(g)
         self.gradient = g
         self.gradient_norm_squared = self.scalar_product(g, g)
         return g
+
+    # -- p-Laplace projector (shape_gradient_problem.py:329-427)
+    def p_laplace_forms(self, U, p):
+        """Element residual [Nc, (d+1) d] and Jacobian [Nc, (d+1) d, (d+1) d] of
+        ``mu (eps + (grad U : grad U)^((p-2)/2)) grad U : grad W + delta U . W`` (``:370-386``; the Jacobian is
+        ``fenics.derivative`` of it, ``nonlinear_solvers/snes.py:121``)."""
+        d, n = self.d, self.d + 1
+        c = self.cfg
+        _, vol, G = self._geom()
+        Ue = U.reshape(-1, d)[self.cells]                               # [Nc, d+1, d]
+        H = np.einsum("cai,caj->cij", Ue, G)                            # d_j U_i
+        s = np.einsum("cij,cij->c", H, H)
+        w0 = vol * self.mu[self.cells].mean(axis=1)
+        kappa = np.ones_like(s) if p == 2 else s ** (0.5 * (p - 2))
+        w1 = w0 * (c.p_laplacian_stabilization + kappa)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            w2 = np.where(s > 0.0, w0 * (p - 2) * s ** (0.5 * (p - 4)), 0.0) if p != 2 else np.zeros_like(s)
+        HG = np.einsum("cij,caj->cai", H, G)                            # (grad U G_a)_i
+        M = fem.mass_elements(vol, d)
+        eye = np.eye(d)
+        Fe = w1[:, None, None] * HG + c.damping_factor * np.einsum("cab,cbi->cai", M, Ue)
+        Je = np.einsum("c,cab,ij->caibj", w1, np.einsum("cak,cbk->cab", G, G), eye, optimize=True)
+        Je += np.einsum("c,cai,cbj->caibj", w2, HG, HG, optimize=True)
+        Je += c.damping_factor * np.einsum("cab,ij->caibj", M, eye)
+        return Fe.reshape(-1, n * d), Je.reshape(-1, n * d, n * d)
+
+    def p_laplace_projection(self, dJ, snes_rtol=1e-8, snes_atol=1e-50, snes_stol=1e-8, snes_max_it=50):
+        """``_PLaplaceProjector.solve`` (``:396-427``): for p = 2 .. p_target Newton's method with full steps (SNES
+        ``newtonls`` + ``basic`` line search, PETSc's default tolerances) on ``F_p(U) = dJ``, each p starting from the
+        previous solution; homogeneous shape boundary conditions."""
+        nd = self.d * self.nv
+        U = np.zeros(nd)
+        bc = self.shape_bc_dofs
+        self.its["p_laplace_newton"] = []
+        for p in range(2, int(self.cfg.p_laplacian_power) + 1):
+            def residual(U):
+                Fe, Je = self.p_laplace_forms(U, p)
+                F = fem.assemble_vector(Fe, self.vcell_dofs, nd) - dJ
+                F[bc] = 0.0
+                return F, Je
+
+            F, Je = residual(U)
+            f0 = fnorm = np.linalg.norm(F)
+            n_it = 0
+            while fnorm >= snes_atol and n_it < snes_max_it:
+                A, _ = fem.assemble_system(Je, None, self.vcell_dofs, nd, bc, 0.0)
+                y, reason, _, _ = krylov.solve(A, F, self.gradient_ksp, block_size=self.d, coords=self.coords)
+                self._check(reason)
+                U = U - y
+                U[bc] = 0.0
+                F, Je = residual(U)
+                fnorm = np.linalg.norm(F)
+                n_it += 1
+                if fnorm <= snes_rtol * f0 or np.linalg.norm(y) < snes_stol * np.linalg.norm(U):
+                    break
+            else:
+                if fnorm >= snes_atol:
+                    raise RuntimeError("p-Laplace Newton iteration did not converge")
+            self.its["p_laplace_newton"].append(n_it)
+        return U
 
     # -- mesh handling (a12, a13, a15, a16)
     def move_mesh(self, deformation):

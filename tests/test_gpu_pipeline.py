@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import cashocs_b200 as cb
-from oracle import meshes, pipeline
+from oracle import fem, meshes, pipeline
 
 pytestmark = pytest.mark.gpu
 
@@ -124,6 +124,114 @@ def test_distance_mu_like_the_reference(dim, n, smooth):
     assert rel(d1, d0) < 1e-8 and abs(d1[np.argmax(om.coords[:, 0])] - 1.0) < 0.05
     with pytest.raises(cb.InputError):
         boundary_distance.compute_boundary_distance(dm, method="poisson")
+
+
+def _p_laplace_cfgs(power, **extra):
+    keys = dict(mu_def=1.0, mu_fix=1.0, damping_factor=1.0, use_p_laplacian=True, p_laplacian_power=power,
+                p_laplacian_stabilization=0.0)
+    keys.update(extra)
+    cfg = sop_config(**keys)
+    ocfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, mu_def=1.0, mu_fix=1.0, damping_factor=1.0,
+                                use_p_laplacian=True, p_laplacian_power=power,
+                                **{k: (tuple(eval(v)) if isinstance(v, str) else v) for k, v in extra.items()})
+    return cfg, ocfg
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_p_laplace_kernels_match_oracle(dim, rng):
+    """csrc/plaplace.cu: residual, Jacobian (block CSR, symmetric Dirichlet elimination) and the nonlinear "scalar
+    product" of the p-Laplace form (shape_gradient_problem.py:370-386, shape_form_handler.py:761-815) at a random
+    deformation, p = 2, 3 and 6, against the oracle's element tensors."""
+    import scipy.sparse as sps
+
+    from cashocs_b200 import _lib
+    from cashocs_b200._pde_problems import shape_gradient_problem as sgp
+
+    if dim == 2:
+        dm, om = circle()
+        extra, markers = {}, (1,)
+    else:
+        dm, om = cb.regular_mesh(4, 1.0, 1.0, 1.0), meshes.regular_mesh(4, 1.0, 1.0, 1.0)
+        extra, markers = dict(shape_bdry_def="[2]", shape_bdry_fix="[1, 3]", shape_bdry_fix_y="[5]"), (1, 2, 3, 4, 5, 6)
+    for power in (2, 3, 6):
+        cfg, ocfg = _p_laplace_cfgs(power, **extra)
+        sop = make_sop(dm, cfg, bc_markers=markers, ksp=None)
+        prob = pipeline.PoissonShapeProblem(om, bc_markers=markers, config=ocfg)
+        fh, gp = sop.form_handler, sop.gradient_problem
+        # a non-constant mu exercises the cell average
+        mu_h = 1.0 + rng.rand(om.num_vertices)
+        fh.mu_lame.vector.copy_(torch.from_numpy(mu_h))
+        prob.mu = mu_h
+        nd = dim * om.num_vertices
+        U = 0.1 * rng.rand(nd)
+        U[prob.shape_bc_dofs] = 0.0
+        shift = rng.rand(nd)
+        gp.gradient.vector.copy_(torch.from_numpy(U))
+        proj = sgp._PLaplaceProjector(gp, None)
+        fnorm = proj._residual(power, torch.from_numpy(shift).to(dm.coords.device))
+        Fe, Je = prob.p_laplace_forms(U, power)
+        F0 = fem.assemble_vector(Fe, prob.vcell_dofs, nd) - shift
+        F0[prob.shape_bc_dofs] = 0.0
+        assert np.max(np.abs(proj.residual.cpu().numpy() - F0)) <= 1e-12 * np.max(np.abs(F0))
+        assert abs(fnorm - np.linalg.norm(F0)) <= 1e-12 * np.linalg.norm(F0)
+        proj._jacobian(power)
+        A0, _ = fem.assemble_system(Je, None, prob.vcell_dofs, nd, prob.shape_bc_dofs, 0.0)
+        x = rng.rand(nd)
+        y = proj.A.mult(torch.from_numpy(x).to(dm.coords.device)).cpu().numpy()
+        assert np.max(np.abs(y - A0 @ x)) <= 1e-12 * np.max(np.abs(A0 @ x))
+        b = rng.rand(nd)
+        sp1 = fh.scalar_product(gp.gradient.vector, torch.from_numpy(b).to(dm.coords.device))
+        assert abs(sp1 - prob.p_laplace_product(U, b)) <= 1e-12 * abs(prob.p_laplace_product(U, b))
+        # the Jacobian is the derivative of the residual: finite-difference check
+        if power > 2:
+            h = 1e-6 * rng.rand(nd)
+            h[prob.shape_bc_dofs] = 0.0
+            Fe2, _ = prob.p_laplace_forms(U + h, power)
+            dF = fem.assemble_vector(Fe2 - Fe, prob.vcell_dofs, nd)
+            dF[prob.shape_bc_dofs] = 0.0
+            lin = A0 @ h
+            lin[prob.shape_bc_dofs] = 0.0
+            assert np.max(np.abs(dF - lin)) <= 1e-4 * np.max(np.abs(lin))
+
+
+def test_p_laplacian_like_the_reference(rng):
+    """tests/test_p_laplacian.py:82-160 (``use_p_laplacian``): p = 2 is the vector Laplace + mass Riesz problem and
+    gradient descent meets the reference's budget of 22 iterations with the oracle's count; p = 10: the gradient
+    deformation of the Newton continuation p = 2 .. 10 equals the oracle's, the Taylor test -- with the p-Laplace form as
+    "scalar product" -- has rate > 1.9, gradient descent reaches rtol 1e-1 within the budget of 6 with the oracle's
+    iteration count; an iterative inner solver (Eisenstat-Walker forcing) lands on the same deformation."""
+    dm, om = circle()
+    cfg, ocfg = _p_laplace_cfgs(2)
+    sop = make_sop(dm, cfg, ksp=None)
+    prob = pipeline.PoissonShapeProblem(om, config=ocfg)
+    g1 = sop.compute_shape_gradient()[0].vector.cpu().numpy()
+    g0 = prob.compute_shape_gradient()
+    assert rel(g1, g0) < 1e-8 and sop.gradient_problem.p_laplace_projector.newton_iterations == [1]
+    sop.solve(algorithm="gd", rtol=1e-2, atol=0.0, max_iter=22)
+    ok, hist = pipeline.gradient_descent(prob, rtol=1e-2, max_iter=22)
+    assert ok and sop.solver.converged and sop.solver.iteration == len(hist) - 1 <= 22
+    assert abs(sop.solver.objective_value - hist[-1][1]) <= 1e-8 * abs(hist[-1][1])
+
+    dm, om = circle()
+    cfg, ocfg = _p_laplace_cfgs(10)
+    sop = make_sop(dm, cfg, ksp=None)
+    prob = pipeline.PoissonShapeProblem(om, config=ocfg)
+    g1 = sop.compute_shape_gradient()[0].vector.cpu().numpy()
+    g0 = prob.compute_shape_gradient()
+    proj = sop.gradient_problem.p_laplace_projector
+    assert rel(g1, g0) < 1e-7 and proj.newton_iterations == prob.its["p_laplace_newton"]
+    assert abs(sop.gradient_problem.gradient_norm_squared - prob.gradient_norm_squared) <= 1e-7 * prob.gradient_norm_squared
+    assert sop.gradient_test(rng=rng) > 1.9
+    sop.solve(algorithm="gd", rtol=1e-1, atol=0.0, max_iter=6)
+    ok, hist = pipeline.gradient_descent(prob, rtol=1e-1, max_iter=6)
+    assert ok and sop.solver.converged and sop.solver.iteration == len(hist) - 1 <= 6
+    assert sop.solver.relative_norm <= 1e-1
+    assert abs(sop.solver.objective_value - hist[-1][1]) <= 1e-6 * abs(hist[-1][1])
+
+    dm, om = circle()
+    sop_it = make_sop(dm, _p_laplace_cfgs(10)[0])  # cg + jacobi: inexact Newton with Eisenstat-Walker forcing
+    g2 = sop_it.compute_shape_gradient()[0].vector.cpu().numpy()
+    assert rel(g2, g0) < 1e-5
 
 
 @pytest.mark.parametrize("n", [16, 32])

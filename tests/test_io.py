@@ -167,9 +167,9 @@ def test_config_validation_matches_the_reference_case_by_case():
 
 
 def test_unsupported_subsystems_are_refused_loudly():
-    for sec, key, val in (("ShapeGradient", "use_p_laplacian", "True"), ("Regularization", "use_relative_scaling", "True"),
+    for sec, key, val in (("Regularization", "use_relative_scaling", "True"),
                           ("StateSystem", "backend", "petsc"), ("Mesh", "remesh", "True"),
-                          ("Regularization", "use_relative_scaling", "True")):
+                          ("MeshQuality", "remesh_iter", "3")):
         cfg = cb.Config()
         cfg.set(sec, key, val)
         with pytest.raises(cb.ConfigError, match="outside the B200 hot path"):

@@ -548,3 +548,24 @@ def test_distance_mu_known_answers():
     assert np.allclose(pipeline.distance_mu(dist, 0.1, 0.25, 1.0, 10.0), [1.0, 1.0, 5.5, 10.0, 10.0])
     sm = pipeline.distance_mu(dist, 0.1, 0.25, 1.0, 10.0, smooth=True)
     assert np.allclose(sm[[0, 1, 3, 4]], [1.0, 1.0, 10.0, 10.0]) and abs(sm[2] - 5.5) < 1e-12  # odd about the midpoint
+
+
+def test_p_laplacian_reference_scenarios():
+    """tests/test_p_laplacian.py:82-160: with ``use_p_laplacian`` (mu = 1, damping 1) gradient descent with p = 2
+    converges to rtol 1e-2 within 22 iterations (oracle: 21), with p = 10 to rtol 1e-1 within 6 (oracle: 5), and the
+    Taylor test -- the p-Laplace form as "scalar product" (shape_form_handler.py:761-770) -- has rate > 1.9."""
+    base = dict(tol_lower=0.01, tol_upper=0.02, mu_def=1.0, mu_fix=1.0, damping_factor=1.0, use_p_laplacian=True)
+    load = lambda: meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))  # noqa: E731
+    prob = pipeline.PoissonShapeProblem(load(), config=pipeline.ShapeConfig(p_laplacian_power=2, **base))
+    g = prob.compute_shape_gradient()
+    assert prob.its["p_laplace_newton"] == [1]  # p = 2 is linear: one Newton step
+    Fe, Je = prob.p_laplace_forms(g, 2)
+    A, _ = fem.assemble_system(Je, None, prob.vcell_dofs, g.size)
+    assert np.linalg.norm(A @ g - prob.dJ) <= 1e-12 * np.linalg.norm(prob.dJ)
+    ok, hist = pipeline.gradient_descent(prob, rtol=1e-2, max_iter=22)
+    assert ok and len(hist) - 1 == 21
+    prob = pipeline.PoissonShapeProblem(load(), config=pipeline.ShapeConfig(p_laplacian_power=10, **base))
+    ok, hist = pipeline.gradient_descent(prob, rtol=1e-1, max_iter=6)
+    assert ok and len(hist) - 1 == 5 and hist[-1][2] <= 1e-1
+    prob = pipeline.PoissonShapeProblem(load(), config=pipeline.ShapeConfig(p_laplacian_power=10, **base))
+    assert pipeline.shape_gradient_test(prob)[0] > 1.9
