@@ -95,6 +95,34 @@ class ShapeRegularization:
                 self.target_surface = self.compute_surface()
         if self.mu_curvature > 0.0:
             self._setup_curvature()
+        if config.getboolean("Regularization", "use_relative_scaling"):
+            self.scale()
+
+    def scale(self) -> None:
+        """``scale`` of the four terms (``:194-211,289-305,461-484,621-643``): with ``use_relative_scaling`` every active
+        term's factor is divided by the term's value on the initial geometry, unless that vanishes."""
+        from cashocs_b200 import log
+
+        def scaled(name: str, mu: float, value: float) -> float:
+            if mu <= 0.0:
+                return mu
+            if abs(value) < 1e-15:
+                log.info(f"The {name} regularization vanishes for the initial iteration. Multiplying this term with "
+                         "the factor you supplied as weight.")
+                return mu
+            return mu / abs(value)
+
+        if self.mu_volume > 0.0:
+            self.mu_volume = scaled("volume", self.mu_volume, 0.5 * (self.compute_volume() - self.target_volume) ** 2)
+        if self.mu_surface > 0.0:
+            self.mu_surface = scaled("surface", self.mu_surface, 0.5 * (self.compute_surface() - self.target_surface) ** 2)
+        if self.mu_barycenter > 0.0:
+            bc = self.compute_barycenter()
+            self.mu_barycenter = scaled("barycenter", self.mu_barycenter,
+                                        0.5 * sum((bc[k] - self.target_barycenter[k]) ** 2 for k in range(3)))
+        if self.mu_curvature > 0.0:
+            mu, self.mu_curvature = self.mu_curvature, 1.0
+            self.mu_curvature = scaled("curvature", mu, self.compute_curvature_objective())
 
     # -- geometric quantities
     def _integral(self, w: torch.Tensor) -> float:

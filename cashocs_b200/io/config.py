@@ -349,8 +349,6 @@ class Config(configparser.ConfigParser):
             flag("ShapeGradient", "distance_method", "the device path computes boundary distances with eikonal")
         if self.get("ShapeGradient", "shape_volume_fix").replace(" ", "") != "[]":
             flag("ShapeGradient", "shape_volume_fix", "it must be empty")
-        if boolean("Regularization", "use_relative_scaling"):
-            flag("Regularization", "use_relative_scaling", "it must be False")
         if boolean("Mesh", "remesh"):
             flag("Mesh", "remesh", "remeshing needs the gmsh executable, it must be False")
         if (number("MeshQuality", "remesh_iter") or 0) > 0:

@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import collections
 import dataclasses
+import types
 
 import numpy as np
 
@@ -102,6 +103,7 @@ class ShapeConfig:
     use_initial_barycenter: bool = False
     factor_surface: float = 0.0          # :224-316
     factor_curvature: float = 0.0        # :512-646 (boundary mass solve for the mean-curvature vector)
+    use_relative_scaling: bool = False   # every active term's factor is divided by its initial value (`scale`)
     target_surface: float = 0.0
     use_initial_surface: bool = False
     line_search: str = "armijo"          # [LineSearch] method: armijo | basic | polynomial
@@ -191,6 +193,9 @@ class PoissonShapeProblem:
         tb = list(self.cfg.target_barycenter) + [0.0] * 3
         self.target_barycenter = self.barycenter() if self.cfg.use_initial_barycenter else np.asarray(tb[:3], dtype=float)
         self.target_surface = self.surface() if self.cfg.use_initial_surface else self.cfg.target_surface
+        self.reg_mu = {k: float(getattr(self.cfg, "factor_" + k)) for k in ("volume", "surface", "barycenter", "curvature")}
+        if self.cfg.use_relative_scaling:
+            self._scale_regularization()
         self.update_scalar_product()
 
     # -- geometric regularisation: volume and barycenter (shape_regularization.py)
@@ -307,7 +312,7 @@ class PoissonShapeProblem:
         kb = k.copy()
         kb[interior] = 0.0
         M = self._boundary_mass
-        return 0.5 * self.cfg.factor_curvature * float(sum((M @ kb[:, i]) @ kb[:, i] for i in range(self.d)))
+        return 0.5 * self.reg_mu["curvature"] * float(sum((M @ kb[:, i]) @ kb[:, i] for i in range(self.d)))
 
     def curvature_derivative_vector(self):
         """``compute_shape_derivative`` (``:554-575``) for V = phi_a e_i with the current kappa:
@@ -322,10 +327,27 @@ class PoissonShapeProblem:
         second = 0.5 * np.einsum("fii->f", tK)[:, None, None] * tg
         out = np.zeros((self.nv, d))
         np.add.at(out, C.reshape(-1), (m[:, None, None] * (first + second)).reshape(-1, d))
-        return self.cfg.factor_curvature * out.reshape(-1)
+        return self.reg_mu["curvature"] * out.reshape(-1)
+
+    def _scale_regularization(self):
+        """``scale`` of every term (``shape_regularization.py:194-211,289-305,461-484,621-643``): the factor is divided by
+        the term's value on the initial geometry unless that vanishes (< 1e-15)."""
+        initial = {
+            "volume": 0.5 * (self.volume() - self.target_volume) ** 2,
+            "surface": 0.5 * (self.surface() - self.target_surface) ** 2,
+            "barycenter": 0.5 * float(np.sum((self.barycenter() - self.target_barycenter) ** 2)),
+        }
+        if self.reg_mu["curvature"] > 0.0:
+            self.reg_mu["curvature"], keep = 1.0, self.reg_mu["curvature"]
+            initial["curvature"] = self.curvature_objective()
+            self.reg_mu["curvature"] = keep
+        for k, v in initial.items():
+            if self.reg_mu[k] > 0.0 and abs(v) >= 1e-15:
+                self.reg_mu[k] /= abs(v)
 
     def regularization_objective(self):
-        c = self.cfg
+        c = types.SimpleNamespace(factor_volume=self.reg_mu["volume"], factor_surface=self.reg_mu["surface"],
+                                  factor_barycenter=self.reg_mu["barycenter"], factor_curvature=self.reg_mu["curvature"])
         val = 0.0
         if c.factor_surface > 0.0:
             val += 0.5 * c.factor_surface * (self.surface() - self.target_surface) ** 2
@@ -345,15 +367,15 @@ class PoissonShapeProblem:
         _, vol, G = self._geom()
         dvol = vol[:, None, None] * G                                              # |K| G_a[i]
         be = np.zeros_like(dvol)
-        if c.factor_volume > 0.0:
-            be += c.factor_volume * (self.volume() - self.target_volume) * dvol
-        if c.factor_barycenter > 0.0:
+        if self.reg_mu["volume"] > 0.0:
+            be += self.reg_mu["volume"] * (self.volume() - self.target_volume) * dvol
+        if self.reg_mu["barycenter"] > 0.0:
             v, bc = self.volume(), self.barycenter()
             xbar = self.coords[self.cells].mean(axis=1)                              # [Nc, d]
             for k in range(d):
                 dxk = dvol * xbar[:, k][:, None, None]                              # int_K x_k div V
                 dxk[:, :, k] += (vol / (d + 1))[:, None]                            # int_K V_k
-                be += c.factor_barycenter * (bc[k] - self.target_barycenter[k]) * (bc[k] / v * dvol + dxk / v)
+                be += self.reg_mu["barycenter"] * (bc[k] - self.target_barycenter[k]) * (bc[k] / v * dvol + dxk / v)
         return be
 
     # -- boundary conditions of the deformation space (shape_form_handler.py:551-588)
@@ -560,8 +582,8 @@ class PoissonShapeProblem:
 
     def shape_derivative_vector(self):
         vec = self._cell_shape_derivative_vector()
-        if self.cfg.factor_surface > 0.0:
-            extra = self.cfg.factor_surface * (self.surface() - self.target_surface) * self.surface_derivative_vector()
+        if self.reg_mu["surface"] > 0.0:
+            extra = self.reg_mu["surface"] * (self.surface() - self.target_surface) * self.surface_derivative_vector()
             extra[self.shape_bc_dofs] = 0.0
             vec = vec + extra
         if self.cfg.factor_curvature > 0.0:

@@ -878,6 +878,32 @@ def test_curvature_regularization_like_the_reference():
     assert len(got) == len(hist) == 4 and np.allclose(got, [h[1] for h in hist], rtol=1e-8) and got[-1] < got[0]
 
 
+def test_scaling_shape_regularization_like_the_reference():
+    """tests/test_shape_optimization.py:800-831: with ``use_relative_scaling`` every regularisation term is divided by
+    its initial value, so the initial cost equals the sum of the four weights (1e-14; the reference asserts 1e-15 on
+    its own sums) -- five random weight sets, volume + surface + curvature + barycenter together."""
+    rng = np.random.RandomState(300696)
+    weights = rng.rand(5, 4)
+    for w in weights:
+        dm, om = circle()
+        cfg = sop_config()
+        cfg.set("Regularization", "use_relative_scaling", "True")
+        cfg.set("Regularization", "target_barycenter", "[1.0, 1.0, 0.0]")
+        for key, val in zip(("factor_volume", "factor_surface", "factor_curvature", "factor_barycenter"), w):
+            cfg.set("Regularization", key, repr(float(val)))
+        sop = make_sop_zero_cost(dm, cfg)
+        val = sop.reduced_cost_functional.evaluate()
+        assert abs(val - w.sum()) < 1e-14
+        ocfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, use_relative_scaling=True, target_barycenter=(1.0, 1.0, 0.0),
+                                    factor_volume=w[0], factor_surface=w[1], factor_curvature=w[2], factor_barycenter=w[3])
+        prob = pipeline.PoissonShapeProblem(om, config=ocfg, c_state=0.0)
+        reg = sop.form_handler.shape_regularization
+        got = np.array([reg.mu_volume, reg.mu_surface, reg.mu_barycenter, reg.mu_curvature])
+        want = np.array([prob.reg_mu[k] for k in ("volume", "surface", "barycenter", "curvature")])
+        assert np.allclose(got, want, rtol=1e-9)
+    assert rel(sop.compute_shape_gradient()[0].vector.cpu().numpy(), prob.compute_shape_gradient()) < 1e-8
+
+
 def test_curvature_kernels_3d():
     """The facet kernels of the curvature term on a perturbed unit cube: boundary mass matrix (row sums = vertex shares
     of the boundary measure, total = |Gamma|), kappa, objective and derivative against the oracle."""

@@ -167,8 +167,7 @@ def test_config_validation_matches_the_reference_case_by_case():
 
 
 def test_unsupported_subsystems_are_refused_loudly():
-    for sec, key, val in (("Regularization", "use_relative_scaling", "True"),
-                          ("StateSystem", "backend", "petsc"), ("Mesh", "remesh", "True"),
+    for sec, key, val in (("StateSystem", "backend", "petsc"), ("Mesh", "remesh", "True"),
                           ("MeshQuality", "remesh_iter", "3")):
         cfg = cb.Config()
         cfg.set(sec, key, val)

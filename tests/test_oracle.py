@@ -569,3 +569,16 @@ def test_p_laplacian_reference_scenarios():
     assert ok and len(hist) - 1 == 5 and hist[-1][2] <= 1e-1
     prob = pipeline.PoissonShapeProblem(load(), config=pipeline.ShapeConfig(p_laplacian_power=10, **base))
     assert pipeline.shape_gradient_test(prob)[0] > 1.9
+
+
+def test_scaling_shape_regularization_known_answer():
+    """tests/test_shape_optimization.py:800-831: with ``use_relative_scaling`` the initial cost of the four regularisation
+    terms equals the sum of their weights (the reference asserts 1e-15) for five random weight sets."""
+    weights = np.random.RandomState(300696).rand(5, 4)
+    for w in weights:
+        om = meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))
+        cfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, use_relative_scaling=True, target_barycenter=(1.0, 1.0, 0.0),
+                                   factor_volume=w[0], factor_surface=w[1], factor_curvature=w[2], factor_barycenter=w[3])
+        prob = pipeline.PoissonShapeProblem(om, config=cfg, c_state=0.0)
+        prob.solve_state()
+        assert abs(prob.cost() - w.sum()) < 1e-15
