@@ -589,9 +589,12 @@ class LinearSolver:
             f64 = dict(dtype=torch.float64, device=mesh.device)
             buf = h._rbm_buf = dict(c=torch.zeros(A.ncols * bs, **f64), v=torch.zeros(A.ncols * bs, **f64),
                                     w=torch.zeros(A.nrows * bs, **f64), G=torch.zeros(k * k, **f64),
-                                    einv=torch.zeros(k * k, **f64), work=torch.zeros(8, **f64))
+                                    einv=torch.zeros(k * k, **f64), work=torch.zeros(8, **f64),
+                                    # own reduction scratch (the set-up may be issued from another stream than the
+                                    # mesh-level reductions)
+                                    scratch=torch.zeros(int(_lib.load().cb_reduce_scratch_len()), **f64))
         lib, s = _lib.load(), _lib.stream_ptr()
-        scratch = mesh.reduce_scratch()
+        scratch = buf["scratch"]
         m = A.struct()
         _lib.check(lib.cb_rbm_galerkin(s, C.byref(m), _lib.ptr(mesh.coords), C.cast(centre, C.c_void_p), _lib.ptr(buf["c"]),
                                        _lib.ptr(buf["v"]), _lib.ptr(buf["w"]), _lib.ptr(buf["G"]), _lib.ptr(scratch),
@@ -601,6 +604,42 @@ class LinearSolver:
         _lib.check(lib.cb_rbm_invert(s, k, _lib.ptr(buf["G"]), _lib.ptr(buf["einv"])), "cb_rbm_invert")
         h.rbm = (buf["c"], buf["einv"], buf["work"])
         return h.rbm
+
+    def _setup_preconditioner(self, A: Matrix, ksp_options, opts):
+        """AMG hierarchy (numeric phase if the matrix changed) and rigid-body coarse correction for ``opts``; fills the
+        pointers of ``opts`` and returns the objects that own them."""
+        hierarchy = hstruct = None
+        nullspace = str((ksp_options or {}).get("pc_amg_nullspace", "translations")).casefold()
+        if opts.pc_type == _PC_TYPES["amg"] and nullspace == "rigid_body":
+            # smoothed aggregation with the six rigid-body modes inside the hierarchy (block prolongator, p_block = 1)
+            if A.bs != 3 or A.mesh.dist is not None:
+                raise _exceptions.InputError("cashocs_b200.LinearSolver", "pc_amg_nullspace",
+                                             "rigid_body needs a 3 x 3 block operator on an unpartitioned mesh")
+            hierarchy = self.rbm_hierarchy(A)
+            hstruct = hierarchy.struct()
+            opts.amg = C.cast(C.pointer(hstruct), C.c_void_p)
+        elif opts.pc_type == _PC_TYPES["amg"]:
+            hierarchy = self.amg_hierarchy(A, ksp_options or {})
+            hstruct = hierarchy.struct()
+            opts.amg = C.cast(C.pointer(hstruct), C.c_void_p)
+            if opts.flexible < 0:
+                opts.flexible = 1 if hierarchy.mixed else 0
+            # rigid-body coarse correction: default for vertex-blocked vector operators (the elasticity Riesz
+            # problem), on one GPU and on partitioned meshes (one extra 6-value all-reduce per iteration)
+            applicable = (A.bs >= 2 and A.bs == A.mesh.dim and A.nrows == A.mesh.n_owned_vertices
+                          and nullspace != "rigid_body")
+            wanted = (ksp_options or {}).get("pc_amg_rigid_body_correction", None)
+            use_rbm = applicable and (True if wanted is None else _truthy(wanted))
+            if use_rbm:
+                rbm = self.rigid_body_correction(A, hierarchy)
+                opts.rbm_coords, opts.rbm_einv, opts.rbm_work = (t.data_ptr() for t in rbm)
+        return hierarchy, hstruct
+
+    def prepare_preconditioner(self, A: Matrix, ksp_options: KspOption | None = None) -> None:
+        """Set up the preconditioner of a later ``solve(A=A, ksp_options=ksp_options)`` now -- everything is cached on
+        the matrix version, so the solve finds it ready (used to time the set-up apart from the iteration)."""
+        opts = parse_ksp_options(ksp_options, None, None, distributed=A.mesh.dist is not None)
+        self._setup_preconditioner(A, ksp_options, opts)
 
     def _workspace(self, n_doubles: int, device) -> torch.Tensor:
         if self._work is None or self._work.numel() < n_doubles or self._work.device != device:
@@ -633,31 +672,7 @@ class LinearSolver:
             return self.last_result
         opts = parse_ksp_options(ksp_options, rtol, atol, distributed=A.mesh.dist is not None)
         lib = _lib.load()
-        hierarchy = None
-        nullspace = str((ksp_options or {}).get("pc_amg_nullspace", "translations")).casefold()
-        if opts.pc_type == _PC_TYPES["amg"] and nullspace == "rigid_body":
-            # smoothed aggregation with the six rigid-body modes inside the hierarchy (block prolongator, p_block = 1)
-            if A.bs != 3 or A.mesh.dist is not None:
-                raise _exceptions.InputError("cashocs_b200.LinearSolver", "pc_amg_nullspace",
-                                             "rigid_body needs a 3 x 3 block operator on an unpartitioned mesh")
-            hierarchy = self.rbm_hierarchy(A)
-            hstruct = hierarchy.struct()
-            opts.amg = C.cast(C.pointer(hstruct), C.c_void_p)
-        elif opts.pc_type == _PC_TYPES["amg"]:
-            hierarchy = self.amg_hierarchy(A, ksp_options or {})
-            hstruct = hierarchy.struct()
-            opts.amg = C.cast(C.pointer(hstruct), C.c_void_p)
-            if opts.flexible < 0:
-                opts.flexible = 1 if hierarchy.mixed else 0
-            # rigid-body coarse correction: default for vertex-blocked vector operators (the elasticity Riesz
-            # problem), on one GPU and on partitioned meshes (one extra 6-value all-reduce per iteration)
-            applicable = (A.bs >= 2 and A.bs == A.mesh.dim and A.nrows == A.mesh.n_owned_vertices
-                          and nullspace != "rigid_body")
-            wanted = (ksp_options or {}).get("pc_amg_rigid_body_correction", None)
-            use_rbm = applicable and (True if wanted is None else _truthy(wanted))
-            if use_rbm:
-                rbm = self.rigid_body_correction(A, hierarchy)
-                opts.rbm_coords, opts.rbm_einv, opts.rbm_work = (t.data_ptr() for t in rbm)
+        keep = self._setup_preconditioner(A, ksp_options, opts)  # noqa: F841  (keeps the C structs alive)
         if opts.flexible < 0:
             opts.flexible = 0
         n, nc = A.nrows * A.bs, A.ncols * A.bs

@@ -6,7 +6,8 @@
 namespace cb {
 
 static thread_local char g_err[1024] = "";
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
+thread_local long long t_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -66,4 +67,4 @@ extern "C" int cb_num_sms(void) {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cb::set_error("cudaDeviceGetAttribute failed"); return CB_ERR_CUDA; }
   return n;
 }
-extern "C" long long cb_launch_count(void) { return cb::g_launch_count; }
+extern "C" long long cb_launch_count(void) { return cb::g_launch_count.load(); }

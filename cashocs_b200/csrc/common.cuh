@@ -1,5 +1,6 @@
 // Shared device helpers: error handling, deterministic grid reductions, small linear algebra.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -20,11 +21,15 @@ void set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
-extern long long g_launch_count;  // kernels launched by this library (bench.py's gpu_launches)
-#define CB_LAUNCH_CHECK()                 \
-  do {                                    \
-    ++cb::g_launch_count;                 \
-    CB_CUDA_CHECK(cudaGetLastError());    \
+// kernels launched by this library (bench.py's gpu_launches); atomic so that callers may drive the library from several
+// host threads, the per-thread twin serves the graph-capture bookkeeping of krylov.cu
+extern std::atomic<long long> g_launch_count;
+extern thread_local long long t_launch_count;
+#define CB_LAUNCH_CHECK()                                            \
+  do {                                                               \
+    ++cb::t_launch_count;                                            \
+    cb::g_launch_count.fetch_add(1, std::memory_order_relaxed);      \
+    CB_CUDA_CHECK(cudaGetLastError());                               \
   } while (0)
 
 #define CB_REQUIRE(cond, msg)                                \

@@ -1307,7 +1307,7 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
           // capture on a private stream (the caller's may be the legacy default stream, which cannot
           // be captured); the launches go to `s` / `S.s`, so both are redirected for the capture
           cudaGraph_t graph = nullptr;
-          const long long before = g_launch_count;
+          const long long before = t_launch_count;
           cudaStream_t user_stream = s, cs = nullptr;
           CB_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
           S.capturing = true;
@@ -1326,8 +1326,9 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
           S.s = user_stream;
           S.capturing = false;
           cudaStreamDestroy(cs);
-          graph_kernels = g_launch_count - before;
-          g_launch_count = before;
+          graph_kernels = t_launch_count - before;  // launches of this thread only (captured, not executed)
+          t_launch_count = before;
+          g_launch_count.fetch_sub(graph_kernels, std::memory_order_relaxed);
           if (brc) { if (graph) cudaGraphDestroy(graph); return brc; }
           CB_CUDA_CHECK(ce);
           const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
@@ -1338,7 +1339,7 @@ extern "C" int cb_ksp_solve(void* stream, const cb_mat* A, const double* b, doub
         for (int c = 0; c < check_every && enq < o->max_it; ++c, ++enq) {
           const cudaError_t le = cudaGraphLaunch(gexec, s);
           CB_CUDA_CHECK(le);
-          g_launch_count += graph_kernels;
+          g_launch_count.fetch_add(graph_kernels, std::memory_order_relaxed);
           S.spmv_launches += 1;
         }
       } else {

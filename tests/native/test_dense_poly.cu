@@ -5,7 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 using namespace cb;
-namespace cb { void set_error(const char*, ...) {} long long g_launch_count = 0; }
+namespace cb { void set_error(const char*, ...) {} std::atomic<long long> g_launch_count{0}; thread_local long long t_launch_count = 0; }
 
 template <int DEG, bool ZDEP>
 static double run(int trials) {
