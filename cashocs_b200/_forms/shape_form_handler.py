@@ -136,10 +136,8 @@ class ShapeFormHandler:
         self.p_laplacian_power = config.getint("ShapeGradient", "p_laplacian_power")
         self.p_laplacian_stabilization = config.getfloat("ShapeGradient", "p_laplacian_stabilization")
         self.reextend_from_boundary = config.getboolean("ShapeGradient", "reextend_from_boundary")
-        if self.reextend_from_boundary and config.get("ShapeGradient", "reextension_mode") != "surface":
-            raise _exceptions.InputError("cashocs_b200.ShapeFormHandler", "reextension_mode",
-                                         "only the default mode `surface` is implemented (the facet-normal projection of "
-                                         "`normal`, shape_gradient_problem.py:225-299, is not)")
+        self.reextension_mode = config.get("ShapeGradient", "reextension_mode")
+        self._normal_space = None
         self.inhomogeneous = config.getboolean("ShapeGradient", "inhomogeneous")
         self.update_inhomogeneous = config.getboolean("ShapeGradient", "update_inhomogeneous")
         self.lambda_lame = config.getfloat("ShapeGradient", "lambda_lame")
@@ -171,6 +169,9 @@ class ShapeFormHandler:
             self.fe_reextension_matrix = linalg.Matrix(mesh, d)
             self.reextension_matrix = self.fe_reextension_matrix
             self.fe_reextension_vector = torch.zeros(mesh.n_owned_vertices * d, dtype=torch.float64, device=mesh.device)
+            # mode `normal`: the boundary values are the normal deformation, which does not vanish on the fixed
+            # boundaries, so the lifting needs the operator without the shape boundary conditions
+            self.fe_lifting_matrix = linalg.Matrix(mesh, d) if self.reextension_mode == "normal" else None
         from cashocs_b200._forms import shape_regularization
 
         self.shape_regularization = shape_regularization.ShapeRegularization(mesh, config, self.bc_flag)
@@ -217,6 +218,60 @@ class ShapeFormHandler:
                 self.mesh, self.mu_lame.vector, self.lambda_lame, self.damping_factor, bc_flag=self.bc_flag_ext,
                 cell_scale=self.cell_scale if self.inhomogeneous else None, A=self.fe_reextension_matrix,
             )
+            if self.fe_lifting_matrix is not None:
+                linalg.assemble_elasticity_matrix(
+                    self.mesh, self.mu_lame.vector, self.lambda_lame, self.damping_factor, bc_flag=None,
+                    cell_scale=self.cell_scale if self.inhomogeneous else None, A=self.fe_lifting_matrix,
+                )
+
+    def compute_normal_deformation(self, g: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """``_compute_normal_deformation`` (``shape_gradient_problem.py:225-299``): the part of the deformation ``g`` normal
+        to the boundaries the [ShapeGradient] section names, by two L2 projections with the boundary mass matrix --
+        ``phi = P(g . n)``, then ``out = P(phi n)`` -- zero in the interior.  A boundary facet carries a marker when all
+        its vertices do.  The reference solves both with cg + boomeramg at rtol 1e-8 (``:281-287``); the boundary systems
+        are tiny, the device solves them tight."""
+        from cashocs_b200 import _lib
+        from cashocs_b200._forms import boundary_space
+
+        mesh = self.mesh
+        d = mesh.dim
+        if self._normal_space is None:
+            markers = (self.shape_bdry_def + self.shape_bdry_fix + self.shape_bdry_fix_x + self.shape_bdry_fix_y
+                       + self.shape_bdry_fix_z)
+            tagged = torch.zeros(mesh.num_vertices, dtype=torch.bool, device=mesh.device)
+            tagged[mesh.boundary_vertices(markers)] = True
+            facets = mesh.boundary_facet_table()[0]
+            facets = facets[tagged[facets.long()].all(dim=1)].contiguous()
+            sp = self._normal_space = boundary_space.BoundarySpace(mesh, facets, "reextension_mode = normal")
+            mesh.build_pattern()
+            sp.opposite = torch.zeros(max(sp.nf, 1), dtype=torch.int32, device=mesh.device)
+            _lib.check(_lib.load().cb_boundary_facet_opposite(
+                _lib.stream_ptr(), d, sp.nf, _lib.ptr(sp.facets), _lib.ptr(mesh.v2c_ptr), _lib.ptr(mesh.v2c_idx),
+                _lib.ptr(mesh.cells), _lib.ptr(sp.opposite)), "cb_boundary_facet_opposite")
+            f64 = dict(dtype=torch.float64, device=mesh.device)
+            sp.phi = torch.zeros(mesh.num_vertices, **f64)
+            sp.rhs_scalar = torch.zeros(mesh.n_owned_vertices, **f64)
+            sp.rhs_vector = torch.zeros(mesh.n_owned_vertices * d, **f64)
+        sp = self._normal_space
+        lib, s = _lib.load(), _lib.stream_ptr()
+
+        def rhs(vector_in: int, src: torch.Tensor, dst: torch.Tensor) -> None:
+            _lib.check(lib.cb_boundary_normal_rhs(s, d, vector_in, sp.nf, mesh.n_owned_vertices, _lib.ptr(mesh.coords),
+                                                  _lib.ptr(sp.facets), _lib.ptr(sp.opposite), _lib.ptr(src), _lib.ptr(sp.v2f_ptr),
+                                                  _lib.ptr(sp.v2f_idx), _lib.ptr(sp.facet_vec), _lib.ptr(dst)),
+                       "cb_boundary_normal_rhs")
+
+        sp.assemble_mass()
+        sp.iterations = 0
+        rhs(1, g, sp.rhs_scalar)
+        sp.phi.zero_()
+        sp.project(sp.rhs_scalar, sp.phi)
+        rhs(0, sp.phi, sp.rhs_vector)
+        out.zero_()
+        b, w = sp.rhs_vector.view(-1, d), out.view(-1, d)
+        for c in range(d):
+            sp.project(b[:, c], w[:, c])
+        return out
 
     def scalar_product(self, a: torch.Tensor, b: torch.Tensor) -> float:
         """``b^T A a`` (``shape_form_handler.py:748-780``); with the p-Laplace projection the p-Laplace form with
@@ -283,12 +338,13 @@ class ShapeFormHandler:
         source with the boundary values of ``gradient`` lifted symmetrically -- row i of a free dof gets
         ``-sum_j A_ij g_j`` over the Dirichlet dofs j, a Dirichlet row its value times the diagonal the elimination
         leaves there (the number of cells at the vertex).  The lifting is one SpMV with the scalar-product matrix:
-        its own Dirichlet rows / columns (``bcs_shape``) belong to dofs where the gradient deformation is zero."""
+        its own Dirichlet rows / columns (``bcs_shape``) belong to dofs where the gradient deformation is zero -- in
+        mode ``normal`` they do not, and the operator without boundary conditions is used."""
         n, d = self.mesh.n_owned_vertices * self.mesh.dim, self.mesh.dim
         flag = self.bc_flag_ext.bool()
         gb = torch.where(flag, gradient, torch.zeros_like(gradient))
         b = self.fe_reextension_vector
-        self.scalar_product_matrix.mult(gb, b)
+        (self.fe_lifting_matrix if self.fe_lifting_matrix is not None else self.scalar_product_matrix).mult(gb, b)
         b.neg_()
         valence = self.mesh.valence[: self.mesh.n_owned_vertices].to(torch.float64).repeat_interleave(d)
         b.copy_(torch.where(flag[:n], valence * gradient[:n], b))

@@ -29,28 +29,9 @@ from __future__ import annotations
 
 import torch
 
-from cashocs_b200 import _exceptions
 from cashocs_b200 import _lib
 from cashocs_b200._forms import expressions
 from cashocs_b200._utils import linalg
-
-
-class _BoundarySpace:
-    """What ``linalg.Matrix`` / ``LinearSolver`` read from a mesh, for the P1 space on the boundary vertices."""
-
-    def __init__(self, mesh, nb: int, rowptr: torch.Tensor, col: torch.Tensor, nnz: int) -> None:
-        self._mesh = mesh
-        self.dim = mesh.dim
-        self.device = mesh.device
-        self.dist = None
-        self.n_owned_vertices = self.num_vertices = nb
-        self.rowptr, self.col, self.nnz = rowptr, col, nnz
-
-    def build_pattern(self) -> None:
-        return None
-
-    def reduce_scratch(self) -> torch.Tensor:
-        return self._mesh.reduce_scratch()
 
 
 class ShapeRegularization:
@@ -167,41 +148,18 @@ class ShapeRegularization:
 
     # -- curvature (shape_regularization.py:512-646)
     def _setup_curvature(self) -> None:
-        """Topology-only data of the boundary mass matrix: compressed boundary vertices, their facet graph, its CSR
-        pattern (the pattern builder of the volume meshes with the facets as cells)."""
+        """The P1 space on the boundary vertices (``boundary_space.BoundarySpace``: compressed numbering, pattern of the
+        facet graph, mass matrix) and the buffers of the mean-curvature vector."""
+        from cashocs_b200._forms import boundary_space
+
         mesh = self.mesh
-        if mesh.dist is not None:
-            raise _exceptions.InputError("cashocs_b200.ShapeRegularization", "factor_curvature",
-                                         "curvature regularisation runs on unpartitioned meshes")
-        d, dev = mesh.dim, mesh.device
-        lib, s = _lib.load(), _lib.stream_ptr()
-        f64 = dict(dtype=torch.float64, device=dev)
-        facets = self._facets.long()
-        bvert = torch.unique(facets.reshape(-1))  # sorted
-        nb, nf = int(bvert.numel()), int(facets.shape[0])
-        facets_c = torch.searchsorted(bvert, facets.reshape(-1)).to(torch.int32).reshape(nf, d).contiguous()
-        v2f_ptr = torch.zeros(nb + 1, dtype=torch.int64, device=dev)
-        v2f_idx = torch.zeros(max(nf * d, 1), dtype=torch.int32, device=dev)
-        _lib.check(lib.cb_v2c_build(s, nb, nf, d, _lib.ptr(facets_c), _lib.ptr(v2f_ptr), _lib.ptr(v2f_idx)), "cb_v2c_build")
-        rowptr = torch.empty(nb + 1, dtype=torch.int64, device=dev)
-        _lib.check(lib.cb_pattern_rowptr(s, nb, d, _lib.ptr(facets_c), _lib.ptr(v2f_ptr), _lib.ptr(v2f_idx),
-                                         _lib.ptr(rowptr)), "cb_pattern_rowptr")
-        nnz = int(rowptr[-1].item())
-        col = torch.empty(nnz, dtype=torch.int32, device=dev)
-        f2n = torch.empty(nf * d * d, dtype=torch.int32, device=dev)
-        _lib.check(lib.cb_pattern_fill(s, nb, nf, d, _lib.ptr(facets_c), _lib.ptr(v2f_ptr), _lib.ptr(v2f_idx),
-                                       _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(f2n)), "cb_pattern_fill")
-        self._bvert, self._bvert32 = bvert, bvert.to(torch.int32).contiguous()
-        self._facets_c, self._bv2f_ptr, self._bv2f_idx = facets_c, v2f_ptr, v2f_idx
-        self._boundary_space = _BoundarySpace(mesh, nb, rowptr, col, nnz)
-        self.boundary_mass = linalg.Matrix(self._boundary_space, 1)
+        d = mesh.dim
+        f64 = dict(dtype=torch.float64, device=mesh.device)
+        self._bspace = boundary_space.BoundarySpace(mesh, self._facets, "factor_curvature")
+        self.boundary_mass = self._bspace.mass
         self.kappa_curvature = torch.zeros(mesh.num_vertices * d, **f64)
-        self._kappa_b = [torch.zeros(nb, **f64) for _ in range(d)]
-        self._rhs_b = torch.zeros(nb, **f64)
+        self._kappa_b = [torch.zeros(self._bspace.n, **f64) for _ in range(d)]
         self._curv_vector = torch.zeros(mesh.n_owned_vertices * d, **f64)
-        if not hasattr(self, "_facet_vec"):
-            self._facet_vec = torch.zeros(max(nf * d * d, 1), **f64)
-        self._curv_solver = linalg.LinearSolver()
         self.curvature_iterations = 0
 
     def _facet_measure_gradient(self, out: torch.Tensor) -> torch.Tensor:
@@ -217,23 +175,14 @@ class ShapeRegularization:
 
     def compute_curvature(self) -> torch.Tensor:
         """``_compute_curvature`` (``:596-613``): the mean-curvature vector, zero at the interior vertices."""
-        mesh, d = self.mesh, self.mesh.dim
-        A = self.boundary_mass
-        _lib.check(
-            _lib.load().cb_boundary_mass(_lib.stream_ptr(), d, A.nrows, _lib.ptr(mesh.coords), _lib.ptr(self._bvert32),
-                                         _lib.ptr(self._facets_c), _lib.ptr(self._bv2f_ptr), _lib.ptr(self._bv2f_idx),
-                                         _lib.ptr(A.rowptr), _lib.ptr(A.col), _lib.ptr(A.val)),
-            "cb_boundary_mass",
-        )
-        A.touch()
+        d, sp = self.mesh.dim, self._bspace
+        sp.assemble_mass()
         b = self._facet_measure_gradient(self._curv_vector).view(-1, d)
         kappa = self.kappa_curvature.view(-1, d)
-        self.curvature_iterations = 0
+        sp.iterations = 0
         for c in range(d):
-            torch.index_select(b[:, c], 0, self._bvert, out=self._rhs_b)
-            res = self._curv_solver.solve(self._kappa_b[c], A=A, b=self._rhs_b, ksp_options=None)
-            self.curvature_iterations += res.its
-            kappa[:, c].index_copy_(0, self._bvert, self._kappa_b[c])
+            self._kappa_b[c].copy_(sp.project(b[:, c], kappa[:, c]))
+        self.curvature_iterations = sp.iterations
         return self.kappa_curvature
 
     def compute_curvature_objective(self) -> float:

@@ -252,6 +252,8 @@ SIGNATURES = {
     "cb_eikonal_rhs": (I32, [P, I32, I64, P, P, P, P, P, P, P]),
     "cb_eikonal_residual": (I32, [P, I32, I64, P, P, P, P, P, I64]),
     "cb_distance_mu": (I32, [P, I64, P, DBL, DBL, DBL, DBL, I32, P]),
+    "cb_boundary_facet_opposite": (I32, [P, I32, I64, P, P, P, P, P]),
+    "cb_boundary_normal_rhs": (I32, [P, I32, I32, I64, I64, P, P, P, P, P, P, P, P]),
     "cb_boundary_mass": (I32, [P, I32, I64, P, P, P, P, P, P, P, P]),
     "cb_boundary_curvature_derivative": (I32, [P, I32, I64, I64, P, P, P, P, P, P, P]),
     "cb_intersection_test": (I32, [P, I32, I64, I64, P, P, P, P, P]),

@@ -66,12 +66,17 @@ class ShapeGradientProblem(pde_problem.PDEProblem):
 
     def reextend_gradient_from_boundaries(self) -> None:
         """Re-extends the gradient deformation to the volume from its boundary values
-        (``shape_gradient_problem.py:175-223``, mode ``surface``): one more solve with the scalar product's operator,
+        (``shape_gradient_problem.py:175-223``; mode ``normal`` first replaces it by its normal part): one more solve with the scalar product's operator,
         now with Dirichlet conditions on every boundary; the result overwrites the gradient deformation."""
         fh = self.form_handler
         if not getattr(fh, "reextend_from_boundary", False):
             return
         g = self.gradient.vector
+        if fh.reextension_mode == "normal":  # shape_gradient_problem.py:186-191
+            w = getattr(self, "_normal_deformation", None)
+            if w is None or w.numel() != g.numel():
+                w = self._normal_deformation = g.new_zeros(g.numel())
+            g.copy_(fh.compute_normal_deformation(g, w))
         b = fh.assemble_reextension_vector(g)
         x = getattr(self, "_reextended", None)
         if x is None or x.numel() != g.numel():

@@ -203,6 +203,81 @@ k_boundary_curvature_derivative(int64_t nf, const double* __restrict__ coords, c
   }
 }
 
+// opp[f] = the vertex of the cell behind boundary facet f that is not on the facet (orients the facet normal)
+template <int D>
+__global__ void __launch_bounds__(128)
+k_facet_opposite(int64_t nf, const int32_t* __restrict__ facets, const int64_t* __restrict__ v2c_ptr,
+                 const int32_t* __restrict__ v2c_idx, const int32_t* __restrict__ cells, int32_t* __restrict__ opp) {
+  constexpr int K = D + 1;
+  const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  int32_t fv[D];
+#pragma unroll
+  for (int a = 0; a < D; ++a) fv[a] = facets[f * D + a];
+  int32_t found = -1;
+  for (int64_t k = v2c_ptr[fv[0]]; k < v2c_ptr[fv[0] + 1] && found < 0; ++k) {
+    int cv[K];
+    load_cell<D>(cells, v2c_idx[k], cv);
+    int hits = 0, other = -1;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      bool on = false;
+#pragma unroll
+      for (int a = 0; a < D; ++a) on = on || (cv[j] == fv[a]);
+      if (on) ++hits; else other = cv[j];
+    }
+    if (hits == D) found = other;
+  }
+  opp[f] = found;
+}
+
+// L2 projections of the re-extension mode `normal` (shape_gradient_problem.py:262-297), facet shares of the right-hand
+// sides with the OUTWARD unit normal n:  VEC_IN: int (g . n) phi_a ds  (one value per facet vertex);  otherwise
+// int phi (n . e_i) phi_a ds  (D values per facet vertex).  P1 data on a flat facet: int f phi_a = |F|/(D(D+1)) (sum_b f_b + f_a).
+template <int D, bool VEC_IN>
+__global__ void __launch_bounds__(128)
+k_boundary_normal_rhs(int64_t nf, const double* __restrict__ coords, const int32_t* __restrict__ facets,
+                      const int32_t* __restrict__ opp, const double* __restrict__ in, double* __restrict__ facet_vec) {
+  for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x) {
+    double x[D][D], g[D][D], n[D];
+    load_facet<D>(coords, facets, f, x);
+    const double w = facet_measure<D>(x, g) / (double)(D * (D + 1));
+    facet_normal<D>(x, n);
+    const int64_t o = opp[f];
+    double side = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) side += n[i] * (__ldg(coords + o * D + i) - x[0][i]);
+    if (side > 0.0) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) n[i] = -n[i];
+    }
+    double val[D], sum = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      const int64_t v = __ldg(facets + f * D + a);
+      if constexpr (VEC_IN) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) t += __ldg(in + v * D + i) * n[i];
+        val[a] = t;
+      } else {
+        val[a] = __ldg(in + v);
+      }
+      sum += val[a];
+    }
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      const double t = w * (sum + val[a]);
+      if constexpr (VEC_IN) {
+        facet_vec[f * D + a] = t;
+      } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) facet_vec[(f * D + a) * D + i] = t * n[i];
+      }
+    }
+  }
+}
+
 }  // namespace cb
 
 using namespace cb;
@@ -272,6 +347,43 @@ extern "C" int cb_boundary_curvature_derivative(void* stream, int dim, int64_t n
   }
   const int grid = grid_for(nrows, 256, 8);
   if (dim == 2) k_gather_cell_vectors<1, 2><<<grid, 256, 0, s>>>(nrows, v2f_ptr, v2f_idx, facets, facet_vec, out);
+  else k_gather_cell_vectors<2, 3><<<grid, 256, 0, s>>>(nrows, v2f_ptr, v2f_idx, facets, facet_vec, out);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int cb_boundary_facet_opposite(void* stream, int dim, int64_t nf, const int32_t* facets, const int64_t* v2c_ptr,
+                                          const int32_t* v2c_idx, const int32_t* cells, int32_t* opp) {
+  CB_REQUIRE(dim == 2 || dim == 3, "cb_boundary_facet_opposite: dim must be 2 or 3");
+  CB_REQUIRE(nf == 0 || (facets && v2c_ptr && v2c_idx && cells && opp), "cb_boundary_facet_opposite: missing argument");
+  if (nf == 0) return CB_OK;
+  cudaStream_t s = as_stream(stream);
+  const int grid = (int)((nf + 127) / 128);
+  if (dim == 2) k_facet_opposite<2><<<grid, 128, 0, s>>>(nf, facets, v2c_ptr, v2c_idx, cells, opp);
+  else k_facet_opposite<3><<<grid, 128, 0, s>>>(nf, facets, v2c_ptr, v2c_idx, cells, opp);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int cb_boundary_normal_rhs(void* stream, int dim, int vector_in, int64_t nf, int64_t nrows, const double* coords,
+                                      const int32_t* facets, const int32_t* opp, const double* in, const int64_t* v2f_ptr,
+                                      const int32_t* v2f_idx, double* facet_vec, double* out) {
+  CB_REQUIRE(dim == 2 || dim == 3, "cb_boundary_normal_rhs: dim must be 2 or 3");
+  CB_REQUIRE(coords && in && v2f_ptr && out && (nf == 0 || (facets && opp && v2f_idx && facet_vec)),
+             "cb_boundary_normal_rhs: missing argument");
+  cudaStream_t s = as_stream(stream);
+  if (nf > 0) {
+    const int grid = grid_for(nf, 128, 8);
+    if (dim == 2 && vector_in) k_boundary_normal_rhs<2, true><<<grid, 128, 0, s>>>(nf, coords, facets, opp, in, facet_vec);
+    else if (dim == 2) k_boundary_normal_rhs<2, false><<<grid, 128, 0, s>>>(nf, coords, facets, opp, in, facet_vec);
+    else if (vector_in) k_boundary_normal_rhs<3, true><<<grid, 128, 0, s>>>(nf, coords, facets, opp, in, facet_vec);
+    else k_boundary_normal_rhs<3, false><<<grid, 128, 0, s>>>(nf, coords, facets, opp, in, facet_vec);
+    CB_LAUNCH_CHECK();
+  }
+  const int grid = grid_for(nrows, 256, 8);
+  if (dim == 2 && vector_in) k_gather_cell_vectors<1, 1><<<grid, 256, 0, s>>>(nrows, v2f_ptr, v2f_idx, facets, facet_vec, out);
+  else if (dim == 2) k_gather_cell_vectors<1, 2><<<grid, 256, 0, s>>>(nrows, v2f_ptr, v2f_idx, facets, facet_vec, out);
+  else if (vector_in) k_gather_cell_vectors<2, 1><<<grid, 256, 0, s>>>(nrows, v2f_ptr, v2f_idx, facets, facet_vec, out);
   else k_gather_cell_vectors<2, 3><<<grid, 256, 0, s>>>(nrows, v2f_ptr, v2f_idx, facets, facet_vec, out);
   CB_LAUNCH_CHECK();
   return CB_OK;

@@ -555,6 +555,18 @@ int cb_plaplace_jacobian(void* stream, int dim, int64_t nrows, const int64_t* v2
 int cb_plaplace_product(void* stream, int dim, int64_t nc, const double* coords, const int32_t* cells,
                         const double* a, const double* b, const double* mu, int p, double eps, double delta,
                         double* result_dev, double* scratch, int64_t scratch_len);
+/* opp[f] = vertex of the cell behind boundary facet f that does not lie on the facet (orients the outward facet
+ * normal, fenics.FacetNormal); v2c_*: vertex -> cell adjacency of the mesh. */
+int cb_boundary_facet_opposite(void* stream, int dim, int64_t nf, const int32_t* facets, const int64_t* v2c_ptr,
+                               const int32_t* v2c_idx, const int32_t* cells, int32_t* opp);
+/* Right-hand sides of the two L2 projections of the re-extension mode `normal`
+ * (_compute_normal_deformation, cashocs/_pde_problems/shape_gradient_problem.py:262-297) over the facets [nf, dim]
+ * with the outward unit normal n: vector_in != 0: in [nv*dim] = g, out[v] = int (g . n) phi_v ds; vector_in == 0:
+ * in [nv] = phi, out[v, i] = int phi n_i phi_v ds; v < nrows.  v2f_*: vertex -> facet adjacency of these facets,
+ * facet_vec [nf*dim*dim] scratch. */
+int cb_boundary_normal_rhs(void* stream, int dim, int vector_in, int64_t nf, int64_t nrows, const double* coords,
+                           const int32_t* facets, const int32_t* opp, const double* in, const int64_t* v2f_ptr,
+                           const int32_t* v2f_idx, double* facet_vec, double* out);
 /* Per-vertex collision counts (compute_collisions, cashocs/geometry/mesh_testing.py:201-241)
  * with a uniform-grid broad phase built on the device; mismatch_dev (device int64) receives the
  * number of vertices whose count differs from `valence`. */

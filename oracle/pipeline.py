@@ -113,7 +113,7 @@ class ShapeConfig:
     p_laplacian_stabilization: float = 0.0
     # re-extension of the gradient deformation from its boundary values (shape_gradient_problem.py:175-223)
     reextend_from_boundary: bool = False
-    reextension_mode: str = "surface"    # "normal" (the facet-normal projection, :225-299) is not restated
+    reextension_mode: str = "surface"    # or "normal": only the normal part of the boundary values (:225-299)
     polynomial_model: str = "cubic"
     factor_low: float = 0.1
     factor_high: float = 0.5
@@ -503,13 +503,53 @@ class PoissonShapeProblem:
             dofs.append(d * np.arange(self.nv) + int(k))
         return np.unique(np.concatenate(dofs)).astype(np.int64)
 
+    def compute_normal_deformation(self, g):
+        """``_compute_normal_deformation`` (shape_gradient_problem.py:225-299): two L2 projections on the boundaries the
+        [ShapeGradient] section names -- the scalar ``phi`` with ``int phi v ds = int (g . n) v ds`` for all P1 ``v``, then
+        the vector ``w`` with ``int w . v ds = int phi (n . v) ds``; rows without a boundary facet are identities
+        (``ident_zeros``), so ``w`` vanishes in the interior.  ``n`` is the outward unit normal.
+        A boundary facet carries a marker when all its vertices do (facet tags are not stored with the oracle's meshes)."""
+        import scipy.sparse as sps
+        import scipy.sparse.linalg as spla
+
+        d, c = self.d, self.cfg
+        markers = (tuple(c.shape_bdry_def) + tuple(c.shape_bdry_fix) + tuple(c.shape_bdry_fix_x)
+                   + tuple(c.shape_bdry_fix_y) + tuple(c.shape_bdry_fix_z))
+        tagged = np.zeros(self.nv, dtype=bool)
+        tagged[self.mesh.boundary_vertices(markers)] = True
+        allF, C, _, _, all_m = self._boundary_frames()
+        sel = np.all(tagged[allF], axis=1)
+        F, C, m = allF[sel], C[sel], all_m[sel]
+        # outward unit normal: minus the (normalised) gradient of the hat function of the opposite vertex
+        _, _, G = fem.cell_geometry(self.coords, C)
+        opp = np.array([[v not in set(f) for v in c] for c, f in zip(C, F)])
+        n = -G[opp]
+        n = n / np.linalg.norm(n, axis=1)[:, None]
+        loc = (np.ones((d, d)) + np.eye(d)) / (d * (d + 1))
+        Me = m[:, None, None] * loc[None]                                   # facet mass matrices [nf, d, d]
+        rows, cols = np.repeat(F, d, axis=1).reshape(-1), np.tile(F, (1, d)).reshape(-1)
+        M = sps.coo_matrix((Me.reshape(-1), (rows, cols)), shape=(self.nv, self.nv)).tocsr()
+        free = np.setdiff1d(np.arange(self.nv), np.unique(F))
+        M = (M + sps.coo_matrix((np.ones(len(free)), (free, free)), shape=(self.nv, self.nv))).tocsc()
+        lu = spla.splu(M)
+        gF = g.reshape(-1, d)[F]                                            # [nf, d(vertex), d(component)]
+        b1 = np.zeros(self.nv)
+        np.add.at(b1, F.reshape(-1), np.einsum("fab,fbi,fi->fa", Me, gF, n).reshape(-1))
+        phi = lu.solve(b1)
+        b2 = np.zeros((self.nv, d))
+        np.add.at(b2, F.reshape(-1), np.einsum("fab,fb,fi->fai", Me, phi[F], n).reshape(-1, d))
+        w = np.column_stack([lu.solve(b2[:, i]) for i in range(d)])
+        return w.reshape(-1)
+
     def reextend_gradient_from_boundaries(self, g):
         """``ShapeGradientProblem.reextend_gradient_from_boundaries`` (shape_gradient_problem.py:175-223), mode
         ``surface``: solve the homogeneous elasticity equation of the scalar product with the boundary values of the
         gradient deformation as Dirichlet data (symmetric elimination with those values: ``setup_assembler`` with
         ``bcs_extension``, shape_form_handler.py:343-367) and take the solution as the new gradient deformation."""
-        if self.cfg.reextension_mode != "surface":
-            raise NotImplementedError("reextension_mode = normal is not restated")
+        if self.cfg.reextension_mode == "normal":  # :186-191: only the normal part of the boundary values is kept
+            g = self.compute_normal_deformation(g)
+        elif self.cfg.reextension_mode != "surface":
+            raise ValueError("reextension_mode is surface or normal")
         dofs = self._reextension_bc_dofs()
         A, b = fem.assemble_system(self._Ae_elas.copy(), np.zeros(self.vcell_dofs.shape), self.vcell_dofs,
                                    self.d * self.nv, dofs, g[dofs])

@@ -371,8 +371,46 @@ def test_reextension_surface_like_the_reference():
     ok, hist = pipeline.lbfgs(pipeline.PoissonShapeProblem(om2, config=ocfg), rtol=1e-2, max_iter=7)
     assert ok and len(hist) - 1 == sop.solver.iteration
     assert abs(sop.solver.objective_value - hist[-1][1]) < 1e-8 * abs(hist[-1][1])
-    with pytest.raises(cb.InputError):
-        make_sop(dm2, sop_config(reextend_from_boundary=True, reextension_mode="normal"))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_reextension_normal_like_the_reference(dim, rng):
+    """tests/test_shape_optimization.py:1084-1110 (``reextension_mode = normal``): the normal part of a deformation from
+    the two boundary L2 projections (outward facet normals, csrc/boundary.cu) equals the oracle's -- a radial field on the
+    disc is reproduced, a tangential one vanishes --, the re-extended gradient agrees, and L-BFGS meets the reference's
+    budget of 11 iterations with the oracle's iteration count (10)."""
+    if dim == 2:
+        dm, om = circle()
+        markers, extra, oextra = (1,), {}, {}
+    else:
+        dm, om = cb.regular_mesh(5, 1.0, 1.0, 1.0), meshes.regular_mesh(5, 1.0, 1.0, 1.0)
+        markers = (1, 2, 3, 4, 5, 6)
+        extra = dict(shape_bdry_def="[2, 4]", shape_bdry_fix="[1]")
+        oextra = dict(shape_bdry_def=(2, 4), shape_bdry_fix=(1,))
+    sop = make_sop(dm, sop_config(reextend_from_boundary=True, reextension_mode="normal", **extra), bc_markers=markers)
+    ocfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, reextend_from_boundary=True, reextension_mode="normal", **oextra)
+    prob = pipeline.PoissonShapeProblem(om, bc_markers=markers, config=ocfg)
+    fh = sop.form_handler
+    field = rng.rand(om.num_vertices * dim)
+    out = torch.zeros(om.num_vertices * dim, dtype=torch.float64, device=dm.coords.device)
+    w1 = fh.compute_normal_deformation(torch.from_numpy(field).to(out.device), out).cpu().numpy()
+    w0 = prob.compute_normal_deformation(field)
+    assert np.max(np.abs(w1 - w0)) <= 1e-10 * np.max(np.abs(w0))
+    if dim == 2:
+        radial = om.coords.reshape(-1).copy()
+        wr = fh.compute_normal_deformation(torch.from_numpy(radial).to(out.device), out).cpu().numpy().reshape(-1, 2)
+        b = om.boundary_vertices((1,))
+        assert np.max(np.abs(wr[b] - om.coords[b])) < 1e-3
+        tang = np.stack([-om.coords[:, 1], om.coords[:, 0]], axis=1).reshape(-1)
+        assert np.max(np.abs(fh.compute_normal_deformation(torch.from_numpy(tang).to(out.device), out).cpu().numpy())) < 1e-12
+    g1 = sop.compute_shape_gradient()[0].vector.cpu().numpy()
+    g0 = prob.compute_shape_gradient()
+    assert rel(g1, g0) < 1e-8
+    if dim == 2:
+        sop.solve(algorithm="bfgs", rtol=1e-2, atol=0.0, max_iter=11)
+        ok, hist = pipeline.lbfgs(prob, rtol=1e-2, max_iter=11, memory=3)
+        assert ok and sop.solver.converged and sop.solver.iteration == len(hist) - 1 <= 11
+        assert abs(sop.solver.objective_value - hist[-1][1]) < 1e-8 * abs(hist[-1][1])
 
 
 @pytest.mark.parametrize("method,budget", [("FR", 21), ("PR", 16), ("HS", 18), ("DY", 18), ("HZ", 18)])

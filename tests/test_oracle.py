@@ -582,3 +582,19 @@ def test_scaling_shape_regularization_known_answer():
         prob = pipeline.PoissonShapeProblem(om, config=cfg, c_state=0.0)
         prob.solve_state()
         assert abs(prob.cost() - w.sum()) < 1e-15
+
+
+def test_reextension_normal_reference_budget():
+    """tests/test_shape_optimization.py:1084-1110 (``reextension_mode = normal``): L-BFGS reaches rtol 1e-2 within the
+    reference's 11 iterations (oracle: 10); the normal projection reproduces a radial field on the disc's boundary and
+    annihilates a tangential one."""
+    cfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, reextend_from_boundary=True, reextension_mode="normal")
+    om = meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))
+    prob = pipeline.PoissonShapeProblem(om, config=cfg)
+    b = om.boundary_vertices((1,))
+    w = prob.compute_normal_deformation(om.coords.reshape(-1).copy()).reshape(-1, 2)
+    assert np.max(np.abs(w[b] - om.coords[b])) < 1e-3 and np.count_nonzero(np.delete(w, b, axis=0)) == 0
+    tang = np.stack([-om.coords[:, 1], om.coords[:, 0]], axis=1).reshape(-1)
+    assert np.max(np.abs(prob.compute_normal_deformation(tang))) < 1e-12
+    ok, hist = pipeline.lbfgs(prob, rtol=1e-2, max_iter=11, memory=3)
+    assert ok and len(hist) - 1 == 10
