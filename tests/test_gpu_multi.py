@@ -3,7 +3,8 @@ same path is covered on CPU by tests/test_distributed_cpu.py over gloo).
 
 * one-sided NVLink transport vs the expected values, bit for bit (tools/check_p2p.py),
 * distributed AMG-PCG vs Jacobi-PCG on 2 ranks, partitioned + agglomerated levels (tools/debug_dist_amg.py),
-* P2 state / adjoint pipeline on a partition vs the one-GPU result (tools/check_dist_p2.py).
+* P2 state / adjoint pipeline on a partition vs the one-GPU result (tools/check_dist_p2.py),
+* distance-based mu and re-extension on a partition vs the one-GPU result (tools/check_dist_features.py).
 """
 
 import os
@@ -45,3 +46,9 @@ def test_distributed_amg(args):
 def test_distributed_p2_pipeline(pc):
     out = _torchrun("check_dist_p2.py", 8, pc, port=29613)
     assert "DIST_P2_OK" in out, out[-2000:]
+
+
+@needs2
+def test_distributed_round2_features():
+    out = _torchrun("check_dist_features.py", 10, port=29614)
+    assert "DIST_FEATURES_OK" in out, out[-2000:]
