@@ -20,6 +20,8 @@ from cashocs_b200.geometry.mesh_testing import APrioriMeshTester, IntersectionTe
 from cashocs_b200.geometry.deformations import DeformationHandler
 from cashocs_b200.geometry.quality import compute_mesh_quality
 from cashocs_b200.io.config import Config, load_config
+from cashocs_b200 import nonlinear_solvers
+from cashocs_b200.nonlinear_solvers import linear_solve, newton_solve
 
 __version__ = "0.1.0"
 
@@ -27,6 +29,6 @@ __all__ = [
     "APrioriMeshTester", "CashocsException", "Config", "ConfigError", "DeformationHandler", "DirichletBC",
     "Function", "InputError", "IntegralFunctional", "IntersectionTester", "LinearSolver", "Matrix", "Mesh",
     "NotConvergedError", "OptimalControlProblem", "PETScKSPError", "PoissonForm", "Polynomial",
-    "ShapeOptimizationProblem", "compute_mesh_quality", "create_dirichlet_bcs", "import_mesh", "load_config", "log",
+    "ShapeOptimizationProblem", "compute_mesh_quality", "create_dirichlet_bcs", "import_mesh", "linear_solve", "load_config", "log", "newton_solve", "nonlinear_solvers",
     "mesh_from_arrays", "regular_box_mesh", "regular_mesh", "spatial_coordinate",
 ]

@@ -453,6 +453,45 @@ def test_control_problem_matches_reference_definitions(rng):
     assert abs(ocp.reduced_cost_functional.evaluate() - ref.cost()) < 1e-10 * abs(ref.cost())
 
 
+def test_public_linear_and_newton_solve():
+    """``cashocs.linear_solve`` / ``cashocs.newton_solve`` (nonlinear_solvers/linear_solver.py:37-110,
+    newton_solver.py:365-470; tests/test_nonlinear_solvers.py:28-61): the stand-alone entry points over the same
+    assembly + Krylov primitives -- a Poisson problem with inhomogeneous Dirichlet data against the oracle's direct
+    solve, -Laplace u + 1e2 u^3 = 1 against the oracle's Newton iteration (same number of steps)."""
+    import scipy.sparse.linalg as spla
+
+    from oracle import fem, nonlinear
+
+    dm, om = cb.regular_mesh(5), meshes.regular_mesh(5)
+    _, vol, G = fem.cell_geometry(om.coords, om.cells)
+    one = cb.Function(dm)
+    one.vector.fill_(1.0)
+    u = cb.Function(dm)
+    bcs = cb.create_dirichlet_bcs(0.25, [1, 2]) + cb.create_dirichlet_bcs(0.0, [3, 4])
+    out = cb.linear_solve(cb.PoissonForm(source=one, kappa=2.0, reaction=0.5), u, bcs, ksp_options=KSP)
+    assert out is u
+    Ke = 2.0 * fem.stiffness_elements(vol, G) + 0.5 * fem.mass_elements(vol, 2)
+    dofs = np.unique(np.concatenate([om.boundary_vertices((1, 2)), om.boundary_vertices((3, 4))]))
+    vals = np.zeros(om.num_vertices)
+    vals[om.boundary_vertices((1, 2))] = 0.25
+    vals[om.boundary_vertices((3, 4))] = 0.0  # later conditions overwrite earlier ones
+    A, b = fem.assemble_system(Ke, fem.load_elements_p1(vol, om.cells, np.ones(om.num_vertices), 2), om.cells,
+                               om.num_vertices, dofs, vals[dofs])
+    assert rel(u.vector.cpu().numpy(), spla.spsolve(A.tocsc(), b)) < 1e-8
+    y = cb.Function(dm)
+    cb.newton_solve(cb.PoissonForm(source=one, cubic=1e2), y, cb.create_dirichlet_bcs(0.0, [1, 2, 3, 4]), rtol=1e-9,
+                    atol=1e-10, max_iter=50, ksp_options=KSP)
+    load = fem.load_elements_p1(vol, om.cells, np.ones(om.num_vertices), 2)
+    y0, its0 = nonlinear.newton_solve(om.coords, om.cells, load, 1e2, om.boundary_vertices((1, 2, 3, 4)), rtol=1e-9,
+                                      atol=1e-10, max_iter=50)
+    assert y.iterations == its0 and rel(y.vector.cpu().numpy(), y0) < 1e-8
+    with pytest.raises(cb.InputError):
+        cb.linear_solve(cb.PoissonForm(source=one, cubic=1.0), u, bcs)
+    with pytest.raises(cb.NotConvergedError):
+        cb.newton_solve(cb.PoissonForm(source=one, cubic=1e2), cb.Function(dm), cb.create_dirichlet_bcs(0.0, [1, 2, 3, 4]),
+                        rtol=1e-9, atol=1e-10, max_iter=1, ksp_options=KSP)
+
+
 def test_semilinear_state_newton_like_the_reference():
     """SURVEY.md 8f row 1, the nonlinear state path on the device.
     (i) tests/test_nonlinear_solvers.py:28-61: -Laplace u + 1e2 u^3 = 1 on regular_mesh(5), Newton from zero with
