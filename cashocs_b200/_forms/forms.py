@@ -146,13 +146,17 @@ class PoissonForm:
 
 @dataclasses.dataclass
 class IntegralFunctional:
-    """``J = int (c_state*u + c_track/2 (u-u_d)^2) dx + c_control/2 int control^2 dx``
-    (``cashocs.IntegralFunctional``, ``cashocs/_optimization/cost_functional.py:146-206``)."""
+    """``J = int (c_state*u + c_track/2 (u-u_d)^2) dx + c_control/2 int control^2 dx + c_volume int 1 dx + c_surface int 1 ds``
+    (``cashocs.IntegralFunctional``, ``cashocs/_optimization/cost_functional.py:146-206``); the last two are the
+    geometric terms of shape problems (``Constant(alpha) * dx + Constant(alpha) * ds`` in
+    ``demos/documented/shape_optimization/regularization/demo_regularization.py``)."""
 
     c_state: float = 0.0
     c_track: float = 0.0
     desired_state: Function | None = None
     c_control: float = 0.0
+    c_volume: float = 0.0
+    c_surface: float = 0.0
 
     def __post_init__(self):
         if self.c_track != 0.0 and self.desired_state is None:

@@ -174,7 +174,7 @@ class ShapeFormHandler:
             self.fe_lifting_matrix = linalg.Matrix(mesh, d) if self.reextension_mode == "normal" else None
         from cashocs_b200._forms import shape_regularization
 
-        self.shape_regularization = shape_regularization.ShapeRegularization(mesh, config, self.bc_flag)
+        self.shape_regularization = shape_regularization.ShapeRegularization(mesh, config, self.bc_flag, cost)
         self.update_scalar_product()
 
     def _setup_bcs_shape(self) -> list[forms.DirichletBC]:

@@ -35,15 +35,19 @@ from cashocs_b200._utils import linalg
 
 
 class ShapeRegularization:
-    def __init__(self, mesh, config, bc_flag) -> None:
+    def __init__(self, mesh, config, bc_flag, cost=None) -> None:
         self.mesh, self.config, self.bc_flag = mesh, config, bc_flag
         d = mesh.dim
+        # geometric terms of the cost functional itself (IntegralFunctional.c_volume / .c_surface): linear in the
+        # volume / the boundary measure, they ride on the same kernels as the quadratic regularisation terms
+        self.j_volume = float(getattr(cost, "c_volume", 0.0) or 0.0)
+        self.j_surface = float(getattr(cost, "c_surface", 0.0) or 0.0)
         self.mu_volume = config.getfloat("Regularization", "factor_volume")
         self.mu_barycenter = config.getfloat("Regularization", "factor_barycenter")
         self.mu_surface = config.getfloat("Regularization", "factor_surface")
         self.mu_curvature = config.getfloat("Regularization", "factor_curvature")
         self.is_active = (self.mu_volume > 0.0 or self.mu_barycenter > 0.0 or self.mu_surface > 0.0
-                          or self.mu_curvature > 0.0)
+                          or self.mu_curvature > 0.0 or self.j_volume != 0.0 or self.j_surface != 0.0)
         if not self.is_active:
             return
         f64 = dict(dtype=torch.float64, device=mesh.device)
@@ -64,7 +68,7 @@ class ShapeRegularization:
         self.current_barycenter = [0.0, 0.0, 0.0]
         self.current_surface = 1.0
         self.target_surface = config.getfloat("Regularization", "target_surface")
-        if self.mu_surface > 0.0 or self.mu_curvature > 0.0:
+        if self.mu_surface > 0.0 or self.mu_curvature > 0.0 or self.j_surface != 0.0:
             self._facets, self._v2f_ptr, self._v2f_idx, counted = mesh.boundary_facet_table()
             # facets this rank adds to the global measure (all of them on one GPU; on a partition every boundary
             # facet is counted by exactly one rank)
@@ -197,7 +201,7 @@ class ShapeRegularization:
             self.current_volume = self.compute_volume()
             if self.mu_barycenter > 0.0:
                 self.current_barycenter = self.compute_barycenter()
-            if self.mu_surface > 0.0:
+            if self.mu_surface > 0.0 or self.j_surface != 0.0:
                 self.current_surface = self.compute_surface()
 
     def compute_objective(self) -> float:
@@ -214,6 +218,10 @@ class ShapeRegularization:
             value += 0.5 * self.mu_barycenter * sum((bc[k] - self.target_barycenter[k]) ** 2 for k in range(3))
         if self.mu_curvature > 0.0:
             value += self.compute_curvature_objective()
+        if self.j_volume != 0.0:
+            value += self.j_volume * self.compute_volume()
+        if self.j_surface != 0.0:
+            value += self.j_surface * self.compute_surface()
         return value
 
     def add_shape_derivative(self, b: torch.Tensor) -> torch.Tensor:
@@ -222,7 +230,7 @@ class ShapeRegularization:
         if not self.is_active:
             return b
         d = self.mesh.dim
-        if self.mu_surface > 0.0:  # mu (surface - target) int_Gamma t_div(V, n) ds  (:248-269)
+        if self.mu_surface > 0.0 or self.j_surface != 0.0:  # mu (surface - target) int_Gamma t_div(V, n) ds  (:248-269)
             mesh = self.mesh
             _lib.check(
                 _lib.load().cb_boundary_measure_gradient(
@@ -233,7 +241,10 @@ class ShapeRegularization:
             )
             if self.bc_flag is not None:
                 self._surface_vector.masked_fill_(self.bc_flag[: self._surface_vector.numel()].bool(), 0.0)
-            b.add_(self._surface_vector, alpha=self.mu_surface * (self.current_surface - self.target_surface))
+            coef = self.j_surface
+            if self.mu_surface > 0.0:
+                coef += self.mu_surface * (self.current_surface - self.target_surface)
+            b.add_(self._surface_vector, alpha=coef)
         if self.mu_curvature > 0.0:  # :554-575 with the mean-curvature vector of the current mesh
             mesh = self.mesh
             self.compute_curvature()
@@ -247,10 +258,10 @@ class ShapeRegularization:
             if self.bc_flag is not None:
                 self._curv_vector.masked_fill_(self.bc_flag[: self._curv_vector.numel()].bool(), 0.0)
             b.add_(self._curv_vector, alpha=self.mu_curvature)
-        if self.mu_volume <= 0.0 and self.mu_barycenter <= 0.0:
+        if self.mu_volume <= 0.0 and self.mu_barycenter <= 0.0 and self.j_volume == 0.0:
             return b
         vol, bc, target = self.current_volume, self.current_barycenter, self.target_barycenter
-        a0 = self.mu_volume * (vol - self.target_volume) if self.mu_volume > 0.0 else 0.0
+        a0 = self.j_volume + (self.mu_volume * (vol - self.target_volume) if self.mu_volume > 0.0 else 0.0)
         f = expressions.Polynomial.constant(0.0)
         if self.mu_barycenter > 0.0:
             for k in range(d):

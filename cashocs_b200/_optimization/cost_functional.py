@@ -55,4 +55,9 @@ class ReducedCostFunctional:
             val += 0.5 * c.c_control * self.mass_scalar_product(self.control.vector, self.control.vector)
         if self.shape_regularization is not None and self.shape_regularization.is_active:
             val += self.shape_regularization.compute_objective()
+        elif getattr(c, "c_volume", 0.0) != 0.0 or getattr(c, "c_surface", 0.0) != 0.0:
+            from cashocs_b200 import _exceptions
+
+            raise _exceptions.InputError("cashocs_b200.IntegralFunctional", "c_volume",
+                                         "the geometric terms int 1 dx / int 1 ds belong to shape optimisation problems")
         return val

@@ -141,6 +141,8 @@ class PoissonShapeProblem:
         c_track: float = 0.0,
         u_d=None,
         use_pull_back: bool = True,
+        c_volume: float = 0.0,
+        c_surface: float = 0.0,
     ):
         """State ``kappa grad u . grad p + reaction u p - f p`` (= 0), cost
         ``J = c_state int u + c_track / 2 int (u - u_d)^2`` with a P1 (vertex-valued) ``u_d`` that is transported with the
@@ -151,6 +153,9 @@ class PoissonShapeProblem:
         self.kappa, self.reaction, self.c_track = float(kappa), float(reaction), float(c_track)
         self.u_d = None if u_d is None else np.asarray(u_d, dtype=float)
         self.use_pull_back = bool(use_pull_back)
+        # geometric terms of the cost functional itself, J += c_volume int 1 dx + c_surface int 1 ds
+        # (demos/documented/shape_optimization/regularization/demo_regularization.py: Constant(alpha)*dx + Constant(alpha)*ds)
+        self.c_volume, self.c_surface = float(c_volume), float(c_surface)
         if self.c_track != 0.0 and self.u_d is None:
             raise ValueError("oracle: the tracking term needs u_d")
         general = (self.kappa != 1.0 or self.reaction != 0.0 or self.c_track != 0.0)
@@ -369,6 +374,8 @@ class PoissonShapeProblem:
         be = np.zeros_like(dvol)
         if self.reg_mu["volume"] > 0.0:
             be += self.reg_mu["volume"] * (self.volume() - self.target_volume) * dvol
+        if self.c_volume != 0.0:
+            be += self.c_volume * dvol
         if self.reg_mu["barycenter"] > 0.0:
             v, bc = self.volume(), self.barycenter()
             xbar = self.coords[self.cells].mean(axis=1)                              # [Nc, d]
@@ -438,6 +445,10 @@ class PoissonShapeProblem:
         """``IntegralFunctional.evaluate`` (``cashocs/_optimization/cost_functional.py:160-168``)."""
         _, vol, _ = self._geom()
         reg = self.regularization_objective()  # cost_functional.py:84-86
+        if self.c_volume != 0.0:
+            reg += self.c_volume * self.volume()
+        if self.c_surface != 0.0:
+            reg += self.c_surface * self.surface()
         if self.state_degree == 2:
             return self.c_state * p2.integral(self.u, self.p2_dofs, vol, self.d) + reg
         J = self.c_state * float(np.sum(vol * self.u[self.cells].mean(axis=1)))
@@ -622,8 +633,11 @@ class PoissonShapeProblem:
 
     def shape_derivative_vector(self):
         vec = self._cell_shape_derivative_vector()
-        if self.reg_mu["surface"] > 0.0:
-            extra = self.reg_mu["surface"] * (self.surface() - self.target_surface) * self.surface_derivative_vector()
+        if self.reg_mu["surface"] > 0.0 or self.c_surface != 0.0:
+            coef = self.c_surface
+            if self.reg_mu["surface"] > 0.0:
+                coef += self.reg_mu["surface"] * (self.surface() - self.target_surface)
+            extra = coef * self.surface_derivative_vector()
             extra[self.shape_bc_dofs] = 0.0
             vec = vec + extra
         if self.cfg.factor_curvature > 0.0:
@@ -635,7 +649,7 @@ class PoissonShapeProblem:
 
     def _cell_shape_derivative_vector(self):
         be = self.shape_derivative_elements()
-        if self.cfg.factor_volume > 0.0 or self.cfg.factor_barycenter > 0.0:
+        if self.cfg.factor_volume > 0.0 or self.cfg.factor_barycenter > 0.0 or self.c_volume != 0.0:
             be = be + self.regularization_derivative_elements().reshape(be.shape)
         if self.shape_bc_dofs.size:
             _, be = fem.apply_bcs_elementwise(None, be, self.vcell_dofs, self.shape_bc_dofs, 0.0,

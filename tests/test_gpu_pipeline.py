@@ -723,6 +723,47 @@ def test_documented_demo_shape_poisson():
     assert abs(sop.solver.objective_value - hist[-1][1]) < 1e-8 * abs(hist[-1][1])
 
 
+def _run_demo(folder: str, script: str):
+    import importlib.util
+
+    path = os.path.join(os.path.dirname(GOLDEN), "..", "examples", folder, script)
+    spec = importlib.util.spec_from_file_location(script[:-3], path)
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    return demo.main(verbose=False)
+
+
+def test_documented_demos_regularization_p_laplacian_nonlinear_pdes():
+    """Three more of the reference's documented demos run through the drop-in surface with their own config keys
+    (examples/*/config.ini) and land where the oracle's loops land with the same settings:
+    shape_optimization/regularization (volume + surface + curvature regularisation, geometric terms in J; L-BFGS),
+    shape_optimization/p_laplacian (p = 10, gradient descent; the oracle needs 48 iterations and ends at
+    J = -0.0937373769731638 -- 45 s of scipy, so its result is quoted, not recomputed, here) and
+    optimal_control/nonlinear_pdes (semilinear state by Newton's method, is_linear left at its default; L-BFGS)."""
+    sop = _run_demo("shape_regularization", "demo_regularization.py")
+    om = meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))
+    ocfg = pipeline.ShapeConfig(lambda_lame=0.0, mu_def=1.0, mu_fix=1.0, damping_factor=0.5, factor_volume=1.0,
+                                target_volume=1.5, factor_surface=1.0, target_surface=4.5, factor_curvature=1e-4)
+    prob = pipeline.PoissonShapeProblem(om, config=ocfg, c_volume=0.1, c_surface=0.1)
+    ok, hist = pipeline.lbfgs(prob, rtol=1e-3, max_iter=100, memory=5)
+    assert ok and sop.solver.converged and abs(sop.solver.iteration - (len(hist) - 1)) <= 1
+    assert abs(sop.solver.objective_value - hist[-1][1]) <= 1e-5 * abs(hist[-1][1])
+    reg = sop.form_handler.shape_regularization
+    assert abs(reg.compute_volume() - prob.volume()) < 1e-4 and abs(reg.compute_surface() - prob.surface()) < 1e-4
+
+    sop = _run_demo("shape_p_laplacian", "demo_p_laplacian.py")
+    assert sop.solver.converged and sop.solver.relative_norm <= 1e-2 and abs(sop.solver.iteration - 48) <= 2
+    assert abs(sop.solver.objective_value - (-0.0937373769731638)) <= 1e-4 * 0.0937373769731638
+
+    ocp = _run_demo("optimal_control_nonlinear_pdes", "demo_nonlinear_pdes.py")
+    om = meshes.regular_mesh(25)
+    yd = np.sin(2 * np.pi * om.coords[:, 0]) * np.sin(2 * np.pi * om.coords[:, 1])
+    oprob = pipeline.PoissonControlProblem(om, yd, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4), cubic=1e2)
+    ok, hist = pipeline.lbfgs(oprob, rtol=1e-3, max_iter=100, memory=5)
+    assert ok and ocp.solver.converged and ocp.solver.iteration == len(hist) - 1
+    assert abs(ocp.solver.objective_value - hist[-1][1]) <= 1e-6 * abs(hist[-1][1])
+
+
 def test_default_is_linear_false_runs_newton_on_the_linear_state():
     """The reference's default is ``is_linear = False`` (io/config.py:599): ``newton_solve``
     (nonlinear_solvers/newton_solver.py:285-362).  For the linear form family Newton converges after one
