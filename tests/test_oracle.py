@@ -598,3 +598,18 @@ def test_reextension_normal_reference_budget():
     assert np.max(np.abs(prob.compute_normal_deformation(tang))) < 1e-12
     ok, hist = pipeline.lbfgs(prob, rtol=1e-2, max_iter=11, memory=3)
     assert ok and len(hist) - 1 == 10
+
+
+def test_geometric_cost_terms_and_regularization_demo_settings():
+    """J = int u dx + alpha int 1 dx + alpha int 1 ds with volume + surface + curvature regularisation
+    (demos/documented/shape_optimization/regularization: alpha = 0.1, factor_volume = factor_surface = 1, targets 1.5 /
+    4.5, factor_curvature = 1e-4, damping 0.5): the shape gradient of the full functional passes the Taylor test."""
+    om = meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))
+    cfg = pipeline.ShapeConfig(lambda_lame=0.0, mu_def=1.0, mu_fix=1.0, damping_factor=0.5, factor_volume=1.0,
+                               target_volume=1.5, factor_surface=1.0, target_surface=4.5, factor_curvature=1e-4)
+    prob = pipeline.PoissonShapeProblem(om, config=cfg, c_volume=0.1, c_surface=0.1)
+    prob.solve_state()
+    plain = pipeline.PoissonShapeProblem(meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz")), config=cfg)
+    plain.solve_state()
+    assert abs(prob.cost() - plain.cost() - 0.1 * (prob.volume() + prob.surface())) < 1e-13
+    assert pipeline.shape_gradient_test(prob)[0] > 1.9
