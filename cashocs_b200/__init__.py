@@ -10,7 +10,7 @@ from cashocs_b200 import _exceptions
 from cashocs_b200 import log
 from cashocs_b200._exceptions import CashocsException, ConfigError, InputError, NotConvergedError, PETScKSPError
 from cashocs_b200._forms.expressions import Polynomial, spatial_coordinate
-from cashocs_b200._forms.forms import (DirichletBC, Function, IntegralFunctional, PoissonForm,
+from cashocs_b200._forms.forms import (DirichletBC, Function, IntegralFunctional, PoissonForm, ScalarTrackingFunctional,
                                        create_dirichlet_bcs)
 from cashocs_b200._optimization.optimal_control_problem import OptimalControlProblem
 from cashocs_b200._optimization.shape_optimization_problem import ShapeOptimizationProblem
@@ -28,7 +28,7 @@ __version__ = "0.1.0"
 __all__ = [
     "APrioriMeshTester", "CashocsException", "Config", "ConfigError", "DeformationHandler", "DirichletBC",
     "Function", "InputError", "IntegralFunctional", "IntersectionTester", "LinearSolver", "Matrix", "Mesh",
-    "NotConvergedError", "OptimalControlProblem", "PETScKSPError", "PoissonForm", "Polynomial",
+    "NotConvergedError", "OptimalControlProblem", "PETScKSPError", "PoissonForm", "Polynomial", "ScalarTrackingFunctional",
     "ShapeOptimizationProblem", "compute_mesh_quality", "create_dirichlet_bcs", "import_mesh", "linear_solve", "load_config", "log", "newton_solve", "nonlinear_solvers",
     "mesh_from_arrays", "regular_box_mesh", "regular_mesh", "spatial_coordinate",
 ]

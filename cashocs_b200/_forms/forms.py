@@ -161,3 +161,90 @@ class IntegralFunctional:
     def __post_init__(self):
         if self.c_track != 0.0 and self.desired_state is None:
             raise _exceptions.InputError("IntegralFunctional", "desired_state", "tracking term needs u_d")
+
+
+@dataclasses.dataclass
+class ScalarTrackingFunctional:
+    """``weight / 2 (int integrand - tracking_goal)^2`` (``cashocs.ScalarTrackingFunctional``,
+    ``cashocs/_optimization/cost_functional.py:209-316``); the integrand is an :class:`IntegralFunctional` of the state
+    and the geometry (``c_state``, ``c_track`` -- e.g. ``u*u*dx`` is ``c_track = 2`` with a zero ``desired_state`` --,
+    ``c_volume``, ``c_surface``)."""
+
+    integrand: IntegralFunctional
+    tracking_goal: float
+    weight: float = 1.0
+
+    def __post_init__(self):
+        if self.integrand.c_control != 0.0:
+            raise _exceptions.InputError("ScalarTrackingFunctional", "integrand",
+                                         "integrands of the control are not supported on the device path")
+
+
+_COEFFICIENTS = ("c_state", "c_track", "c_volume", "c_surface")
+
+
+class CostFunctionalList:
+    """A list of cost functionals, ``J = sum_i J_i`` (``cost_functional_form`` may be a list,
+    ``cashocs/_optimization/optimization_problem.py:150-160``), seen by the adjoint problem, the shape derivative and
+    the geometric terms as ONE :class:`IntegralFunctional` with *effective* coefficients: the derivative of a scalar
+    tracking term is its integrand's derivative times ``weight (int integrand - goal)``, so after every state solve
+    :meth:`update` folds those factors into ``c_state / c_track / c_volume / c_surface``.  All quadratic state terms
+    must share one ``desired_state``."""
+
+    def __init__(self, functionals) -> None:
+        self.integral = [f for f in functionals if isinstance(f, IntegralFunctional)]
+        self.tracking = [f for f in functionals if isinstance(f, ScalarTrackingFunctional)]
+        if len(self.integral) + len(self.tracking) != len(functionals):
+            raise _exceptions.InputError("cashocs_b200.CostFunctionalList", "cost_functional_form",
+                                         "IntegralFunctional and ScalarTrackingFunctional terms are supported")
+        terms = self.integral + [t.integrand for t in self.tracking]
+        targets = [f.desired_state for f in terms if f.c_track != 0.0]
+        if any(t is not targets[0] for t in targets[1:]):
+            raise _exceptions.InputError("cashocs_b200.CostFunctionalList", "desired_state",
+                                         "all quadratic state terms must use the same desired_state Function")
+        self.desired_state = targets[0] if targets else None
+        self.c_control = float(sum(f.c_control for f in self.integral))
+        self.base = {k: float(sum(getattr(f, k) for f in self.integral)) for k in _COEFFICIENTS}
+        self.has_surface_terms = any(f.c_surface != 0.0 for f in terms)
+        self.has_volume_terms = any(f.c_volume != 0.0 for f in terms)
+        for k in _COEFFICIENTS:
+            setattr(self, k, self.base[k])
+        self._evaluator = None
+
+    def bind(self, evaluator) -> None:
+        """``evaluator()`` returns (int u, 1/2 int (u - u_d)^2, volume, boundary measure) for the current state."""
+        self._evaluator = evaluator
+
+    def tracking_values(self, ints=None):
+        iu, it, vol, surf = ints if ints is not None else self._evaluator()
+        return [t.integrand.c_state * iu + t.integrand.c_track * it + t.integrand.c_volume * vol
+                + t.integrand.c_surface * surf for t in self.tracking]
+
+    def update(self) -> None:
+        """Effective coefficients for the current state (call after every state solve)."""
+        eff = dict(self.base)
+        for t, val in zip(self.tracking, self.tracking_values()):
+            m = t.weight * (val - t.tracking_goal)
+            for k in _COEFFICIENTS:
+                eff[k] += m * getattr(t.integrand, k)
+        for k in _COEFFICIENTS:
+            setattr(self, k, eff[k])
+
+    def value(self) -> float:
+        """``sum_i J_i`` without the control term (added by the reduced cost functional)."""
+        ints = self._evaluator()
+        iu, it, vol, surf = ints
+        b = self.base
+        val = b["c_state"] * iu + b["c_track"] * it + b["c_volume"] * vol + b["c_surface"] * surf
+        for t, v in zip(self.tracking, self.tracking_values(ints)):
+            val += 0.5 * t.weight * (v - t.tracking_goal) ** 2
+        return val
+
+
+def as_cost_functional(cost):
+    """A single :class:`IntegralFunctional` stays what it is; lists and scalar tracking terms become a
+    :class:`CostFunctionalList`."""
+    items = list(cost) if isinstance(cost, (list, tuple)) else [cost]
+    if len(items) == 1 and isinstance(items[0], IntegralFunctional):
+        return items[0]
+    return CostFunctionalList(items)

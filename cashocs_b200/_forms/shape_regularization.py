@@ -40,14 +40,16 @@ class ShapeRegularization:
         d = mesh.dim
         # geometric terms of the cost functional itself (IntegralFunctional.c_volume / .c_surface): linear in the
         # volume / the boundary measure, they ride on the same kernels as the quadratic regularisation terms
-        self.j_volume = float(getattr(cost, "c_volume", 0.0) or 0.0)
-        self.j_surface = float(getattr(cost, "c_surface", 0.0) or 0.0)
+        # (read at use: the effective coefficients of a CostFunctionalList follow the state)
+        self._cost = cost
+        self._j_volume_possible = bool(getattr(cost, "has_volume_terms", getattr(cost, "c_volume", 0.0) != 0.0))
+        self._j_surface_possible = bool(getattr(cost, "has_surface_terms", getattr(cost, "c_surface", 0.0) != 0.0))
         self.mu_volume = config.getfloat("Regularization", "factor_volume")
         self.mu_barycenter = config.getfloat("Regularization", "factor_barycenter")
         self.mu_surface = config.getfloat("Regularization", "factor_surface")
         self.mu_curvature = config.getfloat("Regularization", "factor_curvature")
         self.is_active = (self.mu_volume > 0.0 or self.mu_barycenter > 0.0 or self.mu_surface > 0.0
-                          or self.mu_curvature > 0.0 or self.j_volume != 0.0 or self.j_surface != 0.0)
+                          or self.mu_curvature > 0.0 or self._j_volume_possible or self._j_surface_possible)
         if not self.is_active:
             return
         f64 = dict(dtype=torch.float64, device=mesh.device)
@@ -68,7 +70,7 @@ class ShapeRegularization:
         self.current_barycenter = [0.0, 0.0, 0.0]
         self.current_surface = 1.0
         self.target_surface = config.getfloat("Regularization", "target_surface")
-        if self.mu_surface > 0.0 or self.mu_curvature > 0.0 or self.j_surface != 0.0:
+        if self.mu_surface > 0.0 or self.mu_curvature > 0.0 or self._j_surface_possible:
             self._facets, self._v2f_ptr, self._v2f_idx, counted = mesh.boundary_facet_table()
             # facets this rank adds to the global measure (all of them on one GPU; on a partition every boundary
             # facet is counted by exactly one rank)
@@ -110,6 +112,23 @@ class ShapeRegularization:
             self.mu_curvature = scaled("curvature", mu, self.compute_curvature_objective())
 
     # -- geometric quantities
+    @property
+    def j_volume(self) -> float:
+        return float(getattr(self._cost, "c_volume", 0.0) or 0.0) if self._j_volume_possible else 0.0
+
+    @property
+    def j_surface(self) -> float:
+        return float(getattr(self._cost, "c_surface", 0.0) or 0.0) if self._j_surface_possible else 0.0
+
+    def geometric_cost_terms(self) -> float:
+        """``c_volume int 1 dx + c_surface int 1 ds`` of a plain IntegralFunctional (lists evaluate their own terms)."""
+        value = 0.0
+        if self.j_volume != 0.0:
+            value += self.j_volume * self.compute_volume()
+        if self.j_surface != 0.0:
+            value += self.j_surface * self.compute_surface()
+        return value
+
     def _integral(self, w: torch.Tensor) -> float:
         mesh = self.mesh
         scratch = mesh.reduce_scratch()
@@ -201,7 +220,7 @@ class ShapeRegularization:
             self.current_volume = self.compute_volume()
             if self.mu_barycenter > 0.0:
                 self.current_barycenter = self.compute_barycenter()
-            if self.mu_surface > 0.0 or self.j_surface != 0.0:
+            if self.mu_surface > 0.0 or self._j_surface_possible:
                 self.current_surface = self.compute_surface()
 
     def compute_objective(self) -> float:
@@ -218,10 +237,6 @@ class ShapeRegularization:
             value += 0.5 * self.mu_barycenter * sum((bc[k] - self.target_barycenter[k]) ** 2 for k in range(3))
         if self.mu_curvature > 0.0:
             value += self.compute_curvature_objective()
-        if self.j_volume != 0.0:
-            value += self.j_volume * self.compute_volume()
-        if self.j_surface != 0.0:
-            value += self.j_surface * self.compute_surface()
         return value
 
     def add_shape_derivative(self, b: torch.Tensor) -> torch.Tensor:
@@ -230,7 +245,7 @@ class ShapeRegularization:
         if not self.is_active:
             return b
         d = self.mesh.dim
-        if self.mu_surface > 0.0 or self.j_surface != 0.0:  # mu (surface - target) int_Gamma t_div(V, n) ds  (:248-269)
+        if self.mu_surface > 0.0 or self.j_surface != 0.0:  # (mu (surface - target) + c_surface) int_Gamma t_div(V, n) ds  (:248-269)
             mesh = self.mesh
             _lib.check(
                 _lib.load().cb_boundary_measure_gradient(

@@ -5,6 +5,7 @@ from __future__ import annotations
 import torch
 
 from cashocs_b200 import _lib
+from cashocs_b200._forms import forms
 
 
 class ReducedCostFunctional:
@@ -17,6 +18,29 @@ class ReducedCostFunctional:
         self.mass_scalar_product = mass_scalar_product
         self._out = torch.zeros(1, dtype=torch.float64, device=mesh.device)
         self.shape_regularization = None  # set by ShapeOptimizationProblem (cost_functional.py:84-86)
+        if isinstance(cost, forms.CostFunctionalList):
+            if states[0].space is not None:
+                from cashocs_b200 import _exceptions
+
+                raise _exceptions.InputError("cashocs_b200.ReducedCostFunctional", "cost_functional_form",
+                                             "lists of functionals / scalar tracking terms are supported for P1 states")
+            cost.bind(self._integrand_values)
+            state_problem.after_solve = cost.update
+
+    def _integrand_values(self):
+        """(int u, 1/2 int (u - u_d)^2, volume, boundary measure) at the current state, for CostFunctionalList."""
+        c, u = self.cost, self.states[0].vector
+        iu = self._integral(u, 1.0, 0.0, None)
+        it = self._integral(u, 0.0, 1.0, c.desired_state.vector) if c.desired_state is not None else 0.0
+        reg = self.shape_regularization
+        vol = reg.compute_volume() if (c.has_volume_terms and reg is not None) else 0.0
+        surf = reg.compute_surface() if (c.has_surface_terms and reg is not None) else 0.0
+        if (c.has_volume_terms or c.has_surface_terms) and reg is None:
+            from cashocs_b200 import _exceptions
+
+            raise _exceptions.InputError("cashocs_b200.IntegralFunctional", "c_volume",
+                                         "the geometric terms int 1 dx / int 1 ds belong to shape optimisation problems")
+        return iu, it, vol, surf
 
     def _integral(self, u, c_u, c_track, ud) -> float:
         mesh = self.mesh
@@ -48,14 +72,21 @@ class ReducedCostFunctional:
         """``ReducedCostFunctional.evaluate`` (``cost_functional.py:65-88``)."""
         self.state_problem.solve()
         c = self.cost
-        ud = c.desired_state.vector if c.c_track != 0.0 else None
-        val = self._integral(self.states[0].vector, c.c_state, c.c_track, ud)
+        reg = self.shape_regularization
+        if isinstance(c, forms.CostFunctionalList):
+            val = c.value()
+        else:
+            ud = c.desired_state.vector if c.c_track != 0.0 else None
+            val = self._integral(self.states[0].vector, c.c_state, c.c_track, ud)
+            if reg is not None and reg.is_active:
+                val += reg.geometric_cost_terms()
         if c.c_control != 0.0 and self.control is not None:
             # alpha/2 int u^2 = alpha/2 u^T M u
             val += 0.5 * c.c_control * self.mass_scalar_product(self.control.vector, self.control.vector)
         if self.shape_regularization is not None and self.shape_regularization.is_active:
             val += self.shape_regularization.compute_objective()
-        elif getattr(c, "c_volume", 0.0) != 0.0 or getattr(c, "c_surface", 0.0) != 0.0:
+        elif getattr(c, "has_volume_terms", getattr(c, "c_volume", 0.0) != 0.0) or \
+                getattr(c, "has_surface_terms", getattr(c, "c_surface", 0.0) != 0.0):
             from cashocs_b200 import _exceptions
 
             raise _exceptions.InputError("cashocs_b200.IntegralFunctional", "c_volume",

@@ -36,7 +36,7 @@ class OptimalControlProblem:
                                          "one state / control / adjoint is on the hot path")
         bcs_list = _enlist(bcs_list) if bcs_list is not None else []
         self.bcs_list = [bcs_list] if (not bcs_list or isinstance(bcs_list[0], forms.DirichletBC)) else bcs_list
-        self.cost = cost_functional_form
+        self.cost = forms.as_cost_functional(cost_functional_form)
         self.mesh = self.states[0].mesh
         self.config = config if config is not None else config_module.Config()
         self.config.validate_config()

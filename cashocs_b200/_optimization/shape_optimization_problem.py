@@ -57,7 +57,7 @@ class ShapeOptimizationProblem:
                                          "coupled systems are outside the hot path (one state variable)")
         bcs_list = _enlist(bcs_list)
         self.bcs_list = [bcs_list] if (bcs_list and isinstance(bcs_list[0], forms.DirichletBC)) else bcs_list
-        self.cost = cost_functional_form
+        self.cost = forms.as_cost_functional(cost_functional_form)
         self.mesh = mesh if mesh is not None else self.states[0].mesh
         self.config = config if config is not None else config_module.Config()
         self.config.validate_config()

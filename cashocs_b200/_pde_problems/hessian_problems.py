@@ -60,6 +60,10 @@ class HessianProblem:
         if getattr(form, "cubic", 0.0) != 0.0:
             raise _exceptions.InputError("cashocs_b200.HessianProblem", "state_forms",
                                          "second-order forms of the semilinear state equation are not built")
+        if getattr(pr.cost, "tracking", None):
+            # control_form_handler.py:506-520: "Newton's method is not available with scalar tracking or min_max terms."
+            raise _exceptions.InputError("cashocs_b200.HessianProblem", "cost_functional_form",
+                                         "Newton's method is not available with scalar tracking terms.")
         if pr.states[0].space is not None:
             raise _exceptions.InputError("cashocs_b200.HessianProblem", "states", "Newton's method drives P1 states")
         self.mesh = pr.mesh

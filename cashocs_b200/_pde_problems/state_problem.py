@@ -45,6 +45,7 @@ class StateProblem(pde_problem.PDEProblem):
                                       device=mesh.device) for sp in self.spaces]
         self.bc_arrays = [forms.bc_flag_arrays(mesh, bcs, 1, space=sp) for bcs, sp in zip(bcs_list, self.spaces)]
         self._checkpoint = None
+        self.after_solve = None  # CostFunctionalList.update: effective cost coefficients follow the state
 
     def _generate_checkpoint(self) -> None:
         """``state_problem.py:252-258``."""
@@ -192,4 +193,6 @@ class StateProblem(pde_problem.PDEProblem):
                     plan.halo_exchange(self.states[i].vector, 1)
             self.has_solution = True
             self.number_of_solves += 1
+            if self.after_solve is not None:
+                self.after_solve()
         return self.states

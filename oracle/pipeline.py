@@ -143,6 +143,7 @@ class PoissonShapeProblem:
         use_pull_back: bool = True,
         c_volume: float = 0.0,
         c_surface: float = 0.0,
+        scalar_tracking=(),
     ):
         """State ``kappa grad u . grad p + reaction u p - f p`` (= 0), cost
         ``J = c_state int u + c_track / 2 int (u - u_d)^2`` with a P1 (vertex-valued) ``u_d`` that is transported with the
@@ -156,6 +157,15 @@ class PoissonShapeProblem:
         # geometric terms of the cost functional itself, J += c_volume int 1 dx + c_surface int 1 ds
         # (demos/documented/shape_optimization/regularization/demo_regularization.py: Constant(alpha)*dx + Constant(alpha)*ds)
         self.c_volume, self.c_surface = float(c_volume), float(c_surface)
+        # ScalarTrackingFunctional terms weight / 2 (int integrand - goal)^2 (cost_functional.py:209-316), the integrand from
+        # the same family: dicts with c_state, c_track, c_volume, c_surface, goal, weight.  Their derivative is the
+        # integrand's derivative times weight (int integrand - goal), i.e. effective coefficients that follow the state.
+        self.scalar_tracking = [{**dict(c_state=0.0, c_track=0.0, c_volume=0.0, c_surface=0.0, weight=1.0), **t} for t in scalar_tracking]
+        self._base = dict(c_state=self.c_state, c_track=self.c_track, c_volume=self.c_volume, c_surface=self.c_surface)
+        if self.u_d is None and any(t["c_track"] != 0.0 for t in self.scalar_tracking):
+            self.u_d = np.zeros(mesh.num_vertices)
+        if self.scalar_tracking and state_degree == 2:
+            raise ValueError("oracle: scalar tracking functionals are written for P1 states")
         if self.c_track != 0.0 and self.u_d is None:
             raise ValueError("oracle: the tracking term needs u_d")
         general = (self.kappa != 1.0 or self.reaction != 0.0 or self.c_track != 0.0)
@@ -416,7 +426,35 @@ class PoissonShapeProblem:
         self._check(reason)
         self.its["state"] = its
         self.A_state, self.b_state = A, b
+        self._update_effective_cost_coefficients()
         return self.u
+
+    def _integrand_values(self):
+        """(int u, 1/2 int (u - u_d)^2, volume, boundary measure) for the current state and mesh."""
+        _, vol, _ = self._geom()
+        iu = float(np.sum(vol * self.u[self.cells].mean(axis=1)))
+        it = 0.0
+        if self.u_d is not None:
+            w = (self.u - self.u_d)[self.cells]
+            it = 0.5 * float(np.einsum("ca,cab,cb->", w, fem.mass_elements(vol, self.d), w))
+        need_surf = self._base["c_surface"] != 0.0 or any(t["c_surface"] != 0.0 for t in self.scalar_tracking)
+        return iu, it, float(np.sum(vol)), (self.surface() if need_surf else 0.0)
+
+    def _tracking_values(self):
+        iu, it, vol, surf = self._integrand_values()
+        return [t["c_state"] * iu + t["c_track"] * it + t["c_volume"] * vol + t["c_surface"] * surf for t in self.scalar_tracking]
+
+    def _update_effective_cost_coefficients(self):
+        """c_x <- c_x of the integral terms + sum_k weight_k (I_k - goal_k) c_x,k: what the adjoint equation and the shape
+        derivative see (the derivative of a scalar tracking term is its integrand's derivative times that factor)."""
+        if not self.scalar_tracking:
+            return
+        eff = dict(self._base)
+        for t, val in zip(self.scalar_tracking, self._tracking_values()):
+            m = t["weight"] * (val - t["goal"])
+            for k in eff:
+                eff[k] += m * t[k]
+        self.c_state, self.c_track, self.c_volume, self.c_surface = (eff[k] for k in ("c_state", "c_track", "c_volume", "c_surface"))
 
     def solve_adjoint(self):
         _, vol, G = self._geom()
@@ -445,16 +483,19 @@ class PoissonShapeProblem:
         """``IntegralFunctional.evaluate`` (``cashocs/_optimization/cost_functional.py:160-168``)."""
         _, vol, _ = self._geom()
         reg = self.regularization_objective()  # cost_functional.py:84-86
-        if self.c_volume != 0.0:
-            reg += self.c_volume * self.volume()
-        if self.c_surface != 0.0:
-            reg += self.c_surface * self.surface()
+        b = self._base
+        if b["c_volume"] != 0.0:
+            reg += b["c_volume"] * self.volume()
+        if b["c_surface"] != 0.0:
+            reg += b["c_surface"] * self.surface()
         if self.state_degree == 2:
-            return self.c_state * p2.integral(self.u, self.p2_dofs, vol, self.d) + reg
-        J = self.c_state * float(np.sum(vol * self.u[self.cells].mean(axis=1)))
-        if self.c_track != 0.0:
+            return b["c_state"] * p2.integral(self.u, self.p2_dofs, vol, self.d) + reg
+        J = b["c_state"] * float(np.sum(vol * self.u[self.cells].mean(axis=1)))
+        if b["c_track"] != 0.0:
             w = (self.u - self.u_d)[self.cells]
-            J += 0.5 * self.c_track * float(np.einsum("ca,cab,cb->", w, fem.mass_elements(vol, self.d), w))
+            J += 0.5 * b["c_track"] * float(np.einsum("ca,cab,cb->", w, fem.mass_elements(vol, self.d), w))
+        for t, val in zip(self.scalar_tracking, self._tracking_values()):  # cost_functional.py:268-283
+            J += 0.5 * t["weight"] * (val - t["goal"]) ** 2
         return J + reg
 
     # -- Lame mu (a5)

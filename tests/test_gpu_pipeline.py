@@ -1022,6 +1022,59 @@ def test_scaling_shape_regularization_like_the_reference():
     assert rel(sop.compute_shape_gradient()[0].vector.cpu().numpy(), prob.compute_shape_gradient()) < 1e-8
 
 
+def test_scalar_tracking_functionals_like_the_reference():
+    """tests/test_shape_optimization.py:549-592 (``cashocs.ScalarTrackingFunctional``, lists of cost functionals).
+    (i) J = 1/2 (int 1 dx - pi r^2)^2: Taylor rate > 1.9, L-BFGS to rtol 1e-6 within 50 iterations, the disc shrinks to
+    radius r (5e-3), 1/2 (vol - goal)^2 < 1e-10 -- with the oracle's iteration count;  (ii) J = 1/2 (int u^2 dx - goal)^2:
+    L-BFGS to rtol 1e-5 within 50 iterations leaves 1/2 (int u^2 - goal)^2 < 1e-14;  (iii) a list
+    [int u dx, 1/2 (int 1 ds - goal)^2]: cost and shape gradient against the oracle."""
+    rng = np.random.RandomState(300696)
+    radius = rng.uniform(0.33, 0.66)
+    goal = np.pi * radius**2
+    dm, om = circle()
+    J = cb.ScalarTrackingFunctional(cb.IntegralFunctional(c_volume=1.0), goal)
+    u, p = cb.Function(dm), cb.Function(dm)
+    sop = cb.ShapeOptimizationProblem(cb.PoissonForm(source=demo_poly(2)), cb.create_dirichlet_bcs(0.0, [1]), J, u, p,
+                                      config=sop_config(volume_change=10), ksp_options=KSP, adjoint_ksp_options=KSP,
+                                      gradient_ksp_options=KSP)
+    ocfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, volume_change=10.0)
+    prob = pipeline.PoissonShapeProblem(om, config=ocfg, c_state=0.0, scalar_tracking=[dict(c_volume=1.0, goal=goal)])
+    assert rel(sop.compute_shape_gradient()[0].vector.cpu().numpy(), prob.compute_shape_gradient()) < 1e-8
+    assert abs(sop.reduced_cost_functional.evaluate() - prob.cost()) <= 1e-10 * abs(prob.cost())
+    assert sop.gradient_test(rng=rng) > 1.9
+    sop.solve(algorithm="bfgs", rtol=1e-6, atol=0.0, max_iter=50)
+    ok, hist = pipeline.lbfgs(prob, rtol=1e-6, max_iter=50, memory=3)
+    assert ok and sop.solver.converged and sop.solver.iteration == len(hist) - 1
+    coords = dm.coords.cpu().numpy()
+    assert abs(coords.max() - radius) < 5e-3 and abs(-coords.min() - radius) < 5e-3
+    assert 0.5 * (sop.form_handler.shape_regularization.compute_volume() - goal) ** 2 < 1e-10
+
+    goal2 = np.random.RandomState(300696).uniform(0.25, 0.75)
+    dm, om = circle()
+    u, p, zero = cb.Function(dm), cb.Function(dm), cb.Function(dm)
+    J = cb.ScalarTrackingFunctional(cb.IntegralFunctional(c_track=2.0, desired_state=zero), goal2)  # u*u*dx
+    sop = cb.ShapeOptimizationProblem(cb.PoissonForm(source=demo_poly(2)), cb.create_dirichlet_bcs(0.0, [1]), J, u, p,
+                                      config=sop_config(), ksp_options=KSP, adjoint_ksp_options=KSP, gradient_ksp_options=KSP)
+    prob = pipeline.PoissonShapeProblem(om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02), c_state=0.0,
+                                        scalar_tracking=[dict(c_track=2.0, goal=goal2)])
+    assert rel(sop.compute_shape_gradient()[0].vector.cpu().numpy(), prob.compute_shape_gradient()) < 1e-8
+    sop.solve(algorithm="bfgs", rtol=1e-5, atol=0.0, max_iter=50)
+    assert sop.solver.converged
+    norm_u = sop.cost.tracking_values()[0]
+    assert 0.5 * (norm_u - goal2) ** 2 < 1e-14
+
+    dm, om = circle()
+    u, p = cb.Function(dm), cb.Function(dm)
+    J = [cb.IntegralFunctional(c_state=1.0), cb.ScalarTrackingFunctional(cb.IntegralFunctional(c_surface=1.0), 5.0, weight=0.5)]
+    sop = cb.ShapeOptimizationProblem(cb.PoissonForm(source=demo_poly(2)), cb.create_dirichlet_bcs(0.0, [1]), J, u, p,
+                                      config=sop_config(), ksp_options=KSP, adjoint_ksp_options=KSP, gradient_ksp_options=KSP)
+    prob = pipeline.PoissonShapeProblem(om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02), c_state=1.0,
+                                        scalar_tracking=[dict(c_surface=1.0, goal=5.0, weight=0.5)])
+    assert rel(sop.compute_shape_gradient()[0].vector.cpu().numpy(), prob.compute_shape_gradient()) < 1e-8
+    assert abs(sop.reduced_cost_functional.evaluate() - prob.cost()) <= 1e-10 * abs(prob.cost())
+    assert sop.gradient_test(rng=np.random.RandomState(1)) > 1.9
+
+
 def test_curvature_kernels_3d():
     """The facet kernels of the curvature term on a perturbed unit cube: boundary mass matrix (row sums = vertex shares
     of the boundary measure, total = |Gamma|), kappa, objective and derivative against the oracle."""

@@ -613,3 +613,25 @@ def test_geometric_cost_terms_and_regularization_demo_settings():
     plain.solve_state()
     assert abs(prob.cost() - plain.cost() - 0.1 * (prob.volume() + prob.surface())) < 1e-13
     assert pipeline.shape_gradient_test(prob)[0] > 1.9
+
+
+def test_scalar_tracking_reference_scenarios():
+    """tests/test_shape_optimization.py:549-592: J = 1/2 (int 1 dx - pi r^2)^2 -- Taylor rate > 1.9, L-BFGS to rtol 1e-6
+    within 50 iterations (oracle: 8), radius r to 5e-3, 1/2 (vol - goal)^2 < 1e-10; J = 1/2 (int u^2 dx - goal)^2 --
+    L-BFGS to rtol 1e-5 within 50 iterations (oracle: 10) leaves 1/2 (int u^2 - goal)^2 < 1e-14."""
+    rng = np.random.RandomState(300696)
+    radius = rng.uniform(0.33, 0.66)
+    goal = np.pi * radius**2
+    load = lambda: meshes.load_npz(os.path.join(GOLDEN, "unit_circle.npz"))  # noqa: E731
+    cfg = pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02, volume_change=10.0)
+    prob = pipeline.PoissonShapeProblem(load(), config=cfg, c_state=0.0, scalar_tracking=[dict(c_volume=1.0, goal=goal)])
+    assert pipeline.shape_gradient_test(prob, rng=rng)[0] > 1.9
+    ok, hist = pipeline.lbfgs(prob, rtol=1e-6, max_iter=50, memory=3)
+    assert ok and len(hist) - 1 <= 50
+    assert abs(prob.coords.max() - radius) < 5e-3 and abs(-prob.coords.min() - radius) < 5e-3
+    assert 0.5 * (prob.volume() - goal) ** 2 < 1e-10
+    goal2 = np.random.RandomState(300696).uniform(0.25, 0.75)
+    prob = pipeline.PoissonShapeProblem(load(), config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02), c_state=0.0,
+                                        scalar_tracking=[dict(c_track=2.0, goal=goal2)])
+    ok, hist = pipeline.lbfgs(prob, rtol=1e-5, max_iter=50, memory=3)
+    assert ok and 0.5 * (prob._tracking_values()[0] - goal2) ** 2 < 1e-14
