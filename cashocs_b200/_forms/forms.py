@@ -192,6 +192,11 @@ class CostFunctionalList:
     must share one ``desired_state``."""
 
     def __init__(self, functionals) -> None:
+        self._evaluator = None
+        self._set(list(functionals))
+
+    def _set(self, functionals) -> None:
+        self.functionals = functionals  # in the caller's order (desired_weights refers to it)
         self.integral = [f for f in functionals if isinstance(f, IntegralFunctional)]
         self.tracking = [f for f in functionals if isinstance(f, ScalarTrackingFunctional)]
         if len(self.integral) + len(self.tracking) != len(functionals):
@@ -209,7 +214,29 @@ class CostFunctionalList:
         self.has_volume_terms = any(f.c_volume != 0.0 for f in terms)
         for k in _COEFFICIENTS:
             setattr(self, k, self.base[k])
-        self._evaluator = None
+
+    def term_values(self, ints, control_value: float = 0.0) -> list[float]:
+        """The value of every functional of the list; ``control_value`` = 1/2 int control^2."""
+        iu, it, vol, surf = ints
+        out = []
+        for f in self.functionals:
+            g = f.integrand if isinstance(f, ScalarTrackingFunctional) else f
+            val = g.c_state * iu + g.c_track * it + g.c_volume * vol + g.c_surface * surf + g.c_control * control_value
+            out.append(0.5 * f.weight * (val - f.tracking_goal) ** 2 if isinstance(f, ScalarTrackingFunctional) else val)
+        return out
+
+    def scale(self, factors) -> None:
+        """``functional.scale(factor)`` for every term (``cost_functional.py:195-202,293-300``): integral functionals
+        are multiplied by their factor, scalar tracking functionals get it as their weight.  The caller's objects are
+        left alone, the list holds scaled copies."""
+        scaled = []
+        for f, factor in zip(self.functionals, factors):
+            if isinstance(f, ScalarTrackingFunctional):
+                scaled.append(dataclasses.replace(f, weight=float(factor)))
+            else:
+                scaled.append(dataclasses.replace(f, **{k: getattr(f, k) * float(factor)
+                                                        for k in _COEFFICIENTS + ("c_control",)}))
+        self._set(scaled)
 
     def bind(self, evaluator) -> None:
         """``evaluator()`` returns (int u, 1/2 int (u - u_d)^2, volume, boundary measure) for the current state."""
@@ -241,10 +268,10 @@ class CostFunctionalList:
         return val
 
 
-def as_cost_functional(cost):
+def as_cost_functional(cost, force_list: bool = False):
     """A single :class:`IntegralFunctional` stays what it is; lists and scalar tracking terms become a
-    :class:`CostFunctionalList`."""
+    :class:`CostFunctionalList` (also a single functional that is to be scaled, ``force_list``)."""
     items = list(cost) if isinstance(cost, (list, tuple)) else [cost]
-    if len(items) == 1 and isinstance(items[0], IntegralFunctional):
+    if len(items) == 1 and isinstance(items[0], IntegralFunctional) and not force_list:
         return items[0]
     return CostFunctionalList(items)

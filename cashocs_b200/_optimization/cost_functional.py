@@ -27,6 +27,36 @@ class ReducedCostFunctional:
             cost.bind(self._integrand_values)
             state_problem.after_solve = cost.update
 
+    def scale(self, desired_weights) -> None:
+        """``_scale_cost_functional`` (``cashocs/_optimization/optimization_problem.py:791-824``): every term of the
+        list is scaled so that its value on the initial iterate is ``|desired_weights[i]|`` (a term that vanishes there
+        is multiplied by its weight instead)."""
+        from cashocs_b200 import _exceptions
+        from cashocs_b200 import log
+
+        c = self.cost
+        if not isinstance(c, forms.CostFunctionalList) or len(desired_weights) != len(c.functionals):
+            raise _exceptions.InputError("cashocs_b200.OptimizationProblem", "desired_weights",
+                                         "Length of desired_weights and cost_functional does not match.")
+        log.warning("You are using the automatic scaling functionality of cashocs."
+                    "This may lead to unexpected results if you try to scale the cost "
+                    "functional yourself or if you supply custom forms.")
+        self.state_problem.solve()
+        control_value = 0.0
+        if c.c_control != 0.0 and self.control is not None:
+            control_value = 0.5 * self.mass_scalar_product(self.control.vector, self.control.vector)
+        values = c.term_values(self._integrand_values(), control_value)
+        factors = []
+        for i, (w, val) in enumerate(zip(desired_weights, values)):
+            if abs(val) <= 1e-15:
+                val = 1.0
+                log.info(f"Term {i:d} of the cost functional vanishes for the initial iteration. Multiplying this term "
+                         "with the factor you supplied in desired weights.")
+            factors.append(abs(float(w) / val))
+        c.scale(factors)
+        c.update()
+        self.initial_function_values, self.scaling_factors = values, factors
+
     def _integrand_values(self):
         """(int u, 1/2 int (u - u_d)^2, volume, boundary measure) at the current state, for CostFunctionalList."""
         c, u = self.cost, self.states[0].vector

@@ -28,7 +28,7 @@ def _enlist(x):
 class OptimalControlProblem:
     def __init__(self, state_forms, bcs_list, cost_functional_form, states, controls, adjoints, config=None,
                  ksp_options=None, adjoint_ksp_options=None, gradient_ksp_options=None, linear_solver=None,
-                 adjoint_linear_solver=None, control_constraints=None, control_bcs_list=None) -> None:
+                 adjoint_linear_solver=None, control_constraints=None, control_bcs_list=None, desired_weights=None) -> None:
         self.state_forms = _enlist(state_forms)
         self.states, self.controls, self.adjoints = _enlist(states), _enlist(controls), _enlist(adjoints)
         if not (len(self.states) == len(self.adjoints) == len(self.state_forms) == 1 and len(self.controls) == 1):
@@ -36,7 +36,7 @@ class OptimalControlProblem:
                                          "one state / control / adjoint is on the hot path")
         bcs_list = _enlist(bcs_list) if bcs_list is not None else []
         self.bcs_list = [bcs_list] if (not bcs_list or isinstance(bcs_list[0], forms.DirichletBC)) else bcs_list
-        self.cost = forms.as_cost_functional(cost_functional_form)
+        self.cost = forms.as_cost_functional(cost_functional_form, force_list=desired_weights is not None)
         self.mesh = self.states[0].mesh
         self.config = config if config is not None else config_module.Config()
         self.config.validate_config()
@@ -64,6 +64,8 @@ class OptimalControlProblem:
         self.reduced_cost_functional = cost_functional.ReducedCostFunctional(
             self.mesh, self.cost, self.states, self.state_problem, self.controls[0],
             self.gradient_problem.mass_product)
+        if desired_weights is not None:  # optimization_problem.py:300-303
+            self.reduced_cost_functional.scale(list(desired_weights))
 
         # the optimisation loop sees the same surface as for shape problems
         self.problem_type = "control"

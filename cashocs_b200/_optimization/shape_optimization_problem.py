@@ -45,7 +45,7 @@ def _algorithm_name(name: str) -> str:
 class ShapeOptimizationProblem:
     def __init__(self, state_forms, bcs_list, cost_functional_form, states, adjoints, mesh=None, config=None,
                  ksp_options=None, adjoint_ksp_options=None, gradient_ksp_options=None, linear_solver=None,
-                 adjoint_linear_solver=None, gradient_linear_solver=None) -> None:
+                 adjoint_linear_solver=None, gradient_linear_solver=None, desired_weights=None) -> None:
         self.state_forms = _enlist(state_forms)
         self.states = _enlist(states)
         self.adjoints = _enlist(adjoints)
@@ -57,7 +57,7 @@ class ShapeOptimizationProblem:
                                          "coupled systems are outside the hot path (one state variable)")
         bcs_list = _enlist(bcs_list)
         self.bcs_list = [bcs_list] if (bcs_list and isinstance(bcs_list[0], forms.DirichletBC)) else bcs_list
-        self.cost = forms.as_cost_functional(cost_functional_form)
+        self.cost = forms.as_cost_functional(cost_functional_form, force_list=desired_weights is not None)
         self.mesh = mesh if mesh is not None else self.states[0].mesh
         self.config = config if config is not None else config_module.Config()
         self.config.validate_config()
@@ -88,6 +88,8 @@ class ShapeOptimizationProblem:
         self.reduced_cost_functional = cost_functional.ReducedCostFunctional(
             self.mesh, self.cost, self.states, self.state_problem)
         self.reduced_cost_functional.shape_regularization = self.form_handler.shape_regularization
+        if desired_weights is not None:  # optimization_problem.py:300-303
+            self.reduced_cost_functional.scale(list(desired_weights))
         self.optimization_variable_abstractions = ls.ShapeVariableAbstractions(self)
         self.solver = None
 

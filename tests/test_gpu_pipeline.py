@@ -1075,6 +1075,48 @@ def test_scalar_tracking_functionals_like_the_reference():
     assert sop.gradient_test(rng=np.random.RandomState(1)) > 1.9
 
 
+def test_scaling_of_cost_functional_lists_like_the_reference():
+    """tests/test_shape_optimization.py:776-932 (``desired_weights``): every term of the list is scaled to its weight on
+    the initial iterate, so the initial cost is -w0 + w1 (+ w2 + w3) -- int u dx is negative on this problem -- to
+    1e-14, and the Taylor test of the scaled functional has rate > 1.9: [int u, int u^2] (``test_scaling_shape``),
+    two scalar tracking terms (``test_scaling_scalar_only``) and all four together (``test_scaling_all``).  The shape
+    gradient of the scaled list equals the oracle's for the same factors."""
+    def problem(J, weights):
+        dm, om = circle()
+        u, p = cb.Function(dm), cb.Function(dm)
+        sop = cb.ShapeOptimizationProblem(cb.PoissonForm(source=demo_poly(2)), cb.create_dirichlet_bcs(0.0, [1]), J, u, p,
+                                          config=sop_config(), ksp_options=KSP, adjoint_ksp_options=KSP,
+                                          gradient_ksp_options=KSP, desired_weights=weights)
+        return dm, om, sop
+
+    def functionals(dm, which):
+        zero = cb.Function(dm)
+        goals = np.random.RandomState(300696).uniform(0.25, 0.75, 2)
+        table = {"u": cb.IntegralFunctional(c_state=1.0), "uu": cb.IntegralFunctional(c_track=2.0, desired_state=zero),
+                 "vol": cb.ScalarTrackingFunctional(cb.IntegralFunctional(c_volume=1.0), goals[0]),
+                 "surf": cb.ScalarTrackingFunctional(cb.IntegralFunctional(c_surface=1.0), goals[1])}
+        return [table[k] for k in which], goals
+
+    for which, signs in ((("u", "uu"), (-1, 1)), (("vol", "surf"), (1, 1)), (("u", "uu", "vol", "surf"), (-1, 1, 1, 1))):
+        rng = np.random.RandomState(300696)
+        dm0, _ = circle()
+        J, goals = functionals(dm0, which)
+        weights = rng.rand(len(which)).tolist()
+        dm, om, sop = problem(J, weights)
+        val = sop.reduced_cost_functional.evaluate()
+        assert abs(val - sum(s * w for s, w in zip(signs, weights))) < 1e-14, which
+        assert sop.gradient_test(rng=rng) > 1.9, which
+        f = dict(zip(which, sop.reduced_cost_functional.scaling_factors))
+        prob = pipeline.PoissonShapeProblem(
+            om, config=pipeline.ShapeConfig(tol_lower=0.01, tol_upper=0.02), c_state=f.get("u", 0.0), c_track=2.0 * f.get("uu", 0.0),
+            u_d=np.zeros(om.num_vertices),
+            scalar_tracking=([dict(c_volume=1.0, goal=goals[0], weight=f["vol"])] if "vol" in f else [])
+            + ([dict(c_surface=1.0, goal=goals[1], weight=f["surf"])] if "surf" in f else []))
+        assert rel(sop.compute_shape_gradient()[0].vector.cpu().numpy(), prob.compute_shape_gradient()) < 1e-8, which
+    with pytest.raises(cb.InputError):
+        problem([cb.IntegralFunctional(c_state=1.0)], [1.0, 2.0])
+
+
 def test_curvature_kernels_3d():
     """The facet kernels of the curvature term on a perturbed unit cube: boundary mass matrix (row sums = vertex shares
     of the boundary measure, total = |Gamma|), kappa, objective and derivative against the oracle."""
