@@ -1117,6 +1117,40 @@ def test_scaling_of_cost_functional_lists_like_the_reference():
         problem([cb.IntegralFunctional(c_state=1.0)], [1.0, 2.0])
 
 
+def test_scalar_tracking_control_like_the_reference(rng):
+    """tests/test_optimal_control.py:249-296: J = 1/2 (int y^2 dx - goal)^2 for the distributed control problem --
+    L-BFGS (initial_stepsize 4e3, rtol 1e-3) drives 1/2 (int y^2 - goal)^2 below 1e-15, the Taylor test has rate > 1.9,
+    and with weight / J(initial) as weight the initial cost equals the weight (1e-15)."""
+    def ocp_for(weight=1.0):
+        dm = cb.regular_mesh(10)
+        y, p, u, zero = (cb.Function(dm) for _ in range(4))
+        u.vector.fill_(1e-3)
+        cfg = cb.Config()
+        cfg.set("Output", "save_results", "False")
+        cfg.set("StateSystem", "is_linear", "True")
+        cfg.set("AlgoLBFGS", "bfgs_memory_size", "3")
+        cfg.set("LineSearch", "initial_stepsize", "4e3")
+        J = cb.ScalarTrackingFunctional(cb.IntegralFunctional(c_track=2.0, desired_state=zero), goal, weight=weight)
+        return cb.OptimalControlProblem(cb.PoissonForm(source=u), cb.create_dirichlet_bcs(0.0, [1, 2, 3, 4]), J, y, u, p, config=cfg)
+
+    goal = rng.uniform(0.25, 0.75)
+    weight = rng.uniform(0.1, 1e1)
+    ocp = ocp_for()
+    ocp.compute_state_variables()
+    initial = ocp.reduced_cost_functional.evaluate()
+    assert abs(initial - 0.5 * (ocp.cost.tracking_values()[0] - goal) ** 2) <= 1e-15
+    assert ocp.gradient_test(rng=rng) > 1.9
+    scaled = ocp_for(weight / initial)
+    assert abs(scaled.reduced_cost_functional.evaluate() - weight) < 1e-14
+    ocp = ocp_for()
+    ocp.solve(algorithm="bfgs", rtol=1e-3, atol=0.0, max_iter=100)
+    assert ocp.solver.converged
+    ocp.compute_state_variables()
+    assert 0.5 * (ocp.cost.tracking_values()[0] - goal) ** 2 < 1e-15
+    with pytest.raises(cb.InputError):
+        ocp.solve(algorithm="newton", rtol=1e-3, atol=0.0, max_iter=2)
+
+
 def test_curvature_kernels_3d():
     """The facet kernels of the curvature term on a perturbed unit cube: boundary mass matrix (row sums = vertex shares
     of the boundary measure, total = |Gamma|), kappa, objective and derivative against the oracle."""
