@@ -305,3 +305,36 @@ def test_dense_polynomial_evaluator(tmp_path):
                     os.path.join(root, "tests", "native", "test_dense_poly.cu")], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert "degree-5 rejected 1" in out
+
+
+def test_cost_functional_list_algebra():
+    """``CostFunctionalList`` (lists of cost functionals, ``ScalarTrackingFunctional``, ``desired_weights``;
+    cashocs/_optimization/cost_functional.py:209-316, optimization_problem.py:791-824) without a device: the value is
+    the sum of the terms, the effective coefficients carry weight * (integrand - goal) of every tracking term, scaling
+    multiplies integral functionals and ASSIGNS the weight of tracking functionals."""
+    import types
+
+    from cashocs_b200._forms import forms
+
+    ud = types.SimpleNamespace(vector=None)
+    J = [cb.IntegralFunctional(c_state=2.0, c_volume=0.5), cb.IntegralFunctional(c_track=2.0, desired_state=ud),
+         cb.ScalarTrackingFunctional(cb.IntegralFunctional(c_volume=1.0, c_surface=3.0), 4.0, weight=0.5)]
+    c = forms.as_cost_functional(J)
+    ints = (1.5, 0.25, 2.0, 1.0)  # int u, 1/2 int (u - u_d)^2, volume, boundary measure
+    c.bind(lambda: ints)
+    track = 1.0 * 2.0 + 3.0 * 1.0
+    assert c.tracking_values() == [track] and c.has_volume_terms and c.has_surface_terms and c.desired_state is ud
+    assert abs(c.value() - (2.0 * 1.5 + 0.5 * 2.0 + 2.0 * 0.25 + 0.5 * 0.5 * (track - 4.0) ** 2)) < 1e-15
+    c.update()
+    m = 0.5 * (track - 4.0)
+    assert (c.c_state, c.c_track, c.c_volume, c.c_surface) == (2.0, 2.0, 0.5 + m * 1.0, m * 3.0)
+    vals = c.term_values(ints)
+    assert vals == [2.0 * 1.5 + 0.5 * 2.0, 2.0 * 0.25, 0.5 * 0.5 * (track - 4.0) ** 2]
+    c.scale([2.0, 3.0, 7.0])
+    assert c.base == {"c_state": 4.0, "c_track": 6.0, "c_volume": 1.0, "c_surface": 0.0} and c.tracking[0].weight == 7.0
+    assert J[0].c_state == 2.0 and J[2].weight == 0.5  # the caller's objects are untouched
+    assert forms.as_cost_functional(J[0]) is J[0] and isinstance(forms.as_cost_functional(J[0], force_list=True), forms.CostFunctionalList)
+    with pytest.raises(cb.InputError):
+        forms.as_cost_functional([J[1], cb.IntegralFunctional(c_track=1.0, desired_state=types.SimpleNamespace(vector=None))])
+    with pytest.raises(cb.InputError):
+        cb.ScalarTrackingFunctional(cb.IntegralFunctional(c_control=1.0), 1.0)
