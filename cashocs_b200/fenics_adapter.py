@@ -8,7 +8,7 @@ This module is the glue a cashocs maintainer installs on the *reference* side so
 * :class:`B200LinearSolver` -- the documented plug-in point (``linear_solver=`` kwarg; example
   ``demos/undocumented/shape_optimization/python_pc/python_pc.py:48-108``): a PETSc AIJ matrix and right-hand side in,
   the solution written into ``function.vector()``, ``PETScKSPError`` on a negative reason.
-* :func:`recognise_bilinear` / :func:`recognise_linear` / :func:`fit_polynomial` -- which member of the supported
+* :func:`recognise_bilinear` / :func:`recognise_linear` / :func:`recognise_semilinear` / :func:`fit_polynomial` -- which member of the supported
   form family a UFL form is, decided *numerically*: dolfin tabulates the element tensor of the user's form on a few
   cells (``fenics.assemble_local``), the adapter fits ``kappa K_e + c M_e`` (resp. a polynomial / nodal source) to
   it and accepts the form only if the fit is exact to round-off.  No UFL tree matching, so any way of writing the
@@ -30,7 +30,7 @@ import numpy as np
 
 from cashocs_b200 import _exceptions
 
-__all__ = ["aij_to_baij", "fit_polynomial", "recognise_bilinear", "recognise_linear", "B200LinearSolver",
+__all__ = ["aij_to_baij", "fit_polynomial", "recognise_bilinear", "recognise_linear", "recognise_semilinear", "B200LinearSolver",
            "device_mesh_from_dolfin", "install"]
 
 
@@ -175,6 +175,44 @@ def recognise_linear(element_vectors, cell_vertices, nodal_fields=(), polynomial
         return None
     coef = [float(c) for c in coef]
     return (coef[0], coef[1:]) if polynomial is not None else (0.0, coef)
+
+
+def recognise_semilinear(residual_vectors, cell_vertices, state_values, source_values=None, tol: float = 1e-9):
+    """Is the residual ``F(u; v)`` of the semilinear family ``kappa grad u . grad v + c u v + gamma u^3 v - s w v``
+    (``PoissonForm`` with ``cubic``; the equation of ``tests/test_nonlinear_solvers.py:28-61`` and of the
+    ``nonlinear_pdes`` demo)?
+
+    ``residual_vectors [ncell, d+1]``: the form's element vectors on a few cells, tabulated by dolfin at the P1 state
+    with the vertex values ``state_values [ncell, d+1]`` (``fenics.assemble_local`` of the nonlinear form);
+    ``source_values``: vertex values of the P1 source ``w`` (the control) on those cells, or ``None``.  The candidate
+    columns are ``K_e u_e``, ``M_e u_e``, ``int u^3 phi`` (degree-4 rule: exact for P1 ``u``) and ``M_e w_e``; returns
+    ``(kappa, c, gamma, s)`` when the fit is exact to ``tol``, else ``None`` -- the state must not be (close to) zero,
+    otherwise the columns cannot be told apart."""
+    from cashocs_b200._forms import expressions
+
+    F = np.asarray(residual_vectors, dtype=float)
+    X = np.asarray(cell_vertices, dtype=float)
+    U = np.asarray(state_values, dtype=float)
+    d = X.shape[2]
+    lam, w = expressions.simplex_quadrature(d, 4)
+    lam = lam[:, : d + 1]
+    cols = [np.zeros_like(F) for _ in range(4 if source_values is not None else 3)]
+    for c, (x, u) in enumerate(zip(X, U)):
+        K, M, vol = _p1_reference_tensors(x)
+        cols[0][c], cols[1][c] = K @ u, M @ u
+        cols[2][c] = vol * (w * (lam @ u) ** 3) @ lam
+        if source_values is not None:
+            cols[3][c] = -(M @ np.asarray(source_values[c], dtype=float))
+    B = np.stack([col.reshape(-1) for col in cols], axis=1)
+    y = F.reshape(-1)
+    if np.linalg.matrix_rank(B, tol=1e-12 * max(np.linalg.norm(B), 1e-300)) < B.shape[1]:
+        return None
+    coef, *_ = np.linalg.lstsq(B, y, rcond=None)
+    if np.linalg.norm(B @ coef - y) > tol * max(np.linalg.norm(y), 1e-300):
+        return None
+    scale = max(np.max(np.abs(coef)), 1e-300)
+    out = [0.0 if abs(v) < tol * scale else float(v) for v in coef]
+    return tuple(out) if source_values is not None else (out[0], out[1], out[2], 0.0)
 
 
 # ----------------------------------------------------------------------------- the LinearSolver plug-in

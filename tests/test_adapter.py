@@ -60,6 +60,32 @@ def test_recognise_bilinear_and_linear_forms(dim):
     assert fa.recognise_linear(bn ** 2, X, nodal_fields=[w[cells]]) is None
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_recognise_semilinear_forms(dim):
+    """The residual of ``grad y . grad p + 1e2 y^3 p - u p`` (demos/documented/optimal_control/nonlinear_pdes) tabulated
+    at a random P1 state is recognised with its coefficients; a quadratic nonlinearity is refused."""
+    from oracle import nonlinear
+
+    om = meshes.regular_mesh(3) if dim == 2 else meshes.regular_mesh(2, 1.0, 1.0, 1.0)
+    rng = np.random.RandomState(2)
+    coords = om.coords + 0.02 * rng.rand(*om.coords.shape)
+    _, vol, G = fem.cell_geometry(coords, om.cells)
+    y, u = rng.rand(om.num_vertices) + 0.5, rng.rand(om.num_vertices)
+    K, M = fem.stiffness_elements(vol, G), fem.mass_elements(vol, dim)
+    cubic = nonlinear.cubic_load_elements(vol, om.cells, y, dim, 1e2)
+    Fe = np.einsum("cab,cb->ca", K, y[om.cells]) + cubic - np.einsum("cab,cb->ca", M, u[om.cells])
+    sel = slice(0, 8)
+    X = coords[om.cells[sel]]
+    got = fa.recognise_semilinear(Fe[sel], X, y[om.cells[sel]], u[om.cells[sel]])
+    assert got == pytest.approx((1.0, 0.0, 1e2, 1.0), rel=1e-8, abs=1e-8)
+    lin = 2.0 * np.einsum("cab,cb->ca", K, y[om.cells]) + 0.3 * np.einsum("cab,cb->ca", M, y[om.cells])
+    assert fa.recognise_semilinear(lin[sel], X, y[om.cells[sel]]) == pytest.approx((2.0, 0.3, 0.0, 0.0), abs=1e-8)
+    lam, w = fem.quadrature(dim, 4)
+    quad = vol[:, None] * np.einsum("cq,q,qa->ca", (y[om.cells] @ lam.T) ** 2, w, lam)
+    assert fa.recognise_semilinear((Fe + quad)[sel], X, y[om.cells[sel]], u[om.cells[sel]]) is None
+    assert fa.recognise_semilinear(Fe[sel] * 0.0, X, 0.0 * y[om.cells[sel]]) is None  # a zero state tells nothing
+
+
 def test_fit_polynomial_recovers_the_demo_source():
     f = lambda p: 2.5 * (p[:, 0] + 0.4 - p[:, 1] ** 2) ** 2 + p[:, 0] ** 2 + p[:, 1] ** 2 - 1  # noqa: E731
     poly = fa.fit_polynomial(f, 2)
