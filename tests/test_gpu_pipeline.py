@@ -764,6 +764,25 @@ def test_documented_demos_regularization_p_laplacian_nonlinear_pdes():
     assert abs(ocp.solver.objective_value - hist[-1][1]) <= 1e-6 * abs(hist[-1][1])
 
 
+def test_documented_demos_iterative_solvers_and_scalar_control_tracking():
+    """Two more documented demos of the reference with their own option dictionaries / config keys:
+    optimal_control/iterative_solvers (cg + hypre for the state, minres + jacobi for the adjoint, L-BFGS to rtol 1e-4:
+    same iteration count and final cost as the oracle's loop with the oracle's own cg / minres) and
+    optimal_control/scalar_control_tracking (J = 1/2 (int y^2 - 1)^2: the demo prints "L2-Norm of y squared: 1.000e+00")."""
+    ocp = _run_demo("optimal_control_iterative_solvers", "demo_iterative_solvers.py")
+    om = meshes.regular_mesh(50)
+    yd = np.sin(2 * np.pi * om.coords[:, 0]) * np.sin(2 * np.pi * om.coords[:, 1])
+    state_ksp = {"ksp_type": "cg", "pc_type": "hypre", "ksp_rtol": 1e-10, "ksp_atol": 1e-13, "ksp_max_it": 100}
+    adjoint_ksp = {"ksp_type": "minres", "pc_type": "jacobi", "ksp_rtol": 1e-6, "ksp_atol": 1e-15, "ksp_max_it": 10000}
+    oprob = pipeline.PoissonControlProblem(om, yd, np.zeros(om.num_vertices), alpha=1e-6, bc_markers=(1, 2, 3, 4),
+                                           state_ksp=state_ksp, adjoint_ksp=adjoint_ksp)
+    ok, hist = pipeline.lbfgs(oprob, rtol=1e-4, max_iter=100, memory=5)
+    assert ok and ocp.solver.converged and abs(ocp.solver.iteration - (len(hist) - 1)) <= 1
+    assert abs(ocp.solver.objective_value - hist[-1][1]) <= 1e-4 * abs(hist[-1][1])  # adjoint solved to 1e-6 only
+    ocp, norm = _run_demo("optimal_control_scalar_control_tracking", "demo_scalar_control_tracking.py")
+    assert ocp.solver.converged and format(norm, ".3e") == "1.000e+00"
+
+
 def test_default_is_linear_false_runs_newton_on_the_linear_state():
     """The reference's default is ``is_linear = False`` (io/config.py:599): ``newton_solve``
     (nonlinear_solvers/newton_solver.py:285-362).  For the linear form family Newton converges after one
