@@ -550,13 +550,26 @@ static int launch_assemble_rows(cudaStream_t s, const cb_mesh_view* m, const dou
                                 const double* cell_scale, const uint8_t* bc_flag, double* val) {
   // mesh stencils (<= 16 entries per row on average with some slack): two rows per warp
   const bool small = m->nnz <= 16 * m->nrows_owned;
-  const int grid = grid_for(m->nrows_owned, 8, 6);  // 8 rows per CTA and sweep; 6 CTAs x 36 KB of staging per SM
-  if (small)
-    k_assemble_rows<D, ELAST, 16><<<grid, 128, 0, s>>>(m->nrows_owned, m->rowptr, m->col, m->v2c_ptr, m->v2c_idx,
-                                                      m->cells_orig, m->coords, mu, p0, p1, cell_scale, bc_flag, val);
-  else
-    k_assemble_rows<D, ELAST, 32><<<grid, 256, 0, s>>>(m->nrows_owned, m->rowptr, m->col, m->v2c_ptr, m->v2c_idx,
-                                                      m->cells_orig, m->coords, mu, p0, p1, cell_scale, bc_flag, val);
+  // One wave exactly: the grid is what is resident (asked from the occupancy calculator -- registers and the 36 KB of
+  // staging per CTA allow 5 CTAs per SM, not the 6 the shared memory alone would; with 6 x 148 CTAs the sixth CTA of
+  // every SM ran as a second wave of its own, 1.2 waves for the price of 2: ncu launch__waves_per_multiprocessor).
+  auto one_wave = [&](auto kernel, int threads) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+      (void)cudaGetLastError();
+      per_sm = 4;
+    }
+    return grid_for(m->nrows_owned, 8, per_sm);  // 8 rows per CTA and sweep
+  };
+  if (small) {
+    auto kernel = k_assemble_rows<D, ELAST, 16>;
+    kernel<<<one_wave(kernel, 128), 128, 0, s>>>(m->nrows_owned, m->rowptr, m->col, m->v2c_ptr, m->v2c_idx,
+                                                  m->cells_orig, m->coords, mu, p0, p1, cell_scale, bc_flag, val);
+  } else {
+    auto kernel = k_assemble_rows<D, ELAST, 32>;
+    kernel<<<one_wave(kernel, 256), 256, 0, s>>>(m->nrows_owned, m->rowptr, m->col, m->v2c_ptr, m->v2c_idx,
+                                                  m->cells_orig, m->coords, mu, p0, p1, cell_scale, bc_flag, val);
+  }
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
